@@ -1,0 +1,195 @@
+/*
+ * resampler_b200.h -- C ABI of the B200-native ResamplerFir path.
+ *
+ * Drop-in boundary for hasenbanck/resampler v0.5.1's `ResamplerFir`
+ * (reference: src/resampler_fir.rs, src/fir/*.rs, src/window.rs).  The reference
+ * has no FFI of its own; these entry points are what a `resampler-cuda` crate
+ * binds so that `ResamplerFir::new / new_from_hz /
+ * buffer_size_output / resample / delay / reset` keep their meaning, plus the
+ * batched multi-stream entry points that are new.
+ *
+ * Plain C: opaque handle, plain pointers and sizes, int status codes.  All
+ * lengths called `*_len` are in f32 VALUES (all channels), exactly like the
+ * reference's slices; `*_frames` are per-channel frames.
+ *
+ * Threading: a handle must not be used from two threads at once (the reference
+ * takes `&mut self`, resampler_fir.rs:509); different handles are independent.
+ * There is no CPU fallback: every compute entry point fails with
+ * RSB_ERR_NO_DEVICE / RSB_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef RESAMPLER_B200_H
+#define RESAMPLER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rsb_fir rsb_fir; /* N independent streams sharing one configuration, on one GPU */
+
+enum rsb_status {
+    RSB_OK = 0,
+    /* ResampleError::InvalidInputBufferSize  (src/error.rs:5, checked first, resampler_fir.rs:514) */
+    RSB_ERR_INVALID_INPUT_BUFFER_SIZE = 1,
+    /* ResampleError::InvalidOutputBufferSize (src/error.rs:7, checked second, resampler_fir.rs:517) */
+    RSB_ERR_INVALID_OUTPUT_BUFFER_SIZE = 2,
+    /* the reference panics with "input sample rate must be greater than zero" (resampler_fir.rs:302-305) */
+    RSB_ERR_ZERO_INPUT_RATE = 10,
+    /* the reference panics with "output sample rate must be greater than zero" (resampler_fir.rs:306-309) */
+    RSB_ERR_ZERO_OUTPUT_RATE = 11,
+    RSB_ERR_INVALID_ARGUMENT = 12,
+    /* batched calls only: an `out` buffer was too small for what its calls produced */
+    RSB_ERR_OUTPUT_CAPACITY = 13,
+    RSB_ERR_NO_DEVICE = 100,
+    RSB_ERR_CUDA = 101,
+    RSB_ERR_OUT_OF_MEMORY = 102,
+    RSB_ERR_PLAN_OVERFLOW = 103
+};
+
+/* Latency (resampler_fir.rs:138-162): taps = 16 / 32 / 64 / 128 */
+enum rsb_latency { RSB_LATENCY_SAMPLE8 = 0, RSB_LATENCY_SAMPLE16 = 1, RSB_LATENCY_SAMPLE32 = 2,
+                   RSB_LATENCY_SAMPLE64 = 3 /* reference default */ };
+/* Attenuation (resampler_fir.rs:101-123): Kaiser beta 7 / 10 / 13 */
+enum rsb_attenuation { RSB_ATTENUATION_DB60 = 0, RSB_ATTENUATION_DB90 = 1,
+                       RSB_ATTENUATION_DB120 = 2 /* reference default */ };
+
+enum rsb_memspace { RSB_MEM_DEVICE = 0, /* pointers are device pointers on the handle's GPU */
+                    RSB_MEM_HOST = 1    /* host pointers (pinned is fastest); the call copies */ };
+
+/* Which convolution kernel serves a handle.
+ *   EXACT: two-phase dot product in the reference's AVX-512 order (fir/avx512.rs:5-50);
+ *          output samples are bit-identical to that path.
+ *   FAST : interpolates the two phase rows once per output frame and reuses the row for
+ *          every stream/channel of the tile; samples within 1e-6 absolute of EXACT.
+ *   AUTO : FAST where it applies (stream count, ratio), else EXACT. */
+enum rsb_kernel { RSB_KERNEL_AUTO = 0, RSB_KERNEL_EXACT = 1, RSB_KERNEL_FAST = 2 };
+
+enum rsb_flags {
+    RSB_FLAG_NONE = 0,
+    RSB_FLAG_ASYNC = 1,        /* device memspace only: return after enqueueing; counts are
+                                  written by rsb_fir_sync() */
+    RSB_FLAG_RECORD_CALLS = 2, /* keep per-call (consumed, produced) for rsb_fir_last_call_counts */
+    RSB_FLAG_KEEP_PLAN = 4     /* keep the device plan for rsb_fir_last_plan */
+};
+
+const char *rsb_version(void);
+const char *rsb_status_string(int status);
+const char *rsb_last_error(void); /* thread-local detail of the last failure */
+int rsb_device_count(void);       /* usable CUDA devices; 0 when none / no driver */
+
+/* ---- construction: ResamplerFir::new_from_hz (resampler_fir.rs:295-404) ----
+ * One handle = n_streams independent resamplers with identical parameters on GPU
+ * `device`.  ResamplerFir::new (resampler_fir.rs:252-266) maps SampleRate -> Hz
+ * (lib.rs:219-234) and calls this. */
+int rsb_fir_create(rsb_fir **out, int device, uint32_t n_streams, uint32_t channels,
+                   uint32_t input_rate_hz, uint32_t output_rate_hz, int latency, int attenuation);
+void rsb_fir_destroy(rsb_fir *h);
+int rsb_fir_set_kernel(rsb_fir *h, int kernel);
+
+uint32_t rsb_fir_channels(const rsb_fir *h);
+uint32_t rsb_fir_n_streams(const rsb_fir *h);
+uint32_t rsb_fir_taps(const rsb_fir *h);
+double rsb_fir_ratio(const rsb_fir *h);
+int rsb_fir_device(const rsb_fir *h);
+/* ResamplerFir::buffer_size_output (resampler_fir.rs:456-465), in values */
+size_t rsb_fir_buffer_size_output(const rsb_fir *h);
+/* ResamplerFir::delay (resampler_fir.rs:630-632) */
+size_t rsb_fir_delay(const rsb_fir *h);
+/* ResamplerFir::reset (resampler_fir.rs:638-642); stream < 0 resets every stream */
+int rsb_fir_reset(rsb_fir *h, int64_t stream);
+/* copies the [1024][taps] coefficient table (resampler_fir.rs:406-421) to `out` */
+int rsb_fir_coeffs(const rsb_fir *h, float *out, size_t out_len);
+
+/* ---- ResamplerFir::resample (resampler_fir.rs:509-621) for one stream, host slices.
+ * Synchronous.  Returns RSB_ERR_INVALID_INPUT_BUFFER_SIZE / _OUTPUT_ (in that order)
+ * when a length is not a multiple of `channels`. */
+int rsb_fir_resample(rsb_fir *h, uint32_t stream, const float *input, size_t input_len,
+                     float *output, size_t output_len, size_t *consumed, size_t *produced);
+
+/* ---- batched submit: n independent resample() calls, one per listed stream ----
+ * Semantically identical to calling rsb_fir_resample once for every i in [0, n)
+ * with (streams[i], in[i], in_lens[i], out[i], out_lens[i]); streams == NULL means
+ * 0..n-1; a stream may appear at most once.  consumed/produced receive values. */
+int rsb_fir_submit_batch(rsb_fir *h, uint32_t n, const uint32_t *streams,
+                         const float *const *in, const size_t *in_lens, float *const *out,
+                         const size_t *out_lens, size_t *consumed, size_t *produced,
+                         int memspace, uint32_t flags);
+
+/* ---- batched multi-call: the canonical caller loop per stream, in one launch ----
+ * For every listed stream runs, as if sequentially on that stream,
+ *     while off < total_len { c,p = resample(in[off .. off+min(call_len, total_len-off)],
+ *                                           buf[out_cap_len]); append buf[..p] to out;
+ *                             off += c; if c == 0 break }
+ * (resample/src/main.rs:226-254, resampler_fir.rs:719-735).  out_cap_len == 0 means
+ * buffer_size_output().  Appended output goes to out[i] (capacity out_capacities[i]
+ * values; too small => RSB_ERR_OUTPUT_CAPACITY, nothing is written past the end).
+ * consumed_totals / produced_totals / n_calls (each may be NULL) receive per-stream
+ * totals in values / calls. */
+int rsb_fir_process_batch(rsb_fir *h, uint32_t n, const uint32_t *streams,
+                          const float *const *in, const size_t *total_lens, size_t call_len,
+                          size_t out_cap_len, float *const *out, const size_t *out_capacities,
+                          size_t *consumed_totals, size_t *produced_totals, uint32_t *n_calls,
+                          int memspace, uint32_t flags);
+
+/* completes RSB_FLAG_ASYNC work (writes the deferred counts) and waits for the GPU */
+int rsb_fir_sync(rsb_fir *h);
+
+/* per-call (consumed, produced) values of job `job` of the last synchronous batch
+ * submitted with RSB_FLAG_RECORD_CALLS */
+int rsb_fir_last_call_counts(rsb_fir *h, uint32_t job, uint32_t *consumed, uint32_t *produced,
+                             size_t max_calls, size_t *n_calls);
+/* per-output-frame plan of job `job` of the last synchronous batch submitted with
+ * RSB_FLAG_KEEP_PLAN, expanded ON THE DEVICE by the same code the kernels use:
+ * input_offset (relative to the call's read position), phase1, phase2, bits of frac
+ * (resampler_fir.rs:544, 558-565).  Arrays may be NULL. */
+int rsb_fir_last_plan(rsb_fir *h, uint32_t job, uint32_t *input_offset, uint32_t *phase1,
+                      uint32_t *phase2, uint32_t *frac_bits, size_t max_frames, size_t *n_frames);
+
+/* ---- timing on the handle's CUDA stream (for benchmarks) ---- */
+int rsb_fir_timer_start(rsb_fir *h);
+int rsb_fir_timer_stop(rsb_fir *h, float *elapsed_ms); /* waits for the stop event */
+/* kernels launched on this handle since creation (your own count for gpu_launches) */
+uint64_t rsb_fir_launch_count(const rsb_fir *h);
+/* the handle's cudaStream_t, as an opaque pointer */
+void *rsb_fir_cuda_stream(const rsb_fir *h);
+
+/* ---- memory helpers ---- */
+void *rsb_alloc_pinned(size_t bytes);
+void rsb_free_pinned(void *p);
+void *rsb_alloc_device(int device, size_t bytes);
+void rsb_free_device(int device, void *p);
+/* kind: 0 host->device, 1 device->host, 2 device->device; synchronous */
+int rsb_memcpy(int device, void *dst, const void *src, size_t bytes, int kind);
+/* fills a device buffer of n f32 values with the synthetic test signal of SURVEY.md 8(d):
+ * 0.5*sin(2*pi*f*frame/rate) + 0.25*u, f = 110*(1 + (stream % 64)) + 7*channel,
+ * u = splitmix64 counter hash in [-1, 1).  Layout [stream][frame][channel]. */
+int rsb_fill_synthetic(int device, float *dst, uint32_t first_stream, uint32_t n_streams,
+                       uint64_t frames, uint32_t channels, uint32_t rate_hz, uint64_t seed);
+
+/* ---- host-only entry points (no GPU needed): filter design and the phase planner ---- */
+double rsb_host_bessel_i0(double x);                              /* window.rs:96-112 */
+double rsb_host_cutoff_kaiser(uint32_t taps, double beta);        /* window.rs:114-131 */
+void rsb_host_kaiser_window(uint32_t n, double beta, int symmetric, float *out); /* :66-94 */
+void rsb_host_make_sincs(uint32_t sample_count, uint32_t factor, float cutoff, double beta,
+                         int symmetric, float *out);              /* window.rs:17-55 */
+/* table exactly as rsb_fir_create builds it; out_len >= 1024*taps */
+int rsb_host_design_table(uint32_t input_rate_hz, uint32_t output_rate_hz, int latency,
+                          int attenuation, float *out, size_t out_len, uint32_t *cutoff_bits);
+/* Runs the planner (the same code the device executes) on the host for one stream:
+ * starting from (position_bits, available) performs the canonical loop (single_call != 0:
+ * exactly one call) and returns per-call counts in frames and the expanded per-frame plan.
+ * Any output array may be NULL.  Returns the number of calls. */
+size_t rsb_host_plan(uint32_t input_rate_hz, uint32_t output_rate_hz, int latency,
+                     uint64_t *position_bits, uint32_t *available, uint64_t total_frames,
+                     uint32_t call_frames, uint32_t cap_frames, int single_call,
+                     uint32_t *calls_consumed, uint32_t *calls_produced, size_t max_calls,
+                     uint32_t *input_offset, uint32_t *phase1, uint32_t *phase2,
+                     uint32_t *frac_bits, size_t max_frames, size_t *n_frames,
+                     size_t *n_segments);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RESAMPLER_B200_H */

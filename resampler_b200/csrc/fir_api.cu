@@ -1,0 +1,908 @@
+// fir_api.cu -- host library behind include/resampler_b200.h.
+//
+// Mirrors the reference's ResamplerFir (src/resampler_fir.rs) for N streams on
+// one GPU.  All streaming state (history frames, f64 position, buffered frame
+// count) lives on the device; the host keeps only a "cohort" id per stream so
+// that streams whose state and call sequence are identical share one plan.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/resampler_b200.h"
+#include "filter_design.h"
+#include "fir_kernels.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define RSB_CUDA(expr)                                                                   \
+    do {                                                                                 \
+        cudaError_t e__ = (expr);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            return fail(e__ == cudaErrorMemoryAllocation ? RSB_ERR_OUT_OF_MEMORY         \
+                                                         : RSB_ERR_CUDA,                 \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));            \
+        }                                                                                \
+    } while (0)
+
+// grow-only device / pinned buffers
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct Pending {
+    bool active = false;
+    uint32_t n = 0;
+    uint32_t n_units = 0;
+    size_t *consumed = nullptr;
+    size_t *produced = nullptr;
+    uint32_t *n_calls = nullptr;
+    bool check_capacity = false;
+};
+
+}  // namespace
+
+struct rsb_fir {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    uint32_t n_streams = 0, channels = 0, in_hz = 0, out_hz = 0, taps = 0;
+    int latency = 0, attenuation = 0;
+    double ratio = 0.0;
+    int kernel_mode = RSB_KERNEL_AUTO;
+    std::shared_ptr<const rsb::FirTable> table;
+    float *d_coeffs = nullptr;
+    rsb::StreamStateDev st{};
+    std::vector<uint64_t> cohort;   // host-side plan cohort of each stream (0 = fresh state)
+    uint64_t next_cohort = 1;
+    uint64_t launches = 0;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_done = nullptr;
+
+    // workspace of the (single) in-flight submit
+    DevBuf d_units, d_jobs, d_members, d_segs, d_calls, d_tiles, d_counter, d_stage_in,
+        d_stage_out, d_dbg;
+    PinBuf h_units, h_jobs, h_members, h_units_back, h_calls_back;
+    std::vector<uint32_t> job_unit;          // unit of each job of the last batch
+    std::vector<uint64_t> job_out_capacity;  // frames
+    uint32_t last_n_units = 0;
+    bool last_has_calls = false, last_has_plan = false;
+    Pending pending;
+};
+
+namespace {
+
+using rsb::JobDev;
+using rsb::UnitDev;
+
+struct UnitKey {
+    uint64_t cohort, total_frames;
+    uint32_t call_frames, cap_frames, single;
+    bool operator<(const UnitKey &o) const {
+        return std::tie(cohort, total_frames, call_frames, cap_frames, single) <
+               std::tie(o.cohort, o.total_frames, o.call_frames, o.cap_frames, o.single);
+    }
+};
+
+struct JobHost {
+    uint32_t stream;
+    const float *in;
+    float *out;
+    uint64_t total_frames;     // offered frames
+    uint64_t out_capacity;     // frames
+    uint32_t call_frames;      // frames per call (ignored when single)
+    uint32_t cap_frames;       // output capacity per call, frames
+};
+
+uint32_t segs_per_call_bound(double ratio) {
+    int e = 0;
+    std::frexp(ratio, &e);              // ratio = m * 2^e, m in [0.5, 1)
+    int lowest = std::min(0, e - 1);    // lowest binade the accumulator visits after one step
+    return (uint32_t)(2 * (14 - lowest) + 6);
+}
+
+int finalize_pending(rsb_fir *h) {
+    if (!h->pending.active) return RSB_OK;
+    Pending p = h->pending;
+    h->pending.active = false;
+    RSB_CUDA(cudaEventSynchronize(h->ev_done));
+    const UnitDev *ub = h->h_units_back.as<UnitDev>();
+    int rc = RSB_OK;
+    for (uint32_t u = 0; u < p.n_units; ++u) {
+        if (ub[u].status != 0)
+            rc = fail(RSB_ERR_PLAN_OVERFLOW, "plan workspace bound exceeded (status " +
+                                                 std::to_string(ub[u].status) + ")");
+    }
+    const uint32_t ch = h->channels;
+    for (uint32_t i = 0; i < p.n; ++i) {
+        const UnitDev &U = ub[h->job_unit[i]];
+        if (p.consumed) p.consumed[i] = (size_t)U.total_copied * ch;
+        if (p.produced) p.produced[i] = (size_t)U.total_out * ch;
+        if (p.n_calls) p.n_calls[i] = U.n_calls;
+        if (p.check_capacity && U.total_out > h->job_out_capacity[i] && rc == RSB_OK)
+            rc = fail(RSB_ERR_OUTPUT_CAPACITY, "output buffer of job " + std::to_string(i) +
+                                                   " too small: produced " +
+                                                   std::to_string(U.total_out) + " frames");
+    }
+    return rc;
+}
+
+// Core: runs `jobs` (already validated) on the device.
+int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int memspace,
+              uint32_t flags, size_t *consumed, size_t *produced, uint32_t *n_calls_out) {
+    int rc = finalize_pending(h);
+    if (rc != RSB_OK) return rc;
+    RSB_CUDA(cudaSetDevice(h->device));
+    const uint32_t n = (uint32_t)jobs.size();
+    const uint32_t ch = h->channels;
+    if (n == 0) return RSB_OK;
+
+    // ---- group jobs into plan units ----
+    std::map<UnitKey, uint32_t> key_to_unit;
+    std::vector<UnitKey> unit_keys;
+    std::vector<uint32_t> unit_count;
+    h->job_unit.assign(n, 0);
+    h->job_out_capacity.assign(n, 0);
+    for (uint32_t i = 0; i < n; ++i) {
+        UnitKey k{h->cohort[jobs[i].stream], jobs[i].total_frames,
+                  single ? 0u : jobs[i].call_frames, jobs[i].cap_frames, single ? 1u : 0u};
+        auto it = key_to_unit.find(k);
+        uint32_t u;
+        if (it == key_to_unit.end()) {
+            u = (uint32_t)unit_keys.size();
+            key_to_unit.emplace(k, u);
+            unit_keys.push_back(k);
+            unit_count.push_back(0);
+        } else {
+            u = it->second;
+        }
+        h->job_unit[i] = u;
+        h->job_out_capacity[i] = jobs[i].out_capacity;
+        unit_count[u] += 1;
+    }
+    const uint32_t n_units = (uint32_t)unit_keys.size();
+
+    // ---- choose kernel + tile geometry ----
+    bool use_fast = false;
+    if (h->kernel_mode != RSB_KERNEL_EXACT && rsb::fast_supported(ch, h->taps, h->ratio)) {
+        if (h->kernel_mode == RSB_KERNEL_FAST) {
+            use_fast = true;
+        } else {
+            // AUTO: the fast kernel wants enough streams per plan to fill its column tile
+            uint32_t biggest = *std::max_element(unit_count.begin(), unit_count.end());
+            use_fast = (uint64_t)biggest * ch >= 32;
+        }
+    }
+    const uint32_t tile_out = use_fast ? rsb::fast_tile_out(ch, h->taps, h->ratio)
+                                       : rsb::kExactTileOut;
+    const uint32_t spg = use_fast ? rsb::fast_streams_per_group(ch, h->taps, h->ratio)
+                                  : rsb::kExactStreamsPerGroup;
+
+    // ---- size the workspace ----
+    const uint32_t spc = segs_per_call_bound(h->ratio);
+    const bool rec_calls = (flags & RSB_FLAG_RECORD_CALLS) != 0;
+    RSB_CUDA(h->h_units.reserve(sizeof(UnitDev) * n_units));
+    RSB_CUDA(h->h_units_back.reserve(sizeof(UnitDev) * n_units));
+    RSB_CUDA(h->h_jobs.reserve(sizeof(JobDev) * n));
+    RSB_CUDA(h->h_members.reserve(sizeof(uint32_t) * n));
+    UnitDev *hu = h->h_units.as<UnitDev>();
+    uint64_t seg_total = 0, call_total = 0, tile_total = 0, max_tiles_unit = 0;
+    uint32_t member_off = 0, max_groups = 1;
+    for (uint32_t u = 0; u < n_units; ++u) {
+        const UnitKey &k = unit_keys[u];
+        UnitDev U;
+        std::memset(&U, 0, sizeof(U));
+        U.total_frames = k.total_frames;
+        U.call_frames = k.call_frames;
+        U.cap_frames = k.cap_frames;
+        U.single_call = k.single;
+        const double out_bound_d =
+            std::ceil(((double)rsb::kInputCapacity + (double)k.total_frames) / h->ratio) + 2.0;
+        if (out_bound_d > 4.0e9)
+            return fail(RSB_ERR_INVALID_ARGUMENT, "more than 4e9 output frames in one batch");
+        const uint64_t out_bound = (uint64_t)out_bound_d;
+        uint64_t max_calls = 1;
+        if (!k.single) {
+            const uint64_t full = k.call_frames ? (k.total_frames + k.call_frames - 1) / k.call_frames
+                                                : 0;
+            const uint64_t by_cap = k.cap_frames ? out_bound / k.cap_frames : 0;
+            max_calls = 2 * full + by_cap + 4;
+        }
+        if (max_calls > 0x7fffffffull)
+            return fail(RSB_ERR_INVALID_ARGUMENT, "too many calls in one batch");
+        U.max_calls = (uint32_t)max_calls;
+        // a call cannot produce more segments than output frames
+        const uint64_t per_call = std::min<uint64_t>(
+            spc, k.cap_frames ? std::min<uint64_t>(k.cap_frames, out_bound) : 0);
+        const uint64_t seg_cap = std::min<uint64_t>(max_calls * per_call, out_bound) + 1;
+        if (seg_total + seg_cap > 0xffffffffull)
+            return fail(RSB_ERR_INVALID_ARGUMENT, "plan too large for one batch; split it");
+        U.seg_off = (uint32_t)seg_total;
+        U.seg_cap = (uint32_t)seg_cap;
+        seg_total += seg_cap;
+        if (rec_calls) {
+            U.call_off = (uint32_t)call_total;
+            U.call_cap = U.max_calls;
+            call_total += U.max_calls;
+        }
+        const uint64_t tiles = (out_bound + tile_out - 1) / tile_out;
+        if (tiles > 65535ull * 128ull)
+            return fail(RSB_ERR_INVALID_ARGUMENT, "too many output frames per stream in one batch");
+        U.tile_cap = (uint32_t)tiles;
+        tile_total += tiles;
+        max_tiles_unit = std::max(max_tiles_unit, tiles);
+        U.member_off = member_off;
+        U.n_members = 0;   // filled below
+        member_off += unit_count[u];
+        max_groups = std::max(max_groups, (unit_count[u] + spg - 1) / spg);
+        hu[u] = U;
+    }
+    if (tile_total * max_groups > 0xffffffffull)
+        return fail(RSB_ERR_INVALID_ARGUMENT, "too many work items in one batch; split it");
+
+    // ---- host-memory staging ----
+    const bool host_mem = memspace == RSB_MEM_HOST;
+    std::vector<size_t> in_off, out_off, in_vals;
+    size_t in_total = 0, out_total = 0;
+    if (host_mem) {
+        in_off.resize(n);
+        out_off.resize(n);
+        in_vals.resize(n);
+        for (uint32_t i = 0; i < n; ++i) {
+            uint64_t frames = jobs[i].total_frames;
+            if (single) frames = std::min<uint64_t>(frames, rsb::kInputCapacity);   // :526-528
+            in_vals[i] = (size_t)frames * ch;
+            in_off[i] = in_total;
+            in_total += (in_vals[i] + 3) & ~(size_t)3;    // keep 16-byte alignment
+            out_off[i] = out_total;
+            out_total += ((size_t)jobs[i].out_capacity * ch + 3) & ~(size_t)3;
+        }
+        RSB_CUDA(h->d_stage_in.reserve(in_total * sizeof(float) + 16));
+        RSB_CUDA(h->d_stage_out.reserve(out_total * sizeof(float) + 16));
+    }
+
+    JobDev *hj = h->h_jobs.as<JobDev>();
+    uint32_t *hm = h->h_members.as<uint32_t>();
+    for (uint32_t i = 0; i < n; ++i) {
+        JobDev J;
+        J.stream = jobs[i].stream;
+        J.unit = h->job_unit[i];
+        J.out_capacity = jobs[i].out_capacity;
+        if (host_mem) {
+            J.in = h->d_stage_in.as<float>() + in_off[i];
+            J.out = h->d_stage_out.as<float>() + out_off[i];
+        } else {
+            J.in = jobs[i].in;
+            J.out = jobs[i].out;
+        }
+        hj[i] = J;
+        UnitDev &U = hu[J.unit];
+        hm[U.member_off + U.n_members] = i;
+        if (U.n_members == 0) U.rep_stream = J.stream;
+        U.n_members += 1;
+    }
+
+    RSB_CUDA(h->d_units.reserve(sizeof(UnitDev) * n_units));
+    RSB_CUDA(h->d_jobs.reserve(sizeof(JobDev) * n));
+    RSB_CUDA(h->d_members.reserve(sizeof(uint32_t) * n));
+    RSB_CUDA(h->d_segs.reserve(sizeof(rsb::PlanSeg) * seg_total));
+    RSB_CUDA(h->d_tiles.reserve(sizeof(rsb::TileRec) * tile_total));
+    RSB_CUDA(h->d_counter.reserve(sizeof(uint32_t) * 4));
+    if (rec_calls) {
+        RSB_CUDA(h->d_calls.reserve(sizeof(rsb::CallCounts) * std::max<uint64_t>(call_total, 1)));
+        RSB_CUDA(h->h_calls_back.reserve(sizeof(rsb::CallCounts) * std::max<uint64_t>(call_total, 1)));
+    }
+
+    cudaStream_t s = h->stream;
+    RSB_CUDA(cudaMemcpyAsync(h->d_units.p, hu, sizeof(UnitDev) * n_units, cudaMemcpyHostToDevice, s));
+    RSB_CUDA(cudaMemcpyAsync(h->d_jobs.p, hj, sizeof(JobDev) * n, cudaMemcpyHostToDevice, s));
+    RSB_CUDA(cudaMemcpyAsync(h->d_members.p, hm, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s));
+    RSB_CUDA(cudaMemsetAsync(h->d_counter.p, 0, sizeof(uint32_t) * 4, s));
+    if (host_mem) {
+        for (uint32_t i = 0; i < n; ++i)
+            if (in_vals[i])
+                RSB_CUDA(cudaMemcpyAsync(h->d_stage_in.as<float>() + in_off[i], jobs[i].in,
+                                         in_vals[i] * sizeof(float), cudaMemcpyHostToDevice, s));
+    }
+
+    // ---- launch ----
+    rsb::launch_plan(h->d_units.as<UnitDev>(), n_units, h->st, h->ratio, h->taps,
+                     h->d_segs.as<rsb::PlanSeg>(), h->d_calls.as<rsb::CallCounts>(), tile_out,
+                     h->d_counter.as<uint32_t>(), s);
+    rsb::launch_tiles(h->d_units.as<UnitDev>(), n_units, h->d_segs.as<rsb::PlanSeg>(),
+                      h->d_tiles.as<rsb::TileRec>(), tile_out, (uint32_t)max_tiles_unit, s);
+    rsb::ConvParams P;
+    P.units = h->d_units.as<UnitDev>();
+    P.jobs = h->d_jobs.as<JobDev>();
+    P.members = h->d_members.as<uint32_t>();
+    P.segs = h->d_segs.as<rsb::PlanSeg>();
+    P.tiles = h->d_tiles.as<rsb::TileRec>();
+    P.tile_total = h->d_counter.as<uint32_t>();
+    P.coeffs = h->d_coeffs;
+    P.st = h->st;
+    P.channels = ch;
+    P.taps = h->taps;
+    P.groups = max_groups;
+    P.streams_per_group = spg;
+    const uint32_t max_items = (uint32_t)(tile_total * max_groups);
+    if (use_fast)
+        rsb::launch_conv_fast(P, h->ratio, max_items, h->sm_count, s);
+    else
+        rsb::launch_conv_exact(P, max_items, h->sm_count, s);
+    rsb::launch_update(h->d_units.as<UnitDev>(), h->d_jobs.as<JobDev>(), n, h->st, ch, s);
+    h->launches += 4;
+    RSB_CUDA(cudaGetLastError());
+    RSB_CUDA(cudaMemcpyAsync(h->h_units_back.p, h->d_units.p, sizeof(UnitDev) * n_units,
+                             cudaMemcpyDeviceToHost, s));
+    if (rec_calls && call_total)
+        RSB_CUDA(cudaMemcpyAsync(h->h_calls_back.p, h->d_calls.p,
+                                 sizeof(rsb::CallCounts) * call_total, cudaMemcpyDeviceToHost, s));
+    RSB_CUDA(cudaEventRecord(h->ev_done, s));
+
+    // cohorts: every unit becomes a fresh cohort (same state + same calls => same new state)
+    {
+        std::vector<uint64_t> new_id(n_units);
+        for (uint32_t u = 0; u < n_units; ++u) new_id[u] = h->next_cohort++;
+        for (uint32_t i = 0; i < n; ++i) h->cohort[jobs[i].stream] = new_id[h->job_unit[i]];
+    }
+    h->last_n_units = n_units;
+    h->last_has_calls = rec_calls;
+    h->last_has_plan = (flags & RSB_FLAG_KEEP_PLAN) != 0;
+
+    h->pending.active = true;
+    h->pending.n = n;
+    h->pending.n_units = n_units;
+    h->pending.consumed = consumed;
+    h->pending.produced = produced;
+    h->pending.n_calls = n_calls_out;
+    h->pending.check_capacity = !single;
+    if ((flags & RSB_FLAG_ASYNC) && !host_mem) return RSB_OK;
+
+    rc = finalize_pending(h);
+    if (host_mem) {
+        const UnitDev *ub = h->h_units_back.as<UnitDev>();
+        for (uint32_t i = 0; i < n; ++i) {
+            const UnitDev &U = ub[h->job_unit[i]];
+            const uint64_t frames = std::min<uint64_t>(U.total_out, jobs[i].out_capacity);
+            if (frames)
+                RSB_CUDA(cudaMemcpyAsync(jobs[i].out, h->d_stage_out.as<float>() + out_off[i],
+                                         (size_t)frames * ch * sizeof(float),
+                                         cudaMemcpyDeviceToHost, s));
+        }
+        RSB_CUDA(cudaStreamSynchronize(s));
+    }
+    return rc;
+}
+
+int check_handle(const rsb_fir *h) {
+    if (!h) return fail(RSB_ERR_INVALID_ARGUMENT, "null handle");
+    return RSB_OK;
+}
+
+}  // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+const char *rsb_version(void) { return "resampler_b200 0.1.0 (sm_100a)"; }
+
+const char *rsb_status_string(int status) {
+    switch (status) {
+        case RSB_OK: return "ok";
+        case RSB_ERR_INVALID_INPUT_BUFFER_SIZE: return "Input buffer size is invalid";    // error.rs:13
+        case RSB_ERR_INVALID_OUTPUT_BUFFER_SIZE: return "Output buffer size is invalid";  // error.rs:14
+        case RSB_ERR_ZERO_INPUT_RATE: return "input sample rate must be greater than zero";
+        case RSB_ERR_ZERO_OUTPUT_RATE: return "output sample rate must be greater than zero";
+        case RSB_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case RSB_ERR_OUTPUT_CAPACITY: return "output buffer too small for the batch";
+        case RSB_ERR_NO_DEVICE: return "no usable CUDA device";
+        case RSB_ERR_CUDA: return "CUDA error";
+        case RSB_ERR_OUT_OF_MEMORY: return "out of device memory";
+        case RSB_ERR_PLAN_OVERFLOW: return "plan workspace overflow";
+        default: return "unknown status";
+    }
+}
+
+const char *rsb_last_error(void) { return g_last_error.c_str(); }
+
+int rsb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int rsb_fir_create(rsb_fir **out, int device, uint32_t n_streams, uint32_t channels,
+                   uint32_t input_rate_hz, uint32_t output_rate_hz, int latency, int attenuation) {
+    if (!out) return fail(RSB_ERR_INVALID_ARGUMENT, "out is null");
+    *out = nullptr;
+    // same order as the reference's asserts (resampler_fir.rs:302-309)
+    if (input_rate_hz == 0) return fail(RSB_ERR_ZERO_INPUT_RATE, rsb_status_string(RSB_ERR_ZERO_INPUT_RATE));
+    if (output_rate_hz == 0) return fail(RSB_ERR_ZERO_OUTPUT_RATE, rsb_status_string(RSB_ERR_ZERO_OUTPUT_RATE));
+    const int taps = rsb::latency_to_taps(latency);
+    const double beta = rsb::attenuation_to_beta(attenuation);
+    if (taps < 0 || beta < 0.0) return fail(RSB_ERR_INVALID_ARGUMENT, "bad latency/attenuation");
+    if (channels == 0 || n_streams == 0)
+        return fail(RSB_ERR_INVALID_ARGUMENT, "channels and n_streams must be positive");
+    int n_dev = rsb_device_count();
+    if (n_dev <= 0) return fail(RSB_ERR_NO_DEVICE, "no CUDA device visible; there is no CPU fallback");
+    if (device < 0 || device >= n_dev) return fail(RSB_ERR_INVALID_ARGUMENT, "bad device index");
+    RSB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RSB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(RSB_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major) +
+                                           std::to_string(prop.minor) +
+                                           "; this library contains sm_100a code only");
+
+    std::unique_ptr<rsb_fir> h(new rsb_fir());
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    h->n_streams = n_streams;
+    h->channels = channels;
+    h->in_hz = input_rate_hz;
+    h->out_hz = output_rate_hz;
+    h->latency = latency;
+    h->attenuation = attenuation;
+    h->taps = (uint32_t)taps;
+    h->ratio = (double)input_rate_hz / (double)output_rate_hz;   // :311-313
+    const float cutoff = rsb::design_cutoff(input_rate_hz, output_rate_hz, h->taps, beta);
+    h->table = rsb::get_or_create_table(cutoff, h->taps, attenuation);
+    h->cohort.assign(n_streams, 0);
+
+    RSB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    RSB_CUDA(cudaEventCreate(&h->ev_t0));
+    RSB_CUDA(cudaEventCreate(&h->ev_t1));
+    RSB_CUDA(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+    const size_t tab_bytes = h->table->coeffs.size() * sizeof(float);
+    RSB_CUDA(cudaMalloc(&h->d_coeffs, tab_bytes));
+    RSB_CUDA(cudaMemcpyAsync(h->d_coeffs, h->table->coeffs.data(), tab_bytes,
+                             cudaMemcpyHostToDevice, h->stream));
+    const size_t hist_bytes = (size_t)n_streams * rsb::kHistFrames * channels * sizeof(float);
+    RSB_CUDA(cudaMalloc(&h->st.position, sizeof(double) * n_streams));
+    RSB_CUDA(cudaMalloc(&h->st.hist_len, sizeof(uint32_t) * n_streams));
+    RSB_CUDA(cudaMalloc(&h->st.hist_sel, n_streams));
+    RSB_CUDA(cudaMalloc(&h->st.hist[0], hist_bytes));
+    RSB_CUDA(cudaMalloc(&h->st.hist[1], hist_bytes));
+    RSB_CUDA(cudaMemsetAsync(h->st.position, 0, sizeof(double) * n_streams, h->stream));
+    RSB_CUDA(cudaMemsetAsync(h->st.hist_len, 0, sizeof(uint32_t) * n_streams, h->stream));
+    RSB_CUDA(cudaMemsetAsync(h->st.hist_sel, 0, n_streams, h->stream));
+    RSB_CUDA(cudaMemsetAsync(h->st.hist[0], 0, hist_bytes, h->stream));   // :329 zero-filled
+    RSB_CUDA(cudaMemsetAsync(h->st.hist[1], 0, hist_bytes, h->stream));
+    RSB_CUDA(cudaStreamSynchronize(h->stream));
+    *out = h.release();
+    return RSB_OK;
+}
+
+void rsb_fir_destroy(rsb_fir *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_coeffs);
+    cudaFree(h->st.position);
+    cudaFree(h->st.hist_len);
+    cudaFree(h->st.hist_sel);
+    cudaFree(h->st.hist[0]);
+    cudaFree(h->st.hist[1]);
+    for (DevBuf *b : {&h->d_units, &h->d_jobs, &h->d_members, &h->d_segs, &h->d_calls, &h->d_tiles,
+                      &h->d_counter, &h->d_stage_in, &h->d_stage_out, &h->d_dbg})
+        b->release();
+    for (PinBuf *b : {&h->h_units, &h->h_jobs, &h->h_members, &h->h_units_back, &h->h_calls_back})
+        b->release();
+    if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+    if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+    if (h->ev_done) cudaEventDestroy(h->ev_done);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int rsb_fir_set_kernel(rsb_fir *h, int kernel) {
+    if (check_handle(h)) return RSB_ERR_INVALID_ARGUMENT;
+    if (kernel < RSB_KERNEL_AUTO || kernel > RSB_KERNEL_FAST)
+        return fail(RSB_ERR_INVALID_ARGUMENT, "bad kernel id");
+    if (kernel == RSB_KERNEL_FAST && !rsb::fast_supported(h->channels, h->taps, h->ratio))
+        return fail(RSB_ERR_INVALID_ARGUMENT, "fast kernel does not support this configuration");
+    h->kernel_mode = kernel;
+    return RSB_OK;
+}
+
+uint32_t rsb_fir_channels(const rsb_fir *h) { return h ? h->channels : 0; }
+uint32_t rsb_fir_n_streams(const rsb_fir *h) { return h ? h->n_streams : 0; }
+uint32_t rsb_fir_taps(const rsb_fir *h) { return h ? h->taps : 0; }
+double rsb_fir_ratio(const rsb_fir *h) { return h ? h->ratio : 0.0; }
+int rsb_fir_device(const rsb_fir *h) { return h ? h->device : -1; }
+
+size_t rsb_fir_buffer_size_output(const rsb_fir *h) {
+    if (!h) return 0;
+    // resampler_fir.rs:456-465
+    const double usable = (double)(rsb::kInputCapacity - h->taps);
+    const size_t frames = (size_t)std::ceil(usable / h->ratio) + 2;
+    return frames * h->channels;
+}
+
+size_t rsb_fir_delay(const rsb_fir *h) { return h ? h->taps / 2 : 0; }   // :630-632
+
+int rsb_fir_reset(rsb_fir *h, int64_t stream) {
+    if (check_handle(h)) return RSB_ERR_INVALID_ARGUMENT;
+    int rc = finalize_pending(h);
+    if (rc != RSB_OK) return rc;
+    RSB_CUDA(cudaSetDevice(h->device));
+    if (stream >= (int64_t)h->n_streams) return fail(RSB_ERR_INVALID_ARGUMENT, "bad stream index");
+    if (stream < 0) {
+        rsb::launch_reset(h->st, 0, h->n_streams, h->stream);
+        std::fill(h->cohort.begin(), h->cohort.end(), 0);
+    } else {
+        rsb::launch_reset(h->st, (uint32_t)stream, 1, h->stream);
+        h->cohort[(size_t)stream] = 0;
+    }
+    h->launches += 1;
+    RSB_CUDA(cudaGetLastError());
+    return RSB_OK;
+}
+
+int rsb_fir_coeffs(const rsb_fir *h, float *out, size_t out_len) {
+    if (check_handle(h)) return RSB_ERR_INVALID_ARGUMENT;
+    if (!out || out_len < h->table->coeffs.size())
+        return fail(RSB_ERR_INVALID_ARGUMENT, "coefficient buffer too small");
+    // read back from the device copy: this is what the kernels use
+    RSB_CUDA(cudaSetDevice(h->device));
+    RSB_CUDA(cudaMemcpy(out, h->d_coeffs, h->table->coeffs.size() * sizeof(float),
+                        cudaMemcpyDeviceToHost));
+    return RSB_OK;
+}
+
+int rsb_fir_resample(rsb_fir *h, uint32_t stream, const float *input, size_t input_len,
+                     float *output, size_t output_len, size_t *consumed, size_t *produced) {
+    const float *in_ptrs[1] = {input};
+    float *out_ptrs[1] = {output};
+    return rsb_fir_submit_batch(h, 1, &stream, in_ptrs, &input_len, out_ptrs, &output_len, consumed,
+                                produced, RSB_MEM_HOST, 0);
+}
+
+int rsb_fir_submit_batch(rsb_fir *h, uint32_t n, const uint32_t *streams, const float *const *in,
+                         const size_t *in_lens, float *const *out, const size_t *out_lens,
+                         size_t *consumed, size_t *produced, int memspace, uint32_t flags) {
+    if (check_handle(h)) return RSB_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RSB_OK;
+    if (!in || !in_lens || !out || !out_lens)
+        return fail(RSB_ERR_INVALID_ARGUMENT, "null array argument");
+    if (memspace != RSB_MEM_DEVICE && memspace != RSB_MEM_HOST)
+        return fail(RSB_ERR_INVALID_ARGUMENT, "bad memspace");
+    const uint32_t ch = h->channels;
+    // error precedence of resampler_fir.rs:514-519, per job, before any state changes
+    for (uint32_t i = 0; i < n; ++i) {
+        if (in_lens[i] % ch != 0)
+            return fail(RSB_ERR_INVALID_INPUT_BUFFER_SIZE, "input length of job " + std::to_string(i) +
+                                                               " is not a multiple of channels");
+        if (out_lens[i] % ch != 0)
+            return fail(RSB_ERR_INVALID_OUTPUT_BUFFER_SIZE, "output length of job " +
+                                                                std::to_string(i) +
+                                                                " is not a multiple of channels");
+    }
+    std::vector<JobHost> jobs(n);
+    std::vector<uint8_t> seen(h->n_streams, 0);
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t s = streams ? streams[i] : i;
+        if (s >= h->n_streams) return fail(RSB_ERR_INVALID_ARGUMENT, "bad stream index");
+        if (seen[s]) return fail(RSB_ERR_INVALID_ARGUMENT, "stream listed twice in one batch");
+        seen[s] = 1;
+        if (in_lens[i] && !in[i]) return fail(RSB_ERR_INVALID_ARGUMENT, "null input pointer");
+        if (out_lens[i] && !out[i]) return fail(RSB_ERR_INVALID_ARGUMENT, "null output pointer");
+        const uint64_t cap = out_lens[i] / ch;
+        jobs[i] = JobHost{s, in[i], out[i], in_lens[i] / ch, cap, 0u,
+                          (uint32_t)std::min<uint64_t>(cap, 0xffffffffull)};
+    }
+    return run_batch(h, jobs, true, memspace, flags, consumed, produced, nullptr);
+}
+
+int rsb_fir_process_batch(rsb_fir *h, uint32_t n, const uint32_t *streams, const float *const *in,
+                          const size_t *total_lens, size_t call_len, size_t out_cap_len,
+                          float *const *out, const size_t *out_capacities, size_t *consumed_totals,
+                          size_t *produced_totals, uint32_t *n_calls, int memspace, uint32_t flags) {
+    if (check_handle(h)) return RSB_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RSB_OK;
+    if (!in || !total_lens || !out || !out_capacities)
+        return fail(RSB_ERR_INVALID_ARGUMENT, "null array argument");
+    if (memspace != RSB_MEM_DEVICE && memspace != RSB_MEM_HOST)
+        return fail(RSB_ERR_INVALID_ARGUMENT, "bad memspace");
+    const uint32_t ch = h->channels;
+    if (out_cap_len == 0) out_cap_len = rsb_fir_buffer_size_output(h);
+    // every call of the loop sees slices of call_len (or the remainder) and out_cap_len values
+    if (call_len % ch != 0)
+        return fail(RSB_ERR_INVALID_INPUT_BUFFER_SIZE, "call_len is not a multiple of channels");
+    if (out_cap_len % ch != 0)
+        return fail(RSB_ERR_INVALID_OUTPUT_BUFFER_SIZE, "out_cap_len is not a multiple of channels");
+    if (call_len / ch > 0xffffffffull || out_cap_len / ch > 0xffffffffull)
+        return fail(RSB_ERR_INVALID_ARGUMENT, "call too large");
+    std::vector<JobHost> jobs(n);
+    std::vector<uint8_t> seen(h->n_streams, 0);
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t s = streams ? streams[i] : i;
+        if (s >= h->n_streams) return fail(RSB_ERR_INVALID_ARGUMENT, "bad stream index");
+        if (seen[s]) return fail(RSB_ERR_INVALID_ARGUMENT, "stream listed twice in one batch");
+        seen[s] = 1;
+        if (total_lens[i] % ch != 0)
+            return fail(RSB_ERR_INVALID_INPUT_BUFFER_SIZE, "input length of job " + std::to_string(i) +
+                                                               " is not a multiple of channels");
+        if (total_lens[i] && call_len == 0)
+            return fail(RSB_ERR_INVALID_ARGUMENT, "call_len must be positive");
+        if (total_lens[i] && !in[i]) return fail(RSB_ERR_INVALID_ARGUMENT, "null input pointer");
+        if (out_capacities[i] && !out[i]) return fail(RSB_ERR_INVALID_ARGUMENT, "null output pointer");
+        jobs[i] = JobHost{s, in[i], out[i], total_lens[i] / ch, out_capacities[i] / ch,
+                          (uint32_t)(call_len / ch), (uint32_t)(out_cap_len / ch)};
+    }
+    return run_batch(h, jobs, false, memspace, flags, consumed_totals, produced_totals, n_calls);
+}
+
+int rsb_fir_sync(rsb_fir *h) {
+    if (check_handle(h)) return RSB_ERR_INVALID_ARGUMENT;
+    RSB_CUDA(cudaSetDevice(h->device));
+    int rc = finalize_pending(h);
+    RSB_CUDA(cudaStreamSynchronize(h->stream));
+    return rc;
+}
+
+int rsb_fir_last_call_counts(rsb_fir *h, uint32_t job, uint32_t *consumed, uint32_t *produced,
+                             size_t max_calls, size_t *n_calls) {
+    if (check_handle(h)) return RSB_ERR_INVALID_ARGUMENT;
+    int rc = finalize_pending(h);
+    if (rc != RSB_OK && rc != RSB_ERR_OUTPUT_CAPACITY) return rc;
+    if (!h->last_has_calls) return fail(RSB_ERR_INVALID_ARGUMENT, "last batch did not record calls");
+    if (job >= h->job_unit.size()) return fail(RSB_ERR_INVALID_ARGUMENT, "bad job index");
+    const UnitDev &U = h->h_units_back.as<UnitDev>()[h->job_unit[job]];
+    const rsb::CallCounts *cc = h->h_calls_back.as<rsb::CallCounts>() + U.call_off;
+    const size_t nc = std::min<size_t>(U.n_calls, U.call_cap);
+    if (n_calls) *n_calls = nc;
+    for (size_t i = 0; i < nc && i < max_calls; ++i) {
+        if (consumed) consumed[i] = cc[i].copied * h->channels;
+        if (produced) produced[i] = cc[i].produced * h->channels;
+    }
+    return RSB_OK;
+}
+
+int rsb_fir_last_plan(rsb_fir *h, uint32_t job, uint32_t *input_offset, uint32_t *phase1,
+                      uint32_t *phase2, uint32_t *frac_bits, size_t max_frames, size_t *n_frames) {
+    if (check_handle(h)) return RSB_ERR_INVALID_ARGUMENT;
+    int rc = finalize_pending(h);
+    if (rc != RSB_OK && rc != RSB_ERR_OUTPUT_CAPACITY) return rc;
+    if (!h->last_has_plan) return fail(RSB_ERR_INVALID_ARGUMENT, "last batch did not keep its plan");
+    if (job >= h->job_unit.size()) return fail(RSB_ERR_INVALID_ARGUMENT, "bad job index");
+    RSB_CUDA(cudaSetDevice(h->device));
+    const uint32_t unit = h->job_unit[job];
+    const UnitDev &U = h->h_units_back.as<UnitDev>()[unit];
+    const size_t total = (size_t)U.total_out;
+    if (n_frames) *n_frames = total;
+    const size_t cnt = std::min(total, max_frames);
+    if (cnt == 0) return RSB_OK;
+    RSB_CUDA(h->d_dbg.reserve(cnt * 4 * sizeof(uint32_t)));
+    uint32_t *d = h->d_dbg.as<uint32_t>();
+    rsb::launch_expand_plan(h->d_units.as<UnitDev>(), unit, h->d_segs.as<rsb::PlanSeg>(),
+                            (uint32_t)cnt, d, d + cnt, d + 2 * cnt, d + 3 * cnt, h->stream);
+    h->launches += 1;
+    RSB_CUDA(cudaGetLastError());
+    RSB_CUDA(cudaStreamSynchronize(h->stream));
+    uint32_t *dst[4] = {input_offset, phase1, phase2, frac_bits};
+    for (int k = 0; k < 4; ++k)
+        if (dst[k])
+            RSB_CUDA(cudaMemcpy(dst[k], d + (size_t)k * cnt, cnt * sizeof(uint32_t),
+                                cudaMemcpyDeviceToHost));
+    return RSB_OK;
+}
+
+int rsb_fir_timer_start(rsb_fir *h) {
+    if (check_handle(h)) return RSB_ERR_INVALID_ARGUMENT;
+    RSB_CUDA(cudaSetDevice(h->device));
+    RSB_CUDA(cudaEventRecord(h->ev_t0, h->stream));
+    return RSB_OK;
+}
+
+int rsb_fir_timer_stop(rsb_fir *h, float *elapsed_ms) {
+    if (check_handle(h)) return RSB_ERR_INVALID_ARGUMENT;
+    RSB_CUDA(cudaSetDevice(h->device));
+    RSB_CUDA(cudaEventRecord(h->ev_t1, h->stream));
+    RSB_CUDA(cudaEventSynchronize(h->ev_t1));
+    float ms = 0.0f;
+    RSB_CUDA(cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1));
+    if (elapsed_ms) *elapsed_ms = ms;
+    return RSB_OK;
+}
+
+uint64_t rsb_fir_launch_count(const rsb_fir *h) { return h ? h->launches : 0; }
+void *rsb_fir_cuda_stream(const rsb_fir *h) { return h ? (void *)h->stream : nullptr; }
+
+void *rsb_alloc_pinned(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        g_last_error = "cudaMallocHost failed";
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void rsb_free_pinned(void *p) { if (p) cudaFreeHost(p); }
+
+void *rsb_alloc_device(int device, size_t bytes) {
+    void *p = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
+        g_last_error = "cudaMalloc failed";
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void rsb_free_device(int device, void *p) {
+    if (!p) return;
+    cudaSetDevice(device);
+    cudaFree(p);
+}
+
+int rsb_memcpy(int device, void *dst, const void *src, size_t bytes, int kind) {
+    RSB_CUDA(cudaSetDevice(device));
+    cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice
+                     : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    RSB_CUDA(cudaMemcpy(dst, src, bytes, k));
+    return RSB_OK;
+}
+
+int rsb_fill_synthetic(int device, float *dst, uint32_t first_stream, uint32_t n_streams,
+                       uint64_t frames, uint32_t channels, uint32_t rate_hz, uint64_t seed) {
+    if (!dst || rate_hz == 0) return fail(RSB_ERR_INVALID_ARGUMENT, "bad argument");
+    RSB_CUDA(cudaSetDevice(device));
+    rsb::launch_fill_synthetic(dst, first_stream, n_streams, frames, channels, rate_hz, seed, 0);
+    RSB_CUDA(cudaGetLastError());
+    RSB_CUDA(cudaDeviceSynchronize());
+    return RSB_OK;
+}
+
+// ---- host-only entry points ----
+double rsb_host_bessel_i0(double x) { return rsb::bessel_i0(x); }
+double rsb_host_cutoff_kaiser(uint32_t taps, double beta) { return rsb::kaiser_cutoff(taps, beta); }
+void rsb_host_kaiser_window(uint32_t n, double beta, int symmetric, float *out) {
+    rsb::make_kaiser_window(n, beta, symmetric != 0, out);
+}
+void rsb_host_make_sincs(uint32_t sample_count, uint32_t factor, float cutoff, double beta,
+                         int symmetric, float *out) {
+    rsb::make_sincs_for_kaiser(sample_count, factor, cutoff, beta, symmetric != 0, out);
+}
+
+int rsb_host_design_table(uint32_t input_rate_hz, uint32_t output_rate_hz, int latency,
+                          int attenuation, float *out, size_t out_len, uint32_t *cutoff_bits) {
+    if (input_rate_hz == 0) return fail(RSB_ERR_ZERO_INPUT_RATE, rsb_status_string(RSB_ERR_ZERO_INPUT_RATE));
+    if (output_rate_hz == 0) return fail(RSB_ERR_ZERO_OUTPUT_RATE, rsb_status_string(RSB_ERR_ZERO_OUTPUT_RATE));
+    const int taps = rsb::latency_to_taps(latency);
+    const double beta = rsb::attenuation_to_beta(attenuation);
+    if (taps < 0 || beta < 0.0) return fail(RSB_ERR_INVALID_ARGUMENT, "bad latency/attenuation");
+    const float cutoff = rsb::design_cutoff(input_rate_hz, output_rate_hz, (uint32_t)taps, beta);
+    auto t = rsb::get_or_create_table(cutoff, (uint32_t)taps, attenuation);
+    if (cutoff_bits) *cutoff_bits = t->cutoff_bits;
+    if (out) {
+        if (out_len < t->coeffs.size()) return fail(RSB_ERR_INVALID_ARGUMENT, "table buffer too small");
+        std::memcpy(out, t->coeffs.data(), t->coeffs.size() * sizeof(float));
+    }
+    return RSB_OK;
+}
+
+namespace {
+struct HostSink {
+    std::vector<rsb::PlanSeg> *segs;
+    uint32_t out0 = 0;
+    int64_t vbase = 0;
+    void seg(int64_t base_bits, int64_t step_bits, uint32_t n) {
+        segs->push_back(rsb::PlanSeg{base_bits, step_bits, n, out0, vbase});
+        out0 += n;
+    }
+};
+}  // namespace
+
+size_t rsb_host_plan(uint32_t input_rate_hz, uint32_t output_rate_hz, int latency,
+                     uint64_t *position_bits, uint32_t *available, uint64_t total_frames,
+                     uint32_t call_frames, uint32_t cap_frames, int single_call,
+                     uint32_t *calls_consumed, uint32_t *calls_produced, size_t max_calls,
+                     uint32_t *input_offset, uint32_t *phase1, uint32_t *phase2,
+                     uint32_t *frac_bits, size_t max_frames, size_t *n_frames,
+                     size_t *n_segments) {
+    const int taps = rsb::latency_to_taps(latency);
+    if (taps < 0 || input_rate_hz == 0 || output_rate_hz == 0 || !position_bits || !available) {
+        if (n_frames) *n_frames = 0;
+        return 0;
+    }
+    const double ratio = (double)input_rate_hz / (double)output_rate_hz;
+    rsb::PlanState st;
+    st.position = rsb::bits2d((int64_t)*position_bits);
+    st.available = *available;
+    std::vector<rsb::PlanSeg> segs;
+    HostSink sink;
+    sink.segs = &segs;
+    uint64_t offset = 0;
+    int64_t advanced = 0;
+    size_t n_calls = 0;
+    // mirrors plan_units_kernel (fir_kernels.cu)
+    for (;;) {
+        if (!single_call && offset >= total_frames) break;
+        const uint64_t remaining = total_frames - offset;
+        const uint32_t chunk =
+            single_call ? (uint32_t)std::min<uint64_t>(remaining, 0xffffffffull)
+                        : (uint32_t)std::min<uint64_t>(remaining, call_frames);
+        sink.vbase = advanced;
+        const rsb::CallResult r = rsb::plan_call(st, ratio, (uint32_t)taps, chunk, cap_frames, sink);
+        if (n_calls < max_calls) {
+            if (calls_consumed) calls_consumed[n_calls] = r.copied;
+            if (calls_produced) calls_produced[n_calls] = r.produced;
+        }
+        n_calls += 1;
+        offset += r.copied;
+        advanced += r.advanced;
+        if (single_call || r.copied == 0) break;
+    }
+    size_t k = 0;
+    for (const rsb::PlanSeg &sg : segs) {
+        for (uint32_t j = 0; j < sg.n; ++j, ++k) {
+            if (k >= max_frames) continue;
+            const rsb::PhasePoint pp =
+                rsb::phase_point(rsb::bits2d(sg.base_bits + (int64_t)j * sg.step_bits));
+            if (input_offset) input_offset[k] = pp.off;
+            if (phase1) phase1[k] = pp.phase1;
+            if (phase2) phase2[k] = pp.phase2;
+            if (frac_bits) {
+                uint32_t b;
+                std::memcpy(&b, &pp.frac, 4);
+                frac_bits[k] = b;
+            }
+        }
+    }
+    if (n_frames) *n_frames = k;
+    if (n_segments) *n_segments = segs.size();
+    *position_bits = (uint64_t)rsb::d2bits(st.position);
+    *available = st.available;
+    return n_calls;
+}
+
+}  // extern "C"

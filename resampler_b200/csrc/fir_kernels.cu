@@ -1,0 +1,360 @@
+// fir_kernels.cu -- plan / tile / exact-convolution / state kernels for sm_100a.
+//
+// Pipeline of one submit (all on the handle's stream):
+//   plan_units_kernel   one thread per plan unit: exact f64 phase walk in closed form
+//                       (planner.h), emits segments + per-call counts + tile slices
+//   tile_index_kernel   one thread per tile: binary search of its first segment
+//   conv_*_kernel       persistent CTAs over (tile, stream group)
+//   update_state_kernel one CTA per job: history tail -> other history buffer, scalars
+#include "fir_kernels.h"
+
+namespace rsb {
+
+// ---------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------
+struct SegSink {
+    PlanSeg *segs;
+    uint32_t cap;
+    uint32_t n;
+    uint32_t out0;
+    int64_t vbase;
+    __device__ __forceinline__ void seg(int64_t base_bits, int64_t step_bits, uint32_t cnt) {
+        if (n < cap) {
+            PlanSeg s;
+            s.base_bits = base_bits;
+            s.step_bits = step_bits;
+            s.n = cnt;
+            s.out0 = out0;
+            s.vbase = vbase;
+            segs[n] = s;
+        }
+        n += 1;
+        out0 += cnt;
+    }
+};
+
+__global__ void plan_units_kernel(UnitDev *units, uint32_t n_units, StreamStateDev st,
+                                  double ratio, uint32_t taps, PlanSeg *segs, CallCounts *calls,
+                                  uint32_t tile_out, uint32_t *tile_total) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units) return;
+    UnitDev U = units[u];
+    PlanState s;
+    s.position = st.position[U.rep_stream];
+    s.available = st.hist_len[U.rep_stream];
+    const uint32_t hist0 = s.available;
+    SegSink sink{segs + U.seg_off, U.seg_cap, 0u, 0u, 0};
+    uint64_t offset = 0;     // frames handed over so far (the caller loop's input_offset)
+    int64_t advanced = 0;    // frames the read position has moved (virtual frame of position 0)
+    uint32_t n_calls = 0;
+    uint32_t status = 0;
+    for (;;) {
+        if (!U.single_call && offset >= U.total_frames) break;
+        if (n_calls >= U.max_calls) { status = 2; break; }
+        const uint64_t remaining = U.total_frames - offset;
+        const uint32_t chunk =
+            U.single_call ? (uint32_t)(remaining > 0xffffffffull ? 0xffffffffull : remaining)
+                          : (uint32_t)(remaining < U.call_frames ? remaining : U.call_frames);
+        sink.vbase = advanced;
+        const CallResult r = plan_call(s, ratio, taps, chunk, U.cap_frames, sink);
+        if (n_calls < U.call_cap) {
+            CallCounts cc;
+            cc.copied = r.copied;
+            cc.produced = r.produced;
+            calls[U.call_off + n_calls] = cc;
+        }
+        n_calls += 1;
+        offset += r.copied;
+        advanced += r.advanced;
+        if (U.single_call || r.copied == 0) break;
+    }
+    if (sink.n > U.seg_cap) status = 1;
+    const uint32_t n_tiles = (uint32_t)((sink.out0 + tile_out - 1) / tile_out);
+    uint32_t tile_off = 0;
+    if (status != 1 && n_tiles) tile_off = atomicAdd(tile_total, n_tiles);
+    UnitDev *o = units + u;
+    o->total_out = sink.out0;
+    o->total_copied = offset;
+    o->n_calls = n_calls;
+    o->n_segs = sink.n < U.seg_cap ? sink.n : U.seg_cap;
+    o->n_tiles = status == 1 ? 0u : n_tiles;
+    o->tile_off = tile_off;
+    o->status = status;
+    o->hist_len0 = hist0;
+    o->final_available = s.available;
+    o->final_position = s.position;
+}
+
+void launch_plan(UnitDev *units, uint32_t n_units, StreamStateDev st, double ratio, uint32_t taps,
+                 PlanSeg *segs, CallCounts *calls, uint32_t tile_out, uint32_t *tile_total,
+                 cudaStream_t stream) {
+    const uint32_t threads = 32;
+    plan_units_kernel<<<(n_units + threads - 1) / threads, threads, 0, stream>>>(
+        units, n_units, st, ratio, taps, segs, calls, tile_out, tile_total);
+}
+
+// ---------------------------------------------------------------------------
+// tile records
+// ---------------------------------------------------------------------------
+__global__ void tile_index_kernel(const UnitDev *units, const PlanSeg *segs, TileRec *tiles,
+                                  uint32_t tile_out) {
+    const uint32_t u = blockIdx.x;
+    const UnitDev &U = units[u];
+    const uint32_t n_tiles = U.n_tiles;
+    const uint32_t t = blockIdx.y * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    const uint32_t o = t * tile_out;
+    const PlanSeg *sg = segs + U.seg_off;
+    // last segment with out0 <= o
+    uint32_t lo = 0, hi = U.n_segs;   // invariant: sg[lo].out0 <= o, sg[hi] (if any) > o
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (sg[mid].out0 <= o) lo = mid; else hi = mid;
+    }
+    TileRec r;
+    r.unit = u;
+    r.o_start = o;
+    r.seg = U.seg_off + lo;
+    const uint64_t left = U.total_out - o;
+    r.n_out = (uint32_t)(left < tile_out ? left : tile_out);
+    tiles[U.tile_off + t] = r;
+}
+
+void launch_tiles(const UnitDev *units, uint32_t n_units, const PlanSeg *segs, TileRec *tiles,
+                  uint32_t tile_out, uint32_t max_tiles_per_unit, cudaStream_t stream) {
+    if (n_units == 0 || max_tiles_per_unit == 0) return;
+    const uint32_t threads = 128;
+    // gridDim.y is limited to 65535: fold units into x, tile chunks into y
+    uint32_t chunks = (max_tiles_per_unit + threads - 1) / threads;
+    if (chunks > 65535u) chunks = 65535u;   // callers bound tiles per unit below 65535*128
+    dim3 grid(n_units, chunks);
+    tile_index_kernel<<<grid, threads, 0, stream>>>(units, segs, tiles, tile_out);
+}
+
+// ---------------------------------------------------------------------------
+// shared device helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void locate_output(const PlanSeg *segs, uint32_t s, uint32_t o,
+                                              PhasePoint &pp, int64_t &v) {
+    PlanSeg sg = segs[s];
+    while (o >= sg.out0 + sg.n) sg = segs[++s];
+    const double pos = bits2d(sg.base_bits + (int64_t)(o - sg.out0) * sg.step_bits);
+    pp = phase_point(pos);
+    v = sg.vbase + (int64_t)pp.off;
+}
+
+// ---------------------------------------------------------------------------
+// exact convolution: fir/avx512.rs:5-50 mapped lane for lane onto half-warps
+// ---------------------------------------------------------------------------
+// 16 lanes of a half-warp are the 16 lanes of the zmm registers: lane l owns
+// acc1[l], acc2[l] (FMA chains over taps/16 steps, :36-37), blends them with
+// separately rounded mul, mul, add (:41-45), and the half-warp reduces with the
+// halving tree of _mm512_reduce_add_ps (:48) via xor-shuffles 8, 4, 2, 1.
+template <int TAPS>
+__global__ void __launch_bounds__(256) conv_exact_kernel(ConvParams P) {
+    __shared__ int64_t s_v[kExactTileOut];
+    __shared__ uint32_t s_p1[kExactTileOut];
+    __shared__ float s_frac[kExactTileOut];
+
+    const uint32_t ch = P.channels;
+    const uint32_t n_items = *P.tile_total * P.groups;
+    const uint32_t lane16 = threadIdx.x & 15u;
+    const uint32_t half = (threadIdx.x >> 4) & 1u;
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t n_warps = blockDim.x >> 5;
+
+    for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const uint32_t t = w / P.groups, g = w - t * P.groups;
+        const TileRec rec = P.tiles[t];
+        const UnitDev &U = P.units[rec.unit];
+        const uint32_t m0 = g * P.streams_per_group;
+        if (m0 >= U.n_members) continue;
+        const uint32_t nm = min(P.streams_per_group, U.n_members - m0);
+        const int64_t H = (int64_t)U.hist_len0;
+
+        __syncthreads();
+        if (threadIdx.x < rec.n_out) {
+            PhasePoint pp;
+            int64_t v;
+            locate_output(P.segs, rec.seg, rec.o_start + threadIdx.x, pp, v);
+            s_v[threadIdx.x] = v;
+            s_p1[threadIdx.x] = pp.phase1;
+            s_frac[threadIdx.x] = pp.frac;
+        }
+        __syncthreads();
+
+        const uint32_t per_stream = rec.n_out * ch;
+        const uint32_t total = nm * per_stream;
+        for (uint32_t base = warp * 2; base < total; base += n_warps * 2) {
+            const uint32_t idx_raw = base + half;
+            const bool valid = idx_raw < total;
+            const uint32_t idx = valid ? idx_raw : total - 1;
+            const uint32_t m = idx / per_stream;
+            const uint32_t rem = idx - m * per_stream;
+            const uint32_t k = rem / ch;
+            const uint32_t c = rem - k * ch;
+            const JobDev job = P.jobs[P.members[U.member_off + m0 + m]];
+            const float *hist = P.st.hist[P.st.hist_sel[job.stream]] +
+                                (size_t)job.stream * kHistFrames * ch;
+            const int64_t v = s_v[k];
+            const uint32_t p1 = s_p1[k];
+            const uint32_t p2 = p1 + 1 < kPhases - 1 ? p1 + 1 : kPhases - 1;
+            const float frac = s_frac[k];
+            const float *c1 = P.coeffs + (size_t)p1 * TAPS;
+            const float *c2 = P.coeffs + (size_t)p2 * TAPS;
+            float acc1 = 0.0f, acc2 = 0.0f;
+#pragma unroll
+            for (int i = 0; i < TAPS / 16; ++i) {
+                const int64_t vv = v + i * 16 + lane16;
+                const float x = vv < H ? hist[((int64_t)kHistFrames - H + vv) * ch + c]
+                                       : job.in[(vv - H) * ch + c];
+                acc1 = __fmaf_rn(__ldg(c1 + i * 16 + lane16), x, acc1);
+                acc2 = __fmaf_rn(__ldg(c2 + i * 16 + lane16), x, acc2);
+            }
+            const float omf = __fsub_rn(1.0f, frac);
+            float s = __fadd_rn(__fmul_rn(acc1, omf), __fmul_rn(acc2, frac));
+            s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 8));
+            s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 4));
+            s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 2));
+            s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 1));
+            const uint64_t o = (uint64_t)rec.o_start + k;
+            if (valid && lane16 == 0 && o < job.out_capacity) job.out[o * ch + c] = s;
+        }
+    }
+}
+
+void launch_conv_exact(const ConvParams &p, uint32_t max_items, int sm_count,
+                       cudaStream_t stream) {
+    if (max_items == 0) return;
+    uint32_t grid = (uint32_t)sm_count * 8u;
+    if (grid > max_items) grid = max_items;
+    switch (p.taps) {
+        case 16: conv_exact_kernel<16><<<grid, 256, 0, stream>>>(p); break;
+        case 32: conv_exact_kernel<32><<<grid, 256, 0, stream>>>(p); break;
+        case 64: conv_exact_kernel<64><<<grid, 256, 0, stream>>>(p); break;
+        default: conv_exact_kernel<128><<<grid, 256, 0, stream>>>(p); break;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// state write-back
+// ---------------------------------------------------------------------------
+__global__ void update_state_kernel(const UnitDev *units, const JobDev *jobs, StreamStateDev st,
+                                    uint32_t ch) {
+    const JobDev job = jobs[blockIdx.x];
+    const UnitDev &U = units[job.unit];
+    const uint32_t sel = st.hist_sel[job.stream];
+    const float *old_hist = st.hist[sel] + (size_t)job.stream * kHistFrames * ch;
+    float *new_hist = st.hist[sel ^ 1u] + (size_t)job.stream * kHistFrames * ch;
+    const int64_t H0 = U.hist_len0, H1 = U.final_available;
+    const int64_t v_end = H0 + (int64_t)U.total_copied;
+    const int64_t v0 = v_end - H1;   // first virtual frame that stays buffered
+    const int64_t n_vals = H1 * ch;
+    for (int64_t i = threadIdx.x; i < n_vals; i += blockDim.x) {
+        const int64_t f = i / ch, c = i - f * ch;
+        const int64_t vv = v0 + f;
+        const float x = vv < H0 ? old_hist[((int64_t)kHistFrames - H0 + vv) * ch + c]
+                                : job.in[(vv - H0) * ch + c];
+        new_hist[((int64_t)kHistFrames - H1 + f) * ch + c] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st.position[job.stream] = U.final_position;
+        st.hist_len[job.stream] = (uint32_t)H1;
+        st.hist_sel[job.stream] = (uint8_t)(sel ^ 1u);
+    }
+}
+
+void launch_update(const UnitDev *units, const JobDev *jobs, uint32_t n_jobs, StreamStateDev st,
+                   uint32_t channels, cudaStream_t stream) {
+    if (n_jobs == 0) return;
+    update_state_kernel<<<n_jobs, 128, 0, stream>>>(units, jobs, st, channels);
+}
+
+__global__ void reset_state_kernel(StreamStateDev st, uint32_t first, uint32_t count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    st.position[first + i] = 0.0;     // resampler_fir.rs:638-642
+    st.hist_len[first + i] = 0u;
+}
+
+void launch_reset(StreamStateDev st, uint32_t first, uint32_t count, cudaStream_t stream) {
+    if (count == 0) return;
+    reset_state_kernel<<<(count + 255) / 256, 256, 0, stream>>>(st, first, count);
+}
+
+// ---------------------------------------------------------------------------
+// plan expansion (debug / parity of phase indices)
+// ---------------------------------------------------------------------------
+__global__ void expand_plan_kernel(const UnitDev *units, uint32_t unit, const PlanSeg *segs,
+                                   uint32_t n_frames, uint32_t *off, uint32_t *p1, uint32_t *p2,
+                                   uint32_t *fb) {
+    const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_frames) return;
+    const UnitDev &U = units[unit];
+    const PlanSeg *sg = segs + U.seg_off;
+    uint32_t lo = 0, hi = U.n_segs;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (sg[mid].out0 <= o) lo = mid; else hi = mid;
+    }
+    PhasePoint pp;
+    int64_t v;
+    locate_output(segs, U.seg_off + lo, o, pp, v);
+    if (off) off[o] = pp.off;
+    if (p1) p1[o] = pp.phase1;
+    if (p2) p2[o] = pp.phase2;
+    if (fb) fb[o] = __float_as_uint(pp.frac);
+}
+
+void launch_expand_plan(const UnitDev *units, uint32_t unit, const PlanSeg *segs, uint32_t n_frames,
+                        uint32_t *off, uint32_t *p1, uint32_t *p2, uint32_t *fb,
+                        cudaStream_t stream) {
+    if (n_frames == 0) return;
+    expand_plan_kernel<<<(n_frames + 255) / 256, 256, 0, stream>>>(units, unit, segs, n_frames, off,
+                                                                    p1, p2, fb);
+}
+
+// ---------------------------------------------------------------------------
+// synthetic input
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+__global__ void fill_synthetic_kernel(float *dst, uint32_t first_stream, uint32_t n_streams,
+                                      uint64_t frames, uint32_t ch, uint32_t rate, uint64_t seed) {
+    const uint64_t per_stream = frames * ch;
+    const uint64_t total = per_stream * n_streams;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t s_local = i / per_stream;
+        const uint64_t r = i - s_local * per_stream;
+        const uint64_t n = r / ch;
+        const uint32_t c = (uint32_t)(r - n * ch);
+        const uint64_t s = first_stream + s_local;
+        const uint64_t f = 110ull * (1ull + (s % 64ull)) + 7ull * c;   // Hz
+        const uint64_t ph = (f * n) % rate;                            // exact phase numerator
+        const float sine = sinpif(2.0f * (float)ph / (float)rate);
+        const uint64_t h = splitmix64(seed ^ (s << 32) ^ ((uint64_t)c << 62) ^ n);
+        const float u = (float)(h >> 40) * (1.0f / 8388608.0f) - 1.0f;   // [-1, 1)
+        dst[i] = 0.5f * sine + 0.25f * u;
+    }
+}
+
+void launch_fill_synthetic(float *dst, uint32_t first_stream, uint32_t n_streams, uint64_t frames,
+                           uint32_t channels, uint32_t rate_hz, uint64_t seed,
+                           cudaStream_t stream) {
+    const uint64_t total = frames * channels * n_streams;
+    if (total == 0) return;
+    uint64_t blocks = (total + 255) / 256;
+    if (blocks > 148ull * 32ull) blocks = 148ull * 32ull;
+    fill_synthetic_kernel<<<(uint32_t)blocks, 256, 0, stream>>>(dst, first_stream, n_streams, frames,
+                                                                channels, rate_hz, seed);
+}
+
+}  // namespace rsb

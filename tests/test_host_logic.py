@@ -1,0 +1,198 @@
+"""CPU tests of the PRODUCT's host logic against the oracle (no GPU needed):
+  * the C-ABI library loads and exports every symbol include/resampler_b200.h declares;
+  * the host filter design equals the oracle's table bit for bit and passes the
+    reference's known-answer tests (src/window.rs:152-410);
+  * the closed-form phase planner (csrc/planner.h -- the same code the device runs)
+    reproduces the oracle's (consumed, produced) sequence and every per-frame
+    (input_offset, phase1, phase2, frac bits) bit for bit.
+"""
+import random
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from resampler_b200 import _lib
+from resampler_b200.fir import (Attenuation, Latency, ResampleError, SampleRate, host_design_table,
+                                host_plan)
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "resampler_b200.h").read_text()
+    declared = set(re.findall(r"\b(rsb_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    lib = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert b"sm_100a" in lib.rsb_version()
+
+
+def test_no_gpu_fails_loudly_not_silently():
+    """Without a usable device, create must return an error -- there is no CPU fallback."""
+    import ctypes as C
+    lib = _lib.load()
+    if lib.rsb_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    h = C.c_void_p()
+    rc = lib.rsb_fir_create(C.byref(h), 0, 1, 2, 44100, 48000, 3, 1)
+    assert rc == 100 and not h.value
+    # argument errors are still reported first, like the reference's asserts (:302-309)
+    assert lib.rsb_fir_create(C.byref(h), 0, 1, 2, 0, 48000, 3, 1) == 10
+    assert lib.rsb_fir_create(C.byref(h), 0, 1, 2, 44100, 0, 3, 1) == 11
+    assert lib.rsb_status_string(10) == b"input sample rate must be greater than zero"
+    assert lib.rsb_status_string(11) == b"output sample rate must be greater than zero"
+    assert lib.rsb_status_string(1) == b"Input buffer size is invalid"
+    assert lib.rsb_status_string(2) == b"Output buffer size is invalid"
+
+
+def test_enums_mirror_reference():
+    assert [lat.taps() for lat in Latency] == [16, 32, 64, 128]
+    assert Latency.default() == Latency.Sample64 and Attenuation.default() == Attenuation.Db120
+    assert sorted(int(r) for r in SampleRate) == [16000, 22050, 32000, 44100, 48000, 88200, 96000,
+                                                  176400, 192000, 384000]
+    with pytest.raises(ValueError):
+        SampleRate.try_from(12345)
+    assert str(ResampleError(1)) == "Input buffer size is invalid"
+    assert str(ResampleError(2)) == "Output buffer size is invalid"
+
+
+# ---- filter design -------------------------------------------------------------------------
+@pytest.mark.parametrize("in_hz,out_hz,lat,att", [
+    (44100, 48000, 3, 1), (48000, 44100, 3, 1), (16000, 48000, 1, 1), (96000, 48000, 2, 1),
+    (22050, 44100, 3, 1), (48000, 44100, 3, 2), (48000, 44100, 1, 0), (24000, 16000, 2, 0),
+    (384000, 16000, 0, 2)])
+def test_design_table_bit_identical_to_oracle(in_hz, out_hz, lat, att):
+    tab, bits = host_design_table(in_hz, out_hz, Latency(lat), Attenuation(att))
+    ref = O.design_table(in_hz, out_hz, lat, att)
+    assert bits == int(O.cutoff_for(in_hz, out_hz, Latency(lat).taps(),
+                                    [7.0, 10.0, 13.0][att]).view(np.uint32))
+    assert np.array_equal(tab.view(np.uint32), ref.view(np.uint32))
+
+
+def test_host_design_known_answers():
+    """src/window.rs:152-160, 230-237, 273-294, 364-385 through the product's own code."""
+    import ctypes as C
+    lib = _lib.load()
+    for x, e in [(0.0, 1.0), (1.0, 1.266065877752008), (2.0, 2.279585302336067),
+                 (5.0, 27.239871823604442), (10.0, 2815.716628466254)]:
+        assert abs(lib.rsb_host_bessel_i0(x) / e - 1) < 1e-6
+    for n, e in [(64, 0.8999482371370552), (128, 0.9499741185685276), (256, 0.9749870592842638),
+                 (512, 0.9874935296421319), (1024, 0.9937467648210659)]:
+        assert abs(lib.rsb_host_cutoff_kaiser(n, 10.0) / e - 1) < 1e-6
+    for sym, expected in [
+            (0, [[-0.0084796025, 0.4976338439, 0.4976338439, -0.0084796025],
+                 [-0.0000355271, 0.0296676259, 0.9623917926, 0.0296676259]]),
+            (1, [[-0.0135119673, 0.6818196469, 0.3016755841, -0.0000802533],
+                 [-0.0000397065, 0.0471924586, 0.9759149497, 0.0070292878]])]:
+        out = np.zeros((2, 4), np.float32)
+        lib.rsb_host_make_sincs(4, 2, C.c_float(0.9), 10.0, sym, out.ctypes.data_as(_lib.f32p))
+        assert np.allclose(out, np.array(expected), rtol=1e-5, atol=0)
+    w = np.zeros(9, np.float32)
+    lib.rsb_host_kaiser_window(9, 10.0, 1, w.ctypes.data_as(_lib.f32p))
+    assert np.array_equal(w, O.kaiser_window(9, 10.0, True))
+    w = np.zeros(15, np.float32)
+    lib.rsb_host_kaiser_window(15, 5.0, 0, w.ctypes.data_as(_lib.f32p))
+    assert np.array_equal(w, O.kaiser_window(15, 5.0, False))
+
+
+# ---- planner -------------------------------------------------------------------------------
+RATE_PAIRS = [(44100, 48000), (48000, 44100), (16000, 48000), (96000, 48000), (192000, 8000),
+              (8000, 192000), (384000, 1000), (44100, 44101), (22050, 48000), (48000, 48000),
+              (1, 48000), (48000, 1), (11025, 384000), (44100, 176400), (3, 7), (1000003, 999983)]
+
+
+def _oracle_calls(in_hz, out_hz, lat, calls):
+    """Runs the given (in_frames, cap_frames) call list on the oracle, mono."""
+    f = O.OracleFir(1, in_hz, out_hz, lat, 1)
+    res = []
+    for n_in, cap in calls:
+        out = np.zeros(cap, np.float32)
+        err, c, p, tr = f.resample(np.zeros(n_in, np.float32), out, trace=True)
+        assert err == 0
+        res.append((c, p, tr))
+    return res
+
+
+@pytest.mark.parametrize("in_hz,out_hz", RATE_PAIRS)
+def test_planner_single_calls_match_oracle(in_hz, out_hz):
+    """Random call sizes and output capacities: state carried in (position bits, available)."""
+    rnd = random.Random(in_hz * 7 + out_hz)
+    for lat in (0, 1, 3):
+        calls = []
+        for _ in range(60):
+            n_in = rnd.choice([0, 1, 7, 64, 160, 512, 1000, 4096, 9000, rnd.randrange(0, 9000)])
+            cap = rnd.choice([0, 1, 100, 5000, 20000, rnd.randrange(0, 20000)])
+            calls.append((n_in, cap))
+        ref = _oracle_calls(in_hz, out_hz, lat, calls)
+        pos_bits, avail = 0, 0
+        for (n_in, cap), (c, p, tr) in zip(calls, ref):
+            r = host_plan(in_hz, out_hz, Latency(lat), pos_bits, avail, n_in, 0, cap, True,
+                          max_calls=4, max_frames=max(cap, 1))
+            assert r["calls"] == 1
+            assert (int(r["consumed"][0]), int(r["produced"][0])) == (c, p), (n_in, cap)
+            assert r["n_frames"] == p
+            for key in ("input_offset", "phase1", "phase2", "frac_bits"):
+                assert np.array_equal(r[key], tr[key]), (key, n_in, cap)
+            pos_bits, avail = r["position_bits"], r["available"]
+
+
+@pytest.mark.parametrize("in_hz,out_hz,lat,call,cap", [
+    (44100, 48000, 3, 512, 0), (48000, 44100, 3, 512, 0), (16000, 48000, 1, 160, 0),
+    (16000, 48000, 1, 64, 0), (96000, 48000, 2, 512, 0), (44100, 48000, 3, 4096, 0),
+    (44100, 48000, 3, 512, 100), (384000, 1000, 0, 512, 0), (44100, 48000, 3, 5000, 0),
+    (8000, 192000, 3, 33, 0), (44100, 48000, 0, 1, 0), (22050, 48000, 3, 256, 7)])
+def test_planner_canonical_loop_matches_oracle(in_hz, out_hz, lat, call, cap):
+    """The multi-call walk: per-call counts and every frame of the plan, 2 s of audio."""
+    total = in_hz * 2 if in_hz > 100 else 4000
+    total = min(total, 200000)
+    f = O.OracleFir(1, in_hz, out_hz, lat, 1)
+    ref = f.process(np.zeros(total, np.float32), call, out_cap_len=cap, trace=True)
+    bso = f.buffer_size_output()
+    r = host_plan(in_hz, out_hz, Latency(lat), 0, 0, total, call, cap if cap else bso, False,
+                  max_calls=len(ref["consumed"]) + 8, max_frames=len(ref["out"]) + 8)
+    assert r["calls"] == ref["calls"]
+    assert np.array_equal(r["consumed"], ref["consumed"])
+    assert np.array_equal(r["produced"], ref["produced"])
+    assert r["n_frames"] == len(ref["out"])
+    for key in ("input_offset", "phase1", "phase2", "frac_bits"):
+        assert np.array_equal(r[key], ref["trace"][key]), key
+    # the closed form must actually compress: far fewer segments than frames for real audio
+    if r["n_frames"] > 10000 and call >= 64 and cap == 0:
+        assert r["n_segments"] * 4 < r["n_frames"]
+
+
+def test_planner_60s_headline_config():
+    """BASELINE config 2's plan: 60 s 44.1->48 kHz, 128 taps, 512-frame calls."""
+    total = 44100 * 60
+    f = O.OracleFir(1, 44100, 48000, 3, 1)
+    ref = f.process(np.zeros(total, np.float32), 512, trace=True)
+    r = host_plan(44100, 48000, Latency.Sample64, 0, 0, total, 512, 4321, False, max_calls=6000,
+                  max_frames=2900000)
+    assert r["calls"] == 5168 and r["n_frames"] == 2879862
+    assert np.array_equal(r["produced"], ref["produced"])
+    for key in ("input_offset", "phase1", "phase2", "frac_bits"):
+        assert np.array_equal(r[key], ref["trace"][key]), key
+
+
+def test_planner_start_states_with_drifted_positions():
+    """Starts from accumulator values with low-order garbage (as after long runs)."""
+    rnd = random.Random(99)
+    for in_hz, out_hz in [(44100, 48000), (48000, 44100), (16000, 48000), (192000, 8000)]:
+        f = O.OracleFir(1, in_hz, out_hz, 3, 1)
+        pos_bits, avail = 0, 0
+        for it in range(200):
+            n_in = rnd.randrange(0, 3000)
+            cap = rnd.choice([20000, rnd.randrange(1, 3000)])
+            out = np.zeros(cap, np.float32)
+            err, c, p, tr = f.resample(np.zeros(n_in, np.float32), out, trace=True)
+            r = host_plan(in_hz, out_hz, Latency.Sample64, pos_bits, avail, n_in, 0, cap, True,
+                          max_calls=2, max_frames=max(cap, 1))
+            assert (int(r["consumed"][0]), int(r["produced"][0])) == (c, p), it
+            for key in ("input_offset", "phase1", "phase2", "frac_bits"):
+                assert np.array_equal(r[key], tr[key]), (key, it)
+            pos_bits, avail = r["position_bits"], r["available"]
