@@ -1,0 +1,420 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config.
+
+metric : output Msamples/s, batched FIR 44.1->48 kHz, 128 taps (Latency::Sample64, Db90)
+config : configs[1] = 1024 stereo streams x 60 s synthetic audio per GPU, 512-frame calls
+         (5168 virtual resample() calls per stream, all inside one rsb_fir_process_batch)
+step   : one pass of the hot path over that whole batch (reset + plan + convolve + state)
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA path
+  python bench.py --impl reference ...                     the reference's CPU path (oracle port,
+                                                           multi-threaded, one stream per thread)
+Under torchrun (N > 1) every rank drives one GPU with its own 1024 streams (weak scaling,
+streams are independent: no collective on the data path); rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+IN_HZ, OUT_HZ, CHANNELS, TAPS = 44100, 48000, 2, 128
+LATENCY, ATTENUATION = 3, 1          # Sample64, Db90
+CALL_FRAMES = 512
+METRIC = "output Msamples/s, batched FIR 44.1->48k 128-tap"
+FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 74.4: 148 SM x 128 FMA/clk x 1.965 GHz
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=1024, help="streams per GPU")
+    ap.add_argument("--seconds", type=float, default=60.0, help="audio seconds per stream")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "exact", "fast"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-slice-seconds", type=float, default=5.0)
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    return rank, world, local, dist
+
+
+def barrier(dist, local):
+    if dist is not None:
+        import torch
+        dist.barrier()
+        torch.cuda.synchronize(local)
+
+
+def reduce_max(dist, local, value: float) -> float:
+    if dist is None:
+        return value
+    import torch
+    t = torch.tensor([value], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def reduce_sum(dist, local, value: float) -> float:
+    if dist is None:
+        return value
+    import torch
+    t = torch.tensor([value], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle's multi-threaded AVX-512 port
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_run(inp: np.ndarray, frames: int, threads: int, repeats: int = 1):
+    """inp: [n_streams, frames*CHANNELS].  Returns (Msamples/s, produced per pass, seconds)."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import oracle_lib as O
+    best = None
+    produced_total = 0
+    for _ in range(repeats):
+        secs, produced, _ = O.cpu_bench(inp.shape[0], CHANNELS, IN_HZ, OUT_HZ, LATENCY, ATTENUATION,
+                                        inp, frames, CALL_FRAMES, threads, use_avx512=True)
+        produced_total = int(produced.sum())
+        best = secs if best is None else min(best, secs)
+    return produced_total / best / 1e6, produced_total, best
+
+
+def host_synthetic(n_streams: int, frames: int, seed: int = 0x5EED) -> np.ndarray:
+    """Host-side stand-in for the device generator (same spectrum: sine + uniform noise)."""
+    rng = np.random.default_rng(seed)
+    n = np.arange(frames, dtype=np.float64)
+    out = np.empty((n_streams, frames * CHANNELS), np.float32)
+    for s in range(n_streams):
+        for c in range(CHANNELS):
+            f = 110.0 * (1 + (s % 64)) + 7.0 * c
+            out[s, c::CHANNELS] = (0.5 * np.sin(2 * np.pi * f * n / IN_HZ) +
+                                   0.25 * rng.uniform(-1, 1, frames)).astype(np.float32)
+    return out
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, str(ROOT / "tests"))
+    import oracle_lib as O
+    threads = os.cpu_count() or 1
+    # bounded sample of the same workload: 2 streams per thread x 2 s of audio per step
+    n_streams = 2 * threads
+    frames = IN_HZ * 2
+    inp = host_synthetic(n_streams, frames)
+    for _ in range(args.warmup):
+        cpu_reference_run(inp, frames, threads)
+    t_total, produced = 0.0, 0
+    for _ in range(args.steps):
+        _, p, secs = cpu_reference_run(inp, frames, threads)
+        t_total += secs
+        produced += p
+    value = produced / t_total / 1e6
+    sample = (f"{n_streams} stereo streams x 2 s per step, 512-frame calls, one stream per thread, "
+              f"AVX-512 intrinsics={'yes' if O.lib().orc_cpu_has_avx512f() else 'no (scalar-coded 16-lane order)'}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "Msamples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(1e3 * t_total / max(args.steps, 1), 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: 1024 stereo streams x 60 s, 44.1->48 kHz, Sample64 "
+                               "(128 taps), Db90, 512-frame calls (bounded CPU sample of it)"},
+        "cpu_baseline": {"value": round(value, 3), "unit": "Msamples/s", "cores": threads,
+                         "kind": "port", "sample": sample},
+        "e2e": {"value": round(value, 3), "unit": "Msamples/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "note": "the Rust reference cannot be built here (no rustc); this is the line-faithful C "
+                "port of its AVX-512 path (oracle/), multi-threaded on the host cores",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    from resampler_b200 import Attenuation, FirBatch, Kernel, Latency
+    from resampler_b200.fir import FLAG_ASYNC, MEM_DEVICE, MEM_HOST, DeviceBuffer
+    from resampler_b200 import _lib
+    import ctypes as C
+
+    rank, world, local, dist = dist_setup(args.gpus)
+    lib = _lib.load()
+    n_streams = args.streams
+    frames = int(round(args.seconds * IN_HZ))
+    kern = {"auto": Kernel.AUTO, "exact": Kernel.EXACT, "fast": Kernel.FAST}[args.kernel]
+    batch = FirBatch(n_streams, CHANNELS, IN_HZ, OUT_HZ, Latency(LATENCY), Attenuation(ATTENUATION),
+                     device=local, kernel=kern)
+    in_stride = frames * CHANNELS
+    out_frames_cap = int(frames / batch.ratio()) + 8
+    out_stride = (out_frames_cap * CHANNELS + 3) & ~3
+    d_in = DeviceBuffer(local, n_streams * in_stride)
+    d_out = DeviceBuffer(local, n_streams * out_stride)
+    rc = lib.rsb_fill_synthetic(local, d_in.ptr, rank * n_streams, n_streams, frames, CHANNELS,
+                                IN_HZ, 0x5EED)
+    assert rc == 0, _lib.last_error()
+    in_ptrs = [d_in.ptr + 4 * s * in_stride for s in range(n_streams)]
+    out_ptrs = [d_out.ptr + 4 * s * out_stride for s in range(n_streams)]
+    lens = [in_stride] * n_streams
+    caps = [out_stride] * n_streams
+
+    def step(flags=FLAG_ASYNC):
+        batch.reset(-1)
+        return batch.process_ptrs(in_ptrs, lens, CALL_FRAMES * CHANNELS, 0, out_ptrs, caps,
+                                  memspace=MEM_DEVICE, flags=flags)
+
+    # ---- device-resident throughput (value) ----
+    for _ in range(max(args.warmup, 0)):
+        step()
+    batch.sync()
+    launches0 = batch.launch_count()
+    sampler = ClockSampler(local)
+    barrier(dist, local)
+    sampler.start()
+    batch.timer_start()
+    counts = None
+    for _ in range(args.steps):
+        counts = step()
+    ms = batch.timer_stop()
+    batch.sync()
+    clocks = sampler.stop()
+    barrier(dist, local)
+    launches = batch.launch_count() - launches0
+    produced_per_step = int(sum(counts[1][:])) if counts else 0
+    consumed_per_step = int(sum(counts[0][:])) if counts else 0
+    conv_ms = batch.conv_times_ms(min(args.steps, 64))
+    ms_max = reduce_max(dist, local, ms)
+    produced_all = reduce_sum(dist, local, float(produced_per_step))
+    value = produced_all * args.steps / (ms_max * 1e-3) / 1e6          # Msamples/s, whole job
+
+    # ---- roofline of the dominant kernel (the convolution) ----
+    hbm_peak, peak_src = measured_peaks()
+    conv_avg_ms = float(np.mean(conv_ms)) if len(conv_ms) else float("nan")
+    alg_flops = produced_per_step * 2.0 * TAPS
+    alg_bytes = 4.0 * (produced_per_step + consumed_per_step)
+    fp32_tflops = alg_flops / (conv_avg_ms * 1e-3) / 1e12
+    hbm_gbs = alg_bytes / (conv_avg_ms * 1e-3) / 1e9
+    fp32_meas = None
+    r, a = C.c_double(0), C.c_double(0)
+    if rank == 0 and lib.rsb_microbench(local, 1, 4, C.byref(r), C.byref(a)) == 0:
+        fp32_meas = r.value
+    traffic = None
+    tp = ROOT / "profiles" / "conv_traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    fp32_peak = fp32_meas if fp32_meas else FP32_NOMINAL_TFLOPS
+    roofline = {
+        "bound": "fp32", "kernel": "conv (dominant kernel of the step)",
+        "achieved": round(fp32_tflops, 3), "peak": round(fp32_peak, 2), "unit": "TFLOP/s",
+        "frac": round(fp32_tflops / fp32_peak, 4),
+        "peak_source": ("FFMA2 register micro-benchmark run in this process"
+                        if fp32_meas else "nominal 148 SM x 128 FMA/clk x 1.965 GHz"),
+        "frac_of_nominal_74.4": round(fp32_tflops / FP32_NOMINAL_TFLOPS, 4),
+        "traffic": traffic,
+        "hbm": {"achieved": round(hbm_gbs, 1), "peak": hbm_peak, "unit": "GB/s",
+                "frac": round(hbm_gbs / hbm_peak, 4), "peak_source": peak_src},
+        "conv_ms_per_launch": round(conv_avg_ms, 4),
+        "algorithmic": "2*taps flop and 4*(1+in/out) B per output sample (SURVEY.md 8(d))",
+    }
+
+    # ---- end-to-end through the C ABI with pinned HOST buffers ----
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, batch, lib, frames, n_streams, local, dist)
+
+    # ---- CPU baseline beside it (rank 0, N == 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        cs = min(n_streams, 2 * threads)
+        cframes = min(frames, IN_HZ * 2)
+        host_in = np.empty((cs, cframes * CHANNELS), np.float32)
+        for s in range(cs):      # the very bytes the GPU processed
+            host_in[s] = d_in.download(cframes * CHANNELS, s * in_stride)
+        est, _, secs1 = cpu_reference_run(host_in, cframes, threads)
+        repeats = int(min(max(1, round(10.0 / max(secs1, 1e-3))), 40))
+        t_tot, p_tot = 0.0, 0
+        for _ in range(repeats):
+            _, p, secs = cpu_reference_run(host_in, cframes, threads)
+            t_tot += secs
+            p_tot += p
+        cpu = {"value": round(p_tot / t_tot / 1e6, 3), "unit": "Msamples/s", "cores": threads,
+               "kind": "port",
+               "sample": f"{cs} of the GPU's own streams x {cframes / IN_HZ:.1f} s, 512-frame calls, "
+                         f"one stream per thread, repeated {repeats}x (~{t_tot:.1f} s of CPU work)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 3), "unit": "Msamples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_max / max(args.steps, 1), 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"configs[1]: {n_streams} stereo streams x {args.seconds:g} s "
+                                   f"per GPU, 44.1->48 kHz, Sample64 (128 taps), Db90, 512-frame "
+                                   f"virtual calls ({counts[2][0] if counts else 0} per stream)",
+                       "kernel": args.kernel, "streams_per_gpu": n_streams,
+                       "l2_policy": "inputs larger than L2 (in+out per step "
+                                    f"{(alg_bytes) / 1e9:.1f} GB >> 126 MB)"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks,
+            "produced_samples_per_step_per_gpu": produced_per_step,
+        }
+        print(json.dumps(line), flush=True)
+    batch.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, batch, lib, frames, n_streams, local, dist):
+    """Same workload through rsb_fir_process_batch with HOST (pinned) buffers: every step copies
+    the step's inputs host->device and the results device->host inside the timed region.  The
+    60 s are fed as time slices that reuse one pinned slice buffer (the state carries over)."""
+    import ctypes as C
+    from resampler_b200.fir import MEM_HOST
+    slice_frames = int(round(args.e2e_slice_seconds * IN_HZ))
+    slice_frames -= slice_frames % CALL_FRAMES          # whole calls per slice
+    n_slices = max(1, frames // slice_frames)
+    in_vals = slice_frames * CHANNELS
+    out_vals = (int(slice_frames / batch.ratio()) + 4400) * CHANNELS
+    h_in = lib.rsb_alloc_pinned(n_streams * in_vals * 4)
+    h_out = lib.rsb_alloc_pinned(n_streams * out_vals * 4)
+    if not h_in or not h_out:
+        return {"value": None, "unit": "Msamples/s", "error": "pinned allocation failed"}
+    src = np.ctypeslib.as_array(C.cast(h_in, C.POINTER(C.c_float)), shape=(n_streams, in_vals))
+    src[:] = host_synthetic(1, slice_frames)[0][None, :]
+    in_ptrs = [h_in + 4 * s * in_vals for s in range(n_streams)]
+    out_ptrs = [h_out + 4 * s * out_vals for s in range(n_streams)]
+    lens, caps = [in_vals] * n_streams, [out_vals] * n_streams
+
+    def step():
+        batch.reset(-1)
+        tot_p = 0
+        for _ in range(n_slices):
+            c, p, _ = batch.process_ptrs(in_ptrs, lens, CALL_FRAMES * CHANNELS, 0, out_ptrs, caps,
+                                         memspace=MEM_HOST)
+            tot_p += int(sum(p[:]))
+        return tot_p
+
+    steps = max(1, min(args.steps, 3))
+    step()
+    barrier(dist, local)
+    t0 = time.perf_counter()
+    produced = 0
+    for _ in range(steps):
+        produced += step()
+    batch.sync()
+    dt = time.perf_counter() - t0
+    dt_max = reduce_max(dist, local, dt)
+    produced_all = reduce_sum(dist, local, float(produced))
+    lib.rsb_free_pinned(h_in)
+    lib.rsb_free_pinned(h_out)
+    per_step_p = produced // steps
+    return {"value": round(produced_all / dt_max / 1e6, 3), "unit": "Msamples/s",
+            "h2d_bytes_per_step": int(n_slices * n_streams * in_vals * 4),
+            "d2h_bytes_per_step": int(per_step_p * 4), "steps": steps,
+            "how": f"rsb_fir_process_batch(memspace=HOST, pinned), {n_slices} time slices of "
+                   f"{slice_frames / IN_HZ:.2f} s per step; wall clock around the calls, max over ranks"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -2,7 +2,7 @@
  * resampler_b200.h -- C ABI of the B200-native ResamplerFir path.
  *
  * Drop-in boundary for hasenbanck/resampler v0.5.1's `ResamplerFir`
- * (reference: src/resampler_fir.rs, src/fir/*.rs, src/window.rs).  The reference
+ * (reference: src/resampler_fir.rs, src/fir/, src/window.rs).  The reference
  * has no FFI of its own; these entry points are what a `resampler-cuda` crate
  * binds so that `ResamplerFir::new / new_from_hz /
  * buffer_size_output / resample / delay / reset` keep their meaning, plus the
@@ -150,6 +150,9 @@ int rsb_fir_last_plan(rsb_fir *h, uint32_t job, uint32_t *input_offset, uint32_t
 /* ---- timing on the handle's CUDA stream (for benchmarks) ---- */
 int rsb_fir_timer_start(rsb_fir *h);
 int rsb_fir_timer_stop(rsb_fir *h, float *elapsed_ms); /* waits for the stop event */
+/* device time (ms, CUDA events on the handle's stream) of the convolution kernel of the most
+ * recent batches, newest first, at most 64; waits for the stream */
+int rsb_fir_conv_times(rsb_fir *h, float *ms, size_t max, size_t *n);
 /* kernels launched on this handle since creation (your own count for gpu_launches) */
 uint64_t rsb_fir_launch_count(const rsb_fir *h);
 /* the handle's cudaStream_t, as an opaque pointer */
@@ -167,6 +170,11 @@ int rsb_memcpy(int device, void *dst, const void *src, size_t bytes, int kind);
  * u = splitmix64 counter hash in [-1, 1).  Layout [stream][frame][channel]. */
 int rsb_fill_synthetic(int device, float *dst, uint32_t first_stream, uint32_t n_streams,
                        uint64_t frames, uint32_t channels, uint32_t rate_hz, uint64_t seed);
+
+/* device micro-benchmarks backing the kernel design (tools/microbench.py): id 0 scalar FFMA
+ * peak, id 1 packed FFMA2 peak, id >= 10 shared-memory banded-GEMM inner-loop candidates.
+ * result = TFLOP/s, aux = variant specific (resident CTAs per SM). */
+int rsb_microbench(int device, int id, int arg, double *result, double *aux);
 
 /* ---- host-only entry points (no GPU needed): filter design and the phase planner ---- */
 double rsb_host_bessel_i0(double x);                              /* window.rs:96-112 */

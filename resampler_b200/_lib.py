@@ -50,6 +50,7 @@ SIGNATURES = {
                                     szp]),
     "rsb_fir_timer_start": (C.c_int, [C.c_void_p]),
     "rsb_fir_timer_stop": (C.c_int, [C.c_void_p, f32p]),
+    "rsb_fir_conv_times": (C.c_int, [C.c_void_p, f32p, C.c_size_t, szp]),
     "rsb_fir_launch_count": (C.c_uint64, [C.c_void_p]),
     "rsb_fir_cuda_stream": (C.c_void_p, [C.c_void_p]),
     "rsb_alloc_pinned": (C.c_void_p, [C.c_size_t]),
@@ -59,6 +60,8 @@ SIGNATURES = {
     "rsb_memcpy": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
     "rsb_fill_synthetic": (C.c_int, [C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64,
                                      C.c_uint32, C.c_uint32, C.c_uint64]),
+    "rsb_microbench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double),
+                                 C.POINTER(C.c_double)]),
     "rsb_host_bessel_i0": (C.c_double, [C.c_double]),
     "rsb_host_cutoff_kaiser": (C.c_double, [C.c_uint32, C.c_double]),
     "rsb_host_kaiser_window": (None, [C.c_uint32, C.c_double, C.c_int, f32p]),

@@ -16,6 +16,10 @@
 #include <tuple>
 #include <vector>
 
+// planner.h templates are __host__ __device__; the host-only sink below is fine on the host
+#pragma nv_diag_suppress 20011
+#pragma nv_diag_suppress 20014
+
 #include "../../include/resampler_b200.h"
 #include "filter_design.h"
 #include "fir_kernels.h"
@@ -102,6 +106,10 @@ struct rsb_fir {
     uint64_t next_cohort = 1;
     uint64_t launches = 0;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_done = nullptr;
+    // ring of event pairs bracketing the convolution kernel of the most recent batches
+    static constexpr int kConvRing = 64;
+    cudaEvent_t ev_conv[kConvRing][2] = {};
+    uint64_t conv_batches = 0;
 
     // workspace of the (single) in-flight submit
     DevBuf d_units, d_jobs, d_members, d_segs, d_calls, d_tiles, d_counter, d_stage_in,
@@ -369,10 +377,14 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     P.groups = max_groups;
     P.streams_per_group = spg;
     const uint32_t max_items = (uint32_t)(tile_total * max_groups);
+    const int ring = (int)(h->conv_batches % rsb_fir::kConvRing);
+    RSB_CUDA(cudaEventRecord(h->ev_conv[ring][0], s));
     if (use_fast)
         rsb::launch_conv_fast(P, h->ratio, max_items, h->sm_count, s);
     else
         rsb::launch_conv_exact(P, max_items, h->sm_count, s);
+    RSB_CUDA(cudaEventRecord(h->ev_conv[ring][1], s));
+    h->conv_batches += 1;
     rsb::launch_update(h->d_units.as<UnitDev>(), h->d_jobs.as<JobDev>(), n, h->st, ch, s);
     h->launches += 4;
     RSB_CUDA(cudaGetLastError());
@@ -502,6 +514,10 @@ int rsb_fir_create(rsb_fir **out, int device, uint32_t n_streams, uint32_t chann
     RSB_CUDA(cudaEventCreate(&h->ev_t0));
     RSB_CUDA(cudaEventCreate(&h->ev_t1));
     RSB_CUDA(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+    for (int i = 0; i < rsb_fir::kConvRing; ++i) {
+        RSB_CUDA(cudaEventCreate(&h->ev_conv[i][0]));
+        RSB_CUDA(cudaEventCreate(&h->ev_conv[i][1]));
+    }
     const size_t tab_bytes = h->table->coeffs.size() * sizeof(float);
     RSB_CUDA(cudaMalloc(&h->d_coeffs, tab_bytes));
     RSB_CUDA(cudaMemcpyAsync(h->d_coeffs, h->table->coeffs.data(), tab_bytes,
@@ -540,6 +556,9 @@ void rsb_fir_destroy(rsb_fir *h) {
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);
     if (h->ev_t1) cudaEventDestroy(h->ev_t1);
     if (h->ev_done) cudaEventDestroy(h->ev_done);
+    for (int i = 0; i < rsb_fir::kConvRing; ++i)
+        for (int j = 0; j < 2; ++j)
+            if (h->ev_conv[i][j]) cudaEventDestroy(h->ev_conv[i][j]);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -752,6 +771,23 @@ int rsb_fir_timer_stop(rsb_fir *h, float *elapsed_ms) {
     float ms = 0.0f;
     RSB_CUDA(cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1));
     if (elapsed_ms) *elapsed_ms = ms;
+    return RSB_OK;
+}
+
+int rsb_fir_conv_times(rsb_fir *h, float *ms, size_t max, size_t *n) {
+    if (check_handle(h)) return RSB_ERR_INVALID_ARGUMENT;
+    RSB_CUDA(cudaSetDevice(h->device));
+    RSB_CUDA(cudaStreamSynchronize(h->stream));
+    const uint64_t have = std::min<uint64_t>(h->conv_batches, rsb_fir::kConvRing);
+    const size_t cnt = (size_t)std::min<uint64_t>(have, max);
+    if (n) *n = cnt;
+    for (size_t i = 0; i < cnt; ++i) {
+        // most recent first
+        const int slot = (int)((h->conv_batches - 1 - i) % rsb_fir::kConvRing);
+        float t = 0.f;
+        RSB_CUDA(cudaEventElapsedTime(&t, h->ev_conv[slot][0], h->ev_conv[slot][1]));
+        if (ms) ms[i] = t;
+    }
     return RSB_OK;
 }
 

@@ -313,6 +313,14 @@ class FirBatch:
         _check(self._lib.rsb_fir_timer_stop(self._h, C.byref(ms)))
         return ms.value
 
+    def conv_times_ms(self, max_n: int = 64) -> np.ndarray:
+        """Device time of the convolution kernel of the most recent batches, newest first."""
+        ms = np.zeros(max_n, np.float32)
+        n = C.c_size_t(0)
+        _check(self._lib.rsb_fir_conv_times(self._h, ms.ctypes.data_as(_lib.f32p), max_n,
+                                            C.byref(n)))
+        return ms[:n.value]
+
     def launch_count(self) -> int:
         return self._lib.rsb_fir_launch_count(self._h)
 

@@ -1,0 +1,286 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bar (BASELINE.json north_star): (consumed, produced) counts and phase indices bit-exact;
+samples bit-identical for the EXACT kernel (the reference's AVX-512 summation order) and
+within 1e-6 absolute for the FAST kernel.
+"""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from resampler_b200 import (Attenuation, FirBatch, Kernel, Latency, ResampleError, ResamplerFir,
+                            SampleRate)
+from resampler_b200.fir import FLAG_KEEP_PLAN, FLAG_RECORD_CALLS
+
+pytestmark = pytest.mark.gpu
+
+TOL_FAST = 1e-6   # absolute, north_star
+
+
+def noise(rng, n):
+    return rng.uniform(-1.0, 1.0, n).astype(np.float32)
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def oracle_stream(ch, in_hz, out_hz, lat, att, x, call_len, out_cap_len=0, trace=False):
+    f = O.OracleFir(ch, in_hz, out_hz, lat, att)
+    return f.process(x, call_len, out_cap_len=out_cap_len, trace=trace)
+
+
+# ---------------------------------------------------------------------------------------------
+# single-stream mirror of the reference API
+# ---------------------------------------------------------------------------------------------
+CONFIGS = [
+    # ch, in_hz, out_hz, latency, attenuation, call frames
+    (2, 48000, 44100, 3, 1, 512),    # BASELINE config 1
+    (2, 44100, 48000, 3, 1, 512),    # config 2 parameters
+    (1, 16000, 48000, 1, 1, 160),    # config 3 parameters
+    (8, 96000, 48000, 2, 1, 512),    # config 4 parameters
+    (1, 22050, 44100, 3, 1, 256),    # the reference's stop-band test rates
+    (3, 44100, 48000, 0, 0, 100),    # odd channel count, 16 taps, Db60
+    (2, 24000, 16000, 2, 2, 333),    # arbitrary rates (new_from_hz), Db120
+]
+
+
+@pytest.mark.parametrize("ch,in_hz,out_hz,lat,att,call", CONFIGS)
+def test_streaming_resample_bit_exact(ch, in_hz, out_hz, lat, att, call):
+    """The canonical caller loop over ResamplerFir.resample(): counts and samples bit-exact."""
+    rng = np.random.default_rng(ch * 1000 + call)
+    frames = call * 12 + 37
+    x = noise(rng, frames * ch)
+    ref = O.OracleFir(ch, in_hz, out_hz, lat, att)
+    dut = ResamplerFir.new_from_hz(ch, in_hz, out_hz, Latency(lat), Attenuation(att),
+                                   kernel=Kernel.EXACT)
+    assert dut.buffer_size_output() == ref.buffer_size_output()
+    assert dut.delay() == ref.delay()
+    out_ref = np.zeros(ref.buffer_size_output(), np.float32)
+    out_dut = np.zeros(dut.buffer_size_output(), np.float32)
+    off = 0
+    while off < len(x):
+        chunk = x[off:off + call * ch]
+        err, c, p = ref.resample(chunk, out_ref)
+        c2, p2 = dut.resample(chunk, out_dut)
+        assert err == 0 and (c2, p2) == (c, p)
+        assert np.array_equal(bits(out_dut[:p]), bits(out_ref[:p]))
+        off += c
+        if c == 0:
+            break
+    dut.close()
+
+
+def test_new_equals_new_from_hz_and_reset():
+    """src/resampler_fir.rs:817-839 plus reset() (:638-642)."""
+    a = ResamplerFir(1, SampleRate.Hz48000, SampleRate.Hz44100, Latency.Sample64, Attenuation.Db90,
+                     kernel=Kernel.EXACT)
+    b = ResamplerFir.new_from_hz(1, 48000, 44100, Latency.Sample64, Attenuation.Db90,
+                                 kernel=Kernel.EXACT)
+    x = np.full(512, 0.5, np.float32)
+    oa = np.zeros(a.buffer_size_output(), np.float32)
+    ob = np.zeros(b.buffer_size_output(), np.float32)
+    ra, rb = a.resample(x, oa), b.resample(x, ob)
+    assert ra == rb and np.array_equal(bits(oa[:ra[1]]), bits(ob[:rb[1]]))
+    ref = O.OracleFir(1, 48000, 44100, 3, 1)
+    oref = np.zeros(ref.buffer_size_output(), np.float32)
+    _, c, p = ref.resample(x, oref)
+    assert ra == (c, p) and np.array_equal(bits(oa[:p]), bits(oref[:p]))
+    # reset: the next call behaves like the first one
+    a.reset()
+    oa2 = np.zeros_like(oa)
+    assert a.resample(x, oa2) == ra and np.array_equal(bits(oa2[:ra[1]]), bits(oa[:ra[1]]))
+    a.close()
+    b.close()
+
+
+def test_arbitrary_rates_and_errors():
+    """src/resampler_fir.rs:841-862 and the error precedence of :514-519."""
+    r = ResamplerFir.new_from_hz(1, 24000, 16000, Latency.Sample32, Attenuation.Db60)
+    out = np.zeros(r.buffer_size_output(), np.float32)
+    r.resample(np.zeros(256, np.float32), out)
+    r.close()
+    with pytest.raises(ValueError, match="input sample rate must be greater than zero"):
+        ResamplerFir.new_from_hz(1, 0, 44100)
+    with pytest.raises(ValueError, match="output sample rate must be greater than zero"):
+        ResamplerFir.new_from_hz(1, 44100, 0)
+    s = ResamplerFir.new_from_hz(2, 48000, 44100)
+    with pytest.raises(ResampleError) as e:
+        s.resample(np.zeros(3, np.float32), np.zeros(3, np.float32))
+    assert e.value.kind == ResampleError.InvalidInputBufferSize
+    with pytest.raises(ResampleError) as e:
+        s.resample(np.zeros(4, np.float32), np.zeros(3, np.float32))
+    assert e.value.kind == ResampleError.InvalidOutputBufferSize
+    # a failed call must not have touched the state
+    ref = O.OracleFir(2, 48000, 44100, 3, 2)
+    x = noise(np.random.default_rng(3), 1024)
+    o1 = np.zeros(s.buffer_size_output(), np.float32)
+    o2 = np.zeros(ref.buffer_size_output(), np.float32)
+    c, p = s.resample(x, o1)
+    _, c2, p2 = ref.resample(x, o2)
+    assert (c, p) == (c2, p2) and np.array_equal(bits(o1[:p]), bits(o2[:p]))
+    s.close()
+
+
+def test_edge_cases_empty_small_capacity_and_lookahead():
+    """Empty input, output capacity smaller than what is available (:553, :528), a full
+    4096-frame buffer, ratio > taps (the 0.5.1 fix, :593-596)."""
+    rng = np.random.default_rng(11)
+    for (in_hz, out_hz, lat, calls) in [
+            (44100, 48000, 3, [(0, 8642), (512, 100), (512, 100), (0, 100), (4096, 50), (4096, 0),
+                               (9000, 8642), (1, 1), (0, 8642), (4096, 8642), (4096, 8642)]),
+            (384000, 1000, 0, [(512, 100)] * 8 + [(0, 5), (4096, 3)]),
+            (8000, 192000, 3, [(300, 1000), (300, 98306), (10, 98306), (0, 98306)])]:
+        ref = O.OracleFir(1, in_hz, out_hz, lat, 1)
+        dut = ResamplerFir.new_from_hz(1, in_hz, out_hz, Latency(lat), Attenuation.Db90,
+                                       kernel=Kernel.EXACT)
+        for n_in, cap in calls:
+            x = noise(rng, n_in)
+            o_ref = np.zeros(cap, np.float32)
+            o_dut = np.zeros(cap, np.float32)
+            _, c, p = ref.resample(x, o_ref)
+            assert dut.resample(x, o_dut) == (c, p), (n_in, cap)
+            assert np.array_equal(bits(o_dut[:p]), bits(o_ref[:p]))
+        dut.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# batched submit: n independent resample() calls
+# ---------------------------------------------------------------------------------------------
+def test_submit_batch_divergent_streams_bit_exact():
+    """BASELINE config 3 (ii): mono 16->48 kHz, 32 taps, every stream with its own pseudo-random
+    call sizes => divergent state; counts, phases and samples bit-exact per stream."""
+    n = 24
+    rng = np.random.default_rng(5)
+    sizes = [1, 7, 16, 33, 160, 480]
+    batch = FirBatch(n, 1, 16000, 48000, Latency.Sample16, Attenuation.Db90, kernel=Kernel.EXACT)
+    refs = [O.OracleFir(1, 16000, 48000, 1, 1) for _ in range(n)]
+    bso = batch.buffer_size_output()
+    for it in range(14):
+        ins = [noise(rng, int(rng.choice(sizes))) for _ in range(n)]
+        outs = [np.zeros(bso, np.float32) for _ in range(n)]
+        cons, prod = batch.submit(ins, outs, flags=FLAG_KEEP_PLAN)
+        for s in range(n):
+            o = np.zeros(bso, np.float32)
+            _, c, p, tr = refs[s].resample(ins[s], o, trace=True)
+            assert (cons[s], prod[s]) == (c, p), (it, s)
+            assert np.array_equal(bits(outs[s][:p]), bits(o[:p])), (it, s)
+            if s % 5 == 0:
+                plan = batch.last_plan(s)
+                for key in ("input_offset", "phase1", "phase2", "frac_bits"):
+                    assert np.array_equal(plan[key], tr[key]), (key, it, s)
+    batch.close()
+
+
+def test_submit_batch_subset_of_streams_and_mixed_capacities():
+    n = 6
+    rng = np.random.default_rng(8)
+    batch = FirBatch(n, 2, 44100, 48000, Latency.Sample64, Attenuation.Db90, kernel=Kernel.EXACT)
+    refs = [O.OracleFir(2, 44100, 48000, 3, 1) for _ in range(n)]
+    for it in range(6):
+        streams = [int(s) for s in rng.permutation(n)[:4]]
+        ins = [noise(rng, 2 * int(rng.integers(0, 900))) for _ in streams]
+        caps = [2 * int(rng.choice([0, 10, 700, 4321])) for _ in streams]
+        outs = [np.zeros(c, np.float32) for c in caps]
+        cons, prod = batch.submit(ins, outs, streams=streams)
+        for j, s in enumerate(streams):
+            o = np.zeros(caps[j], np.float32)
+            _, c, p = refs[s].resample(ins[j], o)
+            assert (cons[j], prod[j]) == (c, p)
+            assert np.array_equal(bits(outs[j][:p]), bits(o[:p]))
+    with pytest.raises(ValueError):
+        batch.submit([np.zeros(2, np.float32)] * 2, [np.zeros(2, np.float32)] * 2, streams=[1, 1])
+    batch.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# batched multi-call: the canonical caller loop per stream in one launch
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ch,in_hz,out_hz,lat,call_frames,cap_frames,n_streams", [
+    (2, 44100, 48000, 3, 512, 0, 5),      # config 2 pattern
+    (2, 48000, 44100, 3, 512, 0, 3),      # config 1 pattern
+    (1, 16000, 48000, 1, 160, 0, 7),      # config 3 (i)
+    (8, 96000, 48000, 2, 512, 0, 3),      # config 4
+    (2, 44100, 48000, 3, 512, 100, 2),    # capacity-limited calls
+    (1, 384000, 1000, 0, 512, 0, 2),      # ratio > taps
+    (2, 44100, 48000, 3, 4096, 0, 2),     # maximum call size
+])
+def test_process_batch_bit_exact(ch, in_hz, out_hz, lat, call_frames, cap_frames, n_streams):
+    rng = np.random.default_rng(in_hz + call_frames)
+    frames = min(in_hz // 3, 20000) + 13
+    xs = [noise(rng, frames * ch) for _ in range(n_streams)]
+    batch = FirBatch(n_streams, ch, in_hz, out_hz, Latency(lat), Attenuation.Db90,
+                     kernel=Kernel.EXACT)
+    res = batch.process(xs, call_frames * ch, cap_frames * ch,
+                        flags=FLAG_RECORD_CALLS | FLAG_KEEP_PLAN)
+    for s in range(n_streams):
+        ref = oracle_stream(ch, in_hz, out_hz, lat, 1, xs[s], call_frames * ch, cap_frames * ch,
+                            trace=(s == 0))
+        assert res["consumed"][s] == ref["consumed_total"]
+        assert res["produced"][s] == len(ref["out"])
+        assert res["calls"][s] == ref["calls"]
+        assert np.array_equal(bits(res["out"][s]), bits(ref["out"])), s
+        if s == 0:
+            cc, cp = batch.last_call_counts(0)
+            assert np.array_equal(cc, ref["consumed"]) and np.array_equal(cp, ref["produced"])
+            plan = batch.last_plan(0)
+            for key in ("input_offset", "phase1", "phase2", "frac_bits"):
+                assert np.array_equal(plan[key], ref["trace"][key]), key
+    # a second batch continues from the carried state (history + phase), like more calls
+    xs2 = [noise(rng, 777 * ch) for _ in range(n_streams)]
+    res2 = batch.process(xs2, call_frames * ch, cap_frames * ch)
+    for s in range(n_streams):
+        f = O.OracleFir(ch, in_hz, out_hz, lat, 1)
+        f.process(xs[s], call_frames * ch, out_cap_len=cap_frames * ch)
+        ref2 = f.process(xs2[s], call_frames * ch, out_cap_len=cap_frames * ch)
+        assert res2["produced"][s] == len(ref2["out"])
+        assert np.array_equal(bits(res2["out"][s]), bits(ref2["out"])), s
+    batch.close()
+
+
+def test_process_batch_ragged_lengths_and_empty():
+    """Streams of different lengths (incl. empty) in one batch => several plan units."""
+    ch, n = 2, 6
+    rng = np.random.default_rng(21)
+    lens = [0, 1, 127, 128, 5000, 12345]
+    xs = [noise(rng, L * ch) for L in lens]
+    batch = FirBatch(n, ch, 44100, 48000, Latency.Sample64, Attenuation.Db90, kernel=Kernel.EXACT)
+    res = batch.process(xs, 512 * ch)
+    for s in range(n):
+        ref = oracle_stream(ch, 44100, 48000, 3, 1, xs[s], 512 * ch)
+        assert res["consumed"][s] == ref["consumed_total"] and res["calls"][s] == ref["calls"]
+        assert np.array_equal(bits(res["out"][s]), bits(ref["out"]))
+    batch.close()
+
+
+def test_process_batch_output_capacity_error():
+    batch = FirBatch(1, 1, 44100, 48000, Latency.Sample64, Attenuation.Db90, kernel=Kernel.EXACT)
+    x = np.zeros(5000, np.float32)
+    with pytest.raises(RuntimeError, match="too small"):
+        batch.process([x], 512, out_capacity=100)
+    batch.close()
+
+
+def test_stopband_attenuation_on_gpu():
+    """src/resampler_fir.rs:741-815 replayed through the CUDA path (numpy FFT for analysis)."""
+    for in_hz, out_hz in [(22050, 44100), (22050, 48000)]:
+        n = int(np.float32(in_hz) * np.float32(5.0))
+        x = np.zeros(n, np.float32)
+        x[n // 2] = 1.0
+        b = FirBatch(1, 1, in_hz, out_hz, Latency.Sample64, Attenuation.Db90)
+        y = b.process([x], 256)["out"][0]
+        b.close()
+        peak = int(np.argmax(np.abs(y)))
+        win = int(out_hz * 0.1)
+        start = max(peak - win // 2, 0)
+        ir = y[start:min(start + win, len(y))]
+        buf = np.zeros(8192)
+        m = min(len(ir), 8192)
+        buf[:m] = ir[:m]
+        mag = np.abs(np.fft.rfft(buf))
+        db = np.where(mag > 1e-10, 20 * np.log10(np.maximum(mag, 1e-300)), -200.0)
+        tb = lambda f: int(round(f / out_hz * 8192))  # noqa: E731
+        nyq = in_hz / 2
+        pb = db[tb(20.0):tb(nyq * 0.9) + 1].max()
+        sb = db[tb(nyq * 1.1):min(len(db) - 10, tb(out_hz / 2 * 0.95)) + 1].max()
+        assert pb - sb >= 90.0
