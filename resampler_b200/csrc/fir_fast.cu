@@ -63,6 +63,42 @@ __device__ __forceinline__ void ffma2(float2 &d, const float2 a, const float2 b)
         : "l"(reinterpret_cast<const uint64_t &>(a)), "l"(reinterpret_cast<const uint64_t &>(b)));
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA bulk copy global -> shared (SASS: UBLKCP), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 __device__ __forceinline__ void locate_output(const PlanSeg *segs, uint32_t s, uint32_t o,
                                               PhasePoint &pp, int64_t &v) {
     PlanSeg sg = segs[s];
@@ -72,7 +108,29 @@ __device__ __forceinline__ void locate_output(const PlanSeg *segs, uint32_t s, u
     v = sg.vbase + (int64_t)pp.off;
 }
 
-template <int TAPS>
+// Element-wise staging of one float4 `sub` of the 4-frame group starting at virtual frame vg
+// (edges of the window, the seam, and channel counts without a specialised path).
+__device__ __forceinline__ void stage_slow(float *X, uint32_t xs, uint32_t col0, uint32_t ch,
+                                           uint32_t grp, uint32_t sub, int64_t vg, int64_t H,
+                                           int64_t n_valid, const float *hist, const float *in) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const uint32_t idx = sub * 4 + e;          // value inside the group
+        const uint32_t f = idx / ch, c = idx - f * ch;
+        const int64_t vv = vg + f;
+        float xv = 0.f;
+        if (vv >= 0 && vv < n_valid)
+            xv = vv < H ? hist[((int64_t)kHistFrames - H + vv) * ch + c] : in[(vv - H) * ch + c];
+        X[(col0 + c) * xs + 4 * grp + f] = xv;
+    }
+}
+
+// Largest number of float4 one lane holds while a member's window is de-interleaved in place.
+__host__ __device__ constexpr int max_vec_per_lane(int ch) { return ch <= 2 ? 4 : (ch == 4 ? 8 : 12); }
+
+// CH = 1, 2, 4, 8: the member windows arrive by TMA bulk copies (cp.async.bulk, raw interleaved
+// frames) and are de-interleaved in place; CH = 0: any channel count, register-staged loads.
+template <int TAPS, int CH>
 __global__ void __launch_bounds__(kThreads) conv_fast_kernel(ConvParams P, FastGeom geo) {
     extern __shared__ float4 smem_f4[];
     float *G = reinterpret_cast<float *>(smem_f4);      // [kKT][xs]
@@ -86,12 +144,19 @@ __global__ void __launch_bounds__(kThreads) conv_fast_kernel(ConvParams P, FastG
     __shared__ const float *s_hist[kNC];
     __shared__ float *s_out[kNC];
     __shared__ uint64_t s_cap[kNC];
+    __shared__ __align__(8) uint64_t s_bar;
 
-    const uint32_t ch = P.channels;
+    const uint32_t ch = CH ? (uint32_t)CH : P.channels;
     const uint32_t xs = geo.xs;
     const uint32_t n_items = *P.tile_total * P.groups;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t spg = P.streams_per_group;            // members per tile = kNC / ch
+    uint32_t bar_parity = 0;
+
+    if (CH != 0 && tid == 0) {
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
 
     for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x) {
         const uint32_t t = w / P.groups, g = w - t * P.groups;
@@ -105,7 +170,7 @@ __global__ void __launch_bounds__(kThreads) conv_fast_kernel(ConvParams P, FastG
         const int64_t H = (int64_t)U.hist_len0;
         const int64_t n_valid = H + (int64_t)U.total_frames;    // virtual frames that exist
 
-        __syncthreads();   // previous tile fully consumed
+        __syncthreads();   // previous tile fully consumed (also orders the mbarrier init)
         if (tid < n_out) {
             PhasePoint pp;
             int64_t v;
@@ -129,65 +194,172 @@ __global__ void __launch_bounds__(kThreads) conv_fast_kernel(ConvParams P, FastG
         const int64_t v_base = v_first - (((v_first - H) % 4 + 4) % 4);
         const int win = (int)(s_v[n_out - 1] - v_base) + TAPS;
         const int winp = (win + 3) & ~3;
+        const int n_grp = winp >> 2;
         if (tid < n_out) s_d[tid] = (int)(s_v[tid] - v_base);
+        // 4-frame groups [g_lo, g_hi) exist completely; [g_lo, g_seam) history, rest new input
+        const int g_lo = v_base < 0 ? 1 : 0;
+        int g_hi = (int)min((int64_t)n_grp, (n_valid - v_base) >> 2);
+        if (g_hi < g_lo) g_hi = g_lo;
+        const int g_seam = (int)max((int64_t)g_lo, min((int64_t)g_hi, (H - v_base) >> 2));
 
-        // ---- zero G ----
-        for (uint32_t i = tid; i < (uint32_t)kKT * (winp >> 2); i += kThreads) {
-            const uint32_t k = i / (winp >> 2), q = i - k * (winp >> 2);
+        if (CH != 0) {
+            // ---- TMA: one or two bulk copies per member, raw interleaved frames ----
+            const uint32_t bytes_hist = (uint32_t)(g_seam - g_lo) * 16u * ch;
+            const uint32_t bytes_in = (uint32_t)(g_hi - g_seam) * 16u * ch;
+            if (tid == 0) {
+                fence_proxy_async();   // generic-proxy accesses to X of the last tile are done
+                mbar_arrive_expect_tx(&s_bar, nm * (bytes_hist + bytes_in));
+            }
+            __syncthreads();
+            if (tid < nm) {
+                float *dst = X + (size_t)tid * ch * xs;
+                if (bytes_hist)
+                    bulk_g2s(dst + 4 * g_lo * ch,
+                             s_hist[tid] + ((int64_t)kHistFrames - H + v_base + 4 * g_lo) * ch,
+                             bytes_hist, &s_bar);
+                if (bytes_in)
+                    bulk_g2s(dst + 4 * g_seam * ch, s_in[tid] + (v_base + 4 * g_seam - H) * ch,
+                             bytes_in, &s_bar);
+            }
+        }
+
+        // ---- zero G, idle columns ----
+        for (uint32_t i = tid; i < (uint32_t)kKT * n_grp; i += kThreads) {
+            const uint32_t k = i / n_grp, q = i - k * n_grp;
             reinterpret_cast<float4 *>(G + k * xs)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        // ---- stage X: de-interleave [frame][ch] -> planar [col][j] ----
+        for (uint32_t i = tid; i < (kNC - n_cols) * (uint32_t)n_grp; i += kThreads) {
+            const uint32_t c = n_cols + i / n_grp, q = i % n_grp;
+            reinterpret_cast<float4 *>(X + c * xs)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();
+        // ---- build the banded rows (4 taps per item, loads batched); overlaps the TMA ----
         {
-            const uint32_t vps = (uint32_t)(winp >> 2) * ch;   // float4 per member
-            for (uint32_t i = tid; i < nm * vps; i += kThreads) {
-                const uint32_t m = i / vps, q = i - m * vps;
-                const float *hist = s_hist[m];
-                const float *in = s_in[m];
-                // float4 q covers interleaved values [4q, 4q+4) of the member's window
-                const uint32_t grp = q / ch, sub = q - grp * ch;   // 4-frame group, float4 in it
-                const int64_t vg = v_base + 4 * (int64_t)grp;
-                float e4[4];
-                if (vg >= 0 && vg + 4 <= n_valid) {
-                    const float *src = vg < H ? hist + ((int64_t)kHistFrames - H + vg) * ch
-                                              : in + (vg - H) * ch;
-                    const float4 val = reinterpret_cast<const float4 *>(src)[sub];
-                    e4[0] = val.x; e4[1] = val.y; e4[2] = val.z; e4[3] = val.w;
-                } else {
+            constexpr uint32_t kQ = TAPS / 4;
+            constexpr int kBatch = 4;
+            const uint32_t items = n_out * kQ;
+            for (uint32_t i0 = 0; i0 < items; i0 += kThreads * kBatch) {
+                float4 a[kBatch], b[kBatch];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const uint32_t idx = sub * 4 + e;          // value inside the group
-                        const int64_t vv = vg + idx / ch;
-                        const uint32_t c = idx % ch;
-                        float xv = 0.f;
-                        if (vv >= 0 && vv < n_valid)
-                            xv = vv < H ? hist[((int64_t)kHistFrames - H + vv) * ch + c]
-                                        : in[(vv - H) * ch + c];
-                        e4[e] = xv;
+                for (int u = 0; u < kBatch; ++u) {
+                    const uint32_t i = i0 + u * kThreads + tid;
+                    if (i < items) {
+                        const uint32_t k = i / kQ, t4 = i - k * kQ;
+                        const uint32_t p1 = s_p1[k];
+                        const uint32_t p2 = p1 + 1 < kPhases - 1 ? p1 + 1 : kPhases - 1;
+                        a[u] = __ldg(reinterpret_cast<const float4 *>(P.coeffs + (size_t)p1 * TAPS) + t4);
+                        b[u] = __ldg(reinterpret_cast<const float4 *>(P.coeffs + (size_t)p2 * TAPS) + t4);
                     }
                 }
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const uint32_t idx = sub * 4 + e;
-                    const uint32_t f = idx / ch, c = idx - f * ch;
-                    X[(m * ch + c) * xs + 4 * grp + f] = e4[e];
+                for (int u = 0; u < kBatch; ++u) {
+                    const uint32_t i = i0 + u * kThreads + tid;
+                    if (i < items) {
+                        const uint32_t k = i / kQ, t4 = i - k * kQ;
+                        const float fr = s_frac[k];
+                        const float omf = __fsub_rn(1.0f, fr);
+                        float *dst = G + k * xs + s_d[k] + 4 * t4;
+                        dst[0] = __fmaf_rn(b[u].x, fr, __fmul_rn(a[u].x, omf));
+                        dst[1] = __fmaf_rn(b[u].y, fr, __fmul_rn(a[u].y, omf));
+                        dst[2] = __fmaf_rn(b[u].z, fr, __fmul_rn(a[u].z, omf));
+                        dst[3] = __fmaf_rn(b[u].w, fr, __fmul_rn(a[u].w, omf));
+                    }
                 }
             }
-            // idle columns of a partial group read as zero
-            for (uint32_t i = tid; i < (kNC - n_cols) * (uint32_t)(winp >> 2); i += kThreads) {
-                const uint32_t c = n_cols + i / (winp >> 2), q = i % (winp >> 2);
-                reinterpret_cast<float4 *>(X + c * xs)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
         }
-        __syncthreads();
-        // ---- build the banded rows ----
-        for (uint32_t i = tid; i < n_out * TAPS; i += kThreads) {
-            const uint32_t k = i / TAPS, tap = i - k * TAPS;
-            const uint32_t p1 = s_p1[k];
-            const uint32_t p2 = p1 + 1 < kPhases - 1 ? p1 + 1 : kPhases - 1;
-            const float fr = s_frac[k];
-            const float a = __ldg(P.coeffs + (size_t)p1 * TAPS + tap);
-            const float b = __ldg(P.coeffs + (size_t)p2 * TAPS + tap);
-            G[k * xs + s_d[k] + tap] = __fmaf_rn(b, fr, __fmul_rn(a, __fsub_rn(1.0f, fr)));
+
+        // ---- stage X: de-interleave [frame][ch] -> planar [col][j] ----
+        if (CH != 0) {
+            mbar_wait(&s_bar, bar_parity);
+            bar_parity ^= 1u;
+            if (CH > 1) {
+                // in place, one warp per member: read the whole raw window, then write planar
+                const uint32_t vps = (uint32_t)n_grp * CH;   // float4 per member
+                for (uint32_t m = warp; m < nm; m += kThreads / 32) {
+                    float *blk = X + (size_t)m * CH * xs;
+                    constexpr int kMaxB = max_vec_per_lane(CH);
+                    constexpr uint32_t kCq = CH >= 4 ? CH / 4 : 1;   // float4 per frame
+                    float4 buf[kMaxB];
+#pragma unroll
+                    for (int b = 0; b < kMaxB; ++b) {
+                        const uint32_t q = 32 * b + lane;
+                        if (q < vps) buf[b] = reinterpret_cast<const float4 *>(blk)[q];
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int b = 0; b < kMaxB; ++b) {
+                        const uint32_t q = 32 * b + lane;
+                        if (q < vps) {
+                            if (CH == 2) {
+                                // (L0 R0 L1 R1) -> row 0: (L0, L1), row 1: (R0, R1)
+                                reinterpret_cast<float2 *>(blk)[q] = make_float2(buf[b].x, buf[b].z);
+                                reinterpret_cast<float2 *>(blk + xs)[q] =
+                                    make_float2(buf[b].y, buf[b].w);
+                            } else {
+                                // float4 q = channels 4*(q % (CH/4)).. of frame q / (CH/4)
+                                const uint32_t f = q / kCq, c0 = (q % kCq) * 4;
+                                blk[(c0 + 0) * xs + f] = buf[b].x;
+                                blk[(c0 + 1) * xs + f] = buf[b].y;
+                                blk[(c0 + 2) * xs + f] = buf[b].z;
+                                blk[(c0 + 3) * xs + f] = buf[b].w;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            // groups that are not completely inside the stream (window edges): element-wise
+            const uint32_t n_edge = (uint32_t)(g_lo + (n_grp - g_hi));
+            if (n_edge) {
+                __syncthreads();
+                for (uint32_t i = tid; i < nm * n_edge * ch; i += kThreads) {
+                    const uint32_t m = i / (n_edge * ch), r = i - m * (n_edge * ch);
+                    const uint32_t ge = r / ch, sub = r - ge * ch;
+                    const uint32_t grp = ge < (uint32_t)g_lo ? ge : (uint32_t)g_hi + (ge - g_lo);
+                    stage_slow(X, xs, m * ch, ch, grp, sub, v_base + 4 * (int64_t)grp, H, n_valid,
+                               s_hist[m], s_in[m]);
+                }
+            }
+        } else {
+            // any channel count: one warp per member, float4 loads batched before the stores
+            const uint32_t vps = (uint32_t)n_grp * ch;
+            constexpr int kBatch = 4;
+            for (uint32_t m = warp; m < nm; m += kThreads / 32) {
+                const float *hist = s_hist[m];
+                const float *in = s_in[m];
+                const float *hsrc = hist + ((int64_t)kHistFrames - H + v_base) * ch;
+                const float *isrc = in + (v_base - H) * (int64_t)ch;
+                for (uint32_t q0 = 0; q0 < vps; q0 += 32 * kBatch) {
+                    float4 buf[kBatch];
+                    bool fastp[kBatch];
+#pragma unroll
+                    for (int b = 0; b < kBatch; ++b) {
+                        const uint32_t q = q0 + 32 * b + lane;
+                        const int grp = (int)(q / ch);
+                        fastp[b] = q < vps && grp >= g_lo && grp < g_hi;
+                        if (fastp[b])
+                            buf[b] = reinterpret_cast<const float4 *>(grp < g_seam ? hsrc : isrc)[q];
+                    }
+#pragma unroll
+                    for (int b = 0; b < kBatch; ++b) {
+                        const uint32_t q = q0 + 32 * b + lane;
+                        if (q >= vps) continue;
+                        if (!fastp[b]) {
+                            const uint32_t grp = q / ch, sub = q - grp * ch;
+                            stage_slow(X, xs, m * ch, ch, grp, sub, v_base + 4 * (int64_t)grp, H,
+                                       n_valid, hist, in);
+                        } else {
+                            const float e4[4] = {buf[b].x, buf[b].y, buf[b].z, buf[b].w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const uint32_t idx = 4 * q + e;
+                                const uint32_t f = idx / ch, c = idx - f * ch;
+                                X[(m * ch + c) * xs + f] = e4[e];
+                            }
+                        }
+                    }
+                }
+            }
         }
         __syncthreads();
 
@@ -276,12 +448,23 @@ void launch_conv_fast(const ConvParams &p, double ratio, uint32_t max_items, int
         if (grid > max_items) grid = max_items;
         kern<<<grid, kThreads, smem, stream>>>(p, geo);
     };
+#define RSB_FAST_DISPATCH(T)                                             \
+    do {                                                                 \
+        const bool tma_ok = (geo.win_max / 4) * p.channels <=            \
+                            32u * (uint32_t)max_vec_per_lane((int)p.channels); \
+        if (p.channels == 1) launch(conv_fast_kernel<T, 1>);             \
+        else if (p.channels == 2 && tma_ok) launch(conv_fast_kernel<T, 2>); \
+        else if (p.channels == 4 && tma_ok) launch(conv_fast_kernel<T, 4>); \
+        else if (p.channels == 8 && tma_ok) launch(conv_fast_kernel<T, 8>); \
+        else launch(conv_fast_kernel<T, 0>);                             \
+    } while (0)
     switch (p.taps) {
-        case 16: launch(conv_fast_kernel<16>); break;
-        case 32: launch(conv_fast_kernel<32>); break;
-        case 64: launch(conv_fast_kernel<64>); break;
-        default: launch(conv_fast_kernel<128>); break;
+        case 16: RSB_FAST_DISPATCH(16); break;
+        case 32: RSB_FAST_DISPATCH(32); break;
+        case 64: RSB_FAST_DISPATCH(64); break;
+        default: RSB_FAST_DISPATCH(128); break;
     }
+#undef RSB_FAST_DISPATCH
 }
 
 }  // namespace rsb
