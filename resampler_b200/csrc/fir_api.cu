@@ -103,6 +103,7 @@ struct rsb_fir {
     float *d_coeffs = nullptr;
     rsb::StreamStateDev st{};
     std::vector<uint64_t> cohort;   // host-side plan cohort of each stream (0 = fresh state)
+    std::vector<uint8_t> hist_sel;  // which history buffer of a stream is live (host mirror)
     uint64_t next_cohort = 1;
     uint64_t launches = 0;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_done = nullptr;
@@ -112,9 +113,9 @@ struct rsb_fir {
     uint64_t conv_batches = 0;
 
     // workspace of the (single) in-flight submit
-    DevBuf d_units, d_jobs, d_members, d_segs, d_calls, d_tiles, d_counter, d_stage_in,
+    DevBuf d_units, d_jobs, d_segs, d_calls, d_tiles, d_entries, d_counter, d_stage_in,
         d_stage_out, d_dbg;
-    PinBuf h_units, h_jobs, h_members, h_units_back, h_calls_back;
+    PinBuf h_units, h_jobs, h_units_back, h_calls_back;
     std::vector<uint32_t> job_unit;          // unit of each job of the last batch
     std::vector<uint64_t> job_out_capacity;  // frames
     uint32_t last_n_units = 0;
@@ -236,8 +237,7 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
                 break;
             }
     }
-    const uint32_t tile_out = use_fast ? rsb::fast_tile_out(ch, h->taps, h->ratio)
-                                       : rsb::kExactTileOut;
+    const uint32_t tile_out = rsb::kTileOut;
     const uint32_t spg = use_fast ? rsb::fast_streams_per_group(ch, h->taps, h->ratio)
                                   : rsb::kExactStreamsPerGroup;
 
@@ -247,7 +247,6 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     RSB_CUDA(h->h_units.reserve(sizeof(UnitDev) * n_units));
     RSB_CUDA(h->h_units_back.reserve(sizeof(UnitDev) * n_units));
     RSB_CUDA(h->h_jobs.reserve(sizeof(JobDev) * n));
-    RSB_CUDA(h->h_members.reserve(sizeof(uint32_t) * n));
     UnitDev *hu = h->h_units.as<UnitDev>();
     uint64_t seg_total = 0, call_total = 0, tile_total = 0, max_tiles_unit = 0;
     uint32_t member_off = 0, max_groups = 1;
@@ -261,8 +260,8 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
         U.single_call = k.single;
         const double out_bound_d =
             std::ceil(((double)rsb::kInputCapacity + (double)k.total_frames) / h->ratio) + 2.0;
-        if (out_bound_d > 4.0e9)
-            return fail(RSB_ERR_INVALID_ARGUMENT, "more than 4e9 output frames in one batch");
+        if (out_bound_d > 4.0e9 || k.total_frames > 0x7ff00000ull)
+            return fail(RSB_ERR_INVALID_ARGUMENT, "too many frames per stream in one batch; split it");
         const uint64_t out_bound = (uint64_t)out_bound_d;
         uint64_t max_calls = 1;
         if (!k.single) {
@@ -289,7 +288,7 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
             call_total += U.max_calls;
         }
         const uint64_t tiles = (out_bound + tile_out - 1) / tile_out;
-        if (tiles > 65535ull * 128ull)
+        if (tiles > 65535ull * 4ull)
             return fail(RSB_ERR_INVALID_ARGUMENT, "too many output frames per stream in one batch");
         U.tile_cap = (uint32_t)tiles;
         tile_total += tiles;
@@ -324,8 +323,9 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
         RSB_CUDA(h->d_stage_out.reserve(out_total * sizeof(float) + 16));
     }
 
+    // jobs are stored grouped by unit: members of U are hj[U.member_off .. +U.n_members)
     JobDev *hj = h->h_jobs.as<JobDev>();
-    uint32_t *hm = h->h_members.as<uint32_t>();
+    const size_t hist_stride = (size_t)rsb::kHistFrames * ch;
     for (uint32_t i = 0; i < n; ++i) {
         JobDev J;
         J.stream = jobs[i].stream;
@@ -338,18 +338,20 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
             J.in = jobs[i].in;
             J.out = jobs[i].out;
         }
-        hj[i] = J;
+        const uint32_t sel = h->hist_sel[J.stream];
+        J.hist = h->st.hist[sel] + hist_stride * J.stream;
+        J.hist_next = h->st.hist[sel ^ 1u] + hist_stride * J.stream;
         UnitDev &U = hu[J.unit];
-        hm[U.member_off + U.n_members] = i;
+        hj[U.member_off + U.n_members] = J;
         if (U.n_members == 0) U.rep_stream = J.stream;
         U.n_members += 1;
     }
 
     RSB_CUDA(h->d_units.reserve(sizeof(UnitDev) * n_units));
     RSB_CUDA(h->d_jobs.reserve(sizeof(JobDev) * n));
-    RSB_CUDA(h->d_members.reserve(sizeof(uint32_t) * n));
     RSB_CUDA(h->d_segs.reserve(sizeof(rsb::PlanSeg) * seg_total));
     RSB_CUDA(h->d_tiles.reserve(sizeof(rsb::TileRec) * tile_total));
+    RSB_CUDA(h->d_entries.reserve(sizeof(rsb::PlanEntry) * rsb::kTileOut * tile_total));
     RSB_CUDA(h->d_counter.reserve(sizeof(uint32_t) * 4));
     if (rec_calls) {
         RSB_CUDA(h->d_calls.reserve(sizeof(rsb::CallCounts) * std::max<uint64_t>(call_total, 1)));
@@ -359,7 +361,6 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     cudaStream_t s = h->stream;
     RSB_CUDA(cudaMemcpyAsync(h->d_units.p, hu, sizeof(UnitDev) * n_units, cudaMemcpyHostToDevice, s));
     RSB_CUDA(cudaMemcpyAsync(h->d_jobs.p, hj, sizeof(JobDev) * n, cudaMemcpyHostToDevice, s));
-    RSB_CUDA(cudaMemcpyAsync(h->d_members.p, hm, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s));
     RSB_CUDA(cudaMemsetAsync(h->d_counter.p, 0, sizeof(uint32_t) * 4, s));
     if (host_mem) {
         for (uint32_t i = 0; i < n; ++i)
@@ -373,13 +374,14 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
                      h->d_segs.as<rsb::PlanSeg>(), h->d_calls.as<rsb::CallCounts>(), tile_out,
                      h->d_counter.as<uint32_t>(), s);
     rsb::launch_tiles(h->d_units.as<UnitDev>(), n_units, h->d_segs.as<rsb::PlanSeg>(),
-                      h->d_tiles.as<rsb::TileRec>(), tile_out, (uint32_t)max_tiles_unit, s);
+                      h->d_tiles.as<rsb::TileRec>(), h->d_entries.as<rsb::PlanEntry>(),
+                      (uint32_t)max_tiles_unit, s);
     rsb::ConvParams P;
     P.units = h->d_units.as<UnitDev>();
     P.jobs = h->d_jobs.as<JobDev>();
-    P.members = h->d_members.as<uint32_t>();
     P.segs = h->d_segs.as<rsb::PlanSeg>();
     P.tiles = h->d_tiles.as<rsb::TileRec>();
+    P.entries = h->d_entries.as<rsb::PlanEntry>();
     P.tile_total = h->d_counter.as<uint32_t>();
     P.coeffs = h->d_coeffs;
     P.st = h->st;
@@ -410,7 +412,10 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     {
         std::vector<uint64_t> new_id(n_units);
         for (uint32_t u = 0; u < n_units; ++u) new_id[u] = h->next_cohort++;
-        for (uint32_t i = 0; i < n; ++i) h->cohort[jobs[i].stream] = new_id[h->job_unit[i]];
+        for (uint32_t i = 0; i < n; ++i) {
+            h->cohort[jobs[i].stream] = new_id[h->job_unit[i]];
+            h->hist_sel[jobs[i].stream] ^= 1u;   // the update kernel wrote the other buffer
+        }
     }
     h->last_n_units = n_units;
     h->last_has_calls = rec_calls;
@@ -520,6 +525,7 @@ int rsb_fir_create(rsb_fir **out, int device, uint32_t n_streams, uint32_t chann
     const float cutoff = rsb::design_cutoff(input_rate_hz, output_rate_hz, h->taps, beta);
     h->table = rsb::get_or_create_table(cutoff, h->taps, attenuation);
     h->cohort.assign(n_streams, 0);
+    h->hist_sel.assign(n_streams, 0);
 
     RSB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     RSB_CUDA(cudaEventCreate(&h->ev_t0));
@@ -536,12 +542,10 @@ int rsb_fir_create(rsb_fir **out, int device, uint32_t n_streams, uint32_t chann
     const size_t hist_bytes = (size_t)n_streams * rsb::kHistFrames * channels * sizeof(float);
     RSB_CUDA(cudaMalloc(&h->st.position, sizeof(double) * n_streams));
     RSB_CUDA(cudaMalloc(&h->st.hist_len, sizeof(uint32_t) * n_streams));
-    RSB_CUDA(cudaMalloc(&h->st.hist_sel, n_streams));
     RSB_CUDA(cudaMalloc(&h->st.hist[0], hist_bytes));
     RSB_CUDA(cudaMalloc(&h->st.hist[1], hist_bytes));
     RSB_CUDA(cudaMemsetAsync(h->st.position, 0, sizeof(double) * n_streams, h->stream));
     RSB_CUDA(cudaMemsetAsync(h->st.hist_len, 0, sizeof(uint32_t) * n_streams, h->stream));
-    RSB_CUDA(cudaMemsetAsync(h->st.hist_sel, 0, n_streams, h->stream));
     RSB_CUDA(cudaMemsetAsync(h->st.hist[0], 0, hist_bytes, h->stream));   // :329 zero-filled
     RSB_CUDA(cudaMemsetAsync(h->st.hist[1], 0, hist_bytes, h->stream));
     RSB_CUDA(cudaStreamSynchronize(h->stream));
@@ -556,13 +560,12 @@ void rsb_fir_destroy(rsb_fir *h) {
     cudaFree(h->d_coeffs);
     cudaFree(h->st.position);
     cudaFree(h->st.hist_len);
-    cudaFree(h->st.hist_sel);
     cudaFree(h->st.hist[0]);
     cudaFree(h->st.hist[1]);
-    for (DevBuf *b : {&h->d_units, &h->d_jobs, &h->d_members, &h->d_segs, &h->d_calls, &h->d_tiles,
+    for (DevBuf *b : {&h->d_units, &h->d_jobs, &h->d_segs, &h->d_calls, &h->d_tiles, &h->d_entries,
                       &h->d_counter, &h->d_stage_in, &h->d_stage_out, &h->d_dbg})
         b->release();
-    for (PinBuf *b : {&h->h_units, &h->h_jobs, &h->h_members, &h->h_units_back, &h->h_calls_back})
+    for (PinBuf *b : {&h->h_units, &h->h_jobs, &h->h_units_back, &h->h_calls_back})
         b->release();
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);
     if (h->ev_t1) cudaEventDestroy(h->ev_t1);
@@ -757,7 +760,7 @@ int rsb_fir_last_plan(rsb_fir *h, uint32_t job, uint32_t *input_offset, uint32_t
     if (cnt == 0) return RSB_OK;
     RSB_CUDA(h->d_dbg.reserve(cnt * 4 * sizeof(uint32_t)));
     uint32_t *d = h->d_dbg.as<uint32_t>();
-    rsb::launch_expand_plan(h->d_units.as<UnitDev>(), unit, h->d_segs.as<rsb::PlanSeg>(),
+    rsb::launch_expand_plan(h->d_units.as<UnitDev>(), unit, h->d_entries.as<rsb::PlanEntry>(),
                             (uint32_t)cnt, d, d + cnt, d + 2 * cnt, d + 3 * cnt, h->stream);
     h->launches += 1;
     RSB_CUDA(cudaGetLastError());

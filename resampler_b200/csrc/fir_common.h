@@ -17,10 +17,13 @@ namespace rsb {
 
 constexpr uint32_t kHistFrames = kInputCapacity;   // max frames carried between calls (:18)
 
-// One job = one stream's work in a submit (device copy).
+// One job = one stream's work in a submit (device copy).  Jobs are stored grouped by plan
+// unit: the members of unit U are jobs[U.member_off .. U.member_off + U.n_members).
 struct JobDev {
     const float *in;          // interleaved new input (device), may be null when total_frames == 0
     float *out;               // interleaved output (device)
+    const float *hist;        // this stream's live history buffer  [kHistFrames*channels]
+    float *hist_next;         // the other history buffer (written by the state update)
     uint64_t out_capacity;    // frames that fit in `out`
     uint32_t stream;          // stream index inside the handle
     uint32_t unit;            // plan unit this job belongs to
@@ -54,12 +57,23 @@ struct UnitDev {
     double final_position;
 };
 
+constexpr uint32_t kTileOut = 32;   // output frames per tile (both convolution kernels)
+
 // Tile record: tile `t` of a unit covers outputs [o_start, o_start + n_out).
 struct TileRec {
     uint32_t unit;
     uint32_t o_start;
     uint32_t seg;       // absolute index of the segment containing o_start
     uint32_t n_out;
+};
+
+// Per-output-frame plan entry, expanded once per tile by the tile kernel and shared by every
+// stream group that processes the tile: entries[tile * kTileOut + k].
+struct PlanEntry {
+    int32_t v;          // virtual input frame of the window start (vbase + floor(position))
+    uint32_t phase1;
+    float frac;
+    uint32_t off;       // floor(position): the reference's input_offset inside its call
 };
 
 struct CallCounts {
@@ -71,8 +85,9 @@ struct CallCounts {
 struct StreamStateDev {
     double *position;        // [n_streams]
     uint32_t *hist_len;      // [n_streams]  == available_frames between calls
-    uint8_t *hist_sel;       // [n_streams]  which of the two history buffers is live
-    float *hist[2];          // [n_streams][kHistFrames*channels], right-aligned
+    float *hist[2];          // [n_streams][kHistFrames*channels], right-aligned; which of the
+                             // two is live for a stream is tracked by the host (it flips at
+                             // every submit the stream takes part in)
 };
 
 }  // namespace rsb

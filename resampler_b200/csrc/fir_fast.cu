@@ -25,7 +25,7 @@ namespace rsb {
 
 namespace {
 
-constexpr int kKT = 32;        // output frames per tile
+constexpr int kKT = (int)kTileOut;   // output frames per tile (32)
 constexpr int kNC = 128;       // columns per tile
 constexpr int kThreads = 128;  // 4 warps: warp w owns rows 8w..8w+7, all 128 columns
 constexpr int kK = 8;
@@ -95,17 +95,15 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
         "l"(src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-
-__device__ __forceinline__ void locate_output(const PlanSeg *segs, uint32_t s, uint32_t o,
-                                              PhasePoint &pp, int64_t &v) {
-    PlanSeg sg = segs[s];
-    while (o >= sg.out0 + sg.n) sg = segs[++s];
-    const double pos = bits2d(sg.base_bits + (int64_t)(o - sg.out0) * sg.step_bits);
-    pp = phase_point(pos);
-    v = sg.vbase + (int64_t)pp.off;
 }
 
 // Element-wise staging of one float4 `sub` of the 4-frame group starting at virtual frame vg
@@ -172,20 +170,17 @@ __global__ void __launch_bounds__(kThreads) conv_fast_kernel(ConvParams P, FastG
 
         __syncthreads();   // previous tile fully consumed (also orders the mbarrier init)
         if (tid < n_out) {
-            PhasePoint pp;
-            int64_t v;
-            locate_output(P.segs, rec.seg, rec.o_start + tid, pp, v);
-            s_v[tid] = v;
-            s_p1[tid] = pp.phase1;
-            s_frac[tid] = pp.frac;
+            const PlanEntry e = P.entries[(size_t)t * kTileOut + tid];
+            s_v[tid] = e.v;
+            s_p1[tid] = e.phase1;
+            s_frac[tid] = e.frac;
         }
         if (tid < nm) {
-            const JobDev job = P.jobs[P.members[U.member_off + m0 + tid]];
-            s_in[tid] = job.in;
-            s_hist[tid] = P.st.hist[P.st.hist_sel[job.stream]] +
-                          (size_t)job.stream * kHistFrames * ch;
-            s_out[tid] = job.out;
-            s_cap[tid] = job.out_capacity;
+            const JobDev *job = P.jobs + U.member_off + m0 + tid;
+            s_in[tid] = job->in;
+            s_hist[tid] = job->hist;
+            s_out[tid] = job->out;
+            s_cap[tid] = job->out_capacity;
         }
         __syncthreads();
         // window start: aligned so that (v_base - H) % 4 == 0 -> every 4-frame group lies
@@ -272,7 +267,36 @@ __global__ void __launch_bounds__(kThreads) conv_fast_kernel(ConvParams P, FastG
         if (CH != 0) {
             mbar_wait(&s_bar, bar_parity);
             bar_parity ^= 1u;
-            if (CH > 1) {
+            if (CH == 2) {
+                // in place, one warp per member: 3 float4 per lane cover a window of <= 192
+                // frames; (L0 R0 L1 R1) -> row 0: (L0, L1), row 1: (R0, R1)
+                const uint32_t vps = (uint32_t)n_grp * 2u;
+                const bool has2 = lane + 64 < vps;
+                float *blk = X + (size_t)warp * 2 * xs;
+                for (uint32_t m = warp; m < nm; m += kThreads / 32, blk += (kThreads / 32) * 2 * xs) {
+                    const float4 *r4 = reinterpret_cast<const float4 *>(blk);
+                    float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0, b2 = b0;
+                    if (lane < vps) b0 = r4[lane];
+                    if (lane + 32 < vps) b1 = r4[lane + 32];
+                    if (has2) b2 = r4[lane + 64];
+                    __syncwarp();
+                    float2 *w0 = reinterpret_cast<float2 *>(blk);
+                    float2 *w1 = reinterpret_cast<float2 *>(blk + xs);
+                    if (lane < vps) {
+                        w0[lane] = make_float2(b0.x, b0.z);
+                        w1[lane] = make_float2(b0.y, b0.w);
+                    }
+                    if (lane + 32 < vps) {
+                        w0[lane + 32] = make_float2(b1.x, b1.z);
+                        w1[lane + 32] = make_float2(b1.y, b1.w);
+                    }
+                    if (has2) {
+                        w0[lane + 64] = make_float2(b2.x, b2.z);
+                        w1[lane + 64] = make_float2(b2.y, b2.w);
+                    }
+                    __syncwarp();
+                }
+            } else if (CH > 2) {
                 // in place, one warp per member: read the whole raw window, then write planar
                 const uint32_t vps = (uint32_t)n_grp * CH;   // float4 per member
                 for (uint32_t m = warp; m < nm; m += kThreads / 32) {
@@ -375,31 +399,49 @@ __global__ void __launch_bounds__(kThreads) conv_fast_kernel(ConvParams P, FastG
             for (int k = 0; k < kK; ++k)
 #pragma unroll
                 for (int c = 0; c < kC; ++c) acc[k][c] = make_float2(0.f, 0.f);
-            const float *xp = X + lane * xs;
-            const float *gp = G + r0 * xs;
-
-            auto do_chunk = [&](int j) {
-                float4 xv[kC];
+            // 32-bit shared addresses of this thread's 4 columns and 8 rows
+            uint32_t xa[kC], ga[kK];
 #pragma unroll
-                for (int c = 0; c < kC; ++c)
-                    xv[c] = *reinterpret_cast<const float4 *>(xp + c * 32 * xs + j);
+            for (int c = 0; c < kC; ++c) xa[c] = smem_u32(X + (lane + 32 * c) * xs);
+#pragma unroll
+            for (int k = 0; k < kK; ++k) ga[k] = smem_u32(G + (r0 + k) * xs);
+
+            // chunk order is outside-in (both ends of the band first, centre taps last):
+            // step s -> chunk s/2 from the front (s even) or from the back (s odd)
+            auto chunk_byte = [&](int s) {
+                const int idx = (s & 1) ? (n_chunks - 1 - (s >> 1)) : (s >> 1);
+                return (uint32_t)(j_lo + 4 * idx) * 4u;
+            };
+            float4 gv[kK], xv[kC];
+            {
+                const uint32_t jb = chunk_byte(0);
+#pragma unroll
+                for (int c = 0; c < kC; ++c) xv[c] = lds128(xa[c] + jb);
+#pragma unroll
+                for (int k = 0; k < kK; ++k) gv[k] = lds128(ga[k] + jb);
+            }
+            for (int sidx = 0; sidx < n_chunks; ++sidx) {
+                // software pipeline: the next chunk's operands are in flight during the FMAs
+                float4 gn[kK], xn[kC];
+                const int snext = sidx + 1 < n_chunks ? sidx + 1 : sidx;
+                const uint32_t jb = chunk_byte(snext);
+#pragma unroll
+                for (int c = 0; c < kC; ++c) xn[c] = lds128(xa[c] + jb);
+#pragma unroll
+                for (int k = 0; k < kK; ++k) gn[k] = lds128(ga[k] + jb);
 #pragma unroll
                 for (int k = 0; k < kK; ++k) {
-                    const float4 gv = *reinterpret_cast<const float4 *>(gp + k * xs + j);
 #pragma unroll
                     for (int c = 0; c < kC; ++c) {
-                        ffma2(acc[k][c], make_float2(gv.x, gv.y), make_float2(xv[c].x, xv[c].y));
-                        ffma2(acc[k][c], make_float2(gv.z, gv.w), make_float2(xv[c].z, xv[c].w));
+                        ffma2(acc[k][c], make_float2(gv[k].x, gv[k].y), make_float2(xv[c].x, xv[c].y));
+                        ffma2(acc[k][c], make_float2(gv[k].z, gv[k].w), make_float2(xv[c].z, xv[c].w));
                     }
                 }
-            };
-            // outside-in: both ends of the band first, centre taps last
-            const int half = n_chunks >> 1;
-            for (int i = 0; i < half; ++i) {
-                do_chunk(j_lo + 4 * i);
-                do_chunk(j_lo + 4 * (n_chunks - 1 - i));
+#pragma unroll
+                for (int c = 0; c < kC; ++c) xv[c] = xn[c];
+#pragma unroll
+                for (int k = 0; k < kK; ++k) gv[k] = gn[k];
             }
-            if (n_chunks & 1) do_chunk(j_lo + 4 * half);
 
             // ---- store: out[stream][(o_start + row) * ch + c] ----
 #pragma unroll
@@ -430,8 +472,6 @@ bool fast_supported(uint32_t channels, uint32_t taps, double ratio) {
     return fast_smem_bytes(fast_geom(taps, ratio)) <= 200u * 1024u;
 }
 
-uint32_t fast_tile_out(uint32_t, uint32_t, double) { return kKT; }
-
 uint32_t fast_streams_per_group(uint32_t channels, uint32_t, double) { return kNC / channels; }
 
 void launch_conv_fast(const ConvParams &p, double ratio, uint32_t max_items, int sm_count,
@@ -451,7 +491,7 @@ void launch_conv_fast(const ConvParams &p, double ratio, uint32_t max_items, int
 #define RSB_FAST_DISPATCH(T)                                             \
     do {                                                                 \
         const bool tma_ok = (geo.win_max / 4) * p.channels <=            \
-                            32u * (uint32_t)max_vec_per_lane((int)p.channels); \
+                            32u * (uint32_t)(p.channels == 2 ? 3 : max_vec_per_lane((int)p.channels)); \
         if (p.channels == 1) launch(conv_fast_kernel<T, 1>);             \
         else if (p.channels == 2 && tma_ok) launch(conv_fast_kernel<T, 2>); \
         else if (p.channels == 4 && tma_ok) launch(conv_fast_kernel<T, 4>); \

@@ -3,7 +3,7 @@
 // Pipeline of one submit (all on the handle's stream):
 //   plan_units_kernel   one thread per plan unit: exact f64 phase walk in closed form
 //                       (planner.h), emits segments + per-call counts + tile slices
-//   tile_index_kernel   one thread per tile: binary search of its first segment
+//   tile_index_kernel   one warp per tile: first segment + the tile's 32 plan entries
 //   conv_*_kernel       persistent CTAs over (tile, stream group)
 //   update_state_kernel one CTA per job: history tail -> other history buffer, scalars
 #include "fir_kernels.h"
@@ -97,51 +97,60 @@ void launch_plan(UnitDev *units, uint32_t n_units, StreamStateDev st, double rat
 // ---------------------------------------------------------------------------
 // tile records
 // ---------------------------------------------------------------------------
+// One warp per tile: lane 0 finds the tile's first segment by binary search, then every lane
+// expands one output frame of the tile (exact position -> offset, phase, frac).
 __global__ void tile_index_kernel(const UnitDev *units, const PlanSeg *segs, TileRec *tiles,
-                                  uint32_t tile_out) {
+                                  PlanEntry *entries) {
     const uint32_t u = blockIdx.x;
     const UnitDev &U = units[u];
     const uint32_t n_tiles = U.n_tiles;
-    const uint32_t t = blockIdx.y * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t t = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (t >= n_tiles) return;
-    const uint32_t o = t * tile_out;
+    const uint32_t o0 = t * kTileOut;
     const PlanSeg *sg = segs + U.seg_off;
-    // last segment with out0 <= o
-    uint32_t lo = 0, hi = U.n_segs;   // invariant: sg[lo].out0 <= o, sg[hi] (if any) > o
+    // last segment with out0 <= o0
+    uint32_t lo = 0, hi = U.n_segs;
     while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;
-        if (sg[mid].out0 <= o) lo = mid; else hi = mid;
+        if (sg[mid].out0 <= o0) lo = mid; else hi = mid;
     }
-    TileRec r;
-    r.unit = u;
-    r.o_start = o;
-    r.seg = U.seg_off + lo;
-    const uint64_t left = U.total_out - o;
-    r.n_out = (uint32_t)(left < tile_out ? left : tile_out);
-    tiles[U.tile_off + t] = r;
+    const uint64_t left = U.total_out - o0;
+    const uint32_t n_out = (uint32_t)(left < kTileOut ? left : kTileOut);
+    if (lane == 0) {
+        TileRec r;
+        r.unit = u;
+        r.o_start = o0;
+        r.seg = U.seg_off + lo;
+        r.n_out = n_out;
+        tiles[U.tile_off + t] = r;
+    }
+    PlanEntry e;
+    e.v = 0; e.phase1 = 0; e.frac = 0.f; e.off = 0;
+    if (lane < n_out) {
+        uint32_t s = lo;
+        PlanSeg cur = sg[s];
+        const uint32_t o = o0 + lane;
+        while (o >= cur.out0 + cur.n) cur = sg[++s];
+        const double pos = bits2d(cur.base_bits + (int64_t)(o - cur.out0) * cur.step_bits);
+        const PhasePoint pp = phase_point(pos);
+        e.v = (int32_t)(cur.vbase + (int64_t)pp.off);
+        e.phase1 = pp.phase1;
+        e.frac = pp.frac;
+        e.off = pp.off;
+    }
+    entries[(size_t)(U.tile_off + t) * kTileOut + lane] = e;
 }
 
 void launch_tiles(const UnitDev *units, uint32_t n_units, const PlanSeg *segs, TileRec *tiles,
-                  uint32_t tile_out, uint32_t max_tiles_per_unit, cudaStream_t stream) {
+                  PlanEntry *entries, uint32_t max_tiles_per_unit, cudaStream_t stream) {
     if (n_units == 0 || max_tiles_per_unit == 0) return;
-    const uint32_t threads = 128;
-    // gridDim.y is limited to 65535: fold units into x, tile chunks into y
-    uint32_t chunks = (max_tiles_per_unit + threads - 1) / threads;
-    if (chunks > 65535u) chunks = 65535u;   // callers bound tiles per unit below 65535*128
+    const uint32_t threads = 128, per_cta = threads / 32;
+    // gridDim.y is limited to 65535: units in x, tile chunks in y
+    uint32_t chunks = (max_tiles_per_unit + per_cta - 1) / per_cta;
+    if (chunks > 65535u) chunks = 65535u;   // callers bound tiles per unit below 65535*4
     dim3 grid(n_units, chunks);
-    tile_index_kernel<<<grid, threads, 0, stream>>>(units, segs, tiles, tile_out);
-}
-
-// ---------------------------------------------------------------------------
-// shared device helpers
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ void locate_output(const PlanSeg *segs, uint32_t s, uint32_t o,
-                                              PhasePoint &pp, int64_t &v) {
-    PlanSeg sg = segs[s];
-    while (o >= sg.out0 + sg.n) sg = segs[++s];
-    const double pos = bits2d(sg.base_bits + (int64_t)(o - sg.out0) * sg.step_bits);
-    pp = phase_point(pos);
-    v = sg.vbase + (int64_t)pp.off;
+    tile_index_kernel<<<grid, threads, 0, stream>>>(units, segs, tiles, entries);
 }
 
 // ---------------------------------------------------------------------------
@@ -153,9 +162,9 @@ __device__ __forceinline__ void locate_output(const PlanSeg *segs, uint32_t s, u
 // halving tree of _mm512_reduce_add_ps (:48) via xor-shuffles 8, 4, 2, 1.
 template <int TAPS>
 __global__ void __launch_bounds__(256) conv_exact_kernel(ConvParams P) {
-    __shared__ int64_t s_v[kExactTileOut];
-    __shared__ uint32_t s_p1[kExactTileOut];
-    __shared__ float s_frac[kExactTileOut];
+    __shared__ int64_t s_v[kTileOut];
+    __shared__ uint32_t s_p1[kTileOut];
+    __shared__ float s_frac[kTileOut];
 
     const uint32_t ch = P.channels;
     const uint32_t n_items = *P.tile_total * P.groups;
@@ -175,12 +184,10 @@ __global__ void __launch_bounds__(256) conv_exact_kernel(ConvParams P) {
 
         __syncthreads();
         if (threadIdx.x < rec.n_out) {
-            PhasePoint pp;
-            int64_t v;
-            locate_output(P.segs, rec.seg, rec.o_start + threadIdx.x, pp, v);
-            s_v[threadIdx.x] = v;
-            s_p1[threadIdx.x] = pp.phase1;
-            s_frac[threadIdx.x] = pp.frac;
+            const PlanEntry e = P.entries[(size_t)t * kTileOut + threadIdx.x];
+            s_v[threadIdx.x] = e.v;
+            s_p1[threadIdx.x] = e.phase1;
+            s_frac[threadIdx.x] = e.frac;
         }
         __syncthreads();
 
@@ -194,9 +201,8 @@ __global__ void __launch_bounds__(256) conv_exact_kernel(ConvParams P) {
             const uint32_t rem = idx - m * per_stream;
             const uint32_t k = rem / ch;
             const uint32_t c = rem - k * ch;
-            const JobDev job = P.jobs[P.members[U.member_off + m0 + m]];
-            const float *hist = P.st.hist[P.st.hist_sel[job.stream]] +
-                                (size_t)job.stream * kHistFrames * ch;
+            const JobDev job = P.jobs[U.member_off + m0 + m];
+            const float *hist = job.hist;
             const int64_t v = s_v[k];
             const uint32_t p1 = s_p1[k];
             const uint32_t p2 = p1 + 1 < kPhases - 1 ? p1 + 1 : kPhases - 1;
@@ -244,9 +250,8 @@ __global__ void update_state_kernel(const UnitDev *units, const JobDev *jobs, St
                                     uint32_t ch) {
     const JobDev job = jobs[blockIdx.x];
     const UnitDev &U = units[job.unit];
-    const uint32_t sel = st.hist_sel[job.stream];
-    const float *old_hist = st.hist[sel] + (size_t)job.stream * kHistFrames * ch;
-    float *new_hist = st.hist[sel ^ 1u] + (size_t)job.stream * kHistFrames * ch;
+    const float *old_hist = job.hist;
+    float *new_hist = job.hist_next;
     const int64_t H0 = U.hist_len0, H1 = U.final_available;
     const int64_t v_end = H0 + (int64_t)U.total_copied;
     const int64_t v0 = v_end - H1;   // first virtual frame that stays buffered
@@ -262,7 +267,6 @@ __global__ void update_state_kernel(const UnitDev *units, const JobDev *jobs, St
     if (threadIdx.x == 0) {
         st.position[job.stream] = U.final_position;
         st.hist_len[job.stream] = (uint32_t)H1;
-        st.hist_sel[job.stream] = (uint8_t)(sel ^ 1u);
     }
 }
 
@@ -287,33 +291,26 @@ void launch_reset(StreamStateDev st, uint32_t first, uint32_t count, cudaStream_
 // ---------------------------------------------------------------------------
 // plan expansion (debug / parity of phase indices)
 // ---------------------------------------------------------------------------
-__global__ void expand_plan_kernel(const UnitDev *units, uint32_t unit, const PlanSeg *segs,
+__global__ void expand_plan_kernel(const UnitDev *units, uint32_t unit, const PlanEntry *entries,
                                    uint32_t n_frames, uint32_t *off, uint32_t *p1, uint32_t *p2,
                                    uint32_t *fb) {
     const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= n_frames) return;
     const UnitDev &U = units[unit];
-    const PlanSeg *sg = segs + U.seg_off;
-    uint32_t lo = 0, hi = U.n_segs;
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (sg[mid].out0 <= o) lo = mid; else hi = mid;
-    }
-    PhasePoint pp;
-    int64_t v;
-    locate_output(segs, U.seg_off + lo, o, pp, v);
-    if (off) off[o] = pp.off;
-    if (p1) p1[o] = pp.phase1;
-    if (p2) p2[o] = pp.phase2;
-    if (fb) fb[o] = __float_as_uint(pp.frac);
+    // the very entries the convolution kernels consume
+    const PlanEntry e = entries[(size_t)(U.tile_off + o / kTileOut) * kTileOut + (o % kTileOut)];
+    if (off) off[o] = e.off;
+    if (p1) p1[o] = e.phase1;
+    if (p2) p2[o] = e.phase1 + 1 < kPhases - 1 ? e.phase1 + 1 : kPhases - 1;
+    if (fb) fb[o] = __float_as_uint(e.frac);
 }
 
-void launch_expand_plan(const UnitDev *units, uint32_t unit, const PlanSeg *segs, uint32_t n_frames,
-                        uint32_t *off, uint32_t *p1, uint32_t *p2, uint32_t *fb,
+void launch_expand_plan(const UnitDev *units, uint32_t unit, const PlanEntry *entries,
+                        uint32_t n_frames, uint32_t *off, uint32_t *p1, uint32_t *p2, uint32_t *fb,
                         cudaStream_t stream) {
     if (n_frames == 0) return;
-    expand_plan_kernel<<<(n_frames + 255) / 256, 256, 0, stream>>>(units, unit, segs, n_frames, off,
-                                                                    p1, p2, fb);
+    expand_plan_kernel<<<(n_frames + 255) / 256, 256, 0, stream>>>(units, unit, entries, n_frames,
+                                                                    off, p1, p2, fb);
 }
 
 // ---------------------------------------------------------------------------

@@ -10,10 +10,10 @@ namespace rsb {
 
 struct ConvParams {
     const UnitDev *units;
-    const JobDev *jobs;
-    const uint32_t *members;      // job indices grouped by unit
+    const JobDev *jobs;           // grouped by unit (see JobDev)
     const PlanSeg *segs;
     const TileRec *tiles;
+    const PlanEntry *entries;     // [tile][kTileOut]
     const uint32_t *tile_total;   // device counter written by the plan kernel
     const float *coeffs;          // [1024][taps]
     StreamStateDev st;
@@ -23,8 +23,6 @@ struct ConvParams {
     uint32_t streams_per_group;
 };
 
-// outputs per tile record
-constexpr uint32_t kExactTileOut = 32;
 constexpr uint32_t kExactStreamsPerGroup = 4;
 
 // plan: one thread per unit walks its calls; also assigns tile slices
@@ -33,12 +31,11 @@ void launch_plan(UnitDev *units, uint32_t n_units, StreamStateDev st, double rat
                  cudaStream_t stream);
 // tile records: binary search of each tile's first segment
 void launch_tiles(const UnitDev *units, uint32_t n_units, const PlanSeg *segs, TileRec *tiles,
-                  uint32_t tile_out, uint32_t max_tiles_per_unit, cudaStream_t stream);
+                  PlanEntry *entries, uint32_t max_tiles_per_unit, cudaStream_t stream);
 // exact (AVX-512 order) convolution
 void launch_conv_exact(const ConvParams &p, uint32_t max_items, int sm_count, cudaStream_t stream);
 // fast convolution (fir_fast.cu); returns false when the configuration is unsupported
 bool fast_supported(uint32_t channels, uint32_t taps, double ratio);
-uint32_t fast_tile_out(uint32_t channels, uint32_t taps, double ratio);
 uint32_t fast_streams_per_group(uint32_t channels, uint32_t taps, double ratio);
 void launch_conv_fast(const ConvParams &p, double ratio, uint32_t max_items, int sm_count,
                       cudaStream_t stream);
@@ -47,8 +44,8 @@ void launch_update(const UnitDev *units, const JobDev *jobs, uint32_t n_jobs, St
                    uint32_t channels, cudaStream_t stream);
 void launch_reset(StreamStateDev st, uint32_t first, uint32_t count, cudaStream_t stream);
 // expands a unit's plan into per-frame arrays with the kernels' own device code
-void launch_expand_plan(const UnitDev *units, uint32_t unit, const PlanSeg *segs, uint32_t n_frames,
-                        uint32_t *off, uint32_t *p1, uint32_t *p2, uint32_t *fb,
+void launch_expand_plan(const UnitDev *units, uint32_t unit, const PlanEntry *entries,
+                        uint32_t n_frames, uint32_t *off, uint32_t *p1, uint32_t *p2, uint32_t *fb,
                         cudaStream_t stream);
 void launch_fill_synthetic(float *dst, uint32_t first_stream, uint32_t n_streams, uint64_t frames,
                            uint32_t channels, uint32_t rate_hz, uint64_t seed, cudaStream_t stream);
