@@ -153,6 +153,10 @@ int rsb_fir_timer_stop(rsb_fir *h, float *elapsed_ms); /* waits for the stop eve
 /* device time (ms, CUDA events on the handle's stream) of the convolution kernel of the most
  * recent batches, newest first, at most 64; waits for the stream */
 int rsb_fir_conv_times(rsb_fir *h, float *ms, size_t max, size_t *n);
+/* debug: per-phase SM cycle totals of the fast kernel (thread 0 of every CTA): [0] tile setup,
+ * [1] TMA issue + zero fill, [2] banded-row build, [3] TMA wait, [4] de-interleave,
+ * [5] register-tiled product, [6] store.  Returns and clears the counters; sets the enable flag. */
+int rsb_debug_phase_cycles(rsb_fir *h, int enable, uint64_t *out8);
 /* kernels launched on this handle since creation (your own count for gpu_launches) */
 uint64_t rsb_fir_launch_count(const rsb_fir *h);
 /* the handle's cudaStream_t, as an opaque pointer */

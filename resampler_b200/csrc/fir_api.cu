@@ -113,7 +113,7 @@ struct rsb_fir {
     uint64_t conv_batches = 0;
 
     // workspace of the (single) in-flight submit
-    DevBuf d_units, d_jobs, d_segs, d_calls, d_tiles, d_entries, d_counter, d_stage_in,
+    DevBuf d_units, d_jobs, d_segs, d_calls, d_tiles, d_entries, d_gtiles, d_counter, d_stage_in,
         d_stage_out, d_dbg;
     PinBuf h_units, h_jobs, h_units_back, h_calls_back;
     std::vector<uint32_t> job_unit;          // unit of each job of the last batch
@@ -352,6 +352,9 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     RSB_CUDA(h->d_segs.reserve(sizeof(rsb::PlanSeg) * seg_total));
     RSB_CUDA(h->d_tiles.reserve(sizeof(rsb::TileRec) * tile_total));
     RSB_CUDA(h->d_entries.reserve(sizeof(rsb::PlanEntry) * rsb::kTileOut * tile_total));
+    const uint32_t gs = use_fast ? rsb::fast_row_stride(h->taps, h->ratio) : 0;
+    if (use_fast)
+        RSB_CUDA(h->d_gtiles.reserve(sizeof(float) * rsb::kTileOut * gs * tile_total));
     RSB_CUDA(h->d_counter.reserve(sizeof(uint32_t) * 4));
     if (rec_calls) {
         RSB_CUDA(h->d_calls.reserve(sizeof(rsb::CallCounts) * std::max<uint64_t>(call_total, 1)));
@@ -375,13 +378,15 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
                      h->d_counter.as<uint32_t>(), s);
     rsb::launch_tiles(h->d_units.as<UnitDev>(), n_units, h->d_segs.as<rsb::PlanSeg>(),
                       h->d_tiles.as<rsb::TileRec>(), h->d_entries.as<rsb::PlanEntry>(),
-                      (uint32_t)max_tiles_unit, s);
+                      (uint32_t)max_tiles_unit, h->taps, h->d_coeffs,
+                      use_fast ? h->d_gtiles.as<float>() : nullptr, gs, s);
     rsb::ConvParams P;
     P.units = h->d_units.as<UnitDev>();
     P.jobs = h->d_jobs.as<JobDev>();
     P.segs = h->d_segs.as<rsb::PlanSeg>();
     P.tiles = h->d_tiles.as<rsb::TileRec>();
     P.entries = h->d_entries.as<rsb::PlanEntry>();
+    P.gtiles = h->d_gtiles.as<float>();
     P.tile_total = h->d_counter.as<uint32_t>();
     P.coeffs = h->d_coeffs;
     P.st = h->st;
@@ -563,7 +568,7 @@ void rsb_fir_destroy(rsb_fir *h) {
     cudaFree(h->st.hist[0]);
     cudaFree(h->st.hist[1]);
     for (DevBuf *b : {&h->d_units, &h->d_jobs, &h->d_segs, &h->d_calls, &h->d_tiles, &h->d_entries,
-                      &h->d_counter, &h->d_stage_in, &h->d_stage_out, &h->d_dbg})
+                      &h->d_gtiles, &h->d_counter, &h->d_stage_in, &h->d_stage_out, &h->d_dbg})
         b->release();
     for (PinBuf *b : {&h->h_units, &h->h_jobs, &h->h_units_back, &h->h_calls_back})
         b->release();
@@ -805,6 +810,16 @@ int rsb_fir_conv_times(rsb_fir *h, float *ms, size_t max, size_t *n) {
         RSB_CUDA(cudaEventElapsedTime(&t, h->ev_conv[slot][0], h->ev_conv[slot][1]));
         if (ms) ms[i] = t;
     }
+    return RSB_OK;
+}
+
+int rsb_debug_phase_cycles(rsb_fir *h, int enable, uint64_t *out8) {
+    if (check_handle(h)) return RSB_ERR_INVALID_ARGUMENT;
+    RSB_CUDA(cudaSetDevice(h->device));
+    RSB_CUDA(cudaStreamSynchronize(h->stream));
+    static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "u64");
+    rsb::fast_phase_profile(enable, reinterpret_cast<unsigned long long *>(out8));
+    RSB_CUDA(cudaGetLastError());
     return RSB_OK;
 }
 

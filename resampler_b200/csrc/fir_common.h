@@ -65,6 +65,9 @@ struct TileRec {
     uint32_t o_start;
     uint32_t seg;       // absolute index of the segment containing o_start
     uint32_t n_out;
+    int32_t v_base;     // first virtual frame of the tile's input window; (v_base - H) % 4 == 0
+    uint32_t winp;      // window length in frames, multiple of 4
+    uint32_t pad0, pad1;
 };
 
 // Per-output-frame plan entry, expanded once per tile by the tile kernel and shared by every

@@ -23,6 +23,10 @@
 
 namespace rsb {
 
+// Optional per-phase cycle accounting (thread 0 of every CTA; enabled by a debug call).
+__device__ unsigned long long g_phase_cycles[8];
+__device__ int g_phase_enabled = 0;
+
 namespace {
 
 constexpr int kKT = (int)kTileOut;   // output frames per tile (32)
@@ -32,8 +36,10 @@ constexpr int kK = 8;
 constexpr int kC = 4;
 
 struct FastGeom {
-    uint32_t xs;        // row stride of X and G in floats (== 4 mod 32)
+    uint32_t xs;        // row stride of G and of planar X in floats (== 4 mod 32)
     uint32_t win_max;   // largest window (multiple of 4)
+    uint32_t mb;        // stereo: floats per interleaved member block, 4 * odd so that eight
+                        // lanes' 16-byte loads (one member each) hit eight distinct bank quads
 };
 
 __host__ __device__ inline uint32_t fast_win_max(uint32_t taps, double ratio) {
@@ -50,11 +56,16 @@ __host__ inline FastGeom fast_geom(uint32_t taps, double ratio) {
     uint32_t xs = g.win_max;
     while ((xs & 31u) != 4u) xs += 4;
     g.xs = xs;
+    uint32_t mb = 2u * g.win_max;
+    while (((mb >> 2) & 1u) == 0u) mb += 4;
+    g.mb = mb;
     return g;
 }
 
-__host__ inline size_t fast_smem_bytes(const FastGeom &g) {
-    return (size_t)(kKT + kNC) * g.xs * sizeof(float);
+__host__ inline size_t fast_smem_bytes(const FastGeom &g, uint32_t channels) {
+    (void)channels;   // (the disabled interleaved stereo layout would use (kNC / 2) * g.mb)
+    const size_t x_floats = (size_t)kNC * g.xs;
+    return ((size_t)kKT * g.xs + x_floats) * sizeof(float);
 }
 
 __device__ __forceinline__ void ffma2(float2 &d, const float2 a, const float2 b) {
@@ -63,6 +74,16 @@ __device__ __forceinline__ void ffma2(float2 &d, const float2 a, const float2 b)
         : "l"(reinterpret_cast<const uint64_t &>(a)), "l"(reinterpret_cast<const uint64_t &>(b)));
 }
 
+// packs two floats into one 64-bit register pair; volatile so that the compiler keeps the
+// pair alive instead of re-forming it (two moves) in front of every FFMA2 that uses it
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm volatile("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void ffma2_u64(float2 &d, const uint64_t a, const uint64_t b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(reinterpret_cast<uint64_t &>(d)) : "l"(a), "l"(b));
+}
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
@@ -127,12 +148,14 @@ __device__ __forceinline__ void stage_slow(float *X, uint32_t xs, uint32_t col0,
 __host__ __device__ constexpr int max_vec_per_lane(int ch) { return ch <= 2 ? 4 : (ch == 4 ? 8 : 12); }
 
 // CH = 1, 2, 4, 8: the member windows arrive by TMA bulk copies (cp.async.bulk, raw interleaved
-// frames) and are de-interleaved in place; CH = 0: any channel count, register-staged loads.
+// frames).  CH = 1 is already planar; CH = 2 stays interleaved in shared memory and the product
+// loop picks the (tap j, tap j+1) pairs of a channel out of each 16-byte load; CH = 4, 8 are
+// de-interleaved in place.  CH = 0: any channel count, register-staged loads.
 template <int TAPS, int CH>
 __global__ void __launch_bounds__(kThreads) conv_fast_kernel(ConvParams P, FastGeom geo) {
     extern __shared__ float4 smem_f4[];
     float *G = reinterpret_cast<float *>(smem_f4);      // [kKT][xs]
-    float *X = G + kKT * geo.xs;                         // [kNC][xs]
+    float *X = G + kKT * geo.xs;   // planar [kNC][xs], or stereo [kNC/2 members][mb] interleaved
     __shared__ int s_d[kKT];          // band start of row k: v_k - v_base
     __shared__ uint32_t s_p1[kKT];
     __shared__ float s_frac[kKT];
@@ -146,10 +169,24 @@ __global__ void __launch_bounds__(kThreads) conv_fast_kernel(ConvParams P, FastG
 
     const uint32_t ch = CH ? (uint32_t)CH : P.channels;
     const uint32_t xs = geo.xs;
+    // Interleaved stereo layout (no de-interleave pass, the product loop picks the tap pairs out
+    // of each 16-byte load) is implemented below but disabled: ptxas re-forms the 64-bit operand
+    // pairs in front of every FFMA2 (about 100 extra moves per 64 FFMA2, measured 2x slower).
+    constexpr bool kIlv = false;
+    const uint32_t mstride = kIlv ? geo.mb : ch * xs;    // floats per member block in X
     const uint32_t n_items = *P.tile_total * P.groups;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t spg = P.streams_per_group;            // members per tile = kNC / ch
     uint32_t bar_parity = 0;
+    const bool prof = g_phase_enabled != 0 && tid == 0;
+    unsigned long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = prof ? clock64() : 0;
+#define RSB_PHASE(i)                          \
+    if (prof) {                               \
+        const long long tn = clock64();       \
+        pc[i] += (unsigned long long)(tn - tprev); \
+        tprev = tn;                           \
+    }
 
     if (CH != 0 && tid == 0) {
         mbar_init(&s_bar, 1);
@@ -183,12 +220,10 @@ __global__ void __launch_bounds__(kThreads) conv_fast_kernel(ConvParams P, FastG
             s_cap[tid] = job->out_capacity;
         }
         __syncthreads();
-        // window start: aligned so that (v_base - H) % 4 == 0 -> every 4-frame group lies
+        // window (from the tile record): (v_base - H) % 4 == 0, so every 4-frame group lies
         // entirely in the history buffer or entirely in the new input, 16-byte aligned
-        const int64_t v_first = s_v[0];
-        const int64_t v_base = v_first - (((v_first - H) % 4 + 4) % 4);
-        const int win = (int)(s_v[n_out - 1] - v_base) + TAPS;
-        const int winp = (win + 3) & ~3;
+        const int64_t v_base = rec.v_base;
+        const int winp = (int)rec.winp;
         const int n_grp = winp >> 2;
         if (tid < n_out) s_d[tid] = (int)(s_v[tid] - v_base);
         // 4-frame groups [g_lo, g_hi) exist completely; [g_lo, g_seam) history, rest new input
@@ -196,18 +231,21 @@ __global__ void __launch_bounds__(kThreads) conv_fast_kernel(ConvParams P, FastG
         int g_hi = (int)min((int64_t)n_grp, (n_valid - v_base) >> 2);
         if (g_hi < g_lo) g_hi = g_lo;
         const int g_seam = (int)max((int64_t)g_lo, min((int64_t)g_hi, (H - v_base) >> 2));
+        RSB_PHASE(0)
 
         if (CH != 0) {
             // ---- TMA: one or two bulk copies per member, raw interleaved frames ----
             const uint32_t bytes_hist = (uint32_t)(g_seam - g_lo) * 16u * ch;
             const uint32_t bytes_in = (uint32_t)(g_hi - g_seam) * 16u * ch;
             if (tid == 0) {
-                fence_proxy_async();   // generic-proxy accesses to X of the last tile are done
-                mbar_arrive_expect_tx(&s_bar, nm * (bytes_hist + bytes_in));
+                fence_proxy_async();   // generic-proxy accesses to X / G of the last tile are done
+                mbar_arrive_expect_tx(&s_bar, nm * (bytes_hist + bytes_in) + kKT * xs * 4u);
+                // the tile's banded filter matrix, built once by the tile kernel
+                bulk_g2s(G, P.gtiles + (size_t)t * kKT * xs, kKT * xs * 4u, &s_bar);
             }
             __syncthreads();
             if (tid < nm) {
-                float *dst = X + (size_t)tid * ch * xs;
+                float *dst = X + (size_t)tid * mstride;
                 if (bytes_hist)
                     bulk_g2s(dst + 4 * g_lo * ch,
                              s_hist[tid] + ((int64_t)kHistFrames - H + v_base + 4 * g_lo) * ch,
@@ -218,56 +256,33 @@ __global__ void __launch_bounds__(kThreads) conv_fast_kernel(ConvParams P, FastG
             }
         }
 
-        // ---- zero G, idle columns ----
-        for (uint32_t i = tid; i < (uint32_t)kKT * n_grp; i += kThreads) {
-            const uint32_t k = i / n_grp, q = i - k * n_grp;
-            reinterpret_cast<float4 *>(G + k * xs)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        for (uint32_t i = tid; i < (kNC - n_cols) * (uint32_t)n_grp; i += kThreads) {
-            const uint32_t c = n_cols + i / n_grp, q = i % n_grp;
-            reinterpret_cast<float4 *>(X + c * xs)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        __syncthreads();
-        // ---- build the banded rows (4 taps per item, loads batched); overlaps the TMA ----
-        {
-            constexpr uint32_t kQ = TAPS / 4;
-            constexpr int kBatch = 4;
-            const uint32_t items = n_out * kQ;
-            for (uint32_t i0 = 0; i0 < items; i0 += kThreads * kBatch) {
-                float4 a[kBatch], b[kBatch];
-#pragma unroll
-                for (int u = 0; u < kBatch; ++u) {
-                    const uint32_t i = i0 + u * kThreads + tid;
-                    if (i < items) {
-                        const uint32_t k = i / kQ, t4 = i - k * kQ;
-                        const uint32_t p1 = s_p1[k];
-                        const uint32_t p2 = p1 + 1 < kPhases - 1 ? p1 + 1 : kPhases - 1;
-                        a[u] = __ldg(reinterpret_cast<const float4 *>(P.coeffs + (size_t)p1 * TAPS) + t4);
-                        b[u] = __ldg(reinterpret_cast<const float4 *>(P.coeffs + (size_t)p2 * TAPS) + t4);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < kBatch; ++u) {
-                    const uint32_t i = i0 + u * kThreads + tid;
-                    if (i < items) {
-                        const uint32_t k = i / kQ, t4 = i - k * kQ;
-                        const float fr = s_frac[k];
-                        const float omf = __fsub_rn(1.0f, fr);
-                        float *dst = G + k * xs + s_d[k] + 4 * t4;
-                        dst[0] = __fmaf_rn(b[u].x, fr, __fmul_rn(a[u].x, omf));
-                        dst[1] = __fmaf_rn(b[u].y, fr, __fmul_rn(a[u].y, omf));
-                        dst[2] = __fmaf_rn(b[u].z, fr, __fmul_rn(a[u].z, omf));
-                        dst[3] = __fmaf_rn(b[u].w, fr, __fmul_rn(a[u].w, omf));
-                    }
-                }
+        // ---- idle columns of a partial group read as zero ----
+        if (kIlv) {
+            const uint32_t q_per = (uint32_t)n_grp * 2u;     // float4 per member window
+            for (uint32_t i = tid; i < (kNC / 2 - nm) * q_per; i += kThreads) {
+                const uint32_t m = nm + i / q_per, q = i % q_per;
+                reinterpret_cast<float4 *>(X + m * mstride)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+            for (uint32_t i = tid; i < (kNC - n_cols) * (uint32_t)n_grp; i += kThreads) {
+                const uint32_t c = n_cols + i / n_grp, q = i % n_grp;
+                reinterpret_cast<float4 *>(X + c * xs)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-
+        if (CH == 0) {
+            // no TMA in the generic path: plain copy of the banded filter matrix
+            const float4 *src = reinterpret_cast<const float4 *>(P.gtiles + (size_t)t * kKT * xs);
+            for (uint32_t i = tid; i < (uint32_t)kKT * (xs >> 2); i += kThreads)
+                reinterpret_cast<float4 *>(G)[i] = __ldg(src + i);
+        }
+        RSB_PHASE(1)
+        RSB_PHASE(2)
         // ---- stage X: de-interleave [frame][ch] -> planar [col][j] ----
         if (CH != 0) {
             mbar_wait(&s_bar, bar_parity);
             bar_parity ^= 1u;
-            if (CH == 2) {
+            RSB_PHASE(3)
+            if (CH == 2 && !kIlv) {
                 // in place, one warp per member: 3 float4 per lane cover a window of <= 192
                 // frames; (L0 R0 L1 R1) -> row 0: (L0, L1), row 1: (R0, R1)
                 const uint32_t vps = (uint32_t)n_grp * 2u;
@@ -340,8 +355,21 @@ __global__ void __launch_bounds__(kThreads) conv_fast_kernel(ConvParams P, FastG
                     const uint32_t m = i / (n_edge * ch), r = i - m * (n_edge * ch);
                     const uint32_t ge = r / ch, sub = r - ge * ch;
                     const uint32_t grp = ge < (uint32_t)g_lo ? ge : (uint32_t)g_hi + (ge - g_lo);
-                    stage_slow(X, xs, m * ch, ch, grp, sub, v_base + 4 * (int64_t)grp, H, n_valid,
-                               s_hist[m], s_in[m]);
+                    if (kIlv) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const uint32_t idx = sub * 4 + e;            // value inside the group
+                            const int64_t vv = v_base + 4 * (int64_t)grp + (idx >> 1);
+                            float xv = 0.f;
+                            if (vv >= 0 && vv < n_valid)
+                                xv = vv < H ? s_hist[m][((int64_t)kHistFrames - H + vv) * 2 + (idx & 1)]
+                                            : s_in[m][(vv - H) * 2 + (idx & 1)];
+                            X[m * mstride + 8 * grp + idx] = xv;
+                        }
+                    } else {
+                        stage_slow(X, xs, m * ch, ch, grp, sub, v_base + 4 * (int64_t)grp, H,
+                                   n_valid, s_hist[m], s_in[m]);
+                    }
                 }
             }
         } else {
@@ -386,6 +414,7 @@ __global__ void __launch_bounds__(kThreads) conv_fast_kernel(ConvParams P, FastG
             }
         }
         __syncthreads();
+        RSB_PHASE(4)
 
         // ---- register-tiled banded product ----
         const uint32_t r0 = warp * kK;
@@ -400,9 +429,14 @@ __global__ void __launch_bounds__(kThreads) conv_fast_kernel(ConvParams P, FastG
 #pragma unroll
                 for (int c = 0; c < kC; ++c) acc[k][c] = make_float2(0.f, 0.f);
             // 32-bit shared addresses of this thread's 4 columns and 8 rows
+            // planar: column c of this thread is X row lane + 32c.  stereo: the thread owns the
+            // members lane and lane + 32 (columns L, R of each); xa[2s], xa[2s+1] address the
+            // two 16-byte halves (frames j..j+1 and j+2..j+3) of member s's chunk.
             uint32_t xa[kC], ga[kK];
 #pragma unroll
-            for (int c = 0; c < kC; ++c) xa[c] = smem_u32(X + (lane + 32 * c) * xs);
+            for (int c = 0; c < kC; ++c)
+                xa[c] = kIlv ? smem_u32(X + (lane + 32 * (c >> 1)) * mstride) + 16u * (c & 1)
+                             : smem_u32(X + (lane + 32 * c) * xs);
 #pragma unroll
             for (int k = 0; k < kK; ++k) ga[k] = smem_u32(G + (r0 + k) * xs);
 
@@ -416,7 +450,7 @@ __global__ void __launch_bounds__(kThreads) conv_fast_kernel(ConvParams P, FastG
             {
                 const uint32_t jb = chunk_byte(0);
 #pragma unroll
-                for (int c = 0; c < kC; ++c) xv[c] = lds128(xa[c] + jb);
+                for (int c = 0; c < kC; ++c) xv[c] = lds128(xa[c] + (kIlv ? 2u * jb : jb));
 #pragma unroll
                 for (int k = 0; k < kK; ++k) gv[k] = lds128(ga[k] + jb);
             }
@@ -426,15 +460,38 @@ __global__ void __launch_bounds__(kThreads) conv_fast_kernel(ConvParams P, FastG
                 const int snext = sidx + 1 < n_chunks ? sidx + 1 : sidx;
                 const uint32_t jb = chunk_byte(snext);
 #pragma unroll
-                for (int c = 0; c < kC; ++c) xn[c] = lds128(xa[c] + jb);
+                for (int c = 0; c < kC; ++c) xn[c] = lds128(xa[c] + (kIlv ? 2u * jb : jb));
 #pragma unroll
                 for (int k = 0; k < kK; ++k) gn[k] = lds128(ga[k] + jb);
-#pragma unroll
-                for (int k = 0; k < kK; ++k) {
+                // operand pairs (tap j, tap j+1) and (tap j+2, tap j+3) of every column, formed
+                // once per chunk: planar loads already are such pairs, interleaved stereo needs
+                // the even / odd elements of the member's two 16-byte halves
+                if (kIlv) {
+                    uint64_t x01[kC], x23[kC];
 #pragma unroll
                     for (int c = 0; c < kC; ++c) {
-                        ffma2(acc[k][c], make_float2(gv[k].x, gv[k].y), make_float2(xv[c].x, xv[c].y));
-                        ffma2(acc[k][c], make_float2(gv[k].z, gv[k].w), make_float2(xv[c].z, xv[c].w));
+                        const float4 lo = xv[c & ~1], hi = xv[c | 1];
+                        x01[c] = (c & 1) ? pack2(lo.y, lo.w) : pack2(lo.x, lo.z);
+                        x23[c] = (c & 1) ? pack2(hi.y, hi.w) : pack2(hi.x, hi.z);
+                    }
+#pragma unroll
+                    for (int k = 0; k < kK; ++k) {
+                        const uint64_t g01 = reinterpret_cast<const uint64_t *>(&gv[k])[0];
+                        const uint64_t g23 = reinterpret_cast<const uint64_t *>(&gv[k])[1];
+#pragma unroll
+                        for (int c = 0; c < kC; ++c) {
+                            ffma2_u64(acc[k][c], g01, x01[c]);
+                            ffma2_u64(acc[k][c], g23, x23[c]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < kK; ++k) {
+#pragma unroll
+                        for (int c = 0; c < kC; ++c) {
+                            ffma2(acc[k][c], make_float2(gv[k].x, gv[k].y), make_float2(xv[c].x, xv[c].y));
+                            ffma2(acc[k][c], make_float2(gv[k].z, gv[k].w), make_float2(xv[c].z, xv[c].w));
+                        }
                     }
                 }
 #pragma unroll
@@ -443,10 +500,11 @@ __global__ void __launch_bounds__(kThreads) conv_fast_kernel(ConvParams P, FastG
                 for (int k = 0; k < kK; ++k) gv[k] = gn[k];
             }
 
+            RSB_PHASE(5)
             // ---- store: out[stream][(o_start + row) * ch + c] ----
 #pragma unroll
             for (int c = 0; c < kC; ++c) {
-                const uint32_t col = lane + 32u * c;
+                const uint32_t col = kIlv ? 2u * (lane + 32u * (c >> 1)) + (c & 1) : lane + 32u * c;
                 if (col < n_cols) {
                     const uint32_t m = col / ch, cc = col - m * ch;
                     float *out = s_out[m];
@@ -460,25 +518,39 @@ __global__ void __launch_bounds__(kThreads) conv_fast_kernel(ConvParams P, FastG
                 }
             }
         }
+        RSB_PHASE(6)
     }
+    if (prof) {
+        for (int i = 0; i < 8; ++i) atomicAdd(&g_phase_cycles[i], pc[i]);
+    }
+#undef RSB_PHASE
 }
 
 }  // namespace
+
+void fast_phase_profile(int enable, unsigned long long *out8) {
+    if (out8) cudaMemcpyFromSymbol(out8, g_phase_cycles, sizeof(unsigned long long) * 8);
+    unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_phase_cycles, zero, sizeof(zero));
+    cudaMemcpyToSymbol(g_phase_enabled, &enable, sizeof(int));
+}
 
 bool fast_supported(uint32_t channels, uint32_t taps, double ratio) {
     if (channels == 0 || channels > (uint32_t)kNC) return false;
     if (taps != 16 && taps != 32 && taps != 64 && taps != 128) return false;
     if (!(ratio > 0.0) || ratio > 8.0) return false;
-    return fast_smem_bytes(fast_geom(taps, ratio)) <= 200u * 1024u;
+    return fast_smem_bytes(fast_geom(taps, ratio), channels) <= 200u * 1024u;
 }
 
 uint32_t fast_streams_per_group(uint32_t channels, uint32_t, double) { return kNC / channels; }
+
+uint32_t fast_row_stride(uint32_t taps, double ratio) { return fast_geom(taps, ratio).xs; }
 
 void launch_conv_fast(const ConvParams &p, double ratio, uint32_t max_items, int sm_count,
                       cudaStream_t stream) {
     if (max_items == 0) return;
     const FastGeom geo = fast_geom(p.taps, ratio);
-    const size_t smem = fast_smem_bytes(geo);
+    const size_t smem = fast_smem_bytes(geo, p.channels);
     auto launch = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int per_sm = 1;

@@ -97,10 +97,15 @@ void launch_plan(UnitDev *units, uint32_t n_units, StreamStateDev st, double rat
 // ---------------------------------------------------------------------------
 // tile records
 // ---------------------------------------------------------------------------
-// One warp per tile: lane 0 finds the tile's first segment by binary search, then every lane
-// expands one output frame of the tile (exact position -> offset, phase, frac).
+// One warp per tile: lane 0 finds the tile's first segment by binary search, every lane
+// expands one output frame of the tile (exact position -> offset, phase, frac), and -- for the
+// fast kernel -- the warp builds the tile's banded filter matrix G[kTileOut][gs] in global
+// memory:  G[k][(v_k - v_base) + t] = c[phase1_k][t]*(1-frac_k) + c[phase2_k][t]*frac_k, zero
+// elsewhere.  Every stream group that processes the tile fetches it with one TMA bulk copy.
+template <int TAPS>
 __global__ void tile_index_kernel(const UnitDev *units, const PlanSeg *segs, TileRec *tiles,
-                                  PlanEntry *entries) {
+                                  PlanEntry *entries, const float *coeffs, float *gtiles,
+                                  uint32_t gs) {
     const uint32_t u = blockIdx.x;
     const UnitDev &U = units[u];
     const uint32_t n_tiles = U.n_tiles;
@@ -117,14 +122,6 @@ __global__ void tile_index_kernel(const UnitDev *units, const PlanSeg *segs, Til
     }
     const uint64_t left = U.total_out - o0;
     const uint32_t n_out = (uint32_t)(left < kTileOut ? left : kTileOut);
-    if (lane == 0) {
-        TileRec r;
-        r.unit = u;
-        r.o_start = o0;
-        r.seg = U.seg_off + lo;
-        r.n_out = n_out;
-        tiles[U.tile_off + t] = r;
-    }
     PlanEntry e;
     e.v = 0; e.phase1 = 0; e.frac = 0.f; e.off = 0;
     if (lane < n_out) {
@@ -139,18 +136,91 @@ __global__ void tile_index_kernel(const UnitDev *units, const PlanSeg *segs, Til
         e.frac = pp.frac;
         e.off = pp.off;
     }
-    entries[(size_t)(U.tile_off + t) * kTileOut + lane] = e;
+    const size_t tile = (size_t)U.tile_off + t;
+    entries[tile * kTileOut + lane] = e;
+    // window: starts at the first frame needed, aligned so that (v_base - H) % 4 == 0
+    const int32_t H = (int32_t)U.hist_len0;
+    const int32_t v_first = __shfl_sync(0xffffffffu, e.v, 0);
+    const int32_t v_last = __shfl_sync(0xffffffffu, e.v, (int)n_out - 1);
+    const int32_t v_base = v_first - ((((v_first - H) % 4) + 4) % 4);
+    const uint32_t winp = (uint32_t)((v_last - v_base) + TAPS + 3) & ~3u;
+    if (lane == 0) {
+        TileRec r;
+        r.unit = u;
+        r.o_start = o0;
+        r.seg = U.seg_off + lo;
+        r.n_out = n_out;
+        r.v_base = v_base;
+        r.winp = winp;
+        r.pad0 = r.pad1 = 0;
+        tiles[tile] = r;
+    }
+    if (gtiles == nullptr) return;
+    // ---- banded rows ----
+    constexpr int kQ = TAPS / 4;                       // float4 per coefficient row
+    float4 *grow = reinterpret_cast<float4 *>(gtiles + tile * kTileOut * gs);
+    const uint32_t gq = gs >> 2;                       // float4 per G row
+    for (uint32_t k = 0; k < kTileOut; ++k, grow += gq) {
+        const uint32_t p1 = __shfl_sync(0xffffffffu, e.phase1, (int)k);
+        const float fr = __shfl_sync(0xffffffffu, e.frac, (int)k);
+        const int32_t vk = __shfl_sync(0xffffffffu, e.v, (int)k);
+        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < n_out && lane < kQ) {
+            const uint32_t p2 = p1 + 1 < kPhases - 1 ? p1 + 1 : kPhases - 1;
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(coeffs + (size_t)p1 * TAPS) + lane);
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(coeffs + (size_t)p2 * TAPS) + lane);
+            const float omf = __fsub_rn(1.0f, fr);
+            h.x = __fmaf_rn(b.x, fr, __fmul_rn(a.x, omf));
+            h.y = __fmaf_rn(b.y, fr, __fmul_rn(a.y, omf));
+            h.z = __fmaf_rn(b.z, fr, __fmul_rn(a.z, omf));
+            h.w = __fmaf_rn(b.w, fr, __fmul_rn(a.w, omf));
+        }
+        const int d = k < n_out ? (int)(vk - v_base) : 0;
+        const int r = d & 3, q0 = d >> 2;
+        // output float4 q holds taps 4*(q - q0) - r .. +3: parts of h[q - q0 - 1] and h[q - q0]
+        for (uint32_t qb = 0; qb < gq; qb += 32) {
+            const int q = (int)(qb + lane);
+            const int src = q - q0;                    // coefficient float4 index of the upper part
+            const float4 hi4 = make_float4(__shfl_sync(0xffffffffu, h.x, src & 31),
+                                           __shfl_sync(0xffffffffu, h.y, src & 31),
+                                           __shfl_sync(0xffffffffu, h.z, src & 31),
+                                           __shfl_sync(0xffffffffu, h.w, src & 31));
+            const float4 lo4 = make_float4(__shfl_sync(0xffffffffu, h.x, (src - 1) & 31),
+                                           __shfl_sync(0xffffffffu, h.y, (src - 1) & 31),
+                                           __shfl_sync(0xffffffffu, h.z, (src - 1) & 31),
+                                           __shfl_sync(0xffffffffu, h.w, (src - 1) & 31));
+            const bool hi_ok = src >= 0 && src < kQ, lo_ok = src - 1 >= 0 && src - 1 < kQ;
+            const float hv[4] = {hi_ok ? hi4.x : 0.f, hi_ok ? hi4.y : 0.f, hi_ok ? hi4.z : 0.f,
+                                 hi_ok ? hi4.w : 0.f};
+            const float lv[4] = {lo_ok ? lo4.x : 0.f, lo_ok ? lo4.y : 0.f, lo_ok ? lo4.z : 0.f,
+                                 lo_ok ? lo4.w : 0.f};
+            float o4[4];
+#pragma unroll
+            for (int el = 0; el < 4; ++el) {
+                // tap = 4*src + el - r
+                const int idx = el - r;                // index into hv (>= 0) or lv (< 0)
+                o4[el] = idx >= 0 ? hv[idx & 3] : lv[(idx + 4) & 3];
+            }
+            if ((uint32_t)q < gq) grow[q] = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        }
+    }
 }
 
 void launch_tiles(const UnitDev *units, uint32_t n_units, const PlanSeg *segs, TileRec *tiles,
-                  PlanEntry *entries, uint32_t max_tiles_per_unit, cudaStream_t stream) {
+                  PlanEntry *entries, uint32_t max_tiles_per_unit, uint32_t taps,
+                  const float *coeffs, float *gtiles, uint32_t gs, cudaStream_t stream) {
     if (n_units == 0 || max_tiles_per_unit == 0) return;
     const uint32_t threads = 128, per_cta = threads / 32;
     // gridDim.y is limited to 65535: units in x, tile chunks in y
     uint32_t chunks = (max_tiles_per_unit + per_cta - 1) / per_cta;
     if (chunks > 65535u) chunks = 65535u;   // callers bound tiles per unit below 65535*4
     dim3 grid(n_units, chunks);
-    tile_index_kernel<<<grid, threads, 0, stream>>>(units, segs, tiles, entries);
+    switch (taps) {
+        case 16: tile_index_kernel<16><<<grid, threads, 0, stream>>>(units, segs, tiles, entries, coeffs, gtiles, gs); break;
+        case 32: tile_index_kernel<32><<<grid, threads, 0, stream>>>(units, segs, tiles, entries, coeffs, gtiles, gs); break;
+        case 64: tile_index_kernel<64><<<grid, threads, 0, stream>>>(units, segs, tiles, entries, coeffs, gtiles, gs); break;
+        default: tile_index_kernel<128><<<grid, threads, 0, stream>>>(units, segs, tiles, entries, coeffs, gtiles, gs); break;
+    }
 }
 
 // ---------------------------------------------------------------------------

@@ -14,6 +14,7 @@ struct ConvParams {
     const PlanSeg *segs;
     const TileRec *tiles;
     const PlanEntry *entries;     // [tile][kTileOut]
+    const float *gtiles;          // [tile][kTileOut][gs] banded filter rows (fast kernel)
     const uint32_t *tile_total;   // device counter written by the plan kernel
     const float *coeffs;          // [1024][taps]
     StreamStateDev st;
@@ -30,15 +31,20 @@ void launch_plan(UnitDev *units, uint32_t n_units, StreamStateDev st, double rat
                  PlanSeg *segs, CallCounts *calls, uint32_t tile_out, uint32_t *tile_total,
                  cudaStream_t stream);
 // tile records: binary search of each tile's first segment
+// (gtiles != nullptr: also builds the fast kernel's banded filter tiles [tile][kTileOut][gs])
 void launch_tiles(const UnitDev *units, uint32_t n_units, const PlanSeg *segs, TileRec *tiles,
-                  PlanEntry *entries, uint32_t max_tiles_per_unit, cudaStream_t stream);
+                  PlanEntry *entries, uint32_t max_tiles_per_unit, uint32_t taps,
+                  const float *coeffs, float *gtiles, uint32_t gs, cudaStream_t stream);
 // exact (AVX-512 order) convolution
 void launch_conv_exact(const ConvParams &p, uint32_t max_items, int sm_count, cudaStream_t stream);
 // fast convolution (fir_fast.cu); returns false when the configuration is unsupported
 bool fast_supported(uint32_t channels, uint32_t taps, double ratio);
 uint32_t fast_streams_per_group(uint32_t channels, uint32_t taps, double ratio);
+uint32_t fast_row_stride(uint32_t taps, double ratio);   // gs: floats per G / X row
 void launch_conv_fast(const ConvParams &p, double ratio, uint32_t max_items, int sm_count,
                       cudaStream_t stream);
+// debug: returns and clears the fast kernel's per-phase cycle counters, sets the enable flag
+void fast_phase_profile(int enable, unsigned long long *out8);
 // state write-back: new history tail, position, hist_len (one CTA per job)
 void launch_update(const UnitDev *units, const JobDev *jobs, uint32_t n_jobs, StreamStateDev st,
                    uint32_t channels, cudaStream_t stream);

@@ -97,6 +97,21 @@ RSB_HD PhasePoint phase_point(double position) {
     return r;
 }
 
+// ceil(num / den) for 0 < num, den < 2^53.  A 64-bit integer division costs ~100 instructions
+// on the GPU (no hardware divider) and sits on the planner's serial critical path, so the
+// quotient is estimated in f64 and corrected exactly with integer multiplies.
+RSB_HD int64_t ceil_div_53(int64_t num, int64_t den) {
+#if defined(__CUDA_ARCH__)
+    int64_t q = (int64_t)__ddiv_rn((double)num, (double)den);   // floor estimate, off by <= 1
+#else
+    int64_t q = (int64_t)((double)num / (double)den);
+#endif
+    int64_t rem = num - q * den;
+    if (rem < 0) { q -= 1; rem += den; }
+    if (rem >= den) { q += 1; rem -= den; }
+    return rem > 0 ? q + 1 : q;
+}
+
 RSB_HD bool same_binade(int64_t a, int64_t b) {
     // equal biased exponents, and not zero/subnormal
     return ((a ^ b) >> 52) == 0 && ((a >> 52) & 0x7ff) != 0;
@@ -129,14 +144,14 @@ RSB_HD uint32_t plan_call_outputs(double &pos, double ratio, uint32_t available,
                 const int64_t mant_lim = (int64_t)1 << 53;
                 const int64_t B = (b1 & (((int64_t)1 << 52) - 1)) | ((int64_t)1 << 52);
                 // elements j with B + j*D < 2^53 stay below 2^(e+1)
-                int64_t n = (mant_lim - B + D - 1) / D;
+                int64_t n = ceil_div_53(mant_lim - B, D);
                 // elements with position < L
                 const int e = (int)((b1 >> 52) & 0x7ff) - 1023;
                 if (L < bits2d((int64_t)(e + 1 + 1023) << 52)) {
                     // L / u is an exact integer < 2^53
                     const double scale = bits2d((int64_t)(52 - e + 1023) << 52);
                     const int64_t LQ = (int64_t)(L * scale);
-                    const int64_t nL = (LQ - B + D - 1) / D;   // LQ > B because p1 < L
+                    const int64_t nL = ceil_div_53(LQ - B, D);   // LQ > B because p1 < L
                     if (nL < n) n = nL;
                 }
                 const int64_t room = (int64_t)(cap - count - 1);
