@@ -68,8 +68,10 @@ enum rsb_kernel { RSB_KERNEL_AUTO = 0, RSB_KERNEL_EXACT = 1, RSB_KERNEL_FAST = 2
 
 enum rsb_flags {
     RSB_FLAG_NONE = 0,
-    RSB_FLAG_ASYNC = 1,        /* device memspace only: return after enqueueing; counts are
-                                  written by rsb_fir_sync() */
+    RSB_FLAG_ASYNC = 1,        /* device memspace only: return after enqueueing.  The count
+                                  arrays are written by rsb_fir_sync() or by the second
+                                  submit after this one (two submits may be in flight), so
+                                  they must stay valid until then */
     RSB_FLAG_RECORD_CALLS = 2, /* keep per-call (consumed, produced) for rsb_fir_last_call_counts */
     RSB_FLAG_KEEP_PLAN = 4     /* keep the device plan for rsb_fir_last_plan */
 };

@@ -89,6 +89,21 @@ struct Pending {
     bool check_capacity = false;
 };
 
+// Everything one submit needs on the device and in pinned memory.  Two of them alternate so
+// that the (serial) plan of submit i+1 can run on the plan stream while the convolution of
+// submit i is still running on the main stream.
+struct Workspace {
+    DevBuf d_units, d_jobs, d_segs, d_calls, d_tiles, d_entries, d_gtiles, d_counter;
+    PinBuf h_units, h_jobs, h_units_back, h_calls_back;
+    std::vector<uint32_t> job_unit;          // unit of each job of the batch
+    std::vector<uint64_t> job_out_capacity;  // frames
+    uint32_t n_units = 0;
+    bool has_calls = false, has_plan = false;
+    Pending pending;
+    cudaEvent_t ev_plan = nullptr;   // plan + tile kernels and result read-back done
+    cudaEvent_t ev_done = nullptr;   // convolution + state update done
+};
+
 }  // namespace
 
 struct rsb_fir {
@@ -106,21 +121,17 @@ struct rsb_fir {
     std::vector<uint8_t> hist_sel;  // which history buffer of a stream is live (host mirror)
     uint64_t next_cohort = 1;
     uint64_t launches = 0;
-    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_done = nullptr;
+    cudaStream_t plan_stream = nullptr;   // plan / tile kernels and the state scalars
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_sync = nullptr;
     // ring of event pairs bracketing the convolution kernel of the most recent batches
     static constexpr int kConvRing = 64;
     cudaEvent_t ev_conv[kConvRing][2] = {};
     uint64_t conv_batches = 0;
 
-    // workspace of the (single) in-flight submit
-    DevBuf d_units, d_jobs, d_segs, d_calls, d_tiles, d_entries, d_gtiles, d_counter, d_stage_in,
-        d_stage_out, d_dbg;
-    PinBuf h_units, h_jobs, h_units_back, h_calls_back;
-    std::vector<uint32_t> job_unit;          // unit of each job of the last batch
-    std::vector<uint64_t> job_out_capacity;  // frames
-    uint32_t last_n_units = 0;
-    bool last_has_calls = false, last_has_plan = false;
-    Pending pending;
+    Workspace ws[2];
+    uint64_t submits = 0;             // ws[submits & 1] is the next one to use
+    DevBuf d_stage_in, d_stage_out, d_dbg;   // host-memspace staging (those calls are synchronous)
+    Workspace &last_ws() { return ws[(submits + 1) & 1]; }
 };
 
 namespace {
@@ -154,12 +165,12 @@ uint32_t segs_per_call_bound(double ratio) {
     return (uint32_t)(2 * (14 - lowest) + 6);
 }
 
-int finalize_pending(rsb_fir *h) {
-    if (!h->pending.active) return RSB_OK;
-    Pending p = h->pending;
-    h->pending.active = false;
-    RSB_CUDA(cudaEventSynchronize(h->ev_done));
-    const UnitDev *ub = h->h_units_back.as<UnitDev>();
+int finalize_pending(rsb_fir *h, Workspace &W) {
+    if (!W.pending.active) return RSB_OK;
+    Pending p = W.pending;
+    W.pending.active = false;
+    RSB_CUDA(cudaEventSynchronize(W.ev_plan));
+    const UnitDev *ub = W.h_units_back.as<UnitDev>();
     int rc = RSB_OK;
     for (uint32_t u = 0; u < p.n_units; ++u) {
         if (ub[u].status != 0)
@@ -168,11 +179,11 @@ int finalize_pending(rsb_fir *h) {
     }
     const uint32_t ch = h->channels;
     for (uint32_t i = 0; i < p.n; ++i) {
-        const UnitDev &U = ub[h->job_unit[i]];
+        const UnitDev &U = ub[W.job_unit[i]];
         if (p.consumed) p.consumed[i] = (size_t)U.total_copied * ch;
         if (p.produced) p.produced[i] = (size_t)U.total_out * ch;
         if (p.n_calls) p.n_calls[i] = U.n_calls;
-        if (p.check_capacity && U.total_out > h->job_out_capacity[i] && rc == RSB_OK)
+        if (p.check_capacity && U.total_out > W.job_out_capacity[i] && rc == RSB_OK)
             rc = fail(RSB_ERR_OUTPUT_CAPACITY, "output buffer of job " + std::to_string(i) +
                                                    " too small: produced " +
                                                    std::to_string(U.total_out) + " frames");
@@ -180,12 +191,22 @@ int finalize_pending(rsb_fir *h) {
     return rc;
 }
 
+int finalize_all(rsb_fir *h) {
+    // older submit first
+    int rc = finalize_pending(h, h->ws[h->submits & 1]);
+    int rc2 = finalize_pending(h, h->ws[(h->submits + 1) & 1]);
+    return rc != RSB_OK ? rc : rc2;
+}
+
 // Core: runs `jobs` (already validated) on the device.
 int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int memspace,
               uint32_t flags, size_t *consumed, size_t *produced, uint32_t *n_calls_out) {
-    int rc = finalize_pending(h);
-    if (rc != RSB_OK) return rc;
     RSB_CUDA(cudaSetDevice(h->device));
+    Workspace &W = h->ws[h->submits & 1];
+    // this workspace was last used two submits ago: collect its counts, wait for its kernels
+    int rc = finalize_pending(h, W);
+    if (rc != RSB_OK) return rc;
+    RSB_CUDA(cudaEventSynchronize(W.ev_done));
     const uint32_t n = (uint32_t)jobs.size();
     const uint32_t ch = h->channels;
     if (n == 0) return RSB_OK;
@@ -194,8 +215,8 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     std::map<UnitKey, uint32_t> key_to_unit;
     std::vector<UnitKey> unit_keys;
     std::vector<uint32_t> unit_count;
-    h->job_unit.assign(n, 0);
-    h->job_out_capacity.assign(n, 0);
+    W.job_unit.assign(n, 0);
+    W.job_out_capacity.assign(n, 0);
     for (uint32_t i = 0; i < n; ++i) {
         UnitKey k{h->cohort[jobs[i].stream], jobs[i].total_frames,
                   single ? 0u : jobs[i].call_frames, jobs[i].cap_frames, single ? 1u : 0u};
@@ -209,8 +230,8 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
         } else {
             u = it->second;
         }
-        h->job_unit[i] = u;
-        h->job_out_capacity[i] = jobs[i].out_capacity;
+        W.job_unit[i] = u;
+        W.job_out_capacity[i] = jobs[i].out_capacity;
         unit_count[u] += 1;
     }
     const uint32_t n_units = (uint32_t)unit_keys.size();
@@ -244,10 +265,10 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     // ---- size the workspace ----
     const uint32_t spc = segs_per_call_bound(h->ratio);
     const bool rec_calls = (flags & RSB_FLAG_RECORD_CALLS) != 0;
-    RSB_CUDA(h->h_units.reserve(sizeof(UnitDev) * n_units));
-    RSB_CUDA(h->h_units_back.reserve(sizeof(UnitDev) * n_units));
-    RSB_CUDA(h->h_jobs.reserve(sizeof(JobDev) * n));
-    UnitDev *hu = h->h_units.as<UnitDev>();
+    RSB_CUDA(W.h_units.reserve(sizeof(UnitDev) * n_units));
+    RSB_CUDA(W.h_units_back.reserve(sizeof(UnitDev) * n_units));
+    RSB_CUDA(W.h_jobs.reserve(sizeof(JobDev) * n));
+    UnitDev *hu = W.h_units.as<UnitDev>();
     uint64_t seg_total = 0, call_total = 0, tile_total = 0, max_tiles_unit = 0;
     uint32_t member_off = 0, max_groups = 1;
     for (uint32_t u = 0; u < n_units; ++u) {
@@ -324,12 +345,12 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     }
 
     // jobs are stored grouped by unit: members of U are hj[U.member_off .. +U.n_members)
-    JobDev *hj = h->h_jobs.as<JobDev>();
+    JobDev *hj = W.h_jobs.as<JobDev>();
     const size_t hist_stride = (size_t)rsb::kHistFrames * ch;
     for (uint32_t i = 0; i < n; ++i) {
         JobDev J;
         J.stream = jobs[i].stream;
-        J.unit = h->job_unit[i];
+        J.unit = W.job_unit[i];
         J.out_capacity = jobs[i].out_capacity;
         if (host_mem) {
             J.in = h->d_stage_in.as<float>() + in_off[i];
@@ -347,24 +368,25 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
         U.n_members += 1;
     }
 
-    RSB_CUDA(h->d_units.reserve(sizeof(UnitDev) * n_units));
-    RSB_CUDA(h->d_jobs.reserve(sizeof(JobDev) * n));
-    RSB_CUDA(h->d_segs.reserve(sizeof(rsb::PlanSeg) * seg_total));
-    RSB_CUDA(h->d_tiles.reserve(sizeof(rsb::TileRec) * tile_total));
-    RSB_CUDA(h->d_entries.reserve(sizeof(rsb::PlanEntry) * rsb::kTileOut * tile_total));
+    RSB_CUDA(W.d_units.reserve(sizeof(UnitDev) * n_units));
+    RSB_CUDA(W.d_jobs.reserve(sizeof(JobDev) * n));
+    RSB_CUDA(W.d_segs.reserve(sizeof(rsb::PlanSeg) * seg_total));
+    RSB_CUDA(W.d_tiles.reserve(sizeof(rsb::TileRec) * tile_total));
+    RSB_CUDA(W.d_entries.reserve(sizeof(rsb::PlanEntry) * rsb::kTileOut * tile_total));
     const uint32_t gs = use_fast ? rsb::fast_row_stride(h->taps, h->ratio) : 0;
     if (use_fast)
-        RSB_CUDA(h->d_gtiles.reserve(sizeof(float) * rsb::kTileOut * gs * tile_total));
-    RSB_CUDA(h->d_counter.reserve(sizeof(uint32_t) * 4));
+        RSB_CUDA(W.d_gtiles.reserve(sizeof(float) * rsb::kTileOut * gs * tile_total));
+    RSB_CUDA(W.d_counter.reserve(sizeof(uint32_t) * 4));
     if (rec_calls) {
-        RSB_CUDA(h->d_calls.reserve(sizeof(rsb::CallCounts) * std::max<uint64_t>(call_total, 1)));
-        RSB_CUDA(h->h_calls_back.reserve(sizeof(rsb::CallCounts) * std::max<uint64_t>(call_total, 1)));
+        RSB_CUDA(W.d_calls.reserve(sizeof(rsb::CallCounts) * std::max<uint64_t>(call_total, 1)));
+        RSB_CUDA(W.h_calls_back.reserve(sizeof(rsb::CallCounts) * std::max<uint64_t>(call_total, 1)));
     }
 
-    cudaStream_t s = h->stream;
-    RSB_CUDA(cudaMemcpyAsync(h->d_units.p, hu, sizeof(UnitDev) * n_units, cudaMemcpyHostToDevice, s));
-    RSB_CUDA(cudaMemcpyAsync(h->d_jobs.p, hj, sizeof(JobDev) * n, cudaMemcpyHostToDevice, s));
-    RSB_CUDA(cudaMemsetAsync(h->d_counter.p, 0, sizeof(uint32_t) * 4, s));
+    cudaStream_t s = h->stream;        // convolution, history update, data copies
+    cudaStream_t sp = h->plan_stream;  // plan, tiles, state scalars, result read-back
+    RSB_CUDA(cudaMemcpyAsync(W.d_units.p, hu, sizeof(UnitDev) * n_units, cudaMemcpyHostToDevice, sp));
+    RSB_CUDA(cudaMemcpyAsync(W.d_jobs.p, hj, sizeof(JobDev) * n, cudaMemcpyHostToDevice, sp));
+    RSB_CUDA(cudaMemsetAsync(W.d_counter.p, 0, sizeof(uint32_t) * 4, sp));
     if (host_mem) {
         for (uint32_t i = 0; i < n; ++i)
             if (in_vals[i])
@@ -373,21 +395,31 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     }
 
     // ---- launch ----
-    rsb::launch_plan(h->d_units.as<UnitDev>(), n_units, h->st, h->ratio, h->taps,
-                     h->d_segs.as<rsb::PlanSeg>(), h->d_calls.as<rsb::CallCounts>(), tile_out,
-                     h->d_counter.as<uint32_t>(), s);
-    rsb::launch_tiles(h->d_units.as<UnitDev>(), n_units, h->d_segs.as<rsb::PlanSeg>(),
-                      h->d_tiles.as<rsb::TileRec>(), h->d_entries.as<rsb::PlanEntry>(),
+    rsb::launch_plan(W.d_units.as<UnitDev>(), n_units, h->st, h->ratio, h->taps,
+                     W.d_segs.as<rsb::PlanSeg>(), W.d_calls.as<rsb::CallCounts>(), tile_out,
+                     W.d_counter.as<uint32_t>(), sp);
+    rsb::launch_tiles(W.d_units.as<UnitDev>(), n_units, W.d_segs.as<rsb::PlanSeg>(),
+                      W.d_tiles.as<rsb::TileRec>(), W.d_entries.as<rsb::PlanEntry>(),
                       (uint32_t)max_tiles_unit, h->taps, h->d_coeffs,
-                      use_fast ? h->d_gtiles.as<float>() : nullptr, gs, s);
+                      use_fast ? W.d_gtiles.as<float>() : nullptr, gs, sp);
+    // the streams' scalar state (position, buffered frames) moves on the plan stream, so the
+    // next submit can be planned while this one is still convolving
+    rsb::launch_state_scalars(W.d_units.as<UnitDev>(), W.d_jobs.as<JobDev>(), n, h->st, sp);
+    RSB_CUDA(cudaMemcpyAsync(W.h_units_back.p, W.d_units.p, sizeof(UnitDev) * n_units,
+                             cudaMemcpyDeviceToHost, sp));
+    if (rec_calls && call_total)
+        RSB_CUDA(cudaMemcpyAsync(W.h_calls_back.p, W.d_calls.p,
+                                 sizeof(rsb::CallCounts) * call_total, cudaMemcpyDeviceToHost, sp));
+    RSB_CUDA(cudaEventRecord(W.ev_plan, sp));
+    RSB_CUDA(cudaStreamWaitEvent(s, W.ev_plan, 0));
     rsb::ConvParams P;
-    P.units = h->d_units.as<UnitDev>();
-    P.jobs = h->d_jobs.as<JobDev>();
-    P.segs = h->d_segs.as<rsb::PlanSeg>();
-    P.tiles = h->d_tiles.as<rsb::TileRec>();
-    P.entries = h->d_entries.as<rsb::PlanEntry>();
-    P.gtiles = h->d_gtiles.as<float>();
-    P.tile_total = h->d_counter.as<uint32_t>();
+    P.units = W.d_units.as<UnitDev>();
+    P.jobs = W.d_jobs.as<JobDev>();
+    P.segs = W.d_segs.as<rsb::PlanSeg>();
+    P.tiles = W.d_tiles.as<rsb::TileRec>();
+    P.entries = W.d_entries.as<rsb::PlanEntry>();
+    P.gtiles = W.d_gtiles.as<float>();
+    P.tile_total = W.d_counter.as<uint32_t>();
     P.coeffs = h->d_coeffs;
     P.st = h->st;
     P.channels = ch;
@@ -403,43 +435,39 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
         rsb::launch_conv_exact(P, max_items, h->sm_count, s);
     RSB_CUDA(cudaEventRecord(h->ev_conv[ring][1], s));
     h->conv_batches += 1;
-    rsb::launch_update(h->d_units.as<UnitDev>(), h->d_jobs.as<JobDev>(), n, h->st, ch, s);
-    h->launches += 4;
+    rsb::launch_update(W.d_units.as<UnitDev>(), W.d_jobs.as<JobDev>(), n, h->st, ch, s);
+    h->launches += 5;
     RSB_CUDA(cudaGetLastError());
-    RSB_CUDA(cudaMemcpyAsync(h->h_units_back.p, h->d_units.p, sizeof(UnitDev) * n_units,
-                             cudaMemcpyDeviceToHost, s));
-    if (rec_calls && call_total)
-        RSB_CUDA(cudaMemcpyAsync(h->h_calls_back.p, h->d_calls.p,
-                                 sizeof(rsb::CallCounts) * call_total, cudaMemcpyDeviceToHost, s));
-    RSB_CUDA(cudaEventRecord(h->ev_done, s));
+    RSB_CUDA(cudaEventRecord(W.ev_done, s));
+    h->submits += 1;
 
     // cohorts: every unit becomes a fresh cohort (same state + same calls => same new state)
     {
         std::vector<uint64_t> new_id(n_units);
         for (uint32_t u = 0; u < n_units; ++u) new_id[u] = h->next_cohort++;
         for (uint32_t i = 0; i < n; ++i) {
-            h->cohort[jobs[i].stream] = new_id[h->job_unit[i]];
+            h->cohort[jobs[i].stream] = new_id[W.job_unit[i]];
             h->hist_sel[jobs[i].stream] ^= 1u;   // the update kernel wrote the other buffer
         }
     }
-    h->last_n_units = n_units;
-    h->last_has_calls = rec_calls;
-    h->last_has_plan = (flags & RSB_FLAG_KEEP_PLAN) != 0;
+    W.n_units = n_units;
+    W.has_calls = rec_calls;
+    W.has_plan = (flags & RSB_FLAG_KEEP_PLAN) != 0;
 
-    h->pending.active = true;
-    h->pending.n = n;
-    h->pending.n_units = n_units;
-    h->pending.consumed = consumed;
-    h->pending.produced = produced;
-    h->pending.n_calls = n_calls_out;
-    h->pending.check_capacity = !single;
+    W.pending.active = true;
+    W.pending.n = n;
+    W.pending.n_units = n_units;
+    W.pending.consumed = consumed;
+    W.pending.produced = produced;
+    W.pending.n_calls = n_calls_out;
+    W.pending.check_capacity = !single;
     if ((flags & RSB_FLAG_ASYNC) && !host_mem) return RSB_OK;
 
-    rc = finalize_pending(h);
+    rc = finalize_pending(h, W);
     if (host_mem) {
-        const UnitDev *ub = h->h_units_back.as<UnitDev>();
+        const UnitDev *ub = W.h_units_back.as<UnitDev>();
         for (uint32_t i = 0; i < n; ++i) {
-            const UnitDev &U = ub[h->job_unit[i]];
+            const UnitDev &U = ub[W.job_unit[i]];
             const uint64_t frames = std::min<uint64_t>(U.total_out, jobs[i].out_capacity);
             if (frames)
                 RSB_CUDA(cudaMemcpyAsync(jobs[i].out, h->d_stage_out.as<float>() + out_off[i],
@@ -533,9 +561,14 @@ int rsb_fir_create(rsb_fir **out, int device, uint32_t n_streams, uint32_t chann
     h->hist_sel.assign(n_streams, 0);
 
     RSB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    RSB_CUDA(cudaStreamCreateWithFlags(&h->plan_stream, cudaStreamNonBlocking));
     RSB_CUDA(cudaEventCreate(&h->ev_t0));
     RSB_CUDA(cudaEventCreate(&h->ev_t1));
-    RSB_CUDA(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+    RSB_CUDA(cudaEventCreateWithFlags(&h->ev_sync, cudaEventDisableTiming));
+    for (Workspace &W : h->ws) {
+        RSB_CUDA(cudaEventCreateWithFlags(&W.ev_plan, cudaEventDisableTiming));
+        RSB_CUDA(cudaEventCreateWithFlags(&W.ev_done, cudaEventDisableTiming));
+    }
     for (int i = 0; i < rsb_fir::kConvRing; ++i) {
         RSB_CUDA(cudaEventCreate(&h->ev_conv[i][0]));
         RSB_CUDA(cudaEventCreate(&h->ev_conv[i][1]));
@@ -562,23 +595,29 @@ void rsb_fir_destroy(rsb_fir *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->plan_stream) cudaStreamSynchronize(h->plan_stream);
     cudaFree(h->d_coeffs);
     cudaFree(h->st.position);
     cudaFree(h->st.hist_len);
     cudaFree(h->st.hist[0]);
     cudaFree(h->st.hist[1]);
-    for (DevBuf *b : {&h->d_units, &h->d_jobs, &h->d_segs, &h->d_calls, &h->d_tiles, &h->d_entries,
-                      &h->d_gtiles, &h->d_counter, &h->d_stage_in, &h->d_stage_out, &h->d_dbg})
-        b->release();
-    for (PinBuf *b : {&h->h_units, &h->h_jobs, &h->h_units_back, &h->h_calls_back})
-        b->release();
+    for (Workspace &W : h->ws) {
+        for (DevBuf *b : {&W.d_units, &W.d_jobs, &W.d_segs, &W.d_calls, &W.d_tiles, &W.d_entries,
+                          &W.d_gtiles, &W.d_counter})
+            b->release();
+        for (PinBuf *b : {&W.h_units, &W.h_jobs, &W.h_units_back, &W.h_calls_back}) b->release();
+        if (W.ev_plan) cudaEventDestroy(W.ev_plan);
+        if (W.ev_done) cudaEventDestroy(W.ev_done);
+    }
+    for (DevBuf *b : {&h->d_stage_in, &h->d_stage_out, &h->d_dbg}) b->release();
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);
     if (h->ev_t1) cudaEventDestroy(h->ev_t1);
-    if (h->ev_done) cudaEventDestroy(h->ev_done);
+    if (h->ev_sync) cudaEventDestroy(h->ev_sync);
     for (int i = 0; i < rsb_fir::kConvRing; ++i)
         for (int j = 0; j < 2; ++j)
             if (h->ev_conv[i][j]) cudaEventDestroy(h->ev_conv[i][j]);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->plan_stream) cudaStreamDestroy(h->plan_stream);
     delete h;
 }
 
@@ -610,15 +649,14 @@ size_t rsb_fir_delay(const rsb_fir *h) { return h ? h->taps / 2 : 0; }   // :630
 
 int rsb_fir_reset(rsb_fir *h, int64_t stream) {
     if (check_handle(h)) return RSB_ERR_INVALID_ARGUMENT;
-    int rc = finalize_pending(h);
-    if (rc != RSB_OK) return rc;
     RSB_CUDA(cudaSetDevice(h->device));
     if (stream >= (int64_t)h->n_streams) return fail(RSB_ERR_INVALID_ARGUMENT, "bad stream index");
+    // the scalar state lives on the plan stream (ordered with every plan kernel)
     if (stream < 0) {
-        rsb::launch_reset(h->st, 0, h->n_streams, h->stream);
+        rsb::launch_reset(h->st, 0, h->n_streams, h->plan_stream);
         std::fill(h->cohort.begin(), h->cohort.end(), 0);
     } else {
-        rsb::launch_reset(h->st, (uint32_t)stream, 1, h->stream);
+        rsb::launch_reset(h->st, (uint32_t)stream, 1, h->plan_stream);
         h->cohort[(size_t)stream] = 0;
     }
     h->launches += 1;
@@ -726,7 +764,8 @@ int rsb_fir_process_batch(rsb_fir *h, uint32_t n, const uint32_t *streams, const
 int rsb_fir_sync(rsb_fir *h) {
     if (check_handle(h)) return RSB_ERR_INVALID_ARGUMENT;
     RSB_CUDA(cudaSetDevice(h->device));
-    int rc = finalize_pending(h);
+    int rc = finalize_all(h);
+    RSB_CUDA(cudaStreamSynchronize(h->plan_stream));
     RSB_CUDA(cudaStreamSynchronize(h->stream));
     return rc;
 }
@@ -734,12 +773,14 @@ int rsb_fir_sync(rsb_fir *h) {
 int rsb_fir_last_call_counts(rsb_fir *h, uint32_t job, uint32_t *consumed, uint32_t *produced,
                              size_t max_calls, size_t *n_calls) {
     if (check_handle(h)) return RSB_ERR_INVALID_ARGUMENT;
-    int rc = finalize_pending(h);
+    int rc = finalize_all(h);
     if (rc != RSB_OK && rc != RSB_ERR_OUTPUT_CAPACITY) return rc;
-    if (!h->last_has_calls) return fail(RSB_ERR_INVALID_ARGUMENT, "last batch did not record calls");
-    if (job >= h->job_unit.size()) return fail(RSB_ERR_INVALID_ARGUMENT, "bad job index");
-    const UnitDev &U = h->h_units_back.as<UnitDev>()[h->job_unit[job]];
-    const rsb::CallCounts *cc = h->h_calls_back.as<rsb::CallCounts>() + U.call_off;
+    Workspace &W = h->last_ws();
+    if (!W.has_calls) return fail(RSB_ERR_INVALID_ARGUMENT, "last batch did not record calls");
+    if (job >= W.job_unit.size()) return fail(RSB_ERR_INVALID_ARGUMENT, "bad job index");
+    RSB_CUDA(cudaEventSynchronize(W.ev_plan));
+    const UnitDev &U = W.h_units_back.as<UnitDev>()[W.job_unit[job]];
+    const rsb::CallCounts *cc = W.h_calls_back.as<rsb::CallCounts>() + U.call_off;
     const size_t nc = std::min<size_t>(U.n_calls, U.call_cap);
     if (n_calls) *n_calls = nc;
     for (size_t i = 0; i < nc && i < max_calls; ++i) {
@@ -752,20 +793,22 @@ int rsb_fir_last_call_counts(rsb_fir *h, uint32_t job, uint32_t *consumed, uint3
 int rsb_fir_last_plan(rsb_fir *h, uint32_t job, uint32_t *input_offset, uint32_t *phase1,
                       uint32_t *phase2, uint32_t *frac_bits, size_t max_frames, size_t *n_frames) {
     if (check_handle(h)) return RSB_ERR_INVALID_ARGUMENT;
-    int rc = finalize_pending(h);
+    int rc = finalize_all(h);
     if (rc != RSB_OK && rc != RSB_ERR_OUTPUT_CAPACITY) return rc;
-    if (!h->last_has_plan) return fail(RSB_ERR_INVALID_ARGUMENT, "last batch did not keep its plan");
-    if (job >= h->job_unit.size()) return fail(RSB_ERR_INVALID_ARGUMENT, "bad job index");
+    Workspace &W = h->last_ws();
+    if (!W.has_plan) return fail(RSB_ERR_INVALID_ARGUMENT, "last batch did not keep its plan");
+    if (job >= W.job_unit.size()) return fail(RSB_ERR_INVALID_ARGUMENT, "bad job index");
     RSB_CUDA(cudaSetDevice(h->device));
-    const uint32_t unit = h->job_unit[job];
-    const UnitDev &U = h->h_units_back.as<UnitDev>()[unit];
+    RSB_CUDA(cudaEventSynchronize(W.ev_plan));
+    const uint32_t unit = W.job_unit[job];
+    const UnitDev &U = W.h_units_back.as<UnitDev>()[unit];
     const size_t total = (size_t)U.total_out;
     if (n_frames) *n_frames = total;
     const size_t cnt = std::min(total, max_frames);
     if (cnt == 0) return RSB_OK;
     RSB_CUDA(h->d_dbg.reserve(cnt * 4 * sizeof(uint32_t)));
     uint32_t *d = h->d_dbg.as<uint32_t>();
-    rsb::launch_expand_plan(h->d_units.as<UnitDev>(), unit, h->d_entries.as<rsb::PlanEntry>(),
+    rsb::launch_expand_plan(W.d_units.as<UnitDev>(), unit, W.d_entries.as<rsb::PlanEntry>(),
                             (uint32_t)cnt, d, d + cnt, d + 2 * cnt, d + 3 * cnt, h->stream);
     h->launches += 1;
     RSB_CUDA(cudaGetLastError());
@@ -781,13 +824,19 @@ int rsb_fir_last_plan(rsb_fir *h, uint32_t job, uint32_t *input_offset, uint32_t
 int rsb_fir_timer_start(rsb_fir *h) {
     if (check_handle(h)) return RSB_ERR_INVALID_ARGUMENT;
     RSB_CUDA(cudaSetDevice(h->device));
+    // work enqueued after this call must not start before the start event on either stream
+    RSB_CUDA(cudaEventRecord(h->ev_sync, h->plan_stream));
+    RSB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_sync, 0));
     RSB_CUDA(cudaEventRecord(h->ev_t0, h->stream));
+    RSB_CUDA(cudaStreamWaitEvent(h->plan_stream, h->ev_t0, 0));
     return RSB_OK;
 }
 
 int rsb_fir_timer_stop(rsb_fir *h, float *elapsed_ms) {
     if (check_handle(h)) return RSB_ERR_INVALID_ARGUMENT;
     RSB_CUDA(cudaSetDevice(h->device));
+    RSB_CUDA(cudaEventRecord(h->ev_sync, h->plan_stream));
+    RSB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_sync, 0));
     RSB_CUDA(cudaEventRecord(h->ev_t1, h->stream));
     RSB_CUDA(cudaEventSynchronize(h->ev_t1));
     float ms = 0.0f;

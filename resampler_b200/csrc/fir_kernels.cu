@@ -333,11 +333,23 @@ __global__ void update_state_kernel(const UnitDev *units, const JobDev *jobs, St
                                 : job.in[(vv - H0) * ch + c];
         new_hist[((int64_t)kHistFrames - H1 + f) * ch + c] = x;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        st.position[job.stream] = U.final_position;
-        st.hist_len[job.stream] = (uint32_t)H1;
-    }
+}
+
+// Scalar state of every stream of the submit (runs on the plan stream right after the plan).
+__global__ void state_scalars_kernel(const UnitDev *units, const JobDev *jobs, uint32_t n_jobs,
+                                     StreamStateDev st) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_jobs) return;
+    const JobDev &job = jobs[i];
+    const UnitDev &U = units[job.unit];
+    st.position[job.stream] = U.final_position;      // resampler_fir.rs:602
+    st.hist_len[job.stream] = U.final_available;     // resampler_fir.rs:601
+}
+
+void launch_state_scalars(const UnitDev *units, const JobDev *jobs, uint32_t n_jobs,
+                          StreamStateDev st, cudaStream_t stream) {
+    if (n_jobs == 0) return;
+    state_scalars_kernel<<<(n_jobs + 255) / 256, 256, 0, stream>>>(units, jobs, n_jobs, st);
 }
 
 void launch_update(const UnitDev *units, const JobDev *jobs, uint32_t n_jobs, StreamStateDev st,

@@ -48,6 +48,8 @@ void fast_phase_profile(int enable, unsigned long long *out8);
 // state write-back: new history tail, position, hist_len (one CTA per job)
 void launch_update(const UnitDev *units, const JobDev *jobs, uint32_t n_jobs, StreamStateDev st,
                    uint32_t channels, cudaStream_t stream);
+void launch_state_scalars(const UnitDev *units, const JobDev *jobs, uint32_t n_jobs,
+                          StreamStateDev st, cudaStream_t stream);
 void launch_reset(StreamStateDev st, uint32_t first, uint32_t count, cudaStream_t stream);
 // expands a unit's plan into per-frame arrays with the kernels' own device code
 void launch_expand_plan(const UnitDev *units, uint32_t unit, const PlanEntry *entries,

@@ -66,6 +66,36 @@ __global__ void __launch_bounds__(256) k_ffma2_peak(float *out, int iters, float
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// ---- id 2: warp-level tensor-core mma.sync m16n8k8 TF32 (legacy path) peak ----
+__global__ void __launch_bounds__(256) k_mma_tf32_peak(float *out, int iters) {
+    float d[8][4];
+    uint32_t a[4], b[2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d[i][j] = (float)(threadIdx.x + i + j);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = __float_as_uint(1.0f + 0.125f * i);
+    b[0] = __float_as_uint(0.5f);
+    b[1] = __float_as_uint(0.25f);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            asm volatile(
+                "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 "
+                "{%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                : "+f"(d[i][0]), "+f"(d[i][1]), "+f"(d[i][2]), "+f"(d[i][3])
+                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s += d[i][j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // ---- id 10+: banded GEMM core candidates ----
 // CTA tile: KT output rows x NC columns; window WIN (multiple of 4) shared-memory resident.
 // G[KT][GS] (row stride GS words), X[NC][XS] planar columns.
@@ -190,7 +220,25 @@ extern "C" int rsb_microbench(int device, int id, int arg, double *result, doubl
     if (cudaMalloc(&d_out, (size_t)sms * 16 * 256 * sizeof(float)) != cudaSuccess) return RSB_ERR_OUT_OF_MEMORY;
     int rc = 0;
     double r = 0.0, a = 0.0;
-    if (id == 0 || id == 1) {
+    if (id == 2) {
+        const int ctas = sms * (arg > 0 ? arg : 4);
+        const int iters = 4096;
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        k_mma_tf32_peak<<<ctas, 256>>>(d_out, 16);
+        cudaEventRecord(e0);
+        k_mma_tf32_peak<<<ctas, 256>>>(d_out, iters);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) rc = 2;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        // 8 mma per iteration per warp, 16*8*8 MACs each
+        const double mac = (double)ctas * 8.0 * iters * 8.0 * 1024.0;
+        r = 2.0 * mac / (ms * 1e-3) / 1e12;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    } else if (id == 0 || id == 1) {
         const int ctas = sms * (arg > 0 ? arg : 4);
         const int iters = 4096;
         cudaEvent_t e0, e1;

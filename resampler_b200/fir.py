@@ -242,7 +242,7 @@ class FirBatch:
         _check(self._lib.rsb_fir_submit_batch(self._h, n, st, _ptr_array(in_ptrs),
                                               _size_array(in_lens), _ptr_array(out_ptrs),
                                               _size_array(out_lens), cons, prod, memspace, flags))
-        self._keep = (cons, prod)
+        self._hold((cons, prod))
         return cons, prod
 
     def process(self, inputs: Sequence[np.ndarray], call_len: int, out_cap_len: int = 0,
@@ -278,8 +278,17 @@ class FirBatch:
                                                _size_array(total_lens), call_len, out_cap_len,
                                                _ptr_array(out_ptrs), _size_array(out_capacities),
                                                cons, prod, calls, memspace, flags))
-        self._keep = (cons, prod, calls)   # must outlive an async call
+        self._hold((cons, prod, calls))
         return cons, prod, calls
+
+    def _hold(self, arrays) -> None:
+        """Count arrays of an async call are written when a later call (or sync) completes it:
+        keep the most recent ones alive (two submits can be in flight)."""
+        keep = getattr(self, "_keep", None)
+        if keep is None:
+            keep = self._keep = []
+        keep.append(arrays)
+        del keep[:-4]
 
     def sync(self) -> None:
         _check(self._lib.rsb_fir_sync(self._h))
