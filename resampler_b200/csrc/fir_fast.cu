@@ -526,7 +526,263 @@ __global__ void __launch_bounds__(kThreads) conv_fast_kernel(ConvParams P, FastG
 #undef RSB_PHASE
 }
 
+
+// ===========================================================================================
+// Warp-specialised persistent variant (mono and stereo): one CTA per SM, 384 threads.
+//   warpgroup 0, 1 : consumers.  Group b owns shared-memory buffer b and runs the register-tiled
+//                    product + store of every second tile of the CTA, nothing else.
+//   warpgroup 2    : producers.  Per tile: metadata, TMA bulk copies (filter tile + member
+//                    windows), stereo de-interleave, then hands the buffer over.
+// Buffers are passed with mbarriers (full[b]: producer -> consumers, empty[b]: back).  The
+// consumers' registers come from the producers (setmaxnreg), exactly as many as the 8 compute
+// warps of the two-CTA-per-SM kernel above use.
+// ===========================================================================================
+struct TileMeta {
+    int d[kKT];               // band start of row k inside the window
+    uint32_t n_out, nm, n_cols, o_start;
+    float *out[kNC];          // per member
+    uint64_t cap[kNC];
+};
+
+constexpr int kWsThreads = 384;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void producer_bar() {
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
+// The product of one warp (8 rows x 128 columns) and its stores; shared by both kernels' maths.
+template <int TAPS>
+__device__ __forceinline__ void warp_product_store(const float *G, const float *X, uint32_t xs,
+                                                   const int *d, uint32_t n_out, uint32_t r0,
+                                                   uint32_t lane, uint32_t ch, uint32_t n_cols,
+                                                   uint32_t o_start, float *const *outp,
+                                                   const uint64_t *capp) {
+    const uint32_t r_last = min(r0 + kK, n_out) - 1;
+    const int j_lo = d[r0] & ~3;
+    const int j_end = d[r_last] + TAPS;
+    const int n_chunks = (j_end - j_lo + 3) >> 2;
+    float2 acc[kK][kC];
+#pragma unroll
+    for (int k = 0; k < kK; ++k)
+#pragma unroll
+        for (int c = 0; c < kC; ++c) acc[k][c] = make_float2(0.f, 0.f);
+    uint32_t xa[kC], ga[kK];
+#pragma unroll
+    for (int c = 0; c < kC; ++c) xa[c] = smem_u32(X + (lane + 32 * c) * xs);
+#pragma unroll
+    for (int k = 0; k < kK; ++k) ga[k] = smem_u32(G + (r0 + k) * xs);
+    // outside-in chunk order: both ends of the band first, centre taps last
+    auto chunk_byte = [&](int s) {
+        const int idx = (s & 1) ? (n_chunks - 1 - (s >> 1)) : (s >> 1);
+        return (uint32_t)(j_lo + 4 * idx) * 4u;
+    };
+    float4 gv[kK], xv[kC];
+    {
+        const uint32_t jb = chunk_byte(0);
+#pragma unroll
+        for (int c = 0; c < kC; ++c) xv[c] = lds128(xa[c] + jb);
+#pragma unroll
+        for (int k = 0; k < kK; ++k) gv[k] = lds128(ga[k] + jb);
+    }
+    for (int sidx = 0; sidx < n_chunks; ++sidx) {
+        float4 gn[kK], xn[kC];
+        const int snext = sidx + 1 < n_chunks ? sidx + 1 : sidx;
+        const uint32_t jb = chunk_byte(snext);
+#pragma unroll
+        for (int c = 0; c < kC; ++c) xn[c] = lds128(xa[c] + jb);
+#pragma unroll
+        for (int k = 0; k < kK; ++k) gn[k] = lds128(ga[k] + jb);
+#pragma unroll
+        for (int k = 0; k < kK; ++k) {
+#pragma unroll
+            for (int c = 0; c < kC; ++c) {
+                ffma2(acc[k][c], make_float2(gv[k].x, gv[k].y), make_float2(xv[c].x, xv[c].y));
+                ffma2(acc[k][c], make_float2(gv[k].z, gv[k].w), make_float2(xv[c].z, xv[c].w));
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < kC; ++c) xv[c] = xn[c];
+#pragma unroll
+        for (int k = 0; k < kK; ++k) gv[k] = gn[k];
+    }
+#pragma unroll
+    for (int c = 0; c < kC; ++c) {
+        const uint32_t col = lane + 32u * c;
+        if (col < n_cols) {
+            const uint32_t m = col / ch, cc = col - m * ch;
+            float *out = outp[m];
+            const uint64_t cap = capp[m];
+#pragma unroll
+            for (int k = 0; k < kK; ++k) {
+                const uint64_t o = (uint64_t)o_start + r0 + k;
+                if (r0 + k < n_out && o < cap) out[o * ch + cc] = __fadd_rn(acc[k][c].x, acc[k][c].y);
+            }
+        }
+    }
+}
+
+template <int TAPS, int CH>
+__global__ void __launch_bounds__(kWsThreads, 1) conv_fast_ws_kernel(ConvParams P, FastGeom geo) {
+    static_assert(CH == 1 || CH == 2, "warp-specialised kernel: mono or stereo");
+    extern __shared__ float4 smem_f4[];
+    float *smem = reinterpret_cast<float *>(smem_f4);
+    __shared__ TileMeta meta[2];
+    __shared__ const float *p_in[kNC];     // producers only
+    __shared__ const float *p_hist[kNC];
+    __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_tma[2];
+
+    constexpr uint32_t ch = CH;
+    const uint32_t xs = geo.xs;
+    const uint32_t buf_floats = (uint32_t)(kKT + kNC) * xs;
+    const uint32_t n_items = *P.tile_total * P.groups;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t wg = tid >> 7;
+    const uint32_t spg = P.streams_per_group;
+
+    if (tid == 0) {
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&bar_full[b], 1);
+            mbar_init(&bar_empty[b], 128);
+            mbar_init(&bar_tma[b], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (wg == 2) {
+        // ================================ producers ================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        const uint32_t ptid = tid - 256, lane = ptid & 31u, pw = ptid >> 5;
+        uint32_t i = 0;
+        for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, ++i) {
+            const uint32_t b = i & 1u, use = i >> 1;
+            if (use > 0) mbar_wait(&bar_empty[b], (use - 1) & 1u);
+            float *G = smem + b * buf_floats;
+            float *X = G + kKT * xs;
+            TileMeta &M = meta[b];
+            const uint32_t t = w / P.groups, g = w - t * P.groups;
+            const TileRec rec = P.tiles[t];
+            const UnitDev &U = P.units[rec.unit];
+            const uint32_t m0 = g * spg;
+            const uint32_t nm = m0 >= U.n_members ? 0u : min(spg, U.n_members - m0);
+            const uint32_t n_out = rec.n_out;
+            if (ptid == 0) {
+                M.nm = nm;
+                M.n_out = n_out;
+                M.n_cols = nm * ch;
+                M.o_start = rec.o_start;
+            }
+            if (nm) {
+                const int64_t H = (int64_t)U.hist_len0;
+                const int64_t n_valid = H + (int64_t)U.total_frames;
+                const int64_t v_base = rec.v_base;
+                const int n_grp = (int)rec.winp >> 2;
+                if (ptid < n_out) M.d[ptid] = P.entries[(size_t)t * kTileOut + ptid].v - rec.v_base;
+                if (ptid < nm) {
+                    const JobDev *job = P.jobs + U.member_off + m0 + ptid;
+                    p_in[ptid] = job->in;
+                    p_hist[ptid] = job->hist;
+                    M.out[ptid] = job->out;
+                    M.cap[ptid] = job->out_capacity;
+                }
+                const int g_lo = v_base < 0 ? 1 : 0;
+                int g_hi = (int)min((int64_t)n_grp, (n_valid - v_base) >> 2);
+                if (g_hi < g_lo) g_hi = g_lo;
+                const int g_seam = (int)max((int64_t)g_lo, min((int64_t)g_hi, (H - v_base) >> 2));
+                const uint32_t bytes_hist = (uint32_t)(g_seam - g_lo) * 16u * ch;
+                const uint32_t bytes_in = (uint32_t)(g_hi - g_seam) * 16u * ch;
+                producer_bar();
+                if (ptid == 0) {
+                    fence_proxy_async();   // the consumers' reads of this buffer are done
+                    mbar_arrive_expect_tx(&bar_tma[b], nm * (bytes_hist + bytes_in) + kKT * xs * 4u);
+                    bulk_g2s(G, P.gtiles + (size_t)t * kKT * xs, kKT * xs * 4u, &bar_tma[b]);
+                }
+                producer_bar();
+                if (ptid < nm) {
+                    float *dst = X + (size_t)ptid * ch * xs;
+                    if (bytes_hist)
+                        bulk_g2s(dst + 4 * g_lo * ch,
+                                 p_hist[ptid] + ((int64_t)kHistFrames - H + v_base + 4 * g_lo) * ch,
+                                 bytes_hist, &bar_tma[b]);
+                    if (bytes_in)
+                        bulk_g2s(dst + 4 * g_seam * ch, p_in[ptid] + (v_base + 4 * g_seam - H) * ch,
+                                 bytes_in, &bar_tma[b]);
+                }
+                // idle columns of a partial group read as zero
+                for (uint32_t q = ptid; q < (kNC - nm * ch) * (uint32_t)n_grp; q += 128) {
+                    const uint32_t c = nm * ch + q / n_grp, qq = q % n_grp;
+                    reinterpret_cast<float4 *>(X + c * xs)[qq] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                mbar_wait(&bar_tma[b], use & 1u);
+                if (CH == 2) {
+                    // in place, one warp per member: (L0 R0 L1 R1 | L2 R2 L3 R3) per lane ->
+                    // row 0: (L0 L1 L2 L3), row 1: (R0 R1 R2 R3)
+                    const uint32_t vpp = (uint32_t)n_grp;    // float4 PAIRS per member window
+                    float *blk = X + (size_t)pw * 2 * xs;
+                    for (uint32_t m = pw; m < nm; m += 4, blk += 4 * 2 * xs) {
+                        const float4 *r4 = reinterpret_cast<const float4 *>(blk);
+                        float4 a0, a1, c0, c1;
+                        const bool h0 = lane < vpp, h1 = lane + 32 < vpp;
+                        if (h0) { a0 = r4[2 * lane]; a1 = r4[2 * lane + 1]; }
+                        if (h1) { c0 = r4[2 * lane + 64]; c1 = r4[2 * lane + 65]; }
+                        __syncwarp();
+                        float4 *w0 = reinterpret_cast<float4 *>(blk);
+                        float4 *w1 = reinterpret_cast<float4 *>(blk + xs);
+                        if (h0) {
+                            w0[lane] = make_float4(a0.x, a0.z, a1.x, a1.z);
+                            w1[lane] = make_float4(a0.y, a0.w, a1.y, a1.w);
+                        }
+                        if (h1) {
+                            w0[lane + 32] = make_float4(c0.x, c0.z, c1.x, c1.z);
+                            w1[lane + 32] = make_float4(c0.y, c0.w, c1.y, c1.w);
+                        }
+                        __syncwarp();
+                    }
+                }
+                const uint32_t n_edge = (uint32_t)(g_lo + (n_grp - g_hi));
+                if (n_edge) {
+                    producer_bar();
+                    for (uint32_t q = ptid; q < nm * n_edge * ch; q += 128) {
+                        const uint32_t m = q / (n_edge * ch), r = q - m * (n_edge * ch);
+                        const uint32_t ge = r / ch, sub = r - ge * ch;
+                        const uint32_t grp = ge < (uint32_t)g_lo ? ge : (uint32_t)g_hi + (ge - g_lo);
+                        stage_slow(X, xs, m * ch, ch, grp, sub, v_base + 4 * (int64_t)grp, H, n_valid,
+                                   p_hist[m], p_in[m]);
+                    }
+                }
+            }
+            producer_bar();
+            if (ptid == 0) mbar_arrive(&bar_full[b]);
+        }
+    } else {
+        // ================================ consumers ================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        const uint32_t b = wg;
+        const uint32_t ctid = tid - 128 * wg, lane = ctid & 31u, cw = ctid >> 5;
+        const float *G = smem + b * buf_floats;
+        const float *X = G + kKT * xs;
+        const TileMeta &M = meta[b];
+        uint32_t k = 0;
+        for (uint32_t w = blockIdx.x + b * gridDim.x; w < n_items; w += 2 * gridDim.x, ++k) {
+            mbar_wait(&bar_full[b], k & 1u);
+            const uint32_t n_out = M.n_out;
+            const uint32_t r0 = cw * kK;
+            if (M.nm && r0 < n_out)
+                warp_product_store<TAPS>(G, X, xs, M.d, n_out, r0, lane, ch, M.n_cols, M.o_start,
+                                         M.out, M.cap);
+            mbar_arrive(&bar_empty[b]);
+        }
+    }
+}
+
 }  // namespace
+
+// debug switch: 0 selects the two-CTA-per-SM kernel everywhere
+bool g_use_ws = true;
+void fast_set_warp_specialised(int on) { g_use_ws = on != 0; }
 
 void fast_phase_profile(int enable, unsigned long long *out8) {
     if (out8) cudaMemcpyFromSymbol(out8, g_phase_cycles, sizeof(unsigned long long) * 8);
@@ -560,11 +816,23 @@ void launch_conv_fast(const ConvParams &p, double ratio, uint32_t max_items, int
         if (grid > max_items) grid = max_items;
         kern<<<grid, kThreads, smem, stream>>>(p, geo);
     };
+    // warp-specialised persistent kernel (mono / stereo): two shared-memory buffers per CTA
+    const size_t ws_smem = 2 * smem;
+    auto launch_ws = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem);
+        uint32_t grid = (uint32_t)sm_count;
+        if (grid > max_items) grid = max_items;
+        kern<<<grid, kWsThreads, ws_smem, stream>>>(p, geo);
+    };
+    const bool ws_ok = g_use_ws && ws_smem <= 215u * 1024u && (p.channels == 1 || p.channels == 2) &&
+                       (geo.win_max / 4) <= 64u;
 #define RSB_FAST_DISPATCH(T)                                             \
     do {                                                                 \
         const bool tma_ok = (geo.win_max / 4) * p.channels <=            \
                             32u * (uint32_t)(p.channels == 2 ? 3 : max_vec_per_lane((int)p.channels)); \
-        if (p.channels == 1) launch(conv_fast_kernel<T, 1>);             \
+        if (ws_ok && p.channels == 1) launch_ws(conv_fast_ws_kernel<T, 1>); \
+        else if (ws_ok && p.channels == 2) launch_ws(conv_fast_ws_kernel<T, 2>); \
+        else if (p.channels == 1) launch(conv_fast_kernel<T, 1>);        \
         else if (p.channels == 2 && tma_ok) launch(conv_fast_kernel<T, 2>); \
         else if (p.channels == 4 && tma_ok) launch(conv_fast_kernel<T, 4>); \
         else if (p.channels == 8 && tma_ok) launch(conv_fast_kernel<T, 8>); \

@@ -43,6 +43,7 @@ uint32_t fast_streams_per_group(uint32_t channels, uint32_t taps, double ratio);
 uint32_t fast_row_stride(uint32_t taps, double ratio);   // gs: floats per G / X row
 void launch_conv_fast(const ConvParams &p, double ratio, uint32_t max_items, int sm_count,
                       cudaStream_t stream);
+void fast_set_warp_specialised(int on);
 // debug: returns and clears the fast kernel's per-phase cycle counters, sets the enable flag
 void fast_phase_profile(int enable, unsigned long long *out8);
 // state write-back: new history tail, position, hist_len (one CTA per job)
