@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--streams", type=int, default=1024, help="streams per GPU")
     ap.add_argument("--seconds", type=float, default=60.0, help="audio seconds per stream")
     ap.add_argument("--kernel", default="auto", choices=["auto", "exact", "fast"])
+    ap.add_argument("--channels", type=int, default=2, help="experiment only: channels per stream")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-slice-seconds", type=float, default=5.0)
@@ -409,7 +410,9 @@ def run_e2e(args, batch, lib, frames, n_streams, local, dist):
 
 
 def main():
+    global CHANNELS
     args = parse_args()
+    CHANNELS = args.channels
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -398,10 +399,6 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     rsb::launch_plan(W.d_units.as<UnitDev>(), n_units, h->st, h->ratio, h->taps,
                      W.d_segs.as<rsb::PlanSeg>(), W.d_calls.as<rsb::CallCounts>(), tile_out,
                      W.d_counter.as<uint32_t>(), sp);
-    rsb::launch_tiles(W.d_units.as<UnitDev>(), n_units, W.d_segs.as<rsb::PlanSeg>(),
-                      W.d_tiles.as<rsb::TileRec>(), W.d_entries.as<rsb::PlanEntry>(),
-                      (uint32_t)max_tiles_unit, h->taps, h->d_coeffs,
-                      use_fast ? W.d_gtiles.as<float>() : nullptr, gs, sp);
     // the streams' scalar state (position, buffered frames) moves on the plan stream, so the
     // next submit can be planned while this one is still convolving
     rsb::launch_state_scalars(W.d_units.as<UnitDev>(), W.d_jobs.as<JobDev>(), n, h->st, sp);
@@ -412,6 +409,13 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
                                  sizeof(rsb::CallCounts) * call_total, cudaMemcpyDeviceToHost, sp));
     RSB_CUDA(cudaEventRecord(W.ev_plan, sp));
     RSB_CUDA(cudaStreamWaitEvent(s, W.ev_plan, 0));
+    // tile records, per-frame plan entries and (fast kernel) the banded filter tiles: a wide,
+    // short kernel, so it runs on the main stream in front of the convolution; only the
+    // serial plan kernel above overlaps the previous submit's convolution
+    rsb::launch_tiles(W.d_units.as<UnitDev>(), n_units, W.d_segs.as<rsb::PlanSeg>(),
+                      W.d_tiles.as<rsb::TileRec>(), W.d_entries.as<rsb::PlanEntry>(),
+                      (uint32_t)max_tiles_unit, h->taps, h->d_coeffs,
+                      use_fast ? W.d_gtiles.as<float>() : nullptr, gs, s);
     rsb::ConvParams P;
     P.units = W.d_units.as<UnitDev>();
     P.jobs = W.d_jobs.as<JobDev>();
@@ -426,11 +430,31 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     P.taps = h->taps;
     P.groups = max_groups;
     P.streams_per_group = spg;
+    // single plan unit with equally strided member inputs: one TMA tensor map for the batch
+    CUtensorMap tmap;
+    P.tmap_valid = 0;
+    if (use_fast && n_units == 1 && n >= 1 && (ch == 1 || ch == 2)) {
+        const JobDev *sorted = hj;   // grouped by unit == all jobs, in member order
+        const uintptr_t base = reinterpret_cast<uintptr_t>(sorted[0].in);
+        uint64_t stride = n > 1 ? (uint64_t)(reinterpret_cast<uintptr_t>(sorted[1].in) - base) : 0;
+        bool uniform = n == 1 || reinterpret_cast<uintptr_t>(sorted[1].in) > base;
+        for (uint32_t i = 1; uniform && i < n; ++i)
+            uniform = reinterpret_cast<uintptr_t>(sorted[i].in) == base + (uint64_t)i * stride;
+        if (n == 1) stride = ((uint64_t)unit_keys[0].total_frames * ch * 4 + 15) & ~15ull;
+        if (uniform && unit_keys[0].total_frames > 0 &&
+            rsb::fast_make_input_tensor_map(&tmap, sorted[0].in, stride, unit_keys[0].total_frames, n,
+                                            ch, h->taps, h->ratio))
+            P.tmap_valid = 1;
+        if (getenv("RSB_DEBUG"))
+            fprintf(stderr, "[rsb] tensor map: uniform=%d stride=%llu frames=%llu n=%u valid=%u\n",
+                    (int)uniform, (unsigned long long)stride,
+                    (unsigned long long)unit_keys[0].total_frames, n, P.tmap_valid);
+    }
     const uint32_t max_items = (uint32_t)(tile_total * max_groups);
     const int ring = (int)(h->conv_batches % rsb_fir::kConvRing);
     RSB_CUDA(cudaEventRecord(h->ev_conv[ring][0], s));
     if (use_fast)
-        rsb::launch_conv_fast(P, h->ratio, max_items, h->sm_count, s);
+        rsb::launch_conv_fast(P, P.tmap_valid ? &tmap : nullptr, h->ratio, max_items, h->sm_count, s);
     else
         rsb::launch_conv_exact(P, max_items, h->sm_count, s);
     RSB_CUDA(cudaEventRecord(h->ev_conv[ring][1], s));

@@ -67,7 +67,10 @@ struct TileRec {
     uint32_t n_out;
     int32_t v_base;     // first virtual frame of the tile's input window; (v_base - H) % 4 == 0
     uint32_t winp;      // window length in frames, multiple of 4
-    uint32_t pad0, pad1;
+    // copies of the unit's fields, so that a kernel needs one load instead of a dependent two
+    uint32_t n_members, member_off;
+    uint32_t hist_len0, pad0;
+    uint64_t total_frames;
 };
 
 // Per-output-frame plan entry, expanded once per tile by the tile kernel and shared by every

@@ -123,6 +123,23 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
                  : "r"(addr));
     return v;
 }
+// TMA tiled tensor copy global -> shared of one 2-D box (SASS: UTMALDG)
+__device__ __forceinline__ void tensor_g2s_2d(void *dst, const CUtensorMap *tm, int c0, int c1,
+                                              uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+        "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -538,8 +555,12 @@ __global__ void __launch_bounds__(kThreads) conv_fast_kernel(ConvParams P, FastG
 // warps of the two-CTA-per-SM kernel above use.
 // ===========================================================================================
 struct TileMeta {
-    int d[kKT];               // band start of row k inside the window
+    int d[kKT];               // virtual window start v_k of row k (band start = v_k - v_base)
     uint32_t n_out, nm, n_cols, o_start;
+    uint32_t t, winp;         // (producers) tile index, window length
+    uint32_t tensor_path;     // (producers) window fetched by one tensor copy (zero-filled edges)
+    int32_t v_base;
+    int64_t H, n_valid;
     float *out[kNC];          // per member
     uint64_t cap[kNC];
 };
@@ -556,13 +577,13 @@ __device__ __forceinline__ void producer_bar() {
 // The product of one warp (8 rows x 128 columns) and its stores; shared by both kernels' maths.
 template <int TAPS>
 __device__ __forceinline__ void warp_product_store(const float *G, const float *X, uint32_t xs,
-                                                   const int *d, uint32_t n_out, uint32_t r0,
+                                                   const int *v, int v_base, uint32_t n_out, uint32_t r0,
                                                    uint32_t lane, uint32_t ch, uint32_t n_cols,
                                                    uint32_t o_start, float *const *outp,
                                                    const uint64_t *capp) {
     const uint32_t r_last = min(r0 + kK, n_out) - 1;
-    const int j_lo = d[r0] & ~3;
-    const int j_end = d[r_last] + TAPS;
+    const int j_lo = (v[r0] - v_base) & ~3;
+    const int j_end = (v[r_last] - v_base) + TAPS;
     const int n_chunks = (j_end - j_lo + 3) >> 2;
     float2 acc[kK][kC];
 #pragma unroll
@@ -625,13 +646,15 @@ __device__ __forceinline__ void warp_product_store(const float *G, const float *
 }
 
 template <int TAPS, int CH>
-__global__ void __launch_bounds__(kWsThreads, 1) conv_fast_ws_kernel(ConvParams P, FastGeom geo) {
+__global__ void __launch_bounds__(kWsThreads, 1)
+conv_fast_ws_kernel(const __grid_constant__ ConvParams P, const __grid_constant__ FastGeom geo,
+                    const __grid_constant__ CUtensorMap tmap) {
     static_assert(CH == 1 || CH == 2, "warp-specialised kernel: mono or stereo");
-    extern __shared__ float4 smem_f4[];
-    float *smem = reinterpret_cast<float *>(smem_f4);
+    extern __shared__ __align__(1024) uint8_t smem_ws_raw[];   // TMA tensor boxes: 128-byte aligned
+    float *smem = reinterpret_cast<float *>(smem_ws_raw);
     __shared__ TileMeta meta[2];
-    __shared__ const float *p_in[kNC];     // producers only
-    __shared__ const float *p_hist[kNC];
+    __shared__ const float *p_in[2][kNC];     // producers only, per buffer
+    __shared__ const float *p_hist[2][kNC];
     __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_tma[2];
 
     constexpr uint32_t ch = CH;
@@ -654,126 +677,247 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_fast_ws_kernel(ConvParams 
 
     if (wg == 2) {
         // ================================ producers ================================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        // Two-stage software pipeline over the CTA's tiles:
+        //   issue(i+1): wait for the buffer, publish metadata, start the TMA copies
+        //   finish(i) : wait for tile i's copies, de-interleave, hand the buffer over
+        // so the copies of tile i+1 (and the metadata loads of tile i+2) are in flight while
+        // tile i is being de-interleaved.
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
         const uint32_t ptid = tid - 256, lane = ptid & 31u, pw = ptid >> 5;
-        uint32_t i = 0;
-        for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, ++i) {
+        const uint32_t n_mine = blockIdx.x < n_items ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+        const bool prof = g_phase_enabled != 0 && ptid == 0;
+        unsigned long long pc[4] = {0, 0, 0, 0};
+        long long tprev = prof ? clock64() : 0;
+#define RSB_WS_PHASE(i)                                  \
+    if (prof) {                                          \
+        const long long tn = clock64();                  \
+        pc[i] += (unsigned long long)(tn - tprev);       \
+        tprev = tn;                                      \
+    }
+
+        // Metadata: the tile record travels in registers two tiles ahead (level 1); what hangs
+        // off it (rows' window starts, members' output pointers) is copied straight into the
+        // buffer's TileMeta with cp.async, no registers involved.
+        auto item_tile = [&](uint32_t i, uint32_t &g) {
+            const uint32_t w = blockIdx.x + i * gridDim.x;
+            const uint32_t t = w / P.groups;
+            g = w - t * P.groups;
+            return t;
+        };
+        auto load_level1 = [&](uint32_t i) {
+            uint32_t g;
+            return P.tiles[item_tile(i, g)];
+        };
+        // geometry of a tile's window, recomputed where needed (cheap, keeps registers low)
+        struct Geo { int n_grp, g_lo, g_hi, g_seam; };
+        auto window = [&](const TileRec &rec, int64_t H, int64_t n_valid) {
+            Geo q;
+            const int64_t v_base = rec.v_base;
+            q.n_grp = (int)rec.winp >> 2;
+            q.g_lo = v_base < 0 ? 1 : 0;
+            q.g_hi = (int)min((int64_t)q.n_grp, (n_valid - v_base) >> 2);
+            if (q.g_hi < q.g_lo) q.g_hi = q.g_lo;
+            q.g_seam = (int)max((int64_t)q.g_lo, min((int64_t)q.g_hi, (H - v_base) >> 2));
+            return q;
+        };
+        auto issue = [&](uint32_t i, const TileRec &rec) {
             const uint32_t b = i & 1u, use = i >> 1;
+            RSB_WS_PHASE(1)
             if (use > 0) mbar_wait(&bar_empty[b], (use - 1) & 1u);
+            RSB_WS_PHASE(0)
             float *G = smem + b * buf_floats;
             float *X = G + kKT * xs;
             TileMeta &M = meta[b];
-            const uint32_t t = w / P.groups, g = w - t * P.groups;
-            const TileRec rec = P.tiles[t];
-            const UnitDev &U = P.units[rec.unit];
-            const uint32_t m0 = g * spg;
-            const uint32_t nm = m0 >= U.n_members ? 0u : min(spg, U.n_members - m0);
-            const uint32_t n_out = rec.n_out;
+            struct { TileRec rec; uint32_t t, m0, nm; } r;
+            uint32_t g;
+            r.t = item_tile(i, g);
+            r.rec = rec;
+            r.m0 = g * spg;
+            r.nm = r.m0 >= rec.n_members ? 0u : min(spg, rec.n_members - r.m0);
             if (ptid == 0) {
-                M.nm = nm;
-                M.n_out = n_out;
-                M.n_cols = nm * ch;
+                M.nm = r.nm;
+                M.n_out = rec.n_out;
+                M.n_cols = r.nm * ch;
                 M.o_start = rec.o_start;
+                M.t = r.t;
+                M.v_base = rec.v_base;
+                M.winp = rec.winp;
+                M.H = (int64_t)rec.hist_len0;
+                M.n_valid = (int64_t)rec.hist_len0 + (int64_t)rec.total_frames;
             }
-            if (nm) {
-                const int64_t H = (int64_t)U.hist_len0;
-                const int64_t n_valid = H + (int64_t)U.total_frames;
-                const int64_t v_base = rec.v_base;
-                const int n_grp = (int)rec.winp >> 2;
-                if (ptid < n_out) M.d[ptid] = P.entries[(size_t)t * kTileOut + ptid].v - rec.v_base;
-                if (ptid < nm) {
-                    const JobDev *job = P.jobs + U.member_off + m0 + ptid;
-                    p_in[ptid] = job->in;
-                    p_hist[ptid] = job->hist;
-                    M.out[ptid] = job->out;
-                    M.cap[ptid] = job->out_capacity;
-                }
-                const int g_lo = v_base < 0 ? 1 : 0;
-                int g_hi = (int)min((int64_t)n_grp, (n_valid - v_base) >> 2);
-                if (g_hi < g_lo) g_hi = g_lo;
-                const int g_seam = (int)max((int64_t)g_lo, min((int64_t)g_hi, (H - v_base) >> 2));
-                const uint32_t bytes_hist = (uint32_t)(g_seam - g_lo) * 16u * ch;
-                const uint32_t bytes_in = (uint32_t)(g_hi - g_seam) * 16u * ch;
-                producer_bar();
+            if (r.nm == 0) return;
+            const JobDev *jobs = P.jobs + rec.member_off + r.m0;
+            if (ptid < rec.n_out)
+                cp_async4(&M.d[ptid], &P.entries[(size_t)r.t * kTileOut + ptid].v);
+            if (ptid < r.nm) {
+                cp_async8(&M.out[ptid], &jobs[ptid].out);
+                cp_async8(&M.cap[ptid], &jobs[ptid].out_capacity);
+            }
+            cp_async_commit();
+            const int64_t rH = (int64_t)r.rec.hist_len0;
+            const Geo q = window(r.rec, rH, rH + (int64_t)r.rec.total_frames);
+            // one tensor copy for the whole group when the window lies in the new input
+            const bool tensor = P.tmap_valid != 0 && (int64_t)r.rec.v_base >= rH;
+            if (ptid == 0) M.tensor_path = tensor ? 1u : 0u;
+            if (tensor) {
                 if (ptid == 0) {
                     fence_proxy_async();   // the consumers' reads of this buffer are done
-                    mbar_arrive_expect_tx(&bar_tma[b], nm * (bytes_hist + bytes_in) + kKT * xs * 4u);
-                    bulk_g2s(G, P.gtiles + (size_t)t * kKT * xs, kKT * xs * 4u, &bar_tma[b]);
+                    const uint32_t box_bytes = kNC * xs * 4u;   // members x frames x ch, full box
+                    mbar_arrive_expect_tx(&bar_tma[b], box_bytes + kKT * xs * 4u);
+                    bulk_g2s(G, P.gtiles + (size_t)r.t * kKT * xs, kKT * xs * 4u, &bar_tma[b]);
+                    tensor_g2s_2d(X, &tmap, (int)((int64_t)r.rec.v_base - rH), (int)r.m0, &bar_tma[b]);
                 }
-                producer_bar();
-                if (ptid < nm) {
-                    float *dst = X + (size_t)ptid * ch * xs;
-                    if (bytes_hist)
-                        bulk_g2s(dst + 4 * g_lo * ch,
-                                 p_hist[ptid] + ((int64_t)kHistFrames - H + v_base + 4 * g_lo) * ch,
-                                 bytes_hist, &bar_tma[b]);
-                    if (bytes_in)
-                        bulk_g2s(dst + 4 * g_seam * ch, p_in[ptid] + (v_base + 4 * g_seam - H) * ch,
-                                 bytes_in, &bar_tma[b]);
-                }
-                // idle columns of a partial group read as zero
-                for (uint32_t q = ptid; q < (kNC - nm * ch) * (uint32_t)n_grp; q += 128) {
-                    const uint32_t c = nm * ch + q / n_grp, qq = q % n_grp;
-                    reinterpret_cast<float4 *>(X + c * xs)[qq] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                return;
+            }
+            const uint32_t bytes_hist = (uint32_t)(q.g_seam - q.g_lo) * 16u * ch;
+            const uint32_t bytes_in = (uint32_t)(q.g_hi - q.g_seam) * 16u * ch;
+            if (ptid == 0) {
+                fence_proxy_async();   // the consumers' reads of this buffer are done
+                mbar_arrive_expect_tx(&bar_tma[b], r.nm * (bytes_hist + bytes_in) + kKT * xs * 4u);
+                bulk_g2s(G, P.gtiles + (size_t)r.t * kKT * xs, kKT * xs * 4u, &bar_tma[b]);
+            }
+            const float *m_in = nullptr, *m_hist = nullptr;
+            if (ptid < r.nm) {
+                m_in = jobs[ptid].in;
+                m_hist = jobs[ptid].hist;
+                p_in[b][ptid] = m_in;
+                p_hist[b][ptid] = m_hist;
+            }
+            producer_bar();
+            if (ptid < r.nm) {
+                float *dst = X + (size_t)ptid * ch * xs;
+                const int64_t v_base = r.rec.v_base;
+                if (bytes_hist)
+                    bulk_g2s(dst + 4 * q.g_lo * ch,
+                             m_hist + ((int64_t)kHistFrames - rH + v_base + 4 * q.g_lo) * ch,
+                             bytes_hist, &bar_tma[b]);
+                if (bytes_in)
+                    bulk_g2s(dst + 4 * q.g_seam * ch, m_in + (v_base + 4 * q.g_seam - rH) * ch,
+                             bytes_in, &bar_tma[b]);
+            }
+            // idle columns of a partial group read as zero
+            for (uint32_t e = ptid; e < (kNC - r.nm * ch) * (uint32_t)q.n_grp; e += 128) {
+                const uint32_t c = r.nm * ch + e / q.n_grp, qq = e % q.n_grp;
+                reinterpret_cast<float4 *>(X + c * xs)[qq] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        auto finish = [&](uint32_t i) {
+            const uint32_t b = i & 1u, use = i >> 1;
+            float *X = smem + b * buf_floats + kKT * xs;
+            const TileMeta &M = meta[b];
+            const uint32_t nm = M.nm;
+            if (nm) {
+                TileRec rec;
+                rec.v_base = M.v_base;
+                rec.winp = M.winp;
+                const Geo q = window(rec, M.H, M.n_valid);
+                RSB_WS_PHASE(1)
                 mbar_wait(&bar_tma[b], use & 1u);
+                RSB_WS_PHASE(2)
                 if (CH == 2) {
-                    // in place, one warp per member: (L0 R0 L1 R1 | L2 R2 L3 R3) per lane ->
-                    // row 0: (L0 L1 L2 L3), row 1: (R0 R1 R2 R3)
-                    const uint32_t vpp = (uint32_t)n_grp;    // float4 PAIRS per member window
-                    float *blk = X + (size_t)pw * 2 * xs;
-                    for (uint32_t m = pw; m < nm; m += 4, blk += 4 * 2 * xs) {
-                        const float4 *r4 = reinterpret_cast<const float4 *>(blk);
-                        float4 a0, a1, c0, c1;
-                        const bool h0 = lane < vpp, h1 = lane + 32 < vpp;
-                        if (h0) { a0 = r4[2 * lane]; a1 = r4[2 * lane + 1]; }
-                        if (h1) { c0 = r4[2 * lane + 64]; c1 = r4[2 * lane + 65]; }
-                        __syncwarp();
-                        float4 *w0 = reinterpret_cast<float4 *>(blk);
-                        float4 *w1 = reinterpret_cast<float4 *>(blk + xs);
-                        if (h0) {
-                            w0[lane] = make_float4(a0.x, a0.z, a1.x, a1.z);
-                            w1[lane] = make_float4(a0.y, a0.w, a1.y, a1.w);
+                    // in place, one warp per member: 3 float4 per lane cover a window of <= 192
+                    // frames; (L0 R0 L1 R1) -> row 0: (L0, L1), row 1: (R0, R1)
+                    const uint32_t vps = (uint32_t)q.n_grp * 2u;   // float4 per member window
+                    const bool h0 = lane < vps, h1 = lane + 32 < vps, h2 = lane + 64 < vps;
+                    // two members per step (members pw and pw + 4 of every group of 8): twice
+                    // the loads in flight per shared-memory round trip
+                    for (uint32_t m = pw; m < nm; m += 8) {
+                        float *blkA = X + (size_t)m * 2 * xs;
+                        float *blkB = blkA + 4 * 2 * xs;
+                        const bool hasB = m + 4 < nm;
+                        const float4 *rA = reinterpret_cast<const float4 *>(blkA);
+                        const float4 *rB = reinterpret_cast<const float4 *>(blkB);
+                        float4 a0, a1, a2, b0, b1, b2;
+                        if (h0) a0 = rA[lane];
+                        if (h1) a1 = rA[lane + 32];
+                        if (h2) a2 = rA[lane + 64];
+                        if (hasB) {
+                            if (h0) b0 = rB[lane];
+                            if (h1) b1 = rB[lane + 32];
+                            if (h2) b2 = rB[lane + 64];
                         }
-                        if (h1) {
-                            w0[lane + 32] = make_float4(c0.x, c0.z, c1.x, c1.z);
-                            w1[lane + 32] = make_float4(c0.y, c0.w, c1.y, c1.w);
+                        __syncwarp();
+                        float2 *w0 = reinterpret_cast<float2 *>(blkA);
+                        float2 *w1 = reinterpret_cast<float2 *>(blkA + xs);
+                        if (h0) { w0[lane] = make_float2(a0.x, a0.z); w1[lane] = make_float2(a0.y, a0.w); }
+                        if (h1) { w0[lane + 32] = make_float2(a1.x, a1.z); w1[lane + 32] = make_float2(a1.y, a1.w); }
+                        if (h2) { w0[lane + 64] = make_float2(a2.x, a2.z); w1[lane + 64] = make_float2(a2.y, a2.w); }
+                        if (hasB) {
+                            float2 *v0 = reinterpret_cast<float2 *>(blkB);
+                            float2 *v1 = reinterpret_cast<float2 *>(blkB + xs);
+                            if (h0) { v0[lane] = make_float2(b0.x, b0.z); v1[lane] = make_float2(b0.y, b0.w); }
+                            if (h1) { v0[lane + 32] = make_float2(b1.x, b1.z); v1[lane + 32] = make_float2(b1.y, b1.w); }
+                            if (h2) { v0[lane + 64] = make_float2(b2.x, b2.z); v1[lane + 64] = make_float2(b2.y, b2.w); }
                         }
                         __syncwarp();
                     }
                 }
-                const uint32_t n_edge = (uint32_t)(g_lo + (n_grp - g_hi));
+                const uint32_t n_edge = M.tensor_path ? 0u : (uint32_t)(q.g_lo + (q.n_grp - q.g_hi));
                 if (n_edge) {
                     producer_bar();
-                    for (uint32_t q = ptid; q < nm * n_edge * ch; q += 128) {
-                        const uint32_t m = q / (n_edge * ch), r = q - m * (n_edge * ch);
+                    for (uint32_t e = ptid; e < nm * n_edge * ch; e += 128) {
+                        const uint32_t m = e / (n_edge * ch), r = e - m * (n_edge * ch);
                         const uint32_t ge = r / ch, sub = r - ge * ch;
-                        const uint32_t grp = ge < (uint32_t)g_lo ? ge : (uint32_t)g_hi + (ge - g_lo);
-                        stage_slow(X, xs, m * ch, ch, grp, sub, v_base + 4 * (int64_t)grp, H, n_valid,
-                                   p_hist[m], p_in[m]);
+                        const uint32_t grp =
+                            ge < (uint32_t)q.g_lo ? ge : (uint32_t)q.g_hi + (ge - q.g_lo);
+                        stage_slow(X, xs, m * ch, ch, grp, sub, M.v_base + 4 * (int64_t)grp, M.H,
+                                   M.n_valid, p_hist[b][m], p_in[b][m]);
                     }
                 }
             }
+            cp_async_wait_all();       // this thread's metadata copies have landed
             producer_bar();
             if (ptid == 0) mbar_arrive(&bar_full[b]);
+            RSB_WS_PHASE(3)
+        };
+
+        if (n_mine) {
+            TileRec rec1 = load_level1(0), rec2;
+            issue(0, rec1);
+            if (n_mine > 1) rec1 = load_level1(1);
+            if (n_mine > 2) rec2 = load_level1(2);
+            producer_bar();            // metadata of tile 0 visible to every producer thread
+            for (uint32_t i = 0; i < n_mine; ++i) {
+                // tile i is handed over first: tile i+1 needs the buffer tile i-1 occupies, and
+                // waiting for that before finishing tile i would serialise the two groups
+                finish(i);
+                if (i + 1 < n_mine) {
+                    issue(i + 1, rec1);
+                    rec1 = rec2;
+                    if (i + 3 < n_mine) rec2 = load_level1(i + 3);
+                    producer_bar();    // meta of tile i+1 visible to every producer thread
+                }
+            }
         }
+        if (prof)
+            for (int q = 0; q < 4; ++q) atomicAdd(&g_phase_cycles[q], pc[q]);
+#undef RSB_WS_PHASE
     } else {
         // ================================ consumers ================================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
         const uint32_t b = wg;
         const uint32_t ctid = tid - 128 * wg, lane = ctid & 31u, cw = ctid >> 5;
         const float *G = smem + b * buf_floats;
         const float *X = G + kKT * xs;
         const TileMeta &M = meta[b];
         uint32_t k = 0;
+        const bool prof = g_phase_enabled != 0 && ctid == 0;
+        unsigned long long pcw = 0, pcp = 0;
+        long long tprev = prof ? clock64() : 0;
         for (uint32_t w = blockIdx.x + b * gridDim.x; w < n_items; w += 2 * gridDim.x, ++k) {
             mbar_wait(&bar_full[b], k & 1u);
+            if (prof) { const long long tn = clock64(); pcw += (unsigned long long)(tn - tprev); tprev = tn; }
             const uint32_t n_out = M.n_out;
             const uint32_t r0 = cw * kK;
             if (M.nm && r0 < n_out)
-                warp_product_store<TAPS>(G, X, xs, M.d, n_out, r0, lane, ch, M.n_cols, M.o_start,
-                                         M.out, M.cap);
+                warp_product_store<TAPS>(G, X, xs, M.d, M.v_base, n_out, r0, lane, ch, M.n_cols,
+                                         M.o_start, M.out, M.cap);
             mbar_arrive(&bar_empty[b]);
+            if (prof) { const long long tn = clock64(); pcp += (unsigned long long)(tn - tprev); tprev = tn; }
+        }
+        if (prof) {
+            atomicAdd(&g_phase_cycles[4 + 2 * b], pcw);
+            atomicAdd(&g_phase_cycles[5 + 2 * b], pcp);
         }
     }
 }
@@ -802,8 +946,45 @@ uint32_t fast_streams_per_group(uint32_t channels, uint32_t, double) { return kN
 
 uint32_t fast_row_stride(uint32_t taps, double ratio) { return fast_geom(taps, ratio).xs; }
 
-void launch_conv_fast(const ConvParams &p, double ratio, uint32_t max_items, int sm_count,
-                      cudaStream_t stream) {
+bool fast_make_input_tensor_map(CUtensorMap *out, const float *base, uint64_t stride_bytes,
+                                uint64_t total_frames, uint32_t n_members, uint32_t channels,
+                                uint32_t taps, double ratio) {
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                      const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                      const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) !=
+                cudaSuccess || !fn) {
+            cudaGetLastError();
+            return false;
+        }
+        encode = (EncodeTiledFn)fn;
+    }
+    if (channels != 1 && channels != 2) return false;
+    const FastGeom geo = fast_geom(taps, ratio);
+    if (geo.xs > 256 || total_frames == 0 || total_frames >= (1ull << 31)) return false;
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) || (stride_bytes & 15u) || stride_bytes == 0)
+        return false;
+    if (stride_bytes < total_frames * channels * 4ull) return false;
+    // element = one frame (f32 mono, 8-byte stereo); inner dimension = frames, rows = members
+    cuuint64_t dims[2] = {total_frames, n_members};
+    cuuint64_t strides[1] = {stride_bytes};
+    cuuint32_t box[2] = {geo.xs, (cuuint32_t)(kNC / channels)};
+    cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt =
+        channels == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
+    const CUresult r = encode(out, dt, 2, const_cast<float *>(base), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+void launch_conv_fast(const ConvParams &p, const CUtensorMap *tmap, double ratio,
+                      uint32_t max_items, int sm_count, cudaStream_t stream) {
     if (max_items == 0) return;
     const FastGeom geo = fast_geom(p.taps, ratio);
     const size_t smem = fast_smem_bytes(geo, p.channels);
@@ -820,9 +1001,19 @@ void launch_conv_fast(const ConvParams &p, double ratio, uint32_t max_items, int
     const size_t ws_smem = 2 * smem;
     auto launch_ws = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem);
-        uint32_t grid = (uint32_t)sm_count;
+        // one SM is left free: the persistent CTAs take a whole SM each, and the (serial,
+        // single-thread) plan kernel of the next submit needs somewhere to run meanwhile
+        uint32_t grid = (uint32_t)(sm_count > 8 ? sm_count - 1 : sm_count);
         if (grid > max_items) grid = max_items;
-        kern<<<grid, kWsThreads, ws_smem, stream>>>(p, geo);
+        ConvParams pw = p;
+        CUtensorMap tm;
+        if (tmap && p.tmap_valid) {
+            tm = *tmap;
+        } else {
+            memset(&tm, 0, sizeof(tm));
+            pw.tmap_valid = 0;
+        }
+        kern<<<grid, kWsThreads, ws_smem, stream>>>(pw, geo, tm);
     };
     const bool ws_ok = g_use_ws && ws_smem <= 215u * 1024u && (p.channels == 1 || p.channels == 2) &&
                        (geo.win_max / 4) <= 64u;

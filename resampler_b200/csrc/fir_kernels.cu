@@ -152,7 +152,11 @@ __global__ void tile_index_kernel(const UnitDev *units, const PlanSeg *segs, Til
         r.n_out = n_out;
         r.v_base = v_base;
         r.winp = winp;
-        r.pad0 = r.pad1 = 0;
+        r.n_members = U.n_members;
+        r.member_off = U.member_off;
+        r.hist_len0 = U.hist_len0;
+        r.pad0 = 0;
+        r.total_frames = U.total_frames;
         tiles[tile] = r;
     }
     if (gtiles == nullptr) return;

@@ -1,6 +1,7 @@
 // fir_kernels.h -- launch interface between the host library (fir_api.cu) and
 // the sm_100a kernels (fir_kernels.cu, fir_fast.cu).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -22,7 +23,16 @@ struct ConvParams {
     uint32_t taps;
     uint32_t groups;              // member groups per tile (max over units)
     uint32_t streams_per_group;
+    // Optional 2-D TMA tensor map over the new input of a single-unit batch whose member
+    // buffers are equally strided in memory: rows = members, inner = frames.  One tensor
+    // copy then replaces one bulk copy per member (which cost ~100 cycles each to issue).
+    uint32_t tmap_valid;
 };
+
+// Builds the tensor map above (host).  Returns false when the layout does not qualify.
+bool fast_make_input_tensor_map(CUtensorMap *out, const float *base, uint64_t stride_bytes,
+                                uint64_t total_frames, uint32_t n_members, uint32_t channels,
+                                uint32_t taps, double ratio);
 
 constexpr uint32_t kExactStreamsPerGroup = 4;
 
@@ -41,8 +51,8 @@ void launch_conv_exact(const ConvParams &p, uint32_t max_items, int sm_count, cu
 bool fast_supported(uint32_t channels, uint32_t taps, double ratio);
 uint32_t fast_streams_per_group(uint32_t channels, uint32_t taps, double ratio);
 uint32_t fast_row_stride(uint32_t taps, double ratio);   // gs: floats per G / X row
-void launch_conv_fast(const ConvParams &p, double ratio, uint32_t max_items, int sm_count,
-                      cudaStream_t stream);
+void launch_conv_fast(const ConvParams &p, const CUtensorMap *tmap, double ratio,
+                      uint32_t max_items, int sm_count, cudaStream_t stream);
 void fast_set_warp_specialised(int on);
 // debug: returns and clears the fast kernel's per-phase cycle counters, sets the enable flag
 void fast_phase_profile(int enable, unsigned long long *out8);
