@@ -424,12 +424,14 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     P.entries = W.d_entries.as<rsb::PlanEntry>();
     P.gtiles = W.d_gtiles.as<float>();
     P.tile_total = W.d_counter.as<uint32_t>();
+    P.work_counter = W.d_counter.as<uint32_t>() + 1;
     P.coeffs = h->d_coeffs;
     P.st = h->st;
     P.channels = ch;
     P.taps = h->taps;
     P.groups = max_groups;
     P.streams_per_group = spg;
+    P.group_block = std::min<uint32_t>(max_groups, 2u);
     // single plan unit with equally strided member inputs: one TMA tensor map for the batch
     CUtensorMap tmap;
     P.tmap_valid = 0;

@@ -17,12 +17,19 @@ struct ConvParams {
     const PlanEntry *entries;     // [tile][kTileOut]
     const float *gtiles;          // [tile][kTileOut][gs] banded filter rows (fast kernel)
     const uint32_t *tile_total;   // device counter written by the plan kernel
+    uint32_t *work_counter;       // zeroed per submit: dynamic work distribution (fast kernel)
     const float *coeffs;          // [1024][taps]
     StreamStateDev st;
     uint32_t channels;
     uint32_t taps;
     uint32_t groups;              // member groups per tile (max over units)
     uint32_t streams_per_group;
+    // Work item w -> (tile t, group g).  Items are ordered in super-blocks of `group_block`
+    // groups: all tiles of groups [0, gb), then all tiles of [gb, 2gb), ...  Few streams are
+    // in flight at a time (their buffers can be gigabytes apart: measured 1.6x slow-down at
+    // 60 s x 1024 streams with every stream touched round-robin, TLB reach), while a tile's
+    // filter matrix is still reused by gb consecutive items out of L2.
+    uint32_t group_block;
     // Optional 2-D TMA tensor map over the new input of a single-unit batch whose member
     // buffers are equally strided in memory: rows = members, inner = frames.  One tensor
     // copy then replaces one bulk copy per member (which cost ~100 cycles each to issue).
