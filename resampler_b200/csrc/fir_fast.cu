@@ -653,16 +653,27 @@ __device__ __forceinline__ void warp_product_store(const float *G, const float *
 // as a broadcast FFMA2 operand (`FFMA2 Rd, Rg.F32, Rx.F32x2.HI_LO, Rd`), so nothing has to
 // be duplicated.  A thread owns 8 rows x 2 members; one chain per output, taps visited
 // outside-in (max |diff| to the oracle 3.6e-7 in the CPU simulation).
+constexpr uint32_t kStageStride = 33;   // frames per member in the store staging area
+
+__device__ __forceinline__ void consumer_bar(uint32_t id) {
+    asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
+}
+
+// All four warps of a consumer group must call this together (it contains group barriers);
+// `stage` aliases the buffer's input windows (>= 28 KB for any tap count; 16.5 KB needed), which
+// are dead once every warp of the group has finished its products.
 template <int TAPS>
 __device__ __forceinline__ void warp_product_store_stereo(
     const float *G, const float *X, uint32_t xs, uint32_t mb, const int *v, int v_base,
     uint32_t n_out, uint32_t r0, uint32_t lane, uint32_t nm, uint32_t o_start, float *const *outp,
-    const uint64_t *capp) {
+    const uint64_t *capp, float *stage, uint32_t bar_id) {
     constexpr int kS = 2;      // members per thread: lane and lane + 32
-    const uint32_t r_last = min(r0 + kK, n_out) - 1;
-    const int j_lo = (v[r0] - v_base) & ~3;
+    const bool has_rows = r0 < n_out;      // warps without rows only take part in the store
+    const uint32_t r_first = has_rows ? r0 : 0u;
+    const uint32_t r_last = has_rows ? min(r0 + kK, n_out) - 1 : 0u;
+    const int j_lo = (v[r_first] - v_base) & ~3;
     const int j_end = (v[r_last] - v_base) + TAPS;
-    const int n_chunks = (j_end - j_lo + 3) >> 2;
+    const int n_chunks = has_rows ? (j_end - j_lo + 3) >> 2 : 0;
     float2 acc[kK][kS];
 #pragma unroll
     for (int k = 0; k < kK; ++k)
@@ -677,7 +688,7 @@ __device__ __forceinline__ void warp_product_store_stereo(
         return j_lo + 4 * ((s & 1) ? (n_chunks - 1 - (s >> 1)) : (s >> 1));
     };
     float4 gv[kK], xv[kS][2];
-    {
+    if (has_rows) {
         const uint32_t j = (uint32_t)chunk_idx(0);
 #pragma unroll
         for (int m = 0; m < kS; ++m) {
@@ -730,18 +741,36 @@ __device__ __forceinline__ void warp_product_store_stereo(
 #pragma unroll
         for (int k = 0; k < kK; ++k) gv[k] = gn[k];
     }
-    // store: (L, R) of one frame is one 8-byte store
+    // ---- store, staged through shared memory so that global writes are whole 16-byte pieces
+    // of ONE member per 16 lanes (a warp instruction touches 2 members' buffers instead of 32:
+    // the buffers of different members are megabytes apart, and 32 pages per store instruction
+    // measurably throttled the kernel once the batch got large) ----
+    // staging layout: [member][kStageRows frames][2], member stride 33 frames (bank spread)
+    consumer_bar(bar_id);                 // every warp of the group is done reading the windows
 #pragma unroll
     for (int m = 0; m < kS; ++m) {
-        const uint32_t mem = lane + 32u * m;
-        if (mem < nm) {
-            float2 *out = reinterpret_cast<float2 *>(outp[mem]);
-            const uint64_t cap = capp[mem];
+        float2 *st = reinterpret_cast<float2 *>(stage) + (lane + 32u * m) * kStageStride + r0;
 #pragma unroll
-            for (int k = 0; k < kK; ++k) {
-                const uint64_t o = (uint64_t)o_start + r0 + k;
-                if (r0 + k < n_out && o < cap) out[o] = acc[k][m];
-            }
+        for (int k = 0; k < kK; ++k) st[k] = acc[k][m];
+    }
+    consumer_bar(bar_id);
+    // 16 lanes per member: lane part p writes frames 2p, 2p+1 (one float4)
+    const uint32_t gtid = r0 / kK * 32u + lane;           // 0..127 inside the group
+    for (uint32_t e = gtid; e < nm * 16u; e += 128u) {
+        const uint32_t mem = e >> 4, p = e & 15u;
+        const uint32_t row = 2u * p;
+        if (row >= n_out) continue;
+        const float2 *st = reinterpret_cast<const float2 *>(stage) + mem * kStageStride + row;
+        float *outm = outp[mem];
+        const uint64_t cap = capp[mem];
+        const uint64_t o = (uint64_t)o_start + row;
+        const bool two = row + 1 < n_out && o + 1 < cap;
+        if (two && ((reinterpret_cast<uintptr_t>(outm) & 15u) == 0)) {
+            const float2 a = st[0], b2 = st[1];
+            reinterpret_cast<float4 *>(outm)[o >> 1] = make_float4(a.x, a.y, b2.x, b2.y);
+        } else {
+            if (o < cap) reinterpret_cast<float2 *>(outm)[o] = st[0];
+            if (two) reinterpret_cast<float2 *>(outm)[o + 1] = st[1];
         }
     }
 }
@@ -1023,11 +1052,12 @@ conv_fast_ws_kernel(const __grid_constant__ ConvParams P, const __grid_constant_
             if (prof) { const long long tn = clock64(); pcw += (unsigned long long)(tn - tprev); tprev = tn; }
             const uint32_t n_out = M.n_out;
             const uint32_t r0 = cw * kK;
-            if (M.nm && r0 < n_out) {
+            if (M.nm) {
                 if (CH == 2)
                     warp_product_store_stereo<TAPS>(G, X, xs, mstride, M.d, M.v_base, n_out, r0, lane,
-                                                    M.nm, M.o_start, M.out, M.cap);
-                else
+                                                    M.nm, M.o_start, M.out, M.cap,
+                                                    const_cast<float *>(X), 2u + b);
+                else if (r0 < n_out)
                     warp_product_store<TAPS>(G, X, xs, M.d, M.v_base, n_out, r0, lane, ch, M.n_cols,
                                              M.o_start, M.out, M.cap);
             }
