@@ -388,11 +388,36 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     RSB_CUDA(cudaMemcpyAsync(W.d_units.p, hu, sizeof(UnitDev) * n_units, cudaMemcpyHostToDevice, sp));
     RSB_CUDA(cudaMemcpyAsync(W.d_jobs.p, hj, sizeof(JobDev) * n, cudaMemcpyHostToDevice, sp));
     RSB_CUDA(cudaMemsetAsync(W.d_counter.p, 0, sizeof(uint32_t) * 4, sp));
+    // host buffers that are equally sized and equally strided move with ONE 2-D copy
+    bool h2d_uniform = host_mem && n > 1, d2h_uniform = host_mem && n > 1 && n_units == 1;
+    ptrdiff_t in_pitch = 0, out_pitch = 0;
+    if (host_mem && n > 1) {
+        in_pitch = reinterpret_cast<const char *>(jobs[1].in) - reinterpret_cast<const char *>(jobs[0].in);
+        out_pitch = reinterpret_cast<char *>(jobs[1].out) - reinterpret_cast<char *>(jobs[0].out);
+        for (uint32_t i = 1; i < n; ++i) {
+            if (in_vals[i] != in_vals[0] || in_off[i] - in_off[i - 1] != in_off[1] - in_off[0] ||
+                reinterpret_cast<const char *>(jobs[i].in) - reinterpret_cast<const char *>(jobs[0].in) !=
+                    (ptrdiff_t)i * in_pitch)
+                h2d_uniform = false;
+            if (out_off[i] - out_off[i - 1] != out_off[1] - out_off[0] ||
+                reinterpret_cast<char *>(jobs[i].out) - reinterpret_cast<char *>(jobs[0].out) !=
+                    (ptrdiff_t)i * out_pitch)
+                d2h_uniform = false;
+        }
+        if (in_pitch < (ptrdiff_t)(in_vals[0] * sizeof(float))) h2d_uniform = false;
+        if (out_pitch <= 0) d2h_uniform = false;
+    }
     if (host_mem) {
-        for (uint32_t i = 0; i < n; ++i)
-            if (in_vals[i])
-                RSB_CUDA(cudaMemcpyAsync(h->d_stage_in.as<float>() + in_off[i], jobs[i].in,
-                                         in_vals[i] * sizeof(float), cudaMemcpyHostToDevice, s));
+        if (h2d_uniform && in_vals[0]) {
+            RSB_CUDA(cudaMemcpy2DAsync(h->d_stage_in.p, (in_off[1] - in_off[0]) * sizeof(float),
+                                       jobs[0].in, (size_t)in_pitch, in_vals[0] * sizeof(float), n,
+                                       cudaMemcpyHostToDevice, s));
+        } else {
+            for (uint32_t i = 0; i < n; ++i)
+                if (in_vals[i])
+                    RSB_CUDA(cudaMemcpyAsync(h->d_stage_in.as<float>() + in_off[i], jobs[i].in,
+                                             in_vals[i] * sizeof(float), cudaMemcpyHostToDevice, s));
+        }
     }
 
     // ---- launch ----
@@ -492,13 +517,24 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     rc = finalize_pending(h, W);
     if (host_mem) {
         const UnitDev *ub = W.h_units_back.as<UnitDev>();
-        for (uint32_t i = 0; i < n; ++i) {
-            const UnitDev &U = ub[W.job_unit[i]];
-            const uint64_t frames = std::min<uint64_t>(U.total_out, jobs[i].out_capacity);
-            if (frames)
-                RSB_CUDA(cudaMemcpyAsync(jobs[i].out, h->d_stage_out.as<float>() + out_off[i],
-                                         (size_t)frames * ch * sizeof(float),
-                                         cudaMemcpyDeviceToHost, s));
+        uint64_t min_cap = ~0ull;
+        for (uint32_t i = 0; i < n; ++i) min_cap = std::min<uint64_t>(min_cap, jobs[i].out_capacity);
+        if (d2h_uniform && ub[0].total_out <= min_cap) {
+            // one plan unit => every stream produced the same number of frames
+            const size_t width = (size_t)ub[0].total_out * ch * sizeof(float);
+            if (width)
+                RSB_CUDA(cudaMemcpy2DAsync(jobs[0].out, (size_t)out_pitch, h->d_stage_out.p,
+                                           (out_off[1] - out_off[0]) * sizeof(float), width, n,
+                                           cudaMemcpyDeviceToHost, s));
+        } else {
+            for (uint32_t i = 0; i < n; ++i) {
+                const UnitDev &U = ub[W.job_unit[i]];
+                const uint64_t frames = std::min<uint64_t>(U.total_out, jobs[i].out_capacity);
+                if (frames)
+                    RSB_CUDA(cudaMemcpyAsync(jobs[i].out, h->d_stage_out.as<float>() + out_off[i],
+                                             (size_t)frames * ch * sizeof(float),
+                                             cudaMemcpyDeviceToHost, s));
+            }
         }
         RSB_CUDA(cudaStreamSynchronize(s));
     }
