@@ -135,21 +135,13 @@ def barrier(dist, local):
 
 
 def reduce_max(dist, local, value: float) -> float:
-    if dist is None:
-        return value
-    import torch
-    t = torch.tensor([value], dtype=torch.float64, device=f"cuda:{local}")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
+    from resampler_b200.sharding import all_reduce_scalar
+    return all_reduce_scalar(dist, value, "max", f"cuda:{local}" if dist is not None else None)
 
 
 def reduce_sum(dist, local, value: float) -> float:
-    if dist is None:
-        return value
-    import torch
-    t = torch.tensor([value], dtype=torch.float64, device=f"cuda:{local}")
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return float(t.item())
+    from resampler_b200.sharding import all_reduce_scalar
+    return all_reduce_scalar(dist, value, "sum", f"cuda:{local}" if dist is not None else None)
 
 
 # ---------------------------------------------------------------------------------------------
