@@ -45,6 +45,10 @@ def parse_args():
     ap.add_argument("--seconds", type=float, default=60.0, help="audio seconds per stream")
     ap.add_argument("--kernel", default="auto", choices=["auto", "exact", "fast"])
     ap.add_argument("--channels", type=int, default=2, help="experiment only: channels per stream")
+    ap.add_argument("--in-hz", type=int, default=44100, help="experiment only")
+    ap.add_argument("--out-hz", type=int, default=48000, help="experiment only")
+    ap.add_argument("--latency", type=int, default=3, help="experiment only: 0..3 = 16..128 taps")
+    ap.add_argument("--call-frames", type=int, default=512, help="experiment only")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-slice-seconds", type=float, default=2.0)
@@ -427,9 +431,11 @@ def run_e2e(args, batch, lib, frames, n_streams, local, dist):
 
 
 def main():
-    global CHANNELS
+    global CHANNELS, IN_HZ, OUT_HZ, LATENCY, TAPS, CALL_FRAMES
     args = parse_args()
     CHANNELS = args.channels
+    IN_HZ, OUT_HZ, LATENCY, CALL_FRAMES = args.in_hz, args.out_hz, args.latency, args.call_frames
+    TAPS = 16 << LATENCY
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -374,7 +374,7 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     RSB_CUDA(W.d_segs.reserve(sizeof(rsb::PlanSeg) * seg_total));
     RSB_CUDA(W.d_tiles.reserve(sizeof(rsb::TileRec) * tile_total));
     RSB_CUDA(W.d_entries.reserve(sizeof(rsb::PlanEntry) * rsb::kTileOut * tile_total));
-    const uint32_t gs = use_fast ? rsb::fast_row_stride(h->taps, h->ratio) : 0;
+    const uint32_t gs = use_fast ? rsb::fast_row_stride(ch, h->taps, h->ratio) : 0;
     if (use_fast)
         RSB_CUDA(W.d_gtiles.reserve(sizeof(float) * rsb::kTileOut * gs * tile_total));
     RSB_CUDA(W.d_counter.reserve(sizeof(uint32_t) * 4));

@@ -23,6 +23,9 @@
 
 namespace rsb {
 
+// debug switch: false selects the two-CTA-per-SM kernel everywhere
+bool g_use_ws = true;
+
 // Optional per-phase cycle accounting (thread 0 of every CTA; enabled by a debug call).
 __device__ unsigned long long g_phase_cycles[8];
 __device__ int g_phase_enabled = 0;
@@ -59,6 +62,14 @@ __host__ inline FastGeom fast_geom(uint32_t taps, double ratio) {
     uint32_t mb = 2u * g.win_max;
     while (((mb >> 2) & 1u) == 0u) mb += 4;
     g.mb = mb;
+    return g;
+}
+
+// Stereo batches that go to the warp-specialised kernel keep their windows interleaved; only the
+// filter rows use `xs`, they are read as warp-wide broadcasts and need no bank padding.
+__host__ inline FastGeom fast_geom_for(uint32_t taps, double ratio, uint32_t channels, bool ws) {
+    FastGeom g = fast_geom(taps, ratio);
+    if (ws && channels == 2) g.xs = g.win_max;
     return g;
 }
 
@@ -554,6 +565,7 @@ __global__ void __launch_bounds__(kThreads) conv_fast_kernel(ConvParams P, FastG
 // consumers' registers come from the producers (setmaxnreg), exactly as many as the 8 compute
 // warps of the two-CTA-per-SM kernel above use.
 // ===========================================================================================
+template <int NM>
 struct TileMeta {
     int d[kKT];               // virtual window start v_k of row k (band start = v_k - v_base)
     uint32_t n_out, nm, n_cols, o_start;
@@ -562,8 +574,8 @@ struct TileMeta {
     uint32_t terminate;       // no more work: the consumer group leaves its loop
     int32_t v_base;
     int64_t H, n_valid;
-    float *out[kNC];          // per member
-    uint64_t cap[kNC];
+    float *out[NM];           // per member
+    uint64_t cap[NM];
 };
 
 constexpr int kWsThreads = 384;
@@ -576,16 +588,33 @@ __device__ __forceinline__ void producer_bar() {
 }
 
 // The product of one warp (8 rows x 128 columns) and its stores; shared by both kernels' maths.
-template <int TAPS>
+constexpr uint32_t kStageStride = 33;   // frames per member in the store staging area
+
+__device__ __forceinline__ void consumer_bar(uint32_t id) {
+    asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
+}
+
+template <int CH>
+__device__ __forceinline__ void staged_store(const float *stage, uint32_t nm, uint32_t n_out,
+                                             uint32_t o_start, float *const *outp,
+                                             const uint64_t *capp, uint32_t gtid);
+
+// STAGED (mono, warp-specialised kernel): every warp of the consumer group calls it, the tile is
+// staged in shared memory (`stage`, aliasing the dead input windows) and written with coalesced
+// 16-byte stores.  Otherwise: direct stores, only warps that own rows call it.
+template <int TAPS, bool STAGED = false>
 __device__ __forceinline__ void warp_product_store(const float *G, const float *X, uint32_t xs,
                                                    const int *v, int v_base, uint32_t n_out, uint32_t r0,
                                                    uint32_t lane, uint32_t ch, uint32_t n_cols,
                                                    uint32_t o_start, float *const *outp,
-                                                   const uint64_t *capp) {
-    const uint32_t r_last = min(r0 + kK, n_out) - 1;
-    const int j_lo = (v[r0] - v_base) & ~3;
+                                                   const uint64_t *capp, float *stage = nullptr,
+                                                   uint32_t bar_id = 0) {
+    const bool has_rows = r0 < n_out;
+    const uint32_t r_first = has_rows ? r0 : 0u;
+    const uint32_t r_last = has_rows ? min(r0 + kK, n_out) - 1 : 0u;
+    const int j_lo = (v[r_first] - v_base) & ~3;
     const int j_end = (v[r_last] - v_base) + TAPS;
-    const int n_chunks = (j_end - j_lo + 3) >> 2;
+    const int n_chunks = has_rows ? (j_end - j_lo + 3) >> 2 : 0;
     float2 acc[kK][kC];
 #pragma unroll
     for (int k = 0; k < kK; ++k)
@@ -602,7 +631,7 @@ __device__ __forceinline__ void warp_product_store(const float *G, const float *
         return (uint32_t)(j_lo + 4 * idx) * 4u;
     };
     float4 gv[kK], xv[kC];
-    {
+    if (has_rows) {
         const uint32_t jb = chunk_byte(0);
 #pragma unroll
         for (int c = 0; c < kC; ++c) xv[c] = lds128(xa[c] + jb);
@@ -630,6 +659,19 @@ __device__ __forceinline__ void warp_product_store(const float *G, const float *
 #pragma unroll
         for (int k = 0; k < kK; ++k) gv[k] = gn[k];
     }
+    if (STAGED) {
+        // mono: column == member; stage[member][row]
+        consumer_bar(bar_id);             // every warp of the group is done reading the windows
+#pragma unroll
+        for (int c = 0; c < kC; ++c) {
+            float *st = stage + (lane + 32u * c) * kStageStride + r0;
+#pragma unroll
+            for (int k = 0; k < kK; ++k) st[k] = __fadd_rn(acc[k][c].x, acc[k][c].y);
+        }
+        consumer_bar(bar_id);
+        staged_store<1>(stage, n_cols, n_out, o_start, outp, capp, r0 / kK * 32u + lane);
+        return;
+    }
 #pragma unroll
     for (int c = 0; c < kC; ++c) {
         const uint32_t col = lane + 32u * c;
@@ -653,10 +695,36 @@ __device__ __forceinline__ void warp_product_store(const float *G, const float *
 // as a broadcast FFMA2 operand (`FFMA2 Rd, Rg.F32, Rx.F32x2.HI_LO, Rd`), so nothing has to
 // be duplicated.  A thread owns 8 rows x 2 members; one chain per output, taps visited
 // outside-in (max |diff| to the oracle 3.6e-7 in the CPU simulation).
-constexpr uint32_t kStageStride = 33;   // frames per member in the store staging area
-
-__device__ __forceinline__ void consumer_bar(uint32_t id) {
-    asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
+// Writes the group's staged tile to global memory: stage is [member][kStageStride frames][CH]
+// f32; each float4 piece (4 / CH frames of one member) is one store, consecutive lanes write
+// consecutive pieces of the same member.  Called by all 128 threads of a consumer group after
+// the barrier that follows the staging writes.
+template <int CH>
+__device__ __forceinline__ void staged_store(const float *stage, uint32_t nm, uint32_t n_out,
+                                             uint32_t o_start, float *const *outp,
+                                             const uint64_t *capp, uint32_t gtid) {
+    constexpr uint32_t kFpp = 4 / CH;                    // frames per 16-byte piece
+    constexpr uint32_t kPieces = kKT / kFpp;             // pieces per member
+    for (uint32_t e = gtid; e < nm * kPieces; e += 128u) {
+        const uint32_t mem = e / kPieces, p = e - mem * kPieces;
+        const uint32_t row = kFpp * p;
+        if (row >= n_out) continue;
+        const float *st = stage + ((size_t)mem * kStageStride + row) * CH;
+        float *outm = outp[mem];
+        const uint64_t cap = capp[mem];
+        const uint64_t o = (uint64_t)o_start + row;
+        const bool full = row + kFpp <= n_out && o + kFpp <= cap;
+        if (full && ((reinterpret_cast<uintptr_t>(outm) & 15u) == 0)) {
+            reinterpret_cast<float4 *>(outm + o * CH)[0] = make_float4(st[0], st[1], st[2], st[3]);
+        } else {
+#pragma unroll
+            for (uint32_t f = 0; f < kFpp; ++f)
+                if (row + f < n_out && o + f < cap)
+#pragma unroll
+                    for (uint32_t c = 0; c < (uint32_t)CH; ++c)
+                        outm[(o + f) * CH + c] = st[f * CH + c];
+        }
+    }
 }
 
 // All four warps of a consumer group must call this together (it contains group barriers);
@@ -754,25 +822,7 @@ __device__ __forceinline__ void warp_product_store_stereo(
         for (int k = 0; k < kK; ++k) st[k] = acc[k][m];
     }
     consumer_bar(bar_id);
-    // 16 lanes per member: lane part p writes frames 2p, 2p+1 (one float4)
-    const uint32_t gtid = r0 / kK * 32u + lane;           // 0..127 inside the group
-    for (uint32_t e = gtid; e < nm * 16u; e += 128u) {
-        const uint32_t mem = e >> 4, p = e & 15u;
-        const uint32_t row = 2u * p;
-        if (row >= n_out) continue;
-        const float2 *st = reinterpret_cast<const float2 *>(stage) + mem * kStageStride + row;
-        float *outm = outp[mem];
-        const uint64_t cap = capp[mem];
-        const uint64_t o = (uint64_t)o_start + row;
-        const bool two = row + 1 < n_out && o + 1 < cap;
-        if (two && ((reinterpret_cast<uintptr_t>(outm) & 15u) == 0)) {
-            const float2 a = st[0], b2 = st[1];
-            reinterpret_cast<float4 *>(outm)[o >> 1] = make_float4(a.x, a.y, b2.x, b2.y);
-        } else {
-            if (o < cap) reinterpret_cast<float2 *>(outm)[o] = st[0];
-            if (two) reinterpret_cast<float2 *>(outm)[o + 1] = st[1];
-        }
-    }
+    staged_store<2>(stage, nm, n_out, o_start, outp, capp, r0 / kK * 32u + lane);
 }
 
 template <int TAPS, int CH>
@@ -782,9 +832,10 @@ conv_fast_ws_kernel(const __grid_constant__ ConvParams P, const __grid_constant_
     static_assert(CH == 1 || CH == 2, "warp-specialised kernel: mono or stereo");
     extern __shared__ __align__(1024) uint8_t smem_ws_raw[];   // TMA tensor boxes: 128-byte aligned
     float *smem = reinterpret_cast<float *>(smem_ws_raw);
-    __shared__ TileMeta meta[2];
-    __shared__ const float *p_in[2][kNC];     // producers only, per buffer
-    __shared__ const float *p_hist[2][kNC];
+    constexpr int kNM = kNC / CH;             // members per tile
+    __shared__ TileMeta<kNM> meta[2];
+    __shared__ const float *p_in[2][kNM];     // producers only, per buffer
+    __shared__ const float *p_hist[2][kNM];
     __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_tma[2];
     __shared__ uint32_t s_item[8];         // producers: work items fetched ahead (ring)
 
@@ -872,7 +923,7 @@ conv_fast_ws_kernel(const __grid_constant__ ConvParams P, const __grid_constant_
             RSB_WS_PHASE(0)
             float *G = smem + b * buf_floats;
             float *X = G + kKT * xs;
-            TileMeta &M = meta[b];
+            TileMeta<kNM> &M = meta[b];
             struct { TileRec rec; uint32_t t, m0, nm; } r;
             uint32_t g;
             r.t = item_tile(i, g);
@@ -951,7 +1002,7 @@ conv_fast_ws_kernel(const __grid_constant__ ConvParams P, const __grid_constant_
         auto finish = [&](uint32_t i) {
             const uint32_t b = i & 1u, use = i >> 1;
             float *X = smem + b * buf_floats + kKT * xs;
-            const TileMeta &M = meta[b];
+            const TileMeta<kNM> &M = meta[b];
             const uint32_t nm = M.nm;
             if (nm) {
                 TileRec rec;
@@ -1041,7 +1092,7 @@ conv_fast_ws_kernel(const __grid_constant__ ConvParams P, const __grid_constant_
         const uint32_t ctid = tid - 128 * wg, lane = ctid & 31u, cw = ctid >> 5;
         const float *G = smem + b * buf_floats;
         const float *X = G + kKT * xs;
-        const TileMeta &M = meta[b];
+        const TileMeta<kNM> &M = meta[b];
         uint32_t k = 0;
         const bool prof = g_phase_enabled != 0 && ctid == 0;
         unsigned long long pcw = 0, pcp = 0;
@@ -1057,9 +1108,10 @@ conv_fast_ws_kernel(const __grid_constant__ ConvParams P, const __grid_constant_
                     warp_product_store_stereo<TAPS>(G, X, xs, mstride, M.d, M.v_base, n_out, r0, lane,
                                                     M.nm, M.o_start, M.out, M.cap,
                                                     const_cast<float *>(X), 2u + b);
-                else if (r0 < n_out)
-                    warp_product_store<TAPS>(G, X, xs, M.d, M.v_base, n_out, r0, lane, ch, M.n_cols,
-                                             M.o_start, M.out, M.cap);
+                else
+                    warp_product_store<TAPS, true>(G, X, xs, M.d, M.v_base, n_out, r0, lane, ch,
+                                                   M.n_cols, M.o_start, M.out, M.cap,
+                                                   const_cast<float *>(X), 2u + b);
             }
             mbar_arrive(&bar_empty[b]);
             if (prof) { const long long tn = clock64(); pcp += (unsigned long long)(tn - tprev); tprev = tn; }
@@ -1073,8 +1125,6 @@ conv_fast_ws_kernel(const __grid_constant__ ConvParams P, const __grid_constant_
 
 }  // namespace
 
-// debug switch: 0 selects the two-CTA-per-SM kernel everywhere
-bool g_use_ws = true;
 void fast_set_warp_specialised(int on) { g_use_ws = on != 0; }
 
 void fast_phase_profile(int enable, unsigned long long *out8) {
@@ -1083,6 +1133,22 @@ void fast_phase_profile(int enable, unsigned long long *out8) {
     cudaMemcpyToSymbol(g_phase_cycles, zero, sizeof(zero));
     cudaMemcpyToSymbol(g_phase_enabled, &enable, sizeof(int));
 }
+
+namespace {
+size_t ws_smem_bytes(const FastGeom &g, uint32_t channels) {
+    return 2 * sizeof(float) *
+           ((size_t)kKT * g.xs + (channels == 2 ? (size_t)(kNC / 2) * g.mb : (size_t)kNC * g.xs));
+}
+// the warp-specialised kernel serves mono / stereo when two buffers fit next to ~6 KB static
+bool ws_applicable(uint32_t channels, uint32_t taps, double ratio) {
+    if (!g_use_ws || (channels != 1 && channels != 2)) return false;
+    const FastGeom g = fast_geom_for(taps, ratio, channels, true);
+    return ws_smem_bytes(g, channels) <= 220u * 1024u && g.win_max / 4 <= 64u;
+}
+FastGeom geom_in_use(uint32_t channels, uint32_t taps, double ratio) {
+    return fast_geom_for(taps, ratio, channels, ws_applicable(channels, taps, ratio));
+}
+}  // namespace
 
 bool fast_supported(uint32_t channels, uint32_t taps, double ratio) {
     if (channels == 0 || channels > (uint32_t)kNC) return false;
@@ -1093,7 +1159,9 @@ bool fast_supported(uint32_t channels, uint32_t taps, double ratio) {
 
 uint32_t fast_streams_per_group(uint32_t channels, uint32_t, double) { return kNC / channels; }
 
-uint32_t fast_row_stride(uint32_t taps, double ratio) { return fast_geom(taps, ratio).xs; }
+uint32_t fast_row_stride(uint32_t channels, uint32_t taps, double ratio) {
+    return geom_in_use(channels, taps, ratio).xs;
+}
 
 bool fast_make_input_tensor_map(CUtensorMap *out, const float *base, uint64_t stride_bytes,
                                 uint64_t total_frames, uint32_t n_members, uint32_t channels,
@@ -1114,8 +1182,8 @@ bool fast_make_input_tensor_map(CUtensorMap *out, const float *base, uint64_t st
         encode = (EncodeTiledFn)fn;
     }
     if (channels != 1 && channels != 2) return false;
-    const FastGeom geo = fast_geom(taps, ratio);
-    if (geo.xs > 256 || total_frames == 0 || total_frames >= (1ull << 31)) return false;
+    const FastGeom geo = geom_in_use(channels, taps, ratio);
+    if (geo.xs > 256 || geo.mb / 2 > 256 || total_frames == 0 || total_frames >= (1ull << 31)) return false;
     if ((reinterpret_cast<uintptr_t>(base) & 15u) || (stride_bytes & 15u) || stride_bytes == 0)
         return false;
     if (stride_bytes < total_frames * channels * 4ull) return false;
@@ -1135,7 +1203,8 @@ bool fast_make_input_tensor_map(CUtensorMap *out, const float *base, uint64_t st
 void launch_conv_fast(const ConvParams &p, const CUtensorMap *tmap, double ratio,
                       uint32_t max_items, int sm_count, cudaStream_t stream) {
     if (max_items == 0) return;
-    const FastGeom geo = fast_geom(p.taps, ratio);
+    const bool ws_ok = ws_applicable(p.channels, p.taps, ratio);
+    const FastGeom geo = fast_geom_for(p.taps, ratio, p.channels, ws_ok);
     const size_t smem = fast_smem_bytes(geo, p.channels);
     auto launch = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1147,8 +1216,7 @@ void launch_conv_fast(const ConvParams &p, const CUtensorMap *tmap, double ratio
         kern<<<grid, kThreads, smem, stream>>>(p, geo);
     };
     // warp-specialised persistent kernel (mono / stereo): two shared-memory buffers per CTA
-    const size_t ws_smem = 2 * sizeof(float) *
-        ((size_t)kKT * geo.xs + (p.channels == 2 ? (size_t)(kNC / 2) * geo.mb : (size_t)kNC * geo.xs));
+    const size_t ws_smem = ws_smem_bytes(geo, p.channels);
     auto launch_ws = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem);
         // one SM is left free: the persistent CTAs take a whole SM each, and the (serial,
@@ -1165,8 +1233,6 @@ void launch_conv_fast(const ConvParams &p, const CUtensorMap *tmap, double ratio
         }
         kern<<<grid, kWsThreads, ws_smem, stream>>>(pw, geo, tm);
     };
-    const bool ws_ok = g_use_ws && ws_smem <= 215u * 1024u && (p.channels == 1 || p.channels == 2) &&
-                       (geo.win_max / 4) <= 64u;
 #define RSB_FAST_DISPATCH(T)                                             \
     do {                                                                 \
         const bool tma_ok = (geo.win_max / 4) * p.channels <=            \

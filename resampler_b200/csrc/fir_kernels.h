@@ -57,7 +57,7 @@ void launch_conv_exact(const ConvParams &p, uint32_t max_items, int sm_count, cu
 // fast convolution (fir_fast.cu); returns false when the configuration is unsupported
 bool fast_supported(uint32_t channels, uint32_t taps, double ratio);
 uint32_t fast_streams_per_group(uint32_t channels, uint32_t taps, double ratio);
-uint32_t fast_row_stride(uint32_t taps, double ratio);   // gs: floats per G / X row
+uint32_t fast_row_stride(uint32_t channels, uint32_t taps, double ratio);   // floats per G row
 void launch_conv_fast(const ConvParams &p, const CUtensorMap *tmap, double ratio,
                       uint32_t max_items, int sm_count, cudaStream_t stream);
 void fast_set_warp_specialised(int on);
