@@ -608,7 +608,7 @@ __device__ __forceinline__ void warp_product_store(const float *G, const float *
                                                    uint32_t lane, uint32_t ch, uint32_t n_cols,
                                                    uint32_t o_start, float *const *outp,
                                                    const uint64_t *capp, float *stage = nullptr,
-                                                   uint32_t bar_id = 0) {
+                                                   uint32_t bar_id = 0, uint64_t *early = nullptr) {
     const bool has_rows = r0 < n_out;
     const uint32_t r_first = has_rows ? r0 : 0u;
     const uint32_t r_last = has_rows ? min(r0 + kK, n_out) - 1 : 0u;
@@ -662,6 +662,7 @@ __device__ __forceinline__ void warp_product_store(const float *G, const float *
     if (STAGED) {
         // mono: column == member; stage[member][row]
         consumer_bar(bar_id);             // every warp of the group is done reading the windows
+        if (early && r0 == 0 && lane == 0) mbar_arrive(early);
 #pragma unroll
         for (int c = 0; c < kC; ++c) {
             float *st = stage + (lane + 32u * c) * kStageStride + r0;
@@ -734,7 +735,7 @@ template <int TAPS>
 __device__ __forceinline__ void warp_product_store_stereo(
     const float *G, const float *X, uint32_t xs, uint32_t mb, const int *v, int v_base,
     uint32_t n_out, uint32_t r0, uint32_t lane, uint32_t nm, uint32_t o_start, float *const *outp,
-    const uint64_t *capp, float *stage, uint32_t bar_id) {
+    const uint64_t *capp, float *stage, uint32_t bar_id, uint64_t *early) {
     constexpr int kS = 2;      // members per thread: lane and lane + 32
     const bool has_rows = r0 < n_out;      // warps without rows only take part in the store
     const uint32_t r_first = has_rows ? r0 : 0u;
@@ -815,6 +816,7 @@ __device__ __forceinline__ void warp_product_store_stereo(
     // measurably throttled the kernel once the batch got large) ----
     // staging layout: [member][kStageRows frames][2], member stride 33 frames (bank spread)
     consumer_bar(bar_id);                 // every warp of the group is done reading the windows
+    if (early && r0 == 0 && lane == 0) mbar_arrive(early);
 #pragma unroll
     for (int m = 0; m < kS; ++m) {
         float2 *st = reinterpret_cast<float2 *>(stage) + (lane + 32u * m) * kStageStride + r0;
@@ -836,7 +838,10 @@ conv_fast_ws_kernel(const __grid_constant__ ConvParams P, const __grid_constant_
     __shared__ TileMeta<kNM> meta[2];
     __shared__ const float *p_in[2][kNM];     // producers only, per buffer
     __shared__ const float *p_hist[2][kNM];
-    __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_tma[2];
+    // full: producer -> consumers (tile ready).  empty_x: consumers -> producer, the tile's inputs
+    // (windows + filter rows) have been read, the next tile's windows may be fetched while the
+    // group is still storing.  empty: the stores are done, metadata / filter tile may be replaced.
+    __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_empty_x[2], bar_tma[2];
     __shared__ uint32_t s_item[8];         // producers: work items fetched ahead (ring)
 
     constexpr uint32_t ch = CH;
@@ -853,6 +858,7 @@ conv_fast_ws_kernel(const __grid_constant__ ConvParams P, const __grid_constant_
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bar_full[b], 1);
             mbar_init(&bar_empty[b], 128);
+            mbar_init(&bar_empty_x[b], 1);
             mbar_init(&bar_tma[b], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -918,9 +924,6 @@ conv_fast_ws_kernel(const __grid_constant__ ConvParams P, const __grid_constant_
         };
         auto issue = [&](uint32_t i, const TileRec &rec) {
             const uint32_t b = i & 1u, use = i >> 1;
-            RSB_WS_PHASE(1)
-            if (use > 0) mbar_wait(&bar_empty[b], (use - 1) & 1u);
-            RSB_WS_PHASE(0)
             float *G = smem + b * buf_floats;
             float *X = G + kKT * xs;
             TileMeta<kNM> &M = meta[b];
@@ -930,6 +933,21 @@ conv_fast_ws_kernel(const __grid_constant__ ConvParams P, const __grid_constant_
             r.rec = rec;
             r.m0 = g * spg;
             r.nm = r.m0 >= rec.n_members ? 0u : min(spg, rec.n_members - r.m0);
+            const int64_t rH = (int64_t)r.rec.hist_len0;
+            // one tensor copy for the whole group when the window lies in the new input
+            const bool tensor = r.nm != 0 && P.tmap_valid != 0 && (int64_t)r.rec.v_base >= rH;
+            RSB_WS_PHASE(1)
+            // early: the previous tile of this buffer has been read -> fetch the windows now
+            if (use > 0) mbar_wait(&bar_empty_x[b], (use - 1) & 1u);
+            if (tensor && ptid == 0) {
+                fence_proxy_async();   // the consumers' reads of this buffer are done
+                const uint32_t box_bytes = (kNC / CH) * mstride * 4u;   // full box, all members
+                mbar_arrive_expect_tx(&bar_tma[b], box_bytes + kKT * xs * 4u);
+                tensor_g2s_2d(X, &tmap, (int)((int64_t)r.rec.v_base - rH), (int)r.m0, &bar_tma[b]);
+            }
+            // late: the previous tile's stores are done -> metadata and filter tile
+            if (use > 0) mbar_wait(&bar_empty[b], (use - 1) & 1u);
+            RSB_WS_PHASE(0)
             if (ptid == 0) {
                 M.terminate = 0;
                 M.nm = r.nm;
@@ -951,18 +969,12 @@ conv_fast_ws_kernel(const __grid_constant__ ConvParams P, const __grid_constant_
                 cp_async8(&M.cap[ptid], &jobs[ptid].out_capacity);
             }
             cp_async_commit();
-            const int64_t rH = (int64_t)r.rec.hist_len0;
             const Geo q = window(r.rec, rH, rH + (int64_t)r.rec.total_frames);
-            // one tensor copy for the whole group when the window lies in the new input
-            const bool tensor = P.tmap_valid != 0 && (int64_t)r.rec.v_base >= rH;
             if (ptid == 0) M.tensor_path = tensor ? 1u : 0u;
             if (tensor) {
                 if (ptid == 0) {
-                    fence_proxy_async();   // the consumers' reads of this buffer are done
-                    const uint32_t box_bytes = (kNC / CH) * mstride * 4u;   // full box, all members
-                    mbar_arrive_expect_tx(&bar_tma[b], box_bytes + kKT * xs * 4u);
+                    fence_proxy_async();   // the staging writes of the last tile are done
                     bulk_g2s(G, P.gtiles + (size_t)r.t * kKT * xs, kKT * xs * 4u, &bar_tma[b]);
-                    tensor_g2s_2d(X, &tmap, (int)((int64_t)r.rec.v_base - rH), (int)r.m0, &bar_tma[b]);
                 }
                 return;
             }
@@ -1093,6 +1105,7 @@ conv_fast_ws_kernel(const __grid_constant__ ConvParams P, const __grid_constant_
         const float *G = smem + b * buf_floats;
         const float *X = G + kKT * xs;
         const TileMeta<kNM> &M = meta[b];
+        const bool stage_in_g = (uint32_t)kKT * xs >= (uint32_t)kNC * kStageStride;
         uint32_t k = 0;
         const bool prof = g_phase_enabled != 0 && ctid == 0;
         unsigned long long pcw = 0, pcp = 0;
@@ -1104,14 +1117,21 @@ conv_fast_ws_kernel(const __grid_constant__ ConvParams P, const __grid_constant_
             const uint32_t n_out = M.n_out;
             const uint32_t r0 = cw * kK;
             if (M.nm) {
+                // the store staging area aliases the (dead) filter tile when it is big enough:
+                // the windows can then be released before the stores
+                float *stage = const_cast<float *>(stage_in_g ? G : X);
+                uint64_t *early = stage_in_g ? &bar_empty_x[b] : nullptr;
                 if (CH == 2)
                     warp_product_store_stereo<TAPS>(G, X, xs, mstride, M.d, M.v_base, n_out, r0, lane,
-                                                    M.nm, M.o_start, M.out, M.cap,
-                                                    const_cast<float *>(X), 2u + b);
+                                                    M.nm, M.o_start, M.out, M.cap, stage, 2u + b,
+                                                    early);
                 else
                     warp_product_store<TAPS, true>(G, X, xs, M.d, M.v_base, n_out, r0, lane, ch,
-                                                   M.n_cols, M.o_start, M.out, M.cap,
-                                                   const_cast<float *>(X), 2u + b);
+                                                   M.n_cols, M.o_start, M.out, M.cap, stage, 2u + b,
+                                                   early);
+                if (!stage_in_g && ctid == 0) mbar_arrive(&bar_empty_x[b]);
+            } else if (ctid == 0) {
+                mbar_arrive(&bar_empty_x[b]);
             }
             mbar_arrive(&bar_empty[b]);
             if (prof) { const long long tn = clock64(); pcp += (unsigned long long)(tn - tprev); tprev = tn; }
