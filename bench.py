@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=1024, help="streams per GPU")
     ap.add_argument("--seconds", type=float, default=60.0, help="audio seconds per stream")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "exact", "fast"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "exact", "fast", "tensor"])
     ap.add_argument("--channels", type=int, default=2, help="experiment only: channels per stream")
     ap.add_argument("--in-hz", type=int, default=44100, help="experiment only")
     ap.add_argument("--out-hz", type=int, default=48000, help="experiment only")
@@ -229,7 +229,8 @@ def run_ours(args):
     lib = _lib.load()
     n_streams = args.streams
     frames = int(round(args.seconds * IN_HZ))
-    kern = {"auto": Kernel.AUTO, "exact": Kernel.EXACT, "fast": Kernel.FAST}[args.kernel]
+    kern = {"auto": Kernel.AUTO, "exact": Kernel.EXACT, "fast": Kernel.FAST,
+            "tensor": Kernel.TENSOR}[args.kernel]
     batch = FirBatch(n_streams, CHANNELS, IN_HZ, OUT_HZ, Latency(LATENCY), Attenuation(ATTENUATION),
                      device=local, kernel=kern)
     in_stride = frames * CHANNELS

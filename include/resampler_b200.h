@@ -63,8 +63,13 @@ enum rsb_memspace { RSB_MEM_DEVICE = 0, /* pointers are device pointers on the h
  *          output samples are bit-identical to that path.
  *   FAST : interpolates the two phase rows once per output frame and reuses the row for
  *          every stream/channel of the tile; samples within 1e-6 absolute of EXACT.
+ *   TENSOR: the same product on the tcgen05 tensor cores with every operand split into two
+ *          TF32 parts (3xTF32, fp32 accumulation in tensor memory); samples within 1e-6
+ *          absolute of EXACT.  Serves batches whose streams share one plan and whose inputs
+ *          lie at one constant stride (mono / stereo); other batches fall back to FAST / EXACT.
  *   AUTO : FAST where it applies (stream count, ratio), else EXACT. */
-enum rsb_kernel { RSB_KERNEL_AUTO = 0, RSB_KERNEL_EXACT = 1, RSB_KERNEL_FAST = 2 };
+enum rsb_kernel { RSB_KERNEL_AUTO = 0, RSB_KERNEL_EXACT = 1, RSB_KERNEL_FAST = 2,
+                  RSB_KERNEL_TENSOR = 3 };
 
 enum rsb_flags {
     RSB_FLAG_NONE = 0,
@@ -91,6 +96,8 @@ void rsb_fir_destroy(rsb_fir *h);
 int rsb_fir_set_kernel(rsb_fir *h, int kernel);
 
 uint32_t rsb_fir_channels(const rsb_fir *h);
+/* Kernel (rsb_kernel, never AUTO) the most recent batch actually ran on; AUTO before the first. */
+int rsb_fir_last_kernel(const rsb_fir *h);
 uint32_t rsb_fir_n_streams(const rsb_fir *h);
 uint32_t rsb_fir_taps(const rsb_fir *h);
 double rsb_fir_ratio(const rsb_fir *h);
@@ -159,6 +166,9 @@ int rsb_fir_conv_times(rsb_fir *h, float *ms, size_t max, size_t *n);
  * [1] TMA issue + zero fill, [2] banded-row build, [3] TMA wait, [4] de-interleave,
  * [5] register-tiled product, [6] store.  Returns and clears the counters; sets the enable flag. */
 int rsb_debug_phase_cycles(rsb_fir *h, int enable, uint64_t *out8);
+/* debug: per-role SM cycle totals of the tensor kernel (CTA 0; the index list is in
+ * fir_tensor.cu).  Returns and clears the 16 counters; sets the enable flag. */
+int rsb_debug_tc_cycles(rsb_fir *h, int enable, uint64_t *out16);
 /* kernels launched on this handle since creation (your own count for gpu_launches) */
 uint64_t rsb_fir_launch_count(const rsb_fir *h);
 /* the handle's cudaStream_t, as an opaque pointer */

@@ -29,6 +29,7 @@ SIGNATURES = {
     "rsb_fir_destroy": (None, [C.c_void_p]),
     "rsb_fir_set_kernel": (C.c_int, [C.c_void_p, C.c_int]),
     "rsb_fir_channels": (C.c_uint32, [C.c_void_p]),
+    "rsb_fir_last_kernel": (C.c_int, [C.c_void_p]),
     "rsb_fir_n_streams": (C.c_uint32, [C.c_void_p]),
     "rsb_fir_taps": (C.c_uint32, [C.c_void_p]),
     "rsb_fir_ratio": (C.c_double, [C.c_void_p]),
@@ -52,6 +53,7 @@ SIGNATURES = {
     "rsb_fir_timer_stop": (C.c_int, [C.c_void_p, f32p]),
     "rsb_fir_conv_times": (C.c_int, [C.c_void_p, f32p, C.c_size_t, szp]),
     "rsb_debug_phase_cycles": (C.c_int, [C.c_void_p, C.c_int, u64p]),
+    "rsb_debug_tc_cycles": (C.c_int, [C.c_void_p, C.c_int, u64p]),
     "rsb_fir_launch_count": (C.c_uint64, [C.c_void_p]),
     "rsb_fir_cuda_stream": (C.c_void_p, [C.c_void_p]),
     "rsb_alloc_pinned": (C.c_void_p, [C.c_size_t]),

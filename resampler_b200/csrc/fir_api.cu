@@ -94,7 +94,7 @@ struct Pending {
 // that the (serial) plan of submit i+1 can run on the plan stream while the convolution of
 // submit i is still running on the main stream.
 struct Workspace {
-    DevBuf d_units, d_jobs, d_segs, d_calls, d_tiles, d_entries, d_gtiles, d_counter;
+    DevBuf d_units, d_jobs, d_segs, d_calls, d_tiles, d_entries, d_gtiles, d_tct, d_counter;
     PinBuf h_units, h_jobs, h_units_back, h_calls_back;
     std::vector<uint32_t> job_unit;          // unit of each job of the batch
     std::vector<uint64_t> job_out_capacity;  // frames
@@ -115,6 +115,7 @@ struct rsb_fir {
     int latency = 0, attenuation = 0;
     double ratio = 0.0;
     int kernel_mode = RSB_KERNEL_AUTO;
+    int last_kernel = RSB_KERNEL_AUTO;   // kernel the most recent batch ran on
     std::shared_ptr<const rsb::FirTable> table;
     float *d_coeffs = nullptr;
     rsb::StreamStateDev st{};
@@ -369,14 +370,37 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
         U.n_members += 1;
     }
 
+    // member inputs at one constant stride (and one plan unit): the batch's input is a 2-D tensor
+    uint64_t in_stride = 0;
+    bool in_uniform = false;
+    if (n_units == 1 && (ch == 1 || ch == 2) && unit_keys[0].total_frames > 0) {
+        const uintptr_t base = reinterpret_cast<uintptr_t>(hj[0].in);
+        in_stride = n > 1 ? (uint64_t)(reinterpret_cast<uintptr_t>(hj[1].in) - base) : 0;
+        in_uniform = n == 1 || reinterpret_cast<uintptr_t>(hj[1].in) > base;
+        for (uint32_t i = 1; in_uniform && i < n; ++i)
+            in_uniform = reinterpret_cast<uintptr_t>(hj[i].in) == base + (uint64_t)i * in_stride;
+        if (n == 1) in_stride = ((uint64_t)unit_keys[0].total_frames * ch * 4 + 15) & ~15ull;
+    }
+    // tensor-core kernel: needs that tensor view (TMA streams the input chunk by chunk)
+    bool use_tc = false;
+    CUtensorMap tc_tmap;
+    if (h->kernel_mode == RSB_KERNEL_TENSOR && in_uniform && rsb::tc_supported(ch, h->taps, h->ratio))
+        use_tc = rsb::tc_make_input_tensor_map(&tc_tmap, hj[0].in, in_stride,
+                                               unit_keys[0].total_frames, n, ch);
+
     RSB_CUDA(W.d_units.reserve(sizeof(UnitDev) * n_units));
     RSB_CUDA(W.d_jobs.reserve(sizeof(JobDev) * n));
     RSB_CUDA(W.d_segs.reserve(sizeof(rsb::PlanSeg) * seg_total));
     RSB_CUDA(W.d_tiles.reserve(sizeof(rsb::TileRec) * tile_total));
     RSB_CUDA(W.d_entries.reserve(sizeof(rsb::PlanEntry) * rsb::kTileOut * tile_total));
     const uint32_t gs = use_fast ? rsb::fast_row_stride(ch, h->taps, h->ratio) : 0;
-    if (use_fast)
+    if (use_tc) {
+        RSB_CUDA(W.d_gtiles.reserve(sizeof(float) * rsb::tc_gmat_floats_per_tile(h->taps, h->ratio) *
+                                    tile_total));
+        RSB_CUDA(W.d_tct.reserve(sizeof(rsb::TcTile) * tile_total));
+    } else if (use_fast) {
         RSB_CUDA(W.d_gtiles.reserve(sizeof(float) * rsb::kTileOut * gs * tile_total));
+    }
     RSB_CUDA(W.d_counter.reserve(sizeof(uint32_t) * 4));
     if (rec_calls) {
         RSB_CUDA(W.d_calls.reserve(sizeof(rsb::CallCounts) * std::max<uint64_t>(call_total, 1)));
@@ -440,7 +464,11 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     rsb::launch_tiles(W.d_units.as<UnitDev>(), n_units, W.d_segs.as<rsb::PlanSeg>(),
                       W.d_tiles.as<rsb::TileRec>(), W.d_entries.as<rsb::PlanEntry>(),
                       (uint32_t)max_tiles_unit, h->taps, h->d_coeffs,
-                      use_fast ? W.d_gtiles.as<float>() : nullptr, gs, s);
+                      use_fast && !use_tc ? W.d_gtiles.as<float>() : nullptr, gs, s);
+    if (use_tc)
+        rsb::launch_tc_gmat(W.d_units.as<UnitDev>(), W.d_tiles.as<rsb::TileRec>(),
+                            W.d_entries.as<rsb::PlanEntry>(), h->d_coeffs, W.d_gtiles.as<float>(),
+                            W.d_tct.as<rsb::TcTile>(), h->taps, h->ratio, (uint32_t)tile_total, s);
     rsb::ConvParams P;
     P.units = W.d_units.as<UnitDev>();
     P.jobs = W.d_jobs.as<JobDev>();
@@ -460,34 +488,39 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     // single plan unit with equally strided member inputs: one TMA tensor map for the batch
     CUtensorMap tmap;
     P.tmap_valid = 0;
-    if (use_fast && n_units == 1 && n >= 1 && (ch == 1 || ch == 2)) {
-        const JobDev *sorted = hj;   // grouped by unit == all jobs, in member order
-        const uintptr_t base = reinterpret_cast<uintptr_t>(sorted[0].in);
-        uint64_t stride = n > 1 ? (uint64_t)(reinterpret_cast<uintptr_t>(sorted[1].in) - base) : 0;
-        bool uniform = n == 1 || reinterpret_cast<uintptr_t>(sorted[1].in) > base;
-        for (uint32_t i = 1; uniform && i < n; ++i)
-            uniform = reinterpret_cast<uintptr_t>(sorted[i].in) == base + (uint64_t)i * stride;
-        if (n == 1) stride = ((uint64_t)unit_keys[0].total_frames * ch * 4 + 15) & ~15ull;
-        if (uniform && unit_keys[0].total_frames > 0 &&
-            rsb::fast_make_input_tensor_map(&tmap, sorted[0].in, stride, unit_keys[0].total_frames, n,
-                                            ch, h->taps, h->ratio))
-            P.tmap_valid = 1;
-        if (getenv("RSB_DEBUG"))
-            fprintf(stderr, "[rsb] tensor map: uniform=%d stride=%llu frames=%llu n=%u valid=%u\n",
-                    (int)uniform, (unsigned long long)stride,
-                    (unsigned long long)unit_keys[0].total_frames, n, P.tmap_valid);
-    }
+    if (use_fast && !use_tc && in_uniform &&
+        rsb::fast_make_input_tensor_map(&tmap, hj[0].in, in_stride, unit_keys[0].total_frames, n, ch,
+                                        h->taps, h->ratio))
+        P.tmap_valid = 1;
     const uint32_t max_items = (uint32_t)(tile_total * max_groups);
     const int ring = (int)(h->conv_batches % rsb_fir::kConvRing);
     RSB_CUDA(cudaEventRecord(h->ev_conv[ring][0], s));
-    if (use_fast)
+    if (use_tc) {
+        rsb::TcParams T;
+        T.units = P.units;
+        T.jobs = P.jobs;
+        T.tct = W.d_tct.as<rsb::TcTile>();
+        T.gmat = W.d_gtiles.as<float>();
+        T.work_counter = P.work_counter;
+        T.channels = ch;
+        const uint32_t mpg = rsb::tc_rows_per_group() / ch;
+        T.groups = (n + mpg - 1) / mpg;
+        // a run of consecutive tiles is one work item: long enough to amortise filling the input
+        // ring (~6 tiles), short enough that every CTA gets several items
+        const uint64_t want = (tile_total * T.groups) / ((uint64_t)h->sm_count * 8u) + 1;
+        T.run_tiles = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 32), 512);
+        T.kt_max = rsb::tc_kt_extent(h->taps, h->ratio);
+        rsb::launch_conv_tc(T, tc_tmap, h->sm_count, s);
+    } else if (use_fast) {
         rsb::launch_conv_fast(P, P.tmap_valid ? &tmap : nullptr, h->ratio, max_items, h->sm_count, s);
-    else
+    } else {
         rsb::launch_conv_exact(P, max_items, h->sm_count, s);
+    }
+    h->last_kernel = use_tc ? RSB_KERNEL_TENSOR : use_fast ? RSB_KERNEL_FAST : RSB_KERNEL_EXACT;
     RSB_CUDA(cudaEventRecord(h->ev_conv[ring][1], s));
     h->conv_batches += 1;
     rsb::launch_update(W.d_units.as<UnitDev>(), W.d_jobs.as<JobDev>(), n, h->st, ch, s);
-    h->launches += 5;
+    h->launches += use_tc ? 6 : 5;
     RSB_CUDA(cudaGetLastError());
     RSB_CUDA(cudaEventRecord(W.ev_done, s));
     h->submits += 1;
@@ -665,7 +698,7 @@ void rsb_fir_destroy(rsb_fir *h) {
     cudaFree(h->st.hist[1]);
     for (Workspace &W : h->ws) {
         for (DevBuf *b : {&W.d_units, &W.d_jobs, &W.d_segs, &W.d_calls, &W.d_tiles, &W.d_entries,
-                          &W.d_gtiles, &W.d_counter})
+                          &W.d_gtiles, &W.d_tct, &W.d_counter})
             b->release();
         for (PinBuf *b : {&W.h_units, &W.h_jobs, &W.h_units_back, &W.h_calls_back}) b->release();
         if (W.ev_plan) cudaEventDestroy(W.ev_plan);
@@ -685,8 +718,10 @@ void rsb_fir_destroy(rsb_fir *h) {
 
 int rsb_fir_set_kernel(rsb_fir *h, int kernel) {
     if (check_handle(h)) return RSB_ERR_INVALID_ARGUMENT;
-    if (kernel < RSB_KERNEL_AUTO || kernel > RSB_KERNEL_FAST)
+    if (kernel < RSB_KERNEL_AUTO || kernel > RSB_KERNEL_TENSOR)
         return fail(RSB_ERR_INVALID_ARGUMENT, "bad kernel id");
+    if (kernel == RSB_KERNEL_TENSOR && !rsb::tc_supported(h->channels, h->taps, h->ratio))
+        return fail(RSB_ERR_INVALID_ARGUMENT, "tensor kernel does not support this configuration");
     if (kernel == RSB_KERNEL_FAST && !rsb::fast_supported(h->channels, h->taps, h->ratio))
         return fail(RSB_ERR_INVALID_ARGUMENT, "fast kernel does not support this configuration");
     h->kernel_mode = kernel;
@@ -694,6 +729,7 @@ int rsb_fir_set_kernel(rsb_fir *h, int kernel) {
 }
 
 uint32_t rsb_fir_channels(const rsb_fir *h) { return h ? h->channels : 0; }
+int rsb_fir_last_kernel(const rsb_fir *h) { return h ? h->last_kernel : RSB_KERNEL_AUTO; }
 uint32_t rsb_fir_n_streams(const rsb_fir *h) { return h ? h->n_streams : 0; }
 uint32_t rsb_fir_taps(const rsb_fir *h) { return h ? h->taps : 0; }
 double rsb_fir_ratio(const rsb_fir *h) { return h ? h->ratio : 0.0; }
@@ -930,6 +966,15 @@ int rsb_debug_phase_cycles(rsb_fir *h, int enable, uint64_t *out8) {
     RSB_CUDA(cudaStreamSynchronize(h->stream));
     static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "u64");
     rsb::fast_phase_profile(enable, reinterpret_cast<unsigned long long *>(out8));
+    RSB_CUDA(cudaGetLastError());
+    return RSB_OK;
+}
+
+int rsb_debug_tc_cycles(rsb_fir *h, int enable, uint64_t *out16) {
+    if (check_handle(h)) return RSB_ERR_INVALID_ARGUMENT;
+    RSB_CUDA(cudaSetDevice(h->device));
+    RSB_CUDA(cudaStreamSynchronize(h->stream));
+    rsb::tc_phase_profile(enable, reinterpret_cast<unsigned long long *>(out16));
     RSB_CUDA(cudaGetLastError());
     return RSB_OK;
 }

@@ -20,6 +20,7 @@
 // the bar is 1e-6.  Order differs from the reference's 16-lane AVX-512 order on purpose;
 // the bit-identical order is the EXACT kernel (fir_kernels.cu).
 #include "fir_kernels.h"
+#include "sm100_ptx.cuh"
 
 namespace rsb {
 
@@ -31,6 +32,8 @@ __device__ unsigned long long g_phase_cycles[8];
 __device__ int g_phase_enabled = 0;
 
 namespace {
+
+using namespace ptx;
 
 constexpr int kKT = (int)kTileOut;   // output frames per tile (32)
 constexpr int kNC = 128;       // columns per tile
@@ -95,66 +98,6 @@ __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
 __device__ __forceinline__ void ffma2_u64(float2 &d, const uint64_t a, const uint64_t b) {
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(reinterpret_cast<uint64_t &>(d)) : "l"(a), "l"(b));
 }
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-// TMA bulk copy global -> shared (SASS: UBLKCP), completion counted in bytes on `bar`
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-            "r"(smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                 : "r"(addr));
-    return v;
-}
-// TMA tiled tensor copy global -> shared of one 2-D box (SASS: UTMALDG)
-__device__ __forceinline__ void tensor_g2s_2d(void *dst, const CUtensorMap *tm, int c0, int c1,
-                                              uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
-        "[%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
-        "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-
 // Element-wise staging of one float4 `sub` of the 4-frame group starting at virtual frame vg
 // (edges of the window, the seam, and channel counts without a specialised path).
 __device__ __forceinline__ void stage_slow(float *X, uint32_t xs, uint32_t col0, uint32_t ch,
@@ -580,9 +523,6 @@ struct TileMeta {
 
 constexpr int kWsThreads = 384;
 
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void producer_bar() {
     asm volatile("bar.sync 1, 128;" ::: "memory");
 }

@@ -76,4 +76,37 @@ void launch_expand_plan(const UnitDev *units, uint32_t unit, const PlanEntry *en
 void launch_fill_synthetic(float *dst, uint32_t first_stream, uint32_t n_streams, uint64_t frames,
                            uint32_t channels, uint32_t rate_hz, uint64_t seed, cudaStream_t stream);
 
+// ---- tensor-core (tcgen05) convolution, fir_tensor.cu ----
+// Per-tile record of the tensor kernel: the tile's K range in virtual frames.
+struct TcTile {
+    int32_t k0;        // first virtual frame of the tile's K range (multiple of 8)
+    uint32_t kt;       // K extent in frames (multiple of 8)
+    uint32_t n_out;
+    uint32_t o_start;
+};
+struct TcParams {
+    const UnitDev *units;     // exactly one plan unit
+    const JobDev *jobs;
+    const TcTile *tct;        // [tile]
+    const float *gmat;        // [tile][hi, lo][kt_max / 4][32][4]
+    uint32_t *work_counter;   // zeroed per submit
+    uint32_t channels;
+    uint32_t groups;          // member groups of 128 / channels streams
+    uint32_t run_tiles;       // consecutive tiles per work item
+    uint32_t kt_max;
+};
+bool tc_supported(uint32_t channels, uint32_t taps, double ratio);
+uint32_t tc_kt_extent(uint32_t taps, double ratio);
+size_t tc_gmat_floats_per_tile(uint32_t taps, double ratio);
+uint32_t tc_rows_per_group();
+// 2-D tensor map over equally strided member inputs: box = 16 frames x (128 / channels) members
+bool tc_make_input_tensor_map(CUtensorMap *out, const float *base, uint64_t stride_bytes,
+                              uint64_t total_frames, uint32_t n_members, uint32_t channels);
+void launch_tc_gmat(const UnitDev *units, const TileRec *tiles, const PlanEntry *entries,
+                    const float *coeffs, float *gmat, TcTile *tct, uint32_t taps, double ratio,
+                    uint32_t tile_cap, cudaStream_t stream);
+void launch_conv_tc(const TcParams &p, const CUtensorMap &tmap, int sm_count, cudaStream_t stream);
+// debug: returns and clears the tensor kernel's per-role cycle counters, sets the enable flag
+void tc_phase_profile(int enable, unsigned long long *out16);
+
 }  // namespace rsb

@@ -1,0 +1,626 @@
+// fir_tensor.cu -- the tensor-core convolution kernel for sm_100a (tcgen05 + TMEM + TMA).
+//
+// Formulation.  Same banded product as the FFMA2 kernel (fir_fast.cu): for a tile of 32
+// consecutive output frames,  OUT[row][k] = sum_j X[row][j] * G[k][j]  with row = one channel of
+// one member stream and G the tile's interpolated, banded filter rows (the reference blends two
+// dot products per output, fir/avx512.rs:41-45; blending the rows first is the same linear map).
+// Here the product runs on the 5th-generation tensor cores as  D[128 rows x 32 outputs] +=
+// A[128 x 8] * B[32 x 8]^T  per K step of 8 input frames (tcgen05.mma kind::tf32, M = 128,
+// N = 32, accumulator in tensor memory).
+//
+// Precision.  TF32 keeps 11 significant bits, so every operand is split into a TF32 "hi" part and
+// a TF32 "lo" part (x = hi + lo + O(2^-22 |x|)) and three products are accumulated in fp32:
+// lo*hi, hi*lo, then hi*hi ("3xTF32"); the small terms first and the hi*hi K steps outside-in
+// (both ends of the band towards its centre) so that the large centre taps are added last.
+// The parity bar against the oracle is 1e-6 absolute, as for the FFMA2 kernel.
+//
+// Data flow of one CTA (persistent, one per SM, 11 warps):
+//   * work item = (run of consecutive tiles) x (group of 128 rows = 128 / CH member streams).
+//     A run walks forward in time, so every input frame is fetched from HBM/L2 ONCE per row
+//     and kept in a ring while the ~6 tiles whose windows cover it are computed (the FFMA2
+//     kernel re-fetches each tile's whole window: 5.4x the input through L2, 1.7x from HBM).
+//   * warp 9 (one thread): work scheduler (atomic counter) and TMA producer of the input: one
+//     2-D tensor copy per 16-frame chunk (box = 16 frames x 128/CH members, 128B/64B swizzle).
+//   * warps 4-7 ("splitter", thread == row): read the chunk from shared memory, de-interleave,
+//     split into hi/lo and write both into TMEM rings (tcgen05.st): ring column == input frame,
+//     TMEM lane == row.  The rings are the A operands, no second shared-memory copy exists.
+//   * warp 10 (one thread): TMA bulk copies of the tile's G matrices (hi and lo, prebuilt in the
+//     canonical no-swizzle K-major core-matrix layout by tc_gmat_kernel) into a 3-stage ring.
+//   * warp 8 (one thread): issues the tcgen05.mma (66 per 128-tap tile), commits to mbarriers.
+//   * warps 0-3 (epilogue): tcgen05.ld of the 128 x 32 accumulator, staging through shared
+//     memory, coalesced 16-byte stores.  Two accumulators, so tile t+1 runs under the stores.
+//
+// TMEM map (512 columns x 128 lanes): [0,224) X hi ring, [224,448) X lo ring, [448,480) and
+// [480,512) the two accumulators.
+#include <cstring>
+
+#include "fir_kernels.h"
+#include "sm100_ptx.cuh"
+
+namespace rsb {
+
+// Optional per-role cycle accounting (one thread per role of CTA 0; enabled by a debug call):
+// MMA issuer [0] wait x_full [1] wait g_full [2] wait d_empty [3] issue [4] commits + meta;
+// splitter [5] wait x_empty [6] wait xs_full [7] split + tcgen05.st; epilogue [8] wait d_full
+// [9] tcgen05.ld + staging [10] stores; [11] X producer wait xs_empty; [12] G producer wait
+// g_empty; [13] kernel cycles of CTA 0; [14] tiles of CTA 0; [15] chunks of CTA 0.
+__device__ unsigned long long g_tc_cycles[16];
+__device__ int g_tc_prof = 0;
+
+namespace {
+
+using namespace ptx;
+
+struct RoleClock {
+    bool on;
+    long long t;
+    __device__ __forceinline__ void start(bool enable) {
+        on = enable;
+        t = on ? clock64() : 0;
+    }
+    __device__ __forceinline__ void lap(int i) {
+        if (on) {
+            const long long n = clock64();
+            atomicAdd(&g_tc_cycles[i], (unsigned long long)(n - t));
+            t = n;
+        }
+    }
+    __device__ __forceinline__ void count(int i, unsigned long long n) {
+        if (on) atomicAdd(&g_tc_cycles[i], n);
+    }
+};
+
+constexpr uint32_t kRows = 128;                    // MMA M
+constexpr uint32_t kN = kTileOut;                  // MMA N (32 output frames)
+constexpr uint32_t kChunk = 16;                    // frames per input chunk / ring slot
+constexpr uint32_t kRing = 224;                    // frames in a TMEM ring
+constexpr uint32_t kSlots = kRing / kChunk;        // 14
+constexpr uint32_t kColHi = 0, kColLo = kRing, kColD = 2 * kRing;
+constexpr uint32_t kXStages = 4;                   // TMA landing buffers for input chunks
+constexpr uint32_t kXStageBytes = kRows * kChunk * 4;   // 8192 for mono and stereo alike
+constexpr uint32_t kGStages = 3;
+constexpr uint32_t kTcThreads = 11 * 32;
+constexpr uint32_t kKtLimit = 192;                 // largest K extent of a tile (12 + 1 chunks)
+constexpr uint32_t kItemSlots = 2;
+
+// tcgen05 instruction descriptor: D = f32, A = B = tf32, both K-major, N = 32, M = 128
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((kN >> 3) << 17) | ((kRows >> 4) << 24);
+
+__host__ __device__ inline uint32_t tc_kt_max(uint32_t taps, double ratio) {
+    // first and last output of a tile start at most floor(31*ratio)+1 frames apart; up to 7
+    // frames of alignment in front; rounded up to the MMA's K step
+    const uint32_t span = (uint32_t)(31.0 * ratio) + 1u;
+    return (7u + span + taps + 7u) & ~7u;
+}
+__host__ __device__ inline uint32_t tc_stage_pitch(uint32_t ch) { return ch == 2 ? 68u : 36u; }
+
+struct Item {
+    uint32_t t0, t1;       // tiles [t0, t1) of the unit
+    uint32_t group;        // member group
+    uint32_t n_chunks;     // input chunks of the run
+    int32_t vb;            // virtual frame of chunk 0 (multiple of kChunk)
+    uint32_t valid;
+};
+
+// shared-memory descriptor of a B operand: K-major, no swizzle; the two 16-byte K halves of a
+// K step are 512 bytes apart (LBO), 8-row groups 128 bytes apart (SBO); descriptor version 1
+__device__ __forceinline__ uint64_t b_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)(512u >> 4) << 16) |
+           ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+}
+
+struct TcSmem {
+    uint64_t xs_full[kXStages], xs_empty[kXStages];
+    uint64_t g_full[kGStages], g_empty[kGStages];
+    uint64_t x_full[kSlots], x_empty[kSlots];
+    uint64_t d_full[2], d_empty[2];
+    uint64_t item_full[kItemSlots], item_empty[kItemSlots];
+    Item item[kItemSlots];
+    float *out[kRows];
+    uint64_t cap[kRows];
+    uint32_t tmem_base;
+};
+
+template <int CH>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUtensorMap tmap) {
+    static_assert(CH == 1 || CH == 2, "tensor kernel: mono or stereo");
+    constexpr uint32_t kMpg = kRows / CH;               // members per group
+    extern __shared__ __align__(1024) uint8_t smem_tc[];
+    __shared__ TcSmem S;
+    const uint32_t g_bytes = P.kt_max * 128u;           // one G half: kt_max/4 K groups x 512 B
+    uint8_t *xst = smem_tc;                             // [kXStages][kXStageBytes]
+    uint8_t *gst = smem_tc + kXStages * kXStageBytes;   // [kGStages][2][g_bytes]
+    float *stage = reinterpret_cast<float *>(gst + kGStages * 2 * g_bytes);
+
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    const bool prof = g_tc_prof != 0 && blockIdx.x == 0;
+    const long long t_kernel = prof ? clock64() : 0;
+    RoleClock rc;
+    rc.start(false);
+    if (tid == 0) {
+        for (uint32_t i = 0; i < kXStages; ++i) { mbar_init(&S.xs_full[i], 1); mbar_init(&S.xs_empty[i], kRows); }
+        for (uint32_t i = 0; i < kGStages; ++i) { mbar_init(&S.g_full[i], 1); mbar_init(&S.g_empty[i], 1); }
+        for (uint32_t i = 0; i < kSlots; ++i) { mbar_init(&S.x_full[i], kRows); mbar_init(&S.x_empty[i], 1); }
+        for (uint32_t i = 0; i < 2; ++i) { mbar_init(&S.d_full[i], 1); mbar_init(&S.d_empty[i], kRows); }
+        for (uint32_t i = 0; i < kItemSlots; ++i) {
+            mbar_init(&S.item_full[i], 1);
+            mbar_init(&S.item_empty[i], 2 + 2 * kRows);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) tmem_alloc(&S.tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = S.tmem_base;
+
+    const UnitDev &U = P.units[0];
+    const int32_t H = (int32_t)U.hist_len0;
+    const uint32_t n_tiles = U.n_tiles;
+    const TcTile *tct = P.tct + U.tile_off;
+    const uint32_t n_runs = (n_tiles + P.run_tiles - 1) / P.run_tiles;
+    const uint32_t n_items = n_runs * P.groups;
+
+    // every consumer role fetches the next item from the scheduler's two-slot queue
+    auto get_item = [&](uint32_t it) {
+        const uint32_t slot = it % kItemSlots;
+        mbar_wait(&S.item_full[slot], (it / kItemSlots) & 1u);
+        const Item I = S.item[slot];
+        mbar_arrive(&S.item_empty[slot]);
+        return I;
+    };
+
+    if (warp == 9) {
+        // ===== scheduler + TMA producer of the input chunks =====
+        if (lane == 0) {
+            uint32_t xs_seq = 0;
+            rc.start(prof);
+            for (uint32_t it = 0;; ++it) {
+                const uint32_t slot = it % kItemSlots;
+                mbar_wait(&S.item_empty[slot], ((it / kItemSlots) & 1u) ^ 1u);
+                const uint32_t idx = atomicAdd(P.work_counter, 1u);
+                Item I;
+                I.valid = idx < n_items ? 1u : 0u;
+                I.t0 = I.t1 = I.group = I.n_chunks = 0;
+                I.vb = 0;
+                if (I.valid) {
+                    const uint32_t r = idx / P.groups;
+                    I.group = idx - r * P.groups;
+                    I.t0 = r * P.run_tiles;
+                    I.t1 = min(I.t0 + P.run_tiles, n_tiles);
+                    const TcTile first = tct[I.t0], last = tct[I.t1 - 1];
+                    // chunk grid anchored at the first frame of the new input (virtual frame H): a
+                    // TMA box must start 16-byte aligned in global memory (an odd stereo frame is
+                    // an illegal instruction, tools/experiments/tma_swizzle_test.cu), and no
+                    // chunk straddles the history / input seam
+                    const int32_t rel = first.k0 - H;
+                    const int32_t fl = rel >= 0 ? rel / (int32_t)kChunk
+                                                : -((-rel + (int32_t)kChunk - 1) / (int32_t)kChunk);
+                    I.vb = H + fl * (int32_t)kChunk;
+                    I.n_chunks = (uint32_t)(last.k0 + (int32_t)last.kt - I.vb + (int32_t)kChunk - 1) / kChunk;
+                }
+                S.item[slot] = I;
+                mbar_arrive(&S.item_full[slot]);
+                if (!I.valid) break;
+                const int32_t m0 = (int32_t)(I.group * kMpg);
+                for (uint32_t j = 0; j < I.n_chunks; ++j) {
+                    const int32_t v = I.vb + (int32_t)(j * kChunk);
+                    if (v < H) continue;       // touches the history: the splitter loads it itself
+                    const uint32_t s = xs_seq % kXStages;
+                    rc.lap(15);
+                    mbar_wait(&S.xs_empty[s], ((xs_seq / kXStages) & 1u) ^ 1u);
+                    rc.lap(11);
+                    mbar_arrive_expect_tx(&S.xs_full[s], kXStageBytes);
+                    tensor_g2s_2d(xst + s * kXStageBytes, &tmap, v - H, m0, &S.xs_full[s]);
+                    ++xs_seq;
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 10) {
+        // ===== TMA producer of the G matrices =====
+        if (lane == 0) {
+            uint32_t g_seq = 0;
+            rc.start(prof);
+            const size_t tile_floats = (size_t)2 * P.kt_max * kN;
+            for (uint32_t it = 0;; ++it) {
+                const Item I = get_item(it);
+                if (!I.valid) break;
+                uint32_t kt = tct[I.t0].kt;
+                for (uint32_t t = I.t0; t < I.t1; ++t) {
+                    const uint32_t kt_next = t + 1 < I.t1 ? tct[t + 1].kt : 0u;
+                    const uint32_t s = g_seq % kGStages;
+                    rc.lap(15);
+                    mbar_wait(&S.g_empty[s], ((g_seq / kGStages) & 1u) ^ 1u);
+                    rc.lap(12);
+                    const uint32_t bytes = kt * 128u;
+                    const float *src = P.gmat + (size_t)(U.tile_off + t) * tile_floats;
+                    uint8_t *dst = gst + (size_t)s * 2 * g_bytes;
+                    mbar_arrive_expect_tx(&S.g_full[s], 2 * bytes);
+                    bulk_g2s(dst, src, bytes, &S.g_full[s]);
+                    bulk_g2s(dst + g_bytes, src + (size_t)P.kt_max * kN, bytes, &S.g_full[s]);
+                    ++g_seq;
+                    kt = kt_next;
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 8) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t q_base = 0;      // ring sequence number of the run's chunk 0
+            uint32_t q_waited = 0;    // chunks whose x_full barrier has been consumed
+            uint32_t q_rel = 0;       // chunks handed back to the splitter
+            uint32_t g_seq = 0, d_seq = 0;
+            rc.start(prof);
+            for (uint32_t it = 0;; ++it) {
+                const Item I = get_item(it);
+                if (!I.valid) break;
+                rc.count(14, I.t1 - I.t0);
+                TcTile m = tct[I.t0];
+                for (uint32_t t = I.t0; t < I.t1; ++t) {
+                    TcTile mn = m;
+                    if (t + 1 < I.t1) mn = tct[t + 1];
+                    const uint32_t j_last = (uint32_t)(m.k0 + (int32_t)m.kt - 1 - I.vb) / kChunk;
+                    rc.lap(4);
+                    while (q_waited <= q_base + j_last) {
+                        mbar_wait(&S.x_full[q_waited % kSlots], (q_waited / kSlots) & 1u);
+                        ++q_waited;
+                    }
+                    rc.lap(0);
+                    const uint32_t gs = g_seq % kGStages;
+                    mbar_wait(&S.g_full[gs], (g_seq / kGStages) & 1u);
+                    rc.lap(1);
+                    const uint32_t b = d_seq & 1u;
+                    mbar_wait(&S.d_empty[b], ((d_seq >> 1) & 1u) ^ 1u);
+                    rc.lap(2);
+                    tc_fence_after();
+
+                    const uint32_t d_tmem = tmem + kColD + b * kN;
+                    const uint32_t col0 = ((q_base % kSlots) * kChunk + (uint32_t)(m.k0 - I.vb)) % kRing;
+                    const uint32_t n_ks = m.kt >> 3;
+                    const uint32_t ghi = smem_u32(gst + (size_t)gs * 2 * g_bytes);
+                    const uint32_t glo = ghi + g_bytes;
+                    // small terms first: x_lo * g_hi and x_hi * g_lo
+                    uint32_t col = col0;
+                    for (uint32_t ks = 0; ks < n_ks; ++ks) {
+                        tc_mma_tf32_ts(d_tmem, tmem + kColLo + col, b_desc(ghi + ks * 1024u), kIdesc, ks != 0);
+                        tc_mma_tf32_ts(d_tmem, tmem + kColHi + col, b_desc(glo + ks * 1024u), kIdesc, 1u);
+                        col += 8;
+                        if (col >= kRing) col -= kRing;
+                    }
+                    // x_hi * g_hi, K steps outside-in
+                    for (uint32_t i = 0; i < n_ks; ++i) {
+                        const uint32_t ks = (i & 1u) ? n_ks - 1 - (i >> 1) : (i >> 1);
+                        uint32_t c = col0 + 8 * ks;
+                        if (c >= kRing) c -= kRing;
+                        tc_mma_tf32_ts(d_tmem, tmem + kColHi + c, b_desc(ghi + ks * 1024u), kIdesc, 1u);
+                    }
+                    rc.lap(3);
+                    tc_commit(&S.g_empty[gs]);
+                    tc_commit(&S.d_full[b]);
+                    ++g_seq;
+                    ++d_seq;
+                    // chunks that end at or before the next tile's first frame are free again
+                    const bool last = t + 1 == I.t1;
+                    while (q_rel < q_base + I.n_chunks &&
+                           (last || I.vb + (int32_t)((q_rel - q_base + 1) * kChunk) <= mn.k0)) {
+                        tc_commit(&S.x_empty[q_rel % kSlots]);
+                        ++q_rel;
+                    }
+                    m = mn;
+                }
+                q_base += I.n_chunks;
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===== splitter: shared memory (TMA landing buffer) -> hi / lo rings in TMEM =====
+        const uint32_t row = tid - 128u;                    // TMEM lane
+        const uint32_t ml = row / CH, c = row % CH;         // member inside the group, channel
+        const uint32_t lane_base = ((warp & 3u) * 32u) << 16;
+        uint32_t q_seq = 0, xs_seq = 0;
+        rc.start(prof && row == 0);
+        for (uint32_t it = 0;; ++it) {
+            const Item I = get_item(it);
+            if (!I.valid) break;
+            const uint32_t mg = I.group * kMpg + ml;
+            const bool member_ok = mg < U.n_members;
+            const float *hist = nullptr, *in = nullptr;
+            if (I.vb < H && member_ok) {
+                const JobDev *job = P.jobs + U.member_off + mg;
+                hist = job->hist;
+                in = job->in;
+            }
+            for (uint32_t j = 0; j < I.n_chunks; ++j, ++q_seq) {
+                const uint32_t rs = q_seq % kSlots;
+                rc.lap(7);
+                mbar_wait(&S.x_empty[rs], ((q_seq / kSlots) & 1u) ^ 1u);
+                rc.lap(5);
+                tc_fence_after();
+                const int32_t v = I.vb + (int32_t)(j * kChunk);
+                float x[kChunk];
+                if (v >= H) {
+                    const uint32_t s = xs_seq % kXStages;
+                    mbar_wait(&S.xs_full[s], (xs_seq / kXStages) & 1u);
+                    rc.lap(6);
+                    const uint32_t base = smem_u32(xst + s * kXStageBytes);
+                    if (CH == 2) {
+                        // 128-byte rows (16 stereo frames), 128B swizzle: unit u at u ^ (row & 7)
+                        const uint32_t rb = base + ml * 128u;
+#pragma unroll
+                        for (uint32_t u = 0; u < 8; ++u) {
+                            const float4 q4 = lds128(rb + ((u ^ (ml & 7u)) << 4));
+                            x[2 * u] = c ? q4.y : q4.x;
+                            x[2 * u + 1] = c ? q4.w : q4.z;
+                        }
+                    } else {
+                        // 64-byte rows (16 mono frames), 64B swizzle: unit u at u ^ ((row >> 1) & 3)
+                        const uint32_t rb = base + ml * 64u;
+#pragma unroll
+                        for (uint32_t u = 0; u < 4; ++u) {
+                            const float4 q4 = lds128(rb + ((u ^ ((ml >> 1) & 3u)) << 4));
+                            x[4 * u] = q4.x; x[4 * u + 1] = q4.y; x[4 * u + 2] = q4.z; x[4 * u + 3] = q4.w;
+                        }
+                    }
+                    mbar_arrive(&S.xs_empty[s]);
+                    ++xs_seq;
+                } else {
+                    // the chunk touches the history (only at the very start of a batch)
+#pragma unroll
+                    for (uint32_t f = 0; f < kChunk; ++f) {
+                        const int64_t vv = (int64_t)v + f;
+                        float xv = 0.f;
+                        if (member_ok && vv >= 0) {
+                            if (vv < H) xv = hist[((int64_t)kHistFrames - H + vv) * CH + c];
+                            else if ((uint64_t)(vv - H) < U.total_frames) xv = in[(vv - H) * CH + c];
+                        }
+                        x[f] = xv;
+                    }
+                }
+                uint32_t hi[kChunk], lo[kChunk];
+#pragma unroll
+                for (uint32_t f = 0; f < kChunk; ++f) {
+                    const float h = to_tf32(x[f]);
+                    hi[f] = __float_as_uint(h);
+                    lo[f] = __float_as_uint(to_tf32(__fsub_rn(x[f], h)));
+                }
+                tmem_st16(tmem + lane_base + kColHi + rs * kChunk, hi);
+                tmem_st16(tmem + lane_base + kColLo + rs * kChunk, lo);
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(&S.x_full[rs]);
+            }
+        }
+    } else {
+        // ===== epilogue: accumulator (TMEM) -> shared-memory staging -> global =====
+        const uint32_t row = tid;
+        const uint32_t ml = row / CH, c = row % CH;
+        const uint32_t lane_base = ((warp & 3u) * 32u) << 16;
+        const uint32_t pitch = tc_stage_pitch(CH);
+        uint32_t d_seq = 0;
+        rc.start(prof && tid == 0);
+        for (uint32_t it = 0;; ++it) {
+            const Item I = get_item(it);
+            if (!I.valid) break;
+            const uint32_t m0 = I.group * kMpg;
+            const uint32_t nm = min(kMpg, U.n_members - m0);
+            named_bar_sync(1, kRows);                // the previous item's stores are done
+            if (tid < nm) {
+                const JobDev *job = P.jobs + U.member_off + m0 + tid;
+                S.out[tid] = job->out;
+                S.cap[tid] = job->out_capacity;
+            }
+            named_bar_sync(1, kRows);
+            for (uint32_t t = I.t0; t < I.t1; ++t, ++d_seq) {
+                const TcTile m = tct[t];
+                const uint32_t b = d_seq & 1u;
+                rc.lap(10);
+                mbar_wait(&S.d_full[b], (d_seq >> 1) & 1u);
+                rc.lap(8);
+                tc_fence_after();
+                uint32_t acc[kN];
+                tmem_ld32(tmem + lane_base + kColD + b * kN, acc);
+                tmem_wait_ld();
+                tc_fence_before();
+                mbar_arrive(&S.d_empty[b]);
+                // stage[member][frame][channel]
+                float *st = stage + ml * pitch + c;
+#pragma unroll
+                for (uint32_t o = 0; o < kN; ++o) st[o * CH] = __uint_as_float(acc[o]);
+                named_bar_sync(1, kRows);
+                rc.lap(9);
+                constexpr uint32_t kFpp = 4 / CH;            // frames per 16-byte piece
+                constexpr uint32_t kPieces = kN / kFpp;
+                for (uint32_t e = tid; e < nm * kPieces; e += kRows) {
+                    const uint32_t mem = e / kPieces, p = e - mem * kPieces;
+                    const uint32_t fr = kFpp * p;
+                    if (fr >= m.n_out) continue;
+                    const float4 q4 = *reinterpret_cast<const float4 *>(stage + mem * pitch + fr * CH);
+                    float *outm = S.out[mem];
+                    const uint64_t cap = S.cap[mem];
+                    const uint64_t o = (uint64_t)m.o_start + fr;
+                    const bool full = fr + kFpp <= m.n_out && o + kFpp <= cap;
+                    if (full && ((reinterpret_cast<uintptr_t>(outm) & 15u) == 0)) {
+                        *reinterpret_cast<float4 *>(outm + o * CH) = q4;
+                    } else {
+                        const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                        for (uint32_t f = 0; f < kFpp; ++f)
+                            if (fr + f < m.n_out && o + f < cap)
+#pragma unroll
+                                for (uint32_t cc = 0; cc < (uint32_t)CH; ++cc)
+                                    outm[(o + f) * CH + cc] = qv[f * CH + cc];
+                    }
+                }
+                named_bar_sync(1, kRows);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+    if (prof && tid == 0) atomicAdd(&g_tc_cycles[13], (unsigned long long)(clock64() - t_kernel));
+}
+
+// One CTA per tile: builds the tile's banded filter matrix, split into TF32 hi and lo parts, in
+// the canonical K-major core-matrix layout the MMA reads ([K group of 4][32 rows][4 floats]),
+// K counted from k0 = the first needed virtual frame rounded down to the 8-frame grid.
+template <int TAPS>
+__global__ void __launch_bounds__(128)
+tc_gmat_kernel(const UnitDev *units, const TileRec *tiles, const PlanEntry *entries,
+               const float *coeffs, float *gmat, TcTile *tct, uint32_t kt_max) {
+    extern __shared__ float4 sh4[];
+    float *sh = reinterpret_cast<float *>(sh4);          // [2][kt_max/4][32][4]
+    const UnitDev &U = units[0];
+    const uint32_t t = blockIdx.x;
+    if (t >= U.n_tiles) return;
+    const size_t tile = (size_t)U.tile_off + t;
+    const TileRec rec = tiles[tile];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t half = kt_max * kN;                   // floats in the hi (or lo) matrix
+    for (uint32_t i = tid; i < 2 * half / 4; i += 128) sh4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const PlanEntry e0 = entries[tile * kTileOut];
+    const PlanEntry el = entries[tile * kTileOut + rec.n_out - 1];
+    // K origin: the first needed frame rounded down to a multiple of 8 counted from the first
+    // frame of the new input (virtual frame H), the anchor of the input chunk grid
+    const int32_t H = (int32_t)U.hist_len0;
+    const int32_t k0 = e0.v - ((((e0.v - H) % 8) + 8) % 8);
+    uint32_t kt = (uint32_t)(el.v + TAPS - k0 + 7) & ~7u;
+    if (kt > kt_max) kt = kt_max;    // cannot happen for a plan of this ratio (tc_kt_max)
+    if (tid == 0) {
+        TcTile m;
+        m.k0 = k0;
+        m.kt = kt;
+        m.n_out = rec.n_out;
+        m.o_start = rec.o_start;
+        tct[tile] = m;
+    }
+    __syncthreads();
+    const uint32_t o = tid >> 2, part = tid & 3u;        // output row, quarter of its taps
+    if (o < rec.n_out) {
+        const PlanEntry e = entries[tile * kTileOut + o];
+        const uint32_t p1 = e.phase1;
+        const uint32_t p2 = p1 + 1 < kPhases - 1 ? p1 + 1 : kPhases - 1;
+        const float fr = e.frac, omf = __fsub_rn(1.0f, fr);
+        const int d = e.v - k0;
+        constexpr int kPer = TAPS / 4;
+        const float *ca = coeffs + (size_t)p1 * TAPS + part * kPer;
+        const float *cb = coeffs + (size_t)p2 * TAPS + part * kPer;
+#pragma unroll 4
+        for (int j = 0; j < kPer; ++j) {
+            const float g = __fmaf_rn(__ldg(cb + j), fr, __fmul_rn(__ldg(ca + j), omf));
+            const float hi = to_tf32(g);
+            const float lo = to_tf32(__fsub_rn(g, hi));
+            const uint32_t k = (uint32_t)(d + (int)part * kPer + j);
+            if (k >= kt) continue;
+            const uint32_t idx = ((k >> 2) * kN + o) * 4 + (k & 3u);
+            sh[idx] = hi;
+            sh[half + idx] = lo;
+        }
+    }
+    __syncthreads();
+    float4 *dst = reinterpret_cast<float4 *>(gmat + tile * (size_t)2 * half);
+    const uint32_t used = kt * kN / 4;                   // float4 of the K prefix in use
+    for (uint32_t i = tid; i < used; i += 128) {
+        dst[i] = sh4[i];
+        dst[half / 4 + i] = sh4[half / 4 + i];
+    }
+}
+
+}  // namespace
+
+bool tc_supported(uint32_t channels, uint32_t taps, double ratio) {
+    if (channels != 1 && channels != 2) return false;
+    if (taps != 16 && taps != 32 && taps != 64 && taps != 128) return false;
+    return tc_kt_max(taps, ratio) <= kKtLimit;
+}
+
+uint32_t tc_kt_extent(uint32_t taps, double ratio) { return tc_kt_max(taps, ratio); }
+
+size_t tc_gmat_floats_per_tile(uint32_t taps, double ratio) {
+    return (size_t)2 * tc_kt_max(taps, ratio) * kN;
+}
+
+bool tc_make_input_tensor_map(CUtensorMap *out, const float *base, uint64_t stride_bytes,
+                              uint64_t total_frames, uint32_t n_members, uint32_t channels) {
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                      const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                      const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) !=
+                cudaSuccess || !fn) {
+            cudaGetLastError();
+            return false;
+        }
+        encode = (EncodeTiledFn)fn;
+    }
+    if (channels != 1 && channels != 2) return false;
+    if (total_frames == 0 || total_frames >= (1ull << 31)) return false;
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) || (stride_bytes & 15u) || stride_bytes == 0)
+        return false;
+    if (stride_bytes < total_frames * channels * 4ull) return false;
+    // element = one frame (f32 mono, 8-byte stereo); inner dimension = frames, rows = members
+    cuuint64_t dims[2] = {total_frames, n_members};
+    cuuint64_t strides[1] = {stride_bytes};
+    cuuint32_t box[2] = {kChunk, (cuuint32_t)(kRows / channels)};
+    cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt =
+        channels == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
+    const CUtensorMapSwizzle sw = channels == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    const CUresult r = encode(out, dt, 2, const_cast<float *>(base), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+void launch_tc_gmat(const UnitDev *units, const TileRec *tiles, const PlanEntry *entries,
+                    const float *coeffs, float *gmat, TcTile *tct, uint32_t taps, double ratio,
+                    uint32_t tile_cap, cudaStream_t stream) {
+    if (tile_cap == 0) return;
+    const uint32_t kt_max = tc_kt_max(taps, ratio);
+    const size_t smem = (size_t)2 * kt_max * kN * sizeof(float);
+    auto launch = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<tile_cap, 128, smem, stream>>>(units, tiles, entries, coeffs, gmat, tct, kt_max);
+    };
+    switch (taps) {
+        case 16: launch(tc_gmat_kernel<16>); break;
+        case 32: launch(tc_gmat_kernel<32>); break;
+        case 64: launch(tc_gmat_kernel<64>); break;
+        default: launch(tc_gmat_kernel<128>); break;
+    }
+}
+
+void launch_conv_tc(const TcParams &p, const CUtensorMap &tmap, int sm_count, cudaStream_t stream) {
+    const size_t smem = (size_t)kXStages * kXStageBytes + (size_t)kGStages * 2 * p.kt_max * 128u +
+                        (size_t)(kRows / p.channels) * tc_stage_pitch(p.channels) * sizeof(float);
+    // one SM is left free for the (serial) plan kernel of the next submit, as in fir_fast.cu
+    const uint32_t grid = (uint32_t)(sm_count > 8 ? sm_count - 1 : sm_count);
+    auto launch = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<grid, kTcThreads, smem, stream>>>(p, tmap);
+    };
+    if (p.channels == 1) launch(conv_tc_kernel<1>);
+    else launch(conv_tc_kernel<2>);
+}
+
+uint32_t tc_rows_per_group() { return kRows; }
+
+void tc_phase_profile(int enable, unsigned long long *out16) {
+    if (out16) cudaMemcpyFromSymbol(out16, g_tc_cycles, sizeof(unsigned long long) * 16);
+    unsigned long long zero[16] = {0};
+    cudaMemcpyToSymbol(g_tc_cycles, zero, sizeof(zero));
+    cudaMemcpyToSymbol(g_tc_prof, &enable, sizeof(int));
+}
+
+}  // namespace rsb

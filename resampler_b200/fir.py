@@ -66,6 +66,7 @@ class Kernel(enum.IntEnum):
     AUTO = 0
     EXACT = 1   # bit-identical to the reference's AVX-512 summation order
     FAST = 2    # pre-interpolated rows, within 1e-6 absolute
+    TENSOR = 3  # tcgen05 tensor cores, 3xTF32, within 1e-6 absolute (uniform batches)
 
 
 class ResampleError(Exception):
@@ -186,6 +187,10 @@ class FirBatch:
     # -- reference interface -------------------------------------------------
     def set_kernel(self, kernel: Kernel) -> None:
         _check(self._lib.rsb_fir_set_kernel(self._h, int(kernel)))
+
+    def last_kernel(self) -> Kernel:
+        """Kernel the most recent batch actually ran on (``Kernel.AUTO`` before the first)."""
+        return Kernel(self._lib.rsb_fir_last_kernel(self._h))
 
     def buffer_size_output(self) -> int:
         return self._lib.rsb_fir_buffer_size_output(self._h)
