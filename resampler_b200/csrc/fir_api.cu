@@ -95,8 +95,11 @@ struct Pending {
 // submit i is still running on the main stream.
 struct Workspace {
     DevBuf d_units, d_jobs, d_segs, d_calls, d_tiles, d_entries, d_gtiles, d_tct, d_counter;
-    PinBuf h_units, h_jobs, h_units_back, h_calls_back;
+    PinBuf h_units, h_jobs, h_units_back, h_calls_back, h_segs, h_counter;
     std::vector<uint32_t> job_unit;          // unit of each job of the batch
+    std::vector<uint32_t> job_stream;        // stream of each job of the batch
+    bool host_planned = false;               // the plan ran on the host: results already mirrored
+    uint64_t seq = 0;                        // submit number that last used this workspace
     std::vector<uint64_t> job_out_capacity;  // frames
     uint32_t n_units = 0;
     bool has_calls = false, has_plan = false;
@@ -121,6 +124,14 @@ struct rsb_fir {
     rsb::StreamStateDev st{};
     std::vector<uint64_t> cohort;   // host-side plan cohort of each stream (0 = fresh state)
     std::vector<uint8_t> hist_sel;  // which history buffer of a stream is live (host mirror)
+    // Host mirror of the scalar stream state (resampler_fir.rs:191-193).  With it a batch of few
+    // plan units is planned on a host core (one 60 s unit: 1.2 ms, the same code takes 15 ms
+    // on one GPU thread); batches of many units are planned on the GPU, one thread per unit,
+    // and the mirror is refreshed from their read-back.
+    std::vector<double> m_pos;
+    std::vector<uint32_t> m_avail;
+    std::vector<uint8_t> m_ok;
+    std::vector<uint64_t> m_pending;   // submit number whose read-back will refresh the mirror
     uint64_t next_cohort = 1;
     uint64_t launches = 0;
     cudaStream_t plan_stream = nullptr;   // plan / tile kernels and the state scalars
@@ -167,6 +178,79 @@ uint32_t segs_per_call_bound(double ratio) {
     return (uint32_t)(2 * (14 - lowest) + 6);
 }
 
+// Host twin of plan_units_kernel (fir_kernels.cu): the same planner.h code on a host core.
+struct BoundedSink {
+    rsb::PlanSeg *segs;
+    uint32_t cap;
+    uint32_t n;
+    uint32_t out0;
+    int64_t vbase;
+    void seg(int64_t base_bits, int64_t step_bits, uint32_t cnt) {
+        if (n < cap) {
+            rsb::PlanSeg sg;
+            sg.base_bits = base_bits;
+            sg.step_bits = step_bits;
+            sg.n = cnt;
+            sg.out0 = out0;
+            sg.vbase = vbase;
+            segs[n] = sg;
+        }
+        n += 1;
+        out0 += cnt;
+    }
+};
+
+void plan_unit_host(UnitDev &U, rsb::PlanState s, double ratio, uint32_t taps, rsb::PlanSeg *segs,
+                    rsb::CallCounts *calls, uint32_t tile_out, uint64_t &tile_total) {
+    const uint32_t hist0 = s.available;
+    BoundedSink sink{segs + U.seg_off, U.seg_cap, 0u, 0u, 0};
+    uint64_t offset = 0;
+    int64_t advanced = 0;
+    uint32_t n_calls = 0, status = 0;
+    rsb::DivCache dc;
+    rsb::div_cache_reset(dc);
+    for (;;) {
+        if (!U.single_call && offset >= U.total_frames) break;
+        if (n_calls >= U.max_calls) { status = 2; break; }
+        const uint64_t remaining = U.total_frames - offset;
+        const uint32_t chunk =
+            U.single_call ? (uint32_t)std::min<uint64_t>(remaining, 0xffffffffull)
+                          : (uint32_t)std::min<uint64_t>(remaining, U.call_frames);
+        sink.vbase = advanced;
+        const rsb::CallResult r = rsb::plan_call(s, ratio, taps, chunk, U.cap_frames, sink, dc);
+        if (calls && n_calls < U.call_cap) {
+            rsb::CallCounts cc;
+            cc.copied = r.copied;
+            cc.produced = r.produced;
+            calls[U.call_off + n_calls] = cc;
+        }
+        n_calls += 1;
+        offset += r.copied;
+        advanced += r.advanced;
+        if (U.single_call || r.copied == 0) break;
+    }
+    if (sink.n > U.seg_cap) status = 1;
+    const uint32_t n_tiles = (uint32_t)(((uint64_t)sink.out0 + tile_out - 1) / tile_out);
+    uint32_t tile_off = 0;
+    if (status != 1 && n_tiles) {
+        tile_off = (uint32_t)tile_total;
+        tile_total += n_tiles;
+    }
+    U.total_out = sink.out0;
+    U.total_copied = offset;
+    U.n_calls = n_calls;
+    U.n_segs = sink.n < U.seg_cap ? sink.n : U.seg_cap;
+    U.n_tiles = status == 1 ? 0u : n_tiles;
+    U.tile_off = tile_off;
+    U.status = status;
+    U.hist_len0 = hist0;
+    U.final_available = s.available;
+    U.final_position = s.position;
+}
+
+// batches with at most this many plan units are planned on the host
+constexpr uint32_t kHostPlanMaxUnits = 8;
+
 int finalize_pending(rsb_fir *h, Workspace &W) {
     if (!W.pending.active) return RSB_OK;
     Pending p = W.pending;
@@ -182,6 +266,13 @@ int finalize_pending(rsb_fir *h, Workspace &W) {
     const uint32_t ch = h->channels;
     for (uint32_t i = 0; i < p.n; ++i) {
         const UnitDev &U = ub[W.job_unit[i]];
+        if (!W.host_planned && W.job_stream.size() == p.n && !h->m_ok[W.job_stream[i]] &&
+            h->m_pending[W.job_stream[i]] == W.seq) {
+            // the newest GPU-planned batch of this stream: its read-back is the stream's state
+            h->m_pos[W.job_stream[i]] = U.final_position;
+            h->m_avail[W.job_stream[i]] = U.final_available;
+            h->m_ok[W.job_stream[i]] = 1;
+        }
         if (p.consumed) p.consumed[i] = (size_t)U.total_copied * ch;
         if (p.produced) p.produced[i] = (size_t)U.total_out * ch;
         if (p.n_calls) p.n_calls[i] = U.n_calls;
@@ -409,6 +500,37 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
 
     cudaStream_t s = h->stream;        // convolution, history update, data copies
     cudaStream_t sp = h->plan_stream;  // plan, tiles, state scalars, result read-back
+
+    // ---- plan on a host core when the batch has few plan units whose state is mirrored ----
+    bool host_plan = n_units <= kHostPlanMaxUnits;
+    for (uint32_t u = 0; host_plan && u < n_units; ++u) host_plan = h->m_ok[hu[u].rep_stream] != 0;
+    W.host_planned = host_plan;
+    W.seq = h->submits;
+    W.job_stream.resize(n);
+    for (uint32_t i = 0; i < n; ++i) W.job_stream[i] = jobs[i].stream;
+    uint64_t host_tiles = 0;
+    if (host_plan) {
+        RSB_CUDA(W.h_segs.reserve(sizeof(rsb::PlanSeg) * seg_total));
+        RSB_CUDA(W.h_counter.reserve(sizeof(uint32_t) * 4));
+        rsb::PlanSeg *hs = W.h_segs.as<rsb::PlanSeg>();
+        rsb::CallCounts *hc = rec_calls ? W.h_calls_back.as<rsb::CallCounts>() : nullptr;
+        for (uint32_t u = 0; u < n_units; ++u) {
+            const uint32_t rep = hu[u].rep_stream;
+            plan_unit_host(hu[u], rsb::PlanState{h->m_pos[rep], h->m_avail[rep]}, h->ratio, h->taps,
+                           hs, hc, tile_out, host_tiles);
+        }
+        std::memcpy(W.h_units_back.p, hu, sizeof(UnitDev) * n_units);
+        for (uint32_t i = 0; i < n; ++i) {
+            const UnitDev &U = hu[W.job_unit[i]];
+            h->m_pos[jobs[i].stream] = U.final_position;
+            h->m_avail[jobs[i].stream] = U.final_available;
+        }
+    } else {
+        for (uint32_t i = 0; i < n; ++i) {
+            h->m_ok[jobs[i].stream] = 0;
+            h->m_pending[jobs[i].stream] = h->submits;
+        }
+    }
     RSB_CUDA(cudaMemcpyAsync(W.d_units.p, hu, sizeof(UnitDev) * n_units, cudaMemcpyHostToDevice, sp));
     RSB_CUDA(cudaMemcpyAsync(W.d_jobs.p, hj, sizeof(JobDev) * n, cudaMemcpyHostToDevice, sp));
     RSB_CUDA(cudaMemsetAsync(W.d_counter.p, 0, sizeof(uint32_t) * 4, sp));
@@ -445,17 +567,31 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     }
 
     // ---- launch ----
-    rsb::launch_plan(W.d_units.as<UnitDev>(), n_units, h->st, h->ratio, h->taps,
-                     W.d_segs.as<rsb::PlanSeg>(), W.d_calls.as<rsb::CallCounts>(), tile_out,
-                     W.d_counter.as<uint32_t>(), sp);
+    if (host_plan) {
+        // the plan already exists: upload the segments in use and the tile total
+        for (uint32_t u = 0; u < n_units; ++u)
+            if (hu[u].n_segs)
+                RSB_CUDA(cudaMemcpyAsync(W.d_segs.as<rsb::PlanSeg>() + hu[u].seg_off,
+                                         W.h_segs.as<rsb::PlanSeg>() + hu[u].seg_off,
+                                         sizeof(rsb::PlanSeg) * hu[u].n_segs, cudaMemcpyHostToDevice, sp));
+        uint32_t *hcnt = W.h_counter.as<uint32_t>();
+        hcnt[0] = (uint32_t)host_tiles;
+        RSB_CUDA(cudaMemcpyAsync(W.d_counter.p, hcnt, sizeof(uint32_t), cudaMemcpyHostToDevice, sp));
+    } else {
+        rsb::launch_plan(W.d_units.as<UnitDev>(), n_units, h->st, h->ratio, h->taps,
+                         W.d_segs.as<rsb::PlanSeg>(), W.d_calls.as<rsb::CallCounts>(), tile_out,
+                         W.d_counter.as<uint32_t>(), sp);
+    }
     // the streams' scalar state (position, buffered frames) moves on the plan stream, so the
     // next submit can be planned while this one is still convolving
     rsb::launch_state_scalars(W.d_units.as<UnitDev>(), W.d_jobs.as<JobDev>(), n, h->st, sp);
-    RSB_CUDA(cudaMemcpyAsync(W.h_units_back.p, W.d_units.p, sizeof(UnitDev) * n_units,
-                             cudaMemcpyDeviceToHost, sp));
-    if (rec_calls && call_total)
-        RSB_CUDA(cudaMemcpyAsync(W.h_calls_back.p, W.d_calls.p,
-                                 sizeof(rsb::CallCounts) * call_total, cudaMemcpyDeviceToHost, sp));
+    if (!host_plan) {
+        RSB_CUDA(cudaMemcpyAsync(W.h_units_back.p, W.d_units.p, sizeof(UnitDev) * n_units,
+                                 cudaMemcpyDeviceToHost, sp));
+        if (rec_calls && call_total)
+            RSB_CUDA(cudaMemcpyAsync(W.h_calls_back.p, W.d_calls.p,
+                                     sizeof(rsb::CallCounts) * call_total, cudaMemcpyDeviceToHost, sp));
+    }
     RSB_CUDA(cudaEventRecord(W.ev_plan, sp));
     RSB_CUDA(cudaStreamWaitEvent(s, W.ev_plan, 0));
     // tile records, per-frame plan entries and (fast kernel) the banded filter tiles: a wide,
@@ -520,7 +656,7 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     RSB_CUDA(cudaEventRecord(h->ev_conv[ring][1], s));
     h->conv_batches += 1;
     rsb::launch_update(W.d_units.as<UnitDev>(), W.d_jobs.as<JobDev>(), n, h->st, ch, s);
-    h->launches += use_tc ? 6 : 5;
+    h->launches += (use_tc ? 6 : 5) - (host_plan ? 1 : 0);
     RSB_CUDA(cudaGetLastError());
     RSB_CUDA(cudaEventRecord(W.ev_done, s));
     h->submits += 1;
@@ -654,6 +790,10 @@ int rsb_fir_create(rsb_fir **out, int device, uint32_t n_streams, uint32_t chann
     h->table = rsb::get_or_create_table(cutoff, h->taps, attenuation);
     h->cohort.assign(n_streams, 0);
     h->hist_sel.assign(n_streams, 0);
+    h->m_pos.assign(n_streams, 0.0);
+    h->m_avail.assign(n_streams, 0u);
+    h->m_ok.assign(n_streams, 1);
+    h->m_pending.assign(n_streams, 0);
 
     RSB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     RSB_CUDA(cudaStreamCreateWithFlags(&h->plan_stream, cudaStreamNonBlocking));
@@ -700,7 +840,9 @@ void rsb_fir_destroy(rsb_fir *h) {
         for (DevBuf *b : {&W.d_units, &W.d_jobs, &W.d_segs, &W.d_calls, &W.d_tiles, &W.d_entries,
                           &W.d_gtiles, &W.d_tct, &W.d_counter})
             b->release();
-        for (PinBuf *b : {&W.h_units, &W.h_jobs, &W.h_units_back, &W.h_calls_back}) b->release();
+        for (PinBuf *b : {&W.h_units, &W.h_jobs, &W.h_units_back, &W.h_calls_back, &W.h_segs,
+                          &W.h_counter})
+            b->release();
         if (W.ev_plan) cudaEventDestroy(W.ev_plan);
         if (W.ev_done) cudaEventDestroy(W.ev_done);
     }
@@ -753,9 +895,15 @@ int rsb_fir_reset(rsb_fir *h, int64_t stream) {
     if (stream < 0) {
         rsb::launch_reset(h->st, 0, h->n_streams, h->plan_stream);
         std::fill(h->cohort.begin(), h->cohort.end(), 0);
+        std::fill(h->m_pos.begin(), h->m_pos.end(), 0.0);
+        std::fill(h->m_avail.begin(), h->m_avail.end(), 0u);
+        std::fill(h->m_ok.begin(), h->m_ok.end(), 1);
     } else {
         rsb::launch_reset(h->st, (uint32_t)stream, 1, h->plan_stream);
         h->cohort[(size_t)stream] = 0;
+        h->m_pos[(size_t)stream] = 0.0;
+        h->m_avail[(size_t)stream] = 0u;
+        h->m_ok[(size_t)stream] = 1;
     }
     h->launches += 1;
     RSB_CUDA(cudaGetLastError());
@@ -1088,6 +1236,8 @@ size_t rsb_host_plan(uint32_t input_rate_hz, uint32_t output_rate_hz, int latenc
     uint64_t offset = 0;
     int64_t advanced = 0;
     size_t n_calls = 0;
+    rsb::DivCache dc;
+    rsb::div_cache_reset(dc);
     // mirrors plan_units_kernel (fir_kernels.cu)
     for (;;) {
         if (!single_call && offset >= total_frames) break;
@@ -1096,7 +1246,7 @@ size_t rsb_host_plan(uint32_t input_rate_hz, uint32_t output_rate_hz, int latenc
             single_call ? (uint32_t)std::min<uint64_t>(remaining, 0xffffffffull)
                         : (uint32_t)std::min<uint64_t>(remaining, call_frames);
         sink.vbase = advanced;
-        const rsb::CallResult r = rsb::plan_call(st, ratio, (uint32_t)taps, chunk, cap_frames, sink);
+        const rsb::CallResult r = rsb::plan_call(st, ratio, (uint32_t)taps, chunk, cap_frames, sink, dc);
         if (n_calls < max_calls) {
             if (calls_consumed) calls_consumed[n_calls] = r.copied;
             if (calls_produced) calls_produced[n_calls] = r.produced;

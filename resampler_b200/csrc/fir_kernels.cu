@@ -49,6 +49,8 @@ __global__ void plan_units_kernel(UnitDev *units, uint32_t n_units, StreamStateD
     int64_t advanced = 0;    // frames the read position has moved (virtual frame of position 0)
     uint32_t n_calls = 0;
     uint32_t status = 0;
+    DivCache dc;
+    div_cache_reset(dc);
     for (;;) {
         if (!U.single_call && offset >= U.total_frames) break;
         if (n_calls >= U.max_calls) { status = 2; break; }
@@ -57,7 +59,7 @@ __global__ void plan_units_kernel(UnitDev *units, uint32_t n_units, StreamStateD
             U.single_call ? (uint32_t)(remaining > 0xffffffffull ? 0xffffffffull : remaining)
                           : (uint32_t)(remaining < U.call_frames ? remaining : U.call_frames);
         sink.vbase = advanced;
-        const CallResult r = plan_call(s, ratio, taps, chunk, U.cap_frames, sink);
+        const CallResult r = plan_call(s, ratio, taps, chunk, U.cap_frames, sink, dc);
         if (n_calls < U.call_cap) {
             CallCounts cc;
             cc.copied = r.copied;

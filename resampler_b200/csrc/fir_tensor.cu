@@ -41,9 +41,9 @@ namespace rsb {
 
 // Optional per-role cycle accounting (one thread per role of CTA 0; enabled by a debug call):
 // MMA issuer [0] wait x_full [1] wait g_full [2] wait d_empty [3] issue [4] commits + meta;
-// splitter [5] wait x_empty [6] wait xs_full [7] split + tcgen05.st; epilogue [8] wait d_full
-// [9] tcgen05.ld + staging [10] stores; [11] X producer wait xs_empty; [12] G producer wait
-// g_empty; [13] kernel cycles of CTA 0; [14] tiles of CTA 0; [15] chunks of CTA 0.
+// splitter [5] wait x_empty [6] wait xs_full [7] loads + split [11] wait::st + arrive [12] tcgen05.st
+// [15] loop overhead; epilogue [8] wait d_full [9] tcgen05.ld + staging [10] stores;
+// [13] kernel cycles of CTA 0; [14] tiles of CTA 0.
 __device__ unsigned long long g_tc_cycles[16];
 __device__ int g_tc_prof = 0;
 
@@ -102,12 +102,14 @@ struct Item {
     uint32_t valid;
 };
 
-// shared-memory descriptor of a B operand: K-major, no swizzle; the two 16-byte K halves of a
-// K step are 512 bytes apart (LBO), 8-row groups 128 bytes apart (SBO); descriptor version 1
-__device__ __forceinline__ uint64_t b_desc(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)(512u >> 4) << 16) |
-           ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+// Shared-memory descriptor of a B operand: K-major, no swizzle; the two 16-byte K halves of a
+// K step are 512 bytes apart (LBO), 8-row groups 128 bytes apart (SBO); descriptor version 1.
+// The low word holds the start address (>> 4) and the LBO, the high word SBO and version.
+__device__ __forceinline__ uint32_t b_desc_lo(uint32_t smem_addr) {
+    return ((smem_addr & 0x3ffffu) >> 4) | ((512u >> 4) << 16);
 }
+constexpr uint32_t kBDescHi = (128u >> 4) | (1u << 14);
+constexpr uint32_t kBDescKStep = 1024u >> 4;   // descriptor increment per K step of 8 frames
 
 struct TcSmem {
     uint64_t xs_full[kXStages], xs_empty[kXStages];
@@ -116,8 +118,6 @@ struct TcSmem {
     uint64_t d_full[2], d_empty[2];
     uint64_t item_full[kItemSlots], item_empty[kItemSlots];
     Item item[kItemSlots];
-    float *out[kRows];
-    uint64_t cap[kRows];
     uint32_t tmem_base;
 };
 
@@ -171,11 +171,20 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
         return I;
     };
 
+    // the same for a whole converged warp (one arrival)
+    auto get_item_warp = [&](uint32_t it) {
+        const uint32_t slot = it % kItemSlots;
+        mbar_wait(&S.item_full[slot], (it / kItemSlots) & 1u);
+        const Item I = S.item[slot];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.item_empty[slot]);
+        return I;
+    };
+
     if (warp == 9) {
         // ===== scheduler + TMA producer of the input chunks =====
         if (lane == 0) {
             uint32_t xs_seq = 0;
-            rc.start(prof);
             for (uint32_t it = 0;; ++it) {
                 const uint32_t slot = it % kItemSlots;
                 mbar_wait(&S.item_empty[slot], ((it / kItemSlots) & 1u) ^ 1u);
@@ -208,9 +217,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                     const int32_t v = I.vb + (int32_t)(j * kChunk);
                     if (v < H) continue;       // touches the history: the splitter loads it itself
                     const uint32_t s = xs_seq % kXStages;
-                    rc.lap(15);
                     mbar_wait(&S.xs_empty[s], ((xs_seq / kXStages) & 1u) ^ 1u);
-                    rc.lap(11);
                     mbar_arrive_expect_tx(&S.xs_full[s], kXStageBytes);
                     tensor_g2s_2d(xst + s * kXStageBytes, &tmap, v - H, m0, &S.xs_full[s]);
                     ++xs_seq;
@@ -222,7 +229,6 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
         // ===== TMA producer of the G matrices =====
         if (lane == 0) {
             uint32_t g_seq = 0;
-            rc.start(prof);
             const size_t tile_floats = (size_t)2 * P.kt_max * kN;
             for (uint32_t it = 0;; ++it) {
                 const Item I = get_item(it);
@@ -231,9 +237,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                 for (uint32_t t = I.t0; t < I.t1; ++t) {
                     const uint32_t kt_next = t + 1 < I.t1 ? tct[t + 1].kt : 0u;
                     const uint32_t s = g_seq % kGStages;
-                    rc.lap(15);
                     mbar_wait(&S.g_empty[s], ((g_seq / kGStages) & 1u) ^ 1u);
-                    rc.lap(12);
                     const uint32_t bytes = kt * 128u;
                     const float *src = P.gmat + (size_t)(U.tile_off + t) * tile_floats;
                     uint8_t *dst = gst + (size_t)s * 2 * g_bytes;
@@ -247,72 +251,103 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
         }
         __syncwarp();
     } else if (warp == 8) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            uint32_t q_base = 0;      // ring sequence number of the run's chunk 0
-            uint32_t q_waited = 0;    // chunks whose x_full barrier has been consumed
-            uint32_t q_rel = 0;       // chunks handed back to the splitter
-            uint32_t g_seq = 0, d_seq = 0;
-            rc.start(prof);
-            for (uint32_t it = 0;; ++it) {
-                const Item I = get_item(it);
-                if (!I.valid) break;
-                rc.count(14, I.t1 - I.t0);
-                TcTile m = tct[I.t0];
-                for (uint32_t t = I.t0; t < I.t1; ++t) {
-                    TcTile mn = m;
-                    if (t + 1 < I.t1) mn = tct[t + 1];
-                    const uint32_t j_last = (uint32_t)(m.k0 + (int32_t)m.kt - 1 - I.vb) / kChunk;
-                    rc.lap(4);
-                    while (q_waited <= q_base + j_last) {
-                        mbar_wait(&S.x_full[q_waited % kSlots], (q_waited / kSlots) & 1u);
-                        ++q_waited;
-                    }
-                    rc.lap(0);
-                    const uint32_t gs = g_seq % kGStages;
-                    mbar_wait(&S.g_full[gs], (g_seq / kGStages) & 1u);
-                    rc.lap(1);
-                    const uint32_t b = d_seq & 1u;
-                    mbar_wait(&S.d_empty[b], ((d_seq >> 1) & 1u) ^ 1u);
-                    rc.lap(2);
-                    tc_fence_after();
-
-                    const uint32_t d_tmem = tmem + kColD + b * kN;
-                    const uint32_t col0 = ((q_base % kSlots) * kChunk + (uint32_t)(m.k0 - I.vb)) % kRing;
-                    const uint32_t n_ks = m.kt >> 3;
-                    const uint32_t ghi = smem_u32(gst + (size_t)gs * 2 * g_bytes);
-                    const uint32_t glo = ghi + g_bytes;
-                    // small terms first: x_lo * g_hi and x_hi * g_lo
-                    uint32_t col = col0;
-                    for (uint32_t ks = 0; ks < n_ks; ++ks) {
-                        tc_mma_tf32_ts(d_tmem, tmem + kColLo + col, b_desc(ghi + ks * 1024u), kIdesc, ks != 0);
-                        tc_mma_tf32_ts(d_tmem, tmem + kColHi + col, b_desc(glo + ks * 1024u), kIdesc, 1u);
-                        col += 8;
-                        if (col >= kRing) col -= kRing;
-                    }
-                    // x_hi * g_hi, K steps outside-in
-                    for (uint32_t i = 0; i < n_ks; ++i) {
-                        const uint32_t ks = (i & 1u) ? n_ks - 1 - (i >> 1) : (i >> 1);
-                        uint32_t c = col0 + 8 * ks;
-                        if (c >= kRing) c -= kRing;
-                        tc_mma_tf32_ts(d_tmem, tmem + kColHi + c, b_desc(ghi + ks * 1024u), kIdesc, 1u);
-                    }
-                    rc.lap(3);
-                    tc_commit(&S.g_empty[gs]);
-                    tc_commit(&S.d_full[b]);
-                    ++g_seq;
-                    ++d_seq;
-                    // chunks that end at or before the next tile's first frame are free again
-                    const bool last = t + 1 == I.t1;
-                    while (q_rel < q_base + I.n_chunks &&
-                           (last || I.vb + (int32_t)((q_rel - q_base + 1) * kChunk) <= mn.k0)) {
-                        tc_commit(&S.x_empty[q_rel % kSlots]);
-                        ++q_rel;
-                    }
-                    m = mn;
+        // ===== MMA issuer.  The whole warp runs the loop (warp-uniform values), one elected lane
+        // issues.  Issuing costs ~25-30 cycles of the warp's time per MMA (a dozen operand moves
+        // into uniform registers), more than the 16 cycles an M=128, N=32 MMA keeps the tensor pipe
+        // busy: this warp is the kernel's critical path.  (Two issuer warps on alternate tiles were
+        // tried: two tiles in flight need 13 of the 14 ring slots, the input prefetch starves.) =====
+        uint32_t q_base = 0;      // ring sequence number of the run's chunk 0
+        uint32_t q_waited = 0;    // chunks whose x_full barrier has been consumed
+        uint32_t q_rel = 0;       // chunks handed back to the splitter
+        uint32_t d_seq = 0;       // tiles of this CTA so far; tile -> accumulator d_seq & 1
+        rc.start(prof && lane == 0);
+        for (uint32_t it = 0;; ++it) {
+            const Item I = get_item_warp(it);
+            if (!I.valid) break;
+            rc.count(14, I.t1 - I.t0);
+            // a chunk is handed back only after this warp has seen it filled
+            auto release_chunk = [&]() {
+                while (q_waited <= q_rel) {
+                    mbar_wait(&S.x_full[q_waited % kSlots], (q_waited / kSlots) & 1u);
+                    ++q_waited;
                 }
-                q_base += I.n_chunks;
+                tc_commit_elect(&S.x_empty[q_rel % kSlots]);
+                ++q_rel;
+            };
+            TcTile m = tct[I.t0];
+            for (uint32_t t = I.t0; t < I.t1; ++t, ++d_seq) {
+                TcTile mn = m;
+                if (t + 1 < I.t1) mn = tct[t + 1];
+                const uint32_t j_last = (uint32_t)(m.k0 + (int32_t)m.kt - 1 - I.vb) / kChunk;
+                rc.lap(4);
+                while (q_waited <= q_base + j_last) {
+                    mbar_wait(&S.x_full[q_waited % kSlots], (q_waited / kSlots) & 1u);
+                    ++q_waited;
+                }
+                rc.lap(0);
+                const uint32_t gs = d_seq % kGStages;      // G stages follow the tile sequence
+                mbar_wait(&S.g_full[gs], (d_seq / kGStages) & 1u);
+                rc.lap(1);
+                const uint32_t b = d_seq & 1u;
+                mbar_wait(&S.d_empty[b], ((d_seq >> 1) & 1u) ^ 1u);
+                rc.lap(2);
+                tc_fence_after();
+
+                const uint32_t d_tmem = tmem + kColD + b * kN;
+                const uint32_t col0 = ((q_base % kSlots) * kChunk + (uint32_t)(m.k0 - I.vb)) % kRing;
+                const uint32_t n_ks = m.kt >> 3;
+                const uint32_t ghi = b_desc_lo(smem_u32(gst + (size_t)gs * 2 * g_bytes));
+                const uint32_t glo = ghi + (g_bytes >> 4);
+                // small terms first: x_lo * g_hi and x_hi * g_lo, two K steps per issue block
+                const uint32_t ahi = tmem + kColHi, alo = tmem + kColLo;
+                auto wrap = [](uint32_t c) { return c >= kRing ? c - kRing : c; };
+                uint32_t col = col0, dk = 0, ks = 0;
+#pragma unroll 2
+                for (; ks + 2 <= n_ks; ks += 2) {
+                    const uint32_t c1 = wrap(col + 8);
+                    tc_mma_tf32_ts_x4(d_tmem, alo + col, ahi + col, alo + c1, ahi + c1, ghi + dk, glo + dk,
+                                      ghi + dk + kBDescKStep, glo + dk + kBDescKStep, kBDescHi, kIdesc,
+                                      ks != 0);
+                    dk += 2 * kBDescKStep;
+                    col = wrap(c1 + 8);
+                }
+                if (ks < n_ks)
+                    tc_mma_tf32_ts_x2(d_tmem, alo + col, ghi + dk, ahi + col, glo + dk, kBDescHi, kIdesc,
+                                      ks != 0);
+                // x_hi * g_hi, K steps outside-in (front, back, front + 1, back - 1, ...)
+                uint32_t cf = col0, cb = wrap(col0 + 8 * (n_ks - 1));
+                uint32_t df = 0, db = (n_ks - 1) * kBDescKStep, i = 0;
+                auto back = [](uint32_t c) { return c >= 8 ? c - 8 : c + kRing - 8; };
+#pragma unroll 2
+                for (; i + 4 <= n_ks; i += 4) {
+                    const uint32_t cf1 = wrap(cf + 8), cb1 = back(cb);
+                    tc_mma_tf32_ts_x4(d_tmem, ahi + cf, ahi + cb, ahi + cf1, ahi + cb1, ghi + df, ghi + db,
+                                      ghi + df + kBDescKStep, ghi + db - kBDescKStep, kBDescHi, kIdesc, 1u);
+                    df += 2 * kBDescKStep;
+                    db -= 2 * kBDescKStep;
+                    cf = wrap(cf1 + 8);
+                    cb = back(cb1);
+                }
+                for (; i + 2 <= n_ks; i += 2) {
+                    tc_mma_tf32_ts_x2(d_tmem, ahi + cf, ghi + df, ahi + cb, ghi + db, kBDescHi, kIdesc, 1u);
+                    df += kBDescKStep;
+                    db -= kBDescKStep;
+                    cf = wrap(cf + 8);
+                    cb = back(cb);
+                }
+                if (i < n_ks) tc_mma_tf32_ts(d_tmem, ahi + cf, ghi + df, kBDescHi, kIdesc, 1u);
+                rc.lap(3);
+                tc_commit_elect(&S.g_empty[gs]);
+                tc_commit_elect(&S.d_full[b]);
+                // chunks that end at or before the next tile's first frame are free again
+                const bool last = t + 1 == I.t1;
+                while (q_rel < q_base + I.n_chunks &&
+                       (last || I.vb + (int32_t)((q_rel - q_base + 1) * kChunk) <= mn.k0)) {
+                    release_chunk();
+                }
+                m = mn;
             }
+            q_base += I.n_chunks;
         }
         __syncwarp();
     } else if (warp >= 4) {
@@ -333,9 +368,10 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                 hist = job->hist;
                 in = job->in;
             }
+            int pend = -1;      // ring slot whose tcgen05.st are still in flight
             for (uint32_t j = 0; j < I.n_chunks; ++j, ++q_seq) {
                 const uint32_t rs = q_seq % kSlots;
-                rc.lap(7);
+                rc.lap(15);
                 mbar_wait(&S.x_empty[rs], ((q_seq / kSlots) & 1u) ^ 1u);
                 rc.lap(5);
                 tc_fence_after();
@@ -386,11 +422,23 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                     hi[f] = __float_as_uint(h);
                     lo[f] = __float_as_uint(to_tf32(__fsub_rn(x[f], h)));
                 }
+                // the previous chunk's stores had this chunk's loads and arithmetic to complete
+                rc.lap(7);
+                if (pend >= 0) {
+                    tmem_wait_st();
+                    tc_fence_before();
+                    mbar_arrive(&S.x_full[pend]);
+                }
+                rc.lap(11);
                 tmem_st16(tmem + lane_base + kColHi + rs * kChunk, hi);
                 tmem_st16(tmem + lane_base + kColLo + rs * kChunk, lo);
+                pend = (int)rs;
+                rc.lap(12);
+            }
+            if (pend >= 0) {
                 tmem_wait_st();
                 tc_fence_before();
-                mbar_arrive(&S.x_full[rs]);
+                mbar_arrive(&S.x_full[pend]);
             }
         }
     } else {
@@ -399,6 +447,12 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
         const uint32_t ml = row / CH, c = row % CH;
         const uint32_t lane_base = ((warp & 3u) * 32u) << 16;
         const uint32_t pitch = tc_stage_pitch(CH);
+        constexpr uint32_t kFpp = 4 / CH;                    // frames per 16-byte piece
+        constexpr uint32_t kPieces = kN / kFpp;              // pieces per member and tile
+        constexpr uint32_t kIter = kMpg * kPieces / kRows;   // pieces per thread and tile (8)
+        constexpr uint32_t kMemStep = kRows / kPieces;       // member stride between a thread's pieces
+        const uint32_t p_fr = (tid % kPieces) * kFpp;        // first frame of this thread's pieces
+        const uint32_t mem0 = tid / kPieces;
         uint32_t d_seq = 0;
         rc.start(prof && tid == 0);
         for (uint32_t it = 0;; ++it) {
@@ -406,15 +460,27 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
             if (!I.valid) break;
             const uint32_t m0 = I.group * kMpg;
             const uint32_t nm = min(kMpg, U.n_members - m0);
-            named_bar_sync(1, kRows);                // the previous item's stores are done
-            if (tid < nm) {
-                const JobDev *job = P.jobs + U.member_off + m0 + tid;
-                S.out[tid] = job->out;
-                S.cap[tid] = job->out_capacity;
+            // this thread's kIter members: output pointer, capacity, 16-byte alignment
+            float *outp[kIter];
+            uint32_t capf[kIter];
+            uint32_t vec_ok = 0;
+#pragma unroll
+            for (uint32_t i = 0; i < kIter; ++i) {
+                const uint32_t mem = mem0 + kMemStep * i;
+                outp[i] = nullptr;
+                capf[i] = 0;
+                if (mem < nm) {
+                    const JobDev *job = P.jobs + U.member_off + m0 + mem;
+                    outp[i] = job->out;
+                    const uint64_t cap = job->out_capacity;
+                    capf[i] = cap > 0xffffffffull ? 0xffffffffu : (uint32_t)cap;
+                    if ((reinterpret_cast<uintptr_t>(outp[i]) & 15u) == 0) vec_ok |= 1u << i;
+                }
             }
-            named_bar_sync(1, kRows);
+            TcTile m_next = tct[I.t0];
             for (uint32_t t = I.t0; t < I.t1; ++t, ++d_seq) {
-                const TcTile m = tct[t];
+                const TcTile m = m_next;
+                if (t + 1 < I.t1) m_next = tct[t + 1];
                 const uint32_t b = d_seq & 1u;
                 rc.lap(10);
                 mbar_wait(&S.d_full[b], (d_seq >> 1) & 1u);
@@ -425,36 +491,36 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                 tmem_wait_ld();
                 tc_fence_before();
                 mbar_arrive(&S.d_empty[b]);
-                // stage[member][frame][channel]
-                float *st = stage + ml * pitch + c;
+                // stage[buffer][member][frame][channel]; two buffers, so ONE barrier per tile: the
+                // writes of tile t+1 reuse the buffer of tile t-1, whose reads every thread has
+                // finished before it arrives at tile t's barrier
+                float *sb = stage + (d_seq & 1u) * (kMpg * pitch);
+                float *st = sb + ml * pitch + c;
 #pragma unroll
                 for (uint32_t o = 0; o < kN; ++o) st[o * CH] = __uint_as_float(acc[o]);
                 named_bar_sync(1, kRows);
                 rc.lap(9);
-                constexpr uint32_t kFpp = 4 / CH;            // frames per 16-byte piece
-                constexpr uint32_t kPieces = kN / kFpp;
-                for (uint32_t e = tid; e < nm * kPieces; e += kRows) {
-                    const uint32_t mem = e / kPieces, p = e - mem * kPieces;
-                    const uint32_t fr = kFpp * p;
-                    if (fr >= m.n_out) continue;
-                    const float4 q4 = *reinterpret_cast<const float4 *>(stage + mem * pitch + fr * CH);
-                    float *outm = S.out[mem];
-                    const uint64_t cap = S.cap[mem];
-                    const uint64_t o = (uint64_t)m.o_start + fr;
-                    const bool full = fr + kFpp <= m.n_out && o + kFpp <= cap;
-                    if (full && ((reinterpret_cast<uintptr_t>(outm) & 15u) == 0)) {
-                        *reinterpret_cast<float4 *>(outm + o * CH) = q4;
-                    } else {
-                        const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
+                if (p_fr < m.n_out) {
+                    const uint32_t o = m.o_start + p_fr;
+                    const bool rows_full = p_fr + kFpp <= m.n_out;
+                    const float *src = sb + mem0 * pitch + p_fr * CH;
 #pragma unroll
-                        for (uint32_t f = 0; f < kFpp; ++f)
-                            if (fr + f < m.n_out && o + f < cap)
+                    for (uint32_t i = 0; i < kIter; ++i) {
+                        if (outp[i] == nullptr) continue;
+                        const float4 q4 = *reinterpret_cast<const float4 *>(src + i * (kMemStep * pitch));
+                        if (rows_full && ((vec_ok >> i) & 1u) && (uint64_t)o + kFpp <= capf[i]) {
+                            *reinterpret_cast<float4 *>(outp[i] + (size_t)o * CH) = q4;
+                        } else {
+                            const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
-                                for (uint32_t cc = 0; cc < (uint32_t)CH; ++cc)
-                                    outm[(o + f) * CH + cc] = qv[f * CH + cc];
+                            for (uint32_t f = 0; f < kFpp; ++f)
+                                if (p_fr + f < m.n_out && (uint64_t)o + f < capf[i])
+#pragma unroll
+                                    for (uint32_t cc = 0; cc < (uint32_t)CH; ++cc)
+                                        outp[i][((size_t)o + f) * CH + cc] = qv[f * CH + cc];
+                        }
                     }
                 }
-                named_bar_sync(1, kRows);
             }
         }
     }
@@ -603,7 +669,7 @@ void launch_tc_gmat(const UnitDev *units, const TileRec *tiles, const PlanEntry 
 
 void launch_conv_tc(const TcParams &p, const CUtensorMap &tmap, int sm_count, cudaStream_t stream) {
     const size_t smem = (size_t)kXStages * kXStageBytes + (size_t)kGStages * 2 * p.kt_max * 128u +
-                        (size_t)(kRows / p.channels) * tc_stage_pitch(p.channels) * sizeof(float);
+                        (size_t)2 * (kRows / p.channels) * tc_stage_pitch(p.channels) * sizeof(float);
     // one SM is left free for the (serial) plan kernel of the next submit, as in fir_fast.cu
     const uint32_t grid = (uint32_t)(sm_count > 8 ? sm_count - 1 : sm_count);
     auto launch = [&](auto kern) {

@@ -97,18 +97,38 @@ RSB_HD PhasePoint phase_point(double position) {
     return r;
 }
 
-// ceil(num / den) for 0 < num, den < 2^53.  A 64-bit integer division costs ~100 instructions
-// on the GPU (no hardware divider) and sits on the planner's serial critical path, so the
-// quotient is estimated in f64 and corrected exactly with integer multiplies.
-RSB_HD int64_t ceil_div_53(int64_t num, int64_t den) {
+// ceil(num / den) for 0 < num, den < 2^53 with a small quotient (a call's output count).  A
+// 64-bit integer division costs ~100 instructions on the GPU and an f64 division ~250 cycles of
+// latency, and both sit on the planner's serial critical path (about 20 per 512-frame call), so
+// the quotient is estimated with ONE multiply by a cached reciprocal and corrected exactly with
+// integer arithmetic.  The step `den` is a constant of the binade (see the header comment), so
+// the reciprocal is computed once per binade and reused by every later call.
+struct DivCache {
+    int64_t den[16];
+    double inv[16];
+};
+RSB_HD void div_cache_reset(DivCache &c) {
+    for (int i = 0; i < 16; ++i) { c.den[i] = 0; c.inv[i] = 0.0; }
+}
+RSB_HD int64_t ceil_div_53(int64_t num, int64_t den, DivCache &c, int slot) {
+    slot &= 15;
+    if (c.den[slot] != den) {
+        c.den[slot] = den;
 #if defined(__CUDA_ARCH__)
-    int64_t q = (int64_t)__ddiv_rn((double)num, (double)den);   // floor estimate, off by <= 1
+        c.inv[slot] = __ddiv_rn(1.0, (double)den);
 #else
-    int64_t q = (int64_t)((double)num / (double)den);
+        c.inv[slot] = 1.0 / (double)den;
+#endif
+    }
+#if defined(__CUDA_ARCH__)
+    int64_t q = (int64_t)__dmul_rn((double)num, c.inv[slot]);   // floor estimate, off by <= 1
+#else
+    volatile double est = (double)num * c.inv[slot];
+    int64_t q = (int64_t)est;
 #endif
     int64_t rem = num - q * den;
-    if (rem < 0) { q -= 1; rem += den; }
-    if (rem >= den) { q += 1; rem -= den; }
+    while (rem < 0) { q -= 1; rem += den; }
+    while (rem >= den) { q += 1; rem -= den; }
     return rem > 0 ? q + 1 : q;
 }
 
@@ -123,7 +143,7 @@ RSB_HD bool same_binade(int64_t a, int64_t b) {
 // Sink must provide: void seg(int64_t base_bits, int64_t step_bits, uint32_t n).
 template <class Sink>
 RSB_HD uint32_t plan_call_outputs(double &pos, double ratio, uint32_t available, uint32_t taps,
-                                  uint32_t cap, Sink &sink) {
+                                  uint32_t cap, Sink &sink, DivCache &dc) {
     if (available < taps || cap == 0) return 0;
     // off + taps > available  <=>  floor(p) >= available - taps + 1  <=>  p >= L
     const double L = (double)(available - taps + 1);
@@ -144,14 +164,14 @@ RSB_HD uint32_t plan_call_outputs(double &pos, double ratio, uint32_t available,
                 const int64_t mant_lim = (int64_t)1 << 53;
                 const int64_t B = (b1 & (((int64_t)1 << 52) - 1)) | ((int64_t)1 << 52);
                 // elements j with B + j*D < 2^53 stay below 2^(e+1)
-                int64_t n = ceil_div_53(mant_lim - B, D);
-                // elements with position < L
                 const int e = (int)((b1 >> 52) & 0x7ff) - 1023;
+                int64_t n = ceil_div_53(mant_lim - B, D, dc, e);
+                // elements with position < L
                 if (L < bits2d((int64_t)(e + 1 + 1023) << 52)) {
                     // L / u is an exact integer < 2^53
                     const double scale = bits2d((int64_t)(52 - e + 1023) << 52);
                     const int64_t LQ = (int64_t)(L * scale);
-                    const int64_t nL = ceil_div_53(LQ - B, D);   // LQ > B because p1 < L
+                    const int64_t nL = ceil_div_53(LQ - B, D, dc, e);   // LQ > B because p1 < L
                     if (nL < n) n = nL;
                 }
                 const int64_t room = (int64_t)(cap - count - 1);
@@ -196,12 +216,12 @@ struct CallResult {
 // so read_position itself is unobservable and is not modelled.
 template <class Sink>
 RSB_HD CallResult plan_call(PlanState &st, double ratio, uint32_t taps, uint32_t in_frames,
-                            uint32_t cap_frames, Sink &sink) {
+                            uint32_t cap_frames, Sink &sink, DivCache &dc) {
     CallResult r;
     uint32_t room = kInputCapacity - st.available;
     r.copied = in_frames < room ? in_frames : room;               // :526-528
     st.available += r.copied;                                     // :538
-    r.produced = plan_call_outputs(st.position, ratio, st.available, taps, cap_frames, sink);
+    r.produced = plan_call_outputs(st.position, ratio, st.available, taps, cap_frames, sink, dc);
 #if defined(__CUDA_ARCH__)
     double fl = floor(st.position);
 #else

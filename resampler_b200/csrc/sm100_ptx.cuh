@@ -101,16 +101,81 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar) {
                      smem_u32(bar))
                  : "memory");
 }
-// D[tmem] (+)= A[tmem] * B[smem descriptor], kind::tf32, issued by ONE thread for the CTA.
-__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
-                                               uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem descriptor], kind::tf32.  Called by ALL lanes of a converged warp
+// with warp-uniform arguments; one elected lane issues.  (Issuing from inside an `if (lane == 0)`
+// makes ptxas wrap every MMA in an ELECT / BRA.U.ANY loop: measured 66 cycles per MMA, four
+// times the 16 cycles an M=128, N=32 MMA keeps the tensor pipe busy.)  The descriptor is passed
+// as (lo, hi) halves: only `lo` (the start address field) changes between K steps.
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo,
+                                               uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        ".reg .pred p, e;\n\t"
+        ".reg .b64 bd;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "mov.b64 bd, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, p;\n\t"
         "}" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Two MMAs into the same accumulator with one election: the first honours `accumulate`, the
+// second always accumulates.
+__device__ __forceinline__ void tc_mma_tf32_ts_x2(uint32_t d_tmem, uint32_t a0, uint32_t b0_lo,
+                                                  uint32_t a1, uint32_t b1_lo, uint32_t b_hi,
+                                                  uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, t, e;\n\t"
+        ".reg .b64 bd0, bd1;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "mov.b64 bd0, {%2, %5};\n\t"
+        "mov.b64 bd1, {%4, %5};\n\t"
+        "setp.ne.b32 p, %7, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd0, %6, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%3], bd1, %6, t;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(a0), "r"(b0_lo), "r"(a1), "r"(b1_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Four MMAs into the same accumulator with one election (measured 23 cycles per MMA against 36
+// for one asm block per MMA, tools/experiments/mma_issue_test.cu): the first honours
+// `accumulate`, the others always accumulate.
+__device__ __forceinline__ void tc_mma_tf32_ts_x4(uint32_t d_tmem, uint32_t a0, uint32_t a1,
+                                                  uint32_t a2, uint32_t a3, uint32_t b0_lo,
+                                                  uint32_t b1_lo, uint32_t b2_lo, uint32_t b3_lo,
+                                                  uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, t, e;\n\t"
+        ".reg .b64 d0, d1, d2, d3;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "mov.b64 d0, {%5, %9};\n\t"
+        "mov.b64 d1, {%6, %9};\n\t"
+        "mov.b64 d2, {%7, %9};\n\t"
+        "mov.b64 d3, {%8, %9};\n\t"
+        "setp.ne.b32 p, %11, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], d0, %10, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%2], d1, %10, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%3], d2, %10, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%4], d3, %10, t;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0_lo), "r"(b1_lo), "r"(b2_lo), "r"(b3_lo), "r"(b_hi),
+        "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// All prior tcgen05.mma of the electing warp arrive (once) on `bar` when they have completed;
+// called by all lanes of a converged warp.
+__device__ __forceinline__ void tc_commit_elect(uint64_t *bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}" ::"r"(smem_u32(bar))
         : "memory");
 }
 // Each thread of the warp writes 16 consecutive 32-bit columns of its own TMEM lane.

@@ -300,12 +300,54 @@ def test_stopband_attenuation_on_gpu():
     (1, 192000, 48000, 3, 512, 0, 40),    # ratio 4
 ])
 def test_fast_kernel_within_tolerance(ch, in_hz, out_hz, lat, call_frames, cap_frames, n_streams):
+    check_kernel_within_tolerance(Kernel.FAST, ch, in_hz, out_hz, lat, call_frames, cap_frames,
+                                  n_streams)
+
+
+# ---------------------------------------------------------------------------------------------
+# TENSOR kernel (tcgen05, 3xTF32): same bar -- counts/phases bit-exact, samples within 1e-6
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ch,in_hz,out_hz,lat,call_frames,cap_frames,n_streams", [
+    (2, 44100, 48000, 3, 512, 0, 70),     # config 2 pattern; one full + one partial row group
+    (2, 48000, 44100, 3, 512, 0, 9),      # config 1 pattern
+    (1, 16000, 48000, 1, 160, 0, 130),    # config 3 (i), mono, 32 taps; 128 + 2 streams
+    (1, 44100, 48000, 3, 512, 0, 200),    # mono, 128 taps
+    (2, 44100, 48000, 0, 100, 0, 5),      # 16 taps
+    (2, 44100, 48000, 3, 512, 100, 4),    # capacity-limited calls
+    (2, 22050, 48000, 3, 4096, 0, 3),     # maximum call size
+    (1, 96000, 48000, 2, 512, 0, 40),     # ratio 2, 64 taps
+])
+def test_tensor_kernel_within_tolerance(ch, in_hz, out_hz, lat, call_frames, cap_frames, n_streams):
+    check_kernel_within_tolerance(Kernel.TENSOR, ch, in_hz, out_hz, lat, call_frames, cap_frames,
+                                  n_streams)
+
+
+def test_tensor_kernel_falls_back_for_ragged_batches_and_wide_ratios():
+    """Streams with different sizes do not share a plan: the batch runs on FAST / EXACT and is
+    still right; a ratio whose tile window does not fit the TMEM ring is refused up front."""
+    n, ch = 6, 2
+    rng = np.random.default_rng(5)
+    batch = FirBatch(n, ch, 44100, 48000, Latency.Sample64, Attenuation.Db90, kernel=Kernel.TENSOR)
+    xs = [noise(rng, (3000 + 37 * s) * ch) for s in range(n)]
+    res = batch.process(xs, 512 * ch, 0)
+    assert batch.last_kernel() != Kernel.TENSOR
+    for s in range(n):
+        ref = oracle_stream(ch, 44100, 48000, 3, 1, xs[s], 512 * ch, 0)
+        assert res["produced"][s] == len(ref["out"])
+        assert np.max(np.abs(res["out"][s].astype(np.float64) - ref["out"])) <= TOL_FAST
+    batch.close()
+    with pytest.raises(ValueError):
+        FirBatch(4, 1, 192000, 48000, Latency.Sample64, Attenuation.Db90, kernel=Kernel.TENSOR)
+
+
+def check_kernel_within_tolerance(kernel, ch, in_hz, out_hz, lat, call_frames, cap_frames,
+                                  n_streams):
     rng = np.random.default_rng(in_hz + call_frames + n_streams)
     frames = min(in_hz // 4, 9000) + 29
     xs = [noise(rng, frames * ch) for _ in range(n_streams)]
-    batch = FirBatch(n_streams, ch, in_hz, out_hz, Latency(lat), Attenuation.Db90,
-                     kernel=Kernel.FAST)
+    batch = FirBatch(n_streams, ch, in_hz, out_hz, Latency(lat), Attenuation.Db90, kernel=kernel)
     res = batch.process(xs, call_frames * ch, cap_frames * ch, flags=FLAG_KEEP_PLAN)
+    assert batch.last_kernel() == kernel
     worst = 0.0
     for s in range(n_streams):
         ref = oracle_stream(ch, in_hz, out_hz, lat, 1, xs[s], call_frames * ch, cap_frames * ch,
@@ -360,7 +402,7 @@ def test_fast_kernel_streaming_submit_and_divergence():
 def test_device_memspace_async_and_full_size_properties():
     """Device-resident buffers, async submit; at a larger size checks size-independent
     properties: linearity (2x input -> 2x output exactly, scaling by 2 is exact in fp32) and
-    determinism, for both kernels."""
+    determinism, for every kernel."""
     from resampler_b200.fir import FLAG_ASYNC, MEM_DEVICE, DeviceBuffer
     from resampler_b200 import _lib
     n, ch, frames = 256, 2, 44100
@@ -373,7 +415,7 @@ def test_device_memspace_async_and_full_size_properties():
     out_stride = (int(frames * 48000 / 44100) + 8) * ch
     n_expected = len(oracle_stream(ch, 44100, 48000, 3, 1, host[0], 512 * ch)["out"])
     outs = {}
-    for kern in (Kernel.EXACT, Kernel.FAST):
+    for kern in (Kernel.EXACT, Kernel.FAST, Kernel.TENSOR):
         b = FirBatch(n, ch, 44100, 48000, Latency.Sample64, Attenuation.Db90, kernel=kern)
         for name, src in (("x", d_in), ("2x", d_in2), ("x_again", d_in)):
             b.reset(-1)
@@ -390,9 +432,10 @@ def test_device_memspace_async_and_full_size_properties():
         assert np.array_equal(outs[(kern, "x")], outs[(kern, "x_again")])
         assert np.array_equal(outs[(kern, "2x")], outs[(kern, "x")] * np.float32(2.0))
         b.close()
-    # the two kernels agree within the tolerance on every sample of every stream
-    assert np.max(np.abs(outs[(Kernel.FAST, "x")].astype(np.float64) -
-                         outs[(Kernel.EXACT, "x")])) <= TOL_FAST
+    # the kernels agree within the tolerance on every sample of every stream
+    for kern in (Kernel.FAST, Kernel.TENSOR):
+        assert np.max(np.abs(outs[(kern, "x")].astype(np.float64) -
+                             outs[(Kernel.EXACT, "x")])) <= TOL_FAST, kern
     # and stream 0 / stream n-1 equal the oracle (EXACT: bit for bit)
     for s in (0, n - 1):
         ref = oracle_stream(ch, 44100, 48000, 3, 1, host[s], 512 * ch)

@@ -14,7 +14,7 @@ from resampler_b200.fir import FLAG_ASYNC, MEM_DEVICE, DeviceBuffer  # noqa: E40
 
 NAMES = ["M.wait_x_full", "M.wait_g_full", "M.wait_d_empty", "M.issue", "M.commit+meta",
          "S.wait_x_empty", "S.wait_xs_full", "S.split+st", "E.wait_d_full", "E.ld+stage", "E.store",
-         "PX.wait_xs_empty", "PG.wait_g_empty", "kernel", "tiles", "P.other"]
+         "S.wait_st+arrive", "S.st", "kernel", "tiles", "S.other"]
 
 
 def main():
