@@ -44,7 +44,7 @@ namespace rsb {
 // splitter [5] wait x_empty [6] wait xs_full [7] loads + split [11] wait::st + arrive [12] tcgen05.st
 // [15] loop overhead; epilogue [8] wait d_full [9] tcgen05.ld + staging [10] stores;
 // [13] kernel cycles of CTA 0; [14] tiles of CTA 0.
-__device__ unsigned long long g_tc_cycles[16];
+__device__ unsigned long long g_tc_cycles[24];
 __device__ int g_tc_prof = 0;
 
 namespace {
@@ -113,9 +113,10 @@ constexpr uint32_t kBDescKStep = 1024u >> 4;   // descriptor increment per K ste
 
 struct TcSmem {
     uint64_t xs_full[kXStages], xs_empty[kXStages];
-    uint64_t g_full[kGStages], g_empty[kGStages];
+    uint64_t g_full[kGStages];
+    uint64_t t_done[4];       // tile t's MMAs have completed: barrier t & 3 (count 1, tcgen05.commit)
     uint64_t x_full[kSlots], x_empty[kSlots];
-    uint64_t d_full[2], d_empty[2];
+    uint64_t d_empty[2];
     uint64_t item_full[kItemSlots], item_empty[kItemSlots];
     Item item[kItemSlots];
     uint32_t tmem_base;
@@ -140,9 +141,10 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
     rc.start(false);
     if (tid == 0) {
         for (uint32_t i = 0; i < kXStages; ++i) { mbar_init(&S.xs_full[i], 1); mbar_init(&S.xs_empty[i], kRows); }
-        for (uint32_t i = 0; i < kGStages; ++i) { mbar_init(&S.g_full[i], 1); mbar_init(&S.g_empty[i], 1); }
+        for (uint32_t i = 0; i < kGStages; ++i) mbar_init(&S.g_full[i], 1);
+        for (uint32_t i = 0; i < 4; ++i) mbar_init(&S.t_done[i], 1);
         for (uint32_t i = 0; i < kSlots; ++i) { mbar_init(&S.x_full[i], kRows); mbar_init(&S.x_empty[i], 1); }
-        for (uint32_t i = 0; i < 2; ++i) { mbar_init(&S.d_full[i], 1); mbar_init(&S.d_empty[i], kRows); }
+        for (uint32_t i = 0; i < 2; ++i) mbar_init(&S.d_empty[i], kRows);
         for (uint32_t i = 0; i < kItemSlots; ++i) {
             mbar_init(&S.item_full[i], 1);
             mbar_init(&S.item_empty[i], 2 + 2 * kRows);
@@ -237,7 +239,10 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                 for (uint32_t t = I.t0; t < I.t1; ++t) {
                     const uint32_t kt_next = t + 1 < I.t1 ? tct[t + 1].kt : 0u;
                     const uint32_t s = g_seq % kGStages;
-                    mbar_wait(&S.g_empty[s], ((g_seq / kGStages) & 1u) ^ 1u);
+                    if (g_seq >= kGStages) {     // the stage's previous tile has been multiplied
+                        const uint32_t prev = g_seq - kGStages;
+                        mbar_wait(&S.t_done[prev & 3u], (prev >> 2) & 1u);
+                    }
                     const uint32_t bytes = kt * 128u;
                     const float *src = P.gmat + (size_t)(U.tile_off + t) * tile_floats;
                     uint8_t *dst = gst + (size_t)s * 2 * g_bytes;
@@ -337,14 +342,15 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                 }
                 if (i < n_ks) tc_mma_tf32_ts(d_tmem, ahi + cf, ghi + df, kBDescHi, kIdesc, 1u);
                 rc.lap(3);
-                tc_commit_elect(&S.g_empty[gs]);
-                tc_commit_elect(&S.d_full[b]);
-                // chunks that end at or before the next tile's first frame are free again
+                // one commit tells the epilogue (accumulator ready) and the G producer (stage free)
+                tc_commit_elect(&S.t_done[d_seq & 3u]);
+                // Chunks that end at or before the next tile's first frame are free again.  (Handing
+                // them back earlier, right after the front K steps of this pass, was measured
+                // slower: a tcgen05.commit in the middle of the MMA stream stalls the issue.)
                 const bool last = t + 1 == I.t1;
                 while (q_rel < q_base + I.n_chunks &&
-                       (last || I.vb + (int32_t)((q_rel - q_base + 1) * kChunk) <= mn.k0)) {
+                       (last || I.vb + (int32_t)((q_rel - q_base + 1) * kChunk) <= mn.k0))
                     release_chunk();
-                }
                 m = mn;
             }
             q_base += I.n_chunks;
@@ -483,7 +489,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                 if (t + 1 < I.t1) m_next = tct[t + 1];
                 const uint32_t b = d_seq & 1u;
                 rc.lap(10);
-                mbar_wait(&S.d_full[b], (d_seq >> 1) & 1u);
+                mbar_wait(&S.t_done[d_seq & 3u], (d_seq >> 2) & 1u);
                 rc.lap(8);
                 tc_fence_after();
                 uint32_t acc[kN];
@@ -683,8 +689,8 @@ void launch_conv_tc(const TcParams &p, const CUtensorMap &tmap, int sm_count, cu
 uint32_t tc_rows_per_group() { return kRows; }
 
 void tc_phase_profile(int enable, unsigned long long *out16) {
-    if (out16) cudaMemcpyFromSymbol(out16, g_tc_cycles, sizeof(unsigned long long) * 16);
-    unsigned long long zero[16] = {0};
+    if (out16) cudaMemcpyFromSymbol(out16, g_tc_cycles, sizeof(unsigned long long) * 24);
+    unsigned long long zero[24] = {0};
     cudaMemcpyToSymbol(g_tc_cycles, zero, sizeof(zero));
     cudaMemcpyToSymbol(g_tc_prof, &enable, sizeof(int));
 }

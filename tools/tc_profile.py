@@ -14,7 +14,8 @@ from resampler_b200.fir import FLAG_ASYNC, MEM_DEVICE, DeviceBuffer  # noqa: E40
 
 NAMES = ["M.wait_x_full", "M.wait_g_full", "M.wait_d_empty", "M.issue", "M.commit+meta",
          "S.wait_x_empty", "S.wait_xs_full", "S.split+st", "E.wait_d_full", "E.ld+stage", "E.store",
-         "S.wait_st+arrive", "S.st", "kernel", "tiles", "S.other"]
+         "S.wait_st+arrive", "S.st", "kernel", "tiles", "S.other", "M.fence+addr", "M.small_pass",
+         "M.commit1", "M.commit2", "x", "x", "x", "x"]
 
 
 def main():
@@ -34,7 +35,7 @@ def main():
         b.process_ptrs(*args, memspace=MEM_DEVICE, flags=FLAG_ASYNC)
     b.sync()
     assert b.last_kernel() == Kernel.TENSOR
-    out = (C.c_uint64 * 16)()
+    out = (C.c_uint64 * 24)()
     lib.rsb_debug_tc_cycles(b._h, 1, out)
     b.reset(-1)
     b.process_ptrs(*args, memspace=MEM_DEVICE, flags=FLAG_ASYNC)
@@ -44,7 +45,7 @@ def main():
     cyc = np.array(out[:], dtype=np.float64)
     tiles = max(cyc[14], 1.0)
     res = {"conv_ms": conv_ms, "tiles_cta0": int(cyc[14]), "kernel_cycles_per_tile": round(cyc[13] / tiles, 1),
-           "cycles_per_tile": {NAMES[i]: round(cyc[i] / tiles, 1) for i in list(range(13)) + [15]}}
+           "cycles_per_tile": {NAMES[i]: round(cyc[i] / tiles, 1) for i in list(range(13)) + [15, 16, 17, 18, 19]}}
     print(json.dumps(res))
     (ROOT / "gpurun_out").mkdir(exist_ok=True)
     (ROOT / "gpurun_out" / "tc_profile.json").write_text(json.dumps(res, indent=1))
