@@ -475,7 +475,10 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     // tensor-core kernel: needs that tensor view (TMA streams the input chunk by chunk)
     bool use_tc = false;
     CUtensorMap tc_tmap;
-    if (h->kernel_mode == RSB_KERNEL_TENSOR && in_uniform && rsb::tc_supported(ch, h->taps, h->ratio))
+    // AUTO: when at least half of a 128-row group is filled (below that the MMA's M is mostly idle)
+    const bool want_tc = h->kernel_mode == RSB_KERNEL_TENSOR ||
+                         (h->kernel_mode == RSB_KERNEL_AUTO && (uint64_t)n * ch >= 64);
+    if (want_tc && in_uniform && rsb::tc_supported(ch, h->taps, h->ratio))
         use_tc = rsb::tc_make_input_tensor_map(&tc_tmap, hj[0].in, in_stride,
                                                unit_keys[0].total_frames, n, ch);
 
