@@ -76,9 +76,9 @@ constexpr uint32_t kChunk = 16;                    // frames per input chunk / r
 constexpr uint32_t kRing = 224;                    // frames in a TMEM ring
 constexpr uint32_t kSlots = kRing / kChunk;        // 14
 constexpr uint32_t kColHi = 0, kColLo = kRing, kColD = 2 * kRing;
-constexpr uint32_t kXStages = 4;                   // TMA landing buffers for input chunks
+constexpr uint32_t kXStages = 6;                   // TMA landing buffers for input chunks
 constexpr uint32_t kXStageBytes = kRows * kChunk * 4;   // 8192 for mono and stereo alike
-constexpr uint32_t kGStages = 3;
+constexpr uint32_t kGStages = 2;
 constexpr uint32_t kTcThreads = 11 * 32;
 constexpr uint32_t kKtLimit = 192;                 // largest K extent of a tile (12 + 1 chunks)
 constexpr uint32_t kItemSlots = 2;
@@ -542,13 +542,13 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
 
 // One CTA per tile: builds the tile's banded filter matrix, split into TF32 hi and lo parts, in
 // the canonical K-major core-matrix layout the MMA reads ([K group of 4][32 rows][4 floats]),
-// K counted from k0 = the first needed virtual frame rounded down to the 8-frame grid.
+// K counted from k0 = the first needed virtual frame rounded down to the 8-frame grid.  A thread
+// owns one output row and walks along its two coefficient rows, one 16-byte piece (4 K values)
+// of the hi and of the lo matrix per step; consecutive lanes write consecutive pieces.
 template <int TAPS>
 __global__ void __launch_bounds__(128)
 tc_gmat_kernel(const UnitDev *units, const TileRec *tiles, const PlanEntry *entries,
                const float *coeffs, float *gmat, TcTile *tct, uint32_t kt_max) {
-    extern __shared__ float4 sh4[];
-    float *sh = reinterpret_cast<float *>(sh4);          // [2][kt_max/4][32][4]
     const UnitDev &U = units[0];
     const uint32_t t = blockIdx.x;
     if (t >= U.n_tiles) return;
@@ -556,7 +556,6 @@ tc_gmat_kernel(const UnitDev *units, const TileRec *tiles, const PlanEntry *entr
     const TileRec rec = tiles[tile];
     const uint32_t tid = threadIdx.x;
     const uint32_t half = kt_max * kN;                   // floats in the hi (or lo) matrix
-    for (uint32_t i = tid; i < 2 * half / 4; i += 128) sh4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     const PlanEntry e0 = entries[tile * kTileOut];
     const PlanEntry el = entries[tile * kTileOut + rec.n_out - 1];
     // K origin: the first needed frame rounded down to a multiple of 8 counted from the first
@@ -573,35 +572,34 @@ tc_gmat_kernel(const UnitDev *units, const TileRec *tiles, const PlanEntry *entr
         m.o_start = rec.o_start;
         tct[tile] = m;
     }
-    __syncthreads();
-    const uint32_t o = tid >> 2, part = tid & 3u;        // output row, quarter of its taps
-    if (o < rec.n_out) {
-        const PlanEntry e = entries[tile * kTileOut + o];
-        const uint32_t p1 = e.phase1;
-        const uint32_t p2 = p1 + 1 < kPhases - 1 ? p1 + 1 : kPhases - 1;
-        const float fr = e.frac, omf = __fsub_rn(1.0f, fr);
-        const int d = e.v - k0;
-        constexpr int kPer = TAPS / 4;
-        const float *ca = coeffs + (size_t)p1 * TAPS + part * kPer;
-        const float *cb = coeffs + (size_t)p2 * TAPS + part * kPer;
-#pragma unroll 4
-        for (int j = 0; j < kPer; ++j) {
-            const float g = __fmaf_rn(__ldg(cb + j), fr, __fmul_rn(__ldg(ca + j), omf));
-            const float hi = to_tf32(g);
-            const float lo = to_tf32(__fsub_rn(g, hi));
-            const uint32_t k = (uint32_t)(d + (int)part * kPer + j);
-            if (k >= kt) continue;
-            const uint32_t idx = ((k >> 2) * kN + o) * 4 + (k & 3u);
-            sh[idx] = hi;
-            sh[half + idx] = lo;
+    const uint32_t o = tid & 31u;                        // output row of this thread
+    const bool row_ok = o < rec.n_out;
+    PlanEntry e = e0;
+    if (row_ok) e = entries[tile * kTileOut + o];
+    const uint32_t p1 = e.phase1;
+    const uint32_t p2 = p1 + 1 < kPhases - 1 ? p1 + 1 : kPhases - 1;
+    const float fr = e.frac, omf = __fsub_rn(1.0f, fr);
+    const int d = e.v - k0;                              // K index of the row's tap 0
+    const float *ca = coeffs + (size_t)p1 * TAPS;
+    const float *cb = coeffs + (size_t)p2 * TAPS;
+    float4 *dst_hi = reinterpret_cast<float4 *>(gmat + tile * (size_t)2 * half);
+    float4 *dst_lo = dst_hi + half / 4;
+    for (uint32_t kg = tid >> 5; kg < kt / 4; kg += 4) {
+        float hi[4] = {0.f, 0.f, 0.f, 0.f}, lo[4] = {0.f, 0.f, 0.f, 0.f};
+        const int j0 = (int)(4 * kg) - d;
+        if (row_ok && j0 > -4 && j0 < TAPS) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = j0 + q;
+                if (j >= 0 && j < TAPS) {
+                    const float g = __fmaf_rn(__ldg(cb + j), fr, __fmul_rn(__ldg(ca + j), omf));
+                    hi[q] = to_tf32(g);
+                    lo[q] = to_tf32(__fsub_rn(g, hi[q]));
+                }
+            }
         }
-    }
-    __syncthreads();
-    float4 *dst = reinterpret_cast<float4 *>(gmat + tile * (size_t)2 * half);
-    const uint32_t used = kt * kN / 4;                   // float4 of the K prefix in use
-    for (uint32_t i = tid; i < used; i += 128) {
-        dst[i] = sh4[i];
-        dst[half / 4 + i] = sh4[half / 4 + i];
+        dst_hi[kg * kN + o] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        dst_lo[kg * kN + o] = make_float4(lo[0], lo[1], lo[2], lo[3]);
     }
 }
 
@@ -660,16 +658,11 @@ void launch_tc_gmat(const UnitDev *units, const TileRec *tiles, const PlanEntry 
                     uint32_t tile_cap, cudaStream_t stream) {
     if (tile_cap == 0) return;
     const uint32_t kt_max = tc_kt_max(taps, ratio);
-    const size_t smem = (size_t)2 * kt_max * kN * sizeof(float);
-    auto launch = [&](auto kern) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<tile_cap, 128, smem, stream>>>(units, tiles, entries, coeffs, gmat, tct, kt_max);
-    };
     switch (taps) {
-        case 16: launch(tc_gmat_kernel<16>); break;
-        case 32: launch(tc_gmat_kernel<32>); break;
-        case 64: launch(tc_gmat_kernel<64>); break;
-        default: launch(tc_gmat_kernel<128>); break;
+        case 16: tc_gmat_kernel<16><<<tile_cap, 128, 0, stream>>>(units, tiles, entries, coeffs, gmat, tct, kt_max); break;
+        case 32: tc_gmat_kernel<32><<<tile_cap, 128, 0, stream>>>(units, tiles, entries, coeffs, gmat, tct, kt_max); break;
+        case 64: tc_gmat_kernel<64><<<tile_cap, 128, 0, stream>>>(units, tiles, entries, coeffs, gmat, tct, kt_max); break;
+        default: tc_gmat_kernel<128><<<tile_cap, 128, 0, stream>>>(units, tiles, entries, coeffs, gmat, tct, kt_max); break;
     }
 }
 
