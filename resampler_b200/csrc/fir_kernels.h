@@ -94,11 +94,13 @@ struct TcParams {
     uint32_t groups;          // member groups of 128 / channels streams
     uint32_t run_tiles;       // consecutive tiles per work item
     uint32_t kt_max;
+    uint32_t issuers;         // MMA issuer warps: 2 when two consecutive tiles fit the TMEM ring
 };
 bool tc_supported(uint32_t channels, uint32_t taps, double ratio);
 uint32_t tc_kt_extent(uint32_t taps, double ratio);
 size_t tc_gmat_floats_per_tile(uint32_t taps, double ratio);
 uint32_t tc_rows_per_group();
+uint32_t tc_issuers(uint32_t taps, double ratio);
 // 2-D tensor map over equally strided member inputs: box = 16 frames x (128 / channels) members
 bool tc_make_input_tensor_map(CUtensorMap *out, const float *base, uint64_t stride_bytes,
                               uint64_t total_frames, uint32_t n_members, uint32_t channels);

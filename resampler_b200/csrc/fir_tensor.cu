@@ -76,10 +76,10 @@ constexpr uint32_t kChunk = 16;                    // frames per input chunk / r
 constexpr uint32_t kRing = 224;                    // frames in a TMEM ring
 constexpr uint32_t kSlots = kRing / kChunk;        // 14
 constexpr uint32_t kColHi = 0, kColLo = kRing, kColD = 2 * kRing;
-constexpr uint32_t kXStages = 6;                   // TMA landing buffers for input chunks
+constexpr uint32_t kXStages = 4;                   // TMA landing buffers for input chunks
 constexpr uint32_t kXStageBytes = kRows * kChunk * 4;   // 8192 for mono and stereo alike
-constexpr uint32_t kGStages = 2;
-constexpr uint32_t kTcThreads = 11 * 32;
+constexpr uint32_t kGStages = 3;
+constexpr uint32_t kTcThreads = 16 * 32;   // warps 0-3 epilogue, 4-7 + 12-15 splitter, 8 + 11 MMA, 9-10 TMA
 constexpr uint32_t kKtLimit = 192;                 // largest K extent of a tile (12 + 1 chunks)
 constexpr uint32_t kItemSlots = 2;
 
@@ -140,14 +140,14 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
     RoleClock rc;
     rc.start(false);
     if (tid == 0) {
-        for (uint32_t i = 0; i < kXStages; ++i) { mbar_init(&S.xs_full[i], 1); mbar_init(&S.xs_empty[i], kRows); }
+        for (uint32_t i = 0; i < kXStages; ++i) { mbar_init(&S.xs_full[i], 1); mbar_init(&S.xs_empty[i], 2 * kRows); }
         for (uint32_t i = 0; i < kGStages; ++i) mbar_init(&S.g_full[i], 1);
         for (uint32_t i = 0; i < 4; ++i) mbar_init(&S.t_done[i], 1);
-        for (uint32_t i = 0; i < kSlots; ++i) { mbar_init(&S.x_full[i], kRows); mbar_init(&S.x_empty[i], 1); }
+        for (uint32_t i = 0; i < kSlots; ++i) { mbar_init(&S.x_full[i], 2 * kRows); mbar_init(&S.x_empty[i], P.issuers); }
         for (uint32_t i = 0; i < 2; ++i) mbar_init(&S.d_empty[i], kRows);
         for (uint32_t i = 0; i < kItemSlots; ++i) {
             mbar_init(&S.item_full[i], 1);
-            mbar_init(&S.item_empty[i], 2 + 2 * kRows);
+            mbar_init(&S.item_empty[i], 3 + 3 * kRows);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -255,22 +255,28 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
             }
         }
         __syncwarp();
-    } else if (warp == 8) {
-        // ===== MMA issuer.  The whole warp runs the loop (warp-uniform values), one elected lane
-        // issues.  Issuing costs ~25-30 cycles of the warp's time per MMA (a dozen operand moves
-        // into uniform registers), more than the 16 cycles an M=128, N=32 MMA keeps the tensor pipe
-        // busy: this warp is the kernel's critical path.  (Two issuer warps on alternate tiles were
-        // tried: two tiles in flight need 13 of the 14 ring slots, the input prefetch starves.) =====
+    } else if (warp == 8 || warp == 11) {
+        // ===== MMA issuers.  The whole warp runs the loop (warp-uniform values), one elected lane
+        // issues.  Issuing costs ~30 cycles of a warp's time per MMA (a dozen operand moves into
+        // uniform registers per tcgen05.mma, plus waits and commits: ~3400 cycles per tile), about
+        // twice what the tensor pipe needs for the tile.  So two warps issue alternate tiles into
+        // the two accumulators whenever two consecutive tiles' K ranges fit the ring together
+        // (P.issuers == 2); otherwise warp 8 issues every tile.  A ring slot is handed back to
+        // the splitter once BOTH issuers have committed it. =====
+        const uint32_t mine = warp == 8 ? 0u : 1u;
+        const uint32_t step = P.issuers;
         uint32_t q_base = 0;      // ring sequence number of the run's chunk 0
         uint32_t q_waited = 0;    // chunks whose x_full barrier has been consumed
-        uint32_t q_rel = 0;       // chunks handed back to the splitter
+        uint32_t q_rel = 0;       // chunks handed back to the splitter (by this warp)
         uint32_t d_seq = 0;       // tiles of this CTA so far; tile -> accumulator d_seq & 1
-        rc.start(prof && lane == 0);
+        rc.start(prof && lane == 0 && mine == 0);
         for (uint32_t it = 0;; ++it) {
             const Item I = get_item_warp(it);
             if (!I.valid) break;
+            if (mine >= step) continue;           // single-issuer mode: warp 11 only drains the queue
             rc.count(14, I.t1 - I.t0);
-            // a chunk is handed back only after this warp has seen it filled
+            // a chunk is handed back only after this warp has seen it filled (its arrival then
+            // belongs to the slot's current use even if the warp's own tiles never read the chunk)
             auto release_chunk = [&]() {
                 while (q_waited <= q_rel) {
                     mbar_wait(&S.x_full[q_waited % kSlots], (q_waited / kSlots) & 1u);
@@ -279,10 +285,16 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                 tc_commit_elect(&S.x_empty[q_rel % kSlots]);
                 ++q_rel;
             };
-            TcTile m = tct[I.t0];
-            for (uint32_t t = I.t0; t < I.t1; ++t, ++d_seq) {
+            // this warp's first tile of the run: tile parity follows the CTA's tile sequence
+            const uint32_t d_run = d_seq;
+            uint32_t t = I.t0 + (step == 2 ? ((d_seq ^ mine) & 1u) : 0u);
+            d_seq += t - I.t0;
+            TcTile m = {0, 0, 0, 0};
+            if (t < I.t1) m = tct[t];
+            for (; t < I.t1; t += step, d_seq += step) {
+                // the tile whose first frame bounds what this warp still needs: its own next tile
                 TcTile mn = m;
-                if (t + 1 < I.t1) mn = tct[t + 1];
+                if (t + step < I.t1) mn = tct[t + step];
                 const uint32_t j_last = (uint32_t)(m.k0 + (int32_t)m.kt - 1 - I.vb) / kChunk;
                 rc.lap(4);
                 while (q_waited <= q_base + j_last) {
@@ -347,22 +359,29 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                 // Chunks that end at or before the next tile's first frame are free again.  (Handing
                 // them back earlier, right after the front K steps of this pass, was measured
                 // slower: a tcgen05.commit in the middle of the MMA stream stalls the issue.)
-                const bool last = t + 1 == I.t1;
+                const bool last = t + step >= I.t1;     // this warp's last tile of the run
                 while (q_rel < q_base + I.n_chunks &&
                        (last || I.vb + (int32_t)((q_rel - q_base + 1) * kChunk) <= mn.k0))
                     release_chunk();
                 m = mn;
             }
+            // a run this warp had no tile in
+            while (q_rel < q_base + I.n_chunks) release_chunk();
+            d_seq = d_run + (I.t1 - I.t0);
             q_base += I.n_chunks;
         }
         __syncwarp();
     } else if (warp >= 4) {
-        // ===== splitter: shared memory (TMA landing buffer) -> hi / lo rings in TMEM =====
-        const uint32_t row = tid - 128u;                    // TMEM lane
+        // ===== splitter: shared memory (TMA landing buffer) -> hi / lo rings in TMEM.  Two
+        // warpgroups (warps 4-7 and 12-15: the same TMEM lane quadrants); each takes 8 of a
+        // chunk's 16 frames, which halves the time from "ring slot free" to "chunk readable". =====
+        constexpr uint32_t kHalf = kChunk / 2;
+        const uint32_t wg = warp >= 12 ? 1u : 0u;           // which 8 frames of every chunk
+        const uint32_t row = tid & 127u;                    // TMEM lane
         const uint32_t ml = row / CH, c = row % CH;         // member inside the group, channel
         const uint32_t lane_base = ((warp & 3u) * 32u) << 16;
         uint32_t q_seq = 0, xs_seq = 0;
-        rc.start(prof && row == 0);
+        rc.start(prof && row == 0 && wg == 0);
         for (uint32_t it = 0;; ++it) {
             const Item I = get_item(it);
             if (!I.valid) break;
@@ -375,14 +394,23 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                 in = job->in;
             }
             int pend = -1;      // ring slot whose tcgen05.st are still in flight
+            auto publish = [&]() {
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(&S.x_full[pend]);
+                pend = -1;
+            };
             for (uint32_t j = 0; j < I.n_chunks; ++j, ++q_seq) {
                 const uint32_t rs = q_seq % kSlots;
+                const uint32_t par = ((q_seq / kSlots) & 1u) ^ 1u;
                 rc.lap(15);
-                mbar_wait(&S.x_empty[rs], ((q_seq / kSlots) & 1u) ^ 1u);
+                // about to block on a ring slot: first publish the chunk whose stores are pending
+                if (pend >= 0 && !mbar_test(&S.x_empty[rs], par)) publish();
+                mbar_wait(&S.x_empty[rs], par);
                 rc.lap(5);
                 tc_fence_after();
                 const int32_t v = I.vb + (int32_t)(j * kChunk);
-                float x[kChunk];
+                float x[kHalf];
                 if (v >= H) {
                     const uint32_t s = xs_seq % kXStages;
                     mbar_wait(&S.xs_full[s], (xs_seq / kXStages) & 1u);
@@ -392,8 +420,8 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                         // 128-byte rows (16 stereo frames), 128B swizzle: unit u at u ^ (row & 7)
                         const uint32_t rb = base + ml * 128u;
 #pragma unroll
-                        for (uint32_t u = 0; u < 8; ++u) {
-                            const float4 q4 = lds128(rb + ((u ^ (ml & 7u)) << 4));
+                        for (uint32_t u = 0; u < 4; ++u) {
+                            const float4 q4 = lds128(rb + (((u + 4 * wg) ^ (ml & 7u)) << 4));
                             x[2 * u] = c ? q4.y : q4.x;
                             x[2 * u + 1] = c ? q4.w : q4.z;
                         }
@@ -401,18 +429,18 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                         // 64-byte rows (16 mono frames), 64B swizzle: unit u at u ^ ((row >> 1) & 3)
                         const uint32_t rb = base + ml * 64u;
 #pragma unroll
-                        for (uint32_t u = 0; u < 4; ++u) {
-                            const float4 q4 = lds128(rb + ((u ^ ((ml >> 1) & 3u)) << 4));
+                        for (uint32_t u = 0; u < 2; ++u) {
+                            const float4 q4 = lds128(rb + (((u + 2 * wg) ^ ((ml >> 1) & 3u)) << 4));
                             x[4 * u] = q4.x; x[4 * u + 1] = q4.y; x[4 * u + 2] = q4.z; x[4 * u + 3] = q4.w;
                         }
                     }
                     mbar_arrive(&S.xs_empty[s]);
                     ++xs_seq;
                 } else {
-                    // the chunk touches the history (only at the very start of a batch)
+                    // the chunk lies in the history (only at the very start of a batch)
 #pragma unroll
-                    for (uint32_t f = 0; f < kChunk; ++f) {
-                        const int64_t vv = (int64_t)v + f;
+                    for (uint32_t f = 0; f < kHalf; ++f) {
+                        const int64_t vv = (int64_t)v + kHalf * wg + f;
                         float xv = 0.f;
                         if (member_ok && vv >= 0) {
                             if (vv < H) xv = hist[((int64_t)kHistFrames - H + vv) * CH + c];
@@ -421,31 +449,24 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                         x[f] = xv;
                     }
                 }
-                uint32_t hi[kChunk], lo[kChunk];
+                uint32_t hi[kHalf], lo[kHalf];
 #pragma unroll
-                for (uint32_t f = 0; f < kChunk; ++f) {
-                    const float h = to_tf32(x[f]);
-                    hi[f] = __float_as_uint(h);
-                    lo[f] = __float_as_uint(to_tf32(__fsub_rn(x[f], h)));
+                for (uint32_t f = 0; f < kHalf; ++f) {
+                    const float hv = to_tf32(x[f]);
+                    hi[f] = __float_as_uint(hv);
+                    lo[f] = __float_as_uint(to_tf32(__fsub_rn(x[f], hv)));
                 }
                 // the previous chunk's stores had this chunk's loads and arithmetic to complete
                 rc.lap(7);
-                if (pend >= 0) {
-                    tmem_wait_st();
-                    tc_fence_before();
-                    mbar_arrive(&S.x_full[pend]);
-                }
+                if (pend >= 0) publish();
                 rc.lap(11);
-                tmem_st16(tmem + lane_base + kColHi + rs * kChunk, hi);
-                tmem_st16(tmem + lane_base + kColLo + rs * kChunk, lo);
+                const uint32_t colw = rs * kChunk + kHalf * wg;
+                tmem_st8(tmem + lane_base + kColHi + colw, hi);
+                tmem_st8(tmem + lane_base + kColLo + colw, lo);
                 pend = (int)rs;
                 rc.lap(12);
             }
-            if (pend >= 0) {
-                tmem_wait_st();
-                tc_fence_before();
-                mbar_arrive(&S.x_full[pend]);
-            }
+            if (pend >= 0) publish();
         }
     } else {
         // ===== epilogue: accumulator (TMEM) -> shared-memory staging -> global =====
@@ -680,6 +701,14 @@ void launch_conv_tc(const TcParams &p, const CUtensorMap &tmap, int sm_count, cu
 }
 
 uint32_t tc_rows_per_group() { return kRows; }
+
+// Two issuers keep two consecutive tiles in flight: their K ranges (the second starts up to
+// floor(32*ratio)+1 frames later), the 8-frame alignment slack and one chunk of granularity must
+// fit the ring together.
+uint32_t tc_issuers(uint32_t taps, double ratio) {
+    const uint32_t adv = (uint32_t)(32.0 * ratio) + 1u;
+    return tc_kt_max(taps, ratio) + 8u + adv + (kChunk - 1u) <= kRing ? 2u : 1u;
+}
 
 void tc_phase_profile(int enable, unsigned long long *out16) {
     if (out16) cudaMemcpyFromSymbol(out16, g_tc_cycles, sizeof(unsigned long long) * 24);
