@@ -595,26 +595,20 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
             RSB_CUDA(cudaMemcpyAsync(W.h_calls_back.p, W.d_calls.p,
                                      sizeof(rsb::CallCounts) * call_total, cudaMemcpyDeviceToHost, sp));
     }
-    // Tile records, per-frame plan entries and the banded filter tiles.  Tensor path: on the plan
-    // stream, so they run underneath the previous submit's convolution (these kernels use no
-    // shared memory and fit next to the persistent convolution CTAs).  FFMA2 / exact path: on
-    // the main stream in front of the convolution (its persistent CTAs leave no room).
-    cudaStream_t st_tiles = use_tc ? sp : s;
-    if (!use_tc) {
-        RSB_CUDA(cudaEventRecord(W.ev_plan, sp));
-        RSB_CUDA(cudaStreamWaitEvent(s, W.ev_plan, 0));
-    }
+    RSB_CUDA(cudaEventRecord(W.ev_plan, sp));
+    RSB_CUDA(cudaStreamWaitEvent(s, W.ev_plan, 0));
+    // Tile records, per-frame plan entries and the banded filter tiles: wide, short kernels on
+    // the main stream in front of the convolution.  (Running them on the plan stream underneath
+    // the previous submit's convolution was measured: they take 1.1 ms alone but slow the
+    // persistent convolution kernel by 1.5 ms.)
     rsb::launch_tiles(W.d_units.as<UnitDev>(), n_units, W.d_segs.as<rsb::PlanSeg>(),
                       W.d_tiles.as<rsb::TileRec>(), W.d_entries.as<rsb::PlanEntry>(),
                       (uint32_t)max_tiles_unit, h->taps, h->d_coeffs,
-                      use_fast && !use_tc ? W.d_gtiles.as<float>() : nullptr, gs, st_tiles);
-    if (use_tc) {
+                      use_fast && !use_tc ? W.d_gtiles.as<float>() : nullptr, gs, s);
+    if (use_tc)
         rsb::launch_tc_gmat(W.d_units.as<UnitDev>(), W.d_tiles.as<rsb::TileRec>(),
                             W.d_entries.as<rsb::PlanEntry>(), h->d_coeffs, W.d_gtiles.as<float>(),
-                            W.d_tct.as<rsb::TcTile>(), h->taps, h->ratio, (uint32_t)tile_total, sp);
-        RSB_CUDA(cudaEventRecord(W.ev_plan, sp));
-        RSB_CUDA(cudaStreamWaitEvent(s, W.ev_plan, 0));
-    }
+                            W.d_tct.as<rsb::TcTile>(), h->taps, h->ratio, (uint32_t)tile_total, s);
     rsb::ConvParams P;
     P.units = W.d_units.as<UnitDev>();
     P.jobs = W.d_jobs.as<JobDev>();
@@ -657,7 +651,7 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
         T.run_tiles = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 32), 512);
         T.kt_max = rsb::tc_kt_extent(h->taps, h->ratio);
         T.issuers = rsb::tc_issuers(h->taps, h->ratio);
-        rsb::launch_conv_tc(T, tc_tmap, h->sm_count, s);
+        rsb::launch_conv_tc(T, tc_tmap, h->sm_count, !host_plan, s);
     } else if (use_fast) {
         rsb::launch_conv_fast(P, P.tmap_valid ? &tmap : nullptr, h->ratio, max_items, h->sm_count, s);
     } else {

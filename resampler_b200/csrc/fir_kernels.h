@@ -107,7 +107,8 @@ bool tc_make_input_tensor_map(CUtensorMap *out, const float *base, uint64_t stri
 void launch_tc_gmat(const UnitDev *units, const TileRec *tiles, const PlanEntry *entries,
                     const float *coeffs, float *gmat, TcTile *tct, uint32_t taps, double ratio,
                     uint32_t tile_cap, cudaStream_t stream);
-void launch_conv_tc(const TcParams &p, const CUtensorMap &tmap, int sm_count, cudaStream_t stream);
+void launch_conv_tc(const TcParams &p, const CUtensorMap &tmap, int sm_count, bool leave_sm_free,
+                    cudaStream_t stream);
 // debug: returns and clears the tensor kernel's per-role cycle counters, sets the enable flag
 void tc_phase_profile(int enable, unsigned long long *out16);
 

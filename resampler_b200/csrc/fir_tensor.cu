@@ -687,11 +687,12 @@ void launch_tc_gmat(const UnitDev *units, const TileRec *tiles, const PlanEntry 
     }
 }
 
-void launch_conv_tc(const TcParams &p, const CUtensorMap &tmap, int sm_count, cudaStream_t stream) {
+void launch_conv_tc(const TcParams &p, const CUtensorMap &tmap, int sm_count, bool leave_sm_free,
+                    cudaStream_t stream) {
     const size_t smem = (size_t)kXStages * kXStageBytes + (size_t)kGStages * 2 * p.kt_max * 128u +
                         (size_t)2 * (kRows / p.channels) * tc_stage_pitch(p.channels) * sizeof(float);
-    // one SM is left free for the (serial) plan kernel of the next submit, as in fir_fast.cu
-    const uint32_t grid = (uint32_t)(sm_count > 8 ? sm_count - 1 : sm_count);
+    // one SM is left free when the next submit's (serial) plan kernel may need somewhere to run
+    const uint32_t grid = (uint32_t)(leave_sm_free && sm_count > 8 ? sm_count - 1 : sm_count);
     auto launch = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         kern<<<grid, kTcThreads, smem, stream>>>(p, tmap);
