@@ -651,6 +651,7 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
         T.run_tiles = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 32), 512);
         T.kt_max = rsb::tc_kt_extent(h->taps, h->ratio);
         T.issuers = rsb::tc_issuers(h->taps, h->ratio);
+        if (getenv("RSB_TC_ISSUERS")) T.issuers = atoi(getenv("RSB_TC_ISSUERS")) == 1 ? 1u : T.issuers;
         rsb::launch_conv_tc(T, tc_tmap, h->sm_count, !host_plan, s);
     } else if (use_fast) {
         rsb::launch_conv_fast(P, P.tmap_valid ? &tmap : nullptr, h->ratio, max_items, h->sm_count, s);

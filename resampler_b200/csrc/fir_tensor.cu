@@ -297,17 +297,23 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                 if (t + step < I.t1) mn = tct[t + step];
                 const uint32_t j_last = (uint32_t)(m.k0 + (int32_t)m.kt - 1 - I.vb) / kChunk;
                 rc.lap(4);
+                // Order matters with two issuers.  The accumulator wait comes FIRST: it passes only
+                // after the epilogue has drained tile d_seq - 2, hence after tile d_seq - 3 (the
+                // OTHER issuer's, and the previous user of this tile's G stage) has completed.  A
+                // parity wait on g_full before that could be looking at the stage's previous phase
+                // still in flight and pass early (seen as an mbarrier arrival underflow = illegal
+                // instruction in the G producer, with short tiles).
+                const uint32_t b = d_seq & 1u;
+                mbar_wait(&S.d_empty[b], ((d_seq >> 1) & 1u) ^ 1u);
+                rc.lap(2);
+                const uint32_t gs = d_seq % kGStages;      // G stages follow the tile sequence
+                mbar_wait(&S.g_full[gs], (d_seq / kGStages) & 1u);
+                rc.lap(1);
                 while (q_waited <= q_base + j_last) {
                     mbar_wait(&S.x_full[q_waited % kSlots], (q_waited / kSlots) & 1u);
                     ++q_waited;
                 }
                 rc.lap(0);
-                const uint32_t gs = d_seq % kGStages;      // G stages follow the tile sequence
-                mbar_wait(&S.g_full[gs], (d_seq / kGStages) & 1u);
-                rc.lap(1);
-                const uint32_t b = d_seq & 1u;
-                mbar_wait(&S.d_empty[b], ((d_seq >> 1) & 1u) ^ 1u);
-                rc.lap(2);
                 tc_fence_after();
 
                 const uint32_t d_tmem = tmem + kColD + b * kN;
@@ -393,27 +399,21 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                 hist = job->hist;
                 in = job->in;
             }
-            int pend = -1;      // ring slot whose tcgen05.st are still in flight
-            auto publish = [&]() {
-                tmem_wait_st();
-                tc_fence_before();
-                mbar_arrive(&S.x_full[pend]);
-                pend = -1;
-            };
             for (uint32_t j = 0; j < I.n_chunks; ++j, ++q_seq) {
                 const uint32_t rs = q_seq % kSlots;
                 const uint32_t par = ((q_seq / kSlots) & 1u) ^ 1u;
                 rc.lap(15);
-                // about to block on a ring slot: first publish the chunk whose stores are pending
-                if (pend >= 0 && !mbar_test(&S.x_empty[rs], par)) publish();
                 mbar_wait(&S.x_empty[rs], par);
+                __syncwarp();
                 rc.lap(5);
                 tc_fence_after();
                 const int32_t v = I.vb + (int32_t)(j * kChunk);
                 float x[kHalf];
+                int fast_slot = -1;
                 if (v >= H) {
                     const uint32_t s = xs_seq % kXStages;
                     mbar_wait(&S.xs_full[s], (xs_seq / kXStages) & 1u);
+                    __syncwarp();
                     rc.lap(6);
                     const uint32_t base = smem_u32(xst + s * kXStageBytes);
                     if (CH == 2) {
@@ -434,7 +434,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                             x[4 * u] = q4.x; x[4 * u + 1] = q4.y; x[4 * u + 2] = q4.z; x[4 * u + 3] = q4.w;
                         }
                     }
-                    mbar_arrive(&S.xs_empty[s]);
+                    fast_slot = (int)s;
                     ++xs_seq;
                 } else {
                     // the chunk lies in the history (only at the very start of a batch)
@@ -456,17 +456,26 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                     hi[f] = __float_as_uint(hv);
                     lo[f] = __float_as_uint(to_tf32(__fsub_rn(x[f], hv)));
                 }
-                // the previous chunk's stores had this chunk's loads and arithmetic to complete
                 rc.lap(7);
-                if (pend >= 0) publish();
-                rc.lap(11);
                 const uint32_t colw = rs * kChunk + kHalf * wg;
                 tmem_st8(tmem + lane_base + kColHi + colw, hi);
                 tmem_st8(tmem + lane_base + kColLo + colw, lo);
-                pend = (int)rs;
+                // The landing buffer is handed back only now, after the loaded values have been
+                // consumed.  Arriving right behind the ld.shared instructions (the SASS was LDS.128,
+                // LDS.128, SYNCS.ARRIVE back to back) let the producer's next TMA copy overwrite
+                // the buffer before the loads had read it: intermittent single wrong samples in
+                // the first rows of a group.
+                if (fast_slot >= 0) mbar_arrive(&S.xs_empty[fast_slot]);
                 rc.lap(12);
+                // The stores must have completed before hi[] / lo[] are overwritten by the next
+                // chunk: tcgen05.st reads its source registers asynchronously (publishing one
+                // chunk late, after the next chunk's arithmetic, left single stale samples in a
+                // few lanes, intermittently).
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(&S.x_full[rs]);
+                rc.lap(11);
             }
-            if (pend >= 0) publish();
         }
     } else {
         // ===== epilogue: accumulator (TMEM) -> shared-memory staging -> global =====
@@ -511,6 +520,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                 const uint32_t b = d_seq & 1u;
                 rc.lap(10);
                 mbar_wait(&S.t_done[d_seq & 3u], (d_seq >> 2) & 1u);
+                __syncwarp();     // lanes leave the polling loop at different times
                 rc.lap(8);
                 tc_fence_after();
                 uint32_t acc[kN];
@@ -525,6 +535,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                 float *st = sb + ml * pitch + c;
 #pragma unroll
                 for (uint32_t o = 0; o < kN; ++o) st[o * CH] = __uint_as_float(acc[o]);
+                __syncwarp();     // bar.sync counts whole warps: every lane's staging writes first
                 named_bar_sync(1, kRows);
                 rc.lap(9);
                 if (p_fr < m.n_out) {

@@ -340,6 +340,29 @@ def test_tensor_kernel_falls_back_for_ragged_batches_and_wide_ratios():
         FirBatch(4, 1, 192000, 48000, Latency.Sample64, Attenuation.Db90, kernel=Kernel.TENSOR)
 
 
+def test_tensor_kernel_short_tiles_many_items():
+    """Regression: mono 16 -> 48 kHz with 32 taps gives very short tiles (7 K steps), so the two
+    MMA issuers, the G producer and the epilogue interleave tightly, and every CTA works through
+    several items.  An mbarrier parity wait placed before its gating wait used to pass early here
+    (illegal instruction in ~30 % of the runs).  TENSOR against EXACT on every stream, 3 times."""
+    n, ch, frames = 512, 1, 64000
+    rng = np.random.default_rng(11)
+    xs = [noise(rng, frames) for _ in range(n)]
+    ref = FirBatch(n, ch, 16000, 48000, Latency.Sample16, Attenuation.Db90, kernel=Kernel.EXACT)
+    want = [np.array(o, copy=True) for o in ref.process(xs, 160, 0)["out"]]
+    ref.close()
+    o0 = oracle_stream(ch, 16000, 48000, 1, 1, xs[0], 160, 0)["out"]
+    assert np.array_equal(bits(want[0]), bits(o0))
+    for _ in range(3):
+        b = FirBatch(n, ch, 16000, 48000, Latency.Sample16, Attenuation.Db90, kernel=Kernel.TENSOR)
+        got = b.process(xs, 160, 0)["out"]
+        assert b.last_kernel() == Kernel.TENSOR
+        for s in range(n):
+            assert len(got[s]) == len(want[s])
+            assert np.max(np.abs(got[s].astype(np.float64) - want[s])) <= TOL_FAST, s
+        b.close()
+
+
 def check_kernel_within_tolerance(kernel, ch, in_hz, out_hz, lat, call_frames, cap_frames,
                                   n_streams):
     rng = np.random.default_rng(in_hz + call_frames + n_streams)
