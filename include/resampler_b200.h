@@ -66,7 +66,7 @@ enum rsb_memspace { RSB_MEM_DEVICE = 0, /* pointers are device pointers on the h
  *   TENSOR: the same product on the tcgen05 tensor cores with every operand split into two
  *          TF32 parts (3xTF32, fp32 accumulation in tensor memory); samples within 1e-6
  *          absolute of EXACT.  Serves batches whose streams share one plan and whose inputs
- *          lie at one constant stride (mono / stereo); other batches fall back to FAST / EXACT.
+ *          lie at one constant stride (1, 2, 4 or 8 channels); other batches fall back to FAST / EXACT.
  *   AUTO : TENSOR where it applies (one plan, constant stride, >= 64 stream-channels), else
  *          FAST where it applies (stream count, ratio), else EXACT. */
 enum rsb_kernel { RSB_KERNEL_AUTO = 0, RSB_KERNEL_EXACT = 1, RSB_KERNEL_FAST = 2,

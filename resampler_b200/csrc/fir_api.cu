@@ -464,7 +464,7 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     // member inputs at one constant stride (and one plan unit): the batch's input is a 2-D tensor
     uint64_t in_stride = 0;
     bool in_uniform = false;
-    if (n_units == 1 && (ch == 1 || ch == 2) && unit_keys[0].total_frames > 0) {
+    if (n_units == 1 && (ch == 1 || ch == 2 || ch == 4 || ch == 8) && unit_keys[0].total_frames > 0) {
         const uintptr_t base = reinterpret_cast<uintptr_t>(hj[0].in);
         in_stride = n > 1 ? (uint64_t)(reinterpret_cast<uintptr_t>(hj[1].in) - base) : 0;
         in_uniform = n == 1 || reinterpret_cast<uintptr_t>(hj[1].in) > base;

@@ -92,7 +92,9 @@ __host__ __device__ inline uint32_t tc_kt_max(uint32_t taps, double ratio) {
     const uint32_t span = (uint32_t)(31.0 * ratio) + 1u;
     return (7u + span + taps + 7u) & ~7u;
 }
-__host__ __device__ inline uint32_t tc_stage_pitch(uint32_t ch) { return ch == 2 ? 68u : 36u; }
+// floats per member in the epilogue's staging area: 32 frames x channels, + 4 (keeps 16-byte
+// alignment, spreads the members over the banks)
+__host__ __device__ inline uint32_t tc_stage_pitch(uint32_t ch) { return 32u * ch + 4u; }
 
 struct Item {
     uint32_t t0, t1;       // tiles [t0, t1) of the unit
@@ -125,7 +127,7 @@ struct TcSmem {
 template <int CH>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUtensorMap tmap) {
-    static_assert(CH == 1 || CH == 2, "tensor kernel: mono or stereo");
+    static_assert(CH == 1 || CH == 2 || CH == 4 || CH == 8, "tensor kernel: 1, 2, 4 or 8 channels");
     constexpr uint32_t kMpg = kRows / CH;               // members per group
     extern __shared__ __align__(1024) uint8_t smem_tc[];
     __shared__ TcSmem S;
@@ -221,7 +223,10 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                     const uint32_t s = xs_seq % kXStages;
                     mbar_wait(&S.xs_empty[s], ((xs_seq / kXStages) & 1u) ^ 1u);
                     mbar_arrive_expect_tx(&S.xs_full[s], kXStageBytes);
-                    tensor_g2s_2d(xst + s * kXStageBytes, &tmap, v - H, m0, &S.xs_full[s]);
+                    // inner coordinate in tensor-map elements: frames (mono f32, stereo 8-byte
+                    // frames) or floats (4 / 8 channels)
+                    tensor_g2s_2d(xst + s * kXStageBytes, &tmap, (v - H) * (CH >= 4 ? CH : 1), m0,
+                                  &S.xs_full[s]);
                     ++xs_seq;
                 }
             }
@@ -425,7 +430,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                             x[2 * u] = c ? q4.y : q4.x;
                             x[2 * u + 1] = c ? q4.w : q4.z;
                         }
-                    } else {
+                    } else if (CH == 1) {
                         // 64-byte rows (16 mono frames), 64B swizzle: unit u at u ^ ((row >> 1) & 3)
                         const uint32_t rb = base + ml * 64u;
 #pragma unroll
@@ -433,6 +438,14 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                             const float4 q4 = lds128(rb + (((u + 2 * wg) ^ ((ml >> 1) & 3u)) << 4));
                             x[4 * u] = q4.x; x[4 * u + 1] = q4.y; x[4 * u + 2] = q4.z; x[4 * u + 3] = q4.w;
                         }
+                    } else {
+                        // 4 / 8 channels: rows of 16 frames x CH floats, no swizzle; one 4-byte load
+                        // per frame (the 128/CH members of a warp's lanes collide on the banks
+                        // CH-fold at most 4 ways: a few dozen wavefronts per chunk, negligible)
+                        const float *rowp = reinterpret_cast<const float *>(xst + s * kXStageBytes) +
+                                            ml * (kChunk * CH) + (kHalf * wg) * CH + c;
+#pragma unroll
+                        for (uint32_t f = 0; f < kHalf; ++f) x[f] = rowp[f * CH];
                     }
                     fast_slot = (int)s;
                     ++xs_seq;
@@ -483,11 +496,12 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
         const uint32_t ml = row / CH, c = row % CH;
         const uint32_t lane_base = ((warp & 3u) * 32u) << 16;
         const uint32_t pitch = tc_stage_pitch(CH);
-        constexpr uint32_t kFpp = 4 / CH;                    // frames per 16-byte piece
-        constexpr uint32_t kPieces = kN / kFpp;              // pieces per member and tile
+        // A member's tile output is a run of 32 * CH floats, cut into 16-byte pieces.
+        constexpr uint32_t kPieces = kN * CH / 4;            // pieces per member and tile
         constexpr uint32_t kIter = kMpg * kPieces / kRows;   // pieces per thread and tile (8)
         constexpr uint32_t kMemStep = kRows / kPieces;       // member stride between a thread's pieces
-        const uint32_t p_fr = (tid % kPieces) * kFpp;        // first frame of this thread's pieces
+        static_assert(kIter == 8 && kMemStep >= 1, "epilogue piece mapping");
+        const uint32_t p_off = (tid % kPieces) * 4u;         // first float of this thread's pieces
         const uint32_t mem0 = tid / kPieces;
         uint32_t d_seq = 0;
         rc.start(prof && tid == 0);
@@ -538,24 +552,23 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                 __syncwarp();     // bar.sync counts whole warps: every lane's staging writes first
                 named_bar_sync(1, kRows);
                 rc.lap(9);
-                if (p_fr < m.n_out) {
-                    const uint32_t o = m.o_start + p_fr;
-                    const bool rows_full = p_fr + kFpp <= m.n_out;
-                    const float *src = sb + mem0 * pitch + p_fr * CH;
+                const uint32_t valid = m.n_out * CH;               // floats of the run that exist
+                if (p_off < valid) {
+                    const uint64_t g0 = (uint64_t)m.o_start * CH + p_off;   // float index in the stream
+                    const bool piece_full = p_off + 4u <= valid;
+                    const float *src = sb + mem0 * pitch + p_off;
 #pragma unroll
                     for (uint32_t i = 0; i < kIter; ++i) {
                         if (outp[i] == nullptr) continue;
                         const float4 q4 = *reinterpret_cast<const float4 *>(src + i * (kMemStep * pitch));
-                        if (rows_full && ((vec_ok >> i) & 1u) && (uint64_t)o + kFpp <= capf[i]) {
-                            *reinterpret_cast<float4 *>(outp[i] + (size_t)o * CH) = q4;
+                        const uint64_t cap_floats = (uint64_t)capf[i] * CH;
+                        if (piece_full && ((vec_ok >> i) & 1u) && g0 + 4u <= cap_floats) {
+                            *reinterpret_cast<float4 *>(outp[i] + g0) = q4;
                         } else {
                             const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
-                            for (uint32_t f = 0; f < kFpp; ++f)
-                                if (p_fr + f < m.n_out && (uint64_t)o + f < capf[i])
-#pragma unroll
-                                    for (uint32_t cc = 0; cc < (uint32_t)CH; ++cc)
-                                        outp[i][((size_t)o + f) * CH + cc] = qv[f * CH + cc];
+                            for (uint32_t q = 0; q < 4; ++q)
+                                if (p_off + q < valid && g0 + q < cap_floats) outp[i][g0 + q] = qv[q];
                         }
                     }
                 }
@@ -638,7 +651,7 @@ tc_gmat_kernel(const UnitDev *units, const TileRec *tiles, const PlanEntry *entr
 }  // namespace
 
 bool tc_supported(uint32_t channels, uint32_t taps, double ratio) {
-    if (channels != 1 && channels != 2) return false;
+    if (channels != 1 && channels != 2 && channels != 4 && channels != 8) return false;
     if (taps != 16 && taps != 32 && taps != 64 && taps != 128) return false;
     return tc_kt_max(taps, ratio) <= kKtLimit;
 }
@@ -666,19 +679,24 @@ bool tc_make_input_tensor_map(CUtensorMap *out, const float *base, uint64_t stri
         }
         encode = (EncodeTiledFn)fn;
     }
-    if (channels != 1 && channels != 2) return false;
-    if (total_frames == 0 || total_frames >= (1ull << 31)) return false;
+    if (channels != 1 && channels != 2 && channels != 4 && channels != 8) return false;
+    if (total_frames == 0 || total_frames * channels >= (1ull << 31)) return false;
     if ((reinterpret_cast<uintptr_t>(base) & 15u) || (stride_bytes & 15u) || stride_bytes == 0)
         return false;
     if (stride_bytes < total_frames * channels * 4ull) return false;
-    // element = one frame (f32 mono, 8-byte stereo); inner dimension = frames, rows = members
-    cuuint64_t dims[2] = {total_frames, n_members};
+    // mono / stereo: element = one frame (f32, or an 8-byte stereo frame), 64B / 128B swizzle (the
+    // splitter reads 16-byte units, one row per lane).  4 / 8 channels: element = one float, inner
+    // dimension = frames x channels, no swizzle (the splitter reads single floats).
+    const bool wide = channels >= 4;
+    cuuint64_t dims[2] = {wide ? total_frames * channels : total_frames, n_members};
     cuuint64_t strides[1] = {stride_bytes};
-    cuuint32_t box[2] = {kChunk, (cuuint32_t)(kRows / channels)};
+    cuuint32_t box[2] = {wide ? kChunk * channels : kChunk, (cuuint32_t)(kRows / channels)};
     cuuint32_t estr[2] = {1, 1};
     const CUtensorMapDataType dt =
-        channels == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
-    const CUtensorMapSwizzle sw = channels == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+        channels == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const CUtensorMapSwizzle sw = channels == 1   ? CU_TENSOR_MAP_SWIZZLE_64B
+                                  : channels == 2 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                  : CU_TENSOR_MAP_SWIZZLE_NONE;
     const CUresult r = encode(out, dt, 2, const_cast<float *>(base), dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -708,8 +726,12 @@ void launch_conv_tc(const TcParams &p, const CUtensorMap &tmap, int sm_count, bo
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         kern<<<grid, kTcThreads, smem, stream>>>(p, tmap);
     };
-    if (p.channels == 1) launch(conv_tc_kernel<1>);
-    else launch(conv_tc_kernel<2>);
+    switch (p.channels) {
+        case 1: launch(conv_tc_kernel<1>); break;
+        case 2: launch(conv_tc_kernel<2>); break;
+        case 4: launch(conv_tc_kernel<4>); break;
+        default: launch(conv_tc_kernel<8>); break;
+    }
 }
 
 uint32_t tc_rows_per_group() { return kRows; }

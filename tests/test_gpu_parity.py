@@ -316,6 +316,8 @@ def test_fast_kernel_within_tolerance(ch, in_hz, out_hz, lat, call_frames, cap_f
     (2, 44100, 48000, 3, 512, 100, 4),    # capacity-limited calls
     (2, 22050, 48000, 3, 4096, 0, 3),     # maximum call size
     (1, 96000, 48000, 2, 512, 0, 40),     # ratio 2, 64 taps
+    (8, 96000, 48000, 2, 512, 0, 17),     # config 4: 8 channels, 64 taps; 16 + 1 members
+    (4, 44100, 48000, 3, 512, 0, 40),     # 4 channels, 128 taps
 ])
 def test_tensor_kernel_within_tolerance(ch, in_hz, out_hz, lat, call_frames, cap_frames, n_streams):
     check_kernel_within_tolerance(Kernel.TENSOR, ch, in_hz, out_hz, lat, call_frames, cap_frames,
