@@ -646,9 +646,11 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
         const uint32_t mpg = rsb::tc_rows_per_group() / ch;
         T.groups = (n + mpg - 1) / mpg;
         // a run of consecutive tiles is one work item: long enough to amortise filling the input
-        // ring (~6 tiles), short enough that every CTA gets several items
+        // ring (~6 tiles), short enough that every CTA gets several items and the tail is short
+        // (measured on the headline batch: 192 tiles 15.8 ms, 512 tiles 16.0 ms, 1024 tiles 16.1 ms)
         const uint64_t want = (tile_total * T.groups) / ((uint64_t)h->sm_count * 8u) + 1;
-        T.run_tiles = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 32), 512);
+        T.run_tiles = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 32), 192);
+        if (getenv("RSB_TC_RUN_TILES")) T.run_tiles = (uint32_t)atoi(getenv("RSB_TC_RUN_TILES"));
         T.kt_max = rsb::tc_kt_extent(h->taps, h->ratio);
         T.issuers = rsb::tc_issuers(h->taps, h->ratio);
         if (getenv("RSB_TC_ISSUERS")) T.issuers = atoi(getenv("RSB_TC_ISSUERS")) == 1 ? 1u : T.issuers;
