@@ -61,6 +61,20 @@ __device__ __forceinline__ void mma4g(uint32_t d, uint32_t a0, uint32_t a1, uint
                  "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%4], d3, %10, t;\n\t}"
                  ::"r"(d), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(b2), "r"(b3), "r"(bhi), "r"(idesc), "r"(acc) : "memory");
 }
+// 4 MMAs in one block, accumulators alternate d0, d1, d0, d1
+__device__ __forceinline__ void mma4alt(uint32_t d0, uint32_t d1, uint32_t a, uint32_t blo, uint32_t bhi, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p, e;\n\t.reg .b64 b0, b1, b2, b3;\n\t.reg .b32 t1, t2, t3, a1, a2, a3;\n\t"
+                 "elect.sync _|e, 0xffffffff;\n\t"
+                 "add.u32 t1, %3, 64;\n\tadd.u32 t2, %3, 128;\n\tadd.u32 t3, %3, 192;\n\t"
+                 "add.u32 a1, %2, 8;\n\tadd.u32 a2, %2, 16;\n\tadd.u32 a3, %2, 24;\n\t"
+                 "mov.b64 b0, {%3, %4};\n\tmov.b64 b1, {t1, %4};\n\tmov.b64 b2, {t2, %4};\n\tmov.b64 b3, {t3, %4};\n\t"
+                 "setp.eq.b32 p, 0, 0;\n\t"
+                 "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%2], b0, %5, p;\n\t"
+                 "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [a1], b1, %5, p;\n\t"
+                 "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [a2], b2, %5, p;\n\t"
+                 "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [a3], b3, %5, p;\n\t}"
+                 ::"r"(d0), "r"(d1), "r"(a), "r"(blo), "r"(bhi), "r"(idesc) : "memory");
+}
 __device__ __forceinline__ void commit(uint64_t *bar) {
     asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
                  "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
@@ -111,6 +125,18 @@ __global__ void k(int variant, int n_mma, int reps, long long *out, uint32_t col
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
+    if (variant == 5 && warp == 1) {
+        const uint32_t blo0 = (((smem_u32(smem) + 32768u) & 0x3ffffu) >> 4) | ((512u >> 4) << 16);
+        const uint32_t bhi = (128u >> 4) | (1u << 14);
+        for (int r = 0; r < reps; ++r) {
+            uint32_t col = 224, blo = blo0;
+            for (int i = 0; i < n_mma; i += 4) {
+                mma4(tmem + 480, tmem + col, blo, bhi, IDESC(32));
+                blo += 256; col += 32; if (col >= 416) col -= 192;
+                if ((i & 31) == 28) blo = blo0;
+            }
+        }
+    }
     if (warp == 0) {
         const uint32_t blo0 = ((smem_u32(smem) & 0x3ffffu) >> 4) | ((512u >> 4) << 16);
         const uint32_t bhi = (128u >> 4) | (1u << 14);
@@ -121,7 +147,7 @@ __global__ void k(int variant, int n_mma, int reps, long long *out, uint32_t col
         for (int r = 0; r < reps; ++r) {
             const long long t0 = clock64();
             uint32_t col = col_arg, blo = blo0;
-            if (v == 0) {
+            if (v == 0 || false) {
                 for (int i = 0; i < n_mma; ++i) {
                     mma1(tmem + 448, tmem + col, blo, bhi, idesc, 1u);
                     blo += 64; col += 8; if (col >= 224) col -= 224;
@@ -129,9 +155,15 @@ __global__ void k(int variant, int n_mma, int reps, long long *out, uint32_t col
                 }
             } else if (v == 1) {
                 mma_loop(tmem + 448, tmem + col, blo, bhi, idesc, (uint32_t)n_mma);
-            } else if (v == 2) {
+            } else if (v == 2 || v == 5) {
                 for (int i = 0; i < n_mma; i += 4) {
                     mma4(tmem + 448, tmem + col, blo, bhi, idesc);
+                    blo += 256; col += 32; if (col >= 192) col -= 192;
+                    if ((i & 31) == 28) blo = blo0;
+                }
+            } else if (v == 4) {
+                for (int i = 0; i < n_mma; i += 4) {
+                    mma4alt(tmem + 448, tmem + 480, tmem + col, blo, bhi, idesc);
                     blo += 256; col += 32; if (col >= 192) col -= 192;
                     if ((i & 31) == 28) blo = blo0;
                 }
@@ -167,13 +199,13 @@ int main(int argc, char **argv) {
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
     const int n_mma = 64, reps = 200;
     const int fill = argc > 2 ? atoi(argv[2]) : 0;
-    for (int variant : {2, 3, 12}) {
+    for (int variant : {2, 4, 5}) {
         k<<<1, 128, 65536>>>(variant, n_mma, reps, d, (uint32_t)(argc > 1 ? atoi(argv[1]) : 0), fill);
         cudaError_t e = cudaDeviceSynchronize();
         long long h[2] = {0, 0};
         cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
         printf("fill %d variant %2d (N=%d, %s): err=%s issue %.1f cyc/MMA, issue+drain %.1f cyc/MMA\n", fill, variant, variant >= 20 ? 16 : variant >= 10 ? 64 : 32,
-               variant % 10 == 0 ? "one asm per MMA" : variant % 10 == 1 ? "PTX loop" : variant % 10 == 2 ? "4 per asm" : "4 per asm, general", cudaGetErrorString(e),
+               variant % 10 == 4 ? "4 per asm, accumulators alternate" : variant % 10 == 5 ? "4 per asm, a second warp issues into another accumulator" : variant % 10 == 2 ? "4 per asm" : "other", cudaGetErrorString(e),
                (double)h[0] / (n_mma * reps), (double)h[1] / (n_mma * reps));
         if (e != cudaSuccess) return 1;
     }
