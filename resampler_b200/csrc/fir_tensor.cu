@@ -408,10 +408,10 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                 const uint32_t rs = q_seq % kSlots;
                 const uint32_t par = ((q_seq / kSlots) & 1u) ^ 1u;
                 rc.lap(15);
-                mbar_wait(&S.x_empty[rs], par);
-                __syncwarp();
-                rc.lap(5);
-                tc_fence_after();
+                // Load and split BEFORE waiting for the ring slot: the slot becomes free only when
+                // the tile(s) still reading it have completed, and from then on the MMA issuer is
+                // waiting for this chunk; with the values already split in registers only the
+                // TMEM stores remain on that critical path.
                 const int32_t v = I.vb + (int32_t)(j * kChunk);
                 float x[kHalf];
                 int fast_slot = -1;
@@ -470,15 +470,24 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                     lo[f] = __float_as_uint(to_tf32(__fsub_rn(x[f], hv)));
                 }
                 rc.lap(7);
+                // The landing buffer is handed back only after the loaded values have been consumed:
+                // the empty asm below takes every split value as an input, so the loads and the
+                // arithmetic are complete before the arrive.  (Arriving right behind the ld.shared
+                // instructions -- the SASS was LDS.128, LDS.128, SYNCS.ARRIVE back to back -- let
+                // the producer's next TMA copy overwrite the buffer before the loads had read it:
+                // intermittent single wrong samples in the first rows of a group.)
+                asm volatile("" ::"r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]),
+                             "r"(hi[6]), "r"(hi[7]), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]),
+                             "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7])
+                             : "memory");
+                if (fast_slot >= 0) mbar_arrive(&S.xs_empty[fast_slot]);
+                mbar_wait(&S.x_empty[rs], par);
+                __syncwarp();
+                rc.lap(5);
+                tc_fence_after();
                 const uint32_t colw = rs * kChunk + kHalf * wg;
                 tmem_st8(tmem + lane_base + kColHi + colw, hi);
                 tmem_st8(tmem + lane_base + kColLo + colw, lo);
-                // The landing buffer is handed back only now, after the loaded values have been
-                // consumed.  Arriving right behind the ld.shared instructions (the SASS was LDS.128,
-                // LDS.128, SYNCS.ARRIVE back to back) let the producer's next TMA copy overwrite
-                // the buffer before the loads had read it: intermittent single wrong samples in
-                // the first rows of a group.
-                if (fast_slot >= 0) mbar_arrive(&S.xs_empty[fast_slot]);
                 rc.lap(12);
                 // The stores must have completed before hi[] / lo[] are overwritten by the next
                 // chunk: tcgen05.st reads its source registers asynchronously (publishing one
