@@ -86,11 +86,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 
 __global__ void k(int variant, int n_mma, int reps, long long *out, uint32_t col_arg, int fill) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar, bar2;
     __shared__ uint32_t tmem_base;
     const uint32_t warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < 16384; i += blockDim.x) {
@@ -167,6 +168,14 @@ __global__ void k(int variant, int n_mma, int reps, long long *out, uint32_t col
                     blo += 256; col += 32; if (col >= 192) col -= 192;
                     if ((i & 31) == 28) blo = blo0;
                 }
+            } else if (v == 6) {
+                // a commit (to a second barrier nobody waits on) after every 4 MMAs
+                for (int i = 0; i < n_mma; i += 4) {
+                    mma4(tmem + 448, tmem + col, blo, bhi, idesc);
+                    commit(&bar2);
+                    blo += 256; col += 32; if (col >= 192) col -= 192;
+                    if ((i & 31) == 28) blo = blo0;
+                }
             } else if (v == 3) {
                 const uint32_t glo = blo0 + 1408;
                 uint32_t dk = 0;
@@ -199,13 +208,13 @@ int main(int argc, char **argv) {
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
     const int n_mma = 64, reps = 200;
     const int fill = argc > 2 ? atoi(argv[2]) : 0;
-    for (int variant : {2, 4, 5}) {
+    for (int variant : {2, 6}) {
         k<<<1, 128, 65536>>>(variant, n_mma, reps, d, (uint32_t)(argc > 1 ? atoi(argv[1]) : 0), fill);
         cudaError_t e = cudaDeviceSynchronize();
         long long h[2] = {0, 0};
         cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
         printf("fill %d variant %2d (N=%d, %s): err=%s issue %.1f cyc/MMA, issue+drain %.1f cyc/MMA\n", fill, variant, variant >= 20 ? 16 : variant >= 10 ? 64 : 32,
-               variant % 10 == 4 ? "4 per asm, accumulators alternate" : variant % 10 == 5 ? "4 per asm, a second warp issues into another accumulator" : variant % 10 == 2 ? "4 per asm" : "other", cudaGetErrorString(e),
+               variant % 10 == 6 ? "4 per asm + one commit per 4 MMAs" : variant % 10 == 4 ? "4 per asm, accumulators alternate" : variant % 10 == 5 ? "4 per asm, a second warp issues into another accumulator" : variant % 10 == 2 ? "4 per asm" : "other", cudaGetErrorString(e),
                (double)h[0] / (n_mma * reps), (double)h[1] / (n_mma * reps));
         if (e != cudaSuccess) return 1;
     }
