@@ -270,9 +270,13 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
         // the splitter once BOTH issuers have committed it. =====
         const uint32_t mine = warp == 8 ? 0u : 1u;
         const uint32_t step = P.issuers;
-        uint32_t q_base = 0;      // ring sequence number of the run's chunk 0
+        // Ring sequence numbers; their slot (q % kSlots) and phase parity ((q / kSlots) & 1) are
+        // carried along incrementally: a division by 14 in every wait of the critical warp is a
+        // dozen dependent instructions.
+        uint32_t q_base = 0;      // the run's chunk 0
         uint32_t q_waited = 0;    // chunks whose x_full barrier has been consumed
         uint32_t q_rel = 0;       // chunks handed back to the splitter (by this warp)
+        uint32_t base_slot = 0, w_slot = 0, w_par = 0, r_slot = 0;
         uint32_t d_seq = 0;       // tiles of this CTA so far; tile -> accumulator d_seq & 1
         rc.start(prof && lane == 0 && mine == 0);
         for (uint32_t it = 0;; ++it) {
@@ -280,15 +284,18 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
             if (!I.valid) break;
             if (mine >= step) continue;           // single-issuer mode: warp 11 only drains the queue
             rc.count(14, I.t1 - I.t0);
+            auto wait_next_chunk = [&]() {
+                mbar_wait(&S.x_full[w_slot], w_par);
+                ++q_waited;
+                if (++w_slot == kSlots) { w_slot = 0; w_par ^= 1u; }
+            };
             // a chunk is handed back only after this warp has seen it filled (its arrival then
             // belongs to the slot's current use even if the warp's own tiles never read the chunk)
             auto release_chunk = [&]() {
-                while (q_waited <= q_rel) {
-                    mbar_wait(&S.x_full[q_waited % kSlots], (q_waited / kSlots) & 1u);
-                    ++q_waited;
-                }
-                tc_commit_elect(&S.x_empty[q_rel % kSlots]);
+                while (q_waited <= q_rel) wait_next_chunk();
+                tc_commit_elect(&S.x_empty[r_slot]);
                 ++q_rel;
+                if (++r_slot == kSlots) r_slot = 0;
             };
             // this warp's first tile of the run: tile parity follows the CTA's tile sequence
             const uint32_t d_run = d_seq;
@@ -314,15 +321,12 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                 const uint32_t gs = d_seq % kGStages;      // G stages follow the tile sequence
                 mbar_wait(&S.g_full[gs], (d_seq / kGStages) & 1u);
                 rc.lap(1);
-                while (q_waited <= q_base + j_last) {
-                    mbar_wait(&S.x_full[q_waited % kSlots], (q_waited / kSlots) & 1u);
-                    ++q_waited;
-                }
+                while (q_waited <= q_base + j_last) wait_next_chunk();
                 rc.lap(0);
                 tc_fence_after();
 
                 const uint32_t d_tmem = tmem + kColD + b * kN;
-                const uint32_t col0 = ((q_base % kSlots) * kChunk + (uint32_t)(m.k0 - I.vb)) % kRing;
+                const uint32_t col0 = (base_slot * kChunk + (uint32_t)(m.k0 - I.vb)) % kRing;
                 const uint32_t n_ks = m.kt >> 3;
                 const uint32_t ghi = b_desc_lo(smem_u32(gst + (size_t)gs * 2 * g_bytes));
                 const uint32_t glo = ghi + (g_bytes >> 4);
@@ -380,6 +384,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
             while (q_rel < q_base + I.n_chunks) release_chunk();
             d_seq = d_run + (I.t1 - I.t0);
             q_base += I.n_chunks;
+            base_slot = (base_slot + I.n_chunks) % kSlots;
         }
         __syncwarp();
     } else if (warp >= 4) {
@@ -392,6 +397,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
         const uint32_t ml = row / CH, c = row % CH;         // member inside the group, channel
         const uint32_t lane_base = ((warp & 3u) * 32u) << 16;
         uint32_t q_seq = 0, xs_seq = 0;
+        uint32_t rs = 0, par = 1;       // ring slot of chunk q_seq and the parity its x_empty wait uses
         rc.start(prof && row == 0 && wg == 0);
         for (uint32_t it = 0;; ++it) {
             const Item I = get_item(it);
@@ -405,8 +411,6 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                 in = job->in;
             }
             for (uint32_t j = 0; j < I.n_chunks; ++j, ++q_seq) {
-                const uint32_t rs = q_seq % kSlots;
-                const uint32_t par = ((q_seq / kSlots) & 1u) ^ 1u;
                 rc.lap(15);
                 // Load and split BEFORE waiting for the ring slot: the slot becomes free only when
                 // the tile(s) still reading it have completed, and from then on the MMA issuer is
@@ -496,6 +500,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                 tmem_wait_st();
                 tc_fence_before();
                 mbar_arrive(&S.x_full[rs]);
+                if (++rs == kSlots) { rs = 0; par ^= 1u; }
                 rc.lap(11);
             }
         }
