@@ -81,7 +81,17 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
         self.proc = None
-        self.lines = []
+        self.lines = []          # (host time, csv line)
+        self.t_begin = None
+        self.t_end = None
+
+    def begin(self):
+        """Marks the start of the timed region (the sampler itself is started earlier, before the
+        warm-up, because nvidia-smi needs a few hundred ms before its first line)."""
+        self.t_begin = time.time()
+
+    def end(self):
+        self.t_end = time.time()
 
     def start(self):
         try:
@@ -96,7 +106,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if not self.proc:
@@ -108,7 +118,16 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lines = self.lines
+        if self.t_begin is not None and self.t_end is not None:
+            inside = [ln for t, ln in lines if self.t_begin <= t <= self.t_end + 0.05]
+            # a very short timed region may fall between two samples: then the nearest ones
+            if not inside and lines:
+                mid = 0.5 * (self.t_begin + self.t_end)
+                inside = [ln for _, ln in sorted(lines, key=lambda x: abs(x[0] - mid))[:2]]
+        else:
+            inside = [ln for _, ln in lines]
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -260,19 +279,21 @@ def run_ours(args):
                                   memspace=MEM_DEVICE, flags=flags)
 
     # ---- device-resident throughput (value) ----
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 0)):
         step()
     batch.sync()
     launches0 = batch.launch_count()
-    sampler = ClockSampler(local)
     barrier(dist, local)
-    sampler.start()
+    sampler.begin()
     batch.timer_start()
     counts = None
     for _ in range(args.steps):
         counts = step()
     ms = batch.timer_stop()
     batch.sync()
+    sampler.end()
     clocks = sampler.stop()
     barrier(dist, local)
     launches = batch.launch_count() - launches0
