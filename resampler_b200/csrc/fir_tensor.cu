@@ -14,21 +14,26 @@
 // (both ends of the band towards its centre) so that the large centre taps are added last.
 // The parity bar against the oracle is 1e-6 absolute, as for the FFMA2 kernel.
 //
-// Data flow of one CTA (persistent, one per SM, 11 warps):
+// Data flow of one CTA (persistent, one per SM, 16 warps; every hand-off is an mbarrier):
 //   * work item = (run of consecutive tiles) x (group of 128 rows = 128 / CH member streams).
 //     A run walks forward in time, so every input frame is fetched from HBM/L2 ONCE per row
 //     and kept in a ring while the ~6 tiles whose windows cover it are computed (the FFMA2
 //     kernel re-fetches each tile's whole window: 5.4x the input through L2, 1.7x from HBM).
 //   * warp 9 (one thread): work scheduler (atomic counter) and TMA producer of the input: one
-//     2-D tensor copy per 16-frame chunk (box = 16 frames x 128/CH members, 128B/64B swizzle).
-//   * warps 4-7 ("splitter", thread == row): read the chunk from shared memory, de-interleave,
-//     split into hi/lo and write both into TMEM rings (tcgen05.st): ring column == input frame,
-//     TMEM lane == row.  The rings are the A operands, no second shared-memory copy exists.
+//     2-D tensor copy per 16-frame chunk (box = 16 frames x 128/CH members; mono / stereo with
+//     64B / 128B swizzle, 4 / 8 channels unswizzled).  The chunk grid is anchored at the first
+//     new input frame: a TMA box must start 16-byte aligned in global memory.
+//   * warps 4-7 and 12-15 ("splitter", thread == row, each warpgroup takes 8 of a chunk's 16
+//     frames): read the chunk from shared memory, de-interleave, split into hi/lo and write both
+//     into TMEM rings (tcgen05.st): ring column == input frame, TMEM lane == row.  The rings are
+//     the A operands, no second shared-memory copy exists.
 //   * warp 10 (one thread): TMA bulk copies of the tile's G matrices (hi and lo, prebuilt in the
 //     canonical no-swizzle K-major core-matrix layout by tc_gmat_kernel) into a 3-stage ring.
-//   * warp 8 (one thread): issues the tcgen05.mma (66 per 128-tap tile), commits to mbarriers.
+//   * warps 8 and 11: issue the tcgen05.mma (63 per 128-tap tile) for alternate tiles, one
+//     accumulator each (one warp alone when two tiles' K ranges do not fit the ring together);
+//     tcgen05.commit to mbarriers tells the epilogue, the G producer and the splitter.
 //   * warps 0-3 (epilogue): tcgen05.ld of the 128 x 32 accumulator, staging through shared
-//     memory, coalesced 16-byte stores.  Two accumulators, so tile t+1 runs under the stores.
+//     memory, coalesced 16-byte stores.
 //
 // TMEM map (512 columns x 128 lanes): [0,224) X hi ring, [224,448) X lo ring, [448,480) and
 // [480,512) the two accumulators.
