@@ -105,17 +105,15 @@ def _check(rc: int) -> None:
 
 
 def _ptr_array(ptrs: Sequence[int]):
-    arr = (C.c_void_p * len(ptrs))()
-    for i, p in enumerate(ptrs):
-        arr[i] = p
-    return arr
+    if isinstance(ptrs, C.Array):      # already a ctypes array (hot loops build it once)
+        return ptrs
+    return (C.c_void_p * len(ptrs))(*ptrs)
 
 
 def _size_array(vals: Sequence[int]):
-    arr = (C.c_size_t * len(vals))()
-    for i, v in enumerate(vals):
-        arr[i] = int(v)
-    return arr
+    if isinstance(vals, C.Array):
+        return vals
+    return (C.c_size_t * len(vals))(*[int(v) for v in vals])
 
 
 class DeviceBuffer:
