@@ -143,6 +143,33 @@ int rsb_fir_process_batch(rsb_fir *h, uint32_t n, const uint32_t *streams,
                           size_t *consumed_totals, size_t *produced_totals, uint32_t *n_calls,
                           int memspace, uint32_t flags);
 
+/* ---- CLI batch path: the format step in front of the canonical loop ----
+ * (resample/src/main.rs:128-156, then resample_batch_fir :226-254)
+ * Sample formats as hound 3.5 hands them to the CLI (`samples::<i32>()` / `samples::<f32>()`):
+ * integer samples become `s as f32 / 2^(bits-1)` (main.rs:131-136); 8-bit WAV data is unsigned
+ * on disk and 128 is subtracted first; 24-bit samples are 3 packed little-endian bytes.
+ * Reference quirk kept for parity: for 32-bit samples `(1 << 31) as f32` is an i32 shift,
+ * i.e. -2^31, so RSB_PCM_S32 yields -s / 2^31 (inverted polarity) exactly like the CLI. */
+enum rsb_pcm_format { RSB_PCM_U8 = 0, RSB_PCM_S16 = 1, RSB_PCM_S24 = 2, RSB_PCM_S32 = 3,
+                      RSB_PCM_F32 = 4 };
+/* Like rsb_fir_process_batch, but in[i] points at in_frames[i] frames of raw samples with
+ * src_channels interleaved channels.  src_channels == 1: every sample is duplicated into all
+ * of the handle's channels (main.rs:139-146, mono -> stereo); src_channels == channels: passes
+ * through (:148-150); anything else: RSB_ERR_INVALID_ARGUMENT ("Unsupported channel count",
+ * :151-154).  The conversion runs on the GPU (one pass, pcm_ingest.cu) into a staging buffer
+ * owned by the handle; host memspace moves the RAW samples over PCIe (half the bytes of f32
+ * for 16-bit sources).  call_len, out_cap_len, consumed_totals and produced_totals are in f32
+ * values of the converted signal (the CLI uses call_len = 512).  Synchronous
+ * (RSB_FLAG_ASYNC is rejected). */
+int rsb_fir_process_pcm_batch(rsb_fir *h, uint32_t n, const uint32_t *streams,
+                              const void *const *in, const size_t *in_frames, int format,
+                              uint32_t src_channels, size_t call_len, size_t out_cap_len,
+                              float *const *out, const size_t *out_capacities,
+                              size_t *consumed_totals, size_t *produced_totals, uint32_t *n_calls,
+                              int memspace, uint32_t flags);
+/* device time (ms, CUDA events) of the format-step kernel of the most recent PCM batch */
+int rsb_fir_last_ingest_ms(rsb_fir *h, float *ms);
+
 /* completes RSB_FLAG_ASYNC work (writes the deferred counts) and waits for the GPU */
 int rsb_fir_sync(rsb_fir *h);
 

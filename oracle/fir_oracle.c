@@ -383,3 +383,43 @@ size_t orc_fir_process(orc_fir *r, const float *in, size_t total_len, size_t cal
     if (in_total) *in_total = offset;
     return calls;
 }
+
+/* ---- CLI format step: resample/src/main.rs:128-156 ---- */
+void orc_pcm_to_f32(const void *src, int format, size_t n_src, size_t dup, float *dst) {
+    const uint8_t *b = (const uint8_t *)src;
+    for (size_t i = 0; i < n_src; ++i) {
+        float x;
+        if (format == 4) {                    /* SampleFormat::Float, main.rs:129 */
+            uint32_t u = (uint32_t)b[4 * i] | ((uint32_t)b[4 * i + 1] << 8) |
+                         ((uint32_t)b[4 * i + 2] << 16) | ((uint32_t)b[4 * i + 3] << 24);
+            memcpy(&x, &u, 4);
+        } else {                              /* SampleFormat::Int, main.rs:130-136 */
+            int32_t s;
+            int bits;
+            if (format == 0) {                /* hound: u8 on disk, minus 128 */
+                s = (int32_t)b[i] - 128;
+                bits = 8;
+            } else if (format == 1) {
+                s = (int16_t)((uint16_t)b[2 * i] | ((uint16_t)b[2 * i + 1] << 8));
+                bits = 16;
+            } else if (format == 2) {
+                uint32_t u = (uint32_t)b[3 * i] | ((uint32_t)b[3 * i + 1] << 8) |
+                             ((uint32_t)b[3 * i + 2] << 16);
+                s = (u & 0x800000u) ? (int32_t)(u | 0xff000000u) : (int32_t)u;
+                bits = 24;
+            } else {
+                uint32_t u = (uint32_t)b[4 * i] | ((uint32_t)b[4 * i + 1] << 8) |
+                             ((uint32_t)b[4 * i + 2] << 16) | ((uint32_t)b[4 * i + 3] << 24);
+                s = (int32_t)u;
+                bits = 32;
+            }
+            /* `(1 << (bits - 1)) as f32`: the literal is an i32, and for 32-bit samples
+             * `1i32 << 31` is i32::MIN (Rust's shift only panics for amounts >= 32), so
+             * max_value = -2^31 and the CLI yields -s / 2^31: 32-bit integer files come out
+             * with inverted polarity.  The restatement keeps that. */
+            float max_value = bits == 32 ? -2147483648.0f : (float)(1 << (bits - 1));
+            x = (float)s / max_value;         /* `s as f32 / max_value`, main.rs:135 */
+        }
+        for (size_t d = 0; d < dup; ++d) dst[i * dup + d] = x;   /* main.rs:141-146 */
+    }
+}

@@ -13,6 +13,7 @@
  *   src/resampler_fir.rs:509-621 (resample(): the streaming state machine)
  *   src/fir/avx512.rs:5-50       (dual-phase dot product, AVX-512 order)
  *   src/fir/mod.rs:47-62         (scalar dot product)
+ *   resample/src/main.rs:128-156 (CLI format step: integer PCM -> f32, mono -> stereo)
  * The Rust reference cannot be compiled in this image (no rustc/cargo), so
  * there is no oracle/_ref build.
  *
@@ -22,6 +23,11 @@
  *   - convolution formula: PINNED to the reference's SIMD-vs-scalar test
  *     (src/fir/mod.rs:137-192, 1e-5) and the >= 90 dB stop-band test
  *     (src/resampler_fir.rs:741-815).
+ *   - CLI format step (orc_pcm_to_f32): PARITY UNPINNED by the reference (the CLI has no
+ *     tests); the arithmetic is one exact division by a power of two per sample and is
+ *     checked against hand-computed values in tests/test_oracle_golden.py.  The i32 values
+ *     come from hound 3.5.1 (Cargo.lock; not vendored): 8-bit WAV samples are unsigned bytes
+ *     minus 128, 16/24/32-bit ones are little-endian two's complement.
  *   - (consumed, produced) sequences, phase indices and output sample values:
  *     PARITY UNPINNED by the reference -- no reference test or fixture holds
  *     any of them.  They rest on this restatement, cross-checked by a second,
@@ -115,6 +121,12 @@ size_t orc_fir_process(orc_fir *r, const float *in, size_t total_len, size_t cal
                        size_t out_cap_len, float *out, size_t out_capacity, size_t *out_total,
                        size_t *in_total, uint32_t *consumed_calls, uint32_t *produced_calls,
                        size_t max_calls, orc_trace *trace);
+
+/* ---- CLI format step (resample/src/main.rs:128-156) ----
+ * format: 0 = unsigned 8-bit, 1 = s16le, 2 = packed s24le, 3 = s32le, 4 = f32.
+ * Converts n_src source values; each is written `dup` times in a row (dup = 2 for the CLI's
+ * mono -> stereo duplication, :139-146; 1 for stereo, :148-150).  dst holds n_src * dup. */
+void orc_pcm_to_f32(const void *src, int format, size_t n_src, size_t dup, float *dst);
 
 /* ---- multi-threaded CPU baseline (cpu_bench.c) ---- */
 /* Runs `n_streams` independent resamplers, one stream per thread at a time

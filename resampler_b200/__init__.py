@@ -6,9 +6,9 @@ Host-side mirror of the reference's public interface (src/lib.rs:160-163):
 plus the batched multi-stream ``FirBatch`` that is new.  All compute goes through
 the C ABI of ``include/resampler_b200.h`` into hand-written CUDA kernels.
 """
-from .fir import (Attenuation, FirBatch, Kernel, Latency, ResampleError, ResamplerFir,
+from .fir import (Attenuation, FirBatch, Kernel, Latency, PcmFormat, ResampleError, ResamplerFir,
                   SampleRate, device_count)
 
-__all__ = ["Attenuation", "FirBatch", "Kernel", "Latency", "ResampleError", "ResamplerFir",
-           "SampleRate", "device_count"]
+__all__ = ["Attenuation", "FirBatch", "Kernel", "Latency", "PcmFormat", "ResampleError",
+           "ResamplerFir", "SampleRate", "device_count"]
 __version__ = "0.1.0"

@@ -24,6 +24,7 @@
 #include "../../include/resampler_b200.h"
 #include "filter_design.h"
 #include "fir_kernels.h"
+#include "pcm_ingest.h"
 
 namespace {
 
@@ -144,6 +145,11 @@ struct rsb_fir {
     Workspace ws[2];
     uint64_t submits = 0;             // ws[submits & 1] is the next one to use
     DevBuf d_stage_in, d_stage_out, d_dbg;   // host-memspace staging (those calls are synchronous)
+    // PCM format step (rsb_fir_process_pcm_batch): raw samples of host-memspace calls, job table
+    DevBuf d_pcm_raw, d_pcm_jobs;
+    PinBuf h_pcm_jobs;
+    cudaEvent_t ev_pcm[2] = {};
+    bool pcm_timed = false;
     Workspace &last_ws() { return ws[(submits + 1) & 1]; }
 };
 
@@ -169,6 +175,14 @@ struct JobHost {
     uint64_t out_capacity;     // frames
     uint32_t call_frames;      // frames per call (ignored when single)
     uint32_t cap_frames;       // output capacity per call, frames
+};
+
+// Raw-sample input of a batch (rsb_fir_process_pcm_batch): JobHost::in then points at raw
+// samples, which the format step converts into the f32 staging buffer the kernels read.
+struct PcmSpec {
+    int format;
+    uint32_t dup;   // f32 values written per source value (mono source: the handle's channels)
+    uint32_t bps;   // bytes per source sample
 };
 
 uint32_t segs_per_call_bound(double ratio) {
@@ -293,7 +307,8 @@ int finalize_all(rsb_fir *h) {
 
 // Core: runs `jobs` (already validated) on the device.
 int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int memspace,
-              uint32_t flags, size_t *consumed, size_t *produced, uint32_t *n_calls_out) {
+              uint32_t flags, size_t *consumed, size_t *produced, uint32_t *n_calls_out,
+              const PcmSpec *pcm = nullptr) {
     RSB_CUDA(cudaSetDevice(h->device));
     Workspace &W = h->ws[h->submits & 1];
     // this workspace was last used two submits ago: collect its counts, wait for its kernels
@@ -340,7 +355,7 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
             use_fast = (uint64_t)biggest * ch >= 32;
         }
     }
-    if (use_fast && memspace == RSB_MEM_DEVICE) {
+    if (use_fast && memspace == RSB_MEM_DEVICE && !pcm) {
         // the fast kernel stages input with 16-byte vector loads
         for (uint32_t i = 0; i < n; ++i)
             if ((reinterpret_cast<uintptr_t>(jobs[i].in) & 15u) != 0) {
@@ -418,12 +433,14 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
 
     // ---- host-memory staging ----
     const bool host_mem = memspace == RSB_MEM_HOST;
-    std::vector<size_t> in_off, out_off, in_vals;
-    size_t in_total = 0, out_total = 0;
-    if (host_mem) {
+    const bool stage_in = host_mem || pcm != nullptr;   // the kernels read d_stage_in
+    std::vector<size_t> in_off, out_off, in_vals, raw_off;
+    size_t in_total = 0, out_total = 0, raw_total = 0;
+    if (stage_in) {
         in_off.resize(n);
         out_off.resize(n);
         in_vals.resize(n);
+        raw_off.resize(n);
         for (uint32_t i = 0; i < n; ++i) {
             uint64_t frames = jobs[i].total_frames;
             if (single) frames = std::min<uint64_t>(frames, rsb::kInputCapacity);   // :526-528
@@ -432,9 +449,14 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
             in_total += (in_vals[i] + 3) & ~(size_t)3;    // keep 16-byte alignment
             out_off[i] = out_total;
             out_total += ((size_t)jobs[i].out_capacity * ch + 3) & ~(size_t)3;
+            if (pcm) {
+                raw_off[i] = raw_total;
+                raw_total += (in_vals[i] / pcm->dup * pcm->bps + 15) & ~(size_t)15;
+            }
         }
         RSB_CUDA(h->d_stage_in.reserve(in_total * sizeof(float) + 16));
-        RSB_CUDA(h->d_stage_out.reserve(out_total * sizeof(float) + 16));
+        if (host_mem) RSB_CUDA(h->d_stage_out.reserve(out_total * sizeof(float) + 16));
+        if (host_mem && pcm) RSB_CUDA(h->d_pcm_raw.reserve(raw_total + 16));
     }
 
     // jobs are stored grouped by unit: members of U are hj[U.member_off .. +U.n_members)
@@ -445,13 +467,8 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
         J.stream = jobs[i].stream;
         J.unit = W.job_unit[i];
         J.out_capacity = jobs[i].out_capacity;
-        if (host_mem) {
-            J.in = h->d_stage_in.as<float>() + in_off[i];
-            J.out = h->d_stage_out.as<float>() + out_off[i];
-        } else {
-            J.in = jobs[i].in;
-            J.out = jobs[i].out;
-        }
+        J.in = stage_in ? h->d_stage_in.as<float>() + in_off[i] : jobs[i].in;
+        J.out = host_mem ? h->d_stage_out.as<float>() + out_off[i] : jobs[i].out;
         const uint32_t sel = h->hist_sel[J.stream];
         J.hist = h->st.hist[sel] + hist_stride * J.stream;
         J.hist_next = h->st.hist[sel ^ 1u] + hist_stride * J.stream;
@@ -538,7 +555,7 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     RSB_CUDA(cudaMemcpyAsync(W.d_jobs.p, hj, sizeof(JobDev) * n, cudaMemcpyHostToDevice, sp));
     RSB_CUDA(cudaMemsetAsync(W.d_counter.p, 0, sizeof(uint32_t) * 4, sp));
     // host buffers that are equally sized and equally strided move with ONE 2-D copy
-    bool h2d_uniform = host_mem && n > 1, d2h_uniform = host_mem && n > 1 && n_units == 1;
+    bool h2d_uniform = host_mem && !pcm && n > 1, d2h_uniform = host_mem && n > 1 && n_units == 1;
     ptrdiff_t in_pitch = 0, out_pitch = 0;
     if (host_mem && n > 1) {
         in_pitch = reinterpret_cast<const char *>(jobs[1].in) - reinterpret_cast<const char *>(jobs[0].in);
@@ -556,7 +573,57 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
         if (in_pitch < (ptrdiff_t)(in_vals[0] * sizeof(float))) h2d_uniform = false;
         if (out_pitch <= 0) d2h_uniform = false;
     }
-    if (host_mem) {
+    if (pcm) {
+        // ---- format step: raw samples -> interleaved f32 frames in d_stage_in ----
+        uint64_t n_chunks = 0, chunks_per_job = rsb::pcm_chunks(in_vals[0]);
+        RSB_CUDA(h->h_pcm_jobs.reserve(sizeof(rsb::PcmJob) * n + sizeof(uint64_t) * (n + 1)));
+        RSB_CUDA(h->d_pcm_jobs.reserve(sizeof(rsb::PcmJob) * n + sizeof(uint64_t) * (n + 1)));
+        rsb::PcmJob *pj = h->h_pcm_jobs.as<rsb::PcmJob>();
+        uint64_t *cf = reinterpret_cast<uint64_t *>(pj + n);
+        // equally sized host buffers at one pitch move with ONE 2-D copy
+        bool raw_uniform = host_mem && n > 1 && in_vals[0] != 0;
+        ptrdiff_t raw_pitch = 0;
+        if (raw_uniform) {
+            raw_pitch = reinterpret_cast<const char *>(jobs[1].in) - reinterpret_cast<const char *>(jobs[0].in);
+            for (uint32_t i = 1; raw_uniform && i < n; ++i)
+                raw_uniform = in_vals[i] == in_vals[0] &&
+                              reinterpret_cast<const char *>(jobs[i].in) -
+                                      reinterpret_cast<const char *>(jobs[0].in) == (ptrdiff_t)i * raw_pitch;
+            if (raw_pitch < (ptrdiff_t)(in_vals[0] / pcm->dup * pcm->bps)) raw_uniform = false;
+        }
+        if (raw_uniform)
+            RSB_CUDA(cudaMemcpy2DAsync(h->d_pcm_raw.p, raw_off[1] - raw_off[0], jobs[0].in,
+                                       (size_t)raw_pitch, in_vals[0] / pcm->dup * pcm->bps, n,
+                                       cudaMemcpyHostToDevice, s));
+        for (uint32_t i = 0; i < n; ++i) {
+            const size_t raw_bytes = in_vals[i] / pcm->dup * pcm->bps;
+            const void *src = jobs[i].in;
+            if (host_mem) {
+                void *d = static_cast<char *>(h->d_pcm_raw.p) + raw_off[i];
+                if (raw_bytes && !raw_uniform)
+                    RSB_CUDA(cudaMemcpyAsync(d, jobs[i].in, raw_bytes, cudaMemcpyHostToDevice, s));
+                src = d;
+            }
+            pj[i].src = src;
+            pj[i].dst = h->d_stage_in.as<float>() + in_off[i];
+            pj[i].n_out = in_vals[i];
+            pj[i].src_aligned = (reinterpret_cast<uintptr_t>(src) & 15u) == 0 ? 1u : 0u;
+            pj[i].pad_ = 0;
+            cf[i] = n_chunks;
+            n_chunks += rsb::pcm_chunks(in_vals[i]);
+            if (rsb::pcm_chunks(in_vals[i]) != rsb::pcm_chunks(in_vals[0])) chunks_per_job = 0;
+        }
+        cf[n] = n_chunks;
+        RSB_CUDA(cudaMemcpyAsync(h->d_pcm_jobs.p, pj, sizeof(rsb::PcmJob) * n + sizeof(uint64_t) * (n + 1),
+                                 cudaMemcpyHostToDevice, s));
+        RSB_CUDA(cudaEventRecord(h->ev_pcm[0], s));
+        rsb::launch_pcm_ingest(h->d_pcm_jobs.as<rsb::PcmJob>(),
+                               reinterpret_cast<const uint64_t *>(h->d_pcm_jobs.as<rsb::PcmJob>() + n), n,
+                               n_chunks, chunks_per_job, pcm->format, pcm->dup, h->sm_count, s);
+        RSB_CUDA(cudaEventRecord(h->ev_pcm[1], s));
+        h->pcm_timed = n_chunks != 0;
+        if (n_chunks) h->launches += 1;
+    } else if (host_mem) {
         if (h2d_uniform && in_vals[0]) {
             RSB_CUDA(cudaMemcpy2DAsync(h->d_stage_in.p, (in_off[1] - in_off[0]) * sizeof(float),
                                        jobs[0].in, (size_t)in_pitch, in_vals[0] * sizeof(float), n,
@@ -808,6 +875,7 @@ int rsb_fir_create(rsb_fir **out, int device, uint32_t n_streams, uint32_t chann
     RSB_CUDA(cudaEventCreate(&h->ev_t0));
     RSB_CUDA(cudaEventCreate(&h->ev_t1));
     RSB_CUDA(cudaEventCreateWithFlags(&h->ev_sync, cudaEventDisableTiming));
+    for (cudaEvent_t &e : h->ev_pcm) RSB_CUDA(cudaEventCreate(&e));
     for (Workspace &W : h->ws) {
         RSB_CUDA(cudaEventCreateWithFlags(&W.ev_plan, cudaEventDisableTiming));
         RSB_CUDA(cudaEventCreateWithFlags(&W.ev_done, cudaEventDisableTiming));
@@ -854,7 +922,10 @@ void rsb_fir_destroy(rsb_fir *h) {
         if (W.ev_plan) cudaEventDestroy(W.ev_plan);
         if (W.ev_done) cudaEventDestroy(W.ev_done);
     }
-    for (DevBuf *b : {&h->d_stage_in, &h->d_stage_out, &h->d_dbg}) b->release();
+    for (DevBuf *b : {&h->d_stage_in, &h->d_stage_out, &h->d_dbg, &h->d_pcm_raw, &h->d_pcm_jobs})
+        b->release();
+    h->h_pcm_jobs.release();
+    for (cudaEvent_t e : h->ev_pcm) if (e) cudaEventDestroy(e);
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);
     if (h->ev_t1) cudaEventDestroy(h->ev_t1);
     if (h->ev_sync) cudaEventDestroy(h->ev_sync);
@@ -1013,6 +1084,70 @@ int rsb_fir_process_batch(rsb_fir *h, uint32_t n, const uint32_t *streams, const
                           (uint32_t)(call_len / ch), (uint32_t)(out_cap_len / ch)};
     }
     return run_batch(h, jobs, false, memspace, flags, consumed_totals, produced_totals, n_calls);
+}
+
+// CLI batch path: format step (resample/src/main.rs:128-156) + canonical loop (:226-254)
+int rsb_fir_process_pcm_batch(rsb_fir *h, uint32_t n, const uint32_t *streams,
+                              const void *const *in, const size_t *in_frames, int format,
+                              uint32_t src_channels, size_t call_len, size_t out_cap_len,
+                              float *const *out, const size_t *out_capacities,
+                              size_t *consumed_totals, size_t *produced_totals, uint32_t *n_calls,
+                              int memspace, uint32_t flags) {
+    if (check_handle(h)) return RSB_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RSB_OK;
+    if (!in || !in_frames || !out || !out_capacities)
+        return fail(RSB_ERR_INVALID_ARGUMENT, "null array argument");
+    if (memspace != RSB_MEM_DEVICE && memspace != RSB_MEM_HOST)
+        return fail(RSB_ERR_INVALID_ARGUMENT, "bad memspace");
+    if (flags & RSB_FLAG_ASYNC)
+        return fail(RSB_ERR_INVALID_ARGUMENT, "RSB_FLAG_ASYNC is not available for PCM batches");
+    const uint32_t ch = h->channels;
+    PcmSpec spec;
+    spec.format = format;
+    spec.bps = rsb::pcm_bytes_per_sample(format);
+    if (spec.bps == 0) return fail(RSB_ERR_INVALID_ARGUMENT, "unknown PCM format");
+    // main.rs:139-156: a mono source is duplicated into every channel, a source with the
+    // resampler's channel count passes through, anything else is "Unsupported channel count"
+    if (src_channels != 1 && src_channels != ch)
+        return fail(RSB_ERR_INVALID_ARGUMENT, "Unsupported channel count: " + std::to_string(src_channels));
+    spec.dup = src_channels == ch ? 1u : ch;
+    if (out_cap_len == 0) out_cap_len = rsb_fir_buffer_size_output(h);
+    if (call_len % ch != 0)
+        return fail(RSB_ERR_INVALID_INPUT_BUFFER_SIZE, "call_len is not a multiple of channels");
+    if (out_cap_len % ch != 0)
+        return fail(RSB_ERR_INVALID_OUTPUT_BUFFER_SIZE, "out_cap_len is not a multiple of channels");
+    if (call_len / ch > 0xffffffffull || out_cap_len / ch > 0xffffffffull)
+        return fail(RSB_ERR_INVALID_ARGUMENT, "call too large");
+    std::vector<JobHost> jobs(n);
+    std::vector<uint8_t> seen(h->n_streams, 0);
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t s = streams ? streams[i] : i;
+        if (s >= h->n_streams) return fail(RSB_ERR_INVALID_ARGUMENT, "bad stream index");
+        if (seen[s]) return fail(RSB_ERR_INVALID_ARGUMENT, "stream listed twice in one batch");
+        seen[s] = 1;
+        if (in_frames[i] && call_len == 0)
+            return fail(RSB_ERR_INVALID_ARGUMENT, "call_len must be positive");
+        if (in_frames[i] && !in[i]) return fail(RSB_ERR_INVALID_ARGUMENT, "null input pointer");
+        if (out_capacities[i] && !out[i]) return fail(RSB_ERR_INVALID_ARGUMENT, "null output pointer");
+        jobs[i] = JobHost{s, static_cast<const float *>(in[i]), out[i], in_frames[i],
+                          out_capacities[i] / ch, (uint32_t)(call_len / ch), (uint32_t)(out_cap_len / ch)};
+    }
+    // the format step reuses one job table and staging buffer: nothing may still be in flight
+    int rc = finalize_all(h);
+    if (rc != RSB_OK && rc != RSB_ERR_OUTPUT_CAPACITY) return rc;
+    RSB_CUDA(cudaSetDevice(h->device));
+    RSB_CUDA(cudaStreamSynchronize(h->stream));
+    return run_batch(h, jobs, false, memspace, flags, consumed_totals, produced_totals, n_calls, &spec);
+}
+
+int rsb_fir_last_ingest_ms(rsb_fir *h, float *ms) {
+    if (check_handle(h)) return RSB_ERR_INVALID_ARGUMENT;
+    if (!ms) return fail(RSB_ERR_INVALID_ARGUMENT, "null argument");
+    if (!h->pcm_timed) return fail(RSB_ERR_INVALID_ARGUMENT, "no PCM batch has run on this handle");
+    RSB_CUDA(cudaSetDevice(h->device));
+    RSB_CUDA(cudaEventSynchronize(h->ev_pcm[1]));
+    RSB_CUDA(cudaEventElapsedTime(ms, h->ev_pcm[0], h->ev_pcm[1]));
+    return RSB_OK;
 }
 
 int rsb_fir_sync(rsb_fir *h) {

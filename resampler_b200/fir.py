@@ -69,6 +69,22 @@ class Kernel(enum.IntEnum):
     TENSOR = 3  # tcgen05 tensor cores, 3xTF32, within 1e-6 absolute (uniform batches)
 
 
+class PcmFormat(enum.IntEnum):
+    """Raw sample formats of the CLI's format step (resample/src/main.rs:128-137)."""
+    U8 = 0
+    S16 = 1
+    S24 = 2    # 3 packed little-endian bytes per sample
+    S32 = 3    # the reference's `(1 << 31) as f32` quirk: comes out with inverted polarity
+    F32 = 4
+
+    def bytes_per_sample(self) -> int:
+        return (1, 2, 3, 4, 4)[int(self)]
+
+
+_PCM_DTYPES = {PcmFormat.U8: np.uint8, PcmFormat.S16: np.int16, PcmFormat.S24: np.uint8,
+               PcmFormat.S32: np.int32, PcmFormat.F32: np.float32}
+
+
 class ResampleError(Exception):
     """src/error.rs:1-26.  ``kind`` is ``InvalidInputBufferSize`` or ``InvalidOutputBufferSize``."""
 
@@ -269,6 +285,57 @@ class FirBatch:
         return {"out": [o[:prod[i]] for i, o in enumerate(outs)],
                 "consumed": np.array(cons[:], np.int64), "produced": np.array(prod[:], np.int64),
                 "calls": np.array(calls[:], np.int64)}
+
+    def process_pcm(self, inputs: Sequence[np.ndarray], fmt: PcmFormat, src_channels: int,
+                    call_len: int = 512, out_cap_len: int = 0,
+                    out_capacity: Optional[int] = None, streams: Optional[Sequence[int]] = None,
+                    flags: int = 0):
+        """The CLI's batch path (resample/src/main.rs:128-156 + 226-254) for many files at once:
+        ``inputs[i]`` holds one file's raw interleaved samples (dtype of ``fmt``; S24 as bytes),
+        converted to f32 and, for a mono source, duplicated into every channel ON THE GPU, then
+        run through the canonical 512-value-call loop.  Same result dict as ``process``."""
+        fmt = PcmFormat(fmt)
+        n = len(inputs)
+        bps = fmt.bytes_per_sample()
+        inputs = [np.ascontiguousarray(a, _PCM_DTYPES[fmt]) for a in inputs]
+        frames = []
+        for a in inputs:
+            if a.nbytes % (bps * src_channels) != 0:
+                raise ResampleError(1)      # not a whole number of source frames
+            frames.append(a.nbytes // (bps * src_channels))
+        if out_capacity is None:
+            longest = max(frames, default=0) * self.channels
+            out_capacity = int(longest / self.ratio()) + 4 * self.buffer_size_output() + 64
+            out_capacity -= out_capacity % self.channels
+        outs = [np.zeros(out_capacity, np.float32) for _ in range(n)]
+        cons, prod, calls = (C.c_size_t * n)(), (C.c_size_t * n)(), (C.c_uint32 * n)()
+        st = (C.c_uint32 * n)(*streams) if streams is not None else None
+        _check(self._lib.rsb_fir_process_pcm_batch(
+            self._h, n, st, _ptr_array([a.ctypes.data for a in inputs]), _size_array(frames),
+            int(fmt), src_channels, call_len, out_cap_len,
+            _ptr_array([a.ctypes.data for a in outs]), _size_array([out_capacity] * n),
+            cons, prod, calls, MEM_HOST, flags))
+        return {"out": [o[:prod[i]] for i, o in enumerate(outs)],
+                "consumed": np.array(cons[:], np.int64), "produced": np.array(prod[:], np.int64),
+                "calls": np.array(calls[:], np.int64)}
+
+    def process_pcm_ptrs(self, in_ptrs, in_frames, fmt: PcmFormat, src_channels: int, call_len,
+                         out_cap_len, out_ptrs, out_capacities, streams=None,
+                         memspace=MEM_DEVICE, flags: int = 0):
+        n = len(in_ptrs)
+        cons, prod, calls = (C.c_size_t * n)(), (C.c_size_t * n)(), (C.c_uint32 * n)()
+        st = (C.c_uint32 * n)(*streams) if streams is not None else None
+        _check(self._lib.rsb_fir_process_pcm_batch(
+            self._h, n, st, _ptr_array(in_ptrs), _size_array(in_frames), int(fmt), src_channels,
+            call_len, out_cap_len, _ptr_array(out_ptrs), _size_array(out_capacities), cons, prod,
+            calls, memspace, flags))
+        return cons, prod, calls
+
+    def last_ingest_ms(self) -> float:
+        """Device time of the format-step kernel of the most recent PCM batch."""
+        ms = C.c_float(0)
+        _check(self._lib.rsb_fir_last_ingest_ms(self._h, C.byref(ms)))
+        return ms.value
 
     def process_ptrs(self, in_ptrs, total_lens, call_len, out_cap_len, out_ptrs, out_capacities,
                      streams=None, memspace=MEM_DEVICE, flags: int = 0, want_counts: bool = True):

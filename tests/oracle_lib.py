@@ -95,6 +95,7 @@ def lib() -> C.CDLL:
                                     C.c_int, _f32p, C.c_size_t, C.c_size_t, C.c_size_t, _f32p,
                                     C.c_size_t, _u64p, C.c_int, C.c_int]
         L.orc_cpu_has_avx512f.restype = C.c_int
+        L.orc_pcm_to_f32.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, _f32p]
         _lib = L
     return _lib
 
@@ -167,6 +168,20 @@ def _aligned_copy(a: np.ndarray, align: int = 64) -> np.ndarray:
     off = (-raw.ctypes.data) % align
     out = raw[off:off + a.nbytes].view(a.dtype).reshape(a.shape)
     out[...] = a
+    return out
+
+
+PCM_U8, PCM_S16, PCM_S24, PCM_S32, PCM_F32 = 0, 1, 2, 3, 4
+PCM_BYTES = {PCM_U8: 1, PCM_S16: 2, PCM_S24: 3, PCM_S32: 4, PCM_F32: 4}
+
+
+def pcm_to_f32(raw: np.ndarray, fmt: int, dup: int = 1) -> np.ndarray:
+    """The CLI's format step (resample/src/main.rs:128-156): raw little-endian samples ->
+    f32, each value written ``dup`` times in a row (2 = mono -> stereo)."""
+    raw = np.ascontiguousarray(raw).view(np.uint8)
+    n = raw.size // PCM_BYTES[fmt]
+    out = np.empty(n * dup, np.float32)
+    lib().orc_pcm_to_f32(raw.ctypes.data, fmt, n, dup, _fp(out))
     return out
 
 

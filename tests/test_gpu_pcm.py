@@ -1,0 +1,177 @@
+"""GPU parity of the CLI batch path: the format step
+(resample/src/main.rs:128-156: integer PCM -> f32, mono -> stereo) fused in front of the
+canonical 512-value-call loop (:226-254), through the C ABI, against the CPU oracle.
+
+Bar: converted samples, counts and (EXACT kernel) output samples bit-identical; the
+tensor / FFMA2 kernels within 1e-6 absolute.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from resampler_b200 import Attenuation, FirBatch, Kernel, Latency, PcmFormat
+from resampler_b200 import _lib
+from resampler_b200.fir import MEM_DEVICE
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-6   # absolute, north_star
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def raw_samples(rng, fmt, n):
+    """n random samples of the format, extremes included, as the bytes a WAV data chunk holds."""
+    if fmt == PcmFormat.U8:
+        a = rng.integers(0, 256, n, dtype=np.uint8)
+        a[:2] = (0, 255)[:n]
+        return a
+    if fmt == PcmFormat.S16:
+        a = rng.integers(-32768, 32768, n, dtype=np.int16)
+        a[:2] = (-32768, 32767)[:n]
+        return a
+    if fmt == PcmFormat.S24:
+        v = rng.integers(-(1 << 23), 1 << 23, n, dtype=np.int64)
+        v[:2] = (-(1 << 23), (1 << 23) - 1)[:n]
+        u = (v & 0xFFFFFF).astype(np.uint32)
+        return np.stack([u & 0xFF, (u >> 8) & 0xFF, (u >> 16) & 0xFF], axis=1).astype(np.uint8).reshape(-1)
+    if fmt == PcmFormat.S32:
+        a = rng.integers(-(1 << 31), 1 << 31, n, dtype=np.int64).astype(np.int32)
+        a[:3] = (-(1 << 31), (1 << 31) - 1, 16777217)[:n]   # the last one rounds in `as f32`
+        return a
+    return rng.uniform(-1.0, 1.0, n).astype(np.float32)
+
+
+def oracle_cli(ch, in_hz, out_hz, lat, raw, fmt, src_ch, call_len=512):
+    x = O.pcm_to_f32(raw, int(fmt), 1 if src_ch == ch else ch)
+    f = O.OracleFir(ch, in_hz, out_hz, lat, 1)
+    return x, f.process(x, call_len)
+
+
+@pytest.mark.parametrize("fmt", list(PcmFormat))
+@pytest.mark.parametrize("src_ch", [1, 2])
+def test_cli_batch_path_bit_exact(fmt, src_ch):
+    """Mono and stereo files of every sample format, ragged lengths (value counts that are not
+    multiples of 4, one empty file), 44.1 -> 48 kHz as the CLI would run them."""
+    ch = 2
+    rng = np.random.default_rng(100 + int(fmt) * 2 + src_ch)
+    frames = [0, 1, 3, 1021, 4099, 9001]
+    raws = [raw_samples(rng, fmt, f * src_ch) for f in frames]
+    batch = FirBatch(len(frames), ch, 44100, 48000, Latency.Sample64, Attenuation.Db90,
+                     kernel=Kernel.EXACT)
+    res = batch.process_pcm(raws, fmt, src_ch)     # call_len = 512 values, main.rs:227
+    assert batch.launch_count() > 0
+    for s, raw in enumerate(raws):
+        _, ref = oracle_cli(ch, 44100, 48000, 3, raw, fmt, src_ch)
+        assert res["consumed"][s] == ref["consumed_total"], s
+        assert res["calls"][s] == ref["calls"], s
+        assert res["produced"][s] == len(ref["out"]), s
+        assert np.array_equal(bits(res["out"][s]), bits(ref["out"])), s
+    batch.close()
+
+
+def test_format_step_known_values_through_the_gpu():
+    """A 1:1 rate pair with the impulse-like phase-0 row is not an identity filter, so the
+    converted samples are observed directly: resample F32 and integer renderings of the same
+    signal and require bit-identical outputs."""
+    ch = 2
+    rng = np.random.default_rng(5)
+    s16 = raw_samples(rng, PcmFormat.S16, 6000 * ch)
+    as_f32 = (s16.astype(np.float32) / np.float32(32768.0)).astype(np.float32)
+    batch = FirBatch(2, ch, 48000, 44100, Latency.Sample64, Attenuation.Db90, kernel=Kernel.EXACT)
+    a = batch.process_pcm([s16], PcmFormat.S16, ch, streams=[0])
+    b = batch.process_pcm([as_f32], PcmFormat.F32, ch, streams=[1])
+    assert a["produced"][0] == b["produced"][0] > 0
+    assert np.array_equal(bits(a["out"][0]), bits(b["out"][0]))
+    # the 32-bit polarity quirk of the reference (`(1 << 31) as f32` = -2^31) is kept
+    s32 = (s16.astype(np.int32) << 16)
+    batch.reset()
+    c = batch.process_pcm([s32], PcmFormat.S32, ch, streams=[0])
+    neg = batch.process_pcm([-as_f32], PcmFormat.F32, ch, streams=[1])
+    assert np.array_equal(bits(c["out"][0]), bits(neg["out"][0]))
+    batch.close()
+
+
+def test_mono_source_into_eight_channels_and_state_carry():
+    """Generic duplication factor (mono -> 8 channels) and a second batch that continues from
+    the carried history / phase."""
+    ch = 8
+    rng = np.random.default_rng(9)
+    raws1 = [raw_samples(rng, PcmFormat.S16, n) for n in (3001, 2999, 17)]
+    raws2 = [raw_samples(rng, PcmFormat.S16, n) for n in (555, 1, 640)]
+    batch = FirBatch(3, ch, 96000, 48000, Latency.Sample32, Attenuation.Db90, kernel=Kernel.EXACT)
+    r1 = batch.process_pcm(raws1, PcmFormat.S16, 1, call_len=512 * ch)
+    r2 = batch.process_pcm(raws2, PcmFormat.S16, 1, call_len=512 * ch)
+    for s in range(3):
+        f = O.OracleFir(ch, 96000, 48000, 2, 1)
+        o1 = f.process(O.pcm_to_f32(raws1[s], O.PCM_S16, ch), 512 * ch)
+        o2 = f.process(O.pcm_to_f32(raws2[s], O.PCM_S16, ch), 512 * ch)
+        assert np.array_equal(bits(r1["out"][s]), bits(o1["out"])), s
+        assert np.array_equal(bits(r2["out"][s]), bits(o2["out"])), s
+    batch.close()
+
+
+def test_errors():
+    batch = FirBatch(2, 2, 44100, 48000, Latency.Sample64, Attenuation.Db90)
+    x = np.zeros(1000, np.int16)
+    with pytest.raises(ValueError, match="Unsupported channel count"):   # main.rs:151-154
+        batch.process_pcm([np.zeros(999, np.int16)], PcmFormat.S16, 3)
+    with pytest.raises(ValueError, match="unknown PCM format"):
+        n = 1
+        rc = batch._lib.rsb_fir_process_pcm_batch(
+            batch._h, n, None, (C.c_void_p * n)(x.ctypes.data), (C.c_size_t * n)(500), 9, 2, 512, 0,
+            (C.c_void_p * n)(x.ctypes.data), (C.c_size_t * n)(0), None, None, None, 1, 0)
+        from resampler_b200.fir import _check
+        _check(rc)
+    from resampler_b200 import ResampleError
+    with pytest.raises(ResampleError):           # call_len not a multiple of channels
+        batch.process_pcm([x], PcmFormat.S16, 2, call_len=511)
+    batch.close()
+
+
+@pytest.mark.parametrize("kernel,fmt,src_ch", [
+    (Kernel.TENSOR, PcmFormat.S16, 2),
+    (Kernel.TENSOR, PcmFormat.S24, 1),
+    (Kernel.FAST, PcmFormat.S16, 1),
+])
+def test_device_resident_pcm_batch_fast_kernels(kernel, fmt, src_ch):
+    """64 equally long files resident on the device (raw bytes in HBM, one of the layouts
+    deliberately not 16-byte aligned): the converted staging buffer is equally strided, so the
+    tensor kernel takes it; samples within 1e-6 of the oracle, counts exact."""
+    ch, n, frames = 2, 64, 6007
+    lib = _lib.load()
+    rng = np.random.default_rng(77 + int(fmt))
+    raws = [raw_samples(rng, fmt, frames * src_ch) for _ in range(n)]
+    bps = fmt.bytes_per_sample()
+    raw_bytes = frames * src_ch * bps
+    stride = raw_bytes + 2 if fmt == PcmFormat.S16 else (raw_bytes + 15) & ~15   # s16: unaligned rows
+    d_raw = lib.rsb_alloc_device(0, stride * n + 16)
+    batch = FirBatch(n, ch, 44100, 48000, Latency.Sample64, Attenuation.Db90, kernel=kernel)
+    cap = int(frames * ch / batch.ratio()) + 4 * batch.buffer_size_output()
+    cap -= cap % 4
+    d_out = lib.rsb_alloc_device(0, cap * 4 * n)
+    assert d_raw and d_out
+    for i, r in enumerate(raws):
+        b = np.ascontiguousarray(r).view(np.uint8)
+        assert lib.rsb_memcpy(0, d_raw + i * stride, b.ctypes.data, b.nbytes, 0) == 0
+    cons, prod, calls = batch.process_pcm_ptrs(
+        [d_raw + i * stride for i in range(n)], [frames] * n, fmt, src_ch, 512, 0,
+        [d_out + i * cap * 4 for i in range(n)], [cap] * n, memspace=MEM_DEVICE)
+    assert batch.last_kernel() == kernel
+    assert batch.last_ingest_ms() > 0.0
+    worst = 0.0
+    for i in (0, 1, 31, 63):
+        _, ref = oracle_cli(ch, 44100, 48000, 3, raws[i], fmt, src_ch)
+        assert cons[i] == ref["consumed_total"] and prod[i] == len(ref["out"])
+        assert calls[i] == ref["calls"]
+        got = np.empty(prod[i], np.float32)
+        assert lib.rsb_memcpy(0, got.ctypes.data, d_out + i * cap * 4, got.nbytes, 1) == 0
+        worst = max(worst, float(np.max(np.abs(got.astype(np.float64) - ref["out"]))))
+    assert worst <= TOL, worst
+    lib.rsb_free_device(0, d_raw)
+    lib.rsb_free_device(0, d_out)
+    batch.close()

@@ -337,3 +337,35 @@ def test_c_oracle_matches_python_restatement(in_hz, out_hz):
                 assert np.array_equal(arr[:, 1], tr["phase1"])
                 assert np.array_equal(arr[:, 2], tr["phase2"])
                 assert np.array_equal(arr[:, 3], tr["frac_bits"])
+
+
+# ---------------------------------------------------------------------------------------------
+# CLI format step (resample/src/main.rs:128-156) -- the reference has no test for it; the
+# expected values are the exact quotients `s as f32 / 2^(bits-1)` worked out by hand
+# ---------------------------------------------------------------------------------------------
+def test_pcm_format_step_known_answers():
+    s16 = np.array([-32768, 32767, 0, 1, -1, 16384], np.int16)
+    assert np.array_equal(O.pcm_to_f32(s16, O.PCM_S16),
+                          np.array([-1.0, 32767 / 32768, 0.0, 2.0 ** -15, -(2.0 ** -15), 0.5],
+                                   np.float32))
+    u8 = np.array([0, 128, 255, 192], np.uint8)        # hound: unsigned on disk, minus 128
+    assert np.array_equal(O.pcm_to_f32(u8, O.PCM_U8),
+                          np.array([-1.0, 0.0, 127 / 128, 0.5], np.float32))
+    s24 = np.array([0x00, 0x00, 0x80,  0xFF, 0xFF, 0x7F,  0x00, 0x00, 0x40,  0xFF, 0xFF, 0xFF],
+                   np.uint8)                            # -2^23, 2^23-1, 2^22, -1
+    assert np.array_equal(O.pcm_to_f32(s24, O.PCM_S24),
+                          np.array([-1.0, (2 ** 23 - 1) / 2 ** 23, 0.5, -(2.0 ** -23)], np.float32))
+    # 32 bits: `(1 << 31) as f32` is an i32 shift = -2^31, so the CLI inverts the polarity;
+    # `s as f32` rounds 16777217 to 16777216 (nearest even) first
+    s32 = np.array([-(1 << 31), (1 << 31) - 1, 1 << 30, 16777217], np.int32)
+    assert np.array_equal(O.pcm_to_f32(s32, O.PCM_S32),
+                          np.array([1.0, -1.0, -0.5, -(16777216 / 2 ** 31)], np.float32))
+    f32 = np.array([0.25, -1.5, 3e-39], np.float32)     # passes through, denormal included
+    assert np.array_equal(O.pcm_to_f32(f32, O.PCM_F32).view(np.uint32), f32.view(np.uint32))
+
+
+def test_pcm_mono_to_stereo_duplication():
+    s16 = np.array([100, -200, 300], np.int16)          # main.rs:139-146
+    want = np.repeat(s16.astype(np.float32) / np.float32(32768.0), 2)
+    assert np.array_equal(O.pcm_to_f32(s16, O.PCM_S16, dup=2), want)
+    assert O.pcm_to_f32(np.zeros(0, np.int16), O.PCM_S16, dup=2).size == 0
