@@ -167,6 +167,16 @@ int rsb_fir_process_pcm_batch(rsb_fir *h, uint32_t n, const uint32_t *streams,
                               float *const *out, const size_t *out_capacities,
                               size_t *consumed_totals, size_t *produced_totals, uint32_t *n_calls,
                               int memspace, uint32_t flags);
+/* ---- opt-in tail handling (NOT in the reference) ----
+ * The reference never flushes: the last taps - 1 input frames stay in the history and the
+ * output lags by delay() = taps / 2 input frames (resampler_fir.rs:630-632).  This feeds
+ * delay() frames of silence to every listed stream -- exactly
+ * resample(&[0.0; delay * channels], out) per stream -- and appends what that produces
+ * (values, in produced[]) to out[i].  The streams' state carries on as after any other call.
+ * Synchronous. */
+int rsb_fir_flush_batch(rsb_fir *h, uint32_t n, const uint32_t *streams, float *const *out,
+                        const size_t *out_capacities, size_t *produced, int memspace,
+                        uint32_t flags);
 /* device time (ms, CUDA events) of the format-step kernel of the most recent PCM batch */
 int rsb_fir_last_ingest_ms(rsb_fir *h, float *ms);
 

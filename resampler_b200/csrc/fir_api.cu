@@ -146,7 +146,7 @@ struct rsb_fir {
     uint64_t submits = 0;             // ws[submits & 1] is the next one to use
     DevBuf d_stage_in, d_stage_out, d_dbg;   // host-memspace staging (those calls are synchronous)
     // PCM format step (rsb_fir_process_pcm_batch): raw samples of host-memspace calls, job table
-    DevBuf d_pcm_raw, d_pcm_jobs;
+    DevBuf d_pcm_raw, d_pcm_jobs, d_zero;
     PinBuf h_pcm_jobs;
     cudaEvent_t ev_pcm[2] = {};
     bool pcm_timed = false;
@@ -922,7 +922,7 @@ void rsb_fir_destroy(rsb_fir *h) {
         if (W.ev_plan) cudaEventDestroy(W.ev_plan);
         if (W.ev_done) cudaEventDestroy(W.ev_done);
     }
-    for (DevBuf *b : {&h->d_stage_in, &h->d_stage_out, &h->d_dbg, &h->d_pcm_raw, &h->d_pcm_jobs})
+    for (DevBuf *b : {&h->d_stage_in, &h->d_stage_out, &h->d_dbg, &h->d_pcm_raw, &h->d_pcm_jobs, &h->d_zero})
         b->release();
     h->h_pcm_jobs.release();
     for (cudaEvent_t e : h->ev_pcm) if (e) cudaEventDestroy(e);
@@ -1138,6 +1138,42 @@ int rsb_fir_process_pcm_batch(rsb_fir *h, uint32_t n, const uint32_t *streams,
     RSB_CUDA(cudaSetDevice(h->device));
     RSB_CUDA(cudaStreamSynchronize(h->stream));
     return run_batch(h, jobs, false, memspace, flags, consumed_totals, produced_totals, n_calls, &spec);
+}
+
+// Opt-in tail handling.  The reference never flushes: its last
+// taps - 1 input frames stay in the history and the output lags by delay() = taps / 2 input
+// frames (resampler_fir.rs:630-632).  Feeding delay() frames of silence emits the output whose
+// filter centre lies on the last real input frames; it is exactly
+// resample(&[0.0; delay * channels], ..) per stream, state carried on as after any call.
+int rsb_fir_flush_batch(rsb_fir *h, uint32_t n, const uint32_t *streams, float *const *out,
+                        const size_t *out_capacities, size_t *produced, int memspace,
+                        uint32_t flags) {
+    if (check_handle(h)) return RSB_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RSB_OK;
+    if (memspace != RSB_MEM_DEVICE && memspace != RSB_MEM_HOST)
+        return fail(RSB_ERR_INVALID_ARGUMENT, "bad memspace");
+    const size_t len = (size_t)(h->taps / 2) * h->channels;
+    std::vector<float> host_zero;
+    const float *zero = nullptr;
+    if (memspace == RSB_MEM_HOST) {
+        host_zero.assign(len, 0.0f);
+        zero = host_zero.data();
+    } else {
+        RSB_CUDA(cudaSetDevice(h->device));
+        if (!h->d_zero.p) {
+            RSB_CUDA(h->d_zero.reserve(64 * 64 * sizeof(float)));   // taps / 2 <= 64 frames, <= 64 ch
+            RSB_CUDA(cudaMemset(h->d_zero.p, 0, h->d_zero.cap));
+        }
+        if (len * sizeof(float) > h->d_zero.cap) {
+            RSB_CUDA(h->d_zero.reserve(len * sizeof(float)));
+            RSB_CUDA(cudaMemset(h->d_zero.p, 0, h->d_zero.cap));
+        }
+        zero = h->d_zero.as<float>();
+    }
+    std::vector<const float *> in(n, zero);
+    std::vector<size_t> lens(n, len);
+    return rsb_fir_process_batch(h, n, streams, in.data(), lens.data(), len, 0, out, out_capacities,
+                                 nullptr, produced, nullptr, memspace, flags & ~(uint32_t)RSB_FLAG_ASYNC);
 }
 
 int rsb_fir_last_ingest_ms(rsb_fir *h, float *ms) {

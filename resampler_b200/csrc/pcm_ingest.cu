@@ -55,90 +55,145 @@ __device__ __forceinline__ float cv_s24(const uint8_t *p) {
     return (float)((v << 8) >> 8) * (1.0f / 8388608.0f);
 }
 
-// the four source values behind output values [4q, 4q + 4): source index = output index / dup
+// ---- one 16-byte output piece = output values [4q, 4q + 4); source index = output index / dup.
+// A piece is fetched RAW (the 4 / dup source samples packed in at most four 32-bit registers)
+// and converted only when it is stored, so the loads a thread keeps in flight cost as few
+// registers as the format allows (s16 stereo: 2 per piece instead of 4).
 template <int FMT, int DUP>
-__device__ __forceinline__ float4 load4(const void *src, uint64_t q, bool aligned, uint32_t dup) {
-    using S = Src<FMT>;
-    using T = typename S::T;
-    const T *s = static_cast<const T *>(src);
-    float4 r;
-    if constexpr (DUP == 1) {
-        if (aligned) {
-            // 4 source values in one load of 4 * sizeof(T) bytes
-            struct alignas(4 * sizeof(T)) V { T v[4]; };
-            const V v = *reinterpret_cast<const V *>(s + 4 * q);
-            r = make_float4(S::cv(v.v[0]), S::cv(v.v[1]), S::cv(v.v[2]), S::cv(v.v[3]));
-        } else {
-            r = make_float4(S::cv(s[4 * q]), S::cv(s[4 * q + 1]), S::cv(s[4 * q + 2]), S::cv(s[4 * q + 3]));
-        }
-    } else if constexpr (DUP == 2) {
-        float a, b;
-        if (aligned) {
-            struct alignas(2 * sizeof(T)) V { T v[2]; };
-            const V v = *reinterpret_cast<const V *>(s + 2 * q);
-            a = S::cv(v.v[0]);
-            b = S::cv(v.v[1]);
-        } else {
-            a = S::cv(s[2 * q]);
-            b = S::cv(s[2 * q + 1]);
-        }
-        r = make_float4(a, a, b, b);
-    } else {
-        const uint64_t o = 4 * q;
-        r = make_float4(S::cv(s[o / dup]), S::cv(s[(o + 1) / dup]), S::cv(s[(o + 2) / dup]),
-                        S::cv(s[(o + 3) / dup]));
-    }
-    return r;
-}
+struct Piece {
+    using T = typename Src<FMT>::T;
+    static constexpr int kCnt = 4 / DUP;                      // source samples per piece
+    static constexpr int kBytes = kCnt * (int)sizeof(T);       // 2, 4, 8 or 16
+    static constexpr int kWords = (kBytes + 3) / 4;
+    struct Raw { uint32_t r[kWords]; };
 
+    static __device__ __forceinline__ Raw ld(const void *src, uint64_t q, bool aligned, uint32_t) {
+        const T *s = static_cast<const T *>(src) + (uint64_t)kCnt * q;
+        Raw v;
+        if (aligned) {
+            if constexpr (kBytes == 2) v.r[0] = *reinterpret_cast<const uint16_t *>(s);
+            else if constexpr (kBytes == 4) v.r[0] = *reinterpret_cast<const uint32_t *>(s);
+            else if constexpr (kBytes == 8) {
+                const uint2 w = *reinterpret_cast<const uint2 *>(s);
+                v.r[0] = w.x; v.r[1] = w.y;
+            } else {
+                const uint4 w = *reinterpret_cast<const uint4 *>(s);
+                v.r[0] = w.x; v.r[1] = w.y; v.r[2] = w.z; v.r[3] = w.w;
+            }
+        } else {
+#pragma unroll
+            for (int w = 0; w < kWords; ++w) v.r[w] = 0;
+#pragma unroll
+            for (int k = 0; k < kCnt; ++k) {
+                uint32_t e;
+                if constexpr (sizeof(T) == 4) e = reinterpret_cast<const uint32_t *>(s)[k];
+                else if constexpr (sizeof(T) == 2) e = reinterpret_cast<const uint16_t *>(s)[k];
+                else e = reinterpret_cast<const uint8_t *>(s)[k];
+                v.r[k * (int)sizeof(T) / 4] |= e << (8 * ((k * (int)sizeof(T)) % 4));
+            }
+        }
+        return v;
+    }
+    static __device__ __forceinline__ float elem(const Raw &v, int k) {
+        const uint32_t w = v.r[k * (int)sizeof(T) / 4] >> (8 * ((k * (int)sizeof(T)) % 4));
+        if constexpr (FMT == RSB_PCM_F32) return __uint_as_float(w);
+        else if constexpr (sizeof(T) == 4) return Src<FMT>::cv((T)w);
+        else if constexpr (sizeof(T) == 2) return Src<FMT>::cv((T)(uint16_t)w);
+        else return Src<FMT>::cv((T)(uint8_t)w);
+    }
+    static __device__ __forceinline__ float4 cv(const Raw &v) {
+        if constexpr (DUP == 1) return make_float4(elem(v, 0), elem(v, 1), elem(v, 2), elem(v, 3));
+        else {
+            const float a = elem(v, 0), b = elem(v, 1);
+            return make_float4(a, a, b, b);
+        }
+    }
+};
+
+// generic duplication factor (mono into 4 / 8 channels ...): converted on load
 template <int FMT>
-__device__ __forceinline__ float load1(const void *src, uint64_t i) {
-    return Src<FMT>::cv(static_cast<const typename Src<FMT>::T *>(src)[i]);
-}
+struct Piece<FMT, 0> {
+    using T = typename Src<FMT>::T;
+    struct Raw { float4 f; };
+    static __device__ __forceinline__ Raw ld(const void *src, uint64_t q, bool, uint32_t dup) {
+        const T *s = static_cast<const T *>(src);
+        const uint64_t o = 4 * q;
+        return Raw{make_float4(Src<FMT>::cv(s[o / dup]), Src<FMT>::cv(s[(o + 1) / dup]),
+                               Src<FMT>::cv(s[(o + 2) / dup]), Src<FMT>::cv(s[(o + 3) / dup]))};
+    }
+    static __device__ __forceinline__ float4 cv(const Raw &v) { return v.f; }
+};
 
 __device__ __forceinline__ float cv_s24_bits(uint32_t v) {
     return (float)((int)(v << 8) >> 8) * (1.0f / 8388608.0f);
 }
 
-template <int DUP>
-__device__ __forceinline__ float4 load4_s24(const void *src, uint64_t q, bool aligned, uint32_t dup) {
-    const uint8_t *s = static_cast<const uint8_t *>(src);
-    const uint64_t o = 4 * q;
-    if constexpr (DUP == 1) {
+// packed 24-bit: an aligned stereo piece is 12 bytes = three words; everything else goes
+// through byte loads and is converted on load
+template <>
+struct Piece<RSB_PCM_S24, 1> {
+    struct Raw { uint32_t r[3]; };
+    static __device__ __forceinline__ Raw ld(const void *src, uint64_t q, bool aligned, uint32_t) {
+        const uint8_t *s = static_cast<const uint8_t *>(src) + 12 * q;
+        Raw v;
         if (aligned) {
-            // 4 samples = 12 bytes = three aligned words
-            const uint32_t *w = reinterpret_cast<const uint32_t *>(s + 12 * q);
-            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-            return make_float4(cv_s24_bits(w0), cv_s24_bits((w0 >> 24) | (w1 << 8)),
-                               cv_s24_bits((w1 >> 16) | (w2 << 16)), cv_s24_bits(w2 >> 8));
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(s);
+            v.r[0] = w[0]; v.r[1] = w[1]; v.r[2] = w[2];
+        } else {
+#pragma unroll
+            for (int w = 0; w < 3; ++w)
+                v.r[w] = (uint32_t)s[4 * w] | ((uint32_t)s[4 * w + 1] << 8) |
+                         ((uint32_t)s[4 * w + 2] << 16) | ((uint32_t)s[4 * w + 3] << 24);
         }
+        return v;
     }
-    if constexpr (DUP == 1)
-        return make_float4(cv_s24(s + 3 * o), cv_s24(s + 3 * o + 3), cv_s24(s + 3 * o + 6),
-                           cv_s24(s + 3 * o + 9));
-    if constexpr (DUP == 2) {
-        const float a = cv_s24(s + 3 * (2 * q)), b = cv_s24(s + 3 * (2 * q + 1));
-        return make_float4(a, a, b, b);
+    static __device__ __forceinline__ float4 cv(const Raw &v) {
+        return make_float4(cv_s24_bits(v.r[0]), cv_s24_bits((v.r[0] >> 24) | (v.r[1] << 8)),
+                           cv_s24_bits((v.r[1] >> 16) | (v.r[2] << 16)), cv_s24_bits(v.r[2] >> 8));
     }
-    return make_float4(cv_s24(s + 3 * (o / dup)), cv_s24(s + 3 * ((o + 1) / dup)),
-                       cv_s24(s + 3 * ((o + 2) / dup)), cv_s24(s + 3 * ((o + 3) / dup)));
+};
+template <>
+struct Piece<RSB_PCM_S24, 2> {
+    struct Raw { float a, b; };
+    static __device__ __forceinline__ Raw ld(const void *src, uint64_t q, bool, uint32_t) {
+        const uint8_t *s = static_cast<const uint8_t *>(src) + 6 * q;
+        return Raw{cv_s24(s), cv_s24(s + 3)};
+    }
+    static __device__ __forceinline__ float4 cv(const Raw &v) { return make_float4(v.a, v.a, v.b, v.b); }
+};
+template <>
+struct Piece<RSB_PCM_S24, 0> {
+    struct Raw { float4 f; };
+    static __device__ __forceinline__ Raw ld(const void *src, uint64_t q, bool, uint32_t dup) {
+        const uint8_t *s = static_cast<const uint8_t *>(src);
+        const uint64_t o = 4 * q;
+        return Raw{make_float4(cv_s24(s + 3 * (o / dup)), cv_s24(s + 3 * ((o + 1) / dup)),
+                               cv_s24(s + 3 * ((o + 2) / dup)), cv_s24(s + 3 * ((o + 3) / dup)))};
+    }
+    static __device__ __forceinline__ float4 cv(const Raw &v) { return v.f; }
+};
+
+template <int FMT>
+__device__ __forceinline__ float load1(const void *src, uint64_t i) {
+    if constexpr (FMT == RSB_PCM_S24) return cv_s24(static_cast<const uint8_t *>(src) + 3 * i);
+    else return Src<FMT>::cv(static_cast<const typename Src<FMT>::T *>(src)[i]);
 }
 
 // One CTA walks chunks c = blockIdx.x, + gridDim.x, ...; chunk c belongs to the job j with
 // chunk_first[j] <= c < chunk_first[j + 1]: a division when every job has the same number of
 // chunks (cpj != 0), else a binary search (uniform per CTA).  A thread keeps kPer independent
 // loads in flight before its kPer 16-byte stores.
+// resident CTAs per SM the register allocation is asked to allow: five when a piece in flight is
+// at most two registers (40 warps keep 8 loads each in flight; six would spill), free otherwise
 template <int FMT, int DUP>
-__device__ __forceinline__ float4 load_piece(const PcmJob &J, uint64_t q, bool aligned, uint32_t dup) {
-    if constexpr (FMT == RSB_PCM_S24) return load4_s24<DUP>(J.src, q, aligned, dup);
-    else return load4<FMT, DUP>(J.src, q, aligned, dup);
-}
+constexpr int min_ctas() { return sizeof(typename Piece<FMT, DUP>::Raw) <= 8 ? 5 : 1; }
 
 template <int FMT, int DUP>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, min_ctas<FMT, DUP>())
 pcm_ingest_kernel(const PcmJob *__restrict__ jobs, const uint64_t *__restrict__ chunk_first,
                   uint32_t n_jobs, uint64_t n_chunks, uint32_t dup, uint64_t cpj) {
     constexpr uint32_t kPer = kChunkVec / kThreads;
+    using P = Piece<FMT, DUP>;
     for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
         uint32_t lo;
         uint64_t first;
@@ -159,32 +214,29 @@ pcm_ingest_kernel(const PcmJob *__restrict__ jobs, const uint64_t *__restrict__ 
         const uint64_t n_vec = J.n_out >> 2;   // whole float4 pieces of the job
         const bool aligned = J.src_aligned != 0;
         float4 *dst = reinterpret_cast<float4 *>(J.dst);
-        float4 v[kPer];
+        typename P::Raw v[kPer];
         if (q0 - threadIdx.x + kChunkVec <= n_vec) {   // interior chunk: no guards
 #pragma unroll
-            for (uint32_t k = 0; k < kPer; ++k) v[k] = load_piece<FMT, DUP>(J, q0 + k * kThreads, aligned, dup);
+            for (uint32_t k = 0; k < kPer; ++k) v[k] = P::ld(J.src, q0 + k * kThreads, aligned, dup);
 #pragma unroll
-            for (uint32_t k = 0; k < kPer; ++k) __stcs(dst + q0 + k * kThreads, v[k]);
+            for (uint32_t k = 0; k < kPer; ++k) __stcs(dst + q0 + k * kThreads, P::cv(v[k]));
             continue;
         }
 #pragma unroll
         for (uint32_t k = 0; k < kPer; ++k) {
             const uint64_t q = q0 + k * kThreads;
-            if (q < n_vec) v[k] = load_piece<FMT, DUP>(J, q, aligned, dup);
+            if (q < n_vec) v[k] = P::ld(J.src, q, aligned, dup);
         }
 #pragma unroll
         for (uint32_t k = 0; k < kPer; ++k) {
             const uint64_t q = q0 + k * kThreads;
-            if (q < n_vec) dst[q] = v[k];
+            if (q < n_vec) dst[q] = P::cv(v[k]);
         }
         // the job's last 1-3 values (this is the job's last chunk)
         const uint64_t tail0 = n_vec << 2;
         if (threadIdx.x < J.n_out - tail0) {
             const uint64_t o = tail0 + threadIdx.x;
-            float x;
-            if constexpr (FMT == RSB_PCM_S24) x = cv_s24(static_cast<const uint8_t *>(J.src) + 3 * (o / dup));
-            else x = load1<FMT>(J.src, o / dup);
-            J.dst[o] = x;
+            J.dst[o] = load1<FMT>(J.src, o / dup);
         }
     }
 }

@@ -331,6 +331,18 @@ class FirBatch:
             calls, memspace, flags))
         return cons, prod, calls
 
+    def flush(self, streams: Optional[Sequence[int]] = None):
+        """Opt-in tail handling (not in the reference): feeds ``delay()`` frames of silence to
+        the listed streams (default: all) and returns what that produces, one array each."""
+        n = len(streams) if streams is not None else self.n_streams
+        cap = self.buffer_size_output()
+        outs = [np.zeros(cap, np.float32) for _ in range(n)]
+        prod = (C.c_size_t * n)()
+        st = (C.c_uint32 * n)(*streams) if streams is not None else None
+        _check(self._lib.rsb_fir_flush_batch(self._h, n, st, _ptr_array([a.ctypes.data for a in outs]),
+                                             _size_array([cap] * n), prod, MEM_HOST, 0))
+        return [o[:prod[i]] for i, o in enumerate(outs)]
+
     def last_ingest_ms(self) -> float:
         """Device time of the format-step kernel of the most recent PCM batch."""
         ms = C.c_float(0)

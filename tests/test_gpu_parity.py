@@ -465,3 +465,28 @@ def test_device_memspace_async_and_full_size_properties():
     for s in (0, n - 1):
         ref = oracle_stream(ch, 44100, 48000, 3, 1, host[s], 512 * ch)
         assert np.array_equal(bits(outs[(Kernel.EXACT, "x")][s]), bits(ref["out"]))
+
+
+def test_flush_feeds_delay_frames_of_silence():
+    """Opt-in tail handling (not in the reference): flush == resample(zeros(delay * ch)),
+    checked against the oracle doing exactly that; the state carries on afterwards."""
+    ch, n = 2, 3
+    rng = np.random.default_rng(33)
+    xs = [noise(rng, L * ch) for L in (3000, 2500, 64)]
+    batch = FirBatch(n, ch, 44100, 48000, Latency.Sample64, Attenuation.Db90, kernel=Kernel.EXACT)
+    batch.process(xs, 512 * ch)
+    tails = batch.flush()
+    more = batch.process([xs[0][:400]] * n, 512 * ch)
+    for s in range(n):
+        f = O.OracleFir(ch, 44100, 48000, 3, 1)
+        f.process(xs[s], 512 * ch)
+        z = np.zeros(f.delay() * ch, np.float32)
+        ref = f.process(z, len(z))
+        assert len(tails[s]) == len(ref["out"]) and len(tails[s]) > 0
+        assert np.array_equal(bits(tails[s]), bits(ref["out"])), s
+        ref2 = f.process(xs[0][:400], 512 * ch)
+        assert np.array_equal(bits(more["out"][s]), bits(ref2["out"])), s
+    # a subset of the streams
+    t1 = batch.flush(streams=[1])
+    assert len(t1) == 1
+    batch.close()

@@ -196,3 +196,30 @@ def test_planner_start_states_with_drifted_positions():
             for key in ("input_offset", "phase1", "phase2", "frac_bits"):
                 assert np.array_equal(r[key], tr[key]), (key, it)
             pos_bits, avail = r["position_bits"], r["available"]
+
+
+# ---------------------------------------------------------------------------------------------
+# WAV container (host side of the CLI batch path)
+# ---------------------------------------------------------------------------------------------
+def test_wav_roundtrip_and_formats(tmp_path):
+    from resampler_b200 import PcmFormat
+    from resampler_b200.wav import read_wav, write_wav_f32, write_wav_pcm
+    rng = np.random.default_rng(3)
+    s16 = rng.integers(-32768, 32768, 2 * 101, dtype=np.int16)
+    write_wav_pcm(tmp_path / "a.wav", s16, 44100, 2, 16)
+    w = read_wav(tmp_path / "a.wav")
+    assert (w.sample_rate, w.channels, w.bits_per_sample, w.fmt, w.frames) == \
+        (44100, 2, 16, PcmFormat.S16, 101)
+    assert np.array_equal(w.raw.view(np.int16), s16)
+    s24 = rng.integers(0, 256, 3 * 77, dtype=np.uint8)          # mono, odd data size => pad byte
+    write_wav_pcm(tmp_path / "b.wav", s24, 48000, 1, 24)
+    w = read_wav(tmp_path / "b.wav")
+    assert (w.channels, w.fmt, w.frames) == (1, PcmFormat.S24, 77) and np.array_equal(w.raw, s24)
+    f = rng.uniform(-1, 1, 2 * 50).astype(np.float32)
+    write_wav_f32(tmp_path / "c.wav", f, 96000, 2)
+    w = read_wav(tmp_path / "c.wav")
+    assert (w.sample_rate, w.fmt, w.frames) == (96000, PcmFormat.F32, 50)
+    assert np.array_equal(w.raw.view(np.float32), f)
+    (tmp_path / "d.wav").write_bytes(b"RIFX0000WAVE")
+    with pytest.raises(ValueError):
+        read_wav(tmp_path / "d.wav")
