@@ -297,7 +297,9 @@ class FirBatch:
         fmt = PcmFormat(fmt)
         n = len(inputs)
         bps = fmt.bytes_per_sample()
-        inputs = [np.ascontiguousarray(a, _PCM_DTYPES[fmt]) for a in inputs]
+        # uint8 arrays are taken as the file's raw bytes, anything else as sample values
+        inputs = [np.ascontiguousarray(a) if a.dtype == np.uint8
+                  else np.ascontiguousarray(a, _PCM_DTYPES[fmt]) for a in map(np.asarray, inputs)]
         frames = []
         for a in inputs:
             if a.nbytes % (bps * src_channels) != 0:
