@@ -83,6 +83,27 @@ class FirBatch {
                                     call_len, 0, out.data(), out_capacities.data(), consumed.data(),
                                     produced.data(), nullptr, memspace, flags));
     }
+    // The CLI's batch path (resample/src/main.rs:128-156 + 226-254): raw samples in, the
+    // format step and the canonical loop on the GPU.  in_frames are source frames.
+    void process_pcm(const std::vector<const void *> &in, const std::vector<size_t> &in_frames,
+                     rsb_pcm_format format, uint32_t src_channels, size_t call_len,
+                     const std::vector<float *> &out, const std::vector<size_t> &out_capacities,
+                     std::vector<size_t> &consumed, std::vector<size_t> &produced,
+                     int memspace = RSB_MEM_HOST) {
+        consumed.assign(in.size(), 0);
+        produced.assign(in.size(), 0);
+        check(rsb_fir_process_pcm_batch(h_, (uint32_t)in.size(), nullptr, in.data(), in_frames.data(),
+                                        format, src_channels, call_len, 0, out.data(),
+                                        out_capacities.data(), consumed.data(), produced.data(),
+                                        nullptr, memspace, 0));
+    }
+    // Opt-in tail handling (not in the reference): delay() frames of silence per stream.
+    void flush(const std::vector<float *> &out, const std::vector<size_t> &out_capacities,
+               std::vector<size_t> &produced, int memspace = RSB_MEM_HOST) {
+        produced.assign(out.size(), 0);
+        check(rsb_fir_flush_batch(h_, (uint32_t)out.size(), nullptr, out.data(), out_capacities.data(),
+                                  produced.data(), memspace, 0));
+    }
     void sync() { check(rsb_fir_sync(h_)); }
     rsb_fir *raw() { return h_; }
 

@@ -40,6 +40,15 @@ unsafe extern "C" {
                              out: *const *mut f32, out_capacities: *const usize,
                              consumed_totals: *mut usize, produced_totals: *mut usize,
                              n_calls: *mut u32, memspace: c_int, flags: u32) -> c_int;
+    fn rsb_fir_process_pcm_batch(h: *mut RsbFir, n: u32, streams: *const u32, inp: *const *const c_void,
+                                 in_frames: *const usize, format: c_int, src_channels: u32,
+                                 call_len: usize, out_cap_len: usize, out: *const *mut f32,
+                                 out_capacities: *const usize, consumed_totals: *mut usize,
+                                 produced_totals: *mut usize, n_calls: *mut u32, memspace: c_int,
+                                 flags: u32) -> c_int;
+    fn rsb_fir_flush_batch(h: *mut RsbFir, n: u32, streams: *const u32, out: *const *mut f32,
+                           out_capacities: *const usize, produced: *mut usize, memspace: c_int,
+                           flags: u32) -> c_int;
     fn rsb_fir_sync(h: *mut RsbFir) -> c_int;
     fn rsb_alloc_pinned(bytes: usize) -> *mut c_void;
     fn rsb_free_pinned(p: *mut c_void);
@@ -104,6 +113,44 @@ impl FirBatch {
                                  RSB_MEM_HOST, 0)
         })?;
         Ok(c.into_iter().zip(p).collect())
+    }
+    /// The CLI's batch path for many files at once (resample/src/main.rs:128-156 + 226-254):
+    /// `inputs[i]` are one file's raw little-endian sample bytes as hound would decode them
+    /// (`format`: 0 = u8, 1 = s16, 2 = packed s24, 3 = s32, 4 = f32), `src_channels` 1 (mono,
+    /// duplicated into every channel on the GPU) or `channels`.  Output vectors hold the
+    /// resampled interleaved f32 signal of each file (512-value calls like the CLI).
+    pub fn process_pcm(&mut self, inputs: &[&[u8]], format: i32, src_channels: u32)
+                       -> Result<Vec<Vec<f32>>, ResampleError> {
+        let n = inputs.len();
+        let bps = [1usize, 2, 3, 4, 4][format as usize];
+        let frames: Vec<usize> = inputs.iter().map(|b| b.len() / (bps * src_channels as usize)).collect();
+        let ratio_bound = self.buffer_size_output() / self.channels;   // frames per 4096-frame call
+        let caps: Vec<usize> = frames.iter()
+            .map(|f| ((f / 3968 + 2) * ratio_bound + 8) * self.channels).collect();
+        let mut outs: Vec<Vec<f32>> = caps.iter().map(|c| vec![0.0f32; *c]).collect();
+        let in_ptrs: Vec<*const c_void> = inputs.iter().map(|b| b.as_ptr() as *const c_void).collect();
+        let out_ptrs: Vec<*mut f32> = outs.iter_mut().map(|v| v.as_mut_ptr()).collect();
+        let mut produced = vec![0usize; n];
+        map_err(unsafe {
+            rsb_fir_process_pcm_batch(self.h, n as u32, std::ptr::null(), in_ptrs.as_ptr(), frames.as_ptr(),
+                                      format, src_channels, 512, 0, out_ptrs.as_ptr(), caps.as_ptr(),
+                                      std::ptr::null_mut(), produced.as_mut_ptr(), std::ptr::null_mut(),
+                                      RSB_MEM_HOST, 0)
+        })?;
+        for (v, p) in outs.iter_mut().zip(&produced) { v.truncate(*p); }
+        Ok(outs)
+    }
+    /// Opt-in tail handling (not in the reference): `delay()` frames of silence per stream.
+    pub fn flush(&mut self, outputs: &mut [&mut [f32]]) -> Result<Vec<usize>, ResampleError> {
+        let n = outputs.len();
+        let out_ptrs: Vec<*mut f32> = outputs.iter_mut().map(|s| s.as_mut_ptr()).collect();
+        let caps: Vec<usize> = outputs.iter().map(|s| s.len()).collect();
+        let mut produced = vec![0usize; n];
+        map_err(unsafe {
+            rsb_fir_flush_batch(self.h, n as u32, std::ptr::null(), out_ptrs.as_ptr(), caps.as_ptr(),
+                                produced.as_mut_ptr(), RSB_MEM_HOST, 0)
+        })?;
+        Ok(produced)
     }
     pub fn channels(&self) -> usize { self.channels }
 }
