@@ -51,6 +51,7 @@ SIGNATURES = {
                                             C.c_uint32]),
     "rsb_fir_flush_batch": (C.c_int, [C.c_void_p, C.c_uint32, u32p, C.POINTER(C.c_void_p), szp, szp,
                                       C.c_int, C.c_uint32]),
+    "rsb_fir_last_pcm_fused": (C.c_int, [C.c_void_p]),
     "rsb_fir_last_ingest_ms": (C.c_int, [C.c_void_p, f32p]),
     "rsb_fir_sync": (C.c_int, [C.c_void_p]),
     "rsb_fir_last_call_counts": (C.c_int, [C.c_void_p, C.c_uint32, u32p, u32p, C.c_size_t, szp]),

@@ -150,6 +150,7 @@ struct rsb_fir {
     PinBuf h_pcm_jobs;
     cudaEvent_t ev_pcm[2] = {};
     bool pcm_timed = false;
+    bool pcm_fused_last = false;   // the last PCM batch ran with the format step inside the tensor kernel
     Workspace &last_ws() { return ws[(submits + 1) & 1]; }
 };
 
@@ -573,9 +574,10 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
         if (in_pitch < (ptrdiff_t)(in_vals[0] * sizeof(float))) h2d_uniform = false;
         if (out_pitch <= 0) d2h_uniform = false;
     }
+    bool pcm_fused = false;   // the tensor kernel reads the raw s16 frames itself
     if (pcm) {
         // ---- format step: raw samples -> interleaved f32 frames in d_stage_in ----
-        uint64_t n_chunks = 0, chunks_per_job = rsb::pcm_chunks(in_vals[0]);
+        uint64_t n_chunks = 0, chunks_per_job = 0;
         RSB_CUDA(h->h_pcm_jobs.reserve(sizeof(rsb::PcmJob) * n + sizeof(uint64_t) * (n + 1)));
         RSB_CUDA(h->d_pcm_jobs.reserve(sizeof(rsb::PcmJob) * n + sizeof(uint64_t) * (n + 1)));
         rsb::PcmJob *pj = h->h_pcm_jobs.as<rsb::PcmJob>();
@@ -609,9 +611,42 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
             pj[i].n_out = in_vals[i];
             pj[i].src_aligned = (reinterpret_cast<uintptr_t>(src) & 15u) == 0 ? 1u : 0u;
             pj[i].pad_ = 0;
+        }
+        // Stereo s16 batches that run on the tensor kernel skip the format pass: the kernel's TMA
+        // producer streams the RAW frames (tensor map over the raw rows) and its splitter
+        // converts them.  Only the last 4096 frames of every stream are still converted here,
+        // for the history update (update_state_kernel reads them as f32).
+        pcm_fused = false;
+        if (use_tc && host_plan && pcm->format == RSB_PCM_S16 && pcm->dup == 1 && ch == 2 &&
+            !getenv("RSB_PCM_UNFUSED")) {
+            const uintptr_t base = reinterpret_cast<uintptr_t>(pj[0].src);
+            const uint64_t stride = n > 1 ? (uint64_t)(reinterpret_cast<uintptr_t>(pj[1].src) - base)
+                                          : (((uint64_t)in_vals[0] * 2 + 15) & ~15ull);
+            bool ok = n == 1 || reinterpret_cast<uintptr_t>(pj[1].src) > base;
+            for (uint32_t i = 1; ok && i < n; ++i)
+                ok = reinterpret_cast<uintptr_t>(pj[i].src) == base + (uint64_t)i * stride;
+            // jobs are grouped by unit in hj; one unit => hj order == job order
+            CUtensorMap raw_map;
+            if (ok && rsb::tc_make_raw16_tensor_map(&raw_map, pj[0].src, stride,
+                                                    unit_keys[0].total_frames, n)) {
+                tc_tmap = raw_map;
+                pcm_fused = true;
+            }
+        }
+        if (pcm_fused) {
+            const uint64_t copied = hu[0].total_copied;
+            const uint64_t start = (copied > rsb::kHistFrames ? copied - rsb::kHistFrames : 0) & ~3ull;
+            for (uint32_t i = 0; i < n; ++i) {
+                pj[i].src = static_cast<const char *>(pj[i].src) + start * 4;   // 4-byte frames
+                pj[i].dst += start * 2;
+                pj[i].n_out -= start * 2;
+            }
+        }
+        chunks_per_job = rsb::pcm_chunks(pj[0].n_out);
+        for (uint32_t i = 0; i < n; ++i) {
             cf[i] = n_chunks;
-            n_chunks += rsb::pcm_chunks(in_vals[i]);
-            if (rsb::pcm_chunks(in_vals[i]) != rsb::pcm_chunks(in_vals[0])) chunks_per_job = 0;
+            n_chunks += rsb::pcm_chunks(pj[i].n_out);
+            if (rsb::pcm_chunks(pj[i].n_out) != chunks_per_job) chunks_per_job = 0;
         }
         cf[n] = n_chunks;
         RSB_CUDA(cudaMemcpyAsync(h->d_pcm_jobs.p, pj, sizeof(rsb::PcmJob) * n + sizeof(uint64_t) * (n + 1),
@@ -622,6 +657,7 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
                                n_chunks, chunks_per_job, pcm->format, pcm->dup, h->sm_count, s);
         RSB_CUDA(cudaEventRecord(h->ev_pcm[1], s));
         h->pcm_timed = n_chunks != 0;
+        h->pcm_fused_last = pcm_fused;
         if (n_chunks) h->launches += 1;
     } else if (host_mem) {
         if (h2d_uniform && in_vals[0]) {
@@ -720,6 +756,7 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
         if (getenv("RSB_TC_RUN_TILES")) T.run_tiles = (uint32_t)atoi(getenv("RSB_TC_RUN_TILES"));
         T.kt_max = rsb::tc_kt_extent(h->taps, h->ratio);
         T.issuers = rsb::tc_issuers(h->taps, h->ratio);
+        T.raw16 = pcm_fused ? 1u : 0u;
         if (getenv("RSB_TC_ISSUERS")) T.issuers = atoi(getenv("RSB_TC_ISSUERS")) == 1 ? 1u : T.issuers;
         rsb::launch_conv_tc(T, tc_tmap, h->sm_count, !host_plan, s);
     } else if (use_fast) {
@@ -1175,6 +1212,8 @@ int rsb_fir_flush_batch(rsb_fir *h, uint32_t n, const uint32_t *streams, float *
     return rsb_fir_process_batch(h, n, streams, in.data(), lens.data(), len, 0, out, out_capacities,
                                  nullptr, produced, nullptr, memspace, flags & ~(uint32_t)RSB_FLAG_ASYNC);
 }
+
+int rsb_fir_last_pcm_fused(const rsb_fir *h) { return h && h->pcm_fused_last ? 1 : 0; }
 
 int rsb_fir_last_ingest_ms(rsb_fir *h, float *ms) {
     if (check_handle(h)) return RSB_ERR_INVALID_ARGUMENT;

@@ -95,6 +95,8 @@ struct TcParams {
     uint32_t run_tiles;       // consecutive tiles per work item
     uint32_t kt_max;
     uint32_t issuers;         // MMA issuer warps: 2 when two consecutive tiles fit the TMEM ring
+    uint32_t raw16;           // stereo only: the tensor map covers RAW s16 frames (4 bytes each);
+                              // the splitter converts them (v / 32768, main.rs:131-136) itself
 };
 bool tc_supported(uint32_t channels, uint32_t taps, double ratio);
 uint32_t tc_kt_extent(uint32_t taps, double ratio);
@@ -104,6 +106,10 @@ uint32_t tc_issuers(uint32_t taps, double ratio);
 // 2-D tensor map over equally strided member inputs: box = 16 frames x (128 / channels) members
 bool tc_make_input_tensor_map(CUtensorMap *out, const float *base, uint64_t stride_bytes,
                               uint64_t total_frames, uint32_t n_members, uint32_t channels);
+// The same over raw interleaved s16 stereo frames (element = one 4-byte frame, box = 16 frames
+// x 64 members, 64B swizzle): the format step fused into the tensor kernel's loader.
+bool tc_make_raw16_tensor_map(CUtensorMap *out, const void *base, uint64_t stride_bytes,
+                              uint64_t total_frames, uint32_t n_members);
 void launch_tc_gmat(const UnitDev *units, const TileRec *tiles, const PlanEntry *entries,
                     const float *coeffs, float *gmat, TcTile *tct, uint32_t taps, double ratio,
                     uint32_t tile_cap, cudaStream_t stream);

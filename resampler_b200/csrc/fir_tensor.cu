@@ -129,10 +129,13 @@ struct TcSmem {
     uint32_t tmem_base;
 };
 
-template <int CH>
+template <int CH, bool RAW16 = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUtensorMap tmap) {
     static_assert(CH == 1 || CH == 2 || CH == 4 || CH == 8, "tensor kernel: 1, 2, 4 or 8 channels");
+    static_assert(!RAW16 || CH == 2, "raw s16 input: stereo only");
+    // bytes one input chunk lands in shared memory: f32 rows, or 64 members x 16 raw 4-byte frames
+    constexpr uint32_t kXLandBytes = RAW16 ? (kRows / CH) * kChunk * 4u : kXStageBytes;
     constexpr uint32_t kMpg = kRows / CH;               // members per group
     extern __shared__ __align__(1024) uint8_t smem_tc[];
     __shared__ TcSmem S;
@@ -227,7 +230,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                     if (v < H) continue;       // touches the history: the splitter loads it itself
                     const uint32_t s = xs_seq % kXStages;
                     mbar_wait(&S.xs_empty[s], ((xs_seq / kXStages) & 1u) ^ 1u);
-                    mbar_arrive_expect_tx(&S.xs_full[s], kXStageBytes);
+                    mbar_arrive_expect_tx(&S.xs_full[s], kXLandBytes);
                     // inner coordinate in tensor-map elements: frames (mono f32, stereo 8-byte
                     // frames) or floats (4 / 8 channels)
                     tensor_g2s_2d(xst + s * kXStageBytes, &tmap, (v - H) * (CH >= 4 ? CH : 1), m0,
@@ -430,7 +433,23 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                     __syncwarp();
                     rc.lap(6);
                     const uint32_t base = smem_u32(xst + s * kXStageBytes);
-                    if (CH == 2) {
+                    if (RAW16) {
+                        // raw s16 stereo: 64-byte rows (16 frames of 2 x s16), 64B swizzle: unit u
+                        // at u ^ ((row >> 1) & 3); a word is one frame, the channel picks its half;
+                        // s / 2^15 is the reference's `s as f32 / 32768.0` (main.rs:131-136)
+                        const uint32_t rb = base + ml * 64u;
+#pragma unroll
+                        for (uint32_t u = 0; u < 2; ++u) {
+                            const float4 q4 = lds128(rb + (((u + 2 * wg) ^ ((ml >> 1) & 3u)) << 4));
+                            const uint32_t w[4] = {__float_as_uint(q4.x), __float_as_uint(q4.y),
+                                                   __float_as_uint(q4.z), __float_as_uint(q4.w)};
+#pragma unroll
+                            for (uint32_t k = 0; k < 4; ++k) {
+                                const int sv = c ? (int)w[k] >> 16 : (int)(short)(w[k] & 0xffffu);
+                                x[4 * u + k] = (float)sv * (1.0f / 32768.0f);
+                            }
+                        }
+                    } else if (CH == 2) {
                         // 128-byte rows (16 stereo frames), 128B swizzle: unit u at u ^ (row & 7)
                         const uint32_t rb = base + ml * 128u;
 #pragma unroll
@@ -722,6 +741,35 @@ bool tc_make_input_tensor_map(CUtensorMap *out, const float *base, uint64_t stri
     return r == CUDA_SUCCESS;
 }
 
+bool tc_make_raw16_tensor_map(CUtensorMap *out, const void *base, uint64_t stride_bytes,
+                              uint64_t total_frames, uint32_t n_members) {
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                      const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                      const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        !fn) {
+        cudaGetLastError();
+        return false;
+    }
+    if (total_frames == 0 || total_frames >= (1ull << 31)) return false;
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) || (stride_bytes & 15u) || stride_bytes == 0)
+        return false;
+    if (stride_bytes < total_frames * 4ull) return false;
+    cuuint64_t dims[2] = {total_frames, n_members};
+    cuuint64_t strides[1] = {stride_bytes};
+    cuuint32_t box[2] = {kChunk, (cuuint32_t)(kRows / 2)};
+    cuuint32_t estr[2] = {1, 1};
+    // element = one raw stereo frame (two s16 = 32 bits); frames past the end read as zeros
+    const CUresult r = ((EncodeTiledFn)fn)(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(base),
+                                           dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 void launch_tc_gmat(const UnitDev *units, const TileRec *tiles, const PlanEntry *entries,
                     const float *coeffs, float *gmat, TcTile *tct, uint32_t taps, double ratio,
                     uint32_t tile_cap, cudaStream_t stream) {
@@ -747,7 +795,10 @@ void launch_conv_tc(const TcParams &p, const CUtensorMap &tmap, int sm_count, bo
     };
     switch (p.channels) {
         case 1: launch(conv_tc_kernel<1>); break;
-        case 2: launch(conv_tc_kernel<2>); break;
+        case 2:
+            if (p.raw16) launch(conv_tc_kernel<2, true>);
+            else launch(conv_tc_kernel<2>);
+            break;
         case 4: launch(conv_tc_kernel<4>); break;
         default: launch(conv_tc_kernel<8>); break;
     }

@@ -345,6 +345,10 @@ class FirBatch:
                                              _size_array([cap] * n), prod, MEM_HOST, 0))
         return [o[:prod[i]] for i, o in enumerate(outs)]
 
+    def last_pcm_fused(self) -> bool:
+        """True when the last PCM batch was converted inside the tensor kernel's loader."""
+        return bool(self._lib.rsb_fir_last_pcm_fused(self._h))
+
     def last_ingest_ms(self) -> float:
         """Device time of the format-step kernel of the most recent PCM batch."""
         ms = C.c_float(0)

@@ -133,48 +133,88 @@ def test_errors():
     batch.close()
 
 
-@pytest.mark.parametrize("kernel,fmt,src_ch", [
-    (Kernel.TENSOR, PcmFormat.S16, 2),
-    (Kernel.TENSOR, PcmFormat.S24, 1),
-    (Kernel.FAST, PcmFormat.S16, 1),
+@pytest.mark.parametrize("kernel,fmt,src_ch,aligned", [
+    (Kernel.TENSOR, PcmFormat.S16, 2, True),     # format step fused into the tensor kernel
+    (Kernel.TENSOR, PcmFormat.S16, 2, False),    # rows not 16-byte aligned: separate format pass
+    (Kernel.TENSOR, PcmFormat.S24, 1, True),
+    (Kernel.FAST, PcmFormat.S16, 1, True),
 ])
-def test_device_resident_pcm_batch_fast_kernels(kernel, fmt, src_ch):
-    """64 equally long files resident on the device (raw bytes in HBM, one of the layouts
-    deliberately not 16-byte aligned): the converted staging buffer is equally strided, so the
-    tensor kernel takes it; samples within 1e-6 of the oracle, counts exact."""
+def test_device_resident_pcm_batch_fast_kernels(kernel, fmt, src_ch, aligned):
+    """64 equally long files resident on the device (raw bytes in HBM): the converted staging
+    buffer is equally strided, so the tensor kernel takes it; stereo s16 rows that are 16-byte
+    aligned are converted inside the tensor kernel's loader.  Samples within 1e-6 of the oracle,
+    counts exact; a second batch checks the history written from the raw tail."""
     ch, n, frames = 2, 64, 6007
     lib = _lib.load()
     rng = np.random.default_rng(77 + int(fmt))
     raws = [raw_samples(rng, fmt, frames * src_ch) for _ in range(n)]
+    raws2 = [raw_samples(rng, fmt, 1500 * src_ch) for _ in range(n)]
     bps = fmt.bytes_per_sample()
     raw_bytes = frames * src_ch * bps
-    stride = raw_bytes + 2 if fmt == PcmFormat.S16 else (raw_bytes + 15) & ~15   # s16: unaligned rows
+    stride = (raw_bytes + 15) & ~15 if aligned else raw_bytes + 2
     d_raw = lib.rsb_alloc_device(0, stride * n + 16)
     batch = FirBatch(n, ch, 44100, 48000, Latency.Sample64, Attenuation.Db90, kernel=kernel)
     cap = int(frames * ch / batch.ratio()) + 4 * batch.buffer_size_output()
     cap -= cap % 4
     d_out = lib.rsb_alloc_device(0, cap * 4 * n)
     assert d_raw and d_out
-    for i, r in enumerate(raws):
-        b = np.ascontiguousarray(r).view(np.uint8)
-        assert lib.rsb_memcpy(0, d_raw + i * stride, b.ctypes.data, b.nbytes, 0) == 0
-    cons, prod, calls = batch.process_pcm_ptrs(
-        [d_raw + i * stride for i in range(n)], [frames] * n, fmt, src_ch, 512, 0,
-        [d_out + i * cap * 4 for i in range(n)], [cap] * n, memspace=MEM_DEVICE)
+
+    def run(rs, nf):
+        for i, r in enumerate(rs):
+            b = np.ascontiguousarray(r).view(np.uint8)
+            assert lib.rsb_memcpy(0, d_raw + i * stride, b.ctypes.data, b.nbytes, 0) == 0
+        return batch.process_pcm_ptrs(
+            [d_raw + i * stride for i in range(n)], [nf] * n, fmt, src_ch, 512, 0,
+            [d_out + i * cap * 4 for i in range(n)], [cap] * n, memspace=MEM_DEVICE)
+
+    def fetch(i, count):
+        got = np.empty(count, np.float32)
+        assert lib.rsb_memcpy(0, got.ctypes.data, d_out + i * cap * 4, got.nbytes, 1) == 0
+        return got
+
+    cons, prod, calls = run(raws, frames)
     assert batch.last_kernel() == kernel
     assert batch.last_ingest_ms() > 0.0
+    assert batch.last_pcm_fused() == (kernel == Kernel.TENSOR and fmt == PcmFormat.S16
+                                      and src_ch == 2 and aligned)
+    firsts = {i: fetch(i, prod[i]) for i in (0, 1, 31, 63)}
+    cons2, prod2, _ = run(raws2, 1500)
     worst = 0.0
     for i in (0, 1, 31, 63):
-        _, ref = oracle_cli(ch, 44100, 48000, 3, raws[i], fmt, src_ch)
+        x = O.pcm_to_f32(raws[i], int(fmt), 1 if src_ch == ch else ch)
+        x2 = O.pcm_to_f32(raws2[i], int(fmt), 1 if src_ch == ch else ch)
+        f = O.OracleFir(ch, 44100, 48000, 3, 1)
+        ref = f.process(x, 512)
+        ref2 = f.process(x2, 512)
         assert cons[i] == ref["consumed_total"] and prod[i] == len(ref["out"])
         assert calls[i] == ref["calls"]
-        got = np.empty(prod[i], np.float32)
-        assert lib.rsb_memcpy(0, got.ctypes.data, d_out + i * cap * 4, got.nbytes, 1) == 0
-        worst = max(worst, float(np.max(np.abs(got.astype(np.float64) - ref["out"]))))
+        assert cons2[i] == ref2["consumed_total"] and prod2[i] == len(ref2["out"])
+        worst = max(worst, float(np.max(np.abs(firsts[i].astype(np.float64) - ref["out"]))))
+        worst = max(worst, float(np.max(np.abs(fetch(i, prod2[i]).astype(np.float64) - ref2["out"]))))
     assert worst <= TOL, worst
     lib.rsb_free_device(0, d_raw)
     lib.rsb_free_device(0, d_out)
     batch.close()
+
+
+def test_fused_and_separate_format_step_agree_bit_for_bit(monkeypatch):
+    """The tensor kernel converting raw s16 frames in its loader and the separate format pass
+    feed the same f32 values into the same arithmetic: identical output bits (host buffers)."""
+    ch, n, frames = 2, 64, 5000
+    rng = np.random.default_rng(123)
+    raws = [raw_samples(rng, PcmFormat.S16, frames * ch) for _ in range(n)]
+    outs = []
+    for unfused in (False, True):
+        if unfused:
+            monkeypatch.setenv("RSB_PCM_UNFUSED", "1")
+        batch = FirBatch(n, ch, 44100, 48000, Latency.Sample64, Attenuation.Db90, kernel=Kernel.TENSOR)
+        res = batch.process_pcm(raws, PcmFormat.S16, ch)
+        assert batch.last_pcm_fused() == (not unfused)
+        tail = batch.flush()
+        outs.append([np.concatenate([a, b]) for a, b in zip(res["out"], tail)])
+        batch.close()
+    for a, b in zip(*outs):
+        assert np.array_equal(bits(a), bits(b))
 
 
 def test_wav_files_end_to_end(tmp_path):
