@@ -74,7 +74,8 @@ enum rsb_kernel { RSB_KERNEL_AUTO = 0, RSB_KERNEL_EXACT = 1, RSB_KERNEL_FAST = 2
 
 enum rsb_flags {
     RSB_FLAG_NONE = 0,
-    RSB_FLAG_ASYNC = 1,        /* device memspace only: return after enqueueing.  The count
+    RSB_FLAG_ASYNC = 1,        /* device memspace only: return after enqueueing (without it a call
+                                  returns when its outputs are complete).  The count
                                   arrays are written by rsb_fir_sync() or by the second
                                   submit after this one (two submits may be in flight), so
                                   they must stay valid until then */
@@ -159,8 +160,8 @@ enum rsb_pcm_format { RSB_PCM_U8 = 0, RSB_PCM_S16 = 1, RSB_PCM_S24 = 2, RSB_PCM_
  * :151-154).  The conversion runs on the GPU (one pass, pcm_ingest.cu) into a staging buffer
  * owned by the handle; host memspace moves the RAW samples over PCIe (half the bytes of f32
  * for 16-bit sources).  call_len, out_cap_len, consumed_totals and produced_totals are in f32
- * values of the converted signal (the CLI uses call_len = 512).  Synchronous
- * (RSB_FLAG_ASYNC is rejected). */
+ * values of the converted signal (the CLI uses call_len = 512).  RSB_FLAG_ASYNC as for
+ * rsb_fir_process_batch (device memspace; the raw buffers must stay valid until the sync). */
 int rsb_fir_process_pcm_batch(rsb_fir *h, uint32_t n, const uint32_t *streams,
                               const void *const *in, const size_t *in_frames, int format,
                               uint32_t src_channels, size_t call_len, size_t out_cap_len,

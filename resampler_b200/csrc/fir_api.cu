@@ -97,6 +97,8 @@ struct Pending {
 struct Workspace {
     DevBuf d_units, d_jobs, d_segs, d_calls, d_tiles, d_entries, d_gtiles, d_tct, d_counter;
     PinBuf h_units, h_jobs, h_units_back, h_calls_back, h_segs, h_counter;
+    DevBuf d_pcm_jobs;   // job table of the PCM format step (rsb_fir_process_pcm_batch)
+    PinBuf h_pcm_jobs;
     std::vector<uint32_t> job_unit;          // unit of each job of the batch
     std::vector<uint32_t> job_stream;        // stream of each job of the batch
     bool host_planned = false;               // the plan ran on the host: results already mirrored
@@ -145,9 +147,8 @@ struct rsb_fir {
     Workspace ws[2];
     uint64_t submits = 0;             // ws[submits & 1] is the next one to use
     DevBuf d_stage_in, d_stage_out, d_dbg;   // host-memspace staging (those calls are synchronous)
-    // PCM format step (rsb_fir_process_pcm_batch): raw samples of host-memspace calls, job table
-    DevBuf d_pcm_raw, d_pcm_jobs, d_zero;
-    PinBuf h_pcm_jobs;
+    // PCM format step (rsb_fir_process_pcm_batch): raw samples of host-memspace calls
+    DevBuf d_pcm_raw, d_zero;
     cudaEvent_t ev_pcm[2] = {};
     bool pcm_timed = false;
     bool pcm_fused_last = false;   // the last PCM batch ran with the format step inside the tensor kernel
@@ -578,9 +579,9 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     if (pcm) {
         // ---- format step: raw samples -> interleaved f32 frames in d_stage_in ----
         uint64_t n_chunks = 0, chunks_per_job = 0;
-        RSB_CUDA(h->h_pcm_jobs.reserve(sizeof(rsb::PcmJob) * n + sizeof(uint64_t) * (n + 1)));
-        RSB_CUDA(h->d_pcm_jobs.reserve(sizeof(rsb::PcmJob) * n + sizeof(uint64_t) * (n + 1)));
-        rsb::PcmJob *pj = h->h_pcm_jobs.as<rsb::PcmJob>();
+        RSB_CUDA(W.h_pcm_jobs.reserve(sizeof(rsb::PcmJob) * n + sizeof(uint64_t) * (n + 1)));
+        RSB_CUDA(W.d_pcm_jobs.reserve(sizeof(rsb::PcmJob) * n + sizeof(uint64_t) * (n + 1)));
+        rsb::PcmJob *pj = W.h_pcm_jobs.as<rsb::PcmJob>();
         uint64_t *cf = reinterpret_cast<uint64_t *>(pj + n);
         // equally sized host buffers at one pitch move with ONE 2-D copy
         bool raw_uniform = host_mem && n > 1 && in_vals[0] != 0;
@@ -649,11 +650,11 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
             if (rsb::pcm_chunks(pj[i].n_out) != chunks_per_job) chunks_per_job = 0;
         }
         cf[n] = n_chunks;
-        RSB_CUDA(cudaMemcpyAsync(h->d_pcm_jobs.p, pj, sizeof(rsb::PcmJob) * n + sizeof(uint64_t) * (n + 1),
+        RSB_CUDA(cudaMemcpyAsync(W.d_pcm_jobs.p, pj, sizeof(rsb::PcmJob) * n + sizeof(uint64_t) * (n + 1),
                                  cudaMemcpyHostToDevice, s));
         RSB_CUDA(cudaEventRecord(h->ev_pcm[0], s));
-        rsb::launch_pcm_ingest(h->d_pcm_jobs.as<rsb::PcmJob>(),
-                               reinterpret_cast<const uint64_t *>(h->d_pcm_jobs.as<rsb::PcmJob>() + n), n,
+        rsb::launch_pcm_ingest(W.d_pcm_jobs.as<rsb::PcmJob>(),
+                               reinterpret_cast<const uint64_t *>(W.d_pcm_jobs.as<rsb::PcmJob>() + n), n,
                                n_chunks, chunks_per_job, pcm->format, pcm->dup, h->sm_count, s);
         RSB_CUDA(cudaEventRecord(h->ev_pcm[1], s));
         h->pcm_timed = n_chunks != 0;
@@ -796,6 +797,9 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     if ((flags & RSB_FLAG_ASYNC) && !host_mem) return RSB_OK;
 
     rc = finalize_pending(h, W);
+    // a synchronous call returns with its outputs complete (the handle's streams are
+    // non-blocking: nothing else would order a caller's later copy behind the convolution)
+    if (!host_mem) RSB_CUDA(cudaEventSynchronize(W.ev_done));
     if (host_mem) {
         const UnitDev *ub = W.h_units_back.as<UnitDev>();
         uint64_t min_cap = ~0ull;
@@ -951,17 +955,16 @@ void rsb_fir_destroy(rsb_fir *h) {
     cudaFree(h->st.hist[1]);
     for (Workspace &W : h->ws) {
         for (DevBuf *b : {&W.d_units, &W.d_jobs, &W.d_segs, &W.d_calls, &W.d_tiles, &W.d_entries,
-                          &W.d_gtiles, &W.d_tct, &W.d_counter})
+                          &W.d_gtiles, &W.d_tct, &W.d_counter, &W.d_pcm_jobs})
             b->release();
         for (PinBuf *b : {&W.h_units, &W.h_jobs, &W.h_units_back, &W.h_calls_back, &W.h_segs,
-                          &W.h_counter})
+                          &W.h_counter, &W.h_pcm_jobs})
             b->release();
         if (W.ev_plan) cudaEventDestroy(W.ev_plan);
         if (W.ev_done) cudaEventDestroy(W.ev_done);
     }
-    for (DevBuf *b : {&h->d_stage_in, &h->d_stage_out, &h->d_dbg, &h->d_pcm_raw, &h->d_pcm_jobs, &h->d_zero})
+    for (DevBuf *b : {&h->d_stage_in, &h->d_stage_out, &h->d_dbg, &h->d_pcm_raw, &h->d_zero})
         b->release();
-    h->h_pcm_jobs.release();
     for (cudaEvent_t e : h->ev_pcm) if (e) cudaEventDestroy(e);
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);
     if (h->ev_t1) cudaEventDestroy(h->ev_t1);
@@ -1136,8 +1139,6 @@ int rsb_fir_process_pcm_batch(rsb_fir *h, uint32_t n, const uint32_t *streams,
         return fail(RSB_ERR_INVALID_ARGUMENT, "null array argument");
     if (memspace != RSB_MEM_DEVICE && memspace != RSB_MEM_HOST)
         return fail(RSB_ERR_INVALID_ARGUMENT, "bad memspace");
-    if (flags & RSB_FLAG_ASYNC)
-        return fail(RSB_ERR_INVALID_ARGUMENT, "RSB_FLAG_ASYNC is not available for PCM batches");
     const uint32_t ch = h->channels;
     PcmSpec spec;
     spec.format = format;
@@ -1169,11 +1170,6 @@ int rsb_fir_process_pcm_batch(rsb_fir *h, uint32_t n, const uint32_t *streams,
         jobs[i] = JobHost{s, static_cast<const float *>(in[i]), out[i], in_frames[i],
                           out_capacities[i] / ch, (uint32_t)(call_len / ch), (uint32_t)(out_cap_len / ch)};
     }
-    // the format step reuses one job table and staging buffer: nothing may still be in flight
-    int rc = finalize_all(h);
-    if (rc != RSB_OK && rc != RSB_ERR_OUTPUT_CAPACITY) return rc;
-    RSB_CUDA(cudaSetDevice(h->device));
-    RSB_CUDA(cudaStreamSynchronize(h->stream));
     return run_batch(h, jobs, false, memspace, flags, consumed_totals, produced_totals, n_calls, &spec);
 }
 

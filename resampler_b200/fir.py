@@ -331,6 +331,7 @@ class FirBatch:
             self._h, n, st, _ptr_array(in_ptrs), _size_array(in_frames), int(fmt), src_channels,
             call_len, out_cap_len, _ptr_array(out_ptrs), _size_array(out_capacities), cons, prod,
             calls, memspace, flags))
+        self._hold((cons, prod, calls))
         return cons, prod, calls
 
     def flush(self, streams: Optional[Sequence[int]] = None):

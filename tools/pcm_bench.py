@@ -41,7 +41,7 @@ def main():
     args = ap.parse_args()
 
     from resampler_b200 import Attenuation, FirBatch, Latency, PcmFormat, _lib
-    from resampler_b200.fir import MEM_DEVICE, MEM_HOST
+    from resampler_b200.fir import FLAG_ASYNC, MEM_DEVICE, MEM_HOST
     lib = _lib.load()
     n, sc = args.streams, args.src_channels
     frames = int(round(args.seconds * IN_HZ))
@@ -70,7 +70,7 @@ def main():
     def step():
         batch.reset(-1)
         return batch.process_pcm_ptrs(in_ptrs, fr, PcmFormat.S16, sc, CALL_LEN, 0, out_ptrs, caps,
-                                      memspace=MEM_DEVICE)
+                                      memspace=MEM_DEVICE, flags=FLAG_ASYNC)
 
     import os
 
@@ -81,9 +81,10 @@ def main():
         batch.timer_start()
         for _ in range(args.steps):
             _, prod, _ = step()
-            ingest.append(batch.last_ingest_ms())
-            conv.append(float(batch.conv_times_ms(1)[0]))
         ms = batch.timer_stop() / args.steps
+        batch.sync()
+        ingest.append(batch.last_ingest_ms())            # of the last step
+        conv = [float(x) for x in batch.conv_times_ms(args.steps)]
         return ms, int(sum(prod[:])), float(np.mean(ingest)), float(np.mean(conv)), batch.last_pcm_fused()
 
     # (1) as shipped: stereo s16 at an aligned stride => the tensor kernel converts in its loader
