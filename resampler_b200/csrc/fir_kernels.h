@@ -95,8 +95,9 @@ struct TcParams {
     uint32_t run_tiles;       // consecutive tiles per work item
     uint32_t kt_max;
     uint32_t issuers;         // MMA issuer warps: 2 when two consecutive tiles fit the TMEM ring
-    uint32_t raw16;           // stereo only: the tensor map covers RAW s16 frames (4 bytes each);
-                              // the splitter converts them (v / 32768, main.rs:131-136) itself
+    uint32_t raw16;           // mono / stereo: the tensor map covers RAW s16 frames and the splitter
+                              // converts them (v / 32768, main.rs:131-136): 1 = frames of `channels`
+                              // samples, 2 = mono frames duplicated into both channels of a stereo stream
 };
 bool tc_supported(uint32_t channels, uint32_t taps, double ratio);
 uint32_t tc_kt_extent(uint32_t taps, double ratio);
@@ -106,10 +107,12 @@ uint32_t tc_issuers(uint32_t taps, double ratio);
 // 2-D tensor map over equally strided member inputs: box = 16 frames x (128 / channels) members
 bool tc_make_input_tensor_map(CUtensorMap *out, const float *base, uint64_t stride_bytes,
                               uint64_t total_frames, uint32_t n_members, uint32_t channels);
-// The same over raw interleaved s16 stereo frames (element = one 4-byte frame, box = 16 frames
-// x 64 members, 64B swizzle): the format step fused into the tensor kernel's loader.
+// The same over raw interleaved s16 frames (element = one frame: 4 bytes stereo with 64B swizzle,
+// 2 bytes mono unswizzled; box = 16 frames x 128 / channels members): the format step fused into
+// the tensor kernel's loader.  src_channels 1 with channels 2 = mono source of a stereo stream.
 bool tc_make_raw16_tensor_map(CUtensorMap *out, const void *base, uint64_t stride_bytes,
-                              uint64_t total_frames, uint32_t n_members);
+                              uint64_t total_frames, uint32_t n_members, uint32_t src_channels,
+                              uint32_t channels);
 void launch_tc_gmat(const UnitDev *units, const TileRec *tiles, const PlanEntry *entries,
                     const float *coeffs, float *gmat, TcTile *tct, uint32_t taps, double ratio,
                     uint32_t tile_cap, cudaStream_t stream);

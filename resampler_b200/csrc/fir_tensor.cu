@@ -129,13 +129,18 @@ struct TcSmem {
     uint32_t tmem_base;
 };
 
-template <int CH, bool RAW16 = false>
+// RAW: 0 = f32 input; 1 = raw s16 frames of CH channels (CH = 1 or 2); 2 = raw MONO s16 frames
+// duplicated into both channels of a stereo stream (the CLI's mono -> stereo, main.rs:139-146)
+template <int CH, int RAW = 0>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUtensorMap tmap) {
     static_assert(CH == 1 || CH == 2 || CH == 4 || CH == 8, "tensor kernel: 1, 2, 4 or 8 channels");
-    static_assert(!RAW16 || CH == 2, "raw s16 input: stereo only");
-    // bytes one input chunk lands in shared memory: f32 rows, or 64 members x 16 raw 4-byte frames
-    constexpr uint32_t kXLandBytes = RAW16 ? (kRows / CH) * kChunk * 4u : kXStageBytes;
+    static_assert(RAW == 0 || (RAW == 1 && CH <= 2) || (RAW == 2 && CH == 2), "raw s16 input: mono / stereo");
+    constexpr bool kRawStereo = RAW == 1 && CH == 2;   // 4-byte frames, 64-byte rows, 64B swizzle
+    constexpr bool kRawMono = (RAW == 1 && CH == 1) || RAW == 2;   // 2-byte frames, 32-byte rows
+    // bytes one input chunk lands in shared memory: f32 rows, or one row of 16 raw frames per member
+    constexpr uint32_t kXLandBytes = kRawStereo ? (kRows / CH) * kChunk * 4u
+                                     : kRawMono ? (kRows / CH) * kChunk * 2u : kXStageBytes;
     constexpr uint32_t kMpg = kRows / CH;               // members per group
     extern __shared__ __align__(1024) uint8_t smem_tc[];
     __shared__ TcSmem S;
@@ -433,7 +438,18 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                     __syncwarp();
                     rc.lap(6);
                     const uint32_t base = smem_u32(xst + s * kXStageBytes);
-                    if (RAW16) {
+                    if (kRawMono) {
+                        // raw s16 mono: unswizzled 32-byte rows (16 frames), one per member; both
+                        // channel rows of a stereo member read the same samples (RAW == 2)
+                        const float4 q4 = lds128(base + ml * 32u + wg * 16u);
+                        const uint32_t w[4] = {__float_as_uint(q4.x), __float_as_uint(q4.y),
+                                               __float_as_uint(q4.z), __float_as_uint(q4.w)};
+#pragma unroll
+                        for (uint32_t k = 0; k < 4; ++k) {
+                            x[2 * k] = (float)(int)(short)(w[k] & 0xffffu) * (1.0f / 32768.0f);
+                            x[2 * k + 1] = (float)((int)w[k] >> 16) * (1.0f / 32768.0f);
+                        }
+                    } else if (kRawStereo) {
                         // raw s16 stereo: 64-byte rows (16 frames of 2 x s16), 64B swizzle: unit u
                         // at u ^ ((row >> 1) & 3); a word is one frame, the channel picks its half;
                         // s / 2^15 is the reference's `s as f32 / 32768.0` (main.rs:131-136)
@@ -742,7 +758,8 @@ bool tc_make_input_tensor_map(CUtensorMap *out, const float *base, uint64_t stri
 }
 
 bool tc_make_raw16_tensor_map(CUtensorMap *out, const void *base, uint64_t stride_bytes,
-                              uint64_t total_frames, uint32_t n_members) {
+                              uint64_t total_frames, uint32_t n_members, uint32_t src_channels,
+                              uint32_t channels) {
     typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
                                       const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                       const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -754,19 +771,23 @@ bool tc_make_raw16_tensor_map(CUtensorMap *out, const void *base, uint64_t strid
         cudaGetLastError();
         return false;
     }
+    if (!((src_channels == 2 && channels == 2) || (src_channels == 1 && channels <= 2))) return false;
     if (total_frames == 0 || total_frames >= (1ull << 31)) return false;
     if ((reinterpret_cast<uintptr_t>(base) & 15u) || (stride_bytes & 15u) || stride_bytes == 0)
         return false;
-    if (stride_bytes < total_frames * 4ull) return false;
+    if (stride_bytes < total_frames * 2ull * src_channels) return false;
     cuuint64_t dims[2] = {total_frames, n_members};
     cuuint64_t strides[1] = {stride_bytes};
-    cuuint32_t box[2] = {kChunk, (cuuint32_t)(kRows / 2)};
+    cuuint32_t box[2] = {kChunk, (cuuint32_t)(kRows / channels)};
     cuuint32_t estr[2] = {1, 1};
-    // element = one raw stereo frame (two s16 = 32 bits); frames past the end read as zeros
-    const CUresult r = ((EncodeTiledFn)fn)(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(base),
-                                           dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    // element = one raw frame: two s16 (32 bits, 64-byte rows, 64B swizzle) or one s16 (32-byte
+    // rows, no swizzle); frames past the end read as zeros
+    const bool stereo = src_channels == 2;
+    const CUresult r = ((EncodeTiledFn)fn)(
+        out, stereo ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 2,
+        const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        stereo ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
+        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 
@@ -794,9 +815,13 @@ void launch_conv_tc(const TcParams &p, const CUtensorMap &tmap, int sm_count, bo
         kern<<<grid, kTcThreads, smem, stream>>>(p, tmap);
     };
     switch (p.channels) {
-        case 1: launch(conv_tc_kernel<1>); break;
+        case 1:
+            if (p.raw16) launch(conv_tc_kernel<1, 1>);
+            else launch(conv_tc_kernel<1>);
+            break;
         case 2:
-            if (p.raw16) launch(conv_tc_kernel<2, true>);
+            if (p.raw16 == 2) launch(conv_tc_kernel<2, 2>);
+            else if (p.raw16 == 1) launch(conv_tc_kernel<2, 1>);
             else launch(conv_tc_kernel<2>);
             break;
         case 4: launch(conv_tc_kernel<4>); break;

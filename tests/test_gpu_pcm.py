@@ -133,25 +133,27 @@ def test_errors():
     batch.close()
 
 
-@pytest.mark.parametrize("kernel,fmt,src_ch,aligned", [
-    (Kernel.TENSOR, PcmFormat.S16, 2, True),     # format step fused into the tensor kernel
-    (Kernel.TENSOR, PcmFormat.S16, 2, False),    # rows not 16-byte aligned: separate format pass
-    (Kernel.TENSOR, PcmFormat.S24, 1, True),
-    (Kernel.FAST, PcmFormat.S16, 1, True),
+@pytest.mark.parametrize("kernel,fmt,ch,src_ch,aligned", [
+    (Kernel.TENSOR, PcmFormat.S16, 2, 2, True),     # format step fused into the tensor kernel
+    (Kernel.TENSOR, PcmFormat.S16, 2, 2, False),    # rows not 16-byte aligned: separate format pass
+    (Kernel.TENSOR, PcmFormat.S16, 2, 1, True),     # fused, mono source duplicated (main.rs:139-146)
+    (Kernel.TENSOR, PcmFormat.S16, 1, 1, True),     # fused, mono streams
+    (Kernel.TENSOR, PcmFormat.S24, 2, 1, True),
+    (Kernel.FAST, PcmFormat.S16, 2, 1, True),
 ])
-def test_device_resident_pcm_batch_fast_kernels(kernel, fmt, src_ch, aligned):
+def test_device_resident_pcm_batch_fast_kernels(kernel, fmt, ch, src_ch, aligned):
     """64 equally long files resident on the device (raw bytes in HBM): the converted staging
-    buffer is equally strided, so the tensor kernel takes it; stereo s16 rows that are 16-byte
-    aligned are converted inside the tensor kernel's loader.  Samples within 1e-6 of the oracle,
-    counts exact; a second batch checks the history written from the raw tail."""
-    ch, n, frames = 2, 64, 6007
+    buffer is equally strided, so the tensor kernel takes it; s16 rows that are 16-byte aligned
+    are converted inside the tensor kernel's loader.  Samples within 1e-6 of the oracle, counts
+    exact; a second batch checks the history written from the raw tail."""
+    n, frames = 64, 6007
     lib = _lib.load()
     rng = np.random.default_rng(77 + int(fmt))
     raws = [raw_samples(rng, fmt, frames * src_ch) for _ in range(n)]
     raws2 = [raw_samples(rng, fmt, 1500 * src_ch) for _ in range(n)]
     bps = fmt.bytes_per_sample()
     raw_bytes = frames * src_ch * bps
-    stride = (raw_bytes + 15) & ~15 if aligned else raw_bytes + 2
+    stride = (raw_bytes + 15) & ~15 if aligned else raw_bytes + 6
     d_raw = lib.rsb_alloc_device(0, stride * n + 16)
     batch = FirBatch(n, ch, 44100, 48000, Latency.Sample64, Attenuation.Db90, kernel=kernel)
     cap = int(frames * ch / batch.ratio()) + 4 * batch.buffer_size_output()
@@ -175,8 +177,7 @@ def test_device_resident_pcm_batch_fast_kernels(kernel, fmt, src_ch, aligned):
     cons, prod, calls = run(raws, frames)
     assert batch.last_kernel() == kernel
     assert batch.last_ingest_ms() > 0.0
-    assert batch.last_pcm_fused() == (kernel == Kernel.TENSOR and fmt == PcmFormat.S16
-                                      and src_ch == 2 and aligned)
+    assert batch.last_pcm_fused() == (kernel == Kernel.TENSOR and fmt == PcmFormat.S16 and aligned)
     firsts = {i: fetch(i, prod[i]) for i in (0, 1, 31, 63)}
     cons2, prod2, _ = run(raws2, 1500)
     worst = 0.0
@@ -197,24 +198,25 @@ def test_device_resident_pcm_batch_fast_kernels(kernel, fmt, src_ch, aligned):
     batch.close()
 
 
-def test_fused_and_separate_format_step_agree_bit_for_bit(monkeypatch):
+@pytest.mark.parametrize("ch,src_ch", [(2, 2), (2, 1), (1, 1)])
+def test_fused_and_separate_format_step_agree_bit_for_bit(monkeypatch, ch, src_ch):
     """The tensor kernel converting raw s16 frames in its loader and the separate format pass
     feed the same f32 values into the same arithmetic: identical output bits (host buffers)."""
-    ch, n, frames = 2, 64, 5000
+    n, frames = 64, 5000
     rng = np.random.default_rng(123)
-    raws = [raw_samples(rng, PcmFormat.S16, frames * ch) for _ in range(n)]
+    raws = [raw_samples(rng, PcmFormat.S16, frames * src_ch) for _ in range(n)]
     outs = []
     for unfused in (False, True):
         if unfused:
             monkeypatch.setenv("RSB_PCM_UNFUSED", "1")
         batch = FirBatch(n, ch, 44100, 48000, Latency.Sample64, Attenuation.Db90, kernel=Kernel.TENSOR)
-        res = batch.process_pcm(raws, PcmFormat.S16, ch)
+        res = batch.process_pcm(raws, PcmFormat.S16, src_ch, call_len=512 * ch)
         assert batch.last_pcm_fused() == (not unfused)
         tail = batch.flush()
         outs.append([np.concatenate([a, b]) for a, b in zip(res["out"], tail)])
         batch.close()
     for a, b in zip(*outs):
-        assert np.array_equal(bits(a), bits(b))
+        assert a.size > frames * ch and np.array_equal(bits(a), bits(b))
 
 
 def test_wav_files_end_to_end(tmp_path):
