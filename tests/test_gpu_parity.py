@@ -490,3 +490,26 @@ def test_flush_feeds_delay_frames_of_silence():
     t1 = batch.flush(streams=[1])
     assert len(t1) == 1
     batch.close()
+
+
+def test_cuda_path_matches_committed_fixtures():
+    """The CUDA path (bit-exact kernel, through the C ABI) against the frozen fixtures of
+    tests/golden/fir_cases.npz: per-call counts, per-frame plan and output sample bits."""
+    import importlib.util
+    from pathlib import Path
+    gdir = Path(__file__).resolve().parent / "golden"
+    spec = importlib.util.spec_from_file_location("make_fixtures", gdir / "make_fixtures.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    z = np.load(gdir / "fir_cases.npz")
+    for name, (ch, in_hz, out_hz, lat, att, call, cap, frames) in mod.CASES.items():
+        batch = FirBatch(1, ch, in_hz, out_hz, Latency(lat), Attenuation(att), kernel=Kernel.EXACT)
+        res = batch.process([z[f"{name}/x"]], call * ch, cap * ch,
+                            flags=FLAG_RECORD_CALLS | FLAG_KEEP_PLAN)
+        assert np.array_equal(bits(res["out"][0]), bits(z[f"{name}/out"])), name
+        cc, cp = batch.last_call_counts(0)
+        assert np.array_equal(cc, z[f"{name}/consumed"]) and np.array_equal(cp, z[f"{name}/produced"])
+        plan = batch.last_plan(0)
+        for key in ("input_offset", "phase1", "phase2", "frac_bits"):
+            assert np.array_equal(plan[key], z[f"{name}/{key}"]), (name, key)
+        batch.close()

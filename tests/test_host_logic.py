@@ -223,3 +223,25 @@ def test_wav_roundtrip_and_formats(tmp_path):
     (tmp_path / "d.wav").write_bytes(b"RIFX0000WAVE")
     with pytest.raises(ValueError):
         read_wav(tmp_path / "d.wav")
+
+
+def test_host_planner_matches_committed_fixtures():
+    """planner.h (the code the GPU runs) against the frozen per-call counts and per-frame plan."""
+    from pathlib import Path
+    import importlib.util
+    gdir = Path(__file__).resolve().parent / "golden"
+    spec = importlib.util.spec_from_file_location("make_fixtures", gdir / "make_fixtures.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    z = np.load(gdir / "fir_cases.npz")
+    from resampler_b200.fir import host_plan
+    from resampler_b200 import Latency
+    for name, (ch, in_hz, out_hz, lat, att, call, cap, frames) in mod.CASES.items():
+        taps = (16, 32, 64, 128)[lat]
+        ratio = in_hz / out_hz
+        cap_frames = cap if cap else int(np.ceil((4096 - taps) / ratio)) + 2
+        p = host_plan(in_hz, out_hz, Latency(lat), 0, 0, frames, call, cap_frames, False)
+        assert np.array_equal(p["consumed"] * ch, z[f"{name}/consumed"]), name
+        assert np.array_equal(p["produced"] * ch, z[f"{name}/produced"]), name
+        for key in ("input_offset", "phase1", "phase2", "frac_bits"):
+            assert np.array_equal(p[key], z[f"{name}/{key}"]), (name, key)

@@ -369,3 +369,30 @@ def test_pcm_mono_to_stereo_duplication():
     want = np.repeat(s16.astype(np.float32) / np.float32(32768.0), 2)
     assert np.array_equal(O.pcm_to_f32(s16, O.PCM_S16, dup=2), want)
     assert O.pcm_to_f32(np.zeros(0, np.int16), O.PCM_S16, dup=2).size == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# committed regression fixtures (tests/golden/fir_cases.npz, made by tests/golden/make_fixtures.py)
+# ---------------------------------------------------------------------------------------------
+def _golden():
+    import importlib.util
+    from pathlib import Path
+    gdir = Path(__file__).resolve().parent / "golden"
+    spec = importlib.util.spec_from_file_location("make_fixtures", gdir / "make_fixtures.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod, np.load(gdir / "fir_cases.npz")
+
+
+def test_oracle_reproduces_committed_fixtures():
+    """The oracle built here gives the frozen counts, plan entries and sample bits."""
+    mod, z = _golden()
+    for name in mod.CASES:
+        got = mod.run_case(name)
+        for key, val in got.items():
+            want = z[f"{name}/{key}"]
+            assert val.shape == want.shape, (name, key)
+            if val.dtype == np.float32:
+                assert np.array_equal(val.view(np.uint32), want.view(np.uint32)), (name, key)
+            else:
+                assert np.array_equal(val, want), (name, key)
