@@ -25,7 +25,7 @@ sys.path.insert(0, str(ROOT))
 SUPPORTED = (16000, 22050, 32000, 44100, 48000, 88200, 96000, 176400, 192000, 384000)
 
 
-def resample_files(paths, out_dir, sample_rate, latency=64, attenuation=90, device=0):
+def resample_files(paths, out_dir, sample_rate, latency=64, attenuation=90, device=0, devices=None):
     from resampler_b200 import Attenuation, FirBatch, Latency
     from resampler_b200.wav import read_wav, write_wav_f32
     lat = {8: Latency.Sample8, 16: Latency.Sample16, 32: Latency.Sample32, 64: Latency.Sample64}
@@ -48,17 +48,43 @@ def resample_files(paths, out_dir, sample_rate, latency=64, attenuation=90, devi
         if w.channels not in (1, 2):
             raise SystemExit(f"Unsupported channel count: {w.channels}")     # main.rs:151-154
         groups[(w.sample_rate, w.fmt, w.channels)].append((Path(p), w))
-    written = []
+    # Files are independent streams: every (rate, format, channels) group is cut into one
+    # contiguous share per GPU (resampler_b200.sharding), one host thread and handle per share,
+    # no collective.
+    import threading
+    from resampler_b200.sharding import shard_range
+    devices = list(devices) if devices else [device]
+    written, errors, lock = [], [], threading.Lock()
+
+    def run_share(dev, in_rate, fmt, ch, items):
+        try:
+            batch = FirBatch(len(items), 2, in_rate, sample_rate, lat[latency], att[attenuation],
+                             device=dev)
+            res = batch.process_pcm([w.raw for _, w in items], fmt, ch, call_len=512)
+            batch.close()
+            for (p, w), out in zip(items, res["out"]):
+                dst = out_dir / p.name
+                write_wav_f32(dst, out, sample_rate, 2)
+                with lock:
+                    written.append((dst, w.frames, len(out) // 2))
+        except Exception as e:            # surfaced after the join
+            with lock:
+                errors.append(e)
+
+    threads = []
     for (in_rate, fmt, ch), items in groups.items():
-        batch = FirBatch(len(items), 2, in_rate, sample_rate, lat[latency], att[attenuation],
-                         device=device)
-        res = batch.process_pcm([w.raw for _, w in items], fmt, ch, call_len=512)
-        for (p, w), out in zip(items, res["out"]):
-            dst = out_dir / p.name
-            write_wav_f32(dst, out, sample_rate, 2)
-            written.append((dst, w.frames, len(out) // 2))
-        batch.close()
-    return written
+        for r, dev in enumerate(devices):
+            lo, hi = shard_range(len(items), len(devices), r)
+            if hi > lo:
+                threads.append(threading.Thread(target=run_share,
+                                                args=(dev, in_rate, fmt, ch, items[lo:hi])))
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return sorted(written)
 
 
 def main():
@@ -68,10 +94,12 @@ def main():
     ap.add_argument("--attenuation", type=int, default=90, metavar="DB")
     ap.add_argument("--out-dir", required=True)
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--gpus", type=int, default=1, help="shard the files over this many GPUs")
     ap.add_argument("inputs", nargs="+")
     a = ap.parse_args()
+    devices = list(range(a.device, a.device + a.gpus))
     for dst, fin, fout in resample_files(a.inputs, a.out_dir, a.sample_rate, a.latency,
-                                         a.attenuation, a.device):
+                                         a.attenuation, a.device, devices):
         print(f"{dst}: Input frames: {fin}  Output frames: {fout}")
 
 
