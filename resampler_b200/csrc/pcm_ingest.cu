@@ -154,12 +154,22 @@ struct Piece<RSB_PCM_S24, 1> {
 };
 template <>
 struct Piece<RSB_PCM_S24, 2> {
-    struct Raw { float a, b; };
-    static __device__ __forceinline__ Raw ld(const void *src, uint64_t q, bool, uint32_t) {
+    struct Raw { uint32_t a, b; };   // the two samples' 24 bits
+    static __device__ __forceinline__ Raw ld(const void *src, uint64_t q, bool aligned, uint32_t) {
         const uint8_t *s = static_cast<const uint8_t *>(src) + 6 * q;
-        return Raw{cv_s24(s), cv_s24(s + 3)};
+        if (aligned) {
+            // 6 bytes at an even offset: three halfwords
+            const uint16_t *h = reinterpret_cast<const uint16_t *>(s);
+            const uint32_t h0 = h[0], h1 = h[1], h2 = h[2];
+            return Raw{h0 | ((h1 & 0xffu) << 16), (h1 >> 8) | (h2 << 8)};
+        }
+        return Raw{(uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16),
+                   (uint32_t)s[3] | ((uint32_t)s[4] << 8) | ((uint32_t)s[5] << 16)};
     }
-    static __device__ __forceinline__ float4 cv(const Raw &v) { return make_float4(v.a, v.a, v.b, v.b); }
+    static __device__ __forceinline__ float4 cv(const Raw &v) {
+        const float a = cv_s24_bits(v.a), b = cv_s24_bits(v.b);
+        return make_float4(a, a, b, b);
+    }
 };
 template <>
 struct Piece<RSB_PCM_S24, 0> {
