@@ -241,3 +241,42 @@ def test_wav_files_end_to_end(tmp_path):
         assert (w.sample_rate, w.channels, w.fmt) == (48000, 2, PcmFormat.F32)
         _, ref = oracle_cli(2, 44100, 48000, 3, raw, fmt, src_ch)
         assert np.array_equal(w.raw.view(np.uint32), bits(ref["out"]))
+
+
+def test_larger_device_batch_fused_equals_separate_and_exact(monkeypatch):
+    """512 stereo s16 files x 2 s on the device, asynchronous submits: the fused loader and the
+    separate format pass agree bit for bit on EVERY sample of every stream, and both stay within
+    1e-6 of the bit-exact kernel fed by the separate pass."""
+    from resampler_b200.fir import FLAG_ASYNC
+    n, ch, frames = 512, 2, 88200
+    lib = _lib.load()
+    rng = np.random.default_rng(2024)
+    raw = rng.integers(-32768, 32768, (n, frames * ch), dtype=np.int16)
+    stride = frames * ch * 2
+    assert stride % 16 == 0
+    d_raw = lib.rsb_alloc_device(0, stride * n)
+    assert lib.rsb_memcpy(0, d_raw, raw.ctypes.data, raw.nbytes, 0) == 0
+    cap = ((int(frames * 48000 / 44100) + 8) * ch + 3) & ~3
+    d_out = lib.rsb_alloc_device(0, cap * 4 * n)
+    outs = {}
+    for name, kern, unfused in (("fused", Kernel.TENSOR, False), ("separate", Kernel.TENSOR, True),
+                                ("exact", Kernel.EXACT, True)):
+        if unfused:
+            monkeypatch.setenv("RSB_PCM_UNFUSED", "1")
+        b = FirBatch(n, ch, 44100, 48000, Latency.Sample64, Attenuation.Db90, kernel=kern)
+        cons, prod, calls = b.process_pcm_ptrs(
+            [d_raw + s * stride for s in range(n)], [frames] * n, PcmFormat.S16, ch, 512, 0,
+            [d_out + s * cap * 4 for s in range(n)], [cap] * n, memspace=MEM_DEVICE, flags=FLAG_ASYNC)
+        b.sync()
+        assert b.last_pcm_fused() == (name == "fused")
+        assert all(c == frames * ch for c in cons[:]) and len(set(prod[:])) == 1
+        got = np.empty(n * cap, np.float32)
+        assert lib.rsb_memcpy(0, got.ctypes.data, d_out, got.nbytes, 1) == 0
+        outs[name] = got.reshape(n, cap)[:, :prod[0]].copy()
+        b.close()
+    assert np.array_equal(bits(outs["fused"]), bits(outs["separate"]))
+    assert np.max(np.abs(outs["fused"].astype(np.float64) - outs["exact"])) <= TOL
+    ref = oracle_cli(ch, 44100, 48000, 3, raw[n - 1], PcmFormat.S16, ch)[1]
+    assert np.array_equal(bits(outs["exact"][n - 1]), bits(ref["out"]))
+    lib.rsb_free_device(0, d_raw)
+    lib.rsb_free_device(0, d_out)
