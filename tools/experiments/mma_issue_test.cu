@@ -208,7 +208,7 @@ int main(int argc, char **argv) {
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
     const int n_mma = 64, reps = 200;
     const int fill = argc > 2 ? atoi(argv[2]) : 0;
-    for (int variant : {2, 6}) {
+    for (int variant : {2, 6, 12, 16, 22}) {
         k<<<1, 128, 65536>>>(variant, n_mma, reps, d, (uint32_t)(argc > 1 ? atoi(argv[1]) : 0), fill);
         cudaError_t e = cudaDeviceSynchronize();
         long long h[2] = {0, 0};
