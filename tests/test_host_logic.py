@@ -245,3 +245,28 @@ def test_host_planner_matches_committed_fixtures():
         assert np.array_equal(p["produced"] * ch, z[f"{name}/produced"]), name
         for key in ("input_offset", "phase1", "phase2", "frac_bits"):
             assert np.array_equal(p[key], z[f"{name}/{key}"]), (name, key)
+
+
+def test_wav_batch_tool_rejects_what_the_cli_rejects(tmp_path):
+    """tools/resample_wav.py validates like resample/src/main.rs:33-55, 107-126, 151-154 --
+    before any GPU work."""
+    import sys
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    import resample_wav
+    from resampler_b200.wav import write_wav_pcm
+    ok = tmp_path / "ok.wav"
+    write_wav_pcm(ok, np.zeros(200, np.int16), 44100, 2, 16)
+    with pytest.raises(SystemExit, match="Invalid latency value: 48. Must be 8, 16, 32, or 64"):
+        resample_wav.resample_files([ok], tmp_path / "o", 48000, latency=48)
+    with pytest.raises(SystemExit, match="Invalid attenuation value: 100. Must be 60, 90, or 120"):
+        resample_wav.resample_files([ok], tmp_path / "o", 48000, attenuation=100)
+    with pytest.raises(SystemExit, match="Unsupported output sample rate: 47999"):
+        resample_wav.resample_files([ok], tmp_path / "o", 47999)
+    three = tmp_path / "three.wav"
+    write_wav_pcm(three, np.zeros(300, np.int16), 44100, 3, 16)
+    with pytest.raises(SystemExit, match="Unsupported channel count: 3"):
+        resample_wav.resample_files([three], tmp_path / "o", 48000)
+    odd = tmp_path / "odd.wav"
+    write_wav_pcm(odd, np.zeros(200, np.int16), 12345, 2, 16)
+    with pytest.raises(SystemExit, match="Unsupported input sample rate: 12345"):
+        resample_wav.resample_files([odd], tmp_path / "o", 48000)
