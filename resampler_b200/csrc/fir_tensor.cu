@@ -35,6 +35,14 @@
 //   * warps 0-3 (epilogue): tcgen05.ld of the 128 x 32 accumulator, staging through shared
 //     memory, coalesced 16-byte stores.
 //
+// Raw 16-bit input (RAW template parameter; the CLI batch path, resample/src/main.rs:128-156):
+// the TMA producer can stream RAW s16 frames instead of f32 (a second tensor map: 4-byte stereo
+// frames in 64-byte swizzled rows, or 2-byte mono frames in 32-byte rows) and the splitter
+// converts each half word with s * 2^-15 before the hi/lo split; a mono source of a stereo
+// stream is duplicated by letting both channel rows of a member read the same samples.  The
+// arithmetic after the conversion is unchanged, so the output is bit-identical to running the
+// separate format pass (pcm_ingest.cu) first.
+//
 // TMEM map (512 columns x 128 lanes): [0,224) X hi ring, [224,448) X lo ring, [448,480) and
 // [480,512) the two accumulators.
 #include <cstring>
