@@ -396,3 +396,22 @@ def test_oracle_reproduces_committed_fixtures():
                 assert np.array_equal(val.view(np.uint32), want.view(np.uint32)), (name, key)
             else:
                 assert np.array_equal(val, want), (name, key)
+
+
+def test_pcm_format_step_matches_independent_numpy_restatement():
+    """A second restatement of main.rs:131-136 in numpy (`s as f32 / max_value` with the actual
+    f32 division) against the C oracle on random samples of every integer format."""
+    rng = np.random.default_rng(17)
+    n = 20000
+    s16 = rng.integers(-32768, 32768, n, dtype=np.int16)
+    assert np.array_equal(O.pcm_to_f32(s16, O.PCM_S16), s16.astype(np.float32) / np.float32(32768.0))
+    u8 = rng.integers(0, 256, n, dtype=np.uint8)
+    assert np.array_equal(O.pcm_to_f32(u8, O.PCM_U8),
+                          (u8.astype(np.int32) - 128).astype(np.float32) / np.float32(128.0))
+    v24 = rng.integers(-(1 << 23), 1 << 23, n, dtype=np.int64)
+    u = (v24 & 0xFFFFFF).astype(np.uint32)
+    b24 = np.stack([u & 0xFF, (u >> 8) & 0xFF, (u >> 16) & 0xFF], axis=1).astype(np.uint8).reshape(-1)
+    assert np.array_equal(O.pcm_to_f32(b24, O.PCM_S24), v24.astype(np.float32) / np.float32(8388608.0))
+    s32 = rng.integers(-(1 << 31), 1 << 31, n, dtype=np.int64).astype(np.int32)
+    # `(1 << 31) as f32` on an i32 literal = -2147483648.0
+    assert np.array_equal(O.pcm_to_f32(s32, O.PCM_S32), s32.astype(np.float32) / np.float32(-2147483648.0))
