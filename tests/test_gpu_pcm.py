@@ -280,3 +280,27 @@ def test_larger_device_batch_fused_equals_separate_and_exact(monkeypatch):
     assert np.array_equal(bits(outs["exact"][n - 1]), bits(ref["out"]))
     lib.rsb_free_device(0, d_raw)
     lib.rsb_free_device(0, d_out)
+
+
+@pytest.mark.parametrize("ch,src_ch", [(2, 2), (2, 1), (1, 1)])
+def test_fused_loader_tiny_and_odd_lengths(ch, src_ch):
+    """Fused raw-s16 loader at the small end: files of 1 .. 300 frames (shorter than one TMA
+    box, than the filter, not multiples of anything), several batches in a row on the same
+    streams so that history and phase carry through the raw tail conversion."""
+    n = 64
+    rng = np.random.default_rng(900 + ch * 10 + src_ch)
+    batch = FirBatch(n, ch, 44100, 48000, Latency.Sample64, Attenuation.Db90, kernel=Kernel.TENSOR)
+    refs = [O.OracleFir(ch, 44100, 48000, 3, 1) for _ in range(4)]
+    worst = 0.0
+    for frames in (1, 5, 17, 127, 128, 300, 2):
+        raws = [raw_samples(rng, PcmFormat.S16, frames * src_ch) for _ in range(n)]
+        res = batch.process_pcm(raws, PcmFormat.S16, src_ch, call_len=512 * ch)
+        assert batch.last_pcm_fused() and batch.last_kernel() == Kernel.TENSOR
+        for k, s in enumerate((0, 1, 31, 63)):
+            x = O.pcm_to_f32(raws[s], O.PCM_S16, 1 if src_ch == ch else ch)
+            ref = refs[k].process(x, 512 * ch)
+            assert res["consumed"][s] == ref["consumed_total"] and res["produced"][s] == len(ref["out"])
+            if len(ref["out"]):
+                worst = max(worst, float(np.max(np.abs(res["out"][s].astype(np.float64) - ref["out"]))))
+    assert worst <= TOL, worst
+    batch.close()
