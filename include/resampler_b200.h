@@ -178,8 +178,8 @@ int rsb_fir_process_pcm_batch(rsb_fir *h, uint32_t n, const uint32_t *streams,
 int rsb_fir_flush_batch(rsb_fir *h, uint32_t n, const uint32_t *streams, float *const *out,
                         const size_t *out_capacities, size_t *produced, int memspace,
                         uint32_t flags);
-/* 1 when the most recent PCM batch ran with the format step INSIDE the tensor kernel (s16
- * sources of mono or stereo streams, equally long, rows 16-byte aligned at one constant stride,
+/* 1 when the most recent PCM batch ran with the format step INSIDE the tensor kernel (s16 or
+ * packed s24 sources of mono or stereo streams, equally long, rows 16-byte aligned at one constant stride,
  * tensor kernel selected): the kernel's TMA producer streams the raw frames and its splitter converts them;
  * only each stream's last 4096 frames go through the separate format-step kernel (they feed
  * the history).  Results are bit-identical to the unfused path. */

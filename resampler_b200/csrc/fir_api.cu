@@ -620,17 +620,19 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
         // for the history update (update_state_kernel reads them as f32).
         pcm_fused = false;
         const uint32_t src_ch = ch / pcm->dup;   // 1 (mono source) or ch
-        if (use_tc && host_plan && pcm->format == RSB_PCM_S16 && ch <= 2 && !getenv("RSB_PCM_UNFUSED")) {
+        const uint32_t sb = pcm->bps;            // bytes per raw sample
+        if (use_tc && host_plan && (pcm->format == RSB_PCM_S16 || pcm->format == RSB_PCM_S24) && ch <= 2 &&
+            !getenv("RSB_PCM_UNFUSED")) {
             const uintptr_t base = reinterpret_cast<uintptr_t>(pj[0].src);
             const uint64_t stride = n > 1 ? (uint64_t)(reinterpret_cast<uintptr_t>(pj[1].src) - base)
-                                          : (((uint64_t)in_vals[0] / pcm->dup * 2 + 15) & ~15ull);
+                                          : (((uint64_t)in_vals[0] / pcm->dup * sb + 15) & ~15ull);
             bool ok = n == 1 || reinterpret_cast<uintptr_t>(pj[1].src) > base;
             for (uint32_t i = 1; ok && i < n; ++i)
                 ok = reinterpret_cast<uintptr_t>(pj[i].src) == base + (uint64_t)i * stride;
             // jobs are grouped by unit in hj; one unit => hj order == job order
             CUtensorMap raw_map;
             if (ok && rsb::tc_make_raw16_tensor_map(&raw_map, pj[0].src, stride,
-                                                    unit_keys[0].total_frames, n, src_ch, ch)) {
+                                                    unit_keys[0].total_frames, n, src_ch, ch, sb)) {
                 tc_tmap = raw_map;
                 pcm_fused = true;
                 pcm_raw_mode = src_ch == ch ? 1u : 2u;
@@ -640,7 +642,7 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
             const uint64_t copied = hu[0].total_copied;
             const uint64_t start = (copied > rsb::kHistFrames ? copied - rsb::kHistFrames : 0) & ~7ull;
             for (uint32_t i = 0; i < n; ++i) {
-                pj[i].src = static_cast<const char *>(pj[i].src) + start * 2 * src_ch;   // s16 frames
+                pj[i].src = static_cast<const char *>(pj[i].src) + start * sb * src_ch;   // raw frames
                 pj[i].dst += start * ch;
                 pj[i].n_out -= start * ch;
                 pj[i].src_aligned = (reinterpret_cast<uintptr_t>(pj[i].src) & 15u) == 0 ? 1u : 0u;
@@ -761,6 +763,7 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
         T.kt_max = rsb::tc_kt_extent(h->taps, h->ratio);
         T.issuers = rsb::tc_issuers(h->taps, h->ratio);
         T.raw16 = pcm_fused ? pcm_raw_mode : 0u;
+        T.raw_bytes = pcm && pcm_fused ? pcm->bps : 2u;
         if (getenv("RSB_TC_ISSUERS")) T.issuers = atoi(getenv("RSB_TC_ISSUERS")) == 1 ? 1u : T.issuers;
         rsb::launch_conv_tc(T, tc_tmap, h->sm_count, !host_plan, s);
     } else if (use_fast) {

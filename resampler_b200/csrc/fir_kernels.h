@@ -98,6 +98,7 @@ struct TcParams {
     uint32_t raw16;           // mono / stereo: the tensor map covers RAW s16 frames and the splitter
                               // converts them (v / 32768, main.rs:131-136): 1 = frames of `channels`
                               // samples, 2 = mono frames duplicated into both channels of a stereo stream
+    uint32_t raw_bytes;       // bytes per raw sample: 2 (s16) or 3 (packed s24)
 };
 bool tc_supported(uint32_t channels, uint32_t taps, double ratio);
 uint32_t tc_kt_extent(uint32_t taps, double ratio);
@@ -112,7 +113,7 @@ bool tc_make_input_tensor_map(CUtensorMap *out, const float *base, uint64_t stri
 // the tensor kernel's loader.  src_channels 1 with channels 2 = mono source of a stereo stream.
 bool tc_make_raw16_tensor_map(CUtensorMap *out, const void *base, uint64_t stride_bytes,
                               uint64_t total_frames, uint32_t n_members, uint32_t src_channels,
-                              uint32_t channels);
+                              uint32_t channels, uint32_t sample_bytes);
 void launch_tc_gmat(const UnitDev *units, const TileRec *tiles, const PlanEntry *entries,
                     const float *coeffs, float *gmat, TcTile *tct, uint32_t taps, double ratio,
                     uint32_t tile_cap, cudaStream_t stream);

@@ -35,10 +35,11 @@
 //   * warps 0-3 (epilogue): tcgen05.ld of the 128 x 32 accumulator, staging through shared
 //     memory, coalesced 16-byte stores.
 //
-// Raw 16-bit input (RAW template parameter; the CLI batch path, resample/src/main.rs:128-156):
-// the TMA producer can stream RAW s16 frames instead of f32 (a second tensor map: 4-byte stereo
-// frames in 64-byte swizzled rows, or 2-byte mono frames in 32-byte rows) and the splitter
-// converts each half word with s * 2^-15 before the hi/lo split; a mono source of a stereo
+// Raw integer input (RAW / SB template parameters; the CLI batch path, resample/src/main.rs:128-156):
+// the TMA producer can stream RAW s16 or packed s24 frames instead of f32 (a second tensor map:
+// s16 as 4-byte stereo frames in 64-byte swizzled rows or 2-byte mono frames in 32-byte rows, s24
+// as bytes in unswizzled 96- / 48-byte rows) and the splitter converts each sample with
+// s * 2^-(bits-1) before the hi/lo split; a mono source of a stereo
 // stream is duplicated by letting both channel rows of a member read the same samples.  The
 // arithmetic after the conversion is unchanged, so the output is bit-identical to running the
 // separate format pass (pcm_ingest.cu) first.
@@ -139,16 +140,20 @@ struct TcSmem {
 
 // RAW: 0 = f32 input; 1 = raw s16 frames of CH channels (CH = 1 or 2); 2 = raw MONO s16 frames
 // duplicated into both channels of a stereo stream (the CLI's mono -> stereo, main.rs:139-146)
-template <int CH, int RAW = 0>
+// SB: bytes per raw sample, 2 (s16) or 3 (packed little-endian s24)
+template <int CH, int RAW = 0, int SB = 2>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUtensorMap tmap) {
     static_assert(CH == 1 || CH == 2 || CH == 4 || CH == 8, "tensor kernel: 1, 2, 4 or 8 channels");
     static_assert(RAW == 0 || (RAW == 1 && CH <= 2) || (RAW == 2 && CH == 2), "raw s16 input: mono / stereo");
-    constexpr bool kRawStereo = RAW == 1 && CH == 2;   // 4-byte frames, 64-byte rows, 64B swizzle
-    constexpr bool kRawMono = (RAW == 1 && CH == 1) || RAW == 2;   // 2-byte frames, 32-byte rows
+    static_assert(SB == 2 || (SB == 3 && RAW != 0), "raw samples: 16 or packed 24 bits");
+    constexpr bool kRawStereo = RAW == 1 && CH == 2;   // s16: 4-byte frames, 64-byte rows, 64B swizzle
+    constexpr bool kRawMono = (RAW == 1 && CH == 1) || RAW == 2;   // s16: 2-byte frames, 32-byte rows
+    // packed s24: 6-byte stereo / 3-byte mono frames in unswizzled 96- / 48-byte rows (the tensor
+    // map's element is one byte)
+    constexpr uint32_t kRawFrameBytes = RAW == 0 ? 0u : (kRawStereo ? 2u : 1u) * SB;
     // bytes one input chunk lands in shared memory: f32 rows, or one row of 16 raw frames per member
-    constexpr uint32_t kXLandBytes = kRawStereo ? (kRows / CH) * kChunk * 4u
-                                     : kRawMono ? (kRows / CH) * kChunk * 2u : kXStageBytes;
+    constexpr uint32_t kXLandBytes = RAW != 0 ? (kRows / CH) * kChunk * kRawFrameBytes : kXStageBytes;
     constexpr uint32_t kMpg = kRows / CH;               // members per group
     extern __shared__ __align__(1024) uint8_t smem_tc[];
     __shared__ TcSmem S;
@@ -246,7 +251,8 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                     mbar_arrive_expect_tx(&S.xs_full[s], kXLandBytes);
                     // inner coordinate in tensor-map elements: frames (mono f32, stereo 8-byte
                     // frames) or floats (4 / 8 channels)
-                    tensor_g2s_2d(xst + s * kXStageBytes, &tmap, (v - H) * (CH >= 4 ? CH : 1), m0,
+                    tensor_g2s_2d(xst + s * kXStageBytes, &tmap,
+                                  (v - H) * (int32_t)(SB == 3 ? kRawFrameBytes : CH >= 4 ? CH : 1), m0,
                                   &S.xs_full[s]);
                     ++xs_seq;
                 }
@@ -446,7 +452,43 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                     __syncwarp();
                     rc.lap(6);
                     const uint32_t base = smem_u32(xst + s * kXStageBytes);
-                    if (kRawMono) {
+                    if (SB == 3 && kRawStereo) {
+                        // packed s24 stereo: unswizzled 96-byte rows; this half's 8 frames are 48
+                        // bytes = three 16-byte units; sample k of channel c sits at byte 6k + 3c
+                        const uint32_t rb = base + ml * 96u + wg * 48u;
+                        uint32_t w[13];
+#pragma unroll
+                        for (uint32_t u = 0; u < 3; ++u) {
+                            const float4 q4 = lds128(rb + 16u * u);
+                            w[4 * u] = __float_as_uint(q4.x); w[4 * u + 1] = __float_as_uint(q4.y);
+                            w[4 * u + 2] = __float_as_uint(q4.z); w[4 * u + 3] = __float_as_uint(q4.w);
+                        }
+                        w[12] = 0;
+#pragma unroll
+                        for (uint32_t k = 0; k < 8; ++k) {
+                            const uint32_t o0 = 6 * k, o1 = 6 * k + 3;
+                            const uint32_t v0 = __funnelshift_r(w[o0 >> 2], w[(o0 >> 2) + 1], (o0 & 3u) * 8u);
+                            const uint32_t v1 = __funnelshift_r(w[o1 >> 2], w[(o1 >> 2) + 1], (o1 & 3u) * 8u);
+                            const uint32_t vv = c ? v1 : v0;
+                            x[k] = (float)((int)(vv << 8) >> 8) * (1.0f / 8388608.0f);
+                        }
+                    } else if (SB == 3 && kRawMono) {
+                        // packed s24 mono: unswizzled 48-byte rows; this half's 8 frames are 24 bytes
+                        const uint32_t rb = base + ml * 48u + wg * 24u;
+                        uint32_t w[7];
+#pragma unroll
+                        for (uint32_t u = 0; u < 3; ++u) {
+                            const float2 q2 = lds64(rb + 8u * u);
+                            w[2 * u] = __float_as_uint(q2.x); w[2 * u + 1] = __float_as_uint(q2.y);
+                        }
+                        w[6] = 0;
+#pragma unroll
+                        for (uint32_t k = 0; k < 8; ++k) {
+                            const uint32_t o = 3 * k;
+                            const uint32_t vv = __funnelshift_r(w[o >> 2], w[(o >> 2) + 1], (o & 3u) * 8u);
+                            x[k] = (float)((int)(vv << 8) >> 8) * (1.0f / 8388608.0f);
+                        }
+                    } else if (kRawMono) {
                         // raw s16 mono: unswizzled 32-byte rows (16 frames), one per member; both
                         // channel rows of a stereo member read the same samples (RAW == 2)
                         const float4 q4 = lds128(base + ml * 32u + wg * 16u);
@@ -767,7 +809,7 @@ bool tc_make_input_tensor_map(CUtensorMap *out, const float *base, uint64_t stri
 
 bool tc_make_raw16_tensor_map(CUtensorMap *out, const void *base, uint64_t stride_bytes,
                               uint64_t total_frames, uint32_t n_members, uint32_t src_channels,
-                              uint32_t channels) {
+                              uint32_t channels, uint32_t sample_bytes) {
     typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
                                       const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                       const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -783,11 +825,23 @@ bool tc_make_raw16_tensor_map(CUtensorMap *out, const void *base, uint64_t strid
     if (total_frames == 0 || total_frames >= (1ull << 31)) return false;
     if ((reinterpret_cast<uintptr_t>(base) & 15u) || (stride_bytes & 15u) || stride_bytes == 0)
         return false;
-    if (stride_bytes < total_frames * 2ull * src_channels) return false;
+    if (sample_bytes != 2 && sample_bytes != 3) return false;
+    if (stride_bytes < total_frames * (uint64_t)sample_bytes * src_channels) return false;
     cuuint64_t dims[2] = {total_frames, n_members};
     cuuint64_t strides[1] = {stride_bytes};
     cuuint32_t box[2] = {kChunk, (cuuint32_t)(kRows / channels)};
     cuuint32_t estr[2] = {1, 1};
+    if (sample_bytes == 3) {
+        // packed s24: element = one byte, a frame is 3 * src_channels of them, no swizzle
+        const uint32_t fb = 3u * src_channels;
+        dims[0] = total_frames * fb;
+        box[0] = kChunk * fb;
+        const CUresult r3 = ((EncodeTiledFn)fn)(
+            out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        return r3 == CUDA_SUCCESS;
+    }
     // element = one raw frame: two s16 (32 bits, 64-byte rows, 64B swizzle) or one s16 (32-byte
     // rows, no swizzle); frames past the end read as zeros
     const bool stereo = src_channels == 2;
@@ -824,11 +878,14 @@ void launch_conv_tc(const TcParams &p, const CUtensorMap &tmap, int sm_count, bo
     };
     switch (p.channels) {
         case 1:
-            if (p.raw16) launch(conv_tc_kernel<1, 1>);
+            if (p.raw16 && p.raw_bytes == 3) launch(conv_tc_kernel<1, 1, 3>);
+            else if (p.raw16) launch(conv_tc_kernel<1, 1>);
             else launch(conv_tc_kernel<1>);
             break;
         case 2:
-            if (p.raw16 == 2) launch(conv_tc_kernel<2, 2>);
+            if (p.raw16 == 2 && p.raw_bytes == 3) launch(conv_tc_kernel<2, 2, 3>);
+            else if (p.raw16 == 1 && p.raw_bytes == 3) launch(conv_tc_kernel<2, 1, 3>);
+            else if (p.raw16 == 2) launch(conv_tc_kernel<2, 2>);
             else if (p.raw16 == 1) launch(conv_tc_kernel<2, 1>);
             else launch(conv_tc_kernel<2>);
             break;

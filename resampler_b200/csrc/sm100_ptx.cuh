@@ -61,6 +61,11 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
                  : "r"(addr));
     return v;
 }
+__device__ __forceinline__ float2 lds64(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
 // TMA tiled tensor copy global -> shared of one 2-D box (SASS: UTMALDG)
 __device__ __forceinline__ void tensor_g2s_2d(void *dst, const CUtensorMap *tm, int c0, int c1,
                                               uint64_t *bar) {

@@ -138,7 +138,10 @@ def test_errors():
     (Kernel.TENSOR, PcmFormat.S16, 2, 2, False),    # rows not 16-byte aligned: separate format pass
     (Kernel.TENSOR, PcmFormat.S16, 2, 1, True),     # fused, mono source duplicated (main.rs:139-146)
     (Kernel.TENSOR, PcmFormat.S16, 1, 1, True),     # fused, mono streams
-    (Kernel.TENSOR, PcmFormat.S24, 2, 1, True),
+    (Kernel.TENSOR, PcmFormat.S24, 2, 1, True),     # fused, packed 24-bit mono source
+    (Kernel.TENSOR, PcmFormat.S24, 2, 2, True),     # fused, packed 24-bit stereo
+    (Kernel.TENSOR, PcmFormat.S24, 1, 1, True),     # fused, packed 24-bit mono streams
+    (Kernel.TENSOR, PcmFormat.S32, 2, 2, True),     # 32-bit: separate format pass
     (Kernel.FAST, PcmFormat.S16, 2, 1, True),
 ])
 def test_device_resident_pcm_batch_fast_kernels(kernel, fmt, ch, src_ch, aligned):
@@ -177,7 +180,8 @@ def test_device_resident_pcm_batch_fast_kernels(kernel, fmt, ch, src_ch, aligned
     cons, prod, calls = run(raws, frames)
     assert batch.last_kernel() == kernel
     assert batch.last_ingest_ms() > 0.0
-    assert batch.last_pcm_fused() == (kernel == Kernel.TENSOR and fmt == PcmFormat.S16 and aligned)
+    assert batch.last_pcm_fused() == (kernel == Kernel.TENSOR and aligned
+                                      and fmt in (PcmFormat.S16, PcmFormat.S24))
     firsts = {i: fetch(i, prod[i]) for i in (0, 1, 31, 63)}
     cons2, prod2, _ = run(raws2, 1500)
     worst = 0.0
@@ -198,19 +202,20 @@ def test_device_resident_pcm_batch_fast_kernels(kernel, fmt, ch, src_ch, aligned
     batch.close()
 
 
+@pytest.mark.parametrize("fmt", [PcmFormat.S16, PcmFormat.S24])
 @pytest.mark.parametrize("ch,src_ch", [(2, 2), (2, 1), (1, 1)])
-def test_fused_and_separate_format_step_agree_bit_for_bit(monkeypatch, ch, src_ch):
+def test_fused_and_separate_format_step_agree_bit_for_bit(monkeypatch, ch, src_ch, fmt):
     """The tensor kernel converting raw s16 frames in its loader and the separate format pass
     feed the same f32 values into the same arithmetic: identical output bits (host buffers)."""
     n, frames = 64, 5000
     rng = np.random.default_rng(123)
-    raws = [raw_samples(rng, PcmFormat.S16, frames * src_ch) for _ in range(n)]
+    raws = [raw_samples(rng, fmt, frames * src_ch) for _ in range(n)]
     outs = []
     for unfused in (False, True):
         if unfused:
             monkeypatch.setenv("RSB_PCM_UNFUSED", "1")
         batch = FirBatch(n, ch, 44100, 48000, Latency.Sample64, Attenuation.Db90, kernel=Kernel.TENSOR)
-        res = batch.process_pcm(raws, PcmFormat.S16, src_ch, call_len=512 * ch)
+        res = batch.process_pcm(raws, fmt, src_ch, call_len=512 * ch)
         assert batch.last_pcm_fused() == (not unfused)
         tail = batch.flush()
         outs.append([np.concatenate([a, b]) for a, b in zip(res["out"], tail)])
@@ -282,8 +287,9 @@ def test_larger_device_batch_fused_equals_separate_and_exact(monkeypatch):
     lib.rsb_free_device(0, d_out)
 
 
+@pytest.mark.parametrize("fmt", [PcmFormat.S16, PcmFormat.S24])
 @pytest.mark.parametrize("ch,src_ch", [(2, 2), (2, 1), (1, 1)])
-def test_fused_loader_tiny_and_odd_lengths(ch, src_ch):
+def test_fused_loader_tiny_and_odd_lengths(ch, src_ch, fmt):
     """Fused raw-s16 loader at the small end: files of 1 .. 300 frames (shorter than one TMA
     box, than the filter, not multiples of anything), several batches in a row on the same
     streams so that history and phase carry through the raw tail conversion."""
@@ -293,11 +299,11 @@ def test_fused_loader_tiny_and_odd_lengths(ch, src_ch):
     refs = [O.OracleFir(ch, 44100, 48000, 3, 1) for _ in range(4)]
     worst = 0.0
     for frames in (1, 5, 17, 127, 128, 300, 2):
-        raws = [raw_samples(rng, PcmFormat.S16, frames * src_ch) for _ in range(n)]
-        res = batch.process_pcm(raws, PcmFormat.S16, src_ch, call_len=512 * ch)
+        raws = [raw_samples(rng, fmt, frames * src_ch) for _ in range(n)]
+        res = batch.process_pcm(raws, fmt, src_ch, call_len=512 * ch)
         assert batch.last_pcm_fused() and batch.last_kernel() == Kernel.TENSOR
         for k, s in enumerate((0, 1, 31, 63)):
-            x = O.pcm_to_f32(raws[s], O.PCM_S16, 1 if src_ch == ch else ch)
+            x = O.pcm_to_f32(raws[s], int(fmt), 1 if src_ch == ch else ch)
             ref = refs[k].process(x, 512 * ch)
             assert res["consumed"][s] == ref["consumed_total"] and res["produced"][s] == len(ref["out"])
             if len(ref["out"]):
