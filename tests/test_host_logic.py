@@ -270,3 +270,34 @@ def test_wav_batch_tool_rejects_what_the_cli_rejects(tmp_path):
     write_wav_pcm(odd, np.zeros(200, np.int16), 12345, 2, 16)
     with pytest.raises(SystemExit, match="Unsupported input sample rate: 12345"):
         resample_wav.resample_files([odd], tmp_path / "o", 48000)
+
+
+def _c_prototypes(text):
+    """name -> number of parameters, for every rsb_* prototype in a C header."""
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(rsb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    return out
+
+
+def test_rust_and_ctypes_bindings_match_the_header_arity():
+    """The Rust crate cannot be compiled here (no rustc), so at least its extern block is held
+    against include/resampler_b200.h: every bound symbol exists with the same parameter count;
+    the same for the ctypes signature table."""
+    protos = _c_prototypes((ROOT / "include" / "resampler_b200.h").read_text())
+    assert len(protos) > 40
+    rust = (ROOT / "resampler-cuda" / "src" / "lib.rs").read_text()
+    block = rust[rust.index('unsafe extern "C"'):]
+    block = block[:block.index("\n}")]
+    bound = {}
+    for m in re.finditer(r"fn\s+(rsb_[a-z0-9_]+)\s*\(([^)]*)\)", block, flags=re.S):
+        args = m.group(2).strip()
+        bound[m.group(1)] = 0 if not args else len([a for a in args.split(",") if a.strip()])
+    assert len(bound) >= 10
+    for name, n in bound.items():
+        assert name in protos, f"{name} bound in lib.rs but not declared in the header"
+        assert protos[name] == n, f"{name}: header has {protos[name]} parameters, lib.rs {n}"
+    for name, (_, args) in _lib.SIGNATURES.items():
+        assert protos[name] == len(args), f"{name}: header {protos[name]} vs ctypes {len(args)}"
