@@ -301,3 +301,34 @@ def test_rust_and_ctypes_bindings_match_the_header_arity():
         assert protos[name] == n, f"{name}: header has {protos[name]} parameters, lib.rs {n}"
     for name, (_, args) in _lib.SIGNATURES.items():
         assert protos[name] == len(args), f"{name}: header {protos[name]} vs ctypes {len(args)}"
+
+
+def test_cpp_mirror_header_compiles_and_links(tmp_path):
+    """include/resampler_b200.hpp (the C++ mirror of the reference interface) compiles as C++17
+    and links against the built library; without a GPU the constructor must throw, not fall back."""
+    import shutil
+    import subprocess
+    if not shutil.which("g++"):
+        pytest.skip("no g++")
+    src = tmp_path / "t.cpp"
+    src.write_text(
+        '#include "resampler_b200.hpp"\n'
+        '#include <cstdio>\n'
+        'int main() {\n'
+        '    using namespace resampler_b200;\n'
+        '    std::vector<const void *> in; std::vector<size_t> fr, caps, c, p; std::vector<float *> out;\n'
+        '    try {\n'
+        '        FirBatch b(4, 2, 44100, 48000, Latency::Sample64, Attenuation::Db90, 0);\n'
+        '        b.process_pcm(in, fr, RSB_PCM_S16, 2, 512, out, caps, c, p);\n'
+        '        b.flush(out, caps, p);\n'
+        '        std::printf("constructed %zu\\n", b.buffer_size_output());\n'
+        '    } catch (const std::exception &e) { std::printf("threw: %s\\n", e.what()); }\n'
+        '    return 0;\n'
+        '}\n')
+    exe = tmp_path / "t"
+    lib_dir = ROOT / "resampler_b200" / "lib"
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-I", str(ROOT / "include"), str(src), "-o", str(exe),
+                    "-L", str(lib_dir), "-lresampler_b200", f"-Wl,-rpath,{lib_dir}"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert "threw:" in r.stdout or "constructed" in r.stdout
