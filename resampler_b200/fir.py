@@ -297,9 +297,14 @@ class FirBatch:
         fmt = PcmFormat(fmt)
         n = len(inputs)
         bps = fmt.bytes_per_sample()
-        # uint8 arrays are taken as the file's raw bytes, anything else as sample values
-        inputs = [np.ascontiguousarray(a) if a.dtype == np.uint8
-                  else np.ascontiguousarray(a, _PCM_DTYPES[fmt]) for a in map(np.asarray, inputs)]
+        # uint8 arrays are taken as the file's raw bytes, anything else must already have the
+        # format's sample type (a silent value cast would change the audio)
+        inputs = [np.asarray(a) for a in inputs]
+        for a in inputs:
+            if a.dtype != np.uint8 and a.dtype != _PCM_DTYPES[fmt]:
+                raise TypeError(f"{fmt.name} input must be uint8 bytes or {np.dtype(_PCM_DTYPES[fmt]).name}, "
+                                f"not {a.dtype.name}")
+        inputs = [np.ascontiguousarray(a) for a in inputs]
         frames = []
         for a in inputs:
             if a.nbytes % (bps * src_channels) != 0:

@@ -332,3 +332,16 @@ def test_cpp_mirror_header_compiles_and_links(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr
     assert "threw:" in r.stdout or "constructed" in r.stdout
+
+
+def test_process_pcm_rejects_mismatched_sample_types():
+    """A float array handed in as S16 (or int16 as packed S24) would be value-cast silently:
+    refused before anything reaches the library (no GPU needed: the check comes first)."""
+    from resampler_b200 import PcmFormat
+    from resampler_b200.fir import FirBatch
+    fb = FirBatch.__new__(FirBatch)          # no handle: the type check runs before any native call
+    fb.channels = 2
+    with pytest.raises(TypeError, match="S16 input must be uint8 bytes or int16"):
+        FirBatch.process_pcm(fb, [np.zeros(8, np.float32)], PcmFormat.S16, 2)
+    with pytest.raises(TypeError, match="S24 input must be uint8 bytes"):
+        FirBatch.process_pcm(fb, [np.zeros(8, np.int16)], PcmFormat.S24, 2)
