@@ -212,8 +212,9 @@ int rsb_fir_conv_times(rsb_fir *h, float *ms, size_t max, size_t *n);
  * [5] register-tiled product, [6] store.  Returns and clears the counters; sets the enable flag. */
 int rsb_debug_phase_cycles(rsb_fir *h, int enable, uint64_t *out8);
 /* debug: per-role SM cycle totals of the tensor kernel (CTA 0; the index list is in
- * fir_tensor.cu).  Returns and clears the 16 counters; sets the enable flag. */
-int rsb_debug_tc_cycles(rsb_fir *h, int enable, uint64_t *out16);
+ * fir_tc2.cu).  Copies min(count, 24) counters into out (may be NULL), clears them and sets
+ * the enable flag. */
+int rsb_debug_tc_cycles(rsb_fir *h, int enable, uint64_t *out, uint32_t count);
 /* kernels launched on this handle since creation (your own count for gpu_launches) */
 uint64_t rsb_fir_launch_count(const rsb_fir *h);
 /* the handle's cudaStream_t, as an opaque pointer */

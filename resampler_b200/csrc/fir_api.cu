@@ -96,6 +96,7 @@ struct Pending {
 // submit i is still running on the main stream.
 struct Workspace {
     DevBuf d_units, d_jobs, d_segs, d_calls, d_tiles, d_entries, d_gtiles, d_tct, d_counter;
+    DevBuf d_tct2, d_gmat2;   // tensor kernel generation 2: 64-output tile records, fp16 G store
     PinBuf h_units, h_jobs, h_units_back, h_calls_back, h_segs, h_counter;
     DevBuf d_pcm_jobs;   // job table of the PCM format step (rsb_fir_process_pcm_batch)
     PinBuf h_pcm_jobs;
@@ -497,7 +498,8 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     // AUTO: when at least half of a 128-row group is filled (below that the MMA's M is mostly idle)
     const bool want_tc = h->kernel_mode == RSB_KERNEL_TENSOR ||
                          (h->kernel_mode == RSB_KERNEL_AUTO && (uint64_t)n * ch >= 64);
-    if (want_tc && in_uniform && rsb::tc_supported(ch, h->taps, h->ratio))
+    if (want_tc && in_uniform &&
+        (rsb::tc2_supported(ch, h->taps, h->ratio) || rsb::tc_supported(ch, h->taps, h->ratio)))
         use_tc = rsb::tc_make_input_tensor_map(&tc_tmap, hj[0].in, in_stride,
                                                unit_keys[0].total_frames, n, ch);
 
@@ -507,13 +509,7 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     RSB_CUDA(W.d_tiles.reserve(sizeof(rsb::TileRec) * tile_total));
     RSB_CUDA(W.d_entries.reserve(sizeof(rsb::PlanEntry) * rsb::kTileOut * tile_total));
     const uint32_t gs = use_fast ? rsb::fast_row_stride(ch, h->taps, h->ratio) : 0;
-    if (use_tc) {
-        RSB_CUDA(W.d_gtiles.reserve(sizeof(float) * rsb::tc_gmat_floats_per_tile(h->taps, h->ratio) *
-                                    tile_total));
-        RSB_CUDA(W.d_tct.reserve(sizeof(rsb::TcTile) * tile_total));
-    } else if (use_fast) {
-        RSB_CUDA(W.d_gtiles.reserve(sizeof(float) * rsb::kTileOut * gs * tile_total));
-    }
+    if (!use_tc && use_fast) RSB_CUDA(W.d_gtiles.reserve(sizeof(float) * rsb::kTileOut * gs * tile_total));
     RSB_CUDA(W.d_counter.reserve(sizeof(uint32_t) * 4));
     if (rec_calls) {
         RSB_CUDA(W.d_calls.reserve(sizeof(rsb::CallCounts) * std::max<uint64_t>(call_total, 1)));
@@ -552,6 +548,38 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
             h->m_ok[jobs[i].stream] = 0;
             h->m_pending[jobs[i].stream] = h->submits;
         }
+    }
+    // Tensor kernel generation 2 (fir_tc2.cu): additionally needs the plan's totals on the host
+    // (its TMA stores clip to what the plan produces) and equally strided, 16-byte aligned outputs.
+    bool use_tc2 = false;
+    CUtensorMap tc2_out_map;
+    uint64_t tc2_tiles = 0;
+    if (use_tc && host_plan && hu[0].total_out > 0 && rsb::tc2_supported(ch, h->taps, h->ratio) &&
+        rsb::tc2_g_stages(ch, h->taps, h->ratio) >= 2 && !getenv("RSB_TC_V1")) {
+        const uintptr_t obase = reinterpret_cast<uintptr_t>(hj[0].out);
+        uint64_t ostride = n > 1 ? (uint64_t)(reinterpret_cast<uintptr_t>(hj[1].out) - obase) : 0;
+        bool ok = n == 1 || reinterpret_cast<uintptr_t>(hj[1].out) > obase;
+        uint64_t min_cap = ~0ull;
+        for (uint32_t i = 0; i < n; ++i) {
+            if (ok && i > 0) ok = reinterpret_cast<uintptr_t>(hj[i].out) == obase + (uint64_t)i * ostride;
+            min_cap = std::min<uint64_t>(min_cap, hj[i].out_capacity);
+        }
+        const uint64_t valid = std::min<uint64_t>(hu[0].total_out, min_cap);
+        if (n == 1) ostride = (valid * ch * 4 + 15) & ~15ull;
+        if (ok && valid > 0)
+            use_tc2 = rsb::tc2_make_output_tensor_map(&tc2_out_map, hj[0].out, ostride, valid, n, ch);
+        tc2_tiles = (hu[0].total_out + rsb::kTc2TileOut - 1) / rsb::kTc2TileOut;
+    }
+    if (use_tc2) {
+        RSB_CUDA(W.d_tct2.reserve(sizeof(rsb::Tc2Tile) * tc2_tiles));
+        RSB_CUDA(W.d_gmat2.reserve(rsb::tc2_gmat_bytes_per_tile(h->taps, h->ratio) * tc2_tiles));
+    } else if (use_tc && !rsb::tc_supported(ch, h->taps, h->ratio)) {
+        use_tc = false;      // generation 1 cannot take this ratio: FFMA2 / exact kernel
+        if (use_fast) RSB_CUDA(W.d_gtiles.reserve(sizeof(float) * rsb::kTileOut * gs * tile_total));
+    } else if (use_tc) {
+        RSB_CUDA(W.d_gtiles.reserve(sizeof(float) * rsb::tc_gmat_floats_per_tile(h->taps, h->ratio) *
+                                    tile_total));
+        RSB_CUDA(W.d_tct.reserve(sizeof(rsb::TcTile) * tile_total));
     }
     RSB_CUDA(cudaMemcpyAsync(W.d_units.p, hu, sizeof(UnitDev) * n_units, cudaMemcpyHostToDevice, sp));
     RSB_CUDA(cudaMemcpyAsync(W.d_jobs.p, hj, sizeof(JobDev) * n, cudaMemcpyHostToDevice, sp));
@@ -714,7 +742,13 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
                       W.d_tiles.as<rsb::TileRec>(), W.d_entries.as<rsb::PlanEntry>(),
                       (uint32_t)max_tiles_unit, h->taps, h->d_coeffs,
                       use_fast && !use_tc ? W.d_gtiles.as<float>() : nullptr, gs, s);
-    if (use_tc)
+    if (use_tc2) {
+        rsb::launch_tc2_tiles(W.d_units.as<UnitDev>(), W.d_entries.as<rsb::PlanEntry>(),
+                              W.d_tct2.as<rsb::Tc2Tile>(), h->taps, h->ratio, (uint32_t)tc2_tiles, s);
+        rsb::launch_tc2_gmat(W.d_units.as<UnitDev>(), W.d_entries.as<rsb::PlanEntry>(), h->d_coeffs,
+                             W.d_tct2.as<rsb::Tc2Tile>(), nullptr, nullptr, W.d_gmat2.as<uint8_t>(), h->taps,
+                             h->ratio, (uint32_t)tc2_tiles, s);
+    } else if (use_tc)
         rsb::launch_tc_gmat(W.d_units.as<UnitDev>(), W.d_tiles.as<rsb::TileRec>(),
                             W.d_entries.as<rsb::PlanEntry>(), h->d_coeffs, W.d_gtiles.as<float>(),
                             W.d_tct.as<rsb::TcTile>(), h->taps, h->ratio, (uint32_t)tile_total, s);
@@ -744,7 +778,30 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     const uint32_t max_items = (uint32_t)(tile_total * max_groups);
     const int ring = (int)(h->conv_batches % rsb_fir::kConvRing);
     RSB_CUDA(cudaEventRecord(h->ev_conv[ring][0], s));
-    if (use_tc) {
+    if (use_tc2) {
+        rsb::Tc2Params T;
+        T.units = P.units;
+        T.jobs = P.jobs;
+        T.tct = W.d_tct2.as<rsb::Tc2Tile>();
+        T.gmat = W.d_gmat2.as<uint8_t>();
+        T.work_counter = P.work_counter;
+        T.channels = ch;
+        const uint32_t mpg = rsb::tc2_rows_per_group() / ch;
+        T.groups = (n + mpg - 1) / mpg;
+        // a run of consecutive tiles is one work item: long enough to amortise filling the input
+        // ring (~4 tiles), short enough that every CTA gets several items and the tail is short
+        const uint64_t want = (tc2_tiles * T.groups) / ((uint64_t)h->sm_count * 8u) + 1;
+        T.run_tiles = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 16), 96);
+        if (getenv("RSB_TC_RUN_TILES")) T.run_tiles = (uint32_t)atoi(getenv("RSB_TC_RUN_TILES"));
+        T.kt_max = rsb::tc2_kt_extent(h->taps, h->ratio);
+        T.issuers = rsb::tc2_issuers(h->taps, h->ratio);
+        T.g_stages = rsb::tc2_g_stages(ch, h->taps, h->ratio);
+        if (getenv("RSB_TC_GSTAGES")) T.g_stages = std::min<uint32_t>(T.g_stages, (uint32_t)atoi(getenv("RSB_TC_GSTAGES")));
+        T.raw16 = pcm_fused ? pcm_raw_mode : 0u;
+        T.raw_bytes = pcm && pcm_fused ? pcm->bps : 2u;
+        if (getenv("RSB_TC_ISSUERS")) T.issuers = atoi(getenv("RSB_TC_ISSUERS")) == 1 ? 1u : T.issuers;
+        rsb::launch_conv_tc2(T, tc_tmap, tc2_out_map, h->sm_count, false, s);
+    } else if (use_tc) {
         rsb::TcParams T;
         T.units = P.units;
         T.jobs = P.jobs;
@@ -775,7 +832,7 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     RSB_CUDA(cudaEventRecord(h->ev_conv[ring][1], s));
     h->conv_batches += 1;
     rsb::launch_update(W.d_units.as<UnitDev>(), W.d_jobs.as<JobDev>(), n, h->st, ch, s);
-    h->launches += (use_tc ? 6 : 5) - (host_plan ? 1 : 0);
+    h->launches += (use_tc2 ? 7 : use_tc ? 6 : 5) - (host_plan ? 1 : 0);
     RSB_CUDA(cudaGetLastError());
     RSB_CUDA(cudaEventRecord(W.ev_done, s));
     h->submits += 1;
@@ -987,7 +1044,8 @@ int rsb_fir_set_kernel(rsb_fir *h, int kernel) {
     if (check_handle(h)) return RSB_ERR_INVALID_ARGUMENT;
     if (kernel < RSB_KERNEL_AUTO || kernel > RSB_KERNEL_TENSOR)
         return fail(RSB_ERR_INVALID_ARGUMENT, "bad kernel id");
-    if (kernel == RSB_KERNEL_TENSOR && !rsb::tc_supported(h->channels, h->taps, h->ratio))
+    if (kernel == RSB_KERNEL_TENSOR && !rsb::tc2_supported(h->channels, h->taps, h->ratio) &&
+        !rsb::tc_supported(h->channels, h->taps, h->ratio))
         return fail(RSB_ERR_INVALID_ARGUMENT, "tensor kernel does not support this configuration");
     if (kernel == RSB_KERNEL_FAST && !rsb::fast_supported(h->channels, h->taps, h->ratio))
         return fail(RSB_ERR_INVALID_ARGUMENT, "fast kernel does not support this configuration");
@@ -1338,11 +1396,17 @@ int rsb_debug_phase_cycles(rsb_fir *h, int enable, uint64_t *out8) {
     return RSB_OK;
 }
 
-int rsb_debug_tc_cycles(rsb_fir *h, int enable, uint64_t *out16) {
+int rsb_debug_tc_cycles(rsb_fir *h, int enable, uint64_t *out, uint32_t count) {
     if (check_handle(h)) return RSB_ERR_INVALID_ARGUMENT;
     RSB_CUDA(cudaSetDevice(h->device));
-    RSB_CUDA(cudaStreamSynchronize(h->stream));
-    rsb::tc_phase_profile(enable, reinterpret_cast<unsigned long long *>(out16));
+    RSB_CUDA(cudaDeviceSynchronize());
+    if (getenv("RSB_TC_V1")) {
+        unsigned long long tmp[24] = {0};
+        rsb::tc_phase_profile(enable, tmp);
+        if (out) std::memcpy(out, tmp, sizeof(uint64_t) * std::min<uint32_t>(count, 24u));
+    } else {
+        rsb::tc2_phase_profile(enable, reinterpret_cast<unsigned long long *>(out), count);
+    }
     RSB_CUDA(cudaGetLastError());
     return RSB_OK;
 }

@@ -122,4 +122,50 @@ void launch_conv_tc(const TcParams &p, const CUtensorMap &tmap, int sm_count, bo
 // debug: returns and clears the tensor kernel's per-role cycle counters, sets the enable flag
 void tc_phase_profile(int enable, unsigned long long *out16);
 
+// ---- tensor-core convolution, generation 2 (fir_tc2.cu): fp16 hi/lo operands, 64-output tiles ----
+constexpr uint32_t kTc2TileOut = 64;   // output frames per tensor tile (two plan tiles)
+struct Tc2Tile {
+    int32_t k0;        // first virtual frame of the tile's K range (on the 16-frame chunk grid anchored at H)
+    uint32_t kt;       // K extent in frames (multiple of 16)
+    uint32_t n_out;
+    uint32_t o_start;
+    uint32_t g_idx;    // index of the tile's [G_hi, G_lo] matrices in the G store
+    uint32_t pad[3];
+};
+struct Tc2Params {
+    const UnitDev *units;     // exactly one plan unit
+    const JobDev *jobs;
+    const Tc2Tile *tct;       // [tile]
+    const uint8_t *gmat;      // [stored tile][hi, lo][kt_max / 8][64][8 halves]
+    uint32_t *work_counter;   // zeroed per submit
+    uint32_t channels;
+    uint32_t groups;          // member groups of 128 / channels streams
+    uint32_t run_tiles;       // consecutive tiles per work item
+    uint32_t kt_max;
+    uint32_t issuers;         // MMA issuer warps: 2 when two consecutive tiles fit the TMEM ring
+    uint32_t g_stages;        // shared-memory stages of G matrices (2 or 3)
+    uint32_t raw16;           // as TcParams::raw16
+    uint32_t raw_bytes;       // bytes per raw sample: 2 (s16) or 3 (packed s24)
+};
+bool tc2_supported(uint32_t channels, uint32_t taps, double ratio);
+uint32_t tc2_kt_extent(uint32_t taps, double ratio);
+size_t tc2_gmat_bytes_per_tile(uint32_t taps, double ratio);
+uint32_t tc2_rows_per_group();
+uint32_t tc2_issuers(uint32_t taps, double ratio);
+uint32_t tc2_g_stages(uint32_t channels, uint32_t taps, double ratio);
+// Output of an equally strided batch as a 2-D tensor for the epilogue's TMA stores; inner
+// dimension clipped to `valid_frames` (what the plan produces, capped by the smallest capacity).
+bool tc2_make_output_tensor_map(CUtensorMap *out, float *base, uint64_t stride_bytes, uint64_t valid_frames,
+                                uint32_t n_members, uint32_t channels);
+void launch_tc2_tiles(const UnitDev *units, const PlanEntry *entries, Tc2Tile *tct, uint32_t taps, double ratio,
+                      uint32_t tile_cap, cudaStream_t stream);
+// src_tile / n_stored: optional de-duplication (stored matrix g is built from tile src_tile[g])
+void launch_tc2_gmat(const UnitDev *units, const PlanEntry *entries, const float *coeffs, const Tc2Tile *tct,
+                     const uint32_t *src_tile, const uint32_t *n_stored, uint8_t *gmat, uint32_t taps,
+                     double ratio, uint32_t max_stored, cudaStream_t stream);
+bool launch_conv_tc2(const Tc2Params &p, const CUtensorMap &tmap_in, const CUtensorMap &tmap_out, int sm_count,
+                     bool leave_sm_free, cudaStream_t stream);
+// debug: returns (up to `count` of 24) and clears the kernel's per-role cycle counters, sets the enable flag
+void tc2_phase_profile(int enable, unsigned long long *out, uint32_t count);
+
 }  // namespace rsb

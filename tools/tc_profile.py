@@ -13,9 +13,9 @@ from resampler_b200 import Attenuation, FirBatch, Kernel, Latency, _lib  # noqa:
 from resampler_b200.fir import FLAG_ASYNC, MEM_DEVICE, DeviceBuffer  # noqa: E402
 
 NAMES = ["M.wait_x_full", "M.wait_g_full", "M.wait_d_empty", "M.issue", "M.commit+meta",
-         "S.wait_x_empty", "S.wait_xs_full", "S.split+st", "E.wait_d_full", "E.ld+stage", "E.store",
-         "S.wait_st+arrive", "S.st", "kernel", "tiles", "S.other", "M.fence+addr", "M.small_pass",
-         "M.commit1", "M.commit2", "x", "x", "x", "x"]
+         "S.wait_x_empty", "S.wait_xs_full", "S.load+split", "E.wait_t_done", "E.ld+stage", "E.tma_store",
+         "S.wait_st+arrive", "S.st", "kernel", "tiles", "S.other", "J.wait_t_done", "J.release",
+         "G.wait_t_done", "G.issue", "x", "x", "x", "x"]
 
 
 def main():
@@ -36,12 +36,12 @@ def main():
     b.sync()
     assert b.last_kernel() == Kernel.TENSOR
     out = (C.c_uint64 * 24)()
-    lib.rsb_debug_tc_cycles(b._h, 1, out)
+    lib.rsb_debug_tc_cycles(b._h, 1, out, 24)
     b.reset(-1)
     b.process_ptrs(*args, memspace=MEM_DEVICE, flags=FLAG_ASYNC)
     b.sync()
     conv_ms = float(b.conv_times_ms(1)[0])
-    lib.rsb_debug_tc_cycles(b._h, 0, out)
+    lib.rsb_debug_tc_cycles(b._h, 0, out, 24)
     cyc = np.array(out[:], dtype=np.float64)
     tiles = max(cyc[14], 1.0)
     res = {"conv_ms": conv_ms, "tiles_cta0": int(cyc[14]), "kernel_cycles_per_tile": round(cyc[13] / tiles, 1),
