@@ -796,6 +796,8 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
         T.kt_max = rsb::tc2_kt_extent(h->taps, h->ratio);
         T.issuers = rsb::tc2_issuers(h->taps, h->ratio);
         T.g_stages = rsb::tc2_g_stages(ch, h->taps, h->ratio);
+        T.prefetch_chunks = getenv("RSB_TC_PREFETCH") ? (uint32_t)atoi(getenv("RSB_TC_PREFETCH")) : 12u;
+        T.out_scale = rsb::tc2_out_scale(getenv("RSB_TC_COMP") ? atof(getenv("RSB_TC_COMP")) : 0.0);
         if (getenv("RSB_TC_GSTAGES")) T.g_stages = std::min<uint32_t>(T.g_stages, (uint32_t)atoi(getenv("RSB_TC_GSTAGES")));
         T.raw16 = pcm_fused ? pcm_raw_mode : 0u;
         T.raw_bytes = pcm && pcm_fused ? pcm->bps : 2u;

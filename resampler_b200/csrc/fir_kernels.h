@@ -146,7 +146,10 @@ struct Tc2Params {
     uint32_t g_stages;        // shared-memory stages of G matrices (2 or 3)
     uint32_t raw16;           // as TcParams::raw16
     uint32_t raw_bytes;       // bytes per raw sample: 2 (s16) or 3 (packed s24)
+    uint32_t prefetch_chunks; // input chunks the TMA producer prefetches into L2 ahead of its loads
+    float out_scale;          // epilogue factor: 2^-17 x truncation-bias compensation (tc2_out_scale)
 };
+float tc2_out_scale(double comp);
 bool tc2_supported(uint32_t channels, uint32_t taps, double ratio);
 uint32_t tc2_kt_extent(uint32_t taps, double ratio);
 size_t tc2_gmat_bytes_per_tile(uint32_t taps, double ratio);

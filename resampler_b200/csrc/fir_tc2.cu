@@ -203,6 +203,12 @@ __device__ __forceinline__ void tensor_s2g_2d(const CUtensorMap *tm, int c0, int
                  "r"(c0), "r"(c1), "r"(smem_addr)
                  : "memory");
 }
+// L2 prefetch of one 2-D box (no shared memory involved): hides the HBM latency of the input
+// stream behind a handful of landing buffers
+__device__ __forceinline__ void tensor_prefetch_2d(const CUtensorMap *tm, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
@@ -424,17 +430,25 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
                 mbar_arrive(&S.item_full[slot]);
                 if (!I.valid) break;
                 const int32_t m0 = (int32_t)(I.group * kMpg);
+                // inner coordinate in tensor-map elements: frames (mono f32, stereo 8-byte frames,
+                // raw frames), bytes (packed s24) or floats (4 / 8 channels)
+                constexpr int32_t kCoordMul = (int32_t)(SB == 3 ? kRawFrameBytes : CH >= 4 ? CH : 1);
+                const uint32_t pf = P.prefetch_chunks;
+                for (uint32_t j = 0; j < min(pf, I.n_chunks); ++j) {
+                    const int32_t v = I.vb + (int32_t)(j * kChunk);
+                    if (v >= H) tensor_prefetch_2d(&tmap_in, (v - H) * kCoordMul, m0);
+                }
                 for (uint32_t j = 0; j < I.n_chunks; ++j) {
                     const int32_t v = I.vb + (int32_t)(j * kChunk);
+                    if (j + pf < I.n_chunks) {
+                        const int32_t vp = v + (int32_t)(pf * kChunk);
+                        if (vp >= H) tensor_prefetch_2d(&tmap_in, (vp - H) * kCoordMul, m0);
+                    }
                     if (v < H) continue;       // touches the history: the splitter loads it itself
                     const uint32_t s = xs_seq % kXStages;
                     mbar_wait(&S.xs_empty[s], ((xs_seq / kXStages) & 1u) ^ 1u);
                     mbar_arrive_expect_tx(&S.xs_full[s], kXLandBytes);
-                    // inner coordinate in tensor-map elements: frames (mono f32, stereo 8-byte
-                    // frames, raw frames), bytes (packed s24) or floats (4 / 8 channels)
-                    tensor_g2s_2d(xst + s * kXStageBytes, &tmap_in,
-                                  (v - H) * (int32_t)(SB == 3 ? kRawFrameBytes : CH >= 4 ? CH : 1), m0,
-                                  &S.xs_full[s]);
+                    tensor_g2s_2d(xst + s * kXStageBytes, &tmap_in, (v - H) * kCoordMul, m0, &S.xs_full[s]);
                     ++xs_seq;
                 }
             }
@@ -700,6 +714,7 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
         const uint32_t lane_base = (warp * 32u) << 16;
         const uint32_t my_stage = smem_u32(ost + warp * 2 * kHalfBytes);
         uint32_t d_seq = 0, h_seq = 0;
+        const float out_scale = P.out_scale;
         rc.start(prof && tid == 0);
         for (uint32_t it = 0;; ++it) {
             const Item I = get_item(it);
@@ -715,16 +730,17 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
                 __syncwarp();     // lanes leave the polling loop at different times
                 rc.lap(8);
                 tc_fence_after();
-#pragma unroll 1
+                // drain the whole accumulator first and hand it back to the issuers at once
+                uint32_t acc0[32], acc1[32];
+                tmem_ld32(tmem + lane_base + kColD + b * kN, acc0);
+                tmem_ld32(tmem + lane_base + kColD + b * kN + 32u, acc1);
+                tmem_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.d_empty[b]);
+#pragma unroll
                 for (uint32_t hf = 0; hf < 2; ++hf, ++h_seq) {
-                    uint32_t acc[32];
-                    tmem_ld32(tmem + lane_base + kColD + b * kN + hf * 32u, acc);
-                    tmem_wait_ld();
-                    if (hf == 1) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&S.d_empty[b]);
-                    }
+                    uint32_t (&acc)[32] = hf == 0 ? acc0 : acc1;
                     // the staging buffer's previous stores (two half tiles ago) have read it
                     if (lane == 0) bulk_wait_read<1>();
                     __syncwarp();
@@ -734,10 +750,10 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
                         const uint32_t rb = sb + ml * 128u;
 #pragma unroll
                         for (uint32_t u = 0; u < 8; ++u)
-                            sts128(rb + ((u ^ (ml & 7u)) << 4), __uint_as_float(acc[4 * u]) * kScaleOut,
-                                   __uint_as_float(acc[4 * u + 1]) * kScaleOut,
-                                   __uint_as_float(acc[4 * u + 2]) * kScaleOut,
-                                   __uint_as_float(acc[4 * u + 3]) * kScaleOut);
+                            sts128(rb + ((u ^ (ml & 7u)) << 4), __uint_as_float(acc[4 * u]) * out_scale,
+                                   __uint_as_float(acc[4 * u + 1]) * out_scale,
+                                   __uint_as_float(acc[4 * u + 2]) * out_scale,
+                                   __uint_as_float(acc[4 * u + 3]) * out_scale);
                     } else {
                         // float (frame o, channel c) of the member's half-tile row: index o*CH + c;
                         // box = index / 32, 16-byte unit inside the box row XOR-swizzled by the row
@@ -746,7 +762,7 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
                             const uint32_t fi = o * CH + c;
                             const uint32_t box = fi >> 5, unit = (fi >> 2) & 7u;
                             sts32(sb + box * kBoxBytes + ml * 128u + ((unit ^ (ml & 7u)) << 4) + (fi & 3u) * 4u,
-                                  __uint_as_float(acc[o]) * kScaleOut);
+                                  __uint_as_float(acc[o]) * out_scale);
                         }
                     }
                     fence_proxy_async();
@@ -892,6 +908,10 @@ uint32_t tc2_kt_extent(uint32_t taps, double ratio) { return kt_max_of(taps, rat
 size_t tc2_gmat_bytes_per_tile(uint32_t taps, double ratio) { return (size_t)2 * kt_max_of(taps, ratio) * 128u; }
 
 uint32_t tc2_rows_per_group() { return kRows; }
+
+// 2^-17 undoes the operand prescale; `comp` (in units of 2^-24) compensates the expected loss of
+// the tensor core's truncating fp32 accumulation (numerics of the tensor kernel)
+float tc2_out_scale(double comp) { return (float)((double)kScaleOut * (1.0 + comp * 5.9604644775390625e-08)); }
 
 // Two issuers keep two consecutive tiles in flight: their K ranges (the second starts up to
 // floor(64*ratio)+1 frames later, rounded to the chunk grid) must fit the ring together.
