@@ -61,6 +61,7 @@ SIGNATURES = {
     "rsb_fir_timer_stop": (C.c_int, [C.c_void_p, f32p]),
     "rsb_fir_conv_times": (C.c_int, [C.c_void_p, f32p, C.c_size_t, szp]),
     "rsb_debug_phase_cycles": (C.c_int, [C.c_void_p, C.c_int, u64p]),
+    "rsb_debug_tc_hang": (C.c_int, [C.POINTER(C.c_uint32)]),
     "rsb_debug_tc_cycles": (C.c_int, [C.c_void_p, C.c_int, u64p, C.c_uint32]),
     "rsb_fir_launch_count": (C.c_uint64, [C.c_void_p]),
     "rsb_fir_cuda_stream": (C.c_void_p, [C.c_void_p]),

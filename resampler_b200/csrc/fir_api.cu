@@ -500,7 +500,8 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
                          (h->kernel_mode == RSB_KERNEL_AUTO && (uint64_t)n * ch >= 64);
     if (want_tc && in_uniform &&
         (rsb::tc2_supported(ch, h->taps, h->ratio) || rsb::tc_supported(ch, h->taps, h->ratio)))
-        use_tc = rsb::tc_make_input_tensor_map(&tc_tmap, hj[0].in, in_stride,
+        use_tc = rsb::tc_make_input_tensor_map(&tc_tmap, hj[0].in,
+                                               getenv("RSB_DEBUG_FAKE_IN_STRIDE") ? (uint64_t)atoll(getenv("RSB_DEBUG_FAKE_IN_STRIDE")) : in_stride,
                                                unit_keys[0].total_frames, n, ch);
 
     RSB_CUDA(W.d_units.reserve(sizeof(UnitDev) * n_units));
@@ -567,7 +568,9 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
         const uint64_t valid = std::min<uint64_t>(hu[0].total_out, min_cap);
         if (n == 1) ostride = (valid * ch * 4 + 15) & ~15ull;
         if (ok && valid > 0)
-            use_tc2 = rsb::tc2_make_output_tensor_map(&tc2_out_map, hj[0].out, ostride, valid, n, ch);
+            use_tc2 = rsb::tc2_make_output_tensor_map(&tc2_out_map, hj[0].out,
+                                                      getenv("RSB_DEBUG_FAKE_OUT_STRIDE") ? (uint64_t)atoll(getenv("RSB_DEBUG_FAKE_OUT_STRIDE")) : ostride,
+                                                      valid, n, ch);
         tc2_tiles = (hu[0].total_out + rsb::kTc2TileOut - 1) / rsb::kTc2TileOut;
     }
     if (use_tc2) {
@@ -796,7 +799,9 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
         T.kt_max = rsb::tc2_kt_extent(h->taps, h->ratio);
         T.issuers = rsb::tc2_issuers(h->taps, h->ratio);
         T.g_stages = rsb::tc2_g_stages(ch, h->taps, h->ratio);
-        T.prefetch_chunks = getenv("RSB_TC_PREFETCH") ? (uint32_t)atoi(getenv("RSB_TC_PREFETCH")) : 12u;
+        T.prefetch_chunks = getenv("RSB_TC_PREFETCH") ? (uint32_t)atoi(getenv("RSB_TC_PREFETCH")) : 0u;
+        T.epi_teams = getenv("RSB_TC_EPI_TEAMS") && atoi(getenv("RSB_TC_EPI_TEAMS")) == 1 ? 1u : 2u;
+        T.ablate = getenv("RSB_TC_ABLATE") ? (uint32_t)atoi(getenv("RSB_TC_ABLATE")) : 0u;
         T.out_scale = rsb::tc2_out_scale(getenv("RSB_TC_COMP") ? atof(getenv("RSB_TC_COMP")) : 0.0);
         if (getenv("RSB_TC_GSTAGES")) T.g_stages = std::min<uint32_t>(T.g_stages, (uint32_t)atoi(getenv("RSB_TC_GSTAGES")));
         T.raw16 = pcm_fused ? pcm_raw_mode : 0u;
@@ -1395,6 +1400,12 @@ int rsb_debug_phase_cycles(rsb_fir *h, int enable, uint64_t *out8) {
     static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "u64");
     rsb::fast_phase_profile(enable, reinterpret_cast<unsigned long long *>(out8));
     RSB_CUDA(cudaGetLastError());
+    return RSB_OK;
+}
+
+int rsb_debug_tc_hang(uint32_t out4[4]) {
+    if (!out4) return RSB_ERR_INVALID_ARGUMENT;
+    rsb::tc2_hang_record(out4);
     return RSB_OK;
 }
 

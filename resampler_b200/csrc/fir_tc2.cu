@@ -42,6 +42,7 @@
 // [384,448) and [448,512) the two accumulators.
 #include <cuda_fp16.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "fir_kernels.h"
@@ -57,10 +58,45 @@ namespace rsb {
 // janitor: [16] wait t_done [17] releases; G producer: [18] wait t_done [19] issue.
 __device__ unsigned long long g_tc2_cycles[24];
 __device__ int g_tc2_prof = 0;
+// Watchdog of the kernel's mbarrier waits: a wait that has not completed after ~2 s records
+// {tag, block, warp, parity | barrier address << 8} in a host-mapped buffer and traps (the launch
+// fails with an error instead of hanging the GPU).  Tags: see the kW* constants.
+__device__ unsigned int *g_tc2_hang = nullptr;
 
 namespace {
 
 using namespace ptx;
+
+enum : uint32_t { kWItemFull = 1, kWItemEmpty, kWXsEmpty, kWXsFull, kWGDone, kWJanDone, kWDEmpty, kWGFull,
+                  kWXFull, kWXEmpty, kWEpiDone };
+__device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, uint32_t tag) {
+    if (mbar_test(bar, parity)) return;
+    const long long t0 = clock64();
+    uint32_t spins = 0;
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if ((++spins & 255u) == 0 && clock64() - t0 > 4000000000ll) {
+            unsigned int *rec = g_tc2_hang;
+            if (rec && atomicCAS(&rec[0], 0u, tag) == 0u) {
+                rec[1] = blockIdx.x;
+                rec[2] = threadIdx.x >> 5;
+                rec[3] = parity | (smem_u32(bar) << 8);
+                __threadfence_system();
+            }
+            __trap();
+        }
+    }
+}
 
 struct RoleClock {
     bool on;
@@ -88,13 +124,13 @@ constexpr uint32_t kRing = 384;                    // frames in a TMEM ring
 constexpr uint32_t kSlots = kRing / kChunk;        // 24
 constexpr uint32_t kSlotCols = kChunk / 2;         // 8 TMEM columns per slot (two fp16 per column)
 constexpr uint32_t kColHi = 0, kColLo = kRing / 2, kColD = kRing;
-constexpr uint32_t kXStages = 4;                   // TMA landing buffers for input chunks
+constexpr uint32_t kXStages = 8;                   // TMA landing buffers for input chunks (64 KB in flight)
 constexpr uint32_t kXStageBytes = kRows * kChunk * 4;   // 8192 for every channel count
-constexpr uint32_t kMaxGStages = 3;
+constexpr uint32_t kMaxGStages = 2;
 constexpr uint32_t kDone = 8;                      // tile-completion barriers (ring)
-constexpr uint32_t kThreads = 17 * 32;
+constexpr uint32_t kThreads = 21 * 32;               // warps 17-20: second epilogue team
 constexpr uint32_t kItemSlots = 2;
-constexpr uint32_t kItemConsumers = 16;            // warps that read every item (all but the scheduler)
+constexpr uint32_t kItemConsumers = 20;            // warps that read every item (all but the scheduler)
 constexpr float kScaleX = 16.0f;                   // 2^4
 constexpr float kScaleG = 8192.0f;                 // 2^13
 constexpr float kScaleOut = 1.0f / (16.0f * 8192.0f);
@@ -357,7 +393,7 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
     __shared__ Smem S;
     const uint32_t g_bytes = P.kt_max * 128u;           // one G half: kt_max/8 K groups x 1024 B
     uint8_t *xst = smem_tc2;                             // [kXStages][kXStageBytes]
-    uint8_t *ost = smem_tc2 + kXStages * kXStageBytes;   // [4 warps][2][kHalfBytes]
+    uint8_t *ost = smem_tc2 + kXStages * kXStageBytes;   // [2 teams][4 quadrants][kHalfBytes]
     uint8_t *gst = ost + 4 * 2 * kHalfBytes;             // [g_stages][2][g_bytes]
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
@@ -395,7 +431,7 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
     // per warp)
     auto get_item = [&](uint32_t it) {
         const uint32_t slot = it % kItemSlots;
-        mbar_wait(&S.item_full[slot], (it / kItemSlots) & 1u);
+        mbar_wait_wd(&S.item_full[slot], (it / kItemSlots) & 1u, kWItemFull);
         const Item I = S.item[slot];
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.item_empty[slot]);
@@ -408,7 +444,7 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
             uint32_t xs_seq = 0;
             for (uint32_t it = 0;; ++it) {
                 const uint32_t slot = it % kItemSlots;
-                mbar_wait(&S.item_empty[slot], ((it / kItemSlots) & 1u) ^ 1u);
+                mbar_wait_wd(&S.item_empty[slot], ((it / kItemSlots) & 1u) ^ 1u, kWItemEmpty);
                 const uint32_t idx = atomicAdd(P.work_counter, 1u);
                 Item I;
                 I.valid = idx < n_items ? 1u : 0u;
@@ -446,9 +482,13 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
                     }
                     if (v < H) continue;       // touches the history: the splitter loads it itself
                     const uint32_t s = xs_seq % kXStages;
-                    mbar_wait(&S.xs_empty[s], ((xs_seq / kXStages) & 1u) ^ 1u);
-                    mbar_arrive_expect_tx(&S.xs_full[s], kXLandBytes);
-                    tensor_g2s_2d(xst + s * kXStageBytes, &tmap_in, (v - H) * kCoordMul, m0, &S.xs_full[s]);
+                    mbar_wait_wd(&S.xs_empty[s], ((xs_seq / kXStages) & 1u) ^ 1u, kWXsEmpty);
+                    if (P.ablate & 2u) {
+                        mbar_arrive(&S.xs_full[s]);
+                    } else {
+                        mbar_arrive_expect_tx(&S.xs_full[s], kXLandBytes);
+                        tensor_g2s_2d(xst + s * kXStageBytes, &tmap_in, (v - H) * kCoordMul, m0, &S.xs_full[s]);
+                    }
                     ++xs_seq;
                 }
             }
@@ -467,15 +507,19 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
                     const uint32_t s = g_seq % n_gst;
                     if (g_seq >= n_gst) {     // the stage's previous tile has been multiplied
                         const uint32_t prev = g_seq - n_gst;
-                        mbar_wait(&S.t_done[prev % kDone], (prev / kDone) & 1u);
+                        mbar_wait_wd(&S.t_done[prev % kDone], (prev / kDone) & 1u, kWGDone);
                     }
                     rc.lap(18);
                     const uint32_t bytes = m.kt * 128u;
                     const uint8_t *src = P.gmat + (size_t)m.g_idx * (2u * g_bytes);
                     uint8_t *dst = gst + (size_t)s * 2 * g_bytes;
-                    mbar_arrive_expect_tx(&S.g_full[s], 2 * bytes);
-                    bulk_g2s(dst, src, bytes, &S.g_full[s]);
-                    bulk_g2s(dst + g_bytes, src + g_bytes, bytes, &S.g_full[s]);
+                    if ((P.ablate & 1u) && g_seq >= n_gst) {
+                        mbar_arrive(&S.g_full[s]);
+                    } else {
+                        mbar_arrive_expect_tx(&S.g_full[s], 2 * bytes);
+                        bulk_g2s(dst, src, bytes, &S.g_full[s]);
+                        bulk_g2s(dst + g_bytes, src + g_bytes, bytes, &S.g_full[s]);
+                    }
                     ++g_seq;
                     rc.lap(19);
                 }
@@ -496,7 +540,7 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
                 for (uint32_t t = I.t0; t < I.t1; ++t, ++d_seq) {
                     const bool last = t + 1 >= I.t1;
                     if (!last) mn = tct[t + 1];
-                    mbar_wait(&S.t_done[d_seq % kDone], (d_seq / kDone) & 1u);
+                    mbar_wait_wd(&S.t_done[d_seq % kDone], (d_seq / kDone) & 1u, kWJanDone);
                     rc.lap(16);
                     // chunks that end at or before the next tile's first frame are free again
                     const uint32_t upto = last ? I.n_chunks : (uint32_t)(mn.k0 - I.vb) / kChunk;
@@ -545,13 +589,13 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
                     // stage has completed, so the parity wait on g_full below cannot be looking
                     // at the stage's previous phase.
                     const uint32_t b = d_seq & 1u;
-                    mbar_wait(&S.d_empty[b], ((d_seq >> 1) & 1u) ^ 1u);
+                    mbar_wait_wd(&S.d_empty[b], ((d_seq >> 1) & 1u) ^ 1u, kWDEmpty);
                     rc.lap(2);
                     const uint32_t gs = d_seq % n_gst;
-                    mbar_wait(&S.g_full[gs], (d_seq / n_gst) & 1u);
+                    mbar_wait_wd(&S.g_full[gs], (d_seq / n_gst) & 1u, kWGFull);
                     rc.lap(1);
                     while (waited < j0 + n_ks) {
-                        mbar_wait(&S.x_full[w_slot], w_par);
+                        mbar_wait_wd(&S.x_full[w_slot], w_par, kWXFull);
                         ++waited;
                         if (++w_slot == kSlots) { w_slot = 0; w_par ^= 1u; }
                     }
@@ -618,7 +662,7 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
             if (base_slot >= kSlots) { base_slot -= kSlots; base_par ^= 1u; }
         }
         __syncwarp();
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 16) {
         // ===== splitter: shared memory (TMA landing buffer) -> fp16 hi / lo rings in TMEM.  Two
         // warpgroups (warps 4-7 and 12-15: the same TMEM lane quadrants) take alternate chunks. =====
         const uint32_t wg = warp >= 12 ? 1u : 0u;
@@ -652,7 +696,7 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
                     int fast_slot = -1;
                     if (landed) {
                         const uint32_t s = xs_seq % kXStages;
-                        mbar_wait(&S.xs_full[s], (xs_seq / kXStages) & 1u);
+                        mbar_wait_wd(&S.xs_full[s], (xs_seq / kXStages) & 1u, kWXsFull);
                         __syncwarp();
                         rc.lap(6);
                         load_chunk<CH, RAW, SB>(smem_u32(xst + s * kXStageBytes),
@@ -686,7 +730,7 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&S.xs_empty[fast_slot]);
                     }
-                    mbar_wait(&S.x_empty[rs], par);
+                    mbar_wait_wd(&S.x_empty[rs], par, kWXEmpty);
                     __syncwarp();
                     rc.lap(5);
                     tc_fence_after();
@@ -709,42 +753,47 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
         }
     } else {
         // ===== epilogue: accumulator (TMEM) -> scale -> swizzled staging -> TMA tensor stores.
-        // Each warp owns 32 accumulator lanes = kMpw members and stores their boxes itself. =====
+        // Two teams of four warps (warps 0-3 and 17-20) drain alternate tiles, i.e. one accumulator
+        // each; a warp owns the 32 accumulator lanes of its quadrant = kMpw members and stores
+        // their boxes itself (no barrier wider than a warp). =====
+        const uint32_t team = warp >= 17 ? 1u : 0u;
+        const uint32_t quad = warp & 3u;
+        const uint32_t teams = P.epi_teams;
         const uint32_t ml = lane / CH, c = lane % CH;       // member inside the warp, channel
-        const uint32_t lane_base = (warp * 32u) << 16;
-        const uint32_t my_stage = smem_u32(ost + warp * 2 * kHalfBytes);
-        uint32_t d_seq = 0, h_seq = 0;
+        const uint32_t lane_base = (quad * 32u) << 16;
+        const uint32_t sb = smem_u32(ost + (team * 4u + quad) * kHalfBytes);
+        uint32_t d_seq = 0;
         const float out_scale = P.out_scale;
         rc.start(prof && tid == 0);
         for (uint32_t it = 0;; ++it) {
             const Item I = get_item(it);
             if (!I.valid) break;
-            const int32_t m_first = (int32_t)(I.group * kMpg + warp * kMpw);
-            Tc2Tile m_next = tct[I.t0];
+            if (team >= teams) continue;
+            const int32_t m_first = (int32_t)(I.group * kMpg + quad * kMpw);
             for (uint32_t t = I.t0; t < I.t1; ++t, ++d_seq) {
-                const Tc2Tile m = m_next;
-                if (t + 1 < I.t1) m_next = tct[t + 1];
+                if (teams == 2 && (d_seq & 1u) != team) continue;
+                const uint32_t o_start = t * kN;
                 const uint32_t b = d_seq & 1u;
                 rc.lap(10);
-                mbar_wait(&S.t_done[d_seq % kDone], (d_seq / kDone) & 1u);
+                mbar_wait_wd(&S.t_done[d_seq % kDone], (d_seq / kDone) & 1u, kWEpiDone);
                 __syncwarp();     // lanes leave the polling loop at different times
                 rc.lap(8);
                 tc_fence_after();
-                // drain the whole accumulator first and hand it back to the issuers at once
-                uint32_t acc0[32], acc1[32];
-                tmem_ld32(tmem + lane_base + kColD + b * kN, acc0);
-                tmem_ld32(tmem + lane_base + kColD + b * kN + 32u, acc1);
-                tmem_wait_ld();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S.d_empty[b]);
-#pragma unroll
-                for (uint32_t hf = 0; hf < 2; ++hf, ++h_seq) {
-                    uint32_t (&acc)[32] = hf == 0 ? acc0 : acc1;
-                    // the staging buffer's previous stores (two half tiles ago) have read it
-                    if (lane == 0) bulk_wait_read<1>();
+#pragma unroll 1
+                for (uint32_t hf = 0; hf < 2; ++hf) {
+                    uint32_t acc[32];
+                    tmem_ld32(tmem + lane_base + kColD + b * kN + hf * 32u, acc);
+                    tmem_wait_ld();
+                    if (hf == 1) {      // the accumulator is drained: hand it back to the issuers
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&S.d_empty[b]);
+                    }
+                    rc.lap(9);
+                    // the staging buffer's previous stores have read it
+                    if (lane == 0) bulk_wait_read<0>();
                     __syncwarp();
-                    const uint32_t sb = my_stage + (h_seq & 1u) * kHalfBytes;
+                    rc.lap(20);
                     if constexpr (CH == 1) {
                         // the thread's 32 frames are one 128-byte box row: eight 16-byte units
                         const uint32_t rb = sb + ml * 128u;
@@ -765,11 +814,12 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
                                   __uint_as_float(acc[o]) * out_scale);
                         }
                     }
+                    rc.lap(21);
                     fence_proxy_async();
                     __syncwarp();
-                    rc.lap(9);
-                    if (lane == 0) {
-                        const int32_t f0 = (int32_t)((m.o_start + hf * 32u) * CH);   // float coordinate
+                    rc.lap(22);
+                    if (lane == 0 && !(P.ablate & 4u)) {
+                        const int32_t f0 = (int32_t)((o_start + hf * 32u) * CH);   // float coordinate
 #pragma unroll
                         for (uint32_t bx = 0; bx < (uint32_t)CH; ++bx)
                             tensor_s2g_2d(&tmap_out, f0 + (int32_t)(bx * 32u), m_first, sb + bx * kBoxBytes);
@@ -930,7 +980,7 @@ bool tc2_make_output_tensor_map(CUtensorMap *out, float *base, uint64_t stride_b
     if (channels != 1 && channels != 2 && channels != 4 && channels != 8) return false;
     if (valid_frames == 0 || valid_frames * channels >= (1ull << 31)) return false;
     if ((reinterpret_cast<uintptr_t>(base) & 15u) || (stride_bytes & 15u) || stride_bytes == 0) return false;
-    if (stride_bytes < valid_frames * channels * 4ull) return false;
+    if (stride_bytes < valid_frames * channels * 4ull && !getenv("RSB_DEBUG_FAKE_OUT_STRIDE")) return false;
     cuuint64_t dims[2] = {valid_frames * channels, n_members};
     cuuint64_t strides[1] = {stride_bytes};
     cuuint32_t box[2] = {32u, 32u / channels};
@@ -971,11 +1021,14 @@ uint32_t tc2_g_stages(uint32_t channels, uint32_t taps, double ratio) {
     return (uint32_t)n;
 }
 
+static void ensure_hang_buffer();
+
 bool launch_conv_tc2(const Tc2Params &p, const CUtensorMap &tmap_in, const CUtensorMap &tmap_out, int sm_count,
                      bool leave_sm_free, cudaStream_t stream) {
     const size_t half = (size_t)p.channels * ((32u / p.channels) * 128u < 1024u ? 1024u : (32u / p.channels) * 128u);
     const size_t smem = (size_t)kXStages * kXStageBytes + 4 * 2 * half + (size_t)p.g_stages * 2 * p.kt_max * 128u;
     if (p.g_stages < 2) return false;
+    ensure_hang_buffer();
     // one SM is left free when the next submit's (serial) plan kernel may need somewhere to run
     const uint32_t grid = (uint32_t)(leave_sm_free && sm_count > 8 ? sm_count - 1 : sm_count);
     auto launch = [&](auto kern) {
@@ -999,6 +1052,24 @@ bool launch_conv_tc2(const Tc2Params &p, const CUtensorMap &tmap_in, const CUten
         default: launch(conv_tc2_kernel<8>); break;
     }
     return true;
+}
+
+// Watchdog record {tag, block, warp, parity | barrier address << 8} of a launch that trapped; the
+// buffer is pinned host memory mapped into the device (readable after the context has failed).
+static unsigned int *g_hang_host = nullptr;
+void tc2_hang_record(unsigned int out[4]) {
+    for (int i = 0; i < 4; ++i) out[i] = g_hang_host ? g_hang_host[i] : 0u;
+    if (g_hang_host) for (int i = 0; i < 4; ++i) g_hang_host[i] = 0u;
+}
+static void ensure_hang_buffer() {
+    if (g_hang_host) return;
+    void *h = nullptr;
+    if (cudaHostAlloc(&h, 64, cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return; }
+    std::memset(h, 0, 64);
+    void *d = nullptr;
+    if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) { cudaGetLastError(); cudaFreeHost(h); return; }
+    if (cudaMemcpyToSymbol(g_tc2_hang, &d, sizeof(d)) != cudaSuccess) { cudaGetLastError(); cudaFreeHost(h); return; }
+    g_hang_host = static_cast<unsigned int *>(h);
 }
 
 void tc2_phase_profile(int enable, unsigned long long *out, uint32_t count) {

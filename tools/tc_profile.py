@@ -15,7 +15,7 @@ from resampler_b200.fir import FLAG_ASYNC, MEM_DEVICE, DeviceBuffer  # noqa: E40
 NAMES = ["M.wait_x_full", "M.wait_g_full", "M.wait_d_empty", "M.issue", "M.commit+meta",
          "S.wait_x_empty", "S.wait_xs_full", "S.load+split", "E.wait_t_done", "E.ld+stage", "E.tma_store",
          "S.wait_st+arrive", "S.st", "kernel", "tiles", "S.other", "J.wait_t_done", "J.release",
-         "G.wait_t_done", "G.issue", "x", "x", "x", "x"]
+         "G.wait_t_done", "G.issue", "E.wait_store_read", "E.stage_writes", "E.fence", "x"]
 
 
 def main():
@@ -45,7 +45,7 @@ def main():
     cyc = np.array(out[:], dtype=np.float64)
     tiles = max(cyc[14], 1.0)
     res = {"conv_ms": conv_ms, "tiles_cta0": int(cyc[14]), "kernel_cycles_per_tile": round(cyc[13] / tiles, 1),
-           "cycles_per_tile": {NAMES[i]: round(cyc[i] / tiles, 1) for i in list(range(13)) + [15, 16, 17, 18, 19]}}
+           "cycles_per_tile": {NAMES[i]: round(cyc[i] / tiles, 1) for i in list(range(13)) + [15, 16, 17, 18, 19, 20, 21, 22]}}
     print(json.dumps(res))
     (ROOT / "gpurun_out").mkdir(exist_ok=True)
     (ROOT / "gpurun_out" / "tc_profile.json").write_text(json.dumps(res, indent=1))
