@@ -216,8 +216,9 @@ int rsb_debug_phase_cycles(rsb_fir *h, int enable, uint64_t *out8);
  * the enable flag. */
 int rsb_debug_tc_cycles(rsb_fir *h, int enable, uint64_t *out, uint32_t count);
 /* debug: watchdog record of a tensor-kernel launch that failed on a stuck barrier wait:
- * {wait tag, block, warp, parity | barrier address << 8}; zeros when none.  Clears the record. */
-int rsb_debug_tc_hang(uint32_t out4[4]);
+ * {wait tag, block, warp, parity | barrier address << 8}, then for warp w of that block at [4 + w]:
+ * tag | parity << 8 | barrier address << 12; zeros when none.  Clears the record. */
+int rsb_debug_tc_hang(uint32_t out32[32]);
 /* kernels launched on this handle since creation (your own count for gpu_launches) */
 uint64_t rsb_fir_launch_count(const rsb_fir *h);
 /* the handle's cudaStream_t, as an opaque pointer */

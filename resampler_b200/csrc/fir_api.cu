@@ -800,7 +800,7 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
         T.issuers = rsb::tc2_issuers(h->taps, h->ratio);
         T.g_stages = rsb::tc2_g_stages(ch, h->taps, h->ratio);
         T.prefetch_chunks = getenv("RSB_TC_PREFETCH") ? (uint32_t)atoi(getenv("RSB_TC_PREFETCH")) : 0u;
-        T.epi_teams = getenv("RSB_TC_EPI_TEAMS") && atoi(getenv("RSB_TC_EPI_TEAMS")) == 1 ? 1u : 2u;
+        T.g_prefetch = getenv("RSB_TC_GPREFETCH") ? (uint32_t)atoi(getenv("RSB_TC_GPREFETCH")) : 3u;
         T.ablate = getenv("RSB_TC_ABLATE") ? (uint32_t)atoi(getenv("RSB_TC_ABLATE")) : 0u;
         T.out_scale = rsb::tc2_out_scale(getenv("RSB_TC_COMP") ? atof(getenv("RSB_TC_COMP")) : 0.0);
         if (getenv("RSB_TC_GSTAGES")) T.g_stages = std::min<uint32_t>(T.g_stages, (uint32_t)atoi(getenv("RSB_TC_GSTAGES")));
@@ -1403,9 +1403,9 @@ int rsb_debug_phase_cycles(rsb_fir *h, int enable, uint64_t *out8) {
     return RSB_OK;
 }
 
-int rsb_debug_tc_hang(uint32_t out4[4]) {
-    if (!out4) return RSB_ERR_INVALID_ARGUMENT;
-    rsb::tc2_hang_record(out4);
+int rsb_debug_tc_hang(uint32_t out32[32]) {
+    if (!out32) return RSB_ERR_INVALID_ARGUMENT;
+    rsb::tc2_hang_record(out32);
     return RSB_OK;
 }
 

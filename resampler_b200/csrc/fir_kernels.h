@@ -147,8 +147,9 @@ struct Tc2Params {
     uint32_t raw16;           // as TcParams::raw16
     uint32_t raw_bytes;       // bytes per raw sample: 2 (s16) or 3 (packed s24)
     uint32_t prefetch_chunks; // input chunks the TMA producer prefetches into L2 ahead of its loads
-    uint32_t epi_teams;       // epilogue teams of four warps: 1 or 2 (alternate tiles)
-    uint32_t ablate;          // debug (RSB_TC_ABLATE): 1 no G copies, 2 no input TMA, 4 no output stores
+    uint32_t g_prefetch;      // tiles the G producer prefetches into L2 ahead of its copies (0: off)
+    uint32_t ablate;          // debug (RSB_TC_ABLATE): 1 no G copies, 2 no input TMA, 4 no output stores,
+                              // 8 splitter: handshakes only, 16 epilogue: handshakes only, 32 one MMA per tile
     float out_scale;          // epilogue factor: 2^-17 x truncation-bias compensation (tc2_out_scale)
 };
 float tc2_out_scale(double comp);
@@ -173,6 +174,6 @@ bool launch_conv_tc2(const Tc2Params &p, const CUtensorMap &tmap_in, const CUten
 // debug: returns (up to `count` of 24) and clears the kernel's per-role cycle counters, sets the enable flag
 void tc2_phase_profile(int enable, unsigned long long *out, uint32_t count);
 // watchdog record of a tensor-kernel launch that trapped on a stuck mbarrier wait (zeros: none); clears it
-void tc2_hang_record(unsigned int out[4]);
+void tc2_hang_record(unsigned int out[32]);
 
 }  // namespace rsb

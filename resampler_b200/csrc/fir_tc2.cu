@@ -18,25 +18,27 @@
 // of 8.  The parity bar against the oracle is 1e-6 absolute.  Inputs must satisfy |x| < 4094
 // (fp16 range after the prescale); see resampler_b200.h for the non-finite contract.
 //
-// Data flow of one CTA (persistent, one per SM, 17 warps; every hand-off is an mbarrier):
+// Data flow of one CTA (persistent, one per SM, 25 warps; every hand-off is an mbarrier):
 //   * work item = (run of consecutive tiles) x (group of 128 rows = 128 / CH member streams).
 //     A run walks forward in time, so every input frame is fetched from HBM/L2 ONCE per row and
 //     kept in a TMEM ring while the ~4 tiles whose windows cover it are computed.
-//   * warp 9 (one thread): work scheduler (atomic counter) + TMA producer of the input: one 2-D
+//   * warp 22 (one thread): work scheduler (atomic counter) + TMA producer of the input: one 2-D
 //     tensor copy per 16-frame chunk (box = 16 frames x 128/CH members), anchored at the first
 //     new input frame (a TMA box must start 16-byte aligned in global memory).
-//   * warps 4-7 and 12-15 ("splitter", thread == row; the two warpgroups take alternate chunks):
+//   * warps 4-15 ("splitter", thread == row; three teams of four warps take every third chunk:
+//     one chunk is a long serial latency chain, three in flight hide it):
 //     shared memory -> de-interleave -> scale -> fp16 hi / lo pairs -> tcgen05.st into the two
 //     TMEM rings (ring column == 2 input frames, TMEM lane == row).  The rings ARE the A operands.
-//   * warp 10 (one thread): bulk copies of the tile's [G_hi, G_lo] matrices (prebuilt by
+//   * warp 23 (one thread): bulk copies of the tile's [G_hi, G_lo] matrices (prebuilt by
 //     tc2_gmat_kernel in the canonical no-swizzle K-major core-matrix layout) into a stage ring.
-//   * warps 8 and 11: issue the tcgen05.mma (39 per 128-tap tile) for alternate tiles, one
+//   * warps 20 and 21: issue the tcgen05.mma (39 per 128-tap tile) for alternate tiles, one
 //     accumulator each; ONE tcgen05.commit per tile.
-//   * warp 16 ("janitor", one thread): follows the tile-completion barriers in order and hands the
+//   * warp 24 ("janitor", one thread): follows the tile-completion barriers in order and hands the
 //     ring slots no later tile reads back to the splitter (the issuers commit nothing but t_done).
-//   * warps 0-3 (epilogue): tcgen05.ld of their 32 accumulator lanes, scale, 128B-swizzled staging
-//     in shared memory, TMA tensor STORES (one warp stores its own members' boxes; no CTA-wide
-//     barrier anywhere in the steady state).  The store map clips partial tiles and capacity.
+//   * warps 0-3 and 16-19 (epilogue, two teams on alternate tiles = one accumulator each):
+//     tcgen05.ld of their 32 accumulator lanes, scale, 128B-swizzled staging in shared memory,
+//     TMA tensor STORES (one warp stores its own members' boxes; no CTA-wide barrier anywhere in
+//     the steady state).  The store map clips partial tiles and capacity.
 //
 // TMEM map (512 columns x 128 lanes): [0,192) X hi ring (384 frames), [192,384) X lo ring,
 // [384,448) and [448,512) the two accumulators.
@@ -86,13 +88,21 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, uin
             : "memory");
         if (ok) return;
         if ((++spins & 255u) == 0 && clock64() - t0 > 4000000000ll) {
+            // first CTA to time out claims the record; every stuck warp of that CTA adds its own
+            // wait (slot 4 + warp), then the kernel traps half a second later
             unsigned int *rec = g_tc2_hang;
-            if (rec && atomicCAS(&rec[0], 0u, tag) == 0u) {
-                rec[1] = blockIdx.x;
-                rec[2] = threadIdx.x >> 5;
-                rec[3] = parity | (smem_u32(bar) << 8);
+            if (rec) {
+                const unsigned int prev = atomicCAS(&rec[0], 0u, tag);
+                if (prev == 0u) {
+                    rec[1] = blockIdx.x;
+                    rec[2] = threadIdx.x >> 5;
+                    rec[3] = parity | (smem_u32(bar) << 8);
+                }
+                if (prev == 0u || rec[1] == blockIdx.x)
+                    rec[4 + (threadIdx.x >> 5)] = tag | (parity << 8) | (smem_u32(bar) << 12);
                 __threadfence_system();
             }
+            while (clock64() - t0 < 5000000000ll) { }
             __trap();
         }
     }
@@ -124,13 +134,20 @@ constexpr uint32_t kRing = 384;                    // frames in a TMEM ring
 constexpr uint32_t kSlots = kRing / kChunk;        // 24
 constexpr uint32_t kSlotCols = kChunk / 2;         // 8 TMEM columns per slot (two fp16 per column)
 constexpr uint32_t kColHi = 0, kColLo = kRing / 2, kColD = kRing;
-constexpr uint32_t kXStages = 8;                   // TMA landing buffers for input chunks (64 KB in flight)
+// TMA landing buffers for input chunks.  MUST be a multiple of kSplitTeams: a team then meets
+// every use of "its" stages in turn; otherwise it revisits a stage only every few uses and its
+// parity wait can alias when tensor copies land out of order (found by the watchdog).
+constexpr uint32_t kXStages = 6;
 constexpr uint32_t kXStageBytes = kRows * kChunk * 4;   // 8192 for every channel count
 constexpr uint32_t kMaxGStages = 2;
 constexpr uint32_t kDone = 8;                      // tile-completion barriers (ring)
-constexpr uint32_t kThreads = 21 * 32;               // warps 17-20: second epilogue team
+constexpr uint32_t kThreads = 25 * 32;
+constexpr uint32_t kSplitTeams = 3;                // splitter teams of four warps (warps 4-15)
+constexpr uint32_t kEpiTeams = 2;                  // epilogue teams of four warps (warps 0-3, 16-19)
+static_assert(kXStages % kSplitTeams == 0 && kSlots % kSplitTeams == 0, "stage / slot ownership must be fixed per team");
+constexpr uint32_t kWarpIssuer0 = 20, kWarpIssuer1 = 21, kWarpTmaIn = 22, kWarpG = 23, kWarpJanitor = 24;
 constexpr uint32_t kItemSlots = 2;
-constexpr uint32_t kItemConsumers = 20;            // warps that read every item (all but the scheduler)
+constexpr uint32_t kItemConsumers = 24;            // 4 * (kSplitTeams + kEpiTeams) + issuers, G producer, janitor            // warps that read every item (all but the scheduler)
 constexpr float kScaleX = 16.0f;                   // 2^4
 constexpr float kScaleG = 8192.0f;                 // 2^13
 constexpr float kScaleOut = 1.0f / (16.0f * 8192.0f);
@@ -244,6 +261,9 @@ __device__ __forceinline__ void tensor_s2g_2d(const CUtensorMap *tm, int c0, int
 __device__ __forceinline__ void tensor_prefetch_2d(const CUtensorMap *tm, int c0, int c1) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1)
                  : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -393,8 +413,8 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
     __shared__ Smem S;
     const uint32_t g_bytes = P.kt_max * 128u;           // one G half: kt_max/8 K groups x 1024 B
     uint8_t *xst = smem_tc2;                             // [kXStages][kXStageBytes]
-    uint8_t *ost = smem_tc2 + kXStages * kXStageBytes;   // [2 teams][4 quadrants][kHalfBytes]
-    uint8_t *gst = ost + 4 * 2 * kHalfBytes;             // [g_stages][2][g_bytes]
+    uint8_t *ost = smem_tc2 + kXStages * kXStageBytes;   // [kEpiTeams][4 quadrants][kHalfBytes]
+    uint8_t *gst = ost + kEpiTeams * 4 * kHalfBytes;             // [g_stages][2][g_bytes]
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const bool prof = g_tc2_prof != 0 && blockIdx.x == 0;
@@ -413,7 +433,7 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) tmem_alloc(&S.tmem_base, 512);
+    if (warp == kWarpIssuer0) tmem_alloc(&S.tmem_base, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -438,7 +458,7 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
         return I;
     };
 
-    if (warp == 9) {
+    if (warp == kWarpTmaIn) {
         // ===== scheduler + TMA producer of the input chunks =====
         if (lane == 0) {
             uint32_t xs_seq = 0;
@@ -494,7 +514,7 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
             }
         }
         __syncwarp();
-    } else if (warp == 10) {
+    } else if (warp == kWarpG) {
         // ===== TMA producer of the G matrices =====
         uint32_t g_seq = 0;
         rc.start(prof && lane == 0);
@@ -512,6 +532,14 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
                     rc.lap(18);
                     const uint32_t bytes = m.kt * 128u;
                     const uint8_t *src = P.gmat + (size_t)m.g_idx * (2u * g_bytes);
+                    if (t + P.g_prefetch < I.t1 && P.g_prefetch) {
+                        // pull a later tile's matrices into L2 (the first of the 16 member groups
+                        // that reaches a tile would otherwise wait for HBM)
+                        const Tc2Tile mp = tct[t + P.g_prefetch];
+                        const uint8_t *ps = P.gmat + (size_t)mp.g_idx * (2u * g_bytes);
+                        bulk_prefetch_l2(ps, mp.kt * 128u);
+                        bulk_prefetch_l2(ps + g_bytes, mp.kt * 128u);
+                    }
                     uint8_t *dst = gst + (size_t)s * 2 * g_bytes;
                     if ((P.ablate & 1u) && g_seq >= n_gst) {
                         mbar_arrive(&S.g_full[s]);
@@ -526,7 +554,7 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
             }
             g_seq = __shfl_sync(0xffffffffu, g_seq, 0);
         }
-    } else if (warp == 16) {
+    } else if (warp == kWarpJanitor) {
         // ===== janitor: hands ring slots back to the splitter once no later tile reads them =====
         uint32_t d_seq = 0;          // tiles of this CTA so far
         uint32_t r_slot = 0;         // ring slot of the next chunk to release
@@ -556,12 +584,12 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
             d_seq = __shfl_sync(0xffffffffu, d_seq, 0);
             r_slot = __shfl_sync(0xffffffffu, r_slot, 0);
         }
-    } else if (warp == 8 || warp == 11) {
+    } else if (warp == kWarpIssuer0 || warp == kWarpIssuer1) {
         // ===== MMA issuers.  The whole warp runs the loop (warp-uniform values), one elected lane
         // issues.  Two warps issue alternate tiles into the two accumulators whenever two
-        // consecutive tiles' K ranges fit the ring together (P.issuers == 2); otherwise warp 8
+        // consecutive tiles' K ranges fit the ring together (P.issuers == 2); otherwise the first
         // issues every tile. =====
-        const uint32_t mine = warp == 8 ? 0u : 1u;
+        const uint32_t mine = warp == kWarpIssuer0 ? 0u : 1u;
         const uint32_t step = P.issuers;
         uint32_t base_slot = 0, base_par = 0;   // ring slot / phase parity of the run's chunk 0
         uint32_t d_seq = 0;                     // tiles of this CTA so far; tile -> accumulator d_seq & 1
@@ -572,7 +600,6 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
             if (mine < step) {
                 rc.count(14, I.t1 - I.t0);
                 uint32_t waited = 0;                      // chunks of this run already seen full
-                uint32_t w_slot = base_slot, w_par = base_par;
                 const uint32_t d_run = d_seq;
                 uint32_t t = I.t0 + (step == 2 ? ((d_seq ^ mine) & 1u) : 0u);
                 d_seq += t - I.t0;
@@ -594,10 +621,20 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
                     const uint32_t gs = d_seq % n_gst;
                     mbar_wait_wd(&S.g_full[gs], (d_seq / n_gst) & 1u, kWGFull);
                     rc.lap(1);
-                    while (waited < j0 + n_ks) {
-                        mbar_wait_wd(&S.x_full[w_slot], w_par, kWXFull);
-                        ++waited;
-                        if (++w_slot == kSlots) { w_slot = 0; w_par ^= 1u; }
+                    // Only the tile's OWN chunks [j0, j0 + n_ks) are waited for: they cannot be
+                    // recycled before this tile completes.  (Earlier chunks may already have been
+                    // released by the janitor and refilled for the ring's next revolution while
+                    // this warp was held up elsewhere; a parity wait on them would alias and never
+                    // complete -- found by the watchdog with a slow epilogue.)
+                    {
+                        uint32_t cw = waited > j0 ? waited : j0;
+                        const uint32_t lin = base_slot + cw;
+                        uint32_t w_slot = lin % kSlots, w_par = base_par ^ ((lin / kSlots) & 1u);
+                        for (; cw < j0 + n_ks; ++cw) {
+                            mbar_wait_wd(&S.x_full[w_slot], w_par, kWXFull);
+                            if (++w_slot == kSlots) { w_slot = 0; w_par ^= 1u; }
+                        }
+                        waited = j0 + n_ks;
                     }
                     rc.lap(0);
                     tc_fence_after();
@@ -612,8 +649,10 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
                     // small terms first: X_lo * G_hi and X_hi * G_lo, two K steps per issue block
                     const uint32_t col0 = s0 * kSlotCols;
                     uint32_t col = col0, dk = 0, ks = 0;
+                    const uint32_t n_ks_real = n_ks;
+                    const uint32_t n_ks_issue = (P.ablate & 32u) ? 0u : n_ks;
 #pragma unroll 2
-                    for (; ks + 2 <= n_ks; ks += 2) {
+                    for (; ks + 2 <= n_ks_issue; ks += 2) {
                         const uint32_t c1 = wrap(col + kSlotCols);
                         tc_mma_f16_ts_x4(d_tmem, alo + col, ahi + col, alo + c1, ahi + c1, ghi + dk, glo + dk,
                                          ghi + dk + kBDescKStep, glo + dk + kBDescKStep, kBDescHi, kIdesc,
@@ -621,15 +660,15 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
                         dk += 2 * kBDescKStep;
                         col = wrap(c1 + kSlotCols);
                     }
-                    if (ks < n_ks)
+                    if (ks < n_ks_issue)
                         tc_mma_f16_ts_x2(d_tmem, alo + col, ghi + dk, ahi + col, glo + dk, kBDescHi, kIdesc,
                                          ks != 0);
                     // X_hi * G_hi, K steps outside-in (front, back, front + 1, back - 1, ...)
-                    uint32_t cf = col0, cb = wrap(col0 + kSlotCols * (n_ks - 1));
-                    uint32_t df = 0, db = (n_ks - 1) * kBDescKStep, i = 0;
+                    uint32_t cf = col0, cb = wrap(col0 + kSlotCols * (n_ks_real - 1));
+                    uint32_t df = 0, db = (n_ks_real - 1) * kBDescKStep, i = 0;
                     auto back = [](uint32_t c) { return c >= kSlotCols ? c - kSlotCols : c + kWrapCols - kSlotCols; };
 #pragma unroll 2
-                    for (; i + 4 <= n_ks; i += 4) {
+                    for (; i + 4 <= n_ks_issue; i += 4) {
                         const uint32_t cf1 = wrap(cf + kSlotCols), cb1 = back(cb);
                         tc_mma_f16_ts_x4(d_tmem, ahi + cf, ahi + cb, ahi + cf1, ahi + cb1, ghi + df, ghi + db,
                                          ghi + df + kBDescKStep, ghi + db - kBDescKStep, kBDescHi, kIdesc, 1u);
@@ -638,14 +677,14 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
                         cf = wrap(cf1 + kSlotCols);
                         cb = back(cb1);
                     }
-                    for (; i + 2 <= n_ks; i += 2) {
+                    for (; i + 2 <= n_ks_issue; i += 2) {
                         tc_mma_f16_ts_x2(d_tmem, ahi + cf, ghi + df, ahi + cb, ghi + db, kBDescHi, kIdesc, 1u);
                         df += kBDescKStep;
                         db -= kBDescKStep;
                         cf = wrap(cf + kSlotCols);
                         cb = back(cb);
                     }
-                    if (i < n_ks) tc_mma_f16_ts(d_tmem, ahi + cf, ghi + df, kBDescHi, kIdesc, 1u);
+                    if (i < n_ks_issue || (P.ablate & 32u)) tc_mma_f16_ts(d_tmem, ahi + cf, ghi + df, kBDescHi, kIdesc, 1u);
                     rc.lap(3);
                     // the tile's only commit: epilogue (accumulator ready), G producer (stage
                     // free) and janitor (ring slots free) all follow this barrier
@@ -662,10 +701,10 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
             if (base_slot >= kSlots) { base_slot -= kSlots; base_par ^= 1u; }
         }
         __syncwarp();
-    } else if (warp >= 4 && warp < 16) {
-        // ===== splitter: shared memory (TMA landing buffer) -> fp16 hi / lo rings in TMEM.  Two
-        // warpgroups (warps 4-7 and 12-15: the same TMEM lane quadrants) take alternate chunks. =====
-        const uint32_t wg = warp >= 12 ? 1u : 0u;
+    } else if (warp >= 4 && warp < 4 + 4 * kSplitTeams) {
+        // ===== splitter: shared memory (TMA landing buffer) -> fp16 hi / lo rings in TMEM.  Three
+        // teams of four warps (one per TMEM lane quadrant) take every third chunk. =====
+        const uint32_t wg = (warp - 4u) >> 2;
         const uint32_t row = tid & 127u;                    // TMEM lane
         const uint32_t ml = row / CH, c = row % CH;         // member inside the group, channel
         const uint32_t lane_base = ((warp & 3u) * 32u) << 16;
@@ -687,14 +726,23 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
             for (uint32_t j = 0; j < I.n_chunks; ++j, ++q_seq) {
                 const int32_t v = I.vb + (int32_t)(j * kChunk);
                 const bool landed = v >= H;
-                if ((q_seq & 1u) == wg) {
+                if ((q_seq % kSplitTeams) == wg) {
                     rc.lap(15);
                     // Load and split BEFORE waiting for the ring slot: with the values already
                     // split in registers only the TMEM stores remain between "slot free" and
                     // "chunk readable".
                     float x[kChunk];
                     int fast_slot = -1;
-                    if (landed) {
+                    if (P.ablate & 8u) {
+#pragma unroll
+                        for (uint32_t f = 0; f < kChunk; ++f) x[f] = 0.f;
+                        if (landed) {
+                            const uint32_t s = xs_seq % kXStages;
+                            mbar_wait_wd(&S.xs_full[s], (xs_seq / kXStages) & 1u, kWXsFull);
+                            __syncwarp();
+                            fast_slot = (int)s;
+                        }
+                    } else if (landed) {
                         const uint32_t s = xs_seq % kXStages;
                         mbar_wait_wd(&S.xs_full[s], (xs_seq / kXStages) & 1u, kWXsFull);
                         __syncwarp();
@@ -735,8 +783,10 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
                     rc.lap(5);
                     tc_fence_after();
                     const uint32_t colw = rs * kSlotCols;
-                    tmem_st8(tmem + lane_base + kColHi + colw, hi);
-                    tmem_st8(tmem + lane_base + kColLo + colw, lo);
+                    if (!(P.ablate & 8u)) {
+                        tmem_st8(tmem + lane_base + kColHi + colw, hi);
+                        tmem_st8(tmem + lane_base + kColLo + colw, lo);
+                    }
                     rc.lap(12);
                     // the stores must have completed before hi[] / lo[] are overwritten by the
                     // next chunk (tcgen05.st reads its source registers asynchronously) and
@@ -753,12 +803,10 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
         }
     } else {
         // ===== epilogue: accumulator (TMEM) -> scale -> swizzled staging -> TMA tensor stores.
-        // Two teams of four warps (warps 0-3 and 17-20) drain alternate tiles, i.e. one accumulator
-        // each; a warp owns the 32 accumulator lanes of its quadrant = kMpw members and stores
-        // their boxes itself (no barrier wider than a warp). =====
-        const uint32_t team = warp >= 17 ? 1u : 0u;
+        // A warp owns the 32 accumulator lanes of its quadrant = kMpw members and stores their
+        // boxes itself (no barrier wider than a warp). =====
+        const uint32_t team = warp >= 16 ? 1u : 0u;          // drains the tiles with d_seq % 2 == team
         const uint32_t quad = warp & 3u;
-        const uint32_t teams = P.epi_teams;
         const uint32_t ml = lane / CH, c = lane % CH;       // member inside the warp, channel
         const uint32_t lane_base = (quad * 32u) << 16;
         const uint32_t sb = smem_u32(ost + (team * 4u + quad) * kHalfBytes);
@@ -768,10 +816,9 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
         for (uint32_t it = 0;; ++it) {
             const Item I = get_item(it);
             if (!I.valid) break;
-            if (team >= teams) continue;
             const int32_t m_first = (int32_t)(I.group * kMpg + quad * kMpw);
             for (uint32_t t = I.t0; t < I.t1; ++t, ++d_seq) {
-                if (teams == 2 && (d_seq & 1u) != team) continue;
+                if ((d_seq & 1u) != team) continue;
                 const uint32_t o_start = t * kN;
                 const uint32_t b = d_seq & 1u;
                 rc.lap(10);
@@ -779,6 +826,12 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
                 __syncwarp();     // lanes leave the polling loop at different times
                 rc.lap(8);
                 tc_fence_after();
+                if (P.ablate & 16u) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&S.d_empty[b]);
+                    continue;
+                }
 #pragma unroll 1
                 for (uint32_t hf = 0; hf < 2; ++hf) {
                     uint32_t acc[32];
@@ -803,6 +856,27 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
                                    __uint_as_float(acc[4 * u + 1]) * out_scale,
                                    __uint_as_float(acc[4 * u + 2]) * out_scale,
                                    __uint_as_float(acc[4 * u + 3]) * out_scale);
+                    } else if constexpr (CH == 2) {
+                        // Lane pair (member, L) / (member, R): after exchanging 16 values the L lane
+                        // owns frames 0-15 of both channels = box 0's whole 128-byte row of the
+                        // member, the R lane frames 16-31 = box 1's row: eight conflict-free 16-byte
+                        // stores each instead of 32 scalar ones.
+                        float own[16], got[16];
+#pragma unroll
+                        for (uint32_t i = 0; i < 16; ++i) {
+                            const float keep = __uint_as_float(c ? acc[16 + i] : acc[i]) * out_scale;
+                            const float send = __uint_as_float(c ? acc[i] : acc[16 + i]) * out_scale;
+                            own[i] = keep;
+                            got[i] = __shfl_xor_sync(0xffffffffu, send, 1);
+                        }
+                        const uint32_t rb = sb + c * kBoxBytes + ml * 128u;
+#pragma unroll
+                        for (uint32_t u = 0; u < 8; ++u) {
+                            // frames 2u, 2u + 1 of this lane's 16: (L, R, L, R)
+                            const float l0 = c ? got[2 * u] : own[2 * u], r0 = c ? own[2 * u] : got[2 * u];
+                            const float l1 = c ? got[2 * u + 1] : own[2 * u + 1], r1 = c ? own[2 * u + 1] : got[2 * u + 1];
+                            sts128(rb + ((u ^ (ml & 7u)) << 4), l0, r0, l1, r1);
+                        }
                     } else {
                         // float (frame o, channel c) of the member's half-tile row: index o*CH + c;
                         // box = index / 32, 16-byte unit inside the box row XOR-swizzled by the row
@@ -834,7 +908,7 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == kWarpIssuer0) {
         tc_fence_after();
         tmem_dealloc(tmem, 512);
     }
@@ -1013,7 +1087,7 @@ void launch_tc2_gmat(const UnitDev *units, const PlanEntry *entries, const float
 
 uint32_t tc2_g_stages(uint32_t channels, uint32_t taps, double ratio) {
     const size_t half = (size_t)channels * ((32u / channels) * 128u < 1024u ? 1024u : (32u / channels) * 128u);
-    const size_t fixed = (size_t)kXStages * kXStageBytes + 4 * 2 * half + 2048;   // + static barriers
+    const size_t fixed = (size_t)kXStages * kXStageBytes + kEpiTeams * 4 * half + 2048;   // + static barriers
     const size_t per_stage = tc2_gmat_bytes_per_tile(taps, ratio);
     const size_t budget = 232448;    // 227 KB per CTA
     size_t n = (budget - fixed) / per_stage;
@@ -1026,7 +1100,7 @@ static void ensure_hang_buffer();
 bool launch_conv_tc2(const Tc2Params &p, const CUtensorMap &tmap_in, const CUtensorMap &tmap_out, int sm_count,
                      bool leave_sm_free, cudaStream_t stream) {
     const size_t half = (size_t)p.channels * ((32u / p.channels) * 128u < 1024u ? 1024u : (32u / p.channels) * 128u);
-    const size_t smem = (size_t)kXStages * kXStageBytes + 4 * 2 * half + (size_t)p.g_stages * 2 * p.kt_max * 128u;
+    const size_t smem = (size_t)kXStages * kXStageBytes + kEpiTeams * 4 * half + (size_t)p.g_stages * 2 * p.kt_max * 128u;
     if (p.g_stages < 2) return false;
     ensure_hang_buffer();
     // one SM is left free when the next submit's (serial) plan kernel may need somewhere to run
@@ -1054,18 +1128,19 @@ bool launch_conv_tc2(const Tc2Params &p, const CUtensorMap &tmap_in, const CUten
     return true;
 }
 
-// Watchdog record {tag, block, warp, parity | barrier address << 8} of a launch that trapped; the
+// Watchdog record {tag, block, warp, parity | barrier address << 8, then per warp of that block:
+// tag | parity << 8 | barrier address << 12} of a launch that trapped; the
 // buffer is pinned host memory mapped into the device (readable after the context has failed).
 static unsigned int *g_hang_host = nullptr;
-void tc2_hang_record(unsigned int out[4]) {
-    for (int i = 0; i < 4; ++i) out[i] = g_hang_host ? g_hang_host[i] : 0u;
-    if (g_hang_host) for (int i = 0; i < 4; ++i) g_hang_host[i] = 0u;
+void tc2_hang_record(unsigned int out[32]) {
+    for (int i = 0; i < 32; ++i) out[i] = g_hang_host ? g_hang_host[i] : 0u;
+    if (g_hang_host) for (int i = 0; i < 32; ++i) g_hang_host[i] = 0u;
 }
 static void ensure_hang_buffer() {
     if (g_hang_host) return;
     void *h = nullptr;
-    if (cudaHostAlloc(&h, 64, cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return; }
-    std::memset(h, 0, 64);
+    if (cudaHostAlloc(&h, 128, cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return; }
+    std::memset(h, 0, 128);
     void *d = nullptr;
     if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) { cudaGetLastError(); cudaFreeHost(h); return; }
     if (cudaMemcpyToSymbol(g_tc2_hang, &d, sizeof(d)) != cudaSuccess) { cudaGetLastError(); cudaFreeHost(h); return; }

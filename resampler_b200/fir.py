@@ -117,6 +117,14 @@ def _check(rc: int) -> None:
         raise ValueError(lib.rsb_status_string(rc).decode())
     if rc == 12:
         raise ValueError(msg)
+    rec = (C.c_uint32 * 32)()
+    lib.rsb_debug_tc_hang(rec)
+    if rec[0]:     # the tensor kernel's barrier watchdog fired: say where
+        warps = {w: (rec[4 + w] & 0xff, (rec[4 + w] >> 8) & 0xf, rec[4 + w] >> 12) for w in range(24)
+                 if rec[4 + w]}
+        msg += (f" [tensor-kernel watchdog: wait tag {rec[0]}, block {rec[1]}, warp {rec[2]}, "
+                f"parity {rec[3] & 0xff}, barrier smem address {rec[3] >> 8:#x}; stuck warps "
+                f"(tag, parity, barrier): {warps}]")
     raise RuntimeError(f"resampler_b200 error {rc}: {msg}")
 
 
