@@ -117,6 +117,7 @@ struct Workspace {
 struct rsb_fir {
     int device = 0;
     int sm_count = 148;
+    size_t mem_pitch = 0;    // largest pitch cudaMemcpy2D accepts (cudaDeviceProp::memPitch)
     cudaStream_t stream = nullptr;
     uint32_t n_streams = 0, channels = 0, in_hz = 0, out_hz = 0, taps = 0;
     int latency = 0, attenuation = 0;
@@ -603,8 +604,11 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
                     (ptrdiff_t)i * out_pitch)
                 d2h_uniform = false;
         }
-        if (in_pitch < (ptrdiff_t)(in_vals[0] * sizeof(float))) h2d_uniform = false;
-        if (out_pitch <= 0) d2h_uniform = false;
+        // separately allocated host arrays can be terabytes apart: one 2-D copy only within the
+        // pitch the runtime accepts, else one copy per stream
+        if (in_pitch < (ptrdiff_t)(in_vals[0] * sizeof(float)) || (size_t)in_pitch > h->mem_pitch)
+            h2d_uniform = false;
+        if (out_pitch <= 0 || (size_t)out_pitch > h->mem_pitch) d2h_uniform = false;
     }
     bool pcm_fused = false;   // the tensor kernel reads the raw s16 frames itself
     uint32_t pcm_raw_mode = 0;   // TcParams::raw16
@@ -624,7 +628,8 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
                 raw_uniform = in_vals[i] == in_vals[0] &&
                               reinterpret_cast<const char *>(jobs[i].in) -
                                       reinterpret_cast<const char *>(jobs[0].in) == (ptrdiff_t)i * raw_pitch;
-            if (raw_pitch < (ptrdiff_t)(in_vals[0] / pcm->dup * pcm->bps)) raw_uniform = false;
+            if (raw_pitch < (ptrdiff_t)(in_vals[0] / pcm->dup * pcm->bps) || (size_t)raw_pitch > h->mem_pitch)
+                raw_uniform = false;
         }
         if (raw_uniform)
             RSB_CUDA(cudaMemcpy2DAsync(h->d_pcm_raw.p, raw_off[1] - raw_off[0], jobs[0].in,
@@ -750,7 +755,8 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
                               W.d_tct2.as<rsb::Tc2Tile>(), h->taps, h->ratio, (uint32_t)tc2_tiles, s);
         rsb::launch_tc2_gmat(W.d_units.as<UnitDev>(), W.d_entries.as<rsb::PlanEntry>(), h->d_coeffs,
                              W.d_tct2.as<rsb::Tc2Tile>(), nullptr, nullptr, W.d_gmat2.as<uint8_t>(), h->taps,
-                             h->ratio, (uint32_t)tc2_tiles, s);
+                             h->ratio, (uint32_t)tc2_tiles,
+                             getenv("RSB_TC_COMP") ? atof(getenv("RSB_TC_COMP")) : rsb::kTc2TruncationComp, s);
     } else if (use_tc)
         rsb::launch_tc_gmat(W.d_units.as<UnitDev>(), W.d_tiles.as<rsb::TileRec>(),
                             W.d_entries.as<rsb::PlanEntry>(), h->d_coeffs, W.d_gtiles.as<float>(),
@@ -798,11 +804,11 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
         if (getenv("RSB_TC_RUN_TILES")) T.run_tiles = (uint32_t)atoi(getenv("RSB_TC_RUN_TILES"));
         T.kt_max = rsb::tc2_kt_extent(h->taps, h->ratio);
         T.issuers = rsb::tc2_issuers(h->taps, h->ratio);
-        T.g_stages = rsb::tc2_g_stages(ch, h->taps, h->ratio);
+        T.variant = getenv("RSB_TC_VARIANT") ? (uint32_t)atoi(getenv("RSB_TC_VARIANT")) : 0u;
+        T.g_stages = rsb::tc2_g_stages(ch, h->taps, h->ratio, T.variant);
         T.prefetch_chunks = getenv("RSB_TC_PREFETCH") ? (uint32_t)atoi(getenv("RSB_TC_PREFETCH")) : 0u;
-        T.g_prefetch = getenv("RSB_TC_GPREFETCH") ? (uint32_t)atoi(getenv("RSB_TC_GPREFETCH")) : 3u;
         T.ablate = getenv("RSB_TC_ABLATE") ? (uint32_t)atoi(getenv("RSB_TC_ABLATE")) : 0u;
-        T.out_scale = rsb::tc2_out_scale(getenv("RSB_TC_COMP") ? atof(getenv("RSB_TC_COMP")) : 0.0);
+        T.out_scale = rsb::tc2_out_scale();
         if (getenv("RSB_TC_GSTAGES")) T.g_stages = std::min<uint32_t>(T.g_stages, (uint32_t)atoi(getenv("RSB_TC_GSTAGES")));
         T.raw16 = pcm_fused ? pcm_raw_mode : 0u;
         T.raw_bytes = pcm && pcm_fused ? pcm->bps : 2u;
@@ -964,6 +970,7 @@ int rsb_fir_create(rsb_fir **out, int device, uint32_t n_streams, uint32_t chann
     std::unique_ptr<rsb_fir> h(new rsb_fir());
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
+    h->mem_pitch = prop.memPitch;
     h->n_streams = n_streams;
     h->channels = channels;
     h->in_hz = input_rate_hz;

@@ -147,18 +147,23 @@ struct Tc2Params {
     uint32_t raw16;           // as TcParams::raw16
     uint32_t raw_bytes;       // bytes per raw sample: 2 (s16) or 3 (packed s24)
     uint32_t prefetch_chunks; // input chunks the TMA producer prefetches into L2 ahead of its loads
-    uint32_t g_prefetch;      // tiles the G producer prefetches into L2 ahead of its copies (0: off)
+    uint32_t variant;         // role layout (debug / tuning; 0 = default, see kVariants in fir_tc2.cu)
     uint32_t ablate;          // debug (RSB_TC_ABLATE): 1 no G copies, 2 no input TMA, 4 no output stores,
                               // 8 splitter: handshakes only, 16 epilogue: handshakes only, 32 one MMA per tile
-    float out_scale;          // epilogue factor: 2^-17 x truncation-bias compensation (tc2_out_scale)
+    float out_scale;          // epilogue factor 2^-17 (undoes the operand prescale)
 };
-float tc2_out_scale(double comp);
+// Expected relative loss (in units of 2^-24) of the tensor core's truncating fp32 accumulation with the
+// kernel's issue order, measured on B200 against an f64 evaluation for full-scale noise:
+// 0.84 (44.1 -> 48 kHz), 0.87 (48 -> 44.1 kHz); tc2_gmat_kernel folds g * comp * 2^-24 into the G_lo matrices
+// (tools/tc2_error_stats.py).
+constexpr double kTc2TruncationComp = 0.85;
+float tc2_out_scale();
 bool tc2_supported(uint32_t channels, uint32_t taps, double ratio);
 uint32_t tc2_kt_extent(uint32_t taps, double ratio);
 size_t tc2_gmat_bytes_per_tile(uint32_t taps, double ratio);
 uint32_t tc2_rows_per_group();
 uint32_t tc2_issuers(uint32_t taps, double ratio);
-uint32_t tc2_g_stages(uint32_t channels, uint32_t taps, double ratio);
+uint32_t tc2_g_stages(uint32_t channels, uint32_t taps, double ratio, uint32_t variant = 0);
 // Output of an equally strided batch as a 2-D tensor for the epilogue's TMA stores; inner
 // dimension clipped to `valid_frames` (what the plan produces, capped by the smallest capacity).
 bool tc2_make_output_tensor_map(CUtensorMap *out, float *base, uint64_t stride_bytes, uint64_t valid_frames,
@@ -168,7 +173,7 @@ void launch_tc2_tiles(const UnitDev *units, const PlanEntry *entries, Tc2Tile *t
 // src_tile / n_stored: optional de-duplication (stored matrix g is built from tile src_tile[g])
 void launch_tc2_gmat(const UnitDev *units, const PlanEntry *entries, const float *coeffs, const Tc2Tile *tct,
                      const uint32_t *src_tile, const uint32_t *n_stored, uint8_t *gmat, uint32_t taps,
-                     double ratio, uint32_t max_stored, cudaStream_t stream);
+                     double ratio, uint32_t max_stored, double comp_units, cudaStream_t stream);
 bool launch_conv_tc2(const Tc2Params &p, const CUtensorMap &tmap_in, const CUtensorMap &tmap_out, int sm_count,
                      bool leave_sm_free, cudaStream_t stream);
 // debug: returns (up to `count` of 24) and clears the kernel's per-role cycle counters, sets the enable flag

@@ -64,6 +64,7 @@ __device__ int g_tc2_prof = 0;
 // {tag, block, warp, parity | barrier address << 8} in a host-mapped buffer and traps (the launch
 // fails with an error instead of hanging the GPU).  Tags: see the kW* constants.
 __device__ unsigned int *g_tc2_hang = nullptr;
+__device__ int g_tc2_watchdog = 0;
 
 namespace {
 
@@ -71,41 +72,55 @@ using namespace ptx;
 
 enum : uint32_t { kWItemFull = 1, kWItemEmpty, kWXsEmpty, kWXsFull, kWGDone, kWJanDone, kWDEmpty, kWGFull,
                   kWXFull, kWXEmpty, kWEpiDone };
-__device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, uint32_t tag) {
-    if (mbar_test(bar, parity)) return;
+// Suspend-time hint of try_wait: without it a failed attempt returns almost at once and the ~15
+// waiting warps of a CTA burn a third of the SM's issue slots re-polling (ncu: 7500 warp
+// instructions per tile, 0.5 IPC per scheduler = the whole tile time).  The warp still wakes up as
+// soon as the phase completes.
+constexpr uint32_t kSuspendHint = 0x989680u;
+__device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(kSuspendHint)
+        : "memory");
+    return ok != 0;
+}
+// Cold path of a wait (kept out of line: the hot loops stay small).  With the watchdog enabled
+// (debug, RSB_TC_WATCHDOG=1) a wait that has not completed after ~2 s records itself and traps.
+__device__ __noinline__ void mbar_wait_slow(uint64_t *bar, uint32_t parity, uint32_t tag) {
+    unsigned int *rec = g_tc2_hang;
+    if (!g_tc2_watchdog || rec == nullptr) {
+        mbar_wait(bar, parity);
+        return;
+    }
     const long long t0 = clock64();
-    uint32_t spins = 0;
     for (;;) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-        if (ok) return;
-        if ((++spins & 255u) == 0 && clock64() - t0 > 4000000000ll) {
+        if (mbar_try(bar, parity)) return;
+        if (clock64() - t0 > 4000000000ll) {
             // first CTA to time out claims the record; every stuck warp of that CTA adds its own
             // wait (slot 4 + warp), then the kernel traps half a second later
-            unsigned int *rec = g_tc2_hang;
-            if (rec) {
-                const unsigned int prev = atomicCAS(&rec[0], 0u, tag);
-                if (prev == 0u) {
-                    rec[1] = blockIdx.x;
-                    rec[2] = threadIdx.x >> 5;
-                    rec[3] = parity | (smem_u32(bar) << 8);
-                }
-                if (prev == 0u || rec[1] == blockIdx.x)
-                    rec[4 + (threadIdx.x >> 5)] = tag | (parity << 8) | (smem_u32(bar) << 12);
-                __threadfence_system();
+            const unsigned int prev = atomicCAS(&rec[0], 0u, tag);
+            if (prev == 0u) {
+                rec[1] = blockIdx.x;
+                rec[2] = threadIdx.x >> 5;
+                rec[3] = parity | (smem_u32(bar) << 8);
             }
+            if (prev == 0u || rec[1] == blockIdx.x)
+                rec[4 + (threadIdx.x >> 5)] = tag | (parity << 8) | (smem_u32(bar) << 12);
+            __threadfence_system();
             while (clock64() - t0 < 5000000000ll) { }
             __trap();
         }
     }
+}
+__device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, uint32_t tag) {
+    if (mbar_try(bar, parity)) return;       // try_wait's already-complete path is the cheapest test
+    mbar_wait_slow(bar, parity, tag);
 }
 
 struct RoleClock {
@@ -134,20 +149,21 @@ constexpr uint32_t kRing = 384;                    // frames in a TMEM ring
 constexpr uint32_t kSlots = kRing / kChunk;        // 24
 constexpr uint32_t kSlotCols = kChunk / 2;         // 8 TMEM columns per slot (two fp16 per column)
 constexpr uint32_t kColHi = 0, kColLo = kRing / 2, kColD = kRing;
-// TMA landing buffers for input chunks.  MUST be a multiple of kSplitTeams: a team then meets
-// every use of "its" stages in turn; otherwise it revisits a stage only every few uses and its
-// parity wait can alias when tensor copies land out of order (found by the watchdog).
-constexpr uint32_t kXStages = 6;
+// Role layout (template parameters ST / ET / XS of the kernel): ST splitter teams and ET epilogue
+// teams of four warps each, XS landing buffers for input chunks.  XS MUST be a multiple of ST: a
+// team then meets every use of "its" stages in turn; otherwise it revisits a stage only every few
+// uses and its parity wait can alias when tensor copies land out of order (found by the
+// watchdog).  Warps: 0-3 epilogue team 0, then 4 x ST splitter warps, then epilogue team 1 (ET == 2),
+// then issuer 0, issuer 1, input TMA producer + scheduler, G producer, janitor.
+constexpr uint32_t kMaxXStages = 8;
 constexpr uint32_t kXStageBytes = kRows * kChunk * 4;   // 8192 for every channel count
-constexpr uint32_t kMaxGStages = 2;
+constexpr uint32_t kMaxGStages = 3;
 constexpr uint32_t kDone = 8;                      // tile-completion barriers (ring)
-constexpr uint32_t kThreads = 25 * 32;
-constexpr uint32_t kSplitTeams = 3;                // splitter teams of four warps (warps 4-15)
-constexpr uint32_t kEpiTeams = 2;                  // epilogue teams of four warps (warps 0-3, 16-19)
-static_assert(kXStages % kSplitTeams == 0 && kSlots % kSplitTeams == 0, "stage / slot ownership must be fixed per team");
-constexpr uint32_t kWarpIssuer0 = 20, kWarpIssuer1 = 21, kWarpTmaIn = 22, kWarpG = 23, kWarpJanitor = 24;
+__host__ __device__ constexpr uint32_t role_threads(uint32_t st, uint32_t et) { return (4u * (st + et) + 5u) * 32u; }
 constexpr uint32_t kItemSlots = 2;
-constexpr uint32_t kItemConsumers = 24;            // 4 * (kSplitTeams + kEpiTeams) + issuers, G producer, janitor            // warps that read every item (all but the scheduler)
+constexpr uint32_t kListEntries = 32;               // main-pass MMA list per tile (128 bytes, after [G_hi, G_lo])
+constexpr uint32_t kListBytes = kListEntries * 4;
+constexpr uint32_t kListEnd = 0xffffffffu;
 constexpr float kScaleX = 16.0f;                   // 2^4
 constexpr float kScaleG = 8192.0f;                 // 2^13
 constexpr float kScaleOut = 1.0f / (16.0f * 8192.0f);
@@ -181,7 +197,7 @@ constexpr uint32_t kBDescHi = (128u >> 4) | (1u << 14);
 constexpr uint32_t kBDescKStep = 2048u >> 4;   // descriptor increment per K step of 16 frames
 
 struct Smem {
-    uint64_t xs_full[kXStages], xs_empty[kXStages];
+    uint64_t xs_full[kMaxXStages], xs_empty[kMaxXStages];
     uint64_t g_full[kMaxGStages];
     uint64_t t_done[kDone];     // tile d's MMAs have completed: barrier d % 8 (tcgen05.commit)
     uint64_t x_full[kSlots], x_empty[kSlots];
@@ -250,6 +266,38 @@ __device__ __forceinline__ void tc_mma_f16_ts_x4(uint32_t d_tmem, uint32_t a0, u
         "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Up to four MMAs of the tile's list with one election: each has its own accumulator column range,
+// A columns, B descriptor and N (instruction descriptor); MMAs k >= n are predicated off.
+__device__ __forceinline__ void tc_mma_f16_ts_list4(uint32_t n, uint32_t d0, uint32_t d1, uint32_t d2, uint32_t d3,
+                                                    uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                    uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3,
+                                                    uint32_t b_hi, uint32_t i0, uint32_t i1, uint32_t i2,
+                                                    uint32_t i3) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred t, e, e1, e2, e3;\n\t"
+        ".reg .b64 x0, x1, x2, x3;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.gt.u32 e1, %0, 1;\n\t"
+        "setp.gt.u32 e2, %0, 2;\n\t"
+        "setp.gt.u32 e3, %0, 3;\n\t"
+        "and.pred e1, e1, e;\n\t"
+        "and.pred e2, e2, e;\n\t"
+        "and.pred e3, e3, e;\n\t"
+        "mov.b64 x0, {%9, %13};\n\t"
+        "mov.b64 x1, {%10, %13};\n\t"
+        "mov.b64 x2, {%11, %13};\n\t"
+        "mov.b64 x3, {%12, %13};\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], [%5], x0, %14, t;\n\t"
+        "@e1 tcgen05.mma.cta_group::1.kind::f16 [%2], [%6], x1, %15, t;\n\t"
+        "@e2 tcgen05.mma.cta_group::1.kind::f16 [%3], [%7], x2, %16, t;\n\t"
+        "@e3 tcgen05.mma.cta_group::1.kind::f16 [%4], [%8], x3, %17, t;\n\t"
+        "}" ::"r"(n),
+        "r"(d0), "r"(d1), "r"(d2), "r"(d3), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(b2), "r"(b3),
+        "r"(b_hi), "r"(i0), "r"(i1), "r"(i2), "r"(i3)
+        : "memory");
+}
 // TMA tensor store shared -> global of one 2-D box (SASS: UTMASTG), bulk-group completion
 __device__ __forceinline__ void tensor_s2g_2d(const CUtensorMap *tm, int c0, int c1, uint32_t smem_addr) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm),
@@ -261,9 +309,6 @@ __device__ __forceinline__ void tensor_s2g_2d(const CUtensorMap *tm, int c0, int
 __device__ __forceinline__ void tensor_prefetch_2d(const CUtensorMap *tm, int c0, int c1) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1)
                  : "memory");
-}
-__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -392,13 +437,22 @@ __device__ __forceinline__ void load_chunk(uint32_t base, const float *stage_ptr
     }
 }
 
-template <int CH, int RAW = 0, int SB = 2>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int CH, int RAW = 0, int SB = 2, int ST = 3, int ET = 2, int XS = 6>
+__global__ void __launch_bounds__(role_threads(ST, ET), 1)
 conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUtensorMap tmap_in,
                 const __grid_constant__ CUtensorMap tmap_out) {
     static_assert(CH == 1 || CH == 2 || CH == 4 || CH == 8, "tensor kernel: 1, 2, 4 or 8 channels");
     static_assert(RAW == 0 || (RAW == 1 && CH <= 2) || (RAW == 2 && CH == 2), "raw input: mono / stereo");
     static_assert(SB == 2 || (SB == 3 && RAW != 0), "raw samples: 16 or packed 24 bits");
+    constexpr uint32_t kSplitTeams = ST, kEpiTeams = ET, kXStages = XS;
+    static_assert(kXStages % kSplitTeams == 0 && kSlots % kSplitTeams == 0 && kXStages <= kMaxXStages,
+                  "stage / slot ownership must be fixed per team");
+    static_assert(ET == 1 || ET == 2, "one or two epilogue teams");
+    constexpr uint32_t kWarpEpi1 = 4 + 4 * kSplitTeams;                 // first warp of epilogue team 1
+    constexpr uint32_t kWarpIssuer0 = 4 + 4 * (kSplitTeams + kEpiTeams - 1), kWarpIssuer1 = kWarpIssuer0 + 1,
+                       kWarpTmaIn = kWarpIssuer0 + 2, kWarpG = kWarpIssuer0 + 3, kWarpJanitor = kWarpIssuer0 + 4;
+    constexpr uint32_t kItemConsumers = 4 * (kSplitTeams + kEpiTeams) + 4;   // every warp but the scheduler
+    constexpr uint32_t kStageBufs = kEpiTeams == 1 ? 2u : 1u;               // staging buffers per epilogue warp
     constexpr bool kRawStereo = RAW == 1 && CH == 2;
     constexpr uint32_t kRawFrameBytes = RAW == 0 ? 0u : (kRawStereo ? 2u : 1u) * SB;
     // bytes one input chunk lands in shared memory: f32 rows, or one row of 16 raw frames per member
@@ -413,8 +467,9 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
     __shared__ Smem S;
     const uint32_t g_bytes = P.kt_max * 128u;           // one G half: kt_max/8 K groups x 1024 B
     uint8_t *xst = smem_tc2;                             // [kXStages][kXStageBytes]
-    uint8_t *ost = smem_tc2 + kXStages * kXStageBytes;   // [kEpiTeams][4 quadrants][kHalfBytes]
-    uint8_t *gst = ost + kEpiTeams * 4 * kHalfBytes;             // [g_stages][2][g_bytes]
+    uint8_t *ost = smem_tc2 + kXStages * kXStageBytes;   // [kEpiTeams][4 quadrants][kStageBufs][kHalfBytes]
+    uint8_t *gst = ost + 2 * 4 * kHalfBytes;             // [g_stages]{[2][g_bytes], MMA list}
+    const uint32_t g_stage_bytes = 2u * g_bytes + kListBytes;
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const bool prof = g_tc2_prof != 0 && blockIdx.x == 0;
@@ -531,22 +586,15 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
                     }
                     rc.lap(18);
                     const uint32_t bytes = m.kt * 128u;
-                    const uint8_t *src = P.gmat + (size_t)m.g_idx * (2u * g_bytes);
-                    if (t + P.g_prefetch < I.t1 && P.g_prefetch) {
-                        // pull a later tile's matrices into L2 (the first of the 16 member groups
-                        // that reaches a tile would otherwise wait for HBM)
-                        const Tc2Tile mp = tct[t + P.g_prefetch];
-                        const uint8_t *ps = P.gmat + (size_t)mp.g_idx * (2u * g_bytes);
-                        bulk_prefetch_l2(ps, mp.kt * 128u);
-                        bulk_prefetch_l2(ps + g_bytes, mp.kt * 128u);
-                    }
-                    uint8_t *dst = gst + (size_t)s * 2 * g_bytes;
+                    const uint8_t *src = P.gmat + (size_t)m.g_idx * g_stage_bytes;
+                    uint8_t *dst = gst + (size_t)s * g_stage_bytes;
                     if ((P.ablate & 1u) && g_seq >= n_gst) {
                         mbar_arrive(&S.g_full[s]);
                     } else {
-                        mbar_arrive_expect_tx(&S.g_full[s], 2 * bytes);
+                        mbar_arrive_expect_tx(&S.g_full[s], 2 * bytes + kListBytes);
                         bulk_g2s(dst, src, bytes, &S.g_full[s]);
                         bulk_g2s(dst + g_bytes, src + g_bytes, bytes, &S.g_full[s]);
+                        bulk_g2s(dst + 2 * g_bytes, src + 2 * g_bytes, kListBytes, &S.g_full[s]);
                     }
                     ++g_seq;
                     rc.lap(19);
@@ -626,22 +674,27 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
                     // released by the janitor and refilled for the ring's next revolution while
                     // this warp was held up elsewhere; a parity wait on them would alias and never
                     // complete -- found by the watchdog with a slow epilogue.)
+                    // A splitter team fills its chunks in order, so the LAST chunk of each team
+                    // inside the range vouches for the team's earlier ones: at most kSplitTeams
+                    // waits per tile instead of one per chunk (an already-complete try_wait still
+                    // costs ~90 cycles of this warp's critical path).
                     {
-                        uint32_t cw = waited > j0 ? waited : j0;
+                        const uint32_t lo_c = waited > j0 ? waited : j0, hi_c = j0 + n_ks;
+                        uint32_t cw = hi_c - lo_c > kSplitTeams ? hi_c - kSplitTeams : lo_c;
                         const uint32_t lin = base_slot + cw;
                         uint32_t w_slot = lin % kSlots, w_par = base_par ^ ((lin / kSlots) & 1u);
-                        for (; cw < j0 + n_ks; ++cw) {
+                        for (; cw < hi_c; ++cw) {
                             mbar_wait_wd(&S.x_full[w_slot], w_par, kWXFull);
                             if (++w_slot == kSlots) { w_slot = 0; w_par ^= 1u; }
                         }
-                        waited = j0 + n_ks;
+                        waited = hi_c;
                     }
                     rc.lap(0);
                     tc_fence_after();
 
                     const uint32_t d_tmem = tmem + kColD + b * kN;
                     const uint32_t s0 = (base_slot + j0) % kSlots;
-                    const uint32_t ghi = b_desc_lo(smem_u32(gst + (size_t)gs * 2 * g_bytes));
+                    const uint32_t ghi = b_desc_lo(smem_u32(gst + (size_t)gs * g_stage_bytes));
                     const uint32_t glo = ghi + (g_bytes >> 4);
                     const uint32_t ahi = tmem + kColHi, alo = tmem + kColLo;
                     constexpr uint32_t kWrapCols = kSlots * kSlotCols;
@@ -649,7 +702,6 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
                     // small terms first: X_lo * G_hi and X_hi * G_lo, two K steps per issue block
                     const uint32_t col0 = s0 * kSlotCols;
                     uint32_t col = col0, dk = 0, ks = 0;
-                    const uint32_t n_ks_real = n_ks;
                     const uint32_t n_ks_issue = (P.ablate & 32u) ? 0u : n_ks;
 #pragma unroll 2
                     for (; ks + 2 <= n_ks_issue; ks += 2) {
@@ -663,28 +715,40 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
                     if (ks < n_ks_issue)
                         tc_mma_f16_ts_x2(d_tmem, alo + col, ghi + dk, ahi + col, glo + dk, kBDescHi, kIdesc,
                                          ks != 0);
-                    // X_hi * G_hi, K steps outside-in (front, back, front + 1, back - 1, ...)
-                    uint32_t cf = col0, cb = wrap(col0 + kSlotCols * (n_ks_real - 1));
-                    uint32_t df = 0, db = (n_ks_real - 1) * kBDescKStep, i = 0;
-                    auto back = [](uint32_t c) { return c >= kSlotCols ? c - kSlotCols : c + kWrapCols - kSlotCols; };
-#pragma unroll 2
-                    for (; i + 4 <= n_ks_issue; i += 4) {
-                        const uint32_t cf1 = wrap(cf + kSlotCols), cb1 = back(cb);
-                        tc_mma_f16_ts_x4(d_tmem, ahi + cf, ahi + cb, ahi + cf1, ahi + cb1, ghi + df, ghi + db,
-                                         ghi + df + kBDescKStep, ghi + db - kBDescKStep, kBDescHi, kIdesc, 1u);
-                        df += 2 * kBDescKStep;
-                        db -= 2 * kBDescKStep;
-                        cf = wrap(cf1 + kSlotCols);
-                        cb = back(cb1);
+                    // X_hi * G_hi: the tile's MMA list (built with the G matrices, same stage).  Every
+                    // K step appears once per output quarter: "early" (outside-in) for the quarters
+                    // whose main lobe lies elsewhere, "late" for those it carries, as MMAs over
+                    // column sub-ranges (entry = K step | first quarter << 8 | quarters << 12).  The
+                    // tensor core's fp32 accumulation truncates; adding an output's main lobe last
+                    // keeps the number of truncations at full magnitude to one or two.
+                    if (P.ablate & 32u) {
+                        tc_mma_f16_ts(d_tmem, ahi + col0, ghi, kBDescHi, kIdesc, 1u);
+                    } else {
+                        const uint32_t lst = smem_u32(gst + (size_t)gs * g_stage_bytes + 2u * g_bytes);
+#pragma unroll 1
+                        for (uint32_t e = 0; e < kListEntries; e += 4) {
+                            uint32_t w[4];
+                            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
+                                         : "r"(lst + e * 4u));
+                            if (w[0] == kListEnd) break;
+                            uint32_t dd[4], aa[4], bb[4], ii[4], nv = 0;
+#pragma unroll
+                            for (uint32_t k = 0; k < 4; ++k) {
+                                const uint32_t ksx = w[k] & 0xffu, q0 = (w[k] >> 8) & 0xfu, nq = (w[k] >> 12) & 0xfu;
+                                uint32_t sl = s0 + ksx;
+                                sl = sl >= kSlots ? sl - kSlots : sl;
+                                dd[k] = d_tmem + q0 * 16u;
+                                aa[k] = ahi + sl * kSlotCols;
+                                bb[k] = ghi + ksx * kBDescKStep + q0 * 16u;
+                                ii[k] = (kIdesc & ~(0x3fu << 17)) | ((nq * 2u) << 17);   // N = 16 * nq
+                                nv += w[k] != kListEnd ? 1u : 0u;
+                            }
+                            tc_mma_f16_ts_list4(nv, dd[0], dd[1], dd[2], dd[3], aa[0], aa[1], aa[2], aa[3], bb[0], bb[1],
+                                                bb[2], bb[3], kBDescHi, ii[0], ii[1], ii[2], ii[3]);
+                            if (nv < 4u) break;
+                        }
                     }
-                    for (; i + 2 <= n_ks_issue; i += 2) {
-                        tc_mma_f16_ts_x2(d_tmem, ahi + cf, ghi + df, ahi + cb, ghi + db, kBDescHi, kIdesc, 1u);
-                        df += kBDescKStep;
-                        db -= kBDescKStep;
-                        cf = wrap(cf + kSlotCols);
-                        cb = back(cb);
-                    }
-                    if (i < n_ks_issue || (P.ablate & 32u)) tc_mma_f16_ts(d_tmem, ahi + cf, ghi + df, kBDescHi, kIdesc, 1u);
                     rc.lap(3);
                     // the tile's only commit: epilogue (accumulator ready), G producer (stage
                     // free) and janitor (ring slots free) all follow this barrier
@@ -805,11 +869,12 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
         // ===== epilogue: accumulator (TMEM) -> scale -> swizzled staging -> TMA tensor stores.
         // A warp owns the 32 accumulator lanes of its quadrant = kMpw members and stores their
         // boxes itself (no barrier wider than a warp). =====
-        const uint32_t team = warp >= 16 ? 1u : 0u;          // drains the tiles with d_seq % 2 == team
+        const uint32_t team = warp >= kWarpEpi1 ? 1u : 0u;   // drains the tiles with d_seq % kEpiTeams == team
         const uint32_t quad = warp & 3u;
         const uint32_t ml = lane / CH, c = lane % CH;       // member inside the warp, channel
         const uint32_t lane_base = (quad * 32u) << 16;
-        const uint32_t sb = smem_u32(ost + (team * 4u + quad) * kHalfBytes);
+        const uint32_t sb0 = smem_u32(ost + (team * 4u + quad) * kStageBufs * kHalfBytes);
+        uint32_t h_seq = 0;
         uint32_t d_seq = 0;
         const float out_scale = P.out_scale;
         rc.start(prof && tid == 0);
@@ -818,7 +883,7 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
             if (!I.valid) break;
             const int32_t m_first = (int32_t)(I.group * kMpg + quad * kMpw);
             for (uint32_t t = I.t0; t < I.t1; ++t, ++d_seq) {
-                if ((d_seq & 1u) != team) continue;
+                if (kEpiTeams == 2 && (d_seq & 1u) != team) continue;
                 const uint32_t o_start = t * kN;
                 const uint32_t b = d_seq & 1u;
                 rc.lap(10);
@@ -844,8 +909,10 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
                     }
                     rc.lap(9);
                     // the staging buffer's previous stores have read it
-                    if (lane == 0) bulk_wait_read<0>();
+                    if (lane == 0) bulk_wait_read<kStageBufs - 1>();
                     __syncwarp();
+                    const uint32_t sb = sb0 + (kStageBufs == 2 ? (h_seq & 1u) * kHalfBytes : 0u);
+                    ++h_seq;
                     rc.lap(20);
                     if constexpr (CH == 1) {
                         // the thread's 32 frames are one 128-byte box row: eight 16-byte units
@@ -925,7 +992,7 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
 template <int TAPS>
 __global__ void __launch_bounds__(256)
 tc2_gmat_kernel(const UnitDev *units, const PlanEntry *entries, const float *coeffs, const Tc2Tile *tct,
-                const uint32_t *src_tile, const uint32_t *n_stored, uint8_t *gmat, uint32_t kt_max) {
+                const uint32_t *src_tile, const uint32_t *n_stored, uint8_t *gmat, uint32_t kt_max, float comp) {
     const UnitDev &U = units[0];
     const uint32_t g = blockIdx.x;
     if (n_stored ? g >= *n_stored : false) return;
@@ -946,8 +1013,52 @@ tc2_gmat_kernel(const UnitDev *units, const PlanEntry *entries, const float *coe
     const float *ca = coeffs + (size_t)p1 * TAPS;
     const float *cb = coeffs + (size_t)p2 * TAPS;
     const size_t g_bytes = (size_t)kt_max * 128u;
-    uint4 *dst_hi = reinterpret_cast<uint4 *>(gmat + (size_t)g * 2 * g_bytes);
-    uint4 *dst_lo = reinterpret_cast<uint4 *>(gmat + (size_t)g * 2 * g_bytes + g_bytes);
+    const size_t tile_bytes = 2 * g_bytes + kListBytes;
+    uint4 *dst_hi = reinterpret_cast<uint4 *>(gmat + (size_t)g * tile_bytes);
+    uint4 *dst_lo = reinterpret_cast<uint4 *>(gmat + (size_t)g * tile_bytes + g_bytes);
+    // ---- the tile's main-pass MMA list ----
+    __shared__ int s_v[kN];
+    if (tid < kN) s_v[tid] = ent[tid < m.n_out ? tid : 0].v;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t *list = reinterpret_cast<uint32_t *>(gmat + (size_t)g * tile_bytes + 2 * g_bytes);
+        const int n_ks = (int)(m.kt / kChunk);
+        // K steps holding the main lobe (taps TAPS/2 - 1 and TAPS/2) of each quarter's outputs
+        int lo[4], hi[4];
+        for (int q = 0; q < 4; ++q) {
+            lo[q] = 1;
+            hi[q] = 0;
+            if (16u * q < m.n_out) {
+                const uint32_t last = min(16u * q + 15u, m.n_out - 1u);
+                lo[q] = (s_v[16 * q] - m.k0 + TAPS / 2 - 1) / (int)kChunk;
+                hi[q] = min((s_v[last] - m.k0 + TAPS / 2) / (int)kChunk, n_ks - 1);
+            }
+        }
+        uint32_t n = 0;
+        auto emit_ranges = [&](int ks, uint32_t mask) {
+            for (uint32_t q = 0; q < 4;) {
+                if (!((mask >> q) & 1u)) { ++q; continue; }
+                uint32_t q1 = q;
+                while (q1 < 4 && ((mask >> q1) & 1u)) ++q1;
+                if (n < kListEntries - 1) list[n++] = (uint32_t)ks | (q << 8) | ((q1 - q) << 12);
+                q = q1;
+            }
+        };
+        auto central = [&](int ks) {
+            uint32_t mk = 0;
+            for (int q = 0; q < 4; ++q)
+                if (ks >= lo[q] && ks <= hi[q]) mk |= 1u << q;
+            return mk;
+        };
+        // early: outside-in over all K steps, for the quarters the step is not central for
+        for (int f = 0, b = n_ks - 1; f <= b; ++f, --b) {
+            emit_ranges(f, ~central(f) & 0xfu);
+            if (b != f) emit_ranges(b, ~central(b) & 0xfu);
+        }
+        // late: ascending, for the quarters the step is central for
+        for (int ks = 0; ks < n_ks; ++ks) emit_ranges(ks, central(ks));
+        for (; n < kListEntries; ++n) list[n] = kListEnd;
+    }
     for (uint32_t kg = tid >> 6; kg < m.kt / 8; kg += 4) {
         uint32_t hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
         const int j0 = (int)(8 * kg) - d;
@@ -964,7 +1075,11 @@ tc2_gmat_kernel(const UnitDev *units, const PlanEntry *entries, const float *coe
             for (int q = 0; q < 4; ++q) {
                 const __half2 h = __floats2half2_rn(gv[2 * q], gv[2 * q + 1]);
                 const float2 hf = __half22float2(h);
-                const __half2 l = __floats2half2_rn(__fsub_rn(gv[2 * q], hf.x), __fsub_rn(gv[2 * q + 1], hf.y));
+                // lo = residual + g * comp: the compensation of the accumulator's truncation rides
+                // in the lo matrix (the residual is ~2^-12 g, fp32 resolves the 2^-24 g term easily;
+                // (1 + 0.85 * 2^-24) itself is not representable in fp32, so the epilogue cannot apply it)
+                const __half2 l = __floats2half2_rn(__fmaf_rn(gv[2 * q], comp, __fsub_rn(gv[2 * q], hf.x)),
+                                                    __fmaf_rn(gv[2 * q + 1], comp, __fsub_rn(gv[2 * q + 1], hf.y)));
                 hi[q] = *reinterpret_cast<const uint32_t *>(&h);
                 lo[q] = *reinterpret_cast<const uint32_t *>(&l);
             }
@@ -1029,13 +1144,14 @@ bool tc2_supported(uint32_t channels, uint32_t taps, double ratio) {
 
 uint32_t tc2_kt_extent(uint32_t taps, double ratio) { return kt_max_of(taps, ratio); }
 
-size_t tc2_gmat_bytes_per_tile(uint32_t taps, double ratio) { return (size_t)2 * kt_max_of(taps, ratio) * 128u; }
+size_t tc2_gmat_bytes_per_tile(uint32_t taps, double ratio) {
+    return (size_t)2 * kt_max_of(taps, ratio) * 128u + kListBytes;
+}
 
 uint32_t tc2_rows_per_group() { return kRows; }
 
-// 2^-17 undoes the operand prescale; `comp` (in units of 2^-24) compensates the expected loss of
-// the tensor core's truncating fp32 accumulation (numerics of the tensor kernel)
-float tc2_out_scale(double comp) { return (float)((double)kScaleOut * (1.0 + comp * 5.9604644775390625e-08)); }
+// 2^-17 undoes the operand prescale (exact)
+float tc2_out_scale() { return kScaleOut; }
 
 // Two issuers keep two consecutive tiles in flight: their K ranges (the second starts up to
 // floor(64*ratio)+1 frames later, rounded to the chunk grid) must fit the ring together.
@@ -1074,20 +1190,27 @@ void launch_tc2_tiles(const UnitDev *units, const PlanEntry *entries, Tc2Tile *t
 
 void launch_tc2_gmat(const UnitDev *units, const PlanEntry *entries, const float *coeffs, const Tc2Tile *tct,
                      const uint32_t *src_tile, const uint32_t *n_stored, uint8_t *gmat, uint32_t taps,
-                     double ratio, uint32_t max_stored, cudaStream_t stream) {
+                     double ratio, uint32_t max_stored, double comp_units, cudaStream_t stream) {
     if (max_stored == 0) return;
+    const float comp = (float)(comp_units * 5.9604644775390625e-08);   // units of 2^-24
     const uint32_t kt_max = kt_max_of(taps, ratio);
     switch (taps) {
-        case 16: tc2_gmat_kernel<16><<<max_stored, 256, 0, stream>>>(units, entries, coeffs, tct, src_tile, n_stored, gmat, kt_max); break;
-        case 32: tc2_gmat_kernel<32><<<max_stored, 256, 0, stream>>>(units, entries, coeffs, tct, src_tile, n_stored, gmat, kt_max); break;
-        case 64: tc2_gmat_kernel<64><<<max_stored, 256, 0, stream>>>(units, entries, coeffs, tct, src_tile, n_stored, gmat, kt_max); break;
-        default: tc2_gmat_kernel<128><<<max_stored, 256, 0, stream>>>(units, entries, coeffs, tct, src_tile, n_stored, gmat, kt_max); break;
+        case 16: tc2_gmat_kernel<16><<<max_stored, 256, 0, stream>>>(units, entries, coeffs, tct, src_tile, n_stored, gmat, kt_max, comp); break;
+        case 32: tc2_gmat_kernel<32><<<max_stored, 256, 0, stream>>>(units, entries, coeffs, tct, src_tile, n_stored, gmat, kt_max, comp); break;
+        case 64: tc2_gmat_kernel<64><<<max_stored, 256, 0, stream>>>(units, entries, coeffs, tct, src_tile, n_stored, gmat, kt_max, comp); break;
+        default: tc2_gmat_kernel<128><<<max_stored, 256, 0, stream>>>(units, entries, coeffs, tct, src_tile, n_stored, gmat, kt_max, comp); break;
     }
 }
 
-uint32_t tc2_g_stages(uint32_t channels, uint32_t taps, double ratio) {
+// role layouts that are compiled (ST, ET, XS); index = Tc2Params::variant
+struct Variant { uint32_t st, et, xs; };
+static const Variant kVariants[] = {{3, 2, 6}, {2, 1, 4}, {2, 2, 4}, {4, 1, 8}, {2, 1, 8}, {3, 1, 6}};
+constexpr uint32_t kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+
+uint32_t tc2_g_stages(uint32_t channels, uint32_t taps, double ratio, uint32_t variant) {
+    const Variant V = kVariants[variant < kNumVariants ? variant : 0];
     const size_t half = (size_t)channels * ((32u / channels) * 128u < 1024u ? 1024u : (32u / channels) * 128u);
-    const size_t fixed = (size_t)kXStages * kXStageBytes + kEpiTeams * 4 * half + 2048;   // + static barriers
+    const size_t fixed = (size_t)V.xs * kXStageBytes + 2 * 4 * half + 2048;   // + static barriers
     const size_t per_stage = tc2_gmat_bytes_per_tile(taps, ratio);
     const size_t budget = 232448;    // 227 KB per CTA
     size_t n = (budget - fixed) / per_stage;
@@ -1099,31 +1222,46 @@ static void ensure_hang_buffer();
 
 bool launch_conv_tc2(const Tc2Params &p, const CUtensorMap &tmap_in, const CUtensorMap &tmap_out, int sm_count,
                      bool leave_sm_free, cudaStream_t stream) {
+    const uint32_t variant = p.variant < kNumVariants ? p.variant : 0;
+    const Variant V = kVariants[variant];
     const size_t half = (size_t)p.channels * ((32u / p.channels) * 128u < 1024u ? 1024u : (32u / p.channels) * 128u);
-    const size_t smem = (size_t)kXStages * kXStageBytes + kEpiTeams * 4 * half + (size_t)p.g_stages * 2 * p.kt_max * 128u;
+    const size_t smem = (size_t)V.xs * kXStageBytes + 2 * 4 * half + (size_t)p.g_stages * (2 * p.kt_max * 128u + kListBytes);
     if (p.g_stages < 2) return false;
     ensure_hang_buffer();
     // one SM is left free when the next submit's (serial) plan kernel may need somewhere to run
     const uint32_t grid = (uint32_t)(leave_sm_free && sm_count > 8 ? sm_count - 1 : sm_count);
-    auto launch = [&](auto kern) {
+    auto launch = [&](auto kern, uint32_t threads) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<grid, kThreads, smem, stream>>>(p, tmap_in, tmap_out);
+        kern<<<grid, threads, smem, stream>>>(p, tmap_in, tmap_out);
     };
+    const uint32_t thr = role_threads(V.st, V.et);
+    if (variant != 0) {
+        // experiment variants: stereo f32 only
+        if (p.channels != 2 || p.raw16) return false;
+        switch (variant) {
+            case 1: launch(conv_tc2_kernel<2, 0, 2, 2, 1, 4>, thr); break;
+            case 2: launch(conv_tc2_kernel<2, 0, 2, 2, 2, 4>, thr); break;
+            case 3: launch(conv_tc2_kernel<2, 0, 2, 4, 1, 8>, thr); break;
+            case 4: launch(conv_tc2_kernel<2, 0, 2, 2, 1, 8>, thr); break;
+            default: launch(conv_tc2_kernel<2, 0, 2, 3, 1, 6>, thr); break;
+        }
+        return true;
+    }
     switch (p.channels) {
         case 1:
-            if (p.raw16 && p.raw_bytes == 3) launch(conv_tc2_kernel<1, 1, 3>);
-            else if (p.raw16) launch(conv_tc2_kernel<1, 1>);
-            else launch(conv_tc2_kernel<1>);
+            if (p.raw16 && p.raw_bytes == 3) launch(conv_tc2_kernel<1, 1, 3>, thr);
+            else if (p.raw16) launch(conv_tc2_kernel<1, 1>, thr);
+            else launch(conv_tc2_kernel<1>, thr);
             break;
         case 2:
-            if (p.raw16 == 2 && p.raw_bytes == 3) launch(conv_tc2_kernel<2, 2, 3>);
-            else if (p.raw16 == 1 && p.raw_bytes == 3) launch(conv_tc2_kernel<2, 1, 3>);
-            else if (p.raw16 == 2) launch(conv_tc2_kernel<2, 2>);
-            else if (p.raw16 == 1) launch(conv_tc2_kernel<2, 1>);
-            else launch(conv_tc2_kernel<2>);
+            if (p.raw16 == 2 && p.raw_bytes == 3) launch(conv_tc2_kernel<2, 2, 3>, thr);
+            else if (p.raw16 == 1 && p.raw_bytes == 3) launch(conv_tc2_kernel<2, 1, 3>, thr);
+            else if (p.raw16 == 2) launch(conv_tc2_kernel<2, 2>, thr);
+            else if (p.raw16 == 1) launch(conv_tc2_kernel<2, 1>, thr);
+            else launch(conv_tc2_kernel<2>, thr);
             break;
-        case 4: launch(conv_tc2_kernel<4>); break;
-        default: launch(conv_tc2_kernel<8>); break;
+        case 4: launch(conv_tc2_kernel<4>, thr); break;
+        default: launch(conv_tc2_kernel<8>, thr); break;
     }
     return true;
 }
@@ -1145,6 +1283,8 @@ static void ensure_hang_buffer() {
     if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) { cudaGetLastError(); cudaFreeHost(h); return; }
     if (cudaMemcpyToSymbol(g_tc2_hang, &d, sizeof(d)) != cudaSuccess) { cudaGetLastError(); cudaFreeHost(h); return; }
     g_hang_host = static_cast<unsigned int *>(h);
+    const int wd = getenv("RSB_TC_WATCHDOG") && atoi(getenv("RSB_TC_WATCHDOG")) ? 1 : 0;
+    cudaMemcpyToSymbol(g_tc2_watchdog, &wd, sizeof(int));
 }
 
 void tc2_phase_profile(int enable, unsigned long long *out, uint32_t count) {

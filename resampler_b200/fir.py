@@ -278,6 +278,9 @@ class FirBatch:
         """Canonical caller loop per stream (host arrays).  Returns a dict with ``out`` (list of
         arrays), ``consumed``, ``produced`` (values) and ``calls`` per stream."""
         n = len(inputs)
+        for a in inputs:     # the C ABI reads raw f32 memory: no silent reinterpretation
+            if not isinstance(a, np.ndarray) or a.dtype != np.float32 or not a.flags["C_CONTIGUOUS"]:
+                raise TypeError("process() needs C-contiguous float32 arrays")
         if out_capacity is None:
             longest = max((a.size for a in inputs), default=0)
             out_capacity = int(longest / self.ratio()) + 4 * self.buffer_size_output() + 64

@@ -40,9 +40,21 @@ def read_wav(path) -> WavData:
         cid, size = b[pos:pos + 4], struct.unpack_from("<I", b, pos + 4)[0]
         body = b[pos + 8:pos + 8 + size]
         if cid == b"fmt ":
+            if len(body) < 16:
+                raise ValueError(f"{path}: fmt chunk of {len(body)} bytes (at least 16 needed)")
             tag, ch, rate, _, _, bits = struct.unpack_from("<HHIIHH", body, 0)
-            if tag == WAVE_FORMAT_EXTENSIBLE and len(body) >= 26:
+            if tag == WAVE_FORMAT_EXTENSIBLE:
+                if len(body) < 26:
+                    raise ValueError(f"{path}: truncated WAVE_FORMAT_EXTENSIBLE fmt chunk")
+                valid_bits = struct.unpack_from("<H", body, 18)[0]
                 tag = struct.unpack_from("<H", body, 24)[0]      # first word of the sub-format GUID
+                if valid_bits not in (0, bits):
+                    # e.g. 24 valid bits in 32-bit containers: the scale of the format step would
+                    # be wrong; refuse rather than decode with the container width
+                    raise ValueError(f"{path}: {valid_bits} valid bits in {bits}-bit containers "
+                                     "are not supported")
+            if ch == 0:
+                raise ValueError(f"{path}: zero channels")
             spec = (tag, ch, rate, bits)
         elif cid == b"data":
             data = body
@@ -59,7 +71,9 @@ def read_wav(path) -> WavData:
         raise ValueError(f"{path}: unsupported WAV encoding (format tag {tag}, {bits} bits)")
     frame_bytes = ch * fmt.bytes_per_sample()
     raw = np.frombuffer(data, np.uint8)
-    raw = raw[:raw.size - raw.size % frame_bytes].copy()
+    if len(data) < size:
+        raise ValueError(f"{path}: data chunk announces {size} bytes, the file holds {len(data)}")
+    raw = raw[:raw.size - raw.size % frame_bytes].copy()     # hound likewise reads whole frames only
     return WavData(rate, ch, bits, fmt, raw)
 
 

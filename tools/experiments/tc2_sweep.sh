@@ -2,4 +2,4 @@ run() { timeout 100 python bench.py --steps 4 --warmup 2 --no-cpu --no-e2e --sec
 try:
     d=json.loads(l); print(d['roofline']['conv_ms_per_launch'], d['ms_per_step'])
 except Exception: print(l[:600])"; }
-for a in 0 7 15 23 39 31 47 55 63 8 16 32 56; do echo -n "ablate=$a: "; RSB_TC_ABLATE=$a run; done
+for a in ${ABL:-0 7 63 16 4 2 56}; do echo -n "ablate=$a: "; RSB_TC_ABLATE=$a run; done

@@ -31,7 +31,7 @@ __device__ __forceinline__ void tensor_s2g_3d(const CUtensorMap *tm, int c0, int
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(src)) : "memory");
 }
 
-struct Maps { CUtensorMap in2, out2, in3m, out3m, in3p, out3p; };
+struct Maps { CUtensorMap in2, out2, in3m, out3m, in3p, out3p, out2q; };
 
 // units: "piece" = 16 frames.  A run is run_pieces consecutive pieces of one member group.
 __global__ void __launch_bounds__(64, 1) stream_kernel(const __grid_constant__ Maps M, int mode, int do_store, int run_pieces,
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(64, 1) stream_kernel(const __grid_constant__ M
     __shared__ int s_item[2];
     __shared__ uint64_t item_full[2], item_empty[2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t per = mode == 0 ? 1u : kSuper;            // pieces per stage unit
+    const uint32_t per = (mode == 0 || mode == 4) ? 1u : kSuper;            // pieces per stage unit
     const uint32_t n_units = kStages / per;                    // stage units in the ring
     if (threadIdx.x == 0) {
         for (uint32_t i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(64, 1) stream_kernel(const __grid_constant__ M
                     uint8_t *dst = smem + u * per * kPieceBytes;
                     const int piece = run * run_pieces + p;
                     mbar_arrive_expect_tx(&full[u], per * kPieceBytes);
-                    if (mode == 0) tensor_g2s_2d(dst, &M.in2, piece * 16, m0, &full[u]);
+                    if (mode == 0 || mode == 4) tensor_g2s_2d(dst, &M.in2, piece * 16, m0, &full[u]);
                     else if (mode == 1) for (uint32_t q = 0; q < kSuper; ++q) tensor_g2s_2d(dst + q * kPieceBytes, &M.in2, (piece + q) * 16, m0, &full[u]);
                     else if (mode == 2) tensor_g2s_3d(dst, &M.in3m, 0, piece, m0, &full[u]);
                     else tensor_g2s_3d(dst, &M.in3p, 0, m0, piece, &full[u]);
@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(64, 1) stream_kernel(const __grid_constant__ M
                         const uint8_t *src = smem + u * per * kPieceBytes;
                         const int piece = run * run_pieces + p;
                         if (mode == 0) tensor_s2g_2d(&M.out2, piece * 16, m0, src);
+                        else if (mode == 4) for (uint32_t q = 0; q < 4; ++q) tensor_s2g_2d(&M.out2q, piece * 16, m0 + 16 * q, src + q * 2048);
                         else if (mode == 1) for (uint32_t q = 0; q < kSuper; ++q) tensor_s2g_2d(&M.out2, (piece + q) * 16, m0, src + q * kPieceBytes);
                         else if (mode == 2) tensor_s2g_3d(&M.out3m, 0, piece, m0, src);
                         else tensor_s2g_3d(&M.out3p, 0, m0, piece, src);
@@ -141,14 +142,19 @@ int main() {
     mk(&M.in2, in, in_stride, 0); mk(&M.out2, out, out_stride, 0);
     mk(&M.in3m, in, in_stride, 1); mk(&M.out3m, out, out_stride, 1);
     mk(&M.in3p, in, in_stride, 2); mk(&M.out3p, out, out_stride, 2);
+    {
+        cuuint32_t es[2] = {1, 1};
+        cuuint64_t d[2] = {frames, (cuuint64_t)kStreams}; cuuint64_t st[1] = {out_stride}; cuuint32_t b[2] = {16, 16};
+        if (enc(&M.out2q, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, out, d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { printf("encode q failed\n"); exit(1); }
+    }
     const int run_pieces = 352, runs_total = (int)(frames / 16 / run_pieces);
     const size_t smem = kStages * kPieceBytes;
     CK(cudaFuncSetAttribute(stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    const char *names[4] = {"2-D x1 (128 B/member)", "2-D x4 back to back", "3-D member-major 512 B", "3-D piece-major"};
+    const char *names[5] = {"2-D x1 (128 B/member)", "2-D x4 back to back", "3-D member-major 512 B", "3-D piece-major", "2-D x1, stores 4 x 16 rows"};
     for (int do_store = 0; do_store < 2; ++do_store)
-        for (int mode = 0; mode < 4; ++mode) {
+        for (int mode = 0; mode < 5; ++mode) {
             float best = 1e30f;
             for (int rep = 0; rep < 3; ++rep) {
                 CK(cudaMemset(counter, 0, 4));

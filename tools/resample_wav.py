@@ -40,7 +40,14 @@ def resample_files(paths, out_dir, sample_rate, latency=64, attenuation=90, devi
     out_dir = Path(out_dir)
     out_dir.mkdir(parents=True, exist_ok=True)
     groups = defaultdict(list)          # (input rate, format, channels) -> files
+    names = {}
     for p in paths:
+        # every output lands in out_dir under the input's base name: two inputs with the same
+        # base name would overwrite each other (possibly from two threads)
+        if Path(p).name in names:
+            raise SystemExit(f"Error: {p} and {names[Path(p).name]} would both be written to "
+                             f"{Path(out_dir) / Path(p).name}")
+        names[Path(p).name] = p
         w = read_wav(p)
         if w.sample_rate not in SUPPORTED:
             raise SystemExit(f"Unsupported input sample rate: {w.sample_rate}. Supported rates: "
