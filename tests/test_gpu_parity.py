@@ -305,7 +305,7 @@ def test_fast_kernel_within_tolerance(ch, in_hz, out_hz, lat, call_frames, cap_f
 
 
 # ---------------------------------------------------------------------------------------------
-# TENSOR kernel (tcgen05, 3xTF32): same bar -- counts/phases bit-exact, samples within 1e-6
+# TENSOR kernel (tcgen05, split fp16 with prescale): same bar -- counts/phases bit-exact, samples within 1e-6
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("ch,in_hz,out_hz,lat,call_frames,cap_frames,n_streams", [
     (2, 44100, 48000, 3, 512, 0, 70),     # config 2 pattern; one full + one partial row group
@@ -455,7 +455,15 @@ def test_device_memspace_async_and_full_size_properties():
             outs[(kern, name)] = d_out.download().reshape(n, out_stride)[:, :prod[0]]
             d_out.free()
         assert np.array_equal(outs[(kern, "x")], outs[(kern, "x_again")])
-        assert np.array_equal(outs[(kern, "2x")], outs[(kern, "x")] * np.float32(2.0))
+        if kern == Kernel.TENSOR:
+            # fp16 hi/lo operands: the lo part of a sample below 2^-6 is an fp16 subnormal (absolute
+            # quantum 2^-28 in units of x); that ~1e-9 perturbation can flip the last bit of an
+            # accumulation, so scaling by two is exact to ONE ulp of the output (|y| < 4)
+            dev = float(np.max(np.abs(outs[(kern, "2x")].astype(np.float64) -
+                                      2.0 * outs[(kern, "x")].astype(np.float64))))
+            assert dev <= 2.4e-7, dev
+        else:
+            assert np.array_equal(outs[(kern, "2x")], outs[(kern, "x")] * np.float32(2.0))
         b.close()
     # the kernels agree within the tolerance on every sample of every stream
     for kern in (Kernel.FAST, Kernel.TENSOR):
