@@ -96,7 +96,6 @@ struct Pending {
 // submit i is still running on the main stream.
 struct Workspace {
     DevBuf d_units, d_jobs, d_segs, d_calls, d_tiles, d_entries, d_gtiles, d_tct, d_counter;
-    DevBuf d_tct2, d_gmat2;   // tensor kernel generation 2: 64-output tile records, fp16 G store
     PinBuf h_units, h_jobs, h_units_back, h_calls_back, h_segs, h_counter;
     DevBuf d_pcm_jobs;   // job table of the PCM format step (rsb_fir_process_pcm_batch)
     PinBuf h_pcm_jobs;
@@ -146,6 +145,21 @@ struct rsb_fir {
     cudaEvent_t ev_conv[kConvRing][2] = {};
     uint64_t conv_batches = 0;
 
+    // Tensor-kernel plan cache: the tile records and the G store depend only on (start state of
+    // the cohort, call signature), not on sample data; a batch whose plan key equals the cached
+    // one (e.g. the same batch shape after reset()) reuses them and skips the builders.
+    struct Tc2PlanKey {
+        uint64_t pos_bits = 0, total_frames = 0;
+        uint32_t avail = 0, call_frames = 0, cap_frames = 0, single = 0;
+        bool valid = false;
+        bool operator==(const Tc2PlanKey &o) const {
+            return valid && o.valid && pos_bits == o.pos_bits && total_frames == o.total_frames &&
+                   avail == o.avail && call_frames == o.call_frames && cap_frames == o.cap_frames &&
+                   single == o.single;
+        }
+    } tc2_key;
+    DevBuf d_tct2, d_gmat2;          // 64-output tile records, fp16 G store (+ MMA lists) of tc2_key
+    uint64_t tc2_cache_hits = 0;
     Workspace ws[2];
     uint64_t submits = 0;             // ws[submits & 1] is the next one to use
     DevBuf d_stage_in, d_stage_out, d_dbg;   // host-memspace staging (those calls are synchronous)
@@ -529,11 +543,22 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     W.job_stream.resize(n);
     for (uint32_t i = 0; i < n; ++i) W.job_stream[i] = jobs[i].stream;
     uint64_t host_tiles = 0;
+    rsb_fir::Tc2PlanKey plan_key;
     if (host_plan) {
         RSB_CUDA(W.h_segs.reserve(sizeof(rsb::PlanSeg) * seg_total));
         RSB_CUDA(W.h_counter.reserve(sizeof(uint32_t) * 4));
         rsb::PlanSeg *hs = W.h_segs.as<rsb::PlanSeg>();
         rsb::CallCounts *hc = rec_calls ? W.h_calls_back.as<rsb::CallCounts>() : nullptr;
+        if (n_units == 1) {
+            const uint32_t rep = hu[0].rep_stream;
+            std::memcpy(&plan_key.pos_bits, &h->m_pos[rep], sizeof(uint64_t));
+            plan_key.avail = h->m_avail[rep];
+            plan_key.total_frames = hu[0].total_frames;
+            plan_key.call_frames = hu[0].call_frames;
+            plan_key.cap_frames = hu[0].cap_frames;
+            plan_key.single = hu[0].single_call;
+            plan_key.valid = true;
+        }
         for (uint32_t u = 0; u < n_units; ++u) {
             const uint32_t rep = hu[u].rep_stream;
             plan_unit_host(hu[u], rsb::PlanState{h->m_pos[rep], h->m_avail[rep]}, h->ratio, h->taps,
@@ -574,9 +599,16 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
                                                       valid, n, ch);
         tc2_tiles = (hu[0].total_out + rsb::kTc2TileOut - 1) / rsb::kTc2TileOut;
     }
+    bool tc2_hit = false;
     if (use_tc2) {
-        RSB_CUDA(W.d_tct2.reserve(sizeof(rsb::Tc2Tile) * tc2_tiles));
-        RSB_CUDA(W.d_gmat2.reserve(rsb::tc2_gmat_bytes_per_tile(h->taps, h->ratio) * tc2_tiles));
+        tc2_hit = plan_key == h->tc2_key && !getenv("RSB_TC_NO_PLAN_CACHE");
+        if (!tc2_hit) {
+            h->tc2_key.valid = false;      // the buffers are about to be rebuilt (or freed by a failed reserve)
+            RSB_CUDA(h->d_tct2.reserve(sizeof(rsb::Tc2Tile) * tc2_tiles));
+            RSB_CUDA(h->d_gmat2.reserve(rsb::tc2_gmat_bytes_per_tile(h->taps, h->ratio) * tc2_tiles));
+        } else {
+            h->tc2_cache_hits += 1;
+        }
     } else if (use_tc && !rsb::tc_supported(ch, h->taps, h->ratio)) {
         use_tc = false;      // generation 1 cannot take this ratio: FFMA2 / exact kernel
         if (use_fast) RSB_CUDA(W.d_gtiles.reserve(sizeof(float) * rsb::kTileOut * gs * tile_total));
@@ -746,17 +778,24 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     // the main stream in front of the convolution.  (Running them on the plan stream underneath
     // the previous submit's convolution was measured: they take 1.1 ms alone but slow the
     // persistent convolution kernel by 1.5 ms.)
-    rsb::launch_tiles(W.d_units.as<UnitDev>(), n_units, W.d_segs.as<rsb::PlanSeg>(),
-                      W.d_tiles.as<rsb::TileRec>(), W.d_entries.as<rsb::PlanEntry>(),
-                      (uint32_t)max_tiles_unit, h->taps, h->d_coeffs,
-                      use_fast && !use_tc ? W.d_gtiles.as<float>() : nullptr, gs, s);
-    if (use_tc2) {
+    // (a cached tensor plan needs neither tile records nor per-frame entries, unless the caller
+    // wants to read the plan back)
+    const bool skip_tiles = tc2_hit && !(flags & RSB_FLAG_KEEP_PLAN);
+    if (!skip_tiles)
+        rsb::launch_tiles(W.d_units.as<UnitDev>(), n_units, W.d_segs.as<rsb::PlanSeg>(),
+                          W.d_tiles.as<rsb::TileRec>(), W.d_entries.as<rsb::PlanEntry>(),
+                          (uint32_t)max_tiles_unit, h->taps, h->d_coeffs,
+                          use_fast && !use_tc ? W.d_gtiles.as<float>() : nullptr, gs, s);
+    if (use_tc2 && !tc2_hit) {
         rsb::launch_tc2_tiles(W.d_units.as<UnitDev>(), W.d_entries.as<rsb::PlanEntry>(),
-                              W.d_tct2.as<rsb::Tc2Tile>(), h->taps, h->ratio, (uint32_t)tc2_tiles, s);
+                              h->d_tct2.as<rsb::Tc2Tile>(), h->taps, h->ratio, (uint32_t)tc2_tiles, s);
         rsb::launch_tc2_gmat(W.d_units.as<UnitDev>(), W.d_entries.as<rsb::PlanEntry>(), h->d_coeffs,
-                             W.d_tct2.as<rsb::Tc2Tile>(), nullptr, nullptr, W.d_gmat2.as<uint8_t>(), h->taps,
+                             h->d_tct2.as<rsb::Tc2Tile>(), nullptr, nullptr, h->d_gmat2.as<uint8_t>(), h->taps,
                              h->ratio, (uint32_t)tc2_tiles,
                              getenv("RSB_TC_COMP") ? atof(getenv("RSB_TC_COMP")) : rsb::kTc2TruncationComp, s);
+        h->tc2_key = plan_key;
+    } else if (use_tc2) {
+        // cached
     } else if (use_tc)
         rsb::launch_tc_gmat(W.d_units.as<UnitDev>(), W.d_tiles.as<rsb::TileRec>(),
                             W.d_entries.as<rsb::PlanEntry>(), h->d_coeffs, W.d_gtiles.as<float>(),
@@ -791,8 +830,8 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
         rsb::Tc2Params T;
         T.units = P.units;
         T.jobs = P.jobs;
-        T.tct = W.d_tct2.as<rsb::Tc2Tile>();
-        T.gmat = W.d_gmat2.as<uint8_t>();
+        T.tct = h->d_tct2.as<rsb::Tc2Tile>();
+        T.gmat = h->d_gmat2.as<uint8_t>();
         T.work_counter = P.work_counter;
         T.channels = ch;
         const uint32_t mpg = rsb::tc2_rows_per_group() / ch;
@@ -845,7 +884,7 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     RSB_CUDA(cudaEventRecord(h->ev_conv[ring][1], s));
     h->conv_batches += 1;
     rsb::launch_update(W.d_units.as<UnitDev>(), W.d_jobs.as<JobDev>(), n, h->st, ch, s);
-    h->launches += (use_tc2 ? 7 : use_tc ? 6 : 5) - (host_plan ? 1 : 0);
+    h->launches += (use_tc2 ? (tc2_hit ? (skip_tiles ? 4 : 5) : 7) : use_tc ? 6 : 5) - (host_plan ? 1 : 0);
     RSB_CUDA(cudaGetLastError());
     RSB_CUDA(cudaEventRecord(W.ev_done, s));
     h->submits += 1;
@@ -1040,7 +1079,7 @@ void rsb_fir_destroy(rsb_fir *h) {
         if (W.ev_plan) cudaEventDestroy(W.ev_plan);
         if (W.ev_done) cudaEventDestroy(W.ev_done);
     }
-    for (DevBuf *b : {&h->d_stage_in, &h->d_stage_out, &h->d_dbg, &h->d_pcm_raw, &h->d_zero})
+    for (DevBuf *b : {&h->d_stage_in, &h->d_stage_out, &h->d_dbg, &h->d_pcm_raw, &h->d_zero, &h->d_tct2, &h->d_gmat2})
         b->release();
     for (cudaEvent_t e : h->ev_pcm) if (e) cudaEventDestroy(e);
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);
