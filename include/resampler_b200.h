@@ -64,9 +64,21 @@ enum rsb_memspace { RSB_MEM_DEVICE = 0, /* pointers are device pointers on the h
  *   FAST : interpolates the two phase rows once per output frame and reuses the row for
  *          every stream/channel of the tile; samples within 1e-6 absolute of EXACT.
  *   TENSOR: the same product on the tcgen05 tensor cores with every operand split into two
- *          TF32 parts (3xTF32, fp32 accumulation in tensor memory); samples within 1e-6
- *          absolute of EXACT.  Serves batches whose streams share one plan and whose inputs
- *          lie at one constant stride (1, 2, 4 or 8 channels); other batches fall back to FAST / EXACT.
+ *          fp16 parts after a power-of-two prescale (three fp16 products per tap, fp32
+ *          accumulation in tensor memory); samples within 1e-6 absolute of EXACT (measured
+ *          <= 6e-7 on full-scale noise).  Serves batches whose streams share one plan and whose
+ *          inputs and outputs lie at one constant stride (1, 2, 4 or 8 channels); other batches
+ *          fall back to FAST / EXACT.
+ *
+ * Non-finite and out-of-range samples.  EXACT follows IEEE arithmetic sample by sample like the
+ * reference: the same outputs become Inf / NaN, all others are bit-identical.  TENSOR and FAST
+ * multiply whole tiles (64 / 32 output frames x their input window) with zero-padded filter
+ * rows: an Inf / NaN input sample -- and for TENSOR any sample with |x| >= 4094, the fp16 range
+ * after its 2^4 prescale -- makes every output of the tiles whose input range contains it
+ * unspecified (typically NaN) for that stream AND channel; other channels, other streams and
+ * outputs further than one tile plus one filter length away are not affected.  Select
+ * RSB_KERNEL_EXACT for material that may contain such samples
+ * (tests/test_gpu_tensor_margin.py::test_non_finite_and_out_of_range_samples_contract).
  *   AUTO : TENSOR where it applies (one plan, constant stride, >= 64 stream-channels), else
  *          FAST where it applies (stream count, ratio), else EXACT. */
 enum rsb_kernel { RSB_KERNEL_AUTO = 0, RSB_KERNEL_EXACT = 1, RSB_KERNEL_FAST = 2,
