@@ -160,6 +160,22 @@ struct rsb_fir {
     } tc2_key;
     DevBuf d_tct2, d_gmat2;          // 64-output tile records, fp16 G store (+ MMA lists) of tc2_key
     uint64_t tc2_cache_hits = 0;
+    // fused single-launch submits (fir_submit.cu): two slots so that one can be filled while the
+    // previous submit still runs; results are delivered when a slot is reused or at sync
+    struct FusedSlot {
+        PinBuf h_jobs, h_res;
+        DevBuf d_jobs, d_res;
+        cudaEvent_t ev_done = nullptr;
+        bool active = false;
+        uint32_t n = 0;
+        uint64_t seq = 0;
+        std::vector<uint32_t> streams;
+        size_t *consumed = nullptr, *produced = nullptr;
+    } fused[2];
+    uint64_t fused_count = 0;
+    std::vector<uint32_t> seen_epoch;   // duplicate-stream check without clearing an array per submit
+    uint32_t epoch = 0;
+    std::vector<uint64_t> m_fused_seq;  // fused submit whose result will refresh a stream's mirror
     Workspace ws[2];
     uint64_t submits = 0;             // ws[submits & 1] is the next one to use
     DevBuf d_stage_in, d_stage_out, d_dbg;   // host-memspace staging (those calls are synchronous)
@@ -283,6 +299,8 @@ void plan_unit_host(UnitDev &U, rsb::PlanState s, double ratio, uint32_t taps, r
 // batches with at most this many plan units are planned on the host
 constexpr uint32_t kHostPlanMaxUnits = 8;
 
+int finalize_fused_all(rsb_fir *h);
+
 int finalize_pending(rsb_fir *h, Workspace &W) {
     if (!W.pending.active) return RSB_OK;
     Pending p = W.pending;
@@ -328,6 +346,10 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
               uint32_t flags, size_t *consumed, size_t *produced, uint32_t *n_calls_out,
               const PcmSpec *pcm = nullptr) {
     RSB_CUDA(cudaSetDevice(h->device));
+    {   // fused submits in flight: their read-back makes the host mirror valid again
+        const int rf = finalize_fused_all(h);
+        if (rf != RSB_OK) return rf;
+    }
     Workspace &W = h->ws[h->submits & 1];
     // this workspace was last used two submits ago: collect its counts, wait for its kernels
     int rc = finalize_pending(h, W);
@@ -941,6 +963,107 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
     return rc;
 }
 
+// Delivers the results of a fused submit: counts to the caller's arrays, scalar state to the host
+// mirror (unless a later submit has taken the stream on).
+int finalize_fused(rsb_fir *h, rsb_fir::FusedSlot &F) {
+    if (!F.active) return RSB_OK;
+    F.active = false;
+    RSB_CUDA(cudaEventSynchronize(F.ev_done));
+    const rsb::SubmitResult *res = F.h_res.as<rsb::SubmitResult>();
+    const uint32_t ch = h->channels;
+    int rc = RSB_OK;
+    for (uint32_t i = 0; i < F.n; ++i) {
+        const uint32_t s = F.streams[i];
+        if (res[i].status != 0) rc = fail(RSB_ERR_PLAN_OVERFLOW, "plan workspace bound exceeded (fused submit)");
+        if (F.consumed) F.consumed[i] = (size_t)res[i].copied * ch;
+        if (F.produced) F.produced[i] = (size_t)res[i].produced * ch;
+        if (h->m_fused_seq[s] == F.seq && !h->m_ok[s]) {
+            h->m_pos[s] = res[i].position;
+            h->m_avail[s] = res[i].available;
+            h->m_ok[s] = 1;
+        }
+    }
+    return rc;
+}
+
+int finalize_fused_all(rsb_fir *h) {
+    int rc = finalize_fused(h, h->fused[h->fused_count & 1]);      // older first
+    int rc2 = finalize_fused(h, h->fused[(h->fused_count + 1) & 1]);
+    return rc != RSB_OK ? rc : rc2;
+}
+
+// One launch for the whole submit (device memspace): see fir_submit.cu.
+int run_submit_fused(rsb_fir *h, uint32_t n, const uint32_t *streams, const float *const *in,
+                     const size_t *in_lens, float *const *out, const size_t *out_lens, size_t *consumed,
+                     size_t *produced, uint32_t flags) {
+    RSB_CUDA(cudaSetDevice(h->device));
+    rsb_fir::FusedSlot &F = h->fused[h->fused_count & 1];
+    int rc = finalize_fused(h, F);
+    if (rc != RSB_OK) return rc;
+    // GPU-planned batches of the general path may still owe these streams a mirror refresh; their
+    // kernels run on the same streams in order, nothing to wait for here
+    const uint32_t ch = h->channels;
+    if (!F.ev_done) RSB_CUDA(cudaEventCreateWithFlags(&F.ev_done, cudaEventDisableTiming));
+    RSB_CUDA(F.h_jobs.reserve(sizeof(rsb::SubmitJob) * n));
+    RSB_CUDA(F.h_res.reserve(sizeof(rsb::SubmitResult) * n));
+    RSB_CUDA(F.d_jobs.reserve(sizeof(rsb::SubmitJob) * n));
+    RSB_CUDA(F.d_res.reserve(sizeof(rsb::SubmitResult) * n));
+    rsb::SubmitJob *hj = F.h_jobs.as<rsb::SubmitJob>();
+    F.streams.resize(n);
+    const size_t hist_stride = (size_t)rsb::kHistFrames * ch;
+    const uint64_t seq = ++h->fused_count;         // slot index of THIS submit was taken above
+    // all jobs of one cohort with one call signature keep sharing a cohort afterwards
+    bool same = true;
+    const uint32_t s0 = streams ? streams[0] : 0u;
+    const uint64_t c0 = h->cohort[s0];
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t s = streams ? streams[i] : i;
+        rsb::SubmitJob J;
+        J.in = in[i];
+        J.out = out[i];
+        const uint32_t sel = h->hist_sel[s];
+        J.hist = h->st.hist[sel] + hist_stride * s;
+        J.hist_next = h->st.hist[sel ^ 1u] + hist_stride * s;
+        J.in_frames = (uint32_t)std::min<uint64_t>(in_lens[i] / ch, rsb::kInputCapacity);   // :526-528
+        J.cap_frames = (uint32_t)std::min<uint64_t>(out_lens[i] / ch, 0xffffffffull);
+        J.stream = s;
+        J.pad = 0;
+        hj[i] = J;
+        F.streams[i] = s;
+        same = same && h->cohort[s] == c0 && J.in_frames == hj[0].in_frames && J.cap_frames == hj[0].cap_frames;
+    }
+    const uint64_t shared = h->next_cohort;
+    if (same) h->next_cohort += 1;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t s = F.streams[i];
+        h->cohort[s] = same ? shared : h->next_cohort++;
+        h->hist_sel[s] ^= 1u;
+        h->m_ok[s] = 0;
+        h->m_fused_seq[s] = seq;
+        h->m_pending[s] = ~0ull;      // no general-path read-back may refresh this stream any more
+    }
+    cudaStream_t s = h->stream, sp = h->plan_stream;
+    // the streams' scalar state is otherwise touched on the plan stream: order the two
+    RSB_CUDA(cudaEventRecord(h->ev_sync, sp));
+    RSB_CUDA(cudaStreamWaitEvent(s, h->ev_sync, 0));
+    RSB_CUDA(cudaMemcpyAsync(F.d_jobs.p, hj, sizeof(rsb::SubmitJob) * n, cudaMemcpyHostToDevice, s));
+    rsb::launch_submit_fused(F.d_jobs.as<rsb::SubmitJob>(), F.d_res.as<rsb::SubmitResult>(), n, h->st,
+                             h->d_coeffs, h->ratio, h->taps, ch, s);
+    RSB_CUDA(cudaGetLastError());
+    RSB_CUDA(cudaMemcpyAsync(F.h_res.p, F.d_res.p, sizeof(rsb::SubmitResult) * n, cudaMemcpyDeviceToHost, s));
+    RSB_CUDA(cudaEventRecord(F.ev_done, s));
+    RSB_CUDA(cudaStreamWaitEvent(sp, F.ev_done, 0));
+    h->launches += 1;
+    h->last_kernel = RSB_KERNEL_EXACT;
+    F.active = true;
+    F.n = n;
+    F.seq = seq;
+    F.consumed = consumed;
+    F.produced = produced;
+    if (flags & RSB_FLAG_ASYNC) return RSB_OK;
+    return finalize_fused(h, F);
+}
+
 int check_handle(const rsb_fir *h) {
     if (!h) return fail(RSB_ERR_INVALID_ARGUMENT, "null handle");
     return RSB_OK;
@@ -1026,6 +1149,8 @@ int rsb_fir_create(rsb_fir **out, int device, uint32_t n_streams, uint32_t chann
     h->m_avail.assign(n_streams, 0u);
     h->m_ok.assign(n_streams, 1);
     h->m_pending.assign(n_streams, 0);
+    h->m_fused_seq.assign(n_streams, 0);
+    h->seen_epoch.assign(n_streams, 0);
 
     RSB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     RSB_CUDA(cudaStreamCreateWithFlags(&h->plan_stream, cudaStreamNonBlocking));
@@ -1081,6 +1206,10 @@ void rsb_fir_destroy(rsb_fir *h) {
     }
     for (DevBuf *b : {&h->d_stage_in, &h->d_stage_out, &h->d_dbg, &h->d_pcm_raw, &h->d_zero, &h->d_tct2, &h->d_gmat2})
         b->release();
+    for (auto &F : h->fused) {
+        F.h_jobs.release(); F.h_res.release(); F.d_jobs.release(); F.d_res.release();
+        if (F.ev_done) cudaEventDestroy(F.ev_done);
+    }
     for (cudaEvent_t e : h->ev_pcm) if (e) cudaEventDestroy(e);
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);
     if (h->ev_t1) cudaEventDestroy(h->ev_t1);
@@ -1184,6 +1313,29 @@ int rsb_fir_submit_batch(rsb_fir *h, uint32_t n, const uint32_t *streams, const 
             return fail(RSB_ERR_INVALID_OUTPUT_BUFFER_SIZE, "output length of job " +
                                                                 std::to_string(i) +
                                                                 " is not a multiple of channels");
+    }
+    // Small device-resident submits take the single-launch path (fir_submit.cu): plan, samples in
+    // the reference's order and state update in one kernel, per-stream call sizes welcome.  Large
+    // ones (tens of millions of samples) are better served by the tile kernels below.
+    if (memspace == RSB_MEM_DEVICE && !(flags & (RSB_FLAG_RECORD_CALLS | RSB_FLAG_KEEP_PLAN)) &&
+        (h->kernel_mode == RSB_KERNEL_AUTO || h->kernel_mode == RSB_KERNEL_EXACT) && !getenv("RSB_NO_FUSED_SUBMIT")) {
+        h->epoch += 1;
+        if (h->epoch == 0) { std::fill(h->seen_epoch.begin(), h->seen_epoch.end(), 0u); h->epoch = 1; }
+        uint64_t est = 0;
+        bool ok = true;
+        for (uint32_t i = 0; i < n && ok; ++i) {
+            const uint32_t s = streams ? streams[i] : i;
+            if (s >= h->n_streams) return fail(RSB_ERR_INVALID_ARGUMENT, "bad stream index");
+            if (h->seen_epoch[s] == h->epoch) return fail(RSB_ERR_INVALID_ARGUMENT, "stream listed twice in one batch");
+            h->seen_epoch[s] = h->epoch;
+            if (in_lens[i] && !in[i]) return fail(RSB_ERR_INVALID_ARGUMENT, "null input pointer");
+            if (out_lens[i] && !out[i]) return fail(RSB_ERR_INVALID_ARGUMENT, "null output pointer");
+            const uint64_t frames = std::min<uint64_t>(in_lens[i] / ch, rsb::kInputCapacity);
+            est += std::min<uint64_t>((uint64_t)((double)(frames + rsb::kInputCapacity / 8) / h->ratio) + 2, out_lens[i] / ch) * ch;
+        }
+        // AUTO: the tile kernels win once a submit carries tens of millions of samples
+        if (h->kernel_mode == RSB_KERNEL_EXACT || est <= (32ull << 20))
+            return run_submit_fused(h, n, streams, in, in_lens, out, out_lens, consumed, produced, flags);
     }
     std::vector<JobHost> jobs(n);
     std::vector<uint8_t> seen(h->n_streams, 0);
@@ -1342,6 +1494,8 @@ int rsb_fir_sync(rsb_fir *h) {
     if (check_handle(h)) return RSB_ERR_INVALID_ARGUMENT;
     RSB_CUDA(cudaSetDevice(h->device));
     int rc = finalize_all(h);
+    const int rf = finalize_fused_all(h);
+    if (rc == RSB_OK) rc = rf;
     RSB_CUDA(cudaStreamSynchronize(h->plan_stream));
     RSB_CUDA(cudaStreamSynchronize(h->stream));
     return rc;

@@ -181,4 +181,26 @@ void tc2_phase_profile(int enable, unsigned long long *out, uint32_t count);
 // watchdog record of a tensor-kernel launch that trapped on a stuck mbarrier wait (zeros: none); clears it
 void tc2_hang_record(unsigned int out[32]);
 
+// ---- fused single-launch submit (fir_submit.cu): one resample() call per listed stream ----
+struct SubmitJob {
+    const float *in;          // interleaved new input (device)
+    float *out;               // interleaved output (device)
+    const float *hist;        // the stream's live history buffer
+    float *hist_next;         // the other one (written)
+    uint32_t in_frames;       // frames offered (<= kInputCapacity)
+    uint32_t cap_frames;      // output capacity, frames
+    uint32_t stream;
+    uint32_t pad;
+};
+struct SubmitResult {
+    double position;          // state after the call
+    uint32_t copied;          // frames ("consumed", :617-620)
+    uint32_t produced;        // frames
+    uint32_t available;
+    uint32_t status;          // 0 ok, 1 plan segment overflow
+};
+void launch_submit_fused(const SubmitJob *jobs, SubmitResult *results, uint32_t n_jobs, StreamStateDev st,
+                         const float *coeffs, double ratio, uint32_t taps, uint32_t channels,
+                         cudaStream_t stream);
+
 }  // namespace rsb

@@ -521,3 +521,48 @@ def test_cuda_path_matches_committed_fixtures():
         for key in ("input_offset", "phase1", "phase2", "frac_bits"):
             assert np.array_equal(plan[key], z[f"{name}/{key}"]), (name, key)
         batch.close()
+
+
+def test_fused_submit_divergent_streams_bit_exact_and_handoff():
+    """The single-launch submit path (fir_submit.cu, device memspace): per-stream pseudo-random call
+    sizes (BASELINE configs[2] variant (ii)) -> every stream has its own plan.  Counts and samples
+    bit-identical to the oracle on every call; afterwards a big batch on the same handle (the tile
+    kernels, host-side plan from the refreshed mirror) carries on from the right state."""
+    from resampler_b200.fir import MEM_DEVICE, DeviceBuffer
+    n, ch, in_hz, out_hz, lat = 96, 1, 16000, 48000, 1
+    sizes = [0, 1, 7, 16, 33, 160, 480]
+    rng = np.random.default_rng(2)
+    batch = FirBatch(n, ch, in_hz, out_hz, Latency(lat), Attenuation.Db90, kernel=Kernel.AUTO)
+    refs = [O.OracleFir(ch, in_hz, out_hz, lat, 1) for _ in range(n)]
+    bso = batch.buffer_size_output()
+    d_in = DeviceBuffer(0, n * 480 * ch)
+    d_out = DeviceBuffer(0, n * bso)
+    for it in range(25):
+        if it < 3:
+            sz = [160] * n                      # a shared cohort first
+        else:
+            sz = [int(rng.choice(sizes)) for _ in range(n)]
+        ins = [noise(rng, s * ch) for s in sz]
+        for s in range(n):
+            if sz[s]:
+                d_in.upload(ins[s], s * 480 * ch)
+        cons, prod = batch.submit_ptrs([d_in.ptr + 4 * s * 480 * ch for s in range(n)], [x.size for x in ins],
+                                       [d_out.ptr + 4 * s * bso for s in range(n)], [bso] * n,
+                                       memspace=MEM_DEVICE)
+        assert batch.last_kernel() == Kernel.EXACT
+        for s in range(n):
+            o = np.zeros(bso, np.float32)
+            _, c, p = refs[s].resample(ins[s], o)
+            assert (cons[s], prod[s]) == (c, p), (it, s)
+            if p:
+                assert np.array_equal(bits(d_out.download(p, s * bso)), bits(o[:p])), (it, s)
+    # hand-off to the batch path: the same continuation for every stream, 3000 frames
+    tail = [noise(rng, 3000 * ch) for _ in range(n)]
+    res = batch.process(tail, 160 * ch)
+    for s in range(0, n, 7):
+        ref = refs[s].process(tail[s], 160 * ch)
+        assert res["produced"][s] == len(ref["out"]), s
+        assert np.max(np.abs(res["out"][s].astype(np.float64) - ref["out"])) <= TOL_FAST, s
+    batch.close()
+    d_in.free()
+    d_out.free()
