@@ -870,6 +870,9 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
         T.prefetch_chunks = getenv("RSB_TC_PREFETCH") ? (uint32_t)atoi(getenv("RSB_TC_PREFETCH")) : 0u;
         T.ablate = getenv("RSB_TC_ABLATE") ? (uint32_t)atoi(getenv("RSB_TC_ABLATE")) : 0u;
         T.out_scale = rsb::tc2_out_scale();
+        T.epi_split = getenv("RSB_TC_EPI_SPLIT") ? (uint32_t)atoi(getenv("RSB_TC_EPI_SPLIT")) : 0u;
+        T.hint_crit = getenv("RSB_TC_HINT_CRIT") ? (uint32_t)atoi(getenv("RSB_TC_HINT_CRIT")) : 0x989680u;
+        T.hint_other = getenv("RSB_TC_HINT_OTHER") ? (uint32_t)atoi(getenv("RSB_TC_HINT_OTHER")) : 0x989680u;
         if (getenv("RSB_TC_GSTAGES")) T.g_stages = std::min<uint32_t>(T.g_stages, (uint32_t)atoi(getenv("RSB_TC_GSTAGES")));
         T.raw16 = pcm_fused ? pcm_raw_mode : 0u;
         T.raw_bytes = pcm && pcm_fused ? pcm->bps : 2u;

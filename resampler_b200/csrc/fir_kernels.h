@@ -151,6 +151,9 @@ struct Tc2Params {
     uint32_t ablate;          // debug (RSB_TC_ABLATE): 1 no G copies, 2 no input TMA, 4 no output stores,
                               // 8 splitter: handshakes only, 16 epilogue: handshakes only, 32 one MMA per tile
     float out_scale;          // epilogue factor 2^-17 (undoes the operand prescale)
+    uint32_t epi_split;       // two epilogue teams: 1 = each drains one column half of every tile, 0 = alternate tiles
+    uint32_t hint_crit;       // try_wait suspend-time hint (ns) of the issuers' and the epilogue's waits
+    uint32_t hint_other;      // ... of every other role's waits
 };
 // Expected relative loss (in units of 2^-24) of the tensor core's truncating fp32 accumulation with the
 // kernel's issue order, measured on B200 against an f64 evaluation for full-scale noise:

@@ -57,8 +57,9 @@ namespace rsb {
 // splitter wg 0: [5] wait x_empty [6] wait xs_full [7] loads + split [11] wait::st + arrive
 // [12] tcgen05.st [15] loop overhead; epilogue warp 0: [8] wait t_done [9] tcgen05.ld + staging
 // [10] TMA store issue + waits; [13] kernel cycles of CTA 0; [14] tiles of CTA 0;
-// janitor: [16] wait t_done [17] releases; G producer: [18] wait t_done [19] issue.
-__device__ unsigned long long g_tc2_cycles[24];
+// janitor: [16] wait t_done [17] releases; G producer: [18] wait t_done [19] issue;
+// input producer: [23] wait item slot [24] item set-up [25] wait xs_empty [26] TMA issue.
+__device__ unsigned long long g_tc2_cycles[32];
 __device__ int g_tc2_prof = 0;
 // Watchdog of the kernel's mbarrier waits: a wait that has not completed after ~2 s records
 // {tag, block, warp, parity | barrier address << 8} in a host-mapped buffer and traps (the launch
@@ -77,7 +78,8 @@ enum : uint32_t { kWItemFull = 1, kWItemEmpty, kWXsEmpty, kWXsFull, kWGDone, kWJ
 // instructions per tile, 0.5 IPC per scheduler = the whole tile time).  The warp still wakes up as
 // soon as the phase completes.
 constexpr uint32_t kSuspendHint = 0x989680u;
-__device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity) {
+__constant__ uint32_t g_tc2_hint[2] = {kSuspendHint, kSuspendHint};   // [critical roles, others]
+__device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity, uint32_t hint = kSuspendHint) {
     uint32_t ok;
     asm volatile(
         "{\n\t"
@@ -86,16 +88,21 @@ __device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n\t"
         "}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(kSuspendHint)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint)
         : "memory");
     return ok != 0;
 }
 // Cold path of a wait (kept out of line: the hot loops stay small).  With the watchdog enabled
 // (debug, RSB_TC_WATCHDOG=1) a wait that has not completed after ~2 s records itself and traps.
+__device__ __forceinline__ uint32_t wait_hint(uint32_t tag) {
+    const bool crit = tag == kWDEmpty || tag == kWGFull || tag == kWXFull || tag == kWEpiDone;
+    return g_tc2_hint[crit ? 0 : 1];
+}
 __device__ __noinline__ void mbar_wait_slow(uint64_t *bar, uint32_t parity, uint32_t tag) {
     unsigned int *rec = g_tc2_hang;
     if (!g_tc2_watchdog || rec == nullptr) {
-        mbar_wait(bar, parity);
+        const uint32_t hint = wait_hint(tag);
+        while (!mbar_try(bar, parity, hint)) { }
         return;
     }
     const long long t0 = clock64();
@@ -119,7 +126,7 @@ __device__ __noinline__ void mbar_wait_slow(uint64_t *bar, uint32_t parity, uint
     }
 }
 __device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, uint32_t tag) {
-    if (mbar_try(bar, parity)) return;       // try_wait's already-complete path is the cheapest test
+    if (mbar_try(bar, parity, wait_hint(tag))) return;   // try_wait's already-complete path is the cheapest test
     mbar_wait_slow(bar, parity, tag);
 }
 
@@ -481,7 +488,8 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
         for (uint32_t i = 0; i < kMaxGStages; ++i) mbar_init(&S.g_full[i], 1);
         for (uint32_t i = 0; i < kDone; ++i) mbar_init(&S.t_done[i], 1);
         for (uint32_t i = 0; i < kSlots; ++i) { mbar_init(&S.x_full[i], 4); mbar_init(&S.x_empty[i], 1); }
-        for (uint32_t i = 0; i < 2; ++i) mbar_init(&S.d_empty[i], 5);    // 4 epilogue warps + janitor
+        // every epilogue warp that drains the accumulator + janitor
+        for (uint32_t i = 0; i < 2; ++i) mbar_init(&S.d_empty[i], kEpiTeams == 2 && P.epi_split ? 9 : 5);
         for (uint32_t i = 0; i < kItemSlots; ++i) {
             mbar_init(&S.item_full[i], 1);
             mbar_init(&S.item_empty[i], kItemConsumers);
@@ -517,9 +525,11 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
         // ===== scheduler + TMA producer of the input chunks =====
         if (lane == 0) {
             uint32_t xs_seq = 0;
+            rc.start(prof);
             for (uint32_t it = 0;; ++it) {
                 const uint32_t slot = it % kItemSlots;
                 mbar_wait_wd(&S.item_empty[slot], ((it / kItemSlots) & 1u) ^ 1u, kWItemEmpty);
+                rc.lap(23);
                 const uint32_t idx = atomicAdd(P.work_counter, 1u);
                 Item I;
                 I.valid = idx < n_items ? 1u : 0u;
@@ -544,26 +554,29 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
                 // inner coordinate in tensor-map elements: frames (mono f32, stereo 8-byte frames,
                 // raw frames), bytes (packed s24) or floats (4 / 8 channels)
                 constexpr int32_t kCoordMul = (int32_t)(SB == 3 ? kRawFrameBytes : CH >= 4 ? CH : 1);
-                const uint32_t pf = P.prefetch_chunks;
+                const uint32_t pf = P.prefetch_chunks;      // 0: no L2 prefetch
                 for (uint32_t j = 0; j < min(pf, I.n_chunks); ++j) {
                     const int32_t v = I.vb + (int32_t)(j * kChunk);
                     if (v >= H) tensor_prefetch_2d(&tmap_in, (v - H) * kCoordMul, m0);
                 }
+                rc.lap(24);
                 for (uint32_t j = 0; j < I.n_chunks; ++j) {
                     const int32_t v = I.vb + (int32_t)(j * kChunk);
-                    if (j + pf < I.n_chunks) {
+                    if (pf != 0 && j + pf < I.n_chunks) {
                         const int32_t vp = v + (int32_t)(pf * kChunk);
                         if (vp >= H) tensor_prefetch_2d(&tmap_in, (vp - H) * kCoordMul, m0);
                     }
                     if (v < H) continue;       // touches the history: the splitter loads it itself
                     const uint32_t s = xs_seq % kXStages;
                     mbar_wait_wd(&S.xs_empty[s], ((xs_seq / kXStages) & 1u) ^ 1u, kWXsEmpty);
+                    rc.lap(25);
                     if (P.ablate & 2u) {
                         mbar_arrive(&S.xs_full[s]);
                     } else {
                         mbar_arrive_expect_tx(&S.xs_full[s], kXLandBytes);
                         tensor_g2s_2d(xst + s * kXStageBytes, &tmap_in, (v - H) * kCoordMul, m0, &S.xs_full[s]);
                     }
+                    rc.lap(26);
                     ++xs_seq;
                 }
             }
@@ -869,7 +882,12 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
         // ===== epilogue: accumulator (TMEM) -> scale -> swizzled staging -> TMA tensor stores.
         // A warp owns the 32 accumulator lanes of its quadrant = kMpw members and stores their
         // boxes itself (no barrier wider than a warp). =====
-        const uint32_t team = warp >= kWarpEpi1 ? 1u : 0u;   // drains the tiles with d_seq % kEpiTeams == team
+        // Two teams: team h drains column half h of EVERY tile, so an accumulator is back with the
+        // issuers one tcgen05.ld after its tile completes (alternating whole tiles between the teams
+        // held it through the first half's staging and stores: the accumulator turnaround was the
+        // kernel's critical loop).  One team: both halves in turn.
+        const uint32_t team = warp >= kWarpEpi1 ? 1u : 0u;
+        const bool epi_split = kEpiTeams == 2 && P.epi_split != 0;
         const uint32_t quad = warp & 3u;
         const uint32_t ml = lane / CH, c = lane % CH;       // member inside the warp, channel
         const uint32_t lane_base = (quad * 32u) << 16;
@@ -883,7 +901,7 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
             if (!I.valid) break;
             const int32_t m_first = (int32_t)(I.group * kMpg + quad * kMpw);
             for (uint32_t t = I.t0; t < I.t1; ++t, ++d_seq) {
-                if (kEpiTeams == 2 && (d_seq & 1u) != team) continue;
+                if (kEpiTeams == 2 && !epi_split && (d_seq & 1u) != team) continue;
                 const uint32_t o_start = t * kN;
                 const uint32_t b = d_seq & 1u;
                 rc.lap(10);
@@ -898,11 +916,11 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
                     continue;
                 }
 #pragma unroll 1
-                for (uint32_t hf = 0; hf < 2; ++hf) {
+                for (uint32_t hf = (epi_split ? team : 0u); hf < (epi_split ? team + 1u : 2u); ++hf) {
                     uint32_t acc[32];
                     tmem_ld32(tmem + lane_base + kColD + b * kN + hf * 32u, acc);
                     tmem_wait_ld();
-                    if (hf == 1) {      // the accumulator is drained: hand it back to the issuers
+                    if (epi_split || hf == 1) {   // this warp's part is drained: hand it back to the issuers
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&S.d_empty[b]);
@@ -1235,6 +1253,15 @@ bool launch_conv_tc2(const Tc2Params &p, const CUtensorMap &tmap_in, const CUten
         kern<<<grid, threads, smem, stream>>>(p, tmap_in, tmap_out);
     };
     const uint32_t thr = role_threads(V.st, V.et);
+    {
+        static uint32_t cur[2] = {kSuspendHint, kSuspendHint};
+        const uint32_t want[2] = {p.hint_crit, p.hint_other};
+        if (want[0] != cur[0] || want[1] != cur[1]) {
+            cudaMemcpyToSymbolAsync(g_tc2_hint, want, sizeof(want), 0, cudaMemcpyHostToDevice, stream);
+            cur[0] = want[0];
+            cur[1] = want[1];
+        }
+    }
     if (variant != 0) {
         // experiment variants: stereo f32 only
         if (p.channels != 2 || p.raw16) return false;
@@ -1288,10 +1315,10 @@ static void ensure_hang_buffer() {
 }
 
 void tc2_phase_profile(int enable, unsigned long long *out, uint32_t count) {
-    unsigned long long tmp[24];
+    unsigned long long tmp[32];
     cudaMemcpyFromSymbol(tmp, g_tc2_cycles, sizeof(tmp));
-    if (out) std::memcpy(out, tmp, sizeof(unsigned long long) * (count < 24u ? count : 24u));
-    unsigned long long zero[24] = {0};
+    if (out) std::memcpy(out, tmp, sizeof(unsigned long long) * (count < 32u ? count : 32u));
+    unsigned long long zero[32] = {0};
     cudaMemcpyToSymbol(g_tc2_cycles, zero, sizeof(zero));
     cudaMemcpyToSymbol(g_tc2_prof, &enable, sizeof(int));
 }
