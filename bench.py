@@ -52,8 +52,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-legs", action="store_true", help="skip the short legs of the other configs")
-    ap.add_argument("--e2e-slice-seconds", type=float, default=2.0)
-    ap.add_argument("--e2e-threads", type=int, default=4)
+    ap.add_argument("--e2e-slice-seconds", type=float, default=15.0,
+                    help="audio seconds per host-memspace call of the e2e leg (pinned buffer size)")
     return ap.parse_args()
 
 
@@ -371,6 +371,8 @@ def run_ours(args):
     from resampler_b200 import _lib
     import ctypes as C
 
+    all_cpus = os.sched_getaffinity(0)
+    numa = numa_affinity(int(os.environ.get("LOCAL_RANK", "0")))     # before the CUDA context exists
     rank, world, local, dist = dist_setup(args.gpus)
     lib = _lib.load()
     kern = {"auto": Kernel.AUTO, "exact": Kernel.EXACT, "fast": Kernel.FAST,
@@ -439,6 +441,8 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(args, batch, lib, frames, n_streams, local, dist)
+        e2e["host_affinity"] = numa
+    os.sched_setaffinity(0, all_cpus)        # the CPU baseline below uses every core
 
     # ---- CPU baseline beside it (rank 0, N == 1 only) ----
     cpu = None
@@ -508,59 +512,85 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def numa_affinity(local):
+    """Pins this process to the host cores of the GPU's NUMA node (before any pinned allocation, so
+    that the staging memory is node-local).  Returns what was done, for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.lower().split(":", 1)
+        node = int(Path(f"/sys/bus/pci/devices/{dom[-4:]}:{rest}/numa_node").read_text())
+        if node < 0:
+            return {"numa_node": node, "pinned": False}
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "pinned": bool(cpus), "cpus": len(cpus)}
+    except Exception as e:
+        return {"numa_node": None, "pinned": False, "why": str(e)[:80]}
+
+
+def pcie_ceiling(lib, local, dist):
+    """Plain pinned cudaMemcpyAsync rates of this GPU's link (all ranks probe at the same time, so
+    at N > 1 these are the contended rates)."""
+    import ctypes as C
+    out = (C.c_double * 2)()
+    res = {}
+    for mode, name in ((0, "h2d_alone"), (1, "d2h_alone"), (2, "duplex")):
+        barrier(dist, local)
+        if lib.rsb_pcie_probe(local, 512 << 20, 6, mode, out) != 0:
+            return None
+        if mode == 2:
+            res["h2d_duplex"], res["d2h_duplex"] = round(out[0], 2), round(out[1], 2)
+        else:
+            res[name] = round(out[mode], 2)
+    return res
+
+
 def run_e2e(args, batch, lib, frames, n_streams, local, dist):
     """Same workload through rsb_fir_process_batch with HOST (pinned) buffers: every step copies
-    the step's inputs host->device and the results device->host inside the timed region.  The
-    60 s are fed as time slices that reuse one pinned slice buffer (the state carries over).
-    The streams are split over a few host threads, each driving its own handle (own CUDA
-    streams), so one share's copies overlap another share's kernels -- the same structure a
-    multi-threaded host application would use (a handle is single-threaded like the
-    reference's `&mut self`)."""
+    the step's inputs host->device and the results device->host inside the timed region.  One
+    handle, one host thread: the library cuts each call into time slices and overlaps the H2D copy
+    of slice k+1, the kernels of slice k and the D2H copy of slice k-1 itself.  The 60 s are fed
+    as a few calls that reuse one pinned buffer (the state carries over from call to call)."""
     import ctypes as C
     from resampler_b200 import Attenuation, FirBatch, Latency
-    from resampler_b200.fir import MEM_HOST
-    n_workers = max(1, min(args.e2e_threads, n_streams))
-    slice_frames = int(round(args.e2e_slice_seconds * IN_HZ))
-    slice_frames -= slice_frames % CALL_FRAMES          # whole calls per slice
-    n_slices = max(1, frames // slice_frames)
-    in_vals = slice_frames * CHANNELS
+    from resampler_b200.fir import FLAG_ASYNC, MEM_HOST
+    call_seconds = args.e2e_slice_seconds
+    part_frames = int(round(call_seconds * IN_HZ))
+    part_frames -= part_frames % CALL_FRAMES          # whole calls per part
+    part_frames = max(CALL_FRAMES, min(part_frames, frames - frames % CALL_FRAMES))
+    n_parts = max(1, frames // part_frames)
+    in_vals = part_frames * CHANNELS
     ratio = batch.ratio()
-    out_vals = (int(slice_frames / ratio) + 4400) * CHANNELS
+    out_vals = (int(part_frames / ratio) + 4400) * CHANNELS
+    pcie = pcie_ceiling(lib, local, dist)
     h_in = lib.rsb_alloc_pinned(n_streams * in_vals * 4)
     h_out = lib.rsb_alloc_pinned(n_streams * out_vals * 4)
     if not h_in or not h_out:
         return {"value": None, "unit": "Msamples/s", "error": "pinned allocation failed"}
     src = np.ctypeslib.as_array(C.cast(h_in, C.POINTER(C.c_float)), shape=(n_streams, in_vals))
-    src[:] = host_synthetic(1, slice_frames)[0][None, :]
-    bounds = [n_streams * w // n_workers for w in range(n_workers + 1)]
-    workers = []
-    for w in range(n_workers):
-        lo, hi = bounds[w], bounds[w + 1]
-        fb = FirBatch(hi - lo, CHANNELS, IN_HZ, OUT_HZ, Latency(LATENCY), Attenuation(ATTENUATION),
-                      device=local)
-        workers.append((fb, [h_in + 4 * s * in_vals for s in range(lo, hi)],
-                        [h_out + 4 * s * out_vals for s in range(lo, hi)], hi - lo))
-    produced = [0] * n_workers
+    src[:] = host_synthetic(1, part_frames)[0][None, :]
+    fb = FirBatch(n_streams, CHANNELS, IN_HZ, OUT_HZ, Latency(LATENCY), Attenuation(ATTENUATION), device=local)
+    in_ptrs = [h_in + 4 * s * in_vals for s in range(n_streams)]
+    out_ptrs = [h_out + 4 * s * out_vals for s in range(n_streams)]
 
-    def work(w, n_steps):
-        fb, in_ptrs, out_ptrs, cnt = workers[w]
+    def run(n_steps):
         tot = 0
         for _ in range(n_steps):
             fb.reset(-1)
-            for _ in range(n_slices):
-                _, p, _ = fb.process_ptrs(in_ptrs, [in_vals] * cnt, CALL_FRAMES * CHANNELS, 0,
-                                          out_ptrs, [out_vals] * cnt, memspace=MEM_HOST)
+            for _ in range(n_parts):
+                _, p, _ = fb.process_ptrs(in_ptrs, [in_vals] * n_streams, CALL_FRAMES * CHANNELS, 0,
+                                          out_ptrs, [out_vals] * n_streams, memspace=MEM_HOST, flags=FLAG_ASYNC)
                 tot += int(sum(p[:]))
-        fb.sync()
-        produced[w] = tot
-
-    def run(n_steps):
-        ths = [threading.Thread(target=work, args=(w, n_steps)) for w in range(n_workers)]
-        for t in ths:
-            t.start()
-        for t in ths:
-            t.join()
-        return sum(produced)
+            fb.sync()                        # the step's results are in host memory
+        return tot
 
     steps = max(1, min(args.steps, 3))
     run(1)                                   # warm-up: allocations, first touches
@@ -570,17 +600,29 @@ def run_e2e(args, batch, lib, frames, n_streams, local, dist):
     dt = time.perf_counter() - t0
     dt_max = reduce_max(dist, local, dt)
     produced_all = reduce_sum(dist, local, float(total))
-    for fb, _, _, _ in workers:
-        fb.close()
+    pipe_batches, pipe_slices = fb.host_pipeline_stats()
+    fb.close()
     lib.rsb_free_pinned(h_in)
     lib.rsb_free_pinned(h_out)
     per_step_p = total // steps
-    return {"value": round(produced_all / dt_max / 1e6, 3), "unit": "Msamples/s",
-            "h2d_bytes_per_step": int(n_slices * n_streams * in_vals * 4),
-            "d2h_bytes_per_step": int(per_step_p * 4), "steps": steps,
-            "how": f"rsb_fir_process_batch(memspace=HOST, pinned buffers), {n_slices} time slices "
-                   f"of {slice_frames / IN_HZ:.2f} s per step, {n_workers} host threads each "
-                   f"driving its own handle; wall clock around the calls, max over ranks"}
+    h2d = int(n_parts * n_streams * in_vals * 4)
+    d2h = int(per_step_p * 4)
+    res = {"value": round(produced_all / dt_max / 1e6, 3), "unit": "Msamples/s",
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps,
+           "how": f"rsb_fir_process_batch(memspace=HOST, pinned buffers), {n_parts} calls of "
+                  f"{part_frames / IN_HZ:.2f} s per step on one handle / one host thread; inside each call "
+                  f"the library pipelines {pipe_slices // max(pipe_batches, 1)} time slices "
+                  f"(H2D | kernels | D2H on three streams), calls chained with RSB_FLAG_ASYNC, rsb_fir_sync() per step; "
+                  f"wall clock around the calls, max over ranks"}
+    if pcie:
+        # per-GPU time one step's copies need at the duplex rates: the PCIe floor of a step
+        floor_s = max(h2d / (pcie["h2d_duplex"] * 1e9), d2h / (pcie["d2h_duplex"] * 1e9))
+        ceiling = per_step_p / floor_s / 1e6
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        res["pcie"] = dict(pcie, unit="GB/s per GPU (pinned cudaMemcpyAsync, all ranks at once)",
+                           ceiling_msamples_per_gpu=round(ceiling, 1),
+                           frac_of_ceiling=round(produced_all / dt_max / 1e6 / (ceiling * world), 4))
+    return res
 
 
 def main():

@@ -86,11 +86,16 @@ enum rsb_kernel { RSB_KERNEL_AUTO = 0, RSB_KERNEL_EXACT = 1, RSB_KERNEL_FAST = 2
 
 enum rsb_flags {
     RSB_FLAG_NONE = 0,
-    RSB_FLAG_ASYNC = 1,        /* device memspace only: return after enqueueing (without it a call
+    RSB_FLAG_ASYNC = 1,        /* device memspace: return after enqueueing (without it a call
                                   returns when its outputs are complete).  The count
                                   arrays are written by rsb_fir_sync() or by the second
                                   submit after this one (two submits may be in flight), so
-                                  they must stay valid until then */
+                                  they must stay valid until then.  Host memspace: honoured by
+                                  rsb_fir_process_batch calls that run as a pipeline of time
+                                  slices (pinned buffers; counts are written at once, the output
+                                  buffers are complete after rsb_fir_sync(); back-to-back calls
+                                  then overlap one call's last copies with the next one's first);
+                                  ignored (synchronous) otherwise */
     RSB_FLAG_RECORD_CALLS = 2, /* keep per-call (consumed, produced) for rsb_fir_last_call_counts */
     RSB_FLAG_KEEP_PLAN = 4     /* keep the device plan for rsb_fir_last_plan */
 };
@@ -235,6 +240,13 @@ int rsb_debug_tc_hang(uint32_t out32[32]);
 uint64_t rsb_fir_launch_count(const rsb_fir *h);
 /* the handle's cudaStream_t, as an opaque pointer */
 void *rsb_fir_cuda_stream(const rsb_fir *h);
+/* Host-memspace rsb_fir_process_batch calls that ran as a pipeline of time slices (host->device
+ * copy of slice k+1, kernels of slice k and device->host copy of slice k-1 overlapped; results
+ * identical to the unsliced loop), and the slices they were cut into. */
+int rsb_fir_host_pipeline_stats(const rsb_fir *h, uint64_t *batches, uint64_t *slices);
+/* Pinned-memory copy rates of the device's PCIe link in GB/s: mode 0 host->device alone (out[0]),
+ * 1 device->host alone (out[1]), 2 both at once.  The ceiling host-memspace calls are held against. */
+int rsb_pcie_probe(int device, size_t bytes, int iters, int mode, double out[2]);
 
 /* ---- memory helpers ---- */
 void *rsb_alloc_pinned(size_t bytes);

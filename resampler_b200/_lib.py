@@ -65,6 +65,8 @@ SIGNATURES = {
     "rsb_debug_tc_cycles": (C.c_int, [C.c_void_p, C.c_int, u64p, C.c_uint32]),
     "rsb_fir_launch_count": (C.c_uint64, [C.c_void_p]),
     "rsb_fir_cuda_stream": (C.c_void_p, [C.c_void_p]),
+    "rsb_fir_host_pipeline_stats": (C.c_int, [C.c_void_p, u64p, u64p]),
+    "rsb_pcie_probe": (C.c_int, [C.c_int, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "rsb_alloc_pinned": (C.c_void_p, [C.c_size_t]),
     "rsb_free_pinned": (None, [C.c_void_p]),
     "rsb_alloc_device": (C.c_void_p, [C.c_int, C.c_size_t]),

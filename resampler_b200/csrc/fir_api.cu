@@ -176,6 +176,15 @@ struct rsb_fir {
     std::vector<uint32_t> seen_epoch;   // duplicate-stream check without clearing an array per submit
     uint32_t epoch = 0;
     std::vector<uint64_t> m_fused_seq;  // fused submit whose result will refresh a stream's mirror
+    // host-memspace pipeline of rsb_fir_process_batch: time slices, H2D / kernels / D2H overlapped
+    struct HostPipe {
+        cudaStream_t s_in = nullptr, s_out = nullptr;
+        cudaEvent_t ev_h2d[2] = {}, ev_conv[2] = {}, ev_d2h[2] = {};
+        DevBuf d_in[2], d_out[2];
+        std::vector<rsb::CallCounts> calls;     // dry-run plan of the whole batch
+        std::vector<rsb::PlanSeg> seg_scratch;
+        uint64_t batches = 0, slices = 0;
+    } pipe;
     Workspace ws[2];
     uint64_t submits = 0;             // ws[submits & 1] is the next one to use
     DevBuf d_stage_in, d_stage_out, d_dbg;   // host-memspace staging (those calls are synchronous)
@@ -1067,6 +1076,177 @@ int run_submit_fused(rsb_fir *h, uint32_t n, const uint32_t *streams, const floa
     return finalize_fused(h, F);
 }
 
+// Host-memspace batches of one plan unit, long enough to be worth slicing: the batch is cut at call
+// boundaries into time slices, and slice k+1's host->device copy, slice k's kernels and slice
+// k-1's device->host copy run concurrently (three streams, two device buffers each way).  A dry
+// run of the (sample-independent) plan on a host core fixes the slice boundaries at cumulative
+// `copied` offsets, so every slice offers exactly the frames the unsliced loop would have consumed
+// by then: the calls, their counts and the samples are those of the unsliced batch
+// (resampler_fir.rs:509-621 called in a loop; state carries from slice to slice in the handle).
+// Returns false when the batch does not qualify (the caller then takes the unsliced path).
+bool process_host_pipelined(rsb_fir *h, const std::vector<JobHost> &jobs, size_t *consumed, size_t *produced,
+                            uint32_t *n_calls_out, bool async, int *rc_out) {
+    const uint32_t n = (uint32_t)jobs.size();
+    const uint32_t ch = h->channels;
+    const uint64_t T = jobs[0].total_frames;
+    const uint32_t cf = jobs[0].call_frames;
+    if (cf == 0 || T < 16ull * cf || (uint64_t)n * T * ch * sizeof(float) < (64ull << 20)) return false;
+    for (uint32_t i = 1; i < n; ++i)
+        if (jobs[i].total_frames != T || h->cohort[jobs[i].stream] != h->cohort[jobs[0].stream]) return false;
+    if (cudaSetDevice(h->device) != cudaSuccess) return false;
+    if (finalize_fused_all(h) != RSB_OK || finalize_all(h) != RSB_OK) return false;
+    const uint32_t rep = jobs[0].stream;
+    if (!h->m_ok[rep]) return false;
+
+    // ---- dry run of the whole plan: per-call counts ----
+    UnitDev U;
+    std::memset(&U, 0, sizeof(U));
+    U.total_frames = T;
+    U.call_frames = cf;
+    U.cap_frames = jobs[0].cap_frames;
+    const double out_bound_d = std::ceil(((double)rsb::kInputCapacity + (double)T) / h->ratio) + 2.0;
+    if (out_bound_d > 4.0e9 || T > 0x7ff00000ull) return false;
+    const uint64_t max_calls = 2 * ((T + cf - 1) / cf) + (U.cap_frames ? (uint64_t)out_bound_d / U.cap_frames : 0) + 4;
+    if (max_calls > 0x7fffffffull) return false;
+    U.max_calls = (uint32_t)max_calls;
+    U.call_cap = U.max_calls;
+    U.seg_cap = 0;      // segments are not kept (status 1 = "segment bound" is expected)
+    h->pipe.calls.resize(max_calls);
+    uint64_t tiles_dummy = 0;
+    plan_unit_host(U, rsb::PlanState{h->m_pos[rep], h->m_avail[rep]}, h->ratio, h->taps, nullptr,
+                   h->pipe.calls.data(), rsb::kTileOut, tiles_dummy);
+    if (U.n_calls >= U.max_calls || U.total_copied != T || U.n_calls < 16) return false;
+    for (uint32_t i = 0; i < n; ++i)
+        if (jobs[i].out_capacity < U.total_out) return false;     // the unsliced path reports it
+    const uint32_t n_calls = U.n_calls;
+    const rsb::CallCounts *cc = h->pipe.calls.data();
+
+    // ---- slice boundaries (calls per slice) ----
+    const uint64_t row_bytes_per_call = (uint64_t)n * cf * ch * sizeof(float);
+    const uint64_t want_slices = getenv("RSB_HOST_PIPE_SLICES") ? std::max(3, atoi(getenv("RSB_HOST_PIPE_SLICES"))) : 48;
+    uint64_t cps = (n_calls + want_slices - 1) / want_slices;
+    cps = std::max<uint64_t>(cps, 8);
+    cps = std::min<uint64_t>(cps, std::max<uint64_t>(1, (512ull << 20) / std::max<uint64_t>(row_bytes_per_call, 1)));
+    const uint32_t n_slices = (uint32_t)((n_calls + cps - 1) / cps);
+    if (n_slices < 3) return false;
+    struct Slice { uint64_t in_off, in_frames, out_off, out_frames; };
+    std::vector<Slice> sl(n_slices);
+    uint64_t in_acc = 0, out_acc = 0, max_in = 0, max_out = 0;
+    for (uint32_t k = 0, c = 0; k < n_slices; ++k) {
+        Slice S{in_acc, 0, out_acc, 0};
+        for (uint64_t j = 0; j < cps && c < n_calls; ++j, ++c) {
+            S.in_frames += cc[c].copied;
+            S.out_frames += cc[c].produced;
+        }
+        in_acc += S.in_frames;
+        out_acc += S.out_frames;
+        max_in = std::max(max_in, S.in_frames);
+        max_out = std::max(max_out, S.out_frames);
+        sl[k] = S;
+    }
+
+    auto &Pp = h->pipe;
+    auto cuda_ok = [&](cudaError_t e) {
+        if (e == cudaSuccess) return true;
+        *rc_out = fail(RSB_ERR_CUDA, cudaGetErrorString(e));
+        return false;
+    };
+    if (!Pp.s_in) {
+        if (!cuda_ok(cudaStreamCreateWithFlags(&Pp.s_in, cudaStreamNonBlocking))) return true;
+        if (!cuda_ok(cudaStreamCreateWithFlags(&Pp.s_out, cudaStreamNonBlocking))) return true;
+        for (int b = 0; b < 2; ++b) {
+            if (!cuda_ok(cudaEventCreateWithFlags(&Pp.ev_h2d[b], cudaEventDisableTiming))) return true;
+            if (!cuda_ok(cudaEventCreateWithFlags(&Pp.ev_conv[b], cudaEventDisableTiming))) return true;
+            if (!cuda_ok(cudaEventCreateWithFlags(&Pp.ev_d2h[b], cudaEventDisableTiming))) return true;
+        }
+    }
+    const size_t in_pitch = (((size_t)max_in * ch * sizeof(float)) + 15) & ~(size_t)15;
+    const size_t out_pitch = (((size_t)max_out * ch * sizeof(float)) + 15) & ~(size_t)15;
+    for (int b = 0; b < 2; ++b) {
+        if (!cuda_ok(Pp.d_in[b].reserve(in_pitch * n + 16))) return true;
+        if (!cuda_ok(Pp.d_out[b].reserve(out_pitch * n + 16))) return true;
+    }
+    // host rows at one pitch move with one 2-D copy per slice and direction
+    bool in_uniform = n > 1 && !getenv("RSB_HOST_PIPE_1D"), out_uniform = in_uniform;
+    ptrdiff_t h_in_pitch = 0, h_out_pitch = 0;
+    if (n > 1) {
+        h_in_pitch = reinterpret_cast<const char *>(jobs[1].in) - reinterpret_cast<const char *>(jobs[0].in);
+        h_out_pitch = reinterpret_cast<char *>(jobs[1].out) - reinterpret_cast<char *>(jobs[0].out);
+        for (uint32_t i = 1; i < n; ++i) {
+            if (reinterpret_cast<const char *>(jobs[i].in) - reinterpret_cast<const char *>(jobs[0].in) != (ptrdiff_t)i * h_in_pitch)
+                in_uniform = false;
+            if (reinterpret_cast<char *>(jobs[i].out) - reinterpret_cast<char *>(jobs[0].out) != (ptrdiff_t)i * h_out_pitch)
+                out_uniform = false;
+        }
+        if (h_in_pitch < (ptrdiff_t)(T * ch * sizeof(float)) || (size_t)h_in_pitch > h->mem_pitch) in_uniform = false;
+        if (h_out_pitch < (ptrdiff_t)(U.total_out * ch * sizeof(float)) || (size_t)h_out_pitch > h->mem_pitch) out_uniform = false;
+    }
+
+    std::vector<JobHost> sj(n);
+    int rc = RSB_OK;
+    for (uint32_t k = 0; k < n_slices && rc == RSB_OK; ++k) {
+        const int b = (int)(Pp.slices & 1u);
+        const Slice &S = sl[k];
+        const size_t in_w = (size_t)S.in_frames * ch * sizeof(float), out_w = (size_t)S.out_frames * ch * sizeof(float);
+        // the slice two before this one (possibly of the previous, asynchronous call) has been
+        // convolved out of this input buffer
+        if (Pp.slices >= 2 && !cuda_ok(cudaStreamWaitEvent(Pp.s_in, Pp.ev_conv[b], 0))) return true;
+        if (in_w) {
+            if (in_uniform) {
+                if (!cuda_ok(cudaMemcpy2DAsync(Pp.d_in[b].p, in_pitch, jobs[0].in + S.in_off * ch, (size_t)h_in_pitch,
+                                               in_w, n, cudaMemcpyHostToDevice, Pp.s_in))) return true;
+            } else {
+                for (uint32_t i = 0; i < n; ++i)
+                    if (!cuda_ok(cudaMemcpyAsync(static_cast<char *>(Pp.d_in[b].p) + i * in_pitch, jobs[i].in + S.in_off * ch,
+                                                 in_w, cudaMemcpyHostToDevice, Pp.s_in))) return true;
+            }
+        }
+        if (!cuda_ok(cudaEventRecord(Pp.ev_h2d[b], Pp.s_in))) return true;
+        if (!cuda_ok(cudaStreamWaitEvent(h->stream, Pp.ev_h2d[b], 0))) return true;
+        // slice k-2's results have left this output buffer
+        if (Pp.slices >= 2 && !cuda_ok(cudaStreamWaitEvent(h->stream, Pp.ev_d2h[b], 0))) return true;
+        for (uint32_t i = 0; i < n; ++i) {
+            sj[i] = jobs[i];
+            sj[i].in = reinterpret_cast<const float *>(static_cast<const char *>(Pp.d_in[b].p) + i * in_pitch);
+            sj[i].out = reinterpret_cast<float *>(static_cast<char *>(Pp.d_out[b].p) + i * out_pitch);
+            sj[i].total_frames = S.in_frames;
+            sj[i].out_capacity = S.out_frames;
+        }
+        rc = run_batch(h, sj, false, RSB_MEM_DEVICE, RSB_FLAG_ASYNC, nullptr, nullptr, nullptr);
+        if (rc != RSB_OK) break;
+        if (!cuda_ok(cudaEventRecord(Pp.ev_conv[b], h->stream))) return true;
+        if (!cuda_ok(cudaStreamWaitEvent(Pp.s_out, Pp.ev_conv[b], 0))) return true;
+        if (out_w) {
+            if (out_uniform) {
+                if (!cuda_ok(cudaMemcpy2DAsync(jobs[0].out + S.out_off * ch, (size_t)h_out_pitch, Pp.d_out[b].p, out_pitch,
+                                               out_w, n, cudaMemcpyDeviceToHost, Pp.s_out))) return true;
+            } else {
+                for (uint32_t i = 0; i < n; ++i)
+                    if (!cuda_ok(cudaMemcpyAsync(jobs[i].out + S.out_off * ch, static_cast<char *>(Pp.d_out[b].p) + i * out_pitch,
+                                                 out_w, cudaMemcpyDeviceToHost, Pp.s_out))) return true;
+            }
+        }
+        if (!cuda_ok(cudaEventRecord(Pp.ev_d2h[b], Pp.s_out))) return true;
+        Pp.slices += 1;
+    }
+    if (!async || rc != RSB_OK) {
+        const int rf = finalize_all(h);
+        if (rc == RSB_OK) rc = rf;
+        if (!cuda_ok(cudaStreamSynchronize(Pp.s_out))) return true;
+        if (!cuda_ok(cudaStreamSynchronize(h->stream))) return true;
+    }
+    Pp.batches += 1;
+    if (rc == RSB_OK) {
+        for (uint32_t i = 0; i < n; ++i) {
+            if (consumed) consumed[i] = (size_t)T * ch;
+            if (produced) produced[i] = (size_t)U.total_out * ch;
+            if (n_calls_out) n_calls_out[i] = n_calls;
+        }
+    }
+    *rc_out = rc;
+    return true;
+}
+
 int check_handle(const rsb_fir *h) {
     if (!h) return fail(RSB_ERR_INVALID_ARGUMENT, "null handle");
     return RSB_OK;
@@ -1213,6 +1393,13 @@ void rsb_fir_destroy(rsb_fir *h) {
         F.h_jobs.release(); F.h_res.release(); F.d_jobs.release(); F.d_res.release();
         if (F.ev_done) cudaEventDestroy(F.ev_done);
     }
+    for (int b = 0; b < 2; ++b) {
+        h->pipe.d_in[b].release();
+        h->pipe.d_out[b].release();
+        for (cudaEvent_t e : {h->pipe.ev_h2d[b], h->pipe.ev_conv[b], h->pipe.ev_d2h[b]}) if (e) cudaEventDestroy(e);
+    }
+    if (h->pipe.s_in) cudaStreamDestroy(h->pipe.s_in);
+    if (h->pipe.s_out) cudaStreamDestroy(h->pipe.s_out);
     for (cudaEvent_t e : h->ev_pcm) if (e) cudaEventDestroy(e);
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);
     if (h->ev_t1) cudaEventDestroy(h->ev_t1);
@@ -1395,6 +1582,11 @@ int rsb_fir_process_batch(rsb_fir *h, uint32_t n, const uint32_t *streams, const
         jobs[i] = JobHost{s, in[i], out[i], total_lens[i] / ch, out_capacities[i] / ch,
                           (uint32_t)(call_len / ch), (uint32_t)(out_cap_len / ch)};
     }
+    if (memspace == RSB_MEM_HOST && (flags & ~(uint32_t)RSB_FLAG_ASYNC) == 0 && !getenv("RSB_NO_HOST_PIPELINE")) {
+        int rc = RSB_OK;
+        if (process_host_pipelined(h, jobs, consumed_totals, produced_totals, n_calls,
+                                   (flags & RSB_FLAG_ASYNC) != 0, &rc)) return rc;
+    }
     return run_batch(h, jobs, false, memspace, flags, consumed_totals, produced_totals, n_calls);
 }
 
@@ -1501,6 +1693,7 @@ int rsb_fir_sync(rsb_fir *h) {
     if (rc == RSB_OK) rc = rf;
     RSB_CUDA(cudaStreamSynchronize(h->plan_stream));
     RSB_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->pipe.s_out) RSB_CUDA(cudaStreamSynchronize(h->pipe.s_out));
     return rc;
 }
 
@@ -1628,6 +1821,66 @@ int rsb_debug_tc_cycles(rsb_fir *h, int enable, uint64_t *out, uint32_t count) {
 }
 
 uint64_t rsb_fir_launch_count(const rsb_fir *h) { return h ? h->launches : 0; }
+
+int rsb_fir_host_pipeline_stats(const rsb_fir *h, uint64_t *batches, uint64_t *slices) {
+    if (check_handle(h)) return RSB_ERR_INVALID_ARGUMENT;
+    if (batches) *batches = h->pipe.batches;
+    if (slices) *slices = h->pipe.slices;
+    return RSB_OK;
+}
+
+// Pinned-memory copy rates of this GPU's PCIe link (GB/s): mode 0 host->device alone, 1 device->host
+// alone, 2 both directions at once (out[0] = host->device, out[1] = device->host).  Plain
+// cudaMemcpyAsync on two streams: the ceiling the host-memspace calls are measured against.
+int rsb_pcie_probe(int device, size_t bytes, int iters, int mode, double out[2]) {
+    if (!out || bytes == 0 || iters <= 0 || mode < 0 || mode > 2)
+        return fail(RSB_ERR_INVALID_ARGUMENT, "bad probe arguments");
+    if (cudaSetDevice(device) != cudaSuccess) return fail(RSB_ERR_NO_DEVICE, "no such device");
+    out[0] = out[1] = 0.0;
+    void *h_up = nullptr, *h_dn = nullptr, *d_up = nullptr, *d_dn = nullptr;
+    cudaStream_t s_up = nullptr, s_dn = nullptr;
+    cudaEvent_t e[4] = {};
+    int rc = RSB_OK;
+    auto ok = [&](cudaError_t err) {
+        if (err != cudaSuccess && rc == RSB_OK) rc = fail(RSB_ERR_CUDA, cudaGetErrorString(err));
+        return err == cudaSuccess;
+    };
+    ok(cudaMallocHost(&h_up, bytes)) && ok(cudaMallocHost(&h_dn, bytes)) && ok(cudaMalloc(&d_up, bytes)) &&
+        ok(cudaMalloc(&d_dn, bytes)) && ok(cudaStreamCreateWithFlags(&s_up, cudaStreamNonBlocking)) &&
+        ok(cudaStreamCreateWithFlags(&s_dn, cudaStreamNonBlocking));
+    for (int i = 0; i < 4 && rc == RSB_OK; ++i) ok(cudaEventCreate(&e[i]));
+    if (rc == RSB_OK) {
+        std::memset(h_up, 1, bytes);
+        std::memset(h_dn, 0, bytes);
+        const bool up = mode != 1, dn = mode != 0;
+        for (int pass = 0; pass < 2 && rc == RSB_OK; ++pass) {      // pass 0 warms up
+            const int reps = pass == 0 ? 1 : iters;
+            if (up) ok(cudaEventRecord(e[0], s_up));
+            if (dn) ok(cudaEventRecord(e[2], s_dn));
+            for (int i = 0; i < reps; ++i) {
+                if (up) ok(cudaMemcpyAsync(d_up, h_up, bytes, cudaMemcpyHostToDevice, s_up));
+                if (dn) ok(cudaMemcpyAsync(h_dn, d_dn, bytes, cudaMemcpyDeviceToHost, s_dn));
+            }
+            if (up) ok(cudaEventRecord(e[1], s_up));
+            if (dn) ok(cudaEventRecord(e[3], s_dn));
+            if (up) ok(cudaEventSynchronize(e[1]));
+            if (dn) ok(cudaEventSynchronize(e[3]));
+            if (pass == 1 && rc == RSB_OK) {
+                float ms = 0.f;
+                if (up && ok(cudaEventElapsedTime(&ms, e[0], e[1]))) out[0] = (double)bytes * reps / (ms * 1e-3) / 1e9;
+                if (dn && ok(cudaEventElapsedTime(&ms, e[2], e[3]))) out[1] = (double)bytes * reps / (ms * 1e-3) / 1e9;
+            }
+        }
+    }
+    for (cudaEvent_t ev : e) if (ev) cudaEventDestroy(ev);
+    if (s_up) cudaStreamDestroy(s_up);
+    if (s_dn) cudaStreamDestroy(s_dn);
+    if (d_up) cudaFree(d_up);
+    if (d_dn) cudaFree(d_dn);
+    if (h_up) cudaFreeHost(h_up);
+    if (h_dn) cudaFreeHost(h_dn);
+    return rc;
+}
 void *rsb_fir_cuda_stream(const rsb_fir *h) { return h ? (void *)h->stream : nullptr; }
 
 void *rsb_alloc_pinned(size_t bytes) {

@@ -438,6 +438,13 @@ class FirBatch:
     def launch_count(self) -> int:
         return self._lib.rsb_fir_launch_count(self._h)
 
+    def host_pipeline_stats(self):
+        """(batches, slices) of host-memspace ``process`` calls that ran as an overlapped pipeline
+        of time slices (H2D / kernels / D2H), see ``rsb_fir_host_pipeline_stats``."""
+        b, s = C.c_uint64(0), C.c_uint64(0)
+        _check(self._lib.rsb_fir_host_pipeline_stats(self._h, C.byref(b), C.byref(s)))
+        return int(b.value), int(s.value)
+
 
 class ResamplerFir:
     """Drop-in mirror of the reference's single-stream ``ResamplerFir``.

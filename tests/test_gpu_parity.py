@@ -566,3 +566,50 @@ def test_fused_submit_divergent_streams_bit_exact_and_handoff():
     batch.close()
     d_in.free()
     d_out.free()
+
+
+def test_host_pipeline_equals_unsliced_batch(monkeypatch):
+    """Host-memspace process() of a long batch runs as a pipeline of time slices (H2D, kernels and
+    D2H overlapped, slice boundaries from a dry run of the plan).  Counts, call numbers and -- with
+    the bit-exact kernel -- every sample equal the unsliced path's; the state carries on correctly
+    afterwards; the tensor kernel's sliced result stays within the bar of the oracle."""
+    n, ch, in_hz, out_hz, lat = 48, 2, 44100, 48000, 3
+    frames = 200_001                      # not a multiple of the call size
+    rng = np.random.default_rng(11)
+    ins = [noise(rng, frames * ch) for _ in range(n)]
+    tail = [noise(rng, 3000 * ch) for _ in range(n)]
+    results = {}
+    for mode in ("pipelined", "unsliced"):
+        if mode == "unsliced":
+            monkeypatch.setenv("RSB_NO_HOST_PIPELINE", "1")
+        else:
+            monkeypatch.delenv("RSB_NO_HOST_PIPELINE", raising=False)
+        batch = FirBatch(n, ch, in_hz, out_hz, Latency(lat), Attenuation.Db90, kernel=Kernel.EXACT)
+        r1 = batch.process(ins, 512 * ch)
+        b, sl = batch.host_pipeline_stats()
+        assert (b, sl > 2) == ((1, True) if mode == "pipelined" else (0, False))
+        r2 = batch.process(tail, 160 * ch)          # short: always unsliced, carries on from the state
+        results[mode] = (r1, r2)
+        batch.close()
+    (p1, p2), (u1, u2) = results["pipelined"], results["unsliced"]
+    for a, b_ in ((p1, u1), (p2, u2)):
+        assert np.array_equal(a["consumed"], b_["consumed"])
+        assert np.array_equal(a["produced"], b_["produced"])
+        assert np.array_equal(a["calls"], b_["calls"])
+        for s in range(n):
+            assert np.array_equal(bits(a["out"][s]), bits(b_["out"][s])), s
+    # against the oracle (two streams), then the tensor kernel through the same pipeline
+    monkeypatch.delenv("RSB_NO_HOST_PIPELINE", raising=False)
+    refs = {}
+    for s in (0, n - 1):
+        ref = O.OracleFir(ch, in_hz, out_hz, lat, 1)
+        refs[s] = ref.process(ins[s], 512 * ch)
+        assert p1["produced"][s] == len(refs[s]["out"])
+        assert np.array_equal(bits(p1["out"][s]), bits(np.asarray(refs[s]["out"], np.float32)))
+    batch = FirBatch(n, ch, in_hz, out_hz, Latency(lat), Attenuation.Db90, kernel=Kernel.AUTO)
+    rt = batch.process(ins, 512 * ch)
+    assert batch.last_kernel() == Kernel.TENSOR and batch.host_pipeline_stats()[0] == 1
+    for s in (0, n - 1):
+        assert rt["produced"][s] == len(refs[s]["out"])
+        assert np.max(np.abs(rt["out"][s].astype(np.float64) - refs[s]["out"])) <= TOL_FAST
+    batch.close()
