@@ -344,6 +344,141 @@ def device_leg(lib, local, rank, cfg, steps, warmup, kern, dist=None, sampler=No
     return res
 
 
+def strong_leg(lib, local, rank, world, dist, steps, warmup, kern, total_streams=65536, seconds=10.0):
+    """BASELINE configs[4]: 65 536 stereo streams x 10 s, 44.1 -> 48 kHz, 128 taps, sharded BY STREAM ID
+    over the N GPUs of the run (strong scaling: the job is fixed, a rank owns streams
+    [G*r/N, G*(r+1)/N)).  231 GB in + 252 GB out do not fit two GPUs, so every rank feeds its
+    share as time slices of 86 calls (~1 s resident) with the stream state carried from slice to
+    slice; the synthetic second of audio is regenerated nowhere: every slice reads the same device
+    buffer (the state, the plan and the traffic are those of the real 10 s)."""
+    from resampler_b200 import Attenuation, FirBatch, Latency
+    from resampler_b200.fir import FLAG_ASYNC, MEM_DEVICE, DeviceBuffer, _ptr_array, _size_array
+    from resampler_b200.sharding import shard_range
+    lo, hi = shard_range(total_streams, world, rank)
+    n = hi - lo
+    ch, in_hz, out_hz, lat, call = 2, 44100, 48000, 3, 512
+    frames_total = int(round(seconds * in_hz))
+    slice_frames = 86 * call                                   # 0.998 s, whole calls
+    n_full, tail = divmod(frames_total, slice_frames)
+    batch = FirBatch(n, ch, in_hz, out_hz, Latency(lat), Attenuation(ATTENUATION), device=local, kernel=kern)
+    in_stride = slice_frames * ch
+    out_stride = ((int(slice_frames / batch.ratio()) + 8) * ch + 3) & ~3
+    d_in = DeviceBuffer(local, n * in_stride)
+    d_out = DeviceBuffer(local, n * out_stride)
+    assert lib.rsb_fill_synthetic(local, d_in.ptr, lo, n, slice_frames, ch, in_hz, 0x5EED) == 0
+    in_ptrs = _ptr_array([d_in.ptr + 4 * s * in_stride for s in range(n)])
+    out_ptrs = _ptr_array([d_out.ptr + 4 * s * out_stride for s in range(n)])
+    caps = _size_array([out_stride] * n)
+    lens_full, lens_tail = _size_array([in_stride] * n), _size_array([tail * ch] * n)
+
+    def one_pass():
+        batch.reset(-1)
+        res = []
+        for k in range(n_full + (1 if tail else 0)):
+            res.append(batch.process_ptrs(in_ptrs, lens_full if k < n_full else lens_tail, call * ch, 0,
+                                          out_ptrs, caps, memspace=MEM_DEVICE, flags=FLAG_ASYNC))
+        return res
+
+    for _ in range(max(1, min(warmup, 2))):
+        one_pass()
+    batch.sync()
+    barrier(dist, local)
+    batch.timer_start()
+    res = None
+    for _ in range(steps):
+        res = one_pass()
+    ms = batch.timer_stop()
+    batch.sync()
+    barrier(dist, local)
+    cons = np.sum([np.array(r[0][:], np.int64) for r in res], axis=0)
+    prod = np.sum([np.array(r[1][:], np.int64) for r in res], axis=0)
+    calls = np.sum([np.array(r[2][:], np.int64) for r in res], axis=0)
+    uniform = bool((cons == cons[0]).all() and (prod == prod[0]).all() and (calls == calls[0]).all())
+    all_in = bool(cons[0] == frames_total * ch)
+    conv_ms = float(np.sum(batch.conv_times_ms(min(len(res), 64))))
+    kernel = batch.last_kernel().name.lower()
+    d_in.free()
+    d_out.free()
+    batch.close()
+    ms_max = reduce_max(dist, local, ms)
+    prod_all = reduce_sum(dist, local, float(prod.sum()))
+    cons_all = reduce_sum(dist, local, float(cons.sum()))
+    conv_max = reduce_max(dist, local, conv_ms)
+    ok_all = reduce_sum(dist, local, 0.0 if (uniform and all_in) else 1.0) == 0.0
+    hbm_peak, peak_src = measured_peaks()
+    gbs = 4.0 * (prod_all + cons_all) / world / (conv_max * 1e-3) / 1e9
+    return {"workload": f"configs[4]: {total_streams} stereo streams x {seconds:g} s, 44.1->48 kHz, Sample64 (128 taps), "
+                        f"Db90, 512-frame calls, sharded by stream id over {world} GPU(s) ({n} streams on rank 0), "
+                        f"{n_full + (1 if tail else 0)} time slices of <= {slice_frames / in_hz:.3f} s with state carry",
+            "scaling": "strong", "kernel": kernel, "value": round(prod_all * steps / (ms_max * 1e-3) / 1e6, 1),
+            "unit": "Msamples/s", "ms_per_pass": round(ms_max / steps, 3), "steps": steps,
+            "produced_samples_per_pass": int(prod_all), "calls_per_stream": int(calls[0]),
+            "counts_uniform_and_complete": ok_all,
+            "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s per GPU",
+                         "frac": round(gbs / hbm_peak, 4), "peak_source": peak_src,
+                         "conv_ms_per_pass": round(conv_max, 3)}}
+
+
+def divergent_leg(lib, local, rank, dist, n_streams=4096, submits=64):
+    """BASELINE configs[2] variant (ii): 4096 mono streams, 16 -> 48 kHz, Sample16 (32 taps), one
+    resample() per stream per submit with PER-STREAM pseudo-random call sizes (80..480 frames): no two
+    streams share a plan.  Device-resident, one fused launch per submit (fir_submit.cu); every
+    pointer table is built before the timed region."""
+    from resampler_b200 import Attenuation, FirBatch, Latency
+    from resampler_b200.fir import FLAG_ASYNC, MEM_DEVICE, DeviceBuffer, _ptr_array, _size_array
+    ch, in_hz, out_hz, lat = 1, 16000, 48000, 1
+    batch = FirBatch(n_streams, ch, in_hz, out_hz, Latency(lat), Attenuation(ATTENUATION), device=local)
+    rng = np.random.default_rng(1234 + rank)
+    sizes = rng.integers(80, 481, size=(submits, n_streams))
+    span = int(sizes.sum(axis=0).max()) + 16
+    bso = batch.buffer_size_output()
+    d_in = DeviceBuffer(local, n_streams * span)
+    d_out = DeviceBuffer(local, n_streams * bso)
+    assert lib.rsb_fill_synthetic(local, d_in.ptr, rank * n_streams, n_streams, span, ch, in_hz, 0x5EED) == 0
+    cursor = np.zeros(n_streams, np.int64)
+    out_ptrs = _ptr_array([d_out.ptr + 4 * s * bso for s in range(n_streams)])
+    out_lens = _size_array([bso] * n_streams)
+    tables = []
+    for k in range(submits):
+        tables.append((_ptr_array([int(d_in.ptr + 4 * (s * span + cursor[s])) for s in range(n_streams)]),
+                       _size_array(sizes[k].tolist())))
+        cursor += sizes[k]
+
+    def one_pass(timed):
+        batch.reset(-1)
+        res = []
+        if timed:
+            batch.timer_start()
+        for ip, il in tables:
+            res.append(batch.submit_ptrs(ip, il, out_ptrs, out_lens, memspace=MEM_DEVICE, flags=FLAG_ASYNC))
+        ms = batch.timer_stop() if timed else 0.0
+        batch.sync()
+        return res, ms
+
+    one_pass(False)
+    barrier(dist, local)
+    t0 = time.perf_counter()
+    res, ms = one_pass(True)
+    wall = time.perf_counter() - t0
+    cons = np.sum([np.array(r[0][:], np.int64) for r in res], axis=0)
+    prod = np.sum([np.array(r[1][:], np.int64) for r in res], axis=0)
+    complete = bool((cons == sizes.sum(axis=0)).all())
+    kernel = batch.last_kernel().name.lower()
+    d_in.free()
+    d_out.free()
+    batch.close()
+    ms_max = reduce_max(dist, local, ms)
+    wall_max = reduce_max(dist, local, wall)
+    prod_all = reduce_sum(dist, local, float(prod.sum()))
+    return {"workload": f"configs[2] (ii): {n_streams} mono streams per GPU, 16->48 kHz, Sample16 (32 taps), Db90, "
+                        f"{submits} submits of one resample() per stream, per-stream random call sizes 80..480 frames "
+                        "(every stream its own plan), device resident",
+            "kernel": kernel + " (fused single-launch submit)", "value": round(prod_all / (ms_max * 1e-3) / 1e6, 1),
+            "unit": "Msamples/s", "us_per_submit_device": round(ms_max * 1e3 / submits, 2),
+            "us_per_submit_wall": round(wall_max * 1e6 / submits, 2), "submits": submits,
+            "all_input_consumed": complete}
+
+
 def leg_roofline(res, hbm_peak, peak_src):
     conv_avg_ms = float(np.mean(res["conv_ms"])) if res["conv_ms"] else float("nan")
     alg_bytes = 4.0 * (res["produced"] + res["consumed"])
@@ -490,6 +625,17 @@ def run_ours(args):
             except Exception as e:      # a leg must not take the headline line down
                 legs[key] = {"workload": cfg["name"], "error": str(e)[:300]}
 
+        try:
+            legs["C3ii"] = divergent_leg(lib, local, rank, dist)
+        except Exception as e:
+            legs["C3ii"] = {"workload": "configs[2] (ii)", "error": str(e)[:300]}
+    strong = None
+    if not args.no_legs:
+        try:
+            strong = strong_leg(lib, local, rank, world, dist, max(2, min(args.steps, 3)), args.warmup, kern)
+        except Exception as e:
+            strong = {"workload": "configs[4]", "scaling": "strong", "error": str(e)[:300]}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 3), "unit": "Msamples/s", "n_gpus": world,
@@ -505,7 +651,7 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(head_launches),
             "clocks": clocks,
             "produced_samples_per_step_per_gpu": R["produced"],
-            "other_configs": legs,
+            "other_configs": legs, "strong_scaling": strong,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -613,3 +613,56 @@ def test_host_pipeline_equals_unsliced_batch(monkeypatch):
         assert rt["produced"][s] == len(refs[s]["out"])
         assert np.max(np.abs(rt["out"][s].astype(np.float64) - refs[s]["out"])) <= TOL_FAST
     batch.close()
+
+
+def test_config5_share_time_sliced_with_state_carry_matches_oracle():
+    """BASELINE configs[4] as one GPU of eight sees it: the share of rank 3 (streams 24576..32767 of
+    65 536 stereo streams x 10 s, 44.1 -> 48 kHz, 128 taps) fed as 11 device-resident time slices
+    (10 x 86 calls + a tail) with the stream state carried from slice to slice -- the loop of
+    bench.py's strong-scaling leg.  Counts of ALL 8192 streams and every sample of the streams with
+    id = 0 mod 64 are compared with the oracle run over the unsliced 10 s."""
+    from resampler_b200.fir import FLAG_ASYNC, MEM_DEVICE, DeviceBuffer, _ptr_array, _size_array
+    from resampler_b200 import _lib
+    from resampler_b200.sharding import shard_range
+    lib = _lib.load()
+    lo, hi = shard_range(65536, 8, 3)
+    n, ch, in_hz, out_hz, lat, call = hi - lo, 2, 44100, 48000, 3, 512
+    frames_total, slice_frames = 441000, 86 * 512
+    n_full, tail = divmod(frames_total, slice_frames)
+    batch = FirBatch(n, ch, in_hz, out_hz, Latency(lat), Attenuation.Db90, kernel=Kernel.AUTO)
+    in_stride = slice_frames * ch
+    out_stride = ((int(slice_frames / batch.ratio()) + 8) * ch + 3) & ~3
+    d_in, d_out = DeviceBuffer(0, n * in_stride), DeviceBuffer(0, n * out_stride)
+    assert lib.rsb_fill_synthetic(0, d_in.ptr, lo, n, slice_frames, ch, in_hz, 0x5EED) == 0
+    in_ptrs = _ptr_array([d_in.ptr + 4 * s * in_stride for s in range(n)])
+    out_ptrs = _ptr_array([d_out.ptr + 4 * s * out_stride for s in range(n)])
+    caps = _size_array([out_stride] * n)
+    check = [s for s in range(n) if (lo + s) % 64 == 0]
+    got = {s: [] for s in check}
+    cons_t, prod_t, calls_t = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n, np.int64)
+    for k in range(n_full + 1):
+        lens = _size_array([(slice_frames if k < n_full else tail) * ch] * n)
+        c, p, nc = batch.process_ptrs(in_ptrs, lens, call * ch, 0, out_ptrs, caps, memspace=MEM_DEVICE,
+                                      flags=FLAG_ASYNC)
+        batch.sync()
+        assert batch.last_kernel() == Kernel.TENSOR
+        cons_t += np.array(c[:], np.int64)
+        prod_t += np.array(p[:], np.int64)
+        calls_t += np.array(nc[:], np.int64)
+        for s in check:
+            got[s].append(d_out.download(int(p[s]), s * out_stride))
+    worst = 0.0
+    for s in check:
+        one = d_in.download(in_stride, s * in_stride)
+        x = np.concatenate([one] * n_full + [one[:tail * ch]])
+        ref = oracle_stream(ch, in_hz, out_hz, lat, 1, x, call * ch)
+        if s == check[0]:
+            assert (cons_t == frames_total * ch).all() and (prod_t == len(ref["out"])).all()
+            assert (calls_t == len(ref["consumed"])).all()
+        y = np.concatenate(got[s])
+        assert len(y) == len(ref["out"])
+        worst = max(worst, float(np.max(np.abs(y.astype(np.float64) - ref["out"]))))
+    assert worst <= TOL_FAST, worst
+    batch.close()
+    d_in.free()
+    d_out.free()
