@@ -164,7 +164,7 @@ struct rsb_fir {
     // previous submit still runs; results are delivered when a slot is reused or at sync
     struct FusedSlot {
         PinBuf h_jobs, h_res;
-        DevBuf d_jobs, d_res;
+        DevBuf d_jobs, d_res, d_segs;
         cudaEvent_t ev_done = nullptr;
         bool active = false;
         uint32_t n = 0;
@@ -1005,6 +1005,9 @@ int finalize_fused_all(rsb_fir *h) {
 }
 
 // One launch for the whole submit (device memspace): see fir_submit.cu.
+// Returns RSB_OK / an error, or kNotTaken when an AUTO submit is large enough for the tile kernels
+// (nothing has been changed then).
+constexpr int kNotTaken = -1000;
 int run_submit_fused(rsb_fir *h, uint32_t n, const uint32_t *streams, const float *const *in,
                      const size_t *in_lens, float *const *out, const size_t *out_lens, size_t *consumed,
                      size_t *produced, uint32_t flags) {
@@ -1020,34 +1023,70 @@ int run_submit_fused(rsb_fir *h, uint32_t n, const uint32_t *streams, const floa
     RSB_CUDA(F.h_res.reserve(sizeof(rsb::SubmitResult) * n));
     RSB_CUDA(F.d_jobs.reserve(sizeof(rsb::SubmitJob) * n));
     RSB_CUDA(F.d_res.reserve(sizeof(rsb::SubmitResult) * n));
+    RSB_CUDA(F.d_segs.reserve(sizeof(rsb::PlanSeg) * rsb::kSubmitSegs * n));
     rsb::SubmitJob *hj = F.h_jobs.as<rsb::SubmitJob>();
     F.streams.resize(n);
+    uint32_t *fs = F.streams.data();
     const size_t hist_stride = (size_t)rsb::kHistFrames * ch;
-    const uint64_t seq = ++h->fused_count;         // slot index of THIS submit was taken above
-    // all jobs of one cohort with one call signature keep sharing a cohort afterwards
+    // ---- pass 1: validation (error precedence of resampler_fir.rs:514-519 per job) and the job
+    // table; touches scratch only.  The host cost of a submit is this loop: no 64-bit divisions
+    // (channel counts are powers of two in practice), one pass over the caller's arrays. ----
+    const bool pow2 = (ch & (ch - 1)) == 0;
+    const uint32_t sh = pow2 ? (uint32_t)__builtin_ctz(ch) : 0u;
+    const size_t mask = pow2 ? (size_t)ch - 1 : 0;
+    h->epoch += 1;
+    if (h->epoch == 0) { std::fill(h->seen_epoch.begin(), h->seen_epoch.end(), 0u); h->epoch = 1; }
+    const uint32_t epoch = h->epoch, n_streams = h->n_streams;
+    uint32_t *seen = h->seen_epoch.data();
+    const uint8_t *hsel = h->hist_sel.data();
+    const uint64_t *coh = h->cohort.data();
+    float *const hist0 = h->st.hist[0], *const hist1 = h->st.hist[1];
     bool same = true;
-    const uint32_t s0 = streams ? streams[0] : 0u;
-    const uint64_t c0 = h->cohort[s0];
+    uint32_t max_in = 0;
+    uint64_t in_total = 0;
+    const uint64_t c0 = coh[streams ? (streams[0] < n_streams ? streams[0] : 0u) : 0u];
     for (uint32_t i = 0; i < n; ++i) {
         const uint32_t s = streams ? streams[i] : i;
+        const size_t il = in_lens[i], ol = out_lens[i];
+        if (pow2 ? (il & mask) != 0 : il % ch != 0)
+            return fail(RSB_ERR_INVALID_INPUT_BUFFER_SIZE, "input length of job " + std::to_string(i) +
+                                                               " is not a multiple of channels");
+        if (pow2 ? (ol & mask) != 0 : ol % ch != 0)
+            return fail(RSB_ERR_INVALID_OUTPUT_BUFFER_SIZE, "output length of job " + std::to_string(i) +
+                                                                " is not a multiple of channels");
+        if (s >= n_streams) return fail(RSB_ERR_INVALID_ARGUMENT, "bad stream index");
+        if (seen[s] == epoch) return fail(RSB_ERR_INVALID_ARGUMENT, "stream listed twice in one batch");
+        seen[s] = epoch;
+        if (il && !in[i]) return fail(RSB_ERR_INVALID_ARGUMENT, "null input pointer");
+        if (ol && !out[i]) return fail(RSB_ERR_INVALID_ARGUMENT, "null output pointer");
+        const uint64_t fin = pow2 ? il >> sh : il / ch, fout = pow2 ? ol >> sh : ol / ch;
         rsb::SubmitJob J;
         J.in = in[i];
         J.out = out[i];
-        const uint32_t sel = h->hist_sel[s];
-        J.hist = h->st.hist[sel] + hist_stride * s;
-        J.hist_next = h->st.hist[sel ^ 1u] + hist_stride * s;
-        J.in_frames = (uint32_t)std::min<uint64_t>(in_lens[i] / ch, rsb::kInputCapacity);   // :526-528
-        J.cap_frames = (uint32_t)std::min<uint64_t>(out_lens[i] / ch, 0xffffffffull);
+        const uint32_t sel = hsel[s];
+        J.hist = (sel ? hist1 : hist0) + hist_stride * s;
+        J.hist_next = (sel ? hist0 : hist1) + hist_stride * s;
+        J.in_frames = (uint32_t)std::min<uint64_t>(fin, rsb::kInputCapacity);   // :526-528
+        J.cap_frames = (uint32_t)std::min<uint64_t>(fout, 0xffffffffull);
         J.stream = s;
         J.pad = 0;
         hj[i] = J;
-        F.streams[i] = s;
-        same = same && h->cohort[s] == c0 && J.in_frames == hj[0].in_frames && J.cap_frames == hj[0].cap_frames;
+        fs[i] = s;
+        max_in = std::max(max_in, J.in_frames);
+        in_total += J.in_frames;
+        same = same && coh[s] == c0 && J.in_frames == hj[0].in_frames && J.cap_frames == hj[0].cap_frames;
     }
+    // AUTO: the tile kernels win once a submit carries tens of millions of samples
+    if (h->kernel_mode != RSB_KERNEL_EXACT &&
+        ((double)in_total + (double)n * (rsb::kInputCapacity / 8)) / h->ratio * ch > (double)(32ull << 20))
+        return kNotTaken;
+    // ---- pass 2: bookkeeping ----
+    const uint64_t seq = ++h->fused_count;         // slot index of THIS submit was taken above
+    // all jobs of one cohort with one call signature keep sharing a cohort afterwards
     const uint64_t shared = h->next_cohort;
     if (same) h->next_cohort += 1;
     for (uint32_t i = 0; i < n; ++i) {
-        const uint32_t s = F.streams[i];
+        const uint32_t s = fs[i];
         h->cohort[s] = same ? shared : h->next_cohort++;
         h->hist_sel[s] ^= 1u;
         h->m_ok[s] = 0;
@@ -1060,12 +1099,12 @@ int run_submit_fused(rsb_fir *h, uint32_t n, const uint32_t *streams, const floa
     RSB_CUDA(cudaStreamWaitEvent(s, h->ev_sync, 0));
     RSB_CUDA(cudaMemcpyAsync(F.d_jobs.p, hj, sizeof(rsb::SubmitJob) * n, cudaMemcpyHostToDevice, s));
     rsb::launch_submit_fused(F.d_jobs.as<rsb::SubmitJob>(), F.d_res.as<rsb::SubmitResult>(), n, h->st,
-                             h->d_coeffs, h->ratio, h->taps, ch, s);
+                             h->d_coeffs, h->ratio, h->taps, ch, max_in, F.d_segs.as<rsb::PlanSeg>(), s);
     RSB_CUDA(cudaGetLastError());
     RSB_CUDA(cudaMemcpyAsync(F.h_res.p, F.d_res.p, sizeof(rsb::SubmitResult) * n, cudaMemcpyDeviceToHost, s));
     RSB_CUDA(cudaEventRecord(F.ev_done, s));
     RSB_CUDA(cudaStreamWaitEvent(sp, F.ev_done, 0));
-    h->launches += 1;
+    h->launches += 2;      // plan + convolution (one launch on the half-warp fallback)
     h->last_kernel = RSB_KERNEL_EXACT;
     F.active = true;
     F.n = n;
@@ -1390,7 +1429,7 @@ void rsb_fir_destroy(rsb_fir *h) {
     for (DevBuf *b : {&h->d_stage_in, &h->d_stage_out, &h->d_dbg, &h->d_pcm_raw, &h->d_zero, &h->d_tct2, &h->d_gmat2})
         b->release();
     for (auto &F : h->fused) {
-        F.h_jobs.release(); F.h_res.release(); F.d_jobs.release(); F.d_res.release();
+        F.h_jobs.release(); F.h_res.release(); F.d_jobs.release(); F.d_res.release(); F.d_segs.release();
         if (F.ev_done) cudaEventDestroy(F.ev_done);
     }
     for (int b = 0; b < 2; ++b) {
@@ -1494,6 +1533,15 @@ int rsb_fir_submit_batch(rsb_fir *h, uint32_t n, const uint32_t *streams, const 
     if (memspace != RSB_MEM_DEVICE && memspace != RSB_MEM_HOST)
         return fail(RSB_ERR_INVALID_ARGUMENT, "bad memspace");
     const uint32_t ch = h->channels;
+    // Small device-resident submits take the fused path (fir_submit.cu): plan, samples in the
+    // reference's order and state update in two launches, per-stream call sizes welcome.  Large
+    // ones (tens of millions of samples) are better served by the tile kernels below.
+    static const bool no_fused = getenv("RSB_NO_FUSED_SUBMIT") != nullptr;
+    if (memspace == RSB_MEM_DEVICE && !(flags & (RSB_FLAG_RECORD_CALLS | RSB_FLAG_KEEP_PLAN)) &&
+        (h->kernel_mode == RSB_KERNEL_AUTO || h->kernel_mode == RSB_KERNEL_EXACT) && !no_fused) {
+        const int rf = run_submit_fused(h, n, streams, in, in_lens, out, out_lens, consumed, produced, flags);
+        if (rf != kNotTaken) return rf;
+    }
     // error precedence of resampler_fir.rs:514-519, per job, before any state changes
     for (uint32_t i = 0; i < n; ++i) {
         if (in_lens[i] % ch != 0)
@@ -1503,29 +1551,6 @@ int rsb_fir_submit_batch(rsb_fir *h, uint32_t n, const uint32_t *streams, const 
             return fail(RSB_ERR_INVALID_OUTPUT_BUFFER_SIZE, "output length of job " +
                                                                 std::to_string(i) +
                                                                 " is not a multiple of channels");
-    }
-    // Small device-resident submits take the single-launch path (fir_submit.cu): plan, samples in
-    // the reference's order and state update in one kernel, per-stream call sizes welcome.  Large
-    // ones (tens of millions of samples) are better served by the tile kernels below.
-    if (memspace == RSB_MEM_DEVICE && !(flags & (RSB_FLAG_RECORD_CALLS | RSB_FLAG_KEEP_PLAN)) &&
-        (h->kernel_mode == RSB_KERNEL_AUTO || h->kernel_mode == RSB_KERNEL_EXACT) && !getenv("RSB_NO_FUSED_SUBMIT")) {
-        h->epoch += 1;
-        if (h->epoch == 0) { std::fill(h->seen_epoch.begin(), h->seen_epoch.end(), 0u); h->epoch = 1; }
-        uint64_t est = 0;
-        bool ok = true;
-        for (uint32_t i = 0; i < n && ok; ++i) {
-            const uint32_t s = streams ? streams[i] : i;
-            if (s >= h->n_streams) return fail(RSB_ERR_INVALID_ARGUMENT, "bad stream index");
-            if (h->seen_epoch[s] == h->epoch) return fail(RSB_ERR_INVALID_ARGUMENT, "stream listed twice in one batch");
-            h->seen_epoch[s] = h->epoch;
-            if (in_lens[i] && !in[i]) return fail(RSB_ERR_INVALID_ARGUMENT, "null input pointer");
-            if (out_lens[i] && !out[i]) return fail(RSB_ERR_INVALID_ARGUMENT, "null output pointer");
-            const uint64_t frames = std::min<uint64_t>(in_lens[i] / ch, rsb::kInputCapacity);
-            est += std::min<uint64_t>((uint64_t)((double)(frames + rsb::kInputCapacity / 8) / h->ratio) + 2, out_lens[i] / ch) * ch;
-        }
-        // AUTO: the tile kernels win once a submit carries tens of millions of samples
-        if (h->kernel_mode == RSB_KERNEL_EXACT || est <= (32ull << 20))
-            return run_submit_fused(h, n, streams, in, in_lens, out, out_lens, consumed, produced, flags);
     }
     std::vector<JobHost> jobs(n);
     std::vector<uint8_t> seen(h->n_streams, 0);

@@ -201,9 +201,12 @@ struct SubmitResult {
     uint32_t produced;        // frames
     uint32_t available;
     uint32_t status;          // 0 ok, 1 plan segment overflow
+    uint32_t hist0;           // buffered frames BEFORE the call (the convolution kernel's window)
+    uint32_t n_seg;           // plan segments of the call
 };
+constexpr uint32_t kSubmitSegs = 128;       // plan segments of ONE call (bound: segs_per_call_bound)
 void launch_submit_fused(const SubmitJob *jobs, SubmitResult *results, uint32_t n_jobs, StreamStateDev st,
                          const float *coeffs, double ratio, uint32_t taps, uint32_t channels,
-                         cudaStream_t stream);
+                         uint32_t max_in_frames, PlanSeg *seg_store, cudaStream_t stream);
 
 }  // namespace rsb

@@ -15,13 +15,14 @@
 //      the oracle, divergent streams included;
 //   4. the CTA writes the new history tail into the stream's other history buffer and the
 //      scalars (position, buffered frames) back to the device state and to the result record.
+#include <cstdlib>
+
 #include "fir_kernels.h"
 
 namespace rsb {
 
 namespace {
 
-constexpr uint32_t kSubmitSegs = 128;       // plan segments of ONE call (bound: segs_per_call_bound)
 constexpr uint32_t kSubmitBlock = 1024;     // output frames expanded per pass
 
 struct SmemSink {
@@ -77,6 +78,8 @@ __global__ void __launch_bounds__(256) submit_fused_kernel(const SubmitJob *jobs
         res.produced = s_produced;
         res.available = s.available;
         res.status = s_status;
+        res.hist0 = s_h0;
+        res.n_seg = s_nseg;
         results[blockIdx.x] = res;
     }
     __syncthreads();
@@ -152,12 +155,297 @@ __global__ void __launch_bounds__(256) submit_fused_kernel(const SubmitJob *jobs
     }
 }
 
+// ---- thread-per-output variant (the default) ----
+// The half-warp kernel above spends ~60 warp instructions per output sample: every lane owns
+// only taps/16 FMAs per phase, the rest is addressing, shuffles and the blend.  Here ONE thread
+// computes an output sample and keeps all 16 "zmm lanes" as private accumulators, so the
+// reference's arithmetic (per-lane FMA chains over taps l, l + 16, ..., unfused blend per lane,
+// halving tree 8 / 4 / 2 / 1: fir/avx512.rs:22-48) runs entirely in registers, in the same order:
+// the samples stay BIT-IDENTICAL to the oracle.  Neighbouring lanes are advanced two at a time with
+// packed fp32 instructions (fma / mul / add .f32x2: each half is the IEEE scalar operation).
+//   * The call's input window [history | new input] does not depend on the plan: warps 1-3 copy it
+//     into shared memory WHILE thread 0 runs the serial planner (a window that does not fit is read
+//     from global memory instead).
+//   * The per-frame plan is expanded for up to 1024 frames at a time; after that the warps work
+//     independently on blocks of 32 outputs (no CTA-wide barrier per block).
+//   * The two coefficient rows of an output differ from thread to thread (every output has its own
+//     phase), so a warp first copies the rows of its block's frames into shared memory with
+//     16-byte asynchronous copies (row stride TB + 4 floats: the later per-thread 16-byte reads are
+//     bank-conflict free), TB = 32 taps at a time.
+constexpr uint32_t kTpThreads = 128;
+constexpr uint32_t kSuper = 512;           // frames expanded per pass
+constexpr int kTpTapBlock = 16;            // taps staged per round (16: half the staging memory of 32, more CTAs per SM)
+
+__device__ __forceinline__ float2 fmul2(const float2 a, const float2 b) {
+    float2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;"
+        : "=l"(reinterpret_cast<uint64_t &>(d))
+        : "l"(reinterpret_cast<const uint64_t &>(a)), "l"(reinterpret_cast<const uint64_t &>(b)));
+    return d;
+}
+__device__ __forceinline__ float2 fadd2(const float2 a, const float2 b) {
+    float2 d;
+    asm("add.rn.f32x2 %0, %1, %2;"
+        : "=l"(reinterpret_cast<uint64_t &>(d))
+        : "l"(reinterpret_cast<const uint64_t &>(a)), "l"(reinterpret_cast<const uint64_t &>(b)));
+    return d;
+}
+// d = a * b + d on both halves (fma.rn.f32x2, SASS FFMA2): two IEEE fp32 FMAs in one instruction
+__device__ __forceinline__ void ffma2(float2 &d, const float2 a, const float2 b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;"
+        : "+l"(reinterpret_cast<uint64_t &>(d))
+        : "l"(reinterpret_cast<const uint64_t &>(a)), "l"(reinterpret_cast<const uint64_t &>(b)));
+}
+
+// value e of the virtual buffer [history | new input] (interleaved), from shared or global memory
+template <bool XS>
+__device__ __forceinline__ float win_at(const float *s_x, const float *hist, const float *in, int64_t HC, uint32_t e) {
+    if (XS) return s_x[e];
+    return (int64_t)e < HC ? __ldg(hist + e) : __ldg(in + ((int64_t)e - HC));
+}
+
+// One block of 32 consecutive output VALUES (frame-major, channel-minor) of the call, by one warp.
+template <int TAPS, bool XS>
+__device__ __forceinline__ void tp_block(uint32_t idx0, uint32_t n_vals, uint32_t k0, uint32_t ch, const int32_t *s_v,
+                                         const uint16_t *s_p1, const float *s_frac, const float *s_x, const float *hist,
+                                         const float *in, int64_t HC, const float *coeffs, float *cw, float *out,
+                                         uint32_t lane) {
+    constexpr int TB = TAPS < kTpTapBlock ? TAPS : kTpTapBlock;
+    constexpr int CS = TB + 4;
+    constexpr uint32_t CPR = TB / 4, kStageRows = 32u / (2u * CPR);
+    // staging role of this lane: 16-byte piece st_q of phase st_ph, frames st_r, st_r + kStageRows, ...
+    const uint32_t st_q = lane % CPR, st_ph = (lane / CPR) & 1u, st_r = lane / (2u * CPR);
+    const uint32_t st_dst = (uint32_t)__cvta_generic_to_shared(cw) + (st_ph * CS + st_q * 4u) * 4u;
+    const uint32_t idx = idx0 + lane;
+    const bool valid = idx < n_vals;
+    const uint32_t idc = valid ? idx : n_vals - 1;
+    const uint32_t fg = idc / ch, c = idc - fg * ch;                 // frame of the call, channel
+    const uint32_t f_lo = idx0 / ch;
+    const uint32_t f_hi = (min(idx0 + 31u, n_vals - 1)) / ch;
+    const uint32_t nr = f_hi - f_lo + 1u;
+    const uint32_t fr = fg - f_lo;
+    const uint32_t xb = (uint32_t)s_v[fg - k0] * ch + c;
+    float2 acc1[8], acc2[8];
+#pragma unroll
+    for (int l = 0; l < 8; ++l) acc1[l] = acc2[l] = make_float2(0.0f, 0.0f);
+#pragma unroll 1
+    for (int tb = 0; tb < TAPS / TB; ++tb) {
+        {
+            const float *src_l = coeffs + tb * TB + st_q * 4u;
+            for (uint32_t r = st_r; r < nr; r += 4u * kStageRows) {
+                // four rows per trip: the phase look-ups first, then the copies (a single row per
+                // trip exposed the shared-memory latency once per row)
+                uint32_t p[4];
+#pragma unroll
+                for (uint32_t u = 0; u < 4; ++u) {
+                    const uint32_t rr = min(r + u * kStageRows, nr - 1);
+                    p[u] = min((uint32_t)s_p1[f_lo + rr - k0] + st_ph, kPhases - 1);
+                }
+#pragma unroll
+                for (uint32_t u = 0; u < 4; ++u) {
+                    const uint32_t rr = r + u * kStageRows;
+                    if (rr < nr)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(st_dst + rr * (2u * CS * 4u)),
+                                     "l"(src_l + (size_t)p[u] * TAPS)
+                                     : "memory");
+                }
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+        }
+        __syncwarp();
+        const float4 *r1 = reinterpret_cast<const float4 *>(cw + (size_t)fr * 2u * CS);
+        const float4 *r2 = reinterpret_cast<const float4 *>(cw + (size_t)fr * 2u * CS + CS);
+        const uint32_t xq = xb + (uint32_t)tb * TB * ch;
+#pragma unroll
+        for (int q = 0; q < TB / 4; ++q) {
+            const float4 a = r1[q], b = r2[q];
+            const float2 x01 = make_float2(win_at<XS>(s_x, hist, in, HC, xq + (4 * q) * ch),
+                                           win_at<XS>(s_x, hist, in, HC, xq + (4 * q + 1) * ch));
+            const float2 x23 = make_float2(win_at<XS>(s_x, hist, in, HC, xq + (4 * q + 2) * ch),
+                                           win_at<XS>(s_x, hist, in, HC, xq + (4 * q + 3) * ch));
+            // tap t = tb * TB + 4 q + e belongs to zmm lane t % 16 (TB is a multiple of 16)
+            ffma2(acc1[(2 * q) & 7], make_float2(a.x, a.y), x01);
+            ffma2(acc2[(2 * q) & 7], make_float2(b.x, b.y), x01);
+            ffma2(acc1[(2 * q + 1) & 7], make_float2(a.z, a.w), x23);
+            ffma2(acc2[(2 * q + 1) & 7], make_float2(b.z, b.w), x23);
+        }
+        __syncwarp();
+    }
+    // blend per lane (unfused mul, mul, add), then the halving tree of _mm512_reduce_add_ps
+    const float frac = s_frac[fg - k0];
+    const float omf = __fsub_rn(1.0f, frac);
+    const float2 omf2 = make_float2(omf, omf), frac2 = make_float2(frac, frac);
+    float2 t[8];
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+        // products packed, sums scalar: ptxas contracts mul.f32x2 + add.f32x2 into a packed FMA,
+        // the reference's blend is unfused (avx512.rs:41-45)
+        const float2 m1 = fmul2(acc1[l], omf2), m2 = fmul2(acc2[l], frac2);
+        t[l] = make_float2(__fadd_rn(m1.x, m2.x), __fadd_rn(m1.y, m2.y));
+    }
+#pragma unroll
+    for (int l = 0; l < 4; ++l) t[l] = fadd2(t[l], t[l + 4]);      // lanes l += l + 8
+#pragma unroll
+    for (int l = 0; l < 2; ++l) t[l] = fadd2(t[l], t[l + 2]);      // l += l + 4
+    t[0] = fadd2(t[0], t[1]);                                       // l += l + 2
+    const float y = __fadd_rn(t[0].x, t[0].y);                      // l += l + 1
+    if (valid) out[idx] = y;
+}
+
+// The serial part, one call per WARP (lane 0 works: calls of different sizes take different paths
+// through the planner, 32 of them in one warp would run one after the other): exact phase plan of
+// the call (planner.h) from the stream's state -> result record, plan segments, new scalar state.
+// All calls of a submit are planned at the same time instead of one after the other at the head
+// of their convolution CTAs.
+template <int TAPS>
+__global__ void __launch_bounds__(256) submit_plan_kernel(const SubmitJob *jobs, SubmitResult *results, uint32_t n_jobs,
+                                                          StreamStateDev st, double ratio, PlanSeg *seg_store) {
+    const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (j >= n_jobs || (threadIdx.x & 31u) != 0) return;
+    const SubmitJob job = jobs[j];
+    PlanState s;
+    s.position = st.position[job.stream];
+    s.available = st.hist_len[job.stream];
+    const uint32_t h0 = s.available;
+    SmemSink sink{seg_store + (size_t)j * kSubmitSegs, 0u, 0u};
+    DivCache dc;
+    div_cache_reset(dc);
+    const CallResult r = plan_call(s, ratio, (uint32_t)TAPS, job.in_frames, job.cap_frames, sink, dc);
+    const uint32_t status = sink.n > kSubmitSegs ? 1u : 0u;
+    st.position[job.stream] = s.position;        // resampler_fir.rs:602
+    st.hist_len[job.stream] = s.available;       // :601
+    SubmitResult res;
+    res.position = s.position;
+    res.copied = r.copied;
+    res.produced = status ? 0u : r.produced;
+    res.available = s.available;
+    res.status = status;
+    res.hist0 = h0;
+    res.n_seg = sink.n < kSubmitSegs ? sink.n : kSubmitSegs;
+    results[j] = res;
+}
+
+template <int TAPS>
+__global__ void __launch_bounds__(kTpThreads) submit_fused_tp_kernel(const SubmitJob *jobs, const SubmitResult *results,
+                                                                     const float *coeffs,
+                                                                     const PlanSeg *seg_store, uint32_t ch,
+                                                                     uint32_t rows_per_warp, uint32_t xw_vals) {
+    constexpr int TB = TAPS < kTpTapBlock ? TAPS : kTpTapBlock;
+    constexpr int CS = TB + 4;
+    extern __shared__ __align__(16) float sm_tp[];
+    float *s_c = sm_tp;                                            // [4 warps][rows_per_warp][2][CS]
+    float *s_x = sm_tp + 4u * rows_per_warp * 2u * CS;             // [xw_vals]
+    __shared__ PlanSeg s_segs[kSubmitSegs];
+    __shared__ int32_t s_v[kSuper];
+    __shared__ float s_frac[kSuper];
+    __shared__ uint16_t s_p1[kSuper];
+
+    const SubmitJob job = jobs[blockIdx.x];
+    const SubmitResult res = results[blockIdx.x];        // written by submit_plan_kernel
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    const uint32_t H = res.hist0;
+    const int64_t HC = (int64_t)H * ch;                           // values of live history
+    const float *hist = job.hist + ((int64_t)kHistFrames * ch - HC);   // hist[e] = value e of [history | input]
+    const float *in = job.in;
+    const uint32_t n_win = (H + job.in_frames) * ch;
+    const bool xs = n_win <= xw_vals;
+    const uint32_t produced = res.status ? 0u : res.produced, n_seg = res.n_seg;
+    if (tid < n_seg) s_segs[tid] = seg_store[(size_t)blockIdx.x * kSubmitSegs + tid];
+    if (xs) {
+        // the call's input window, four independent loads in flight per thread
+        for (uint32_t i0 = tid; i0 < n_win; i0 += 4u * kTpThreads) {
+            float xv[4];
+#pragma unroll
+            for (uint32_t u = 0; u < 4; ++u) {
+                const uint32_t i = i0 + u * kTpThreads;
+                xv[u] = i < n_win ? ((int64_t)i < HC ? __ldg(hist + i) : __ldg(in + ((int64_t)i - HC))) : 0.0f;
+            }
+#pragma unroll
+            for (uint32_t u = 0; u < 4; ++u) {
+                const uint32_t i = i0 + u * kTpThreads;
+                if (i < n_win) s_x[i] = xv[u];
+            }
+        }
+    }
+    __syncthreads();
+    float *cw = s_c + (size_t)warp * rows_per_warp * 2u * CS;
+
+    for (uint32_t k0 = 0; k0 < produced; k0 += kSuper) {
+        const uint32_t nf = min(kSuper, produced - k0);
+        // ---- per-frame plan of this pass ----
+        for (uint32_t i = tid; i < nf; i += kTpThreads) {
+            const uint32_t o = k0 + i;
+            uint32_t lo = 0, hi = n_seg;
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (s_segs[mid].out0 <= o) lo = mid; else hi = mid;
+            }
+            const PlanSeg sg = s_segs[lo];
+            const double pos = bits2d(sg.base_bits + (int64_t)(o - sg.out0) * sg.step_bits);
+            const PhasePoint pp = phase_point(pos);
+            s_v[i] = (int32_t)pp.off;
+            s_p1[i] = (uint16_t)pp.phase1;
+            s_frac[i] = pp.frac;
+        }
+        __syncthreads();
+        // ---- blocks of 32 output values, warps independent ----
+        const uint32_t v0 = k0 * ch, n_vals = (k0 + nf) * ch;
+        for (uint32_t idx0 = v0 + warp * 32u; idx0 < n_vals; idx0 += kTpThreads) {
+            if (xs) tp_block<TAPS, true>(idx0, n_vals, k0, ch, s_v, s_p1, s_frac, s_x, hist, in, HC, coeffs, cw, job.out, lane);
+            else tp_block<TAPS, false>(idx0, n_vals, k0, ch, s_v, s_p1, s_frac, s_x, hist, in, HC, coeffs, cw, job.out, lane);
+        }
+        __syncthreads();
+    }
+
+    // ---- new history: the last H1 frames of [history | copied input] -> the other buffer ----
+    const int64_t n_keep = (int64_t)res.available * ch;
+    const int64_t e_first = HC + (int64_t)res.copied * ch - n_keep;
+    float *new_hist = job.hist_next + ((int64_t)kHistFrames * ch - n_keep);
+    for (int64_t i = tid; i < n_keep; i += kTpThreads) {
+        const int64_t e = e_first + i;
+        new_hist[i] = e < HC ? hist[e] : in[e - HC];
+    }
+}
+
 }  // namespace
+
+// shared memory of the thread-per-output kernel for this handle geometry and the largest call of the
+// submit; 0 = does not apply
+static size_t tp_smem_bytes(uint32_t taps, uint32_t ch, uint32_t max_in_frames, uint32_t *rows_per_warp,
+                            uint32_t *xw_vals) {
+    if (ch == 0 || ch > 32) return 0;
+    const uint32_t tb = taps < (uint32_t)kTpTapBlock ? taps : (uint32_t)kTpTapBlock, cs = tb + 4;
+    *rows_per_warp = 31u / ch + 2u;
+    const size_t c_bytes = (size_t)4 * *rows_per_warp * 2 * cs * sizeof(float);
+    // window: the call's new input plus the history a stream carries in steady state (taps + a few
+    // frames of look-ahead); a stream holding more than that reads its window from global memory
+    size_t want = ((size_t)max_in_frames + taps + 96u) * ch;
+    const size_t cap = (48u * 1024u) / sizeof(float);
+    if (want > cap) want = 0;           // large calls: no staging, every CTA takes the global path
+    *xw_vals = (uint32_t)want;
+    return c_bytes + want * sizeof(float);
+}
 
 void launch_submit_fused(const SubmitJob *jobs, SubmitResult *results, uint32_t n_jobs, StreamStateDev st,
                          const float *coeffs, double ratio, uint32_t taps, uint32_t channels,
-                         cudaStream_t stream) {
+                         uint32_t max_in_frames, PlanSeg *seg_store, cudaStream_t stream) {
     if (n_jobs == 0) return;
+    uint32_t rpw = 0, xw = 0;
+    const size_t smem = getenv("RSB_SUBMIT_HALFWARP") ? 0 : tp_smem_bytes(taps, channels, max_in_frames, &rpw, &xw);
+    if (smem) {
+        auto go = [&](auto plan, auto kern) {
+            plan<<<(n_jobs + 7) / 8, 256, 0, stream>>>(jobs, results, n_jobs, st, ratio, seg_store);
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            kern<<<n_jobs, kTpThreads, smem, stream>>>(jobs, results, coeffs, seg_store, channels, rpw, xw);
+        };
+        switch (taps) {
+            case 16: go(submit_plan_kernel<16>, submit_fused_tp_kernel<16>); break;
+            case 32: go(submit_plan_kernel<32>, submit_fused_tp_kernel<32>); break;
+            case 64: go(submit_plan_kernel<64>, submit_fused_tp_kernel<64>); break;
+            default: go(submit_plan_kernel<128>, submit_fused_tp_kernel<128>); break;
+        }
+        return;
+    }
     switch (taps) {
         case 16: submit_fused_kernel<16><<<n_jobs, 256, 0, stream>>>(jobs, results, st, coeffs, ratio, channels); break;
         case 32: submit_fused_kernel<32><<<n_jobs, 256, 0, stream>>>(jobs, results, st, coeffs, ratio, channels); break;

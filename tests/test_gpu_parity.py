@@ -666,3 +666,47 @@ def test_config5_share_time_sliced_with_state_carry_matches_oracle():
     batch.close()
     d_in.free()
     d_out.free()
+
+
+@pytest.mark.parametrize("ch,in_hz,out_hz,lat,att,sizes", [
+    (2, 44100, 48000, 3, 1, [0, 1, 100, 512, 513, 1024]),     # 128 taps stereo
+    (2, 48000, 44100, 3, 1, [512]),                           # BASELINE config 1 call shape
+    (8, 96000, 48000, 2, 1, [0, 64, 512, 700]),               # 64 taps, 8 channels, ratio 2
+    (3, 44100, 48000, 0, 0, [7, 100, 333]),                   # odd channel count, 16 taps
+    (1, 48000, 8000, 1, 2, [160, 480, 960]),                  # ratio 6
+    (1, 8000, 48000, 3, 1, [1, 80, 160]),                     # ratio 1/6, 128 taps
+    (2, 1000003, 999983, 2, 1, [512, 4096, 5000]),            # near-unity arbitrary rates, > capacity offers
+])
+def test_fused_submit_configurations_bit_exact(ch, in_hz, out_hz, lat, att, sizes):
+    """The single-launch submit kernels (thread-per-output variant, fir_submit.cu) over channel
+    counts, tap counts and ratios: every call's (consumed, produced) and every sample equal the
+    oracle bit for bit, per-stream call sizes differing, small output capacities included."""
+    from resampler_b200.fir import MEM_DEVICE, DeviceBuffer
+    n = 20
+    rng = np.random.default_rng(ch * 1000 + lat)
+    batch = FirBatch(n, ch, in_hz, out_hz, Latency(lat), Attenuation(att), kernel=Kernel.AUTO)
+    refs = [O.OracleFir(ch, in_hz, out_hz, lat, att) for _ in range(n)]
+    bso = batch.buffer_size_output()
+    mx = max(sizes)
+    d_in = DeviceBuffer(0, n * max(mx, 1) * ch)
+    d_out = DeviceBuffer(0, n * bso)
+    for it in range(10):
+        sz = [int(rng.choice(sizes)) for _ in range(n)]
+        # every third round offers a small output buffer (capacity-limited calls, :542-545)
+        cap = [bso if (it % 3 or s % 2) else 24 * ch for s in range(n)]
+        ins = [noise(rng, s * ch) for s in sz]
+        for s in range(n):
+            if sz[s]:
+                d_in.upload(ins[s], s * mx * ch)
+        cons, prod = batch.submit_ptrs([d_in.ptr + 4 * s * mx * ch for s in range(n)], [x.size for x in ins],
+                                       [d_out.ptr + 4 * s * bso for s in range(n)], cap, memspace=MEM_DEVICE)
+        assert batch.last_kernel() == Kernel.EXACT
+        for s in range(n):
+            o = np.zeros(cap[s], np.float32)
+            _, c, p = refs[s].resample(ins[s], o)
+            assert (cons[s], prod[s]) == (c, p), (it, s)
+            if p:
+                assert np.array_equal(bits(d_out.download(p, s * bso)), bits(o[:p])), (it, s)
+    batch.close()
+    d_in.free()
+    d_out.free()

@@ -28,9 +28,12 @@ out_lens = (C.c_size_t * n)(*([bso] * n))
 for reps in (20, 200):
     b.sync()
     t0 = time.time()
+    b.timer_start()
     for _ in range(reps):
         cons, prod = b.submit_ptrs(ins, in_lens, outs, out_lens, memspace=MEM_DEVICE, flags=FLAG_ASYNC)
+    dev_ms = b.timer_stop()
     b.sync()
     dt = time.time() - t0
 print(f"{n} streams x {ch} ch, {in_hz}->{out_hz}, {call}-frame calls, kernel {b.last_kernel().name}: "
-      f"{dt / reps * 1e3:.3f} ms per submit, {n * prod[0] / (dt / reps) / 1e6:.1f} Msamples/s out")
+      f"{dt / reps * 1e6:.1f} us per submit wall, {dev_ms / reps * 1e3:.1f} us device (events around the loop), "
+      f"{n * prod[0] / (dt / reps) / 1e6:.1f} Msamples/s out (wall)")
