@@ -50,10 +50,18 @@ unsafe extern "C" {
                            out_capacities: *const usize, produced: *mut usize, memspace: c_int,
                            flags: u32) -> c_int;
     fn rsb_fir_sync(h: *mut RsbFir) -> c_int;
+    fn rsb_fir_cuda_stream(h: *const RsbFir) -> *mut c_void;
+    fn rsb_fir_host_pipeline_stats(h: *const RsbFir, batches: *mut u64, slices: *mut u64) -> c_int;
     fn rsb_alloc_pinned(bytes: usize) -> *mut c_void;
     fn rsb_free_pinned(p: *mut c_void);
+    fn rsb_alloc_device(device: c_int, bytes: usize) -> *mut c_void;
+    fn rsb_free_device(device: c_int, p: *mut c_void);
+    fn rsb_memcpy(device: c_int, dst: *mut c_void, src: *const c_void, bytes: usize, kind: c_int) -> c_int;
     fn rsb_status_string(status: c_int) -> *const std::os::raw::c_char;
+    fn rsb_last_error() -> *const std::os::raw::c_char;
 }
+
+const RSB_FLAG_ASYNC: u32 = 1;
 
 fn latency_code(l: Latency) -> c_int {
     match l { Latency::Sample8 => 0, Latency::Sample16 => 1, Latency::Sample32 => 2, Latency::Sample64 => 3 }
@@ -67,7 +75,119 @@ fn map_err(rc: c_int) -> Result<(), ResampleError> {
         1 => Err(ResampleError::InvalidInputBufferSize),
         2 => Err(ResampleError::InvalidOutputBufferSize),
         // CUDA / device failures have no counterpart in the reference's error type
-        other => panic!("resampler-cuda: device error {other}"),
+        other => {
+            let (name, detail) = unsafe {
+                (std::ffi::CStr::from_ptr(rsb_status_string(other)).to_string_lossy().into_owned(),
+                 std::ffi::CStr::from_ptr(rsb_last_error()).to_string_lossy().into_owned())
+            };
+            panic!("resampler-cuda: {name} ({other}): {detail}")
+        }
+    }
+}
+
+/// Page-locked host memory of `len` f32 values (RAII over `rsb_alloc_pinned`).  Host-memspace calls
+/// on pinned buffers copy at the full PCIe rate and let `process_batch` overlap the copies of one
+/// time slice with the kernels of another; pageable slices work too, slower.
+pub struct PinnedBuffer {
+    ptr: *mut f32,
+    len: usize,
+}
+// plain memory owned by the value; no thread affinity
+unsafe impl Send for PinnedBuffer {}
+unsafe impl Sync for PinnedBuffer {}
+impl PinnedBuffer {
+    pub fn new(len: usize) -> Option<Self> {
+        let ptr = unsafe { rsb_alloc_pinned(len * std::mem::size_of::<f32>()) } as *mut f32;
+        if ptr.is_null() { return None; }
+        unsafe { std::ptr::write_bytes(ptr, 0, len) };
+        Some(Self { ptr, len })
+    }
+    pub fn len(&self) -> usize { self.len }
+    pub fn is_empty(&self) -> bool { self.len == 0 }
+}
+impl std::ops::Deref for PinnedBuffer {
+    type Target = [f32];
+    fn deref(&self) -> &[f32] { unsafe { std::slice::from_raw_parts(self.ptr, self.len) } }
+}
+impl std::ops::DerefMut for PinnedBuffer {
+    fn deref_mut(&mut self) -> &mut [f32] { unsafe { std::slice::from_raw_parts_mut(self.ptr, self.len) } }
+}
+impl Drop for PinnedBuffer {
+    fn drop(&mut self) { unsafe { rsb_free_pinned(self.ptr as *mut c_void) } }
+}
+
+/// `len` f32 values of device memory on one GPU (RAII over `rsb_alloc_device`), for callers that keep
+/// their audio resident on the device between submits.
+pub struct DeviceBuffer {
+    ptr: *mut f32,
+    len: usize,
+    device: i32,
+}
+unsafe impl Send for DeviceBuffer {}
+impl DeviceBuffer {
+    pub fn new(device: i32, len: usize) -> Option<Self> {
+        let ptr = unsafe { rsb_alloc_device(device, len * std::mem::size_of::<f32>()) } as *mut f32;
+        if ptr.is_null() { None } else { Some(Self { ptr, len, device }) }
+    }
+    pub fn len(&self) -> usize { self.len }
+    pub fn is_empty(&self) -> bool { self.len == 0 }
+    /// synchronous host -> device copy into `[offset, offset + src.len())`
+    pub fn upload(&mut self, offset: usize, src: &[f32]) {
+        assert!(offset + src.len() <= self.len);
+        let rc = unsafe {
+            rsb_memcpy(self.device, self.ptr.add(offset) as *mut c_void, src.as_ptr() as *const c_void,
+                       std::mem::size_of_val(src), 0)
+        };
+        assert!(rc == 0, "resampler-cuda: upload failed ({rc})");
+    }
+    /// synchronous device -> host copy of `[offset, offset + dst.len())`
+    pub fn download(&self, offset: usize, dst: &mut [f32]) {
+        assert!(offset + dst.len() <= self.len);
+        let rc = unsafe {
+            rsb_memcpy(self.device, dst.as_mut_ptr() as *mut c_void, self.ptr.add(offset) as *const c_void,
+                       std::mem::size_of_val(dst), 1)
+        };
+        assert!(rc == 0, "resampler-cuda: download failed ({rc})");
+    }
+}
+impl Drop for DeviceBuffer {
+    fn drop(&mut self) { unsafe { rsb_free_device(self.device, self.ptr as *mut c_void) } }
+}
+
+/// Totals of one `process_batch` job.
+#[derive(Clone, Copy, Debug, Default, PartialEq, Eq)]
+pub struct BatchCounts {
+    /// input values consumed (always the whole input unless the output capacity ran out)
+    pub consumed: usize,
+    /// output values written
+    pub produced: usize,
+    /// `resample()` calls the canonical loop made
+    pub calls: u32,
+}
+
+/// Work submitted with [`FirBatch::submit_device_async`]; borrows the handle and the buffers until
+/// [`PendingSubmit::sync`] (or drop) has waited for the GPU, so neither can be touched early.
+pub struct PendingSubmit<'a> {
+    batch: &'a mut FirBatch,
+    counts: Vec<(usize, usize)>,
+    consumed: Vec<usize>,
+    produced: Vec<usize>,
+    done: bool,
+    _buffers: std::marker::PhantomData<&'a mut DeviceBuffer>,
+}
+impl PendingSubmit<'_> {
+    /// Waits for the submit (and everything queued before it on the handle's CUDA stream) and
+    /// returns `(consumed, produced)` per listed stream.
+    pub fn sync(mut self) -> Result<Vec<(usize, usize)>, ResampleError> {
+        self.done = true;
+        map_err(unsafe { rsb_fir_sync(self.batch.h) })?;
+        self.counts = self.consumed.iter().copied().zip(self.produced.iter().copied()).collect();
+        Ok(std::mem::take(&mut self.counts))
+    }
+}
+impl Drop for PendingSubmit<'_> {
+    fn drop(&mut self) {
+        if !self.done { unsafe { rsb_fir_sync(self.batch.h) }; }
     }
 }
 
@@ -76,7 +196,10 @@ pub struct FirBatch {
     h: *mut RsbFir,
     channels: usize,
 }
-// one caller at a time per handle (`&mut self`), handles may move between threads
+// Send audit: the handle owns its CUDA streams, events and device buffers and binds the device
+// itself at the top of every entry point (`cudaSetDevice`), so it may move between threads; every
+// mutating entry point takes `&mut self`, i.e. one caller at a time, which is all the library asks
+// for (it is NOT `Sync`: the C side keeps per-handle host mirrors without locks).
 unsafe impl Send for FirBatch {}
 
 impl FirBatch {
@@ -153,6 +276,67 @@ impl FirBatch {
         Ok(produced)
     }
     pub fn channels(&self) -> usize { self.channels }
+
+    /// The canonical caller loop (`resample()` on `call_len` values at a time until the input is
+    /// used up, resample/src/main.rs:226-254) for one job per stream, host slices in and out.
+    /// Long equally sized jobs on pinned buffers ([`PinnedBuffer`]) run as a pipeline of time
+    /// slices inside the library: host->device copy, kernels and device->host copy overlap.
+    pub fn process_batch(&mut self, inputs: &[&[f32]], call_len: usize, outputs: &mut [&mut [f32]])
+                         -> Result<Vec<BatchCounts>, ResampleError> {
+        assert_eq!(inputs.len(), outputs.len());
+        let n = inputs.len();
+        let in_ptrs: Vec<*const f32> = inputs.iter().map(|s| s.as_ptr()).collect();
+        let in_lens: Vec<usize> = inputs.iter().map(|s| s.len()).collect();
+        let out_ptrs: Vec<*mut f32> = outputs.iter_mut().map(|s| s.as_mut_ptr()).collect();
+        let out_caps: Vec<usize> = outputs.iter().map(|s| s.len()).collect();
+        let (mut c, mut p, mut k) = (vec![0usize; n], vec![0usize; n], vec![0u32; n]);
+        map_err(unsafe {
+            rsb_fir_process_batch(self.h, n as u32, std::ptr::null(), in_ptrs.as_ptr(), in_lens.as_ptr(),
+                                  call_len, 0, out_ptrs.as_ptr(), out_caps.as_ptr(), c.as_mut_ptr(),
+                                  p.as_mut_ptr(), k.as_mut_ptr(), RSB_MEM_HOST, 0)
+        })?;
+        Ok((0..n).map(|i| BatchCounts { consumed: c[i], produced: p[i], calls: k[i] }).collect())
+    }
+
+    /// One `resample()` call per listed stream on DEVICE-resident buffers, enqueued on the handle's
+    /// CUDA stream without waiting: `inputs[i]` / `outputs[i]` are `(buffer, offset, len)` in values.
+    /// The returned guard keeps the handle and the buffers borrowed until it has been synchronised.
+    pub fn submit_device_async<'a>(&'a mut self, streams: &[u32], inputs: &[(&'a DeviceBuffer, usize, usize)],
+                                   outputs: &mut [(&'a mut DeviceBuffer, usize, usize)])
+                                   -> Result<PendingSubmit<'a>, ResampleError> {
+        assert!(streams.len() == inputs.len() && inputs.len() == outputs.len());
+        let n = inputs.len();
+        for (b, off, len) in inputs.iter() { assert!(off + len <= b.len()); }
+        for (b, off, len) in outputs.iter() { assert!(off + len <= b.len()); }
+        let in_ptrs: Vec<*const f32> = inputs.iter().map(|(b, off, _)| unsafe { b.ptr.add(*off) as *const f32 }).collect();
+        let in_lens: Vec<usize> = inputs.iter().map(|(_, _, len)| *len).collect();
+        let out_ptrs: Vec<*mut f32> = outputs.iter().map(|(b, off, _)| unsafe { b.ptr.add(*off) }).collect();
+        let out_lens: Vec<usize> = outputs.iter().map(|(_, _, len)| *len).collect();
+        let mut pending = PendingSubmit { batch: self, counts: Vec::new(), consumed: vec![0usize; n],
+                                          produced: vec![0usize; n], done: false,
+                                          _buffers: std::marker::PhantomData };
+        // the count vectors live in the guard: the library writes them at sync() at the latest
+        map_err(unsafe {
+            rsb_fir_submit_batch(pending.batch.h, n as u32, streams.as_ptr(), in_ptrs.as_ptr(), in_lens.as_ptr(),
+                                 out_ptrs.as_ptr(), out_lens.as_ptr(), pending.consumed.as_mut_ptr(),
+                                 pending.produced.as_mut_ptr(), RSB_MEM_DEVICE, RSB_FLAG_ASYNC)
+        })?;
+        Ok(pending)
+    }
+
+    /// Waits for everything enqueued on this handle.
+    pub fn sync(&mut self) -> Result<(), ResampleError> { map_err(unsafe { rsb_fir_sync(self.h) }) }
+
+    /// The handle's `cudaStream_t` as an opaque pointer, for callers that order their own CUDA
+    /// work (copies, kernels) against the submits.
+    pub fn cuda_stream(&self) -> *mut c_void { unsafe { rsb_fir_cuda_stream(self.h) } }
+
+    /// `(batches, slices)` of host-memspace `process_batch` calls that ran pipelined.
+    pub fn host_pipeline_stats(&self) -> (u64, u64) {
+        let (mut b, mut s) = (0u64, 0u64);
+        unsafe { rsb_fir_host_pipeline_stats(self.h, &mut b, &mut s) };
+        (b, s)
+    }
 }
 impl Drop for FirBatch {
     fn drop(&mut self) { unsafe { rsb_fir_destroy(self.h) } }
@@ -187,11 +371,4 @@ impl ResamplerFir {
     pub fn delay(&self) -> usize { self.inner.delay() }
     /// resampler_fir.rs:638-642
     pub fn reset(&mut self) { self.inner.reset(Some(0)) }
-}
-
-#[allow(dead_code)]
-fn _unused() {
-    // keeps the remaining bindings referenced (device-memory batch entry points, pinned helpers)
-    let _ = (rsb_fir_process_batch as usize, rsb_fir_sync as usize, rsb_alloc_pinned as usize,
-             rsb_free_pinned as usize, rsb_status_string as usize, RSB_MEM_DEVICE);
 }
