@@ -600,6 +600,33 @@ def run_ours(args):
                "kind": "port",
                "sample": f"{cs} of the GPU's own streams x {cframes / IN_HZ:.1f} s, 512-frame calls, "
                          f"one stream per thread, repeated {repeats}x (~{t_tot:.1f} s of CPU work)"}
+    # ---- single-stream drop-in call: latency of ONE resample() (512 frames) next to the CPU's ----
+    latency = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            from resampler_b200 import Attenuation, Latency, ResamplerFir
+            r1 = ResamplerFir.new_from_hz(CHANNELS, IN_HZ, OUT_HZ, Latency(LATENCY), Attenuation(ATTENUATION))
+            x = host_synthetic(1, CALL_FRAMES)[0]
+            o = np.zeros(r1.buffer_size_output(), np.float32)
+            for _ in range(20):
+                r1.resample(x, o)
+            ts = []
+            for _ in range(300):
+                t0 = time.perf_counter()
+                r1.resample(x, o)
+                ts.append(time.perf_counter() - t0)
+            r1.close()
+            one = host_synthetic(1, IN_HZ * 10)
+            _, p1, s1 = cpu_reference_run(one, IN_HZ * 10, 1)
+            n_calls_cpu = (IN_HZ * 10 + CALL_FRAMES - 1) // CALL_FRAMES
+            latency = {"call": f"rsb_fir_resample, {CALL_FRAMES} stereo frames, host slices, one stream",
+                       "gpu_us_median": round(float(np.median(ts)) * 1e6, 1),
+                       "gpu_us_p95": round(float(np.percentile(ts, 95)) * 1e6, 1),
+                       "cpu_us_per_call": round(s1 / n_calls_cpu * 1e6, 2),
+                       "note": "a single stream is latency-bound on a GPU (copy in, 5 launches, copy out); "
+                               "the batched entry points are the product, this is the drop-in's cost"}
+        except Exception as e:
+            latency = {"error": str(e)[:200]}
     head_calls, head_launches = R["calls"], R["launches"]
     d_in.free()
     R["d_out"].free()
@@ -651,7 +678,7 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(head_launches),
             "clocks": clocks,
             "produced_samples_per_step_per_gpu": R["produced"],
-            "other_configs": legs, "strong_scaling": strong,
+            "other_configs": legs, "strong_scaling": strong, "single_stream_latency": latency,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

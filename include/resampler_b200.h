@@ -204,7 +204,9 @@ int rsb_fir_last_pcm_fused(const rsb_fir *h);
 /* device time (ms, CUDA events) of the format-step kernel of the most recent PCM batch */
 int rsb_fir_last_ingest_ms(rsb_fir *h, float *ms);
 
-/* completes RSB_FLAG_ASYNC work (writes the deferred counts) and waits for the GPU */
+/* completes RSB_FLAG_ASYNC work (writes the deferred counts) and waits for the GPU.  A failure of an
+ * asynchronous submit (plan workspace overflow, output capacity) that surfaced while a LATER submit
+ * was being started does not abort that later submit: it is returned here, once. */
 int rsb_fir_sync(rsb_fir *h);
 
 /* per-call (consumed, produced) values of job `job` of the last synchronous batch

@@ -138,6 +138,8 @@ struct rsb_fir {
     std::vector<uint64_t> m_pending;   // submit number whose read-back will refresh the mirror
     uint64_t next_cohort = 1;
     uint64_t launches = 0;
+    int deferred_rc = 0;               // failure of an asynchronous submit found while starting a later one
+    std::string deferred_msg;
     cudaStream_t plan_stream = nullptr;   // plan / tile kernels and the state scalars
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_sync = nullptr;
     // ring of event pairs bracketing the convolution kernel of the most recent batches
@@ -360,9 +362,15 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
         if (rf != RSB_OK) return rf;
     }
     Workspace &W = h->ws[h->submits & 1];
-    // this workspace was last used two submits ago: collect its counts, wait for its kernels
+    // this workspace was last used two submits ago: collect its counts, wait for its kernels.  A
+    // failure of that older (asynchronous) submit is not this batch's: it is kept for
+    // rsb_fir_sync() and the current batch still runs.
     int rc = finalize_pending(h, W);
-    if (rc != RSB_OK) return rc;
+    if (rc != RSB_OK && h->deferred_rc == RSB_OK) {
+        h->deferred_rc = rc;
+        h->deferred_msg = g_last_error;
+    }
+    rc = RSB_OK;
     RSB_CUDA(cudaEventSynchronize(W.ev_done));
     const uint32_t n = (uint32_t)jobs.size();
     const uint32_t ch = h->channels;
@@ -436,8 +444,11 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
         U.call_frames = k.call_frames;
         U.cap_frames = k.cap_frames;
         U.single_call = k.single;
-        const double out_bound_d =
+        double out_bound_d =
             std::ceil(((double)rsb::kInputCapacity + (double)k.total_frames) / h->ratio) + 2.0;
+        // a single call produces at most its output capacity (strong up-sampling: the frames the
+        // buffered input could yield may be billions while the caller's buffer is small)
+        if (k.single) out_bound_d = std::min(out_bound_d, (double)k.cap_frames + 2.0);
         if (out_bound_d > 4.0e9 || k.total_frames > 0x7ff00000ull)
             return fail(RSB_ERR_INVALID_ARGUMENT, "too many frames per stream in one batch; split it");
         const uint64_t out_bound = (uint64_t)out_bound_d;
@@ -1716,6 +1727,13 @@ int rsb_fir_sync(rsb_fir *h) {
     int rc = finalize_all(h);
     const int rf = finalize_fused_all(h);
     if (rc == RSB_OK) rc = rf;
+    if (h->deferred_rc != RSB_OK) {      // an older asynchronous submit failed: reported here, once
+        if (rc == RSB_OK) {
+            rc = h->deferred_rc;
+            g_last_error = h->deferred_msg;
+        }
+        h->deferred_rc = RSB_OK;
+    }
     RSB_CUDA(cudaStreamSynchronize(h->plan_stream));
     RSB_CUDA(cudaStreamSynchronize(h->stream));
     if (h->pipe.s_out) RSB_CUDA(cudaStreamSynchronize(h->pipe.s_out));

@@ -1222,7 +1222,7 @@ void launch_tc2_gmat(const UnitDev *units, const PlanEntry *entries, const float
 
 // role layouts that are compiled (ST, ET, XS); index = Tc2Params::variant
 struct Variant { uint32_t st, et, xs; };
-static const Variant kVariants[] = {{3, 2, 6}, {2, 1, 4}, {2, 2, 4}, {4, 1, 8}, {2, 1, 8}, {3, 1, 6}};
+static const Variant kVariants[] = {{3, 2, 6}, {2, 1, 4}, {2, 2, 4}, {4, 1, 8}, {2, 1, 8}, {3, 1, 6}, {3, 2, 3}};
 constexpr uint32_t kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
 uint32_t tc2_g_stages(uint32_t channels, uint32_t taps, double ratio, uint32_t variant) {
@@ -1270,6 +1270,7 @@ bool launch_conv_tc2(const Tc2Params &p, const CUtensorMap &tmap_in, const CUten
             case 2: launch(conv_tc2_kernel<2, 0, 2, 2, 2, 4>, thr); break;
             case 3: launch(conv_tc2_kernel<2, 0, 2, 4, 1, 8>, thr); break;
             case 4: launch(conv_tc2_kernel<2, 0, 2, 2, 1, 8>, thr); break;
+            case 6: launch(conv_tc2_kernel<2, 0, 2, 3, 2, 3>, thr); break;
             default: launch(conv_tc2_kernel<2, 0, 2, 3, 1, 6>, thr); break;
         }
         return true;

@@ -710,3 +710,20 @@ def test_fused_submit_configurations_bit_exact(ch, in_hz, out_hz, lat, att, size
     batch.close()
     d_in.free()
     d_out.free()
+
+
+def test_strong_upsampling_single_call_is_bounded_by_the_output_buffer():
+    """ADVICE: the plan workspace of a single resample() call is bounded by the caller's output
+    capacity, not by what 4096 buffered frames could yield: 8 Hz -> 48 kHz (ratio 1.7e-4) used to be
+    refused as 'too many frames'; the reference produces min(capacity, available) frames."""
+    ch, in_hz, out_hz, lat = 1, 8, 48000, 0
+    r = ResamplerFir.new_from_hz(ch, in_hz, out_hz, Latency(lat), Attenuation.Db60)
+    ref = O.OracleFir(ch, in_hz, out_hz, lat, 0)
+    rng = np.random.default_rng(3)
+    for n_in, cap in ((64, 4096), (0, 1000), (5, 12194)):
+        x = noise(rng, n_in)
+        o1, o2 = np.zeros(cap, np.float32), np.zeros(cap, np.float32)
+        c, p = r.resample(x, o1)
+        _, c2, p2 = ref.resample(x, o2)
+        assert (c, p) == (c2, p2)
+        assert np.array_equal(bits(o1[:p]), bits(o2[:p2]))
