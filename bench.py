@@ -266,11 +266,15 @@ EXTRA_LEGS = {
 
 
 def source_stamp():
-    """sha256 over the tensor kernel's sources: ties profiles/conv_traffic.json to the code."""
+    """sha256 over the tensor kernel's sources with // comments and blank lines stripped: ties
+    profiles/conv_traffic.json to the CODE it was measured on (editing a comment keeps the stamp)."""
     import hashlib
     h = hashlib.sha256()
     for f in ("fir_tc2.cu", "sm100_ptx.cuh", "fir_kernels.h"):
-        h.update((ROOT / "resampler_b200" / "csrc" / f).read_bytes())
+        for line in (ROOT / "resampler_b200" / "csrc" / f).read_text().splitlines():
+            code = line.split("//", 1)[0].rstrip()
+            if code.strip():
+                h.update(code.encode() + b"\n")
     return h.hexdigest()[:16]
 
 

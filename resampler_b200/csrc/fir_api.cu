@@ -878,10 +878,16 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
         T.channels = ch;
         const uint32_t mpg = rsb::tc2_rows_per_group() / ch;
         T.groups = (n + mpg - 1) / mpg;
-        // a run of consecutive tiles is one work item: long enough to amortise filling the input
-        // ring (~4 tiles), short enough that every CTA gets several items and the tail is short
-        const uint64_t want = (tc2_tiles * T.groups) / ((uint64_t)h->sm_count * 8u) + 1;
-        T.run_tiles = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 16), 96);
+        // A run of consecutive tiles is one work item: long enough to amortise filling the input
+        // ring (~4 tiles; measured best at 160-190 tiles), and cut so that the items divide evenly
+        // among the CTAs: k items per CTA (at least 4), n_runs = floor(k * SMs / groups) runs.
+        {
+            const uint64_t total = tc2_tiles * T.groups, sms = (uint64_t)h->sm_count;
+            const uint64_t k = std::max<uint64_t>(4, (total + sms * 85) / (sms * 170));
+            const uint64_t n_runs = std::max<uint64_t>(1, k * sms / T.groups);
+            const uint64_t rt = (tc2_tiles + n_runs - 1) / n_runs;
+            T.run_tiles = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(rt, 16), 256);
+        }
         if (getenv("RSB_TC_RUN_TILES")) T.run_tiles = (uint32_t)atoi(getenv("RSB_TC_RUN_TILES"));
         T.kt_max = rsb::tc2_kt_extent(h->taps, h->ratio);
         T.issuers = rsb::tc2_issuers(h->taps, h->ratio);
@@ -890,7 +896,9 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
         T.prefetch_chunks = getenv("RSB_TC_PREFETCH") ? (uint32_t)atoi(getenv("RSB_TC_PREFETCH")) : 0u;
         T.ablate = getenv("RSB_TC_ABLATE") ? (uint32_t)atoi(getenv("RSB_TC_ABLATE")) : 0u;
         T.out_scale = rsb::tc2_out_scale();
-        T.epi_split = getenv("RSB_TC_EPI_SPLIT") ? (uint32_t)atoi(getenv("RSB_TC_EPI_SPLIT")) : 0u;
+        // both epilogue teams drain every tile, one column half each: the accumulator is back with
+        // the issuers one tcgen05.ld after the tile completes
+        T.epi_split = getenv("RSB_TC_EPI_SPLIT") ? (uint32_t)atoi(getenv("RSB_TC_EPI_SPLIT")) : 1u;
         T.hint_crit = getenv("RSB_TC_HINT_CRIT") ? (uint32_t)atoi(getenv("RSB_TC_HINT_CRIT")) : 0x989680u;
         T.hint_other = getenv("RSB_TC_HINT_OTHER") ? (uint32_t)atoi(getenv("RSB_TC_HINT_OTHER")) : 0x989680u;
         if (getenv("RSB_TC_GSTAGES")) T.g_stages = std::min<uint32_t>(T.g_stages, (uint32_t)atoi(getenv("RSB_TC_GSTAGES")));

@@ -31,14 +31,17 @@
 //     TMEM rings (ring column == 2 input frames, TMEM lane == row).  The rings ARE the A operands.
 //   * warp 23 (one thread): bulk copies of the tile's [G_hi, G_lo] matrices (prebuilt by
 //     tc2_gmat_kernel in the canonical no-swizzle K-major core-matrix layout) into a stage ring.
-//   * warps 20 and 21: issue the tcgen05.mma (39 per 128-tap tile) for alternate tiles, one
+//   * warps 20 and 21: issue the tcgen05.mma (39+ per 128-tap tile) for alternate tiles, one
 //     accumulator each; ONE tcgen05.commit per tile.
 //   * warp 24 ("janitor", one thread): follows the tile-completion barriers in order and hands the
 //     ring slots no later tile reads back to the splitter (the issuers commit nothing but t_done).
-//   * warps 0-3 and 16-19 (epilogue, two teams on alternate tiles = one accumulator each):
-//     tcgen05.ld of their 32 accumulator lanes, scale, 128B-swizzled staging in shared memory,
-//     TMA tensor STORES (one warp stores its own members' boxes; no CTA-wide barrier anywhere in
-//     the steady state).  The store map clips partial tiles and capacity.
+//   * warps 0-3 and 16-19 (epilogue, two teams; team h drains column half h of EVERY tile, so an
+//     accumulator is back with the issuers one tcgen05.ld after its tile completes):
+//     tcgen05.ld of the warp's 32 accumulator lanes x 32 columns, scale, then two rounds of 16
+//     frames each through ONE 128B-swizzled staging buffer per warp and TMA tensor STORES (one
+//     warp stores its own members' boxes; no CTA-wide barrier anywhere in the steady state).  The
+//     quarter-tile rounds halve the staging memory, which buys the third G stage for 128 taps.
+//     The store map clips partial tiles and capacity.
 //
 // TMEM map (512 columns x 128 lanes): [0,192) X hi ring (384 frames), [192,384) X lo ring,
 // [384,448) and [448,512) the two accumulators.
@@ -444,7 +447,7 @@ __device__ __forceinline__ void load_chunk(uint32_t base, const float *stage_ptr
     }
 }
 
-template <int CH, int RAW = 0, int SB = 2, int ST = 3, int ET = 2, int XS = 6>
+template <int CH, int RAW = 0, int SB = 2, int ST = 3, int ET = 2, int XS = 6, int QS = 1>
 __global__ void __launch_bounds__(role_threads(ST, ET), 1)
 conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUtensorMap tmap_in,
                 const __grid_constant__ CUtensorMap tmap_out) {
@@ -470,12 +473,16 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
     // bytes, 128B-swizzled, every box 1024-byte aligned
     constexpr uint32_t kBoxBytes = kMpw * 128u < 1024u ? 1024u : kMpw * 128u;
     constexpr uint32_t kHalfBytes = CH * kBoxBytes;
+    // QS: the epilogue stages a QUARTER tile (16 frames) per round in one buffer per warp: half the
+    // staging memory, which buys a third G stage for the 128-tap configurations
+    constexpr bool kQuarter = QS != 0 && CH >= 2 && ET == 2;
+    constexpr uint32_t kWarpStageBytes = kQuarter ? (CH / 2) * kBoxBytes : kHalfBytes;   // x kStageBufs (ET == 1)
     extern __shared__ __align__(1024) uint8_t smem_tc2[];
     __shared__ Smem S;
     const uint32_t g_bytes = P.kt_max * 128u;           // one G half: kt_max/8 K groups x 1024 B
     uint8_t *xst = smem_tc2;                             // [kXStages][kXStageBytes]
     uint8_t *ost = smem_tc2 + kXStages * kXStageBytes;   // [kEpiTeams][4 quadrants][kStageBufs][kHalfBytes]
-    uint8_t *gst = ost + 2 * 4 * kHalfBytes;             // [g_stages]{[2][g_bytes], MMA list}
+    uint8_t *gst = ost + 2 * 4 * kWarpStageBytes;        // [g_stages]{[2][g_bytes], MMA list}
     const uint32_t g_stage_bytes = 2u * g_bytes + kListBytes;
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
@@ -891,7 +898,7 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
         const uint32_t quad = warp & 3u;
         const uint32_t ml = lane / CH, c = lane % CH;       // member inside the warp, channel
         const uint32_t lane_base = (quad * 32u) << 16;
-        const uint32_t sb0 = smem_u32(ost + (team * 4u + quad) * kStageBufs * kHalfBytes);
+        const uint32_t sb0 = smem_u32(ost + (team * 4u + quad) * (kQuarter ? kWarpStageBytes : kStageBufs * kHalfBytes));
         uint32_t h_seq = 0;
         uint32_t d_seq = 0;
         const float out_scale = P.out_scale;
@@ -926,6 +933,55 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
                         if (lane == 0) mbar_arrive(&S.d_empty[b]);
                     }
                     rc.lap(9);
+                    if constexpr (kQuarter) {
+#pragma unroll
+                        for (uint32_t qr = 0; qr < 2; ++qr) {
+                            // the staging buffer's previous store has read it
+                            if (lane == 0) bulk_wait_read<0>();
+                            __syncwarp();
+                            rc.lap(20);
+                            if constexpr (CH == 2) {
+                                // lane pair (member, L) / (member, R): the L lane writes frames 0-7 of
+                                // the quarter (both channels: units 0-3 of the member's box row), the
+                                // R lane frames 8-15 (units 4-7), after exchanging 8 values
+                                float own[8], got[8];
+#pragma unroll
+                                for (uint32_t i = 0; i < 8; ++i) {
+                                    const float keep = __uint_as_float(c ? acc[16 * qr + 8 + i] : acc[16 * qr + i]) * out_scale;
+                                    const float send = __uint_as_float(c ? acc[16 * qr + i] : acc[16 * qr + 8 + i]) * out_scale;
+                                    own[i] = keep;
+                                    got[i] = __shfl_xor_sync(0xffffffffu, send, 1);
+                                }
+                                const uint32_t rb = sb0 + ml * 128u;
+#pragma unroll
+                                for (uint32_t u = 0; u < 4; ++u) {
+                                    const float l0 = c ? got[2 * u] : own[2 * u], r0 = c ? own[2 * u] : got[2 * u];
+                                    const float l1 = c ? got[2 * u + 1] : own[2 * u + 1], r1 = c ? own[2 * u + 1] : got[2 * u + 1];
+                                    sts128(rb + (((c * 4u + u) ^ (ml & 7u)) << 4), l0, r0, l1, r1);
+                                }
+                            } else {
+#pragma unroll
+                                for (uint32_t o = 0; o < 16; ++o) {
+                                    const uint32_t fi = o * CH + c;
+                                    const uint32_t box = fi >> 5, unit = (fi >> 2) & 7u;
+                                    sts32(sb0 + box * kBoxBytes + ml * 128u + ((unit ^ (ml & 7u)) << 4) + (fi & 3u) * 4u,
+                                          __uint_as_float(acc[16 * qr + o]) * out_scale);
+                                }
+                            }
+                            rc.lap(21);
+                            fence_proxy_async();
+                            __syncwarp();
+                            rc.lap(22);
+                            if (lane == 0 && !(P.ablate & 4u)) {
+                                const int32_t f0 = (int32_t)((o_start + hf * 32u + qr * 16u) * CH);   // float coordinate
+#pragma unroll
+                                for (uint32_t bx = 0; bx < (uint32_t)CH / 2u; ++bx)
+                                    tensor_s2g_2d(&tmap_out, f0 + (int32_t)(bx * 32u), m_first, sb0 + bx * kBoxBytes);
+                                bulk_commit();
+                            }
+                        }
+                        continue;
+                    }
                     // the staging buffer's previous stores have read it
                     if (lane == 0) bulk_wait_read<kStageBufs - 1>();
                     __syncwarp();
@@ -1221,14 +1277,18 @@ void launch_tc2_gmat(const UnitDev *units, const PlanEntry *entries, const float
 }
 
 // role layouts that are compiled (ST, ET, XS); index = Tc2Params::variant
-struct Variant { uint32_t st, et, xs; };
-static const Variant kVariants[] = {{3, 2, 6}, {2, 1, 4}, {2, 2, 4}, {4, 1, 8}, {2, 1, 8}, {3, 1, 6}, {3, 2, 3}};
+struct Variant { uint32_t st, et, xs, qs; };
+static size_t epi_stage_bytes(uint32_t channels, const Variant &V) {
+    const size_t box = (32u / channels) * 128u < 1024u ? 1024u : (32u / channels) * 128u;
+    const bool quarter = V.qs && channels >= 2 && V.et == 2;
+    return 2 * 4 * (quarter ? (channels / 2) * box : channels * box);
+}
+static const Variant kVariants[] = {{3, 2, 6, 1}, {2, 1, 4, 0}, {2, 2, 4, 0}, {4, 1, 8, 0}, {2, 1, 8, 0}, {3, 1, 6, 0}, {3, 2, 3, 0}, {3, 2, 6, 0}};
 constexpr uint32_t kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
 uint32_t tc2_g_stages(uint32_t channels, uint32_t taps, double ratio, uint32_t variant) {
     const Variant V = kVariants[variant < kNumVariants ? variant : 0];
-    const size_t half = (size_t)channels * ((32u / channels) * 128u < 1024u ? 1024u : (32u / channels) * 128u);
-    const size_t fixed = (size_t)V.xs * kXStageBytes + 2 * 4 * half + 2048;   // + static barriers
+    const size_t fixed = (size_t)V.xs * kXStageBytes + epi_stage_bytes(channels, V) + 2048;   // + static barriers
     const size_t per_stage = tc2_gmat_bytes_per_tile(taps, ratio);
     const size_t budget = 232448;    // 227 KB per CTA
     size_t n = (budget - fixed) / per_stage;
@@ -1242,8 +1302,7 @@ bool launch_conv_tc2(const Tc2Params &p, const CUtensorMap &tmap_in, const CUten
                      bool leave_sm_free, cudaStream_t stream) {
     const uint32_t variant = p.variant < kNumVariants ? p.variant : 0;
     const Variant V = kVariants[variant];
-    const size_t half = (size_t)p.channels * ((32u / p.channels) * 128u < 1024u ? 1024u : (32u / p.channels) * 128u);
-    const size_t smem = (size_t)V.xs * kXStageBytes + 2 * 4 * half + (size_t)p.g_stages * (2 * p.kt_max * 128u + kListBytes);
+    const size_t smem = (size_t)V.xs * kXStageBytes + epi_stage_bytes(p.channels, V) + (size_t)p.g_stages * (2 * p.kt_max * 128u + kListBytes);
     if (p.g_stages < 2) return false;
     ensure_hang_buffer();
     // one SM is left free when the next submit's (serial) plan kernel may need somewhere to run
@@ -1266,12 +1325,13 @@ bool launch_conv_tc2(const Tc2Params &p, const CUtensorMap &tmap_in, const CUten
         // experiment variants: stereo f32 only
         if (p.channels != 2 || p.raw16) return false;
         switch (variant) {
-            case 1: launch(conv_tc2_kernel<2, 0, 2, 2, 1, 4>, thr); break;
-            case 2: launch(conv_tc2_kernel<2, 0, 2, 2, 2, 4>, thr); break;
-            case 3: launch(conv_tc2_kernel<2, 0, 2, 4, 1, 8>, thr); break;
-            case 4: launch(conv_tc2_kernel<2, 0, 2, 2, 1, 8>, thr); break;
-            case 6: launch(conv_tc2_kernel<2, 0, 2, 3, 2, 3>, thr); break;
-            default: launch(conv_tc2_kernel<2, 0, 2, 3, 1, 6>, thr); break;
+            case 1: launch(conv_tc2_kernel<2, 0, 2, 2, 1, 4, 0>, thr); break;
+            case 2: launch(conv_tc2_kernel<2, 0, 2, 2, 2, 4, 0>, thr); break;
+            case 3: launch(conv_tc2_kernel<2, 0, 2, 4, 1, 8, 0>, thr); break;
+            case 4: launch(conv_tc2_kernel<2, 0, 2, 2, 1, 8, 0>, thr); break;
+            case 6: launch(conv_tc2_kernel<2, 0, 2, 3, 2, 3, 0>, thr); break;
+            case 7: launch(conv_tc2_kernel<2, 0, 2, 3, 2, 6, 0>, thr); break;     // round-2 layout before quarter staging
+            default: launch(conv_tc2_kernel<2, 0, 2, 3, 1, 6, 0>, thr); break;
         }
         return true;
     }
