@@ -268,7 +268,20 @@ int rsb_fill_synthetic(int device, float *dst, uint32_t first_stream, uint32_t n
  * result = TFLOP/s, aux = variant specific (resident CTAs per SM). */
 int rsb_microbench(int device, int id, int arg, double *result, double *aux);
 
+/* Device-side filter design (window.rs:17-131 on the GPU, bit-identical to the host design; worth it
+ * only for callers that create resamplers for many distinct rate pairs: a table is designed once
+ * per (cutoff bits, taps, attenuation) and cached either way, like the reference's FIR_CACHE).
+ * rsb_set_device_filter_design: tables missing from the cache are designed on the handle's GPU from
+ * now on (returns the previous setting).  rsb_device_design_table: uncached, for tests / timing;
+ * out receives the [1024][taps] table, elapsed_ms (optional) the device time of its kernels. */
+int rsb_set_device_filter_design(int enable);
+int rsb_device_design_table(int device, uint32_t input_rate_hz, uint32_t output_rate_hz, int latency,
+                            int attenuation, float *out, size_t out_len, float *elapsed_ms);
+
 /* ---- host-only entry points (no GPU needed): filter design and the phase planner ---- */
+/* host twin of the device-side design's sine (a restatement of glibc's sinf): equals libm's sinf bit
+ * for bit on the hosts this library is built for; the CPU tests check exactly that */
+float rsb_host_sinf_restated(float x);
 double rsb_host_bessel_i0(double x);                              /* window.rs:96-112 */
 double rsb_host_cutoff_kaiser(uint32_t taps, double beta);        /* window.rs:114-131 */
 void rsb_host_kaiser_window(uint32_t n, double beta, int symmetric, float *out); /* :66-94 */

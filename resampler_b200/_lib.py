@@ -66,6 +66,10 @@ SIGNATURES = {
     "rsb_fir_launch_count": (C.c_uint64, [C.c_void_p]),
     "rsb_fir_cuda_stream": (C.c_void_p, [C.c_void_p]),
     "rsb_fir_host_pipeline_stats": (C.c_int, [C.c_void_p, u64p, u64p]),
+    "rsb_set_device_filter_design": (C.c_int, [C.c_int]),
+    "rsb_host_sinf_restated": (C.c_float, [C.c_float]),
+    "rsb_device_design_table": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, f32p, C.c_size_t,
+                                          C.POINTER(C.c_float)]),
     "rsb_pcie_probe": (C.c_int, [C.c_int, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "rsb_alloc_pinned": (C.c_void_p, [C.c_size_t]),
     "rsb_free_pinned": (None, [C.c_void_p]),

@@ -2,6 +2,7 @@
 // reference computes the sinc, product, running sum and normalisation in f32
 // with one rounding per operation (src/window.rs:29-52).
 #include "filter_design.h"
+#include "sinf_glibc.h"
 
 #include <cmath>
 #include <map>
@@ -9,6 +10,8 @@
 #include <tuple>
 
 namespace rsb {
+
+float sinf_restated(float x) { return sinf_glibc(x); }
 
 int latency_to_taps(int latency) {
     static const int kTaps[4] = {16, 32, 64, 128};
@@ -90,7 +93,8 @@ void make_sincs_for_kaiser(uint32_t sample_count, uint32_t factor, float cutoff,
     }
 }
 
-std::shared_ptr<const FirTable> get_or_create_table(float cutoff, uint32_t taps, int attenuation) {
+std::shared_ptr<const FirTable> get_or_create_table(float cutoff, uint32_t taps, int attenuation,
+                                                    TableBuilder builder, void *ctx) {
     static std::mutex mu;
     static std::map<std::tuple<uint32_t, uint32_t, int>, std::shared_ptr<const FirTable>> cache;
     uint32_t bits;
@@ -105,8 +109,9 @@ std::shared_ptr<const FirTable> get_or_create_table(float cutoff, uint32_t taps,
     t->cutoff_bits = bits;
     t->attenuation = attenuation;
     t->coeffs.resize(static_cast<size_t>(1024) * taps);
-    make_sincs_for_kaiser(taps, 1024, cutoff, attenuation_to_beta(attenuation), true,
-                          t->coeffs.data());
+    if (!builder || !builder(cutoff, taps, attenuation_to_beta(attenuation), t->coeffs.data(), ctx))
+        make_sincs_for_kaiser(taps, 1024, cutoff, attenuation_to_beta(attenuation), true,
+                              t->coeffs.data());
     cache.emplace(key, t);
     return t;
 }

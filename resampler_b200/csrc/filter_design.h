@@ -23,11 +23,18 @@ double bessel_i0(double x);                                                     
 
 // Process-wide cache keyed by (cutoff bits, taps, attenuation) like the reference's
 // FIR_CACHE (src/resampler_fir.rs:91-95, 164-166, 425-443).
-std::shared_ptr<const FirTable> get_or_create_table(float cutoff, uint32_t taps, int attenuation);
+// `builder` (optional) designs the table on a cache miss instead of the host code (the device-side
+// design of filter_design_device.cu); it returns false to fall back to the host design.
+typedef bool (*TableBuilder)(float cutoff, uint32_t taps, double beta, float *out, void *ctx);
+std::shared_ptr<const FirTable> get_or_create_table(float cutoff, uint32_t taps, int attenuation,
+                                                    TableBuilder builder = nullptr, void *ctx = nullptr);
 
 // Uncached general builder (src/window.rs:17-55), exposed for the known-answer tests.
 void make_sincs_for_kaiser(uint32_t sample_count, uint32_t factor, float cutoff, double beta,
                            bool symmetric, float *out /*[factor][sample_count]*/);
 void make_kaiser_window(uint32_t n, double beta, bool symmetric, float *out);
+
+// Host twin of the device-side design's sine (sinf_glibc.h): the CPU tests hold it against libm's sinf.
+float sinf_restated(float x);
 
 }  // namespace rsb

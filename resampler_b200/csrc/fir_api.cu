@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -23,12 +24,14 @@
 
 #include "../../include/resampler_b200.h"
 #include "filter_design.h"
+#include "filter_design_device.h"
 #include "fir_kernels.h"
 #include "pcm_ingest.h"
 
 namespace {
 
 thread_local std::string g_last_error;
+std::atomic<bool> g_device_design{false};   // rsb_set_device_filter_design
 
 int fail(int code, const std::string &msg) {
     g_last_error = msg;
@@ -1383,7 +1386,13 @@ int rsb_fir_create(rsb_fir **out, int device, uint32_t n_streams, uint32_t chann
     h->taps = (uint32_t)taps;
     h->ratio = (double)input_rate_hz / (double)output_rate_hz;   // :311-313
     const float cutoff = rsb::design_cutoff(input_rate_hz, output_rate_hz, h->taps, beta);
-    h->table = rsb::get_or_create_table(cutoff, h->taps, attenuation);
+    // cache miss: the host design, or (rsb_set_device_filter_design) the same table designed on the GPU
+    h->table = rsb::get_or_create_table(
+        cutoff, h->taps, attenuation,
+        g_device_design ? +[](float c, uint32_t t, double b, float *out, void *ctx) {
+            return rsb::design_table_on_device(*static_cast<int *>(ctx), c, t, b, out, nullptr);
+        } : nullptr,
+        &device);
     h->cohort.assign(n_streams, 0);
     h->hist_sel.assign(n_streams, 0);
     h->m_pos.assign(n_streams, 0.0);
@@ -1987,6 +1996,33 @@ void rsb_host_kaiser_window(uint32_t n, double beta, int symmetric, float *out) 
 void rsb_host_make_sincs(uint32_t sample_count, uint32_t factor, float cutoff, double beta,
                          int symmetric, float *out) {
     rsb::make_sincs_for_kaiser(sample_count, factor, cutoff, beta, symmetric != 0, out);
+}
+
+float rsb_host_sinf_restated(float x) { return rsb::sinf_restated(x); }
+
+int rsb_set_device_filter_design(int enable) {
+    const int before = g_device_design ? 1 : 0;
+    g_device_design = enable != 0;
+    return before;
+}
+
+int rsb_device_design_table(int device, uint32_t input_rate_hz, uint32_t output_rate_hz, int latency,
+                            int attenuation, float *out, size_t out_len, float *elapsed_ms) {
+    if (input_rate_hz == 0) return fail(RSB_ERR_ZERO_INPUT_RATE, rsb_status_string(RSB_ERR_ZERO_INPUT_RATE));
+    if (output_rate_hz == 0) return fail(RSB_ERR_ZERO_OUTPUT_RATE, rsb_status_string(RSB_ERR_ZERO_OUTPUT_RATE));
+    const int taps = rsb::latency_to_taps(latency);
+    const double beta = rsb::attenuation_to_beta(attenuation);
+    if (taps < 0 || beta < 0.0 || !out) return fail(RSB_ERR_INVALID_ARGUMENT, "bad latency/attenuation/buffer");
+    if (out_len < (size_t)1024 * taps) return fail(RSB_ERR_INVALID_ARGUMENT, "table buffer too small");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        cudaGetLastError();
+        return fail(RSB_ERR_NO_DEVICE, "no such CUDA device");
+    }
+    const float cutoff = rsb::design_cutoff(input_rate_hz, output_rate_hz, (uint32_t)taps, beta);
+    if (!rsb::design_table_on_device(device, cutoff, (uint32_t)taps, beta, out, elapsed_ms))
+        return fail(RSB_ERR_CUDA, "device-side filter design failed");
+    return RSB_OK;
 }
 
 int rsb_host_design_table(uint32_t input_rate_hz, uint32_t output_rate_hz, int latency,

@@ -508,6 +508,24 @@ def host_design_table(input_rate_hz: int, output_rate_hz: int, latency: Latency,
     return out, bits.value
 
 
+def device_design_table(input_rate_hz: int, output_rate_hz: int, latency: Latency,
+                        attenuation: Attenuation, device: int = 0):
+    """The same table designed ON the GPU (filter_design_device.cu) -> (table, device milliseconds)."""
+    lib = _lib.load()
+    taps = Latency(latency).taps()
+    out = np.empty((1024, taps), np.float32)
+    ms = C.c_float(0)
+    _check(lib.rsb_device_design_table(device, input_rate_hz, output_rate_hz, int(latency), int(attenuation),
+                                       out.ctypes.data_as(_lib.f32p), out.size, C.byref(ms)))
+    return out, ms.value
+
+
+def set_device_filter_design(enable: bool) -> bool:
+    """Tables missing from the process-wide cache are designed on the GPU from now on; returns the
+    previous setting."""
+    return bool(_lib.load().rsb_set_device_filter_design(1 if enable else 0))
+
+
 def host_plan(input_rate_hz: int, output_rate_hz: int, latency: Latency, position_bits: int,
               available: int, total_frames: int, call_frames: int, cap_frames: int,
               single_call: bool, max_calls: int = 1 << 16, max_frames: int = 1 << 22):

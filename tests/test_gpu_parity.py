@@ -727,3 +727,40 @@ def test_strong_upsampling_single_call_is_bounded_by_the_output_buffer():
         _, c2, p2 = ref.resample(x, o2)
         assert (c, p) == (c2, p2)
         assert np.array_equal(bits(o1[:p]), bits(o2[:p2]))
+
+
+def test_device_side_filter_design_is_bit_identical_to_the_host_design():
+    """the Kaiser-windowed-sinc table designed on the GPU (f64 Bessel window, a
+    restatement of glibc's sinf, the reference's sequential f32 normalisation sum; window.rs:17-131)
+    equals the host design -- and through it the oracle's table -- bit for bit, for every tap count
+    and attenuation and for up-/down-sampling cutoffs; a resampler created with the device design
+    switched on produces bit-identical samples (EXACT kernel)."""
+    from resampler_b200.fir import device_design_table, host_design_table, set_device_filter_design
+    worst_ms = 0.0
+    for in_hz, out_hz in ((44100, 48000), (48000, 44100), (96000, 48000), (16000, 48000), (1000003, 999983),
+                          (48000, 8000)):
+        for lat in (0, 1, 2, 3):
+            for att in (0, 1, 2):
+                host, _ = host_design_table(in_hz, out_hz, Latency(lat), Attenuation(att))
+                dev, ms = device_design_table(in_hz, out_hz, Latency(lat), Attenuation(att))
+                worst_ms = max(worst_ms, ms)
+                assert np.array_equal(bits(dev), bits(host)), (in_hz, out_hz, lat, att,
+                                                                int(np.sum(bits(dev) != bits(host))))
+    assert worst_ms < 5.0, worst_ms
+    # a rate pair nobody has designed yet, created with the device design on
+    prev = set_device_filter_design(True)
+    try:
+        ch, in_hz, out_hz, lat = 2, 37800, 48000, 2
+        r = ResamplerFir.new_from_hz(ch, in_hz, out_hz, Latency(lat), Attenuation.Db120)
+        ref = O.OracleFir(ch, in_hz, out_hz, lat, 2)
+        rng = np.random.default_rng(5)
+        for _ in range(4):
+            x = noise(rng, 700 * ch)
+            o1, o2 = np.zeros(r.buffer_size_output(), np.float32), np.zeros(r.buffer_size_output(), np.float32)
+            c, p = r.resample(x, o1)
+            _, c2, p2 = ref.resample(x, o2)
+            assert (c, p) == (c2, p2)
+            assert np.array_equal(bits(o1[:p]), bits(o2[:p2]))
+        r.close()
+    finally:
+        set_device_filter_design(prev)

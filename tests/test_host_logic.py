@@ -303,6 +303,32 @@ def test_rust_and_ctypes_bindings_match_the_header_arity():
         assert protos[name] == len(args), f"{name}: header {protos[name]} vs ctypes {len(args)}"
 
 
+def test_restated_sinf_equals_the_platform_sinf_bit_for_bit():
+    """The device-side filter design (filter_design_device.cu) cannot call the host's libm: it carries
+    a restatement of glibc's sinf (csrc/sinf_glibc.h).  Its host twin must equal libm's sinf bit for
+    bit -- on every argument a table uses (all taps x attenuations of two cutoffs) and on random
+    arguments up to |x| = 260 -- otherwise device- and host-designed tables would differ."""
+    import ctypes as C
+    lib = _lib.load()
+    libm = C.CDLL("libm.so.6")
+    libm.sinf.restype, libm.sinf.argtypes = C.c_float, [C.c_float]
+    rng = np.random.default_rng(9)
+    args = [rng.uniform(-260.0, 260.0, 150_000).astype(np.float32),
+            rng.uniform(-1.0, 1.0, 30_000).astype(np.float32),
+            (rng.uniform(-1.0, 1.0, 5_000) * 1e-4).astype(np.float32)]
+    pi32 = np.float32(3.14159274101257324219)
+    for taps, cutoff in ((128, 0.9), (128, 0.9433594), (16, 0.7), (64, 0.45)):
+        total = taps * 1024
+        a = (np.arange(total, dtype=np.int32) - total // 2).astype(np.float32) * np.float32(cutoff) / np.float32(1024)
+        args.append((a[::7] * pi32).astype(np.float32))
+    bad = 0
+    for arr in args:
+        for v in arr.tolist():
+            if np.float32(lib.rsb_host_sinf_restated(v)).view(np.uint32) != np.float32(libm.sinf(v)).view(np.uint32):
+                bad += 1
+    assert bad == 0, bad
+
+
 def test_rust_crate_surface_and_build_script_cover_the_library():
     """north_star asks the crate for a safe wrapper over pinned host buffers and CUDA streams plus the
     batched submit: the items exist in lib.rs, no binding is kept alive by a dummy function, and
