@@ -19,7 +19,7 @@ $(OUT)/filter_design.o: $(CSRC)/filter_design.cpp $(HDRS)
 	@mkdir -p $(OUT)
 	g++ -O2 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -Wall -c $< -o $@
 
-$(OUT)/libresampler_b200.so: $(OUT)/fir_api.o $(OUT)/fir_kernels.o $(OUT)/fir_fast.o $(OUT)/fir_tensor.o $(OUT)/fir_tc2.o $(OUT)/fir_submit.o $(OUT)/filter_design_device.o $(OUT)/pcm_ingest.o $(OUT)/microbench.o $(OUT)/filter_design.o
+$(OUT)/libresampler_b200.so: $(OUT)/fir_api.o $(OUT)/fir_kernels.o $(OUT)/fir_fast.o $(OUT)/fir_tensor.o $(OUT)/fir_tc2.o $(OUT)/fir_submit.o $(OUT)/filter_design_device.o $(OUT)/fft_resampler.o $(OUT)/pcm_ingest.o $(OUT)/microbench.o $(OUT)/filter_design.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart static
 
 oracle:

@@ -268,6 +268,30 @@ int rsb_fill_synthetic(int device, float *dst, uint32_t first_stream, uint32_t n
  * result = TFLOP/s, aux = variant specific (resident CTAs per SM). */
 int rsb_microbench(int device, int id, int arg, double *result, double *aux);
 
+/* ---- ResamplerFft (src/resampler_fft.rs): the reference's overlap-add FFT resampler, batched ----
+ * Fixed-size chunks: every call consumes chunk_size_input() values and produces chunk_size_output()
+ * values per stream (both include the channels); rates are the SampleRate enum's ten values. */
+typedef struct rsb_fft rsb_fft;
+int rsb_fft_create(rsb_fft **out, int device, uint32_t n_streams, uint32_t channels,
+                   uint32_t input_rate_hz, uint32_t output_rate_hz);      /* ResamplerFft::new :75-128 */
+void rsb_fft_destroy(rsb_fft *h);
+size_t rsb_fft_chunk_size_input(const rsb_fft *h);                         /* :135-137 */
+size_t rsb_fft_chunk_size_output(const rsb_fft *h);                        /* :143-145 */
+size_t rsb_fft_delay(const rsb_fft *h);                                    /* :151-153 */
+int rsb_fft_reset(rsb_fft *h, int64_t stream);                             /* clears the overlap (-1: all streams) */
+/* one chunk of one stream, host slices: ResamplerFft::resample (:182-246), status 1 / 2 for a short
+ * input / output buffer in the reference's order */
+int rsb_fft_resample(rsb_fft *h, uint32_t stream, const float *input, size_t input_len, float *output,
+                     size_t output_len);
+/* batched: per job min(in_len / chunk_size_input, out_len / chunk_size_output) consecutive chunks
+ * (written to chunks_done), one launch; RSB_FLAG_ASYNC for device memspace */
+int rsb_fft_process_batch(rsb_fft *h, uint32_t n, const uint32_t *streams, const float *const *in,
+                          const size_t *in_lens, float *const *out, const size_t *out_lens,
+                          size_t *chunks_done, int memspace, uint32_t flags);
+int rsb_fft_sync(rsb_fft *h);
+uint64_t rsb_fft_launch_count(const rsb_fft *h);
+const char *rsb_fft_last_error(void);
+
 /* Device-side filter design (window.rs:17-131 on the GPU, bit-identical to the host design; worth it
  * only for callers that create resamplers for many distinct rate pairs: a table is designed once
  * per (cutoff bits, taps, attenuation) and cached either way, like the reference's FIR_CACHE).

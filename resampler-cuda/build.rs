@@ -10,7 +10,7 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
     let mut objs = Vec::new();
-    for name in ["fir_api.cu", "fir_kernels.cu", "fir_fast.cu", "fir_tensor.cu", "fir_tc2.cu", "fir_submit.cu", "filter_design_device.cu", "pcm_ingest.cu", "microbench.cu"] {
+    for name in ["fir_api.cu", "fir_kernels.cu", "fir_fast.cu", "fir_tensor.cu", "fir_tc2.cu", "fir_submit.cu", "filter_design_device.cu", "fft_resampler.cu", "pcm_ingest.cu", "microbench.cu"] {
         let obj = out.join(name).with_extension("o");
         let status = Command::new(&nvcc)
             .args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo"])

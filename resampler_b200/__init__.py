@@ -8,7 +8,8 @@ the C ABI of ``include/resampler_b200.h`` into hand-written CUDA kernels.
 """
 from .fir import (Attenuation, FirBatch, Kernel, Latency, PcmFormat, ResampleError, ResamplerFir,
                   SampleRate, device_count)
+from .fft import FftBatch, ResamplerFft
 
-__all__ = ["Attenuation", "FirBatch", "Kernel", "Latency", "PcmFormat", "ResampleError",
-           "ResamplerFir", "SampleRate", "device_count"]
+__all__ = ["Attenuation", "FftBatch", "FirBatch", "Kernel", "Latency", "PcmFormat", "ResampleError",
+           "ResamplerFft", "ResamplerFir", "SampleRate", "device_count"]
 __version__ = "0.1.0"

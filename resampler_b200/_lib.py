@@ -66,6 +66,19 @@ SIGNATURES = {
     "rsb_fir_launch_count": (C.c_uint64, [C.c_void_p]),
     "rsb_fir_cuda_stream": (C.c_void_p, [C.c_void_p]),
     "rsb_fir_host_pipeline_stats": (C.c_int, [C.c_void_p, u64p, u64p]),
+    "rsb_fft_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "rsb_fft_destroy": (None, [C.c_void_p]),
+    "rsb_fft_chunk_size_input": (C.c_size_t, [C.c_void_p]),
+    "rsb_fft_chunk_size_output": (C.c_size_t, [C.c_void_p]),
+    "rsb_fft_delay": (C.c_size_t, [C.c_void_p]),
+    "rsb_fft_reset": (C.c_int, [C.c_void_p, C.c_int64]),
+    "rsb_fft_resample": (C.c_int, [C.c_void_p, C.c_uint32, f32p, C.c_size_t, f32p, C.c_size_t]),
+    "rsb_fft_process_batch": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_void_p),
+                                        C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                        C.POINTER(C.c_size_t), C.c_int, C.c_uint32]),
+    "rsb_fft_sync": (C.c_int, [C.c_void_p]),
+    "rsb_fft_launch_count": (C.c_uint64, [C.c_void_p]),
+    "rsb_fft_last_error": (C.c_char_p, []),
     "rsb_set_device_filter_design": (C.c_int, [C.c_int]),
     "rsb_host_sinf_restated": (C.c_float, [C.c_float]),
     "rsb_device_design_table": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, f32p, C.c_size_t,
