@@ -483,6 +483,54 @@ def divergent_leg(lib, local, rank, dist, n_streams=4096, submits=64):
             "all_input_consumed": complete}
 
 
+def fft_leg(lib, local, rank, dist, n_streams=1024, seconds=10.0, steps=3):
+    """The reference's second resampler (`ResamplerFft`) as a batched GPU workload:
+    1024 stereo streams x 10 s, 44.1 -> 48 kHz (chunks of 1176 -> 1280 frames), device resident, one
+    launch per step.  HBM roofline: 4 B per input value + 4 B per output value."""
+    from resampler_b200 import FftBatch
+    from resampler_b200.fir import FLAG_ASYNC, MEM_DEVICE, DeviceBuffer, _ptr_array, _size_array
+    ch, in_hz, out_hz = 2, 44100, 48000
+    b = FftBatch(n_streams, ch, in_hz, out_hz, device=local)
+    csi, cso = b.chunk_size_input(), b.chunk_size_output()
+    chunks = int(seconds * in_hz * ch) // csi
+    d_in = DeviceBuffer(local, n_streams * chunks * csi)
+    d_out = DeviceBuffer(local, n_streams * chunks * cso)
+    assert lib.rsb_fill_synthetic(local, d_in.ptr, rank * n_streams, n_streams, chunks * csi // ch, ch, in_hz, 0x5EED) == 0
+    ip = _ptr_array([d_in.ptr + 4 * s * chunks * csi for s in range(n_streams)])
+    op = _ptr_array([d_out.ptr + 4 * s * chunks * cso for s in range(n_streams)])
+    il, ol = _size_array([chunks * csi] * n_streams), _size_array([chunks * cso] * n_streams)
+    for _ in range(2):
+        b.reset(-1)
+        b.process_ptrs(ip, il, op, ol, memspace=MEM_DEVICE, flags=FLAG_ASYNC)
+    b.sync()
+    barrier(dist, local)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        b.reset(-1)
+        done = b.process_ptrs(ip, il, op, ol, memspace=MEM_DEVICE, flags=FLAG_ASYNC)
+    b.sync()
+    dt = time.perf_counter() - t0
+    produced = int(sum(done[:])) * cso
+    consumed = int(sum(done[:])) * csi
+    d_in.free()
+    d_out.free()
+    b.close()
+    dt_max = reduce_max(dist, local, dt)
+    prod_all = reduce_sum(dist, local, float(produced))
+    hbm_peak, peak_src = measured_peaks()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    gbs = 4.0 * (produced + consumed) * steps / dt_max / 1e9
+    return {"workload": f"ResamplerFft: {n_streams} stereo streams x {seconds:g} s per GPU, 44.1->48 kHz, chunks of "
+                        f"{csi // ch} -> {cso // ch} frames ({chunks} per stream), device resident, one launch per step",
+            "kernel": "fft_resample_kernel (overlap-add, mixed-radix Stockham FFTs in shared memory)",
+            "value": round(prod_all * steps / dt_max / 1e6, 1), "unit": "Msamples/s",
+            "ms_per_step": round(dt_max / steps * 1e3, 3), "steps": steps,
+            "timing": "wall clock around the asynchronous launches and the final sync (one launch per step)",
+            "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s per GPU",
+                         "frac": round(gbs / hbm_peak, 4), "peak_source": peak_src,
+                         "note": "compute / shared-memory bound, not HBM bound (DESIGN 3.6)"}}
+
+
 def leg_roofline(res, hbm_peak, peak_src):
     conv_avg_ms = float(np.mean(res["conv_ms"])) if res["conv_ms"] else float("nan")
     alg_bytes = 4.0 * (res["produced"] + res["consumed"])
@@ -660,6 +708,11 @@ def run_ours(args):
             legs["C3ii"] = divergent_leg(lib, local, rank, dist)
         except Exception as e:
             legs["C3ii"] = {"workload": "configs[2] (ii)", "error": str(e)[:300]}
+    if not args.no_legs:
+        try:
+            legs["FFT"] = fft_leg(lib, local, rank, dist)
+        except Exception as e:
+            legs["FFT"] = {"workload": "ResamplerFft", "error": str(e)[:300]}
     strong = None
     if not args.no_legs:
         try:

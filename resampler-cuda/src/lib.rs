@@ -59,6 +59,26 @@ unsafe extern "C" {
     fn rsb_memcpy(device: c_int, dst: *mut c_void, src: *const c_void, bytes: usize, kind: c_int) -> c_int;
     fn rsb_status_string(status: c_int) -> *const std::os::raw::c_char;
     fn rsb_last_error() -> *const std::os::raw::c_char;
+    fn rsb_set_device_filter_design(enable: c_int) -> c_int;
+    fn rsb_fft_create(out: *mut *mut RsbFft, device: c_int, n_streams: u32, channels: u32,
+                      input_rate_hz: u32, output_rate_hz: u32) -> c_int;
+    fn rsb_fft_destroy(h: *mut RsbFft);
+    fn rsb_fft_chunk_size_input(h: *const RsbFft) -> usize;
+    fn rsb_fft_chunk_size_output(h: *const RsbFft) -> usize;
+    fn rsb_fft_delay(h: *const RsbFft) -> usize;
+    fn rsb_fft_resample(h: *mut RsbFft, stream: u32, input: *const f32, input_len: usize,
+                        output: *mut f32, output_len: usize) -> c_int;
+}
+
+#[repr(C)]
+struct RsbFft {
+    _private: [u8; 0],
+}
+
+/// Tables missing from the process-wide cache are designed on the GPU from now on (bit-identical to
+/// the host design); returns the previous setting.
+pub fn set_device_filter_design(enable: bool) -> bool {
+    unsafe { rsb_set_device_filter_design(enable as c_int) != 0 }
 }
 
 const RSB_FLAG_ASYNC: u32 = 1;
@@ -371,4 +391,35 @@ impl ResamplerFir {
     pub fn delay(&self) -> usize { self.inner.delay() }
     /// resampler_fir.rs:638-642
     pub fn reset(&mut self) { self.inner.reset(Some(0)) }
+}
+
+/// Drop-in for `resampler::ResamplerFft` (src/resampler_fft.rs:43-246): fixed-size chunks.
+pub struct ResamplerFft { h: *mut RsbFft }
+unsafe impl Send for ResamplerFft {}
+
+impl ResamplerFft {
+    /// `ResamplerFft::new` (resampler_fft.rs:75-128)
+    pub fn new(channels: usize, sample_rate_input: SampleRate, sample_rate_output: SampleRate) -> Self {
+        let mut h = std::ptr::null_mut();
+        let rc = unsafe {
+            rsb_fft_create(&mut h, 0, 1, channels as u32, u32::from(sample_rate_input), u32::from(sample_rate_output))
+        };
+        assert!(rc == 0, "resampler-cuda: create failed ({rc})");
+        Self { h }
+    }
+    /// resampler_fft.rs:135-137
+    pub fn chunk_size_input(&self) -> usize { unsafe { rsb_fft_chunk_size_input(self.h) } }
+    /// resampler_fft.rs:143-145
+    pub fn chunk_size_output(&self) -> usize { unsafe { rsb_fft_chunk_size_output(self.h) } }
+    /// resampler_fft.rs:151-153
+    pub fn delay(&self) -> usize { unsafe { rsb_fft_delay(self.h) } }
+    /// resampler_fft.rs:182-246
+    pub fn resample(&mut self, input: &[f32], output: &mut [f32]) -> Result<(), ResampleError> {
+        map_err(unsafe {
+            rsb_fft_resample(self.h, 0, input.as_ptr(), input.len(), output.as_mut_ptr(), output.len())
+        })
+    }
+}
+impl Drop for ResamplerFft {
+    fn drop(&mut self) { unsafe { rsb_fft_destroy(self.h) } }
 }

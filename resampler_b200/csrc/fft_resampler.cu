@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -60,6 +61,8 @@ struct FftParams {
 struct FftJob {
     const float *in;
     float *out;
+    const float *ov_read;      // the stream's overlap before this call  [channels][n_out]
+    float *ov_write;           // ... after it (the other buffer)
     uint32_t stream;
     uint32_t chunks;
 };
@@ -68,44 +71,98 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
-// One Stockham pass of radix R: x -> y, p = product of the radices already done.
-template <int R>
-__device__ void stockham_pass(const float2 *x, float2 *y, uint32_t n, uint32_t p, const float2 *tw) {
-    const uint32_t t = n / R;
-    const uint32_t tw_step = n / (p * R);       // W_{pR}^{k r} = W_n^{k r tw_step}
-    const uint32_t r_step = n / R;              // W_R^{q r}    = W_n^{q r r_step}
-    for (uint32_t i = threadIdx.x; i < t; i += blockDim.x) {
-        const uint32_t k = i % p;
-        const uint32_t j = (i / p) * p * R + k;
-        float2 u[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const float2 v = x[i + r * t];
-            u[r] = r == 0 ? v : cmul(v, __ldg(&tw[(k * r * tw_step) % n]));
-        }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// multiplication by -i (forward) / +i (inverse)
+template <bool INV>
+__device__ __forceinline__ float2 rot90(float2 a) { return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
+
+// R-point DFT of u in place.  2, 4 and 8 are the usual add / rotate networks; 3, 5 and 7 multiply by
+// the roots W_R^m held in registers (wr).
+template <int R, bool INV>
+__device__ __forceinline__ void dft_small(float2 (&u)[R], const float2 (&wr)[R]) {
+    if constexpr (R == 2) {
+        const float2 a = u[0], b = u[1];
+        u[0] = cadd(a, b);
+        u[1] = csub(a, b);
+    } else if constexpr (R == 4) {
+        const float2 a0 = cadd(u[0], u[2]), a1 = csub(u[0], u[2]), a2 = cadd(u[1], u[3]), a3 = rot90<INV>(csub(u[1], u[3]));
+        u[0] = cadd(a0, a2);
+        u[1] = cadd(a1, a3);
+        u[2] = csub(a0, a2);
+        u[3] = csub(a1, a3);
+    } else if constexpr (R == 8) {
+        float2 e[4] = {u[0], u[2], u[4], u[6]}, o[4] = {u[1], u[3], u[5], u[7]};
+        float2 dummy[4];
+        dft_small<4, INV>(e, dummy);
+        dft_small<4, INV>(o, dummy);
+        const float h = 0.70710678118654752440f;
+        // o[q] *= W_8^q
+        const float2 o1 = INV ? make_float2(h * (o[1].x - o[1].y), h * (o[1].x + o[1].y))
+                              : make_float2(h * (o[1].x + o[1].y), h * (o[1].y - o[1].x));
+        const float2 o2 = rot90<INV>(o[2]);
+        const float2 o3 = INV ? make_float2(-h * (o[3].x + o[3].y), h * (o[3].x - o[3].y))
+                              : make_float2(h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y));
+        u[0] = cadd(e[0], o[0]); u[4] = csub(e[0], o[0]);
+        u[1] = cadd(e[1], o1);   u[5] = csub(e[1], o1);
+        u[2] = cadd(e[2], o2);   u[6] = csub(e[2], o2);
+        u[3] = cadd(e[3], o3);   u[7] = csub(e[3], o3);
+    } else {
+        float2 v[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) {
             float2 acc = u[0];
 #pragma unroll
-            for (int r = 1; r < R; ++r) acc = make_float2(acc.x + cmul(u[r], __ldg(&tw[((q * r) % R) * r_step])).x,
-                                                          acc.y + cmul(u[r], __ldg(&tw[((q * r) % R) * r_step])).y);
-            y[j + q * p] = acc;
+            for (int r = 1; r < R; ++r) {
+                const float2 w = wr[(q * r) % R];
+                acc.x = fmaf(u[r].x, w.x, fmaf(-u[r].y, w.y, acc.x));
+                acc.y = fmaf(u[r].x, w.y, fmaf(u[r].y, w.x, acc.y));
+            }
+            v[q] = acc;
         }
+#pragma unroll
+        for (int q = 0; q < R; ++q) u[q] = v[q];
     }
 }
 
-// In-place-looking complex FFT over two shared buffers; returns the buffer holding the result.
+// One Stockham pass of radix R: x -> y, p = product of the radices already done.  `tw` is the
+// transform's table W_n^m (global memory, L1 resident); the R-point DFT's own roots W_R^m sit in registers.
+template <int R, bool INV>
+__device__ void stockham_pass(const float2 *x, float2 *y, uint32_t n, uint32_t p, const float2 *tw) {
+    const uint32_t t = n / R;
+    const uint32_t tw_step = n / (p * R);       // W_{pR}^{k r} = W_n^{k r tw_step}
+    float2 wr[R];
+#pragma unroll
+    for (int m = 0; m < R; ++m) wr[m] = (R == 3 || R == 5 || R == 7) ? __ldg(&tw[m * (n / R)]) : make_float2(0.f, 0.f);
+    for (uint32_t i = threadIdx.x; i < t; i += blockDim.x) {
+        const uint32_t k = i % p;
+        const uint32_t j = (i / p) * p * R + k;
+        const uint32_t kw = k * tw_step;
+        float2 u[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float2 v = x[i + r * t];
+            u[r] = (r == 0 || p == 1) ? v : cmul(v, __ldg(&tw[kw * r]));    // kw * r < n
+        }
+        dft_small<R, INV>(u, wr);
+#pragma unroll
+        for (int q = 0; q < R; ++q) y[j + q * p] = u[q];
+    }
+}
+
+// Complex FFT over two shared buffers; returns the buffer holding the result.
+template <bool INV>
 __device__ float2 *fft_smem(float2 *a, float2 *b, const FftPlan &P, const float2 *tw) {
     uint32_t p = 1;
     for (uint32_t s = 0; s < P.n_pass; ++s) {
         const uint32_t R = P.radix[s];
         switch (R) {
-            case 8: stockham_pass<8>(a, b, P.n, p, tw); break;
-            case 7: stockham_pass<7>(a, b, P.n, p, tw); break;
-            case 5: stockham_pass<5>(a, b, P.n, p, tw); break;
-            case 4: stockham_pass<4>(a, b, P.n, p, tw); break;
-            case 3: stockham_pass<3>(a, b, P.n, p, tw); break;
-            default: stockham_pass<2>(a, b, P.n, p, tw); break;
+            case 8: stockham_pass<8, INV>(a, b, P.n, p, tw); break;
+            case 7: stockham_pass<7, INV>(a, b, P.n, p, tw); break;
+            case 5: stockham_pass<5, INV>(a, b, P.n, p, tw); break;
+            case 4: stockham_pass<4, INV>(a, b, P.n, p, tw); break;
+            case 3: stockham_pass<3, INV>(a, b, P.n, p, tw); break;
+            default: stockham_pass<2, INV>(a, b, P.n, p, tw); break;
         }
         __syncthreads();
         p *= R;
@@ -116,50 +173,65 @@ __device__ float2 *fft_smem(float2 *a, float2 *b, const FftPlan &P, const float2
     return a;
 }
 
+// One CTA per (job, chunk): the chunks of a stream are independent up to the overlap-add, which is a
+// sum of exactly two terms per output value -- this chunk's first half and the previous chunk's
+// second half (:419-423) -- so both are ADDED into a zeroed output with atomics (a + b == b + a: the
+// result does not depend on which CTA comes first).  Chunk 0 also adds the overlap carried in the
+// handle; the last chunk stores its second half as the new overlap (the other buffer of a pair, so a
+// concurrent chunk 0 never reads what the last chunk writes).
 __global__ void __launch_bounds__(256) fft_resample_kernel(const FftJob *jobs, const FftParams P) {
     extern __shared__ __align__(16) uint8_t sm_fft[];
     float2 *buf_a = reinterpret_cast<float2 *>(sm_fft);
     float2 *buf_b = buf_a + P.buf_len;
     float *s_in = reinterpret_cast<float *>(buf_b + P.buf_len);          // [n_in * channels]
-    float *s_out = s_in + (size_t)P.n_in * P.channels;                    // [n_out * channels]
-    const FftJob job = jobs[blockIdx.x];
+    float *s_out = s_in + (size_t)P.n_in * P.channels;                    // [2 n_out * channels]: both halves
+    const FftJob job = jobs[blockIdx.y];
+    const uint32_t chunk = blockIdx.x;
+    if (chunk >= job.chunks) return;
     const uint32_t ch = P.channels, n_in = P.n_in, n_out = P.n_out;
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
-    float *ov_base = P.overlap + (size_t)job.stream * ch * n_out;
 
-    for (uint32_t chunk = 0; chunk < job.chunks; ++chunk) {
-        const float *src = job.in + (size_t)chunk * n_in * ch;
-        for (uint32_t i = tid; i < n_in * ch; i += nt) s_in[i] = src[i];          // :195-202, coalesced
+    const float *src = job.in + (size_t)chunk * n_in * ch;
+    for (uint32_t i = tid; i < n_in * ch; i += nt) s_in[i] = src[i];              // :195-202, coalesced
+    __syncthreads();
+    for (uint32_t c = 0; c < ch; ++c) {
+        // copy input and clear padding (:390-391)
+        for (uint32_t n = tid; n < 2 * n_in; n += nt)
+            buf_a[n] = make_float2(n < n_in ? s_in[n * ch + c] : 0.0f, 0.0f);
         __syncthreads();
-        for (uint32_t c = 0; c < ch; ++c) {
-            // copy input and clear padding (:390-391)
-            for (uint32_t n = tid; n < 2 * n_in; n += nt)
-                buf_a[n] = make_float2(n < n_in ? s_in[n * ch + c] : 0.0f, 0.0f);
-            __syncthreads();
-            float2 *X = fft_smem(buf_a, buf_b, P.fwd, P.tw_fwd);                  // :393-397
-            float2 *Y = X == buf_a ? buf_b : buf_a;
-            // spectrum x filter, truncated / zero-extended to n_out + 1 bins (:399-411), with its
-            // Hermitian mirror so that a complex inverse transform returns the real signal
-            for (uint32_t k = tid; k <= n_out; k += nt) {
-                float2 v = make_float2(0.0f, 0.0f);
-                if (k < P.new_length) v = cmul(X[k], __ldg(&P.filter[k]));
-                if (k == 0 || k == n_out) v.y = 0.0f;
-                Y[k] = v;
-                if (k != 0 && k != n_out) Y[2 * n_out - k] = make_float2(v.x, -v.y);
-            }
-            __syncthreads();
-            float2 *y = fft_smem(Y, X, P.inv, P.tw_inv);                          // :413-417
-            // overlap-add (:419-423)
-            float *ov = ov_base + (size_t)c * n_out;
-            for (uint32_t n = tid; n < n_out; n += nt) {
-                s_out[n * ch + c] = y[n].x + ov[n];
-                ov[n] = y[n_out + n].x;
-            }
-            __syncthreads();
+        float2 *X = fft_smem<false>(buf_a, buf_b, P.fwd, P.tw_fwd);                      // :393-397
+        float2 *Y = X == buf_a ? buf_b : buf_a;
+        // spectrum x filter, truncated / zero-extended to n_out + 1 bins (:399-411), with its
+        // Hermitian mirror so that a complex inverse transform returns the real signal
+        for (uint32_t k = tid; k <= n_out; k += nt) {
+            float2 v = make_float2(0.0f, 0.0f);
+            if (k < P.new_length) v = cmul(X[k], __ldg(&P.filter[k]));
+            if (k == 0 || k == n_out) v.y = 0.0f;
+            Y[k] = v;
+            if (k != 0 && k != n_out) Y[2 * n_out - k] = make_float2(v.x, -v.y);
         }
-        float *dst = job.out + (size_t)chunk * n_out * ch;
-        for (uint32_t i = tid; i < n_out * ch; i += nt) dst[i] = s_out[i];        // :239-244, coalesced
         __syncthreads();
+        float2 *y = fft_smem<true>(Y, X, P.inv, P.tw_inv);                              // :413-417
+        for (uint32_t n = tid; n < 2 * n_out; n += nt) s_out[n * ch + c] = y[n].x;
+        __syncthreads();
+    }
+    // overlap-add (:419-423) as two contributions
+    float *dst = job.out + (size_t)chunk * n_out * ch;
+    const bool first = chunk == 0, last = chunk + 1 == job.chunks;
+    for (uint32_t i = tid; i < n_out * ch; i += nt) {
+        float v = s_out[i];
+        if (first) {                       // overlap layout in the handle: [channel][n_out]
+            const uint32_t n = i / ch, c = i - n * ch;
+            v += job.ov_read[(size_t)c * n_out + n];
+        }
+        atomicAdd(&dst[i], v);
+        const float tail = s_out[(size_t)n_out * ch + i];
+        if (last) {
+            const uint32_t n = i / ch, c = i - n * ch;
+            job.ov_write[(size_t)c * n_out + n] = tail;
+        } else {
+            atomicAdd(&dst[(size_t)n_out * ch + i], tail);
+        }
     }
 }
 
@@ -212,7 +284,8 @@ struct rsb_fft {
     uint32_t n_streams = 0, channels = 0, in_hz = 0, out_hz = 0, n_in = 0, n_out = 0, new_length = 0;
     FftParams P{};
     float2 *d_tw_fwd = nullptr, *d_tw_inv = nullptr, *d_filter = nullptr;
-    float *d_overlap = nullptr;
+    float *d_overlap = nullptr;           // two buffers of [streams][channels][n_out]
+    std::vector<uint8_t> ov_sel;          // which one is live, per stream
     cudaStream_t stream = nullptr;
     size_t smem = 0;
     // staging of host-memspace calls and the job table
@@ -290,12 +363,13 @@ int rsb_fft_create(rsb_fft **out, int device, uint32_t n_streams, uint32_t chann
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("stream");
     if (cudaMalloc(&h->d_tw_fwd, sizeof(float2) * N1) != cudaSuccess || cudaMalloc(&h->d_tw_inv, sizeof(float2) * N2) != cudaSuccess ||
         cudaMalloc(&h->d_filter, sizeof(float2) * (n_in + 1)) != cudaSuccess ||
-        cudaMalloc(&h->d_overlap, sizeof(float) * (size_t)n_streams * channels * n_out) != cudaSuccess)
+        cudaMalloc(&h->d_overlap, 2 * sizeof(float) * (size_t)n_streams * channels * n_out) != cudaSuccess)
         return bail("out of device memory");
     cudaMemcpy(h->d_tw_fwd, tw1.data(), sizeof(float2) * N1, cudaMemcpyHostToDevice);
     cudaMemcpy(h->d_tw_inv, tw2.data(), sizeof(float2) * N2, cudaMemcpyHostToDevice);
     cudaMemcpy(h->d_filter, filt.data(), sizeof(float2) * (n_in + 1), cudaMemcpyHostToDevice);
-    cudaMemset(h->d_overlap, 0, sizeof(float) * (size_t)n_streams * channels * n_out);
+    cudaMemset(h->d_overlap, 0, 2 * sizeof(float) * (size_t)n_streams * channels * n_out);
+    h->ov_sel.assign(n_streams, 0);
     P.tw_fwd = h->d_tw_fwd;
     P.tw_inv = h->d_tw_inv;
     P.filter = h->d_filter;
@@ -305,7 +379,7 @@ int rsb_fft_create(rsb_fft **out, int device, uint32_t n_streams, uint32_t chann
     P.new_length = h->new_length;
     P.channels = channels;
     P.buf_len = std::max(N1, N2);
-    h->smem = sizeof(float2) * 2 * P.buf_len + sizeof(float) * (size_t)channels * (n_in + n_out);
+    h->smem = sizeof(float2) * 2 * P.buf_len + sizeof(float) * (size_t)channels * (n_in + 2 * n_out);
     if (h->smem > 227 * 1024) return bail("channel count too large for this FFT size");
     if (cudaFuncSetAttribute(fft_resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess)
         return bail("shared memory");
@@ -337,10 +411,12 @@ int rsb_fft_reset(rsb_fft *h, int64_t stream) {
     if (!h) return fft_fail(RSB_ERR_INVALID_ARGUMENT, "null handle");
     FFT_CUDA(cudaSetDevice(h->device));
     const size_t per = (size_t)h->channels * h->n_out;
-    if (stream < 0) FFT_CUDA(cudaMemsetAsync(h->d_overlap, 0, sizeof(float) * per * h->n_streams, h->stream));
-    else if ((uint64_t)stream < h->n_streams)
+    const size_t half = per * h->n_streams;
+    if (stream < 0) FFT_CUDA(cudaMemsetAsync(h->d_overlap, 0, 2 * sizeof(float) * half, h->stream));
+    else if ((uint64_t)stream < h->n_streams) {
         FFT_CUDA(cudaMemsetAsync(h->d_overlap + per * (size_t)stream, 0, sizeof(float) * per, h->stream));
-    else return fft_fail(RSB_ERR_INVALID_ARGUMENT, "bad stream index");
+        FFT_CUDA(cudaMemsetAsync(h->d_overlap + half + per * (size_t)stream, 0, sizeof(float) * per, h->stream));
+    } else return fft_fail(RSB_ERR_INVALID_ARGUMENT, "bad stream index");
     return RSB_OK;
 }
 
@@ -365,6 +441,7 @@ int rsb_fft_process_batch(rsb_fft *h, uint32_t n, const uint32_t *streams, const
     std::vector<uint8_t> seen(h->n_streams, 0);
     std::vector<size_t> off_in(n), off_out(n);
     size_t tot_in = 0, tot_out = 0;
+    uint32_t max_chunks = 0;
     for (uint32_t i = 0; i < n; ++i) {
         const uint32_t s = streams ? streams[i] : i;
         if (s >= h->n_streams) return fft_fail(RSB_ERR_INVALID_ARGUMENT, "bad stream index");
@@ -373,7 +450,11 @@ int rsb_fft_process_batch(rsb_fft *h, uint32_t n, const uint32_t *streams, const
         const size_t c = std::min(in_lens[i] / csi, out_lens[i] / cso);
         if (c > 0xffffffffull) return fft_fail(RSB_ERR_INVALID_ARGUMENT, "too many chunks");
         if (c && (!in[i] || !out[i])) return fft_fail(RSB_ERR_INVALID_ARGUMENT, "null buffer");
-        jobs[i] = FftJob{in[i], out[i], s, (uint32_t)c};
+        const size_t per = (size_t)h->channels * h->n_out, half = per * h->n_streams;
+        const uint32_t sel = h->ov_sel[s];
+        jobs[i] = FftJob{in[i], out[i], h->d_overlap + sel * half + per * s, h->d_overlap + (sel ^ 1u) * half + per * s,
+                         s, (uint32_t)c};
+        max_chunks = std::max<uint32_t>(max_chunks, (uint32_t)c);
         if (chunks_done) chunks_done[i] = c;
         off_in[i] = tot_in;
         off_out[i] = tot_out;
@@ -405,9 +486,18 @@ int rsb_fft_process_batch(rsb_fft *h, uint32_t n, const uint32_t *streams, const
     // through a stream-ordered copy of a host vector that lives until the copy has been issued
     FFT_CUDA(cudaMemcpyAsync(h->d_jobs, jobs.data(), sizeof(FftJob) * n, cudaMemcpyHostToDevice, h->stream));
     FFT_CUDA(cudaStreamSynchronize(h->stream));          // pageable source: the copy must be complete before `jobs` dies
-    fft_resample_kernel<<<n, 256, h->smem, h->stream>>>(static_cast<const FftJob *>(h->d_jobs), h->P);
-    FFT_CUDA(cudaGetLastError());
-    h->launches += 1;
+    if (max_chunks) {
+        // the chunks' contributions are accumulated into the output: it starts from zero
+        for (uint32_t i = 0; i < n; ++i)
+            if (jobs[i].chunks)
+                FFT_CUDA(cudaMemsetAsync(jobs[i].out, 0, jobs[i].chunks * cso * sizeof(float), h->stream));
+        if (max_chunks > 0x7fffffffu || n > 65535u) return fft_fail(RSB_ERR_INVALID_ARGUMENT, "batch too large; split it");
+        fft_resample_kernel<<<dim3(max_chunks, n), (getenv("RSB_FFT_THREADS") ? atoi(getenv("RSB_FFT_THREADS")) : 256), h->smem, h->stream>>>(static_cast<const FftJob *>(h->d_jobs), h->P);
+        FFT_CUDA(cudaGetLastError());
+        h->launches += 1;
+        for (uint32_t i = 0; i < n; ++i)
+            if (jobs[i].chunks) h->ov_sel[jobs[i].stream] ^= 1u;
+    }
     if (memspace == RSB_MEM_HOST) {
         for (uint32_t i = 0; i < n; ++i)
             if (jobs[i].chunks)
