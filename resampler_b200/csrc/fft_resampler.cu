@@ -8,16 +8,15 @@
 // conversion table scaled to at least 512 input frames (src/fft/planner.rs:33-233): 1176 -> 1280 for
 // 44.1 -> 48 kHz, 512 -> 1536 for 16 -> 48 kHz, ...
 //
-// Kernel: one CTA per stream, walking its chunks in order (the overlap-add chains them); inside a
-// chunk the channels in turn.  Both transforms are complex Stockham auto-sort FFTs in shared memory
-// (mixed radix 8 / 4 / 2 / 3 / 5 / 7: every size of the table factors into these), twiddles from a
-// table W_N^m computed in f64 on the host; the input chunk and the output chunk are staged so that
-// global memory sees whole interleaved rows.  The filter spectrum is the f64 DFT of the reference's
-// f32 filter (:349-386), rounded to f32 once.
+// Kernel: one CTA per (stream, chunk) -- the overlap-add is a sum of two terms, accumulated with
+// atomics -- the channels in turn.  The real transforms run as half-size complex Stockham auto-sort
+// FFTs in shared memory (mixed radix 8 / 4 / 2 / 3 / 5 / 7: every size of the table factors into
+// these) with the usual pack / untangle steps, twiddles from tables computed in f64 on the host; the
+// input chunk and the output chunk are staged so that global memory sees whole interleaved rows.
+// The filter spectrum is the f64 DFT of the reference's f32 filter (:349-386), rounded to f32 once.
 //
-// This path is NOT near its roofline: complex transforms of real data, one CTA per
-// stream, O(R^2) butterflies.  It exists to cover the reference's second public type with the same
-// API and parity discipline; the FIR path is the product's hot path.
+// This path is NOT near its roofline.  It exists to cover the reference's second
+// public type with the same API and parity discipline; the FIR path is the product's hot path.
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -51,8 +50,10 @@ struct FftPlan {
 
 struct FftParams {
     FftPlan fwd, inv;
-    const float2 *tw_fwd;      // W_N^m = exp(-2 pi i m / N), N = 2 n_in
-    const float2 *tw_inv;      // exp(+2 pi i m / N), N = 2 n_out
+    const float2 *tw_fwd;      // exp(-2 pi i m / n_in), m < n_in: the forward transform's roots
+    const float2 *tw_inv;      // exp(+2 pi i m / n_out), m < n_out: the inverse transform's roots
+    const float2 *tw_post;     // exp(-2 pi i k / (2 n_in)), k <= n_in: real-input untangling
+    const float2 *tw_pre;      // exp(+2 pi i k / (2 n_out)), k <= n_out: real-output tangling
     const float2 *filter;      // [n_in + 1]
     float *overlap;            // [streams][channels][n_out]
     uint32_t n_in, n_out, new_length, channels, buf_len;
@@ -195,24 +196,45 @@ __global__ void __launch_bounds__(256) fft_resample_kernel(const FftJob *jobs, c
     for (uint32_t i = tid; i < n_in * ch; i += nt) s_in[i] = src[i];              // :195-202, coalesced
     __syncthreads();
     for (uint32_t c = 0; c < ch; ++c) {
-        // copy input and clear padding (:390-391)
-        for (uint32_t n = tid; n < 2 * n_in; n += nt)
-            buf_a[n] = make_float2(n < n_in ? s_in[n * ch + c] : 0.0f, 0.0f);
+        // Real transforms through half-size complex ones.  Forward (:390-397): the zero-padded chunk
+        // x[0 .. 2 n_in) is packed as z[n] = x[2n] + i x[2n+1], n < n_in (zero beyond n_in / 2).
+        for (uint32_t n = tid; n < n_in; n += nt)
+            buf_a[n] = 2 * n < n_in ? make_float2(s_in[(2 * n) * ch + c], s_in[(2 * n + 1) * ch + c])
+                                    : make_float2(0.0f, 0.0f);
         __syncthreads();
-        float2 *X = fft_smem<false>(buf_a, buf_b, P.fwd, P.tw_fwd);                      // :393-397
-        float2 *Y = X == buf_a ? buf_b : buf_a;
-        // spectrum x filter, truncated / zero-extended to n_out + 1 bins (:399-411), with its
-        // Hermitian mirror so that a complex inverse transform returns the real signal
+        float2 *Z = fft_smem<false>(buf_a, buf_b, P.fwd, P.tw_fwd);
+        float2 *Yb = Z == buf_a ? buf_b : buf_a;
+        // untangle: X[k] = (Z[k] + conj(Z[M-k])) / 2 - (i / 2) W_2M^k (Z[k] - conj(Z[M-k])), k <= M;
+        // times the filter, truncated / zero-extended to n_out + 1 bins (:399-411)
         for (uint32_t k = tid; k <= n_out; k += nt) {
             float2 v = make_float2(0.0f, 0.0f);
-            if (k < P.new_length) v = cmul(X[k], __ldg(&P.filter[k]));
+            if (k < P.new_length) {
+                const float2 a = Z[k == n_in ? 0 : k], bq = Z[k == 0 ? 0 : n_in - k];
+                const float2 b = make_float2(bq.x, -bq.y);
+                const float2 sum = cadd(a, b), dif = csub(a, b);
+                const float2 t = cmul(__ldg(&P.tw_post[k]), dif);            // W (Z[k] - conj(Z[M-k]))
+                const float2 X = make_float2(0.5f * (sum.x + t.y), 0.5f * (sum.y - t.x));   // sum/2 - (i/2) t
+                v = cmul(X, __ldg(&P.filter[k]));
+            }
             if (k == 0 || k == n_out) v.y = 0.0f;
-            Y[k] = v;
-            if (k != 0 && k != n_out) Y[2 * n_out - k] = make_float2(v.x, -v.y);
+            Yb[k] = v;
         }
         __syncthreads();
-        float2 *y = fft_smem<true>(Y, X, P.inv, P.tw_inv);                              // :413-417
-        for (uint32_t n = tid; n < 2 * n_out; n += nt) s_out[n * ch + c] = y[n].x;
+        // tangle for the inverse (:413-417): Z'[k] = (Y[k] + conj(Y[M'-k])) + i W_2M'^{-k}... with the
+        // inverse roots e^{+i pi k / M'}: Z'[k] = (Y[k] + conj(Y[M'-k])) + i e^{+i pi k / M'} (Y[k] - conj(Y[M'-k]))
+        for (uint32_t k = tid; k < n_out; k += nt) {
+            const float2 a = Yb[k], bq = Yb[n_out - k];
+            const float2 b = make_float2(bq.x, -bq.y);
+            const float2 sum = cadd(a, b), dif = csub(a, b);
+            const float2 t = cmul(__ldg(&P.tw_pre[k]), dif);
+            Z[k] = make_float2(sum.x - t.y, sum.y + t.x);                     // sum + i t
+        }
+        __syncthreads();
+        float2 *z = fft_smem<true>(Z, Yb, P.inv, P.tw_inv);                      // z[n] = y[2n] + i y[2n+1]
+        for (uint32_t n = tid; n < n_out; n += nt) {
+            s_out[(2 * n) * ch + c] = z[n].x;
+            s_out[(2 * n + 1) * ch + c] = z[n].y;
+        }
         __syncthreads();
     }
     // overlap-add (:419-423) as two contributions
@@ -327,7 +349,7 @@ int rsb_fft_create(rsb_fft **out, int device, uint32_t n_streams, uint32_t chann
     h->n_out = n_out;
     h->new_length = n_in < n_out ? n_in + 1 : n_out;                 // :399-402
     FftParams &P = h->P;
-    if (!factorize(2 * n_in, P.fwd) || !factorize(2 * n_out, P.inv)) {
+    if ((n_in & 1u) || (n_out & 1u) || !factorize(n_in, P.fwd) || !factorize(n_out, P.inv)) {
         delete h;
         return fft_fail(RSB_ERR_INVALID_ARGUMENT, "FFT size does not factor into 2, 3, 5, 7");
     }
@@ -353,32 +375,45 @@ int rsb_fft_create(rsb_fft **out, int device, uint32_t n_streams, uint32_t chann
         }
         filt[k] = make_float2((float)re, (float)im);
     }
-    for (uint32_t m = 0; m < N1; ++m) tw1[m] = make_float2((float)cs[m], (float)-sn[m]);
-    for (uint32_t m = 0; m < N2; ++m)
-        tw2[m] = make_float2((float)std::cos(2.0 * kPi * m / N2), (float)std::sin(2.0 * kPi * m / N2));
+    // tw1 / tw2: [roots of the half-size transform | untangling roots of the full size]
+    std::vector<float2> twf(n_in), twi(n_out);
+    tw1.resize(n_in + 1);
+    tw2.resize(n_out + 1);
+    for (uint32_t m = 0; m < n_in; ++m)
+        twf[m] = make_float2((float)std::cos(2.0 * kPi * m / n_in), (float)-std::sin(2.0 * kPi * m / n_in));
+    for (uint32_t m = 0; m < n_out; ++m)
+        twi[m] = make_float2((float)std::cos(2.0 * kPi * m / n_out), (float)std::sin(2.0 * kPi * m / n_out));
+    for (uint32_t k = 0; k <= n_in; ++k) tw1[k] = make_float2((float)cs[k], (float)-sn[k]);
+    for (uint32_t k = 0; k <= n_out; ++k)
+        tw2[k] = make_float2((float)std::cos(2.0 * kPi * k / N2), (float)std::sin(2.0 * kPi * k / N2));
     auto bail = [&](const char *what) {
         rsb_fft_destroy(h);
         return fft_fail(RSB_ERR_CUDA, what);
     };
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("stream");
-    if (cudaMalloc(&h->d_tw_fwd, sizeof(float2) * N1) != cudaSuccess || cudaMalloc(&h->d_tw_inv, sizeof(float2) * N2) != cudaSuccess ||
+    if (cudaMalloc(&h->d_tw_fwd, sizeof(float2) * (2 * n_in + 1)) != cudaSuccess ||
+        cudaMalloc(&h->d_tw_inv, sizeof(float2) * (2 * n_out + 1)) != cudaSuccess ||
         cudaMalloc(&h->d_filter, sizeof(float2) * (n_in + 1)) != cudaSuccess ||
         cudaMalloc(&h->d_overlap, 2 * sizeof(float) * (size_t)n_streams * channels * n_out) != cudaSuccess)
         return bail("out of device memory");
-    cudaMemcpy(h->d_tw_fwd, tw1.data(), sizeof(float2) * N1, cudaMemcpyHostToDevice);
-    cudaMemcpy(h->d_tw_inv, tw2.data(), sizeof(float2) * N2, cudaMemcpyHostToDevice);
+    cudaMemcpy(h->d_tw_fwd, twf.data(), sizeof(float2) * n_in, cudaMemcpyHostToDevice);
+    cudaMemcpy(h->d_tw_fwd + n_in, tw1.data(), sizeof(float2) * (n_in + 1), cudaMemcpyHostToDevice);
+    cudaMemcpy(h->d_tw_inv, twi.data(), sizeof(float2) * n_out, cudaMemcpyHostToDevice);
+    cudaMemcpy(h->d_tw_inv + n_out, tw2.data(), sizeof(float2) * (n_out + 1), cudaMemcpyHostToDevice);
     cudaMemcpy(h->d_filter, filt.data(), sizeof(float2) * (n_in + 1), cudaMemcpyHostToDevice);
     cudaMemset(h->d_overlap, 0, 2 * sizeof(float) * (size_t)n_streams * channels * n_out);
     h->ov_sel.assign(n_streams, 0);
     P.tw_fwd = h->d_tw_fwd;
     P.tw_inv = h->d_tw_inv;
+    P.tw_post = h->d_tw_fwd + n_in;
+    P.tw_pre = h->d_tw_inv + n_out;
     P.filter = h->d_filter;
     P.overlap = h->d_overlap;
     P.n_in = n_in;
     P.n_out = n_out;
     P.new_length = h->new_length;
     P.channels = channels;
-    P.buf_len = std::max(N1, N2);
+    P.buf_len = std::max(n_in, n_out + 1);
     h->smem = sizeof(float2) * 2 * P.buf_len + sizeof(float) * (size_t)channels * (n_in + 2 * n_out);
     if (h->smem > 227 * 1024) return bail("channel count too large for this FFT size");
     if (cudaFuncSetAttribute(fft_resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess)
