@@ -6,7 +6,7 @@ OUT = resampler_b200/lib
 NVFLAGS = $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -ffp-contract=off \
           -Xcompiler -Wall -Xptxas -v
 HDRS = $(CSRC)/planner.h $(CSRC)/fir_common.h $(CSRC)/fir_kernels.h $(CSRC)/filter_design.h \
-       $(CSRC)/sm100_ptx.cuh $(CSRC)/pcm_ingest.h $(CSRC)/filter_design_device.h \
+       $(CSRC)/sm100_ptx.cuh $(CSRC)/pcm_ingest.h $(CSRC)/filter_design_device.h $(CSRC)/fir_submit.h $(CSRC)/sinf_glibc.h \
        include/resampler_b200.h
 
 all: $(OUT)/libresampler_b200.so oracle

@@ -26,6 +26,7 @@
 #include "filter_design.h"
 #include "filter_design_device.h"
 #include "fir_kernels.h"
+#include "fir_submit.h"
 #include "pcm_ingest.h"
 
 namespace {
@@ -170,7 +171,7 @@ struct rsb_fir {
     struct FusedSlot {
         PinBuf h_jobs, h_res;
         DevBuf d_jobs, d_res, d_segs;
-        cudaEvent_t ev_done = nullptr;
+        cudaEvent_t ev_done = nullptr, ev_plan = nullptr;
         bool active = false;
         uint32_t n = 0;
         uint64_t seq = 0;
@@ -1116,16 +1117,33 @@ int run_submit_fused(rsb_fir *h, uint32_t n, const uint32_t *streams, const floa
         h->m_pending[s] = ~0ull;      // no general-path read-back may refresh this stream any more
     }
     cudaStream_t s = h->stream, sp = h->plan_stream;
-    // the streams' scalar state is otherwise touched on the plan stream: order the two
-    RSB_CUDA(cudaEventRecord(h->ev_sync, sp));
-    RSB_CUDA(cudaStreamWaitEvent(s, h->ev_sync, 0));
-    RSB_CUDA(cudaMemcpyAsync(F.d_jobs.p, hj, sizeof(rsb::SubmitJob) * n, cudaMemcpyHostToDevice, s));
-    rsb::launch_submit_fused(F.d_jobs.as<rsb::SubmitJob>(), F.d_res.as<rsb::SubmitResult>(), n, h->st,
-                             h->d_coeffs, h->ratio, h->taps, ch, max_in, F.d_segs.as<rsb::PlanSeg>(), s);
-    RSB_CUDA(cudaGetLastError());
-    RSB_CUDA(cudaMemcpyAsync(F.h_res.p, F.d_res.p, sizeof(rsb::SubmitResult) * n, cudaMemcpyDeviceToHost, s));
-    RSB_CUDA(cudaEventRecord(F.ev_done, s));
-    RSB_CUDA(cudaStreamWaitEvent(sp, F.ev_done, 0));
+    if (rsb::submit_two_stage(h->taps, ch, max_in)) {
+        // Stage 1 on the plan stream (job table up, planner kernel, result records down): it touches
+        // the scalar stream state only, so it runs underneath the previous submit's convolution.
+        // Stage 2 (samples, history) on the main stream behind it.
+        if (!F.ev_plan) RSB_CUDA(cudaEventCreateWithFlags(&F.ev_plan, cudaEventDisableTiming));
+        RSB_CUDA(cudaMemcpyAsync(F.d_jobs.p, hj, sizeof(rsb::SubmitJob) * n, cudaMemcpyHostToDevice, sp));
+        rsb::launch_submit_plan(F.d_jobs.as<rsb::SubmitJob>(), F.d_res.as<rsb::SubmitResult>(), n, h->st, h->ratio,
+                                h->taps, F.d_segs.as<rsb::PlanSeg>(), sp);
+        RSB_CUDA(cudaMemcpyAsync(F.h_res.p, F.d_res.p, sizeof(rsb::SubmitResult) * n, cudaMemcpyDeviceToHost, sp));
+        RSB_CUDA(cudaEventRecord(F.ev_plan, sp));
+        RSB_CUDA(cudaStreamWaitEvent(s, F.ev_plan, 0));
+        rsb::launch_submit_conv(F.d_jobs.as<rsb::SubmitJob>(), F.d_res.as<rsb::SubmitResult>(), n, h->d_coeffs, h->taps,
+                                ch, max_in, F.d_segs.as<rsb::PlanSeg>(), s);
+        RSB_CUDA(cudaGetLastError());
+        RSB_CUDA(cudaEventRecord(F.ev_done, s));
+    } else {
+        // single-launch fallback: the kernel touches the scalar state on the main stream: order the two
+        RSB_CUDA(cudaEventRecord(h->ev_sync, sp));
+        RSB_CUDA(cudaStreamWaitEvent(s, h->ev_sync, 0));
+        RSB_CUDA(cudaMemcpyAsync(F.d_jobs.p, hj, sizeof(rsb::SubmitJob) * n, cudaMemcpyHostToDevice, s));
+        rsb::launch_submit_fused(F.d_jobs.as<rsb::SubmitJob>(), F.d_res.as<rsb::SubmitResult>(), n, h->st,
+                                 h->d_coeffs, h->ratio, h->taps, ch, max_in, F.d_segs.as<rsb::PlanSeg>(), s);
+        RSB_CUDA(cudaGetLastError());
+        RSB_CUDA(cudaMemcpyAsync(F.h_res.p, F.d_res.p, sizeof(rsb::SubmitResult) * n, cudaMemcpyDeviceToHost, s));
+        RSB_CUDA(cudaEventRecord(F.ev_done, s));
+        RSB_CUDA(cudaStreamWaitEvent(sp, F.ev_done, 0));
+    }
     h->launches += 2;      // plan + convolution (one launch on the half-warp fallback)
     h->last_kernel = RSB_KERNEL_EXACT;
     F.active = true;
@@ -1459,6 +1477,7 @@ void rsb_fir_destroy(rsb_fir *h) {
     for (auto &F : h->fused) {
         F.h_jobs.release(); F.h_res.release(); F.d_jobs.release(); F.d_res.release(); F.d_segs.release();
         if (F.ev_done) cudaEventDestroy(F.ev_done);
+        if (F.ev_plan) cudaEventDestroy(F.ev_plan);
     }
     for (int b = 0; b < 2; ++b) {
         h->pipe.d_in[b].release();

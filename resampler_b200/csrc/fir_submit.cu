@@ -17,7 +17,7 @@
 //      scalars (position, buffered frames) back to the device state and to the result record.
 #include <cstdlib>
 
-#include "fir_kernels.h"
+#include "fir_submit.h"
 
 namespace rsb {
 
@@ -426,26 +426,50 @@ static size_t tp_smem_bytes(uint32_t taps, uint32_t ch, uint32_t max_in_frames, 
     return c_bytes + want * sizeof(float);
 }
 
-void launch_submit_fused(const SubmitJob *jobs, SubmitResult *results, uint32_t n_jobs, StreamStateDev st,
-                         const float *coeffs, double ratio, uint32_t taps, uint32_t channels,
-                         uint32_t max_in_frames, PlanSeg *seg_store, cudaStream_t stream) {
+// Two-stage form (planner kernel, then the thread-per-output convolution) available for this geometry?
+bool submit_two_stage(uint32_t taps, uint32_t channels, uint32_t max_in_frames) {
+    uint32_t rpw = 0, xw = 0;
+    return !getenv("RSB_SUBMIT_HALFWARP") && tp_smem_bytes(taps, channels, max_in_frames, &rpw, &xw) != 0;
+}
+
+// Stage 1 (may run on another stream than stage 2, e.g. underneath the previous submit's convolution:
+// it touches the job table, the result records, the plan segments and the streams' scalar state only)
+void launch_submit_plan(const SubmitJob *jobs, SubmitResult *results, uint32_t n_jobs, StreamStateDev st, double ratio,
+                        uint32_t taps, PlanSeg *seg_store, cudaStream_t stream) {
+    if (n_jobs == 0) return;
+    const uint32_t grid = (n_jobs + 7) / 8;
+    switch (taps) {
+        case 16: submit_plan_kernel<16><<<grid, 256, 0, stream>>>(jobs, results, n_jobs, st, ratio, seg_store); break;
+        case 32: submit_plan_kernel<32><<<grid, 256, 0, stream>>>(jobs, results, n_jobs, st, ratio, seg_store); break;
+        case 64: submit_plan_kernel<64><<<grid, 256, 0, stream>>>(jobs, results, n_jobs, st, ratio, seg_store); break;
+        default: submit_plan_kernel<128><<<grid, 256, 0, stream>>>(jobs, results, n_jobs, st, ratio, seg_store); break;
+    }
+}
+
+// Stage 2: samples and the new history
+void launch_submit_conv(const SubmitJob *jobs, const SubmitResult *results, uint32_t n_jobs, const float *coeffs,
+                        uint32_t taps, uint32_t channels, uint32_t max_in_frames, const PlanSeg *seg_store,
+                        cudaStream_t stream) {
     if (n_jobs == 0) return;
     uint32_t rpw = 0, xw = 0;
-    const size_t smem = getenv("RSB_SUBMIT_HALFWARP") ? 0 : tp_smem_bytes(taps, channels, max_in_frames, &rpw, &xw);
-    if (smem) {
-        auto go = [&](auto plan, auto kern) {
-            plan<<<(n_jobs + 7) / 8, 256, 0, stream>>>(jobs, results, n_jobs, st, ratio, seg_store);
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            kern<<<n_jobs, kTpThreads, smem, stream>>>(jobs, results, coeffs, seg_store, channels, rpw, xw);
-        };
-        switch (taps) {
-            case 16: go(submit_plan_kernel<16>, submit_fused_tp_kernel<16>); break;
-            case 32: go(submit_plan_kernel<32>, submit_fused_tp_kernel<32>); break;
-            case 64: go(submit_plan_kernel<64>, submit_fused_tp_kernel<64>); break;
-            default: go(submit_plan_kernel<128>, submit_fused_tp_kernel<128>); break;
-        }
-        return;
+    const size_t smem = tp_smem_bytes(taps, channels, max_in_frames, &rpw, &xw);
+    auto go = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<n_jobs, kTpThreads, smem, stream>>>(jobs, results, coeffs, seg_store, channels, rpw, xw);
+    };
+    switch (taps) {
+        case 16: go(submit_fused_tp_kernel<16>); break;
+        case 32: go(submit_fused_tp_kernel<32>); break;
+        case 64: go(submit_fused_tp_kernel<64>); break;
+        default: go(submit_fused_tp_kernel<128>); break;
     }
+}
+
+// Single-launch fallback (half-warp kernel: plan, samples and state in one kernel)
+void launch_submit_fused(const SubmitJob *jobs, SubmitResult *results, uint32_t n_jobs, StreamStateDev st,
+                         const float *coeffs, double ratio, uint32_t taps, uint32_t channels,
+                         uint32_t /*max_in_frames*/, PlanSeg * /*seg_store*/, cudaStream_t stream) {
+    if (n_jobs == 0) return;
     switch (taps) {
         case 16: submit_fused_kernel<16><<<n_jobs, 256, 0, stream>>>(jobs, results, st, coeffs, ratio, channels); break;
         case 32: submit_fused_kernel<32><<<n_jobs, 256, 0, stream>>>(jobs, results, st, coeffs, ratio, channels); break;
