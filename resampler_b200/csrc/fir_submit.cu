@@ -225,6 +225,18 @@ __device__ __forceinline__ void tp_block(uint32_t idx0, uint32_t n_vals, uint32_
     const uint32_t nr = f_hi - f_lo + 1u;
     const uint32_t fr = fg - f_lo;
     const uint32_t xb = (uint32_t)s_v[fg - k0] * ch + c;
+    // Frames of the block that share a phase share one staged pair of rows (a 1 : 3 ratio cycles
+    // through three phases: 3 row pairs instead of 32; 44.1 -> 48 kHz has 160 phases: no sharing).
+    // Lane r speaks for frame f_lo + r (nr <= 32).
+    const uint32_t my_p1 = s_p1[f_lo + min(lane, nr - 1u) - k0];
+    const uint32_t same = __match_any_sync(0xffffffffu, lane < nr ? my_p1 : 0x10000u + lane);
+    const uint32_t leader = (uint32_t)__ffs((int)same) - 1u;                    // first frame with this phase
+    const uint32_t lead_mask = __ballot_sync(0xffffffffu, lane < nr && leader == lane);
+    const uint32_t n_lead = (uint32_t)__popc(lead_mask);
+    const uint32_t my_slot = (uint32_t)__popc(lead_mask & ((1u << leader) - 1u));   // staged slot of frame `lane`
+    const uint32_t fr_slot = __shfl_sync(0xffffffffu, my_slot, fr);                  // ... of this thread's frame
+    const uint32_t slot_lane = __fns(lead_mask, 0, (int)lane + 1) & 31u;             // frame that leads slot `lane`
+    const uint32_t slot_p1 = __shfl_sync(0xffffffffu, my_p1, slot_lane);             // valid for lane < n_lead
     float2 acc1[8], acc2[8];
 #pragma unroll
     for (int l = 0; l < 8; ++l) acc1[l] = acc2[l] = make_float2(0.0f, 0.0f);
@@ -232,20 +244,17 @@ __device__ __forceinline__ void tp_block(uint32_t idx0, uint32_t n_vals, uint32_
     for (int tb = 0; tb < TAPS / TB; ++tb) {
         {
             const float *src_l = coeffs + tb * TB + st_q * 4u;
-            for (uint32_t r = st_r; r < nr; r += 4u * kStageRows) {
-                // four rows per trip: the phase look-ups first, then the copies (a single row per
-                // trip exposed the shared-memory latency once per row)
+            for (uint32_t j0 = 0; j0 < n_lead; j0 += 4u * kStageRows) {   // warp-uniform trip count (shuffles inside)
+                // four row pairs per trip: the phase look-ups first, then the copies
                 uint32_t p[4];
 #pragma unroll
-                for (uint32_t u = 0; u < 4; ++u) {
-                    const uint32_t rr = min(r + u * kStageRows, nr - 1);
-                    p[u] = min((uint32_t)s_p1[f_lo + rr - k0] + st_ph, kPhases - 1);
-                }
+                for (uint32_t u = 0; u < 4; ++u)
+                    p[u] = min(__shfl_sync(0xffffffffu, slot_p1, min(j0 + u * kStageRows + st_r, 31u)) + st_ph, kPhases - 1);
 #pragma unroll
                 for (uint32_t u = 0; u < 4; ++u) {
-                    const uint32_t rr = r + u * kStageRows;
-                    if (rr < nr)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(st_dst + rr * (2u * CS * 4u)),
+                    const uint32_t j = j0 + u * kStageRows + st_r;
+                    if (j < n_lead)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(st_dst + j * (2u * CS * 4u)),
                                      "l"(src_l + (size_t)p[u] * TAPS)
                                      : "memory");
                 }
@@ -253,8 +262,8 @@ __device__ __forceinline__ void tp_block(uint32_t idx0, uint32_t n_vals, uint32_
             asm volatile("cp.async.wait_all;" ::: "memory");
         }
         __syncwarp();
-        const float4 *r1 = reinterpret_cast<const float4 *>(cw + (size_t)fr * 2u * CS);
-        const float4 *r2 = reinterpret_cast<const float4 *>(cw + (size_t)fr * 2u * CS + CS);
+        const float4 *r1 = reinterpret_cast<const float4 *>(cw + (size_t)fr_slot * 2u * CS);
+        const float4 *r2 = reinterpret_cast<const float4 *>(cw + (size_t)fr_slot * 2u * CS + CS);
         const uint32_t xq = xb + (uint32_t)tb * TB * ch;
 #pragma unroll
         for (int q = 0; q < TB / 4; ++q) {
