@@ -172,7 +172,8 @@ constexpr uint32_t kDone = 8;                      // tile-completion barriers (
 __host__ __device__ constexpr uint32_t role_threads(uint32_t st, uint32_t et) { return (4u * (st + et) + 5u) * 32u; }
 constexpr uint32_t kItemSlots = 2;
 constexpr uint32_t kListEntries = 32;               // main-pass MMA list per tile (128 bytes, after [G_hi, G_lo])
-constexpr uint32_t kListBytes = kListEntries * 4;
+constexpr uint32_t kKsTabBytes = 16;                // per K step: first active output quarter | quarters << 4
+constexpr uint32_t kListBytes = kListEntries * 4 + kKsTabBytes;
 constexpr uint32_t kListEnd = 0xffffffffu;
 constexpr float kScaleX = 16.0f;                   // 2^4
 constexpr float kScaleG = 8192.0f;                 // 2^13
@@ -306,6 +307,37 @@ __device__ __forceinline__ void tc_mma_f16_ts_list4(uint32_t n, uint32_t d0, uin
         "}" ::"r"(n),
         "r"(d0), "r"(d1), "r"(d2), "r"(d3), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(b2), "r"(b3),
         "r"(b_hi), "r"(i0), "r"(i1), "r"(i2), "r"(i3)
+        : "memory");
+}
+// As above, but the FIRST MMA honours `acc0` (a tile's very first MMA overwrites its accumulator).
+__device__ __forceinline__ void tc_mma_f16_ts_list4a(uint32_t n, uint32_t acc0, uint32_t d0, uint32_t d1, uint32_t d2,
+                                                     uint32_t d3, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                     uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3, uint32_t b_hi,
+                                                     uint32_t i0, uint32_t i1, uint32_t i2, uint32_t i3) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, t, e, e1, e2, e3;\n\t"
+        ".reg .b64 x0, x1, x2, x3;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.gt.u32 e1, %0, 1;\n\t"
+        "setp.gt.u32 e2, %0, 2;\n\t"
+        "setp.gt.u32 e3, %0, 3;\n\t"
+        "and.pred e1, e1, e;\n\t"
+        "and.pred e2, e2, e;\n\t"
+        "and.pred e3, e3, e;\n\t"
+        "mov.b64 x0, {%9, %13};\n\t"
+        "mov.b64 x1, {%10, %13};\n\t"
+        "mov.b64 x2, {%11, %13};\n\t"
+        "mov.b64 x3, {%12, %13};\n\t"
+        "setp.ne.b32 p, %18, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], [%5], x0, %14, p;\n\t"
+        "@e1 tcgen05.mma.cta_group::1.kind::f16 [%2], [%6], x1, %15, t;\n\t"
+        "@e2 tcgen05.mma.cta_group::1.kind::f16 [%3], [%7], x2, %16, t;\n\t"
+        "@e3 tcgen05.mma.cta_group::1.kind::f16 [%4], [%8], x3, %17, t;\n\t"
+        "}" ::"r"(n),
+        "r"(d0), "r"(d1), "r"(d2), "r"(d3), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(b2), "r"(b3),
+        "r"(b_hi), "r"(i0), "r"(i1), "r"(i2), "r"(i3), "r"(acc0)
         : "memory");
 }
 // TMA tensor store shared -> global of one 2-D box (SASS: UTMASTG), bulk-group completion
@@ -719,22 +751,40 @@ conv_tc2_kernel(const __grid_constant__ Tc2Params P, const __grid_constant__ CUt
                     const uint32_t ahi = tmem + kColHi, alo = tmem + kColLo;
                     constexpr uint32_t kWrapCols = kSlots * kSlotCols;
                     auto wrap = [](uint32_t c) { return c >= kWrapCols ? c - kWrapCols : c; };
-                    // small terms first: X_lo * G_hi and X_hi * G_lo, two K steps per issue block
+                    // small terms first: X_lo * G_hi and X_hi * G_lo, two K steps per issue block.  A K
+                    // step's band covers only some of the tile's four output quarters (the tile's
+                    // K-step table: first active quarter | quarters << 4): the MMA's N, accumulator
+                    // columns and G rows are trimmed to them -- the skipped blocks of G are zero, and
+                    // the tensor pipe is the kernel's largest energy consumer.  The tile's very
+                    // first pair runs at full width: it initialises the accumulator.
                     const uint32_t col0 = s0 * kSlotCols;
                     uint32_t col = col0, dk = 0, ks = 0;
                     const uint32_t n_ks_issue = (P.ablate & 32u) ? 0u : n_ks;
+                    uint32_t tw[4];
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(tw[0]), "=r"(tw[1]), "=r"(tw[2]), "=r"(tw[3])
+                                 : "r"(smem_u32(gst + (size_t)gs * g_stage_bytes + 2u * g_bytes) + kListEntries * 4u));
+                    const uint64_t tab_lo = (uint64_t)tw[0] | ((uint64_t)tw[1] << 32);
+                    const uint64_t tab_hi = (uint64_t)tw[2] | ((uint64_t)tw[3] << 32);
+                    auto ks_entry = [&](uint32_t k) -> uint32_t {
+                        const uint32_t b = (uint32_t)((k < 8u ? tab_lo >> (8u * k) : tab_hi >> (8u * (k - 8u))) & 0xffu);
+                        return (k == 0u || (P.ablate & 64u)) ? 0x40u : b;        // K step 0: full width
+                    };
+                    constexpr uint32_t kIdescNoN = kIdesc & ~(0x3fu << 17);
 #pragma unroll 2
-                    for (; ks + 2 <= n_ks_issue; ks += 2) {
+                    for (; ks < n_ks_issue; ks += 2) {
+                        const bool two = ks + 1 < n_ks_issue;
                         const uint32_t c1 = wrap(col + kSlotCols);
-                        tc_mma_f16_ts_x4(d_tmem, alo + col, ahi + col, alo + c1, ahi + c1, ghi + dk, glo + dk,
-                                         ghi + dk + kBDescKStep, glo + dk + kBDescKStep, kBDescHi, kIdesc,
-                                         ks != 0);
+                        const uint32_t e0 = ks_entry(ks), e1 = two ? ks_entry(ks + 1) : 0x40u;
+                        const uint32_t q0a = (e0 & 0xfu) * 16u, ia = kIdescNoN | (((e0 >> 4) * 2u) << 17);
+                        const uint32_t q0b = (e1 & 0xfu) * 16u, ib = kIdescNoN | (((e1 >> 4) * 2u) << 17);
+                        tc_mma_f16_ts_list4a(two ? 4u : 2u, ks != 0, d_tmem + q0a, d_tmem + q0a, d_tmem + q0b, d_tmem + q0b,
+                                             alo + col, ahi + col, alo + c1, ahi + c1, ghi + dk + q0a, glo + dk + q0a,
+                                             ghi + dk + kBDescKStep + q0b, glo + dk + kBDescKStep + q0b, kBDescHi, ia, ia,
+                                             ib, ib);
                         dk += 2 * kBDescKStep;
                         col = wrap(c1 + kSlotCols);
                     }
-                    if (ks < n_ks_issue)
-                        tc_mma_f16_ts_x2(d_tmem, alo + col, ghi + dk, ahi + col, glo + dk, kBDescHi, kIdesc,
-                                         ks != 0);
                     // X_hi * G_hi: the tile's MMA list (built with the G matrices, same stage).  Every
                     // K step appears once per output quarter: "early" (outside-in) for the quarters
                     // whose main lobe lies elsewhere, "late" for those it carries, as MMAs over
@@ -1108,8 +1158,20 @@ tc2_gmat_kernel(const UnitDev *units, const PlanEntry *entries, const float *coe
                 hi[q] = min((s_v[last] - m.k0 + TAPS / 2) / (int)kChunk, n_ks - 1);
             }
         }
+        // output quarters whose band overlaps K step ks (the other blocks of G are zero)
+        auto active = [&](int ks) {
+            uint32_t mk = 0;
+            for (uint32_t q = 0; q < 4; ++q) {
+                if (16u * q >= m.n_out) break;
+                const uint32_t last = min(16u * q + 15u, m.n_out - 1u);
+                const int d_first = s_v[16 * q] - m.k0, d_last = s_v[last] - m.k0;
+                if (16 * ks + 16 > d_first && 16 * ks < d_last + TAPS) mk |= 1u << q;
+            }
+            return mk;
+        };
         uint32_t n = 0;
         auto emit_ranges = [&](int ks, uint32_t mask) {
+            mask &= active(ks);
             for (uint32_t q = 0; q < 4;) {
                 if (!((mask >> q) & 1u)) { ++q; continue; }
                 uint32_t q1 = q;
@@ -1131,6 +1193,20 @@ tc2_gmat_kernel(const UnitDev *units, const PlanEntry *entries, const float *coe
         }
         // late: ascending, for the quarters the step is central for
         for (int ks = 0; ks < n_ks; ++ks) emit_ranges(ks, central(ks));
+        // K-step table of the lo passes: first active quarter | quarters << 4 (contiguous: the band
+        // moves monotonically through the tile); a step without any active quarter keeps full width
+        uint8_t *tab = reinterpret_cast<uint8_t *>(list + kListEntries);
+        for (int ks = 0; ks < 16; ++ks) {
+            uint32_t e = 0x40u;
+            if (ks < n_ks) {
+                const uint32_t mk = active(ks);
+                if (mk) {
+                    const uint32_t q0 = (uint32_t)__ffs((int)mk) - 1u, q1 = 31u - (uint32_t)__clz((int)mk);
+                    e = q0 | ((q1 - q0 + 1u) << 4);
+                }
+            }
+            tab[ks] = (uint8_t)e;
+        }
         for (; n < kListEntries; ++n) list[n] = kListEnd;
     }
     for (uint32_t kg = tid >> 6; kg < m.kt / 8; kg += 4) {
