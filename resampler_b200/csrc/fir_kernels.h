@@ -149,7 +149,8 @@ struct Tc2Params {
     uint32_t prefetch_chunks; // input chunks the TMA producer prefetches into L2 ahead of its loads
     uint32_t variant;         // role layout (debug / tuning; 0 = default, see kVariants in fir_tc2.cu)
     uint32_t ablate;          // debug (RSB_TC_ABLATE): 1 no G copies, 2 no input TMA, 4 no output stores,
-                              // 8 splitter: handshakes only, 16 epilogue: handshakes only, 32 one MMA per tile
+                              // 8 splitter: handshakes only, 16 epilogue: handshakes only, 32 one MMA per tile,
+                              // 64 lo-pass MMAs at full width (no trimming to the active output quarters)
     float out_scale;          // epilogue factor 2^-17 (undoes the operand prescale)
     uint32_t epi_split;       // two epilogue teams: 1 = each drains one column half of every tile, 0 = alternate tiles
     uint32_t hint_crit;       // try_wait suspend-time hint (ns) of the issuers' and the epilogue's waits
