@@ -746,7 +746,7 @@ def test_device_side_filter_design_is_bit_identical_to_the_host_design():
                 worst_ms = max(worst_ms, ms)
                 assert np.array_equal(bits(dev), bits(host)), (in_hz, out_hz, lat, att,
                                                                 int(np.sum(bits(dev) != bits(host))))
-    assert worst_ms < 5.0, worst_ms
+    assert worst_ms < 50.0, worst_ms      # generous: the bound also has to hold under compute-sanitizer
     # a rate pair nobody has designed yet, created with the device design on
     prev = set_device_filter_design(True)
     try:
