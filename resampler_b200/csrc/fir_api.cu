@@ -884,10 +884,11 @@ int run_batch(rsb_fir *h, const std::vector<JobHost> &jobs, bool single, int mem
         T.groups = (n + mpg - 1) / mpg;
         // A run of consecutive tiles is one work item: long enough to amortise filling the input
         // ring (~4 tiles; measured best at 160-190 tiles), and cut so that the items divide evenly
-        // among the CTAs: k items per CTA (at least 4), n_runs = floor(k * SMs / groups) runs.
+        // among the CTAs: k items per CTA (at least 8: with fewer the rounding of k * SMs / groups to
+        // whole runs leaves CTAs idle in small batches), n_runs = floor(k * SMs / groups) runs.
         {
             const uint64_t total = tc2_tiles * T.groups, sms = (uint64_t)h->sm_count;
-            const uint64_t k = std::max<uint64_t>(4, (total + sms * 85) / (sms * 170));
+            const uint64_t k = std::max<uint64_t>(8, (total + sms * 85) / (sms * 170));
             const uint64_t n_runs = std::max<uint64_t>(1, k * sms / T.groups);
             const uint64_t rt = (tc2_tiles + n_runs - 1) / n_runs;
             T.run_tiles = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(rt, 16), 256);
