@@ -772,12 +772,14 @@ def pcie_ceiling(lib, local, dist):
     import ctypes as C
     out = (C.c_double * 2)()
     res = {}
-    for mode, name in ((0, "h2d_alone"), (1, "d2h_alone"), (2, "duplex")):
+    for mode, name in ((0, "h2d_alone"), (1, "d2h_alone"), (2, "duplex"), (3, "duplex_2d")):
         barrier(dist, local)
-        if lib.rsb_pcie_probe(local, 512 << 20, 6, mode, out) != 0:
+        if lib.rsb_pcie_probe(local, (512 << 20) if mode != 3 else (118 << 20), 6 if mode != 3 else 24, mode, out) != 0:
             return None
         if mode == 2:
             res["h2d_duplex"], res["d2h_duplex"] = round(out[0], 2), round(out[1], 2)
+        elif mode == 3:       # 1024 rows of 115 KB: the slices the library's pipeline copies
+            res["h2d_duplex_2d_rows"], res["d2h_duplex_2d_rows"] = round(out[0], 2), round(out[1], 2)
         else:
             res[name] = round(out[mode], 2)
     return res

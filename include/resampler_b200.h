@@ -247,7 +247,8 @@ void *rsb_fir_cuda_stream(const rsb_fir *h);
  * identical to the unsliced loop), and the slices they were cut into. */
 int rsb_fir_host_pipeline_stats(const rsb_fir *h, uint64_t *batches, uint64_t *slices);
 /* Pinned-memory copy rates of the device's PCIe link in GB/s: mode 0 host->device alone (out[0]),
- * 1 device->host alone (out[1]), 2 both at once.  The ceiling host-memspace calls are held against. */
+ * 1 device->host alone (out[1]), 2 both at once, 3 both at once as 2-D copies of 1024 rows (the
+ * shape of a batch slice: one row per stream).  The ceiling host-memspace calls are held against. */
 int rsb_pcie_probe(int device, size_t bytes, int iters, int mode, double out[2]);
 
 /* ---- memory helpers ---- */

@@ -1913,7 +1913,7 @@ int rsb_fir_host_pipeline_stats(const rsb_fir *h, uint64_t *batches, uint64_t *s
 // alone, 2 both directions at once (out[0] = host->device, out[1] = device->host).  Plain
 // cudaMemcpyAsync on two streams: the ceiling the host-memspace calls are measured against.
 int rsb_pcie_probe(int device, size_t bytes, int iters, int mode, double out[2]) {
-    if (!out || bytes == 0 || iters <= 0 || mode < 0 || mode > 2)
+    if (!out || bytes == 0 || iters <= 0 || mode < 0 || mode > 3)
         return fail(RSB_ERR_INVALID_ARGUMENT, "bad probe arguments");
     if (cudaSetDevice(device) != cudaSuccess) return fail(RSB_ERR_NO_DEVICE, "no such device");
     out[0] = out[1] = 0.0;
@@ -1925,21 +1925,31 @@ int rsb_pcie_probe(int device, size_t bytes, int iters, int mode, double out[2])
         if (err != cudaSuccess && rc == RSB_OK) rc = fail(RSB_ERR_CUDA, cudaGetErrorString(err));
         return err == cudaSuccess;
     };
-    ok(cudaMallocHost(&h_up, bytes)) && ok(cudaMallocHost(&h_dn, bytes)) && ok(cudaMalloc(&d_up, bytes)) &&
+    // mode 3: both directions as 2-D copies of 1024 rows (the shape of a host-memspace batch slice:
+    // one row per stream, host rows a whole stream apart = twice the row here)
+    const size_t rows = 1024, row_bytes = ((bytes / rows) + 15) & ~(size_t)15;
+    const size_t host_bytes = mode == 3 ? 2 * row_bytes * rows : bytes;
+    if (mode == 3) bytes = row_bytes * rows;
+    ok(cudaMallocHost(&h_up, host_bytes)) && ok(cudaMallocHost(&h_dn, host_bytes)) && ok(cudaMalloc(&d_up, bytes)) &&
         ok(cudaMalloc(&d_dn, bytes)) && ok(cudaStreamCreateWithFlags(&s_up, cudaStreamNonBlocking)) &&
         ok(cudaStreamCreateWithFlags(&s_dn, cudaStreamNonBlocking));
     for (int i = 0; i < 4 && rc == RSB_OK; ++i) ok(cudaEventCreate(&e[i]));
     if (rc == RSB_OK) {
-        std::memset(h_up, 1, bytes);
-        std::memset(h_dn, 0, bytes);
+        std::memset(h_up, 1, host_bytes);
+        std::memset(h_dn, 0, host_bytes);
         const bool up = mode != 1, dn = mode != 0;
         for (int pass = 0; pass < 2 && rc == RSB_OK; ++pass) {      // pass 0 warms up
             const int reps = pass == 0 ? 1 : iters;
             if (up) ok(cudaEventRecord(e[0], s_up));
             if (dn) ok(cudaEventRecord(e[2], s_dn));
             for (int i = 0; i < reps; ++i) {
-                if (up) ok(cudaMemcpyAsync(d_up, h_up, bytes, cudaMemcpyHostToDevice, s_up));
-                if (dn) ok(cudaMemcpyAsync(h_dn, d_dn, bytes, cudaMemcpyDeviceToHost, s_dn));
+                if (mode == 3) {
+                    ok(cudaMemcpy2DAsync(d_up, row_bytes, h_up, 2 * row_bytes, row_bytes, rows, cudaMemcpyHostToDevice, s_up));
+                    ok(cudaMemcpy2DAsync(h_dn, 2 * row_bytes, d_dn, row_bytes, row_bytes, rows, cudaMemcpyDeviceToHost, s_dn));
+                } else {
+                    if (up) ok(cudaMemcpyAsync(d_up, h_up, bytes, cudaMemcpyHostToDevice, s_up));
+                    if (dn) ok(cudaMemcpyAsync(h_dn, d_dn, bytes, cudaMemcpyDeviceToHost, s_dn));
+                }
             }
             if (up) ok(cudaEventRecord(e[1], s_up));
             if (dn) ok(cudaEventRecord(e[3], s_dn));
