@@ -764,3 +764,16 @@ def test_device_side_filter_design_is_bit_identical_to_the_host_design():
         r.close()
     finally:
         set_device_filter_design(prev)
+
+
+def test_pcie_probe_reports_plausible_rates():
+    """rsb_pcie_probe (the ceiling bench.py holds the end-to-end figure against): every mode returns
+    rates of a PCIe link, and bad arguments are refused."""
+    import ctypes as C
+    from resampler_b200 import _lib
+    lib = _lib.load()
+    out = (C.c_double * 2)()
+    for mode, up, dn in ((0, True, False), (1, False, True), (2, True, True), (3, True, True)):
+        assert lib.rsb_pcie_probe(0, 64 << 20, 2, mode, out) == 0
+        assert (1.0 < out[0] < 200.0) == up and (1.0 < out[1] < 200.0) == dn, (mode, out[0], out[1])
+    assert lib.rsb_pcie_probe(0, 0, 2, 0, out) != 0 and lib.rsb_pcie_probe(0, 1 << 20, 2, 7, out) != 0
