@@ -1100,9 +1100,17 @@ int run_submit_fused(rsb_fir *h, uint32_t n, const uint32_t *streams, const floa
         in_total += J.in_frames;
         same = same && coh[s] == c0 && J.in_frames == hj[0].in_frames && J.cap_frames == hj[0].cap_frames;
     }
-    // AUTO: the tile kernels win once a submit carries tens of millions of samples
+    // AUTO: the tile kernels win once a submit carries tens of millions of samples ...
     if (h->kernel_mode != RSB_KERNEL_EXACT &&
         ((double)in_total + (double)n * (rsb::kInputCapacity / 8)) / h->ratio * ch > (double)(32ull << 20))
+        return kNotTaken;
+    // ... and much earlier when every stream makes the SAME call from the same state: then one plan
+    // and one set of filter tiles serve all streams (the tensor kernel), while this path re-reads two
+    // coefficient rows per output.  Measured crossover ~1e8 sample-taps (1024 stereo x 512 frames at
+    // 128 taps: 70 us against 113 us here; 2048 frames: 87 against 446; 4096 mono x 160 frames at 32
+    // taps stays here: 79 against 150).
+    if (h->kernel_mode == RSB_KERNEL_AUTO && same && (uint64_t)n * ch >= 64 &&
+        (double)in_total / h->ratio * ch * (double)h->taps > 1.0e8)
         return kNotTaken;
     // ---- pass 2: bookkeeping ----
     const uint64_t seq = ++h->fused_count;         // slot index of THIS submit was taken above
