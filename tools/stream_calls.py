@@ -17,12 +17,13 @@ kern = Kernel[a[6].upper()] if len(a) > 6 else Kernel.AUTO
 lib = _lib.load()
 b = FirBatch(n, ch, in_hz, out_hz, Latency(lat), Attenuation.Db90, kernel=kern)
 bso = b.buffer_size_output()
+ostr = (bso + 3) & ~3          # 16-byte aligned rows: the tensor kernel's TMA stores need them
 d_in = DeviceBuffer(0, n * call * ch)
-d_out = DeviceBuffer(0, n * bso)
+d_out = DeviceBuffer(0, n * ostr)
 assert lib.rsb_fill_synthetic(0, d_in.ptr, 0, n, call, ch, in_hz, 1) == 0
 import ctypes as C
 ins = (C.c_void_p * n)(*[d_in.ptr + 4 * s * call * ch for s in range(n)])
-outs = (C.c_void_p * n)(*[d_out.ptr + 4 * s * bso for s in range(n)])
+outs = (C.c_void_p * n)(*[d_out.ptr + 4 * s * ostr for s in range(n)])
 in_lens = (C.c_size_t * n)(*([call * ch] * n))
 out_lens = (C.c_size_t * n)(*([bso] * n))
 for reps in (20, 200):
