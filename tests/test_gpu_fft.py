@@ -77,3 +77,33 @@ def test_batch_of_streams_many_chunks_equals_chunk_by_chunk_and_reference_amplit
     lo, hi = min(b.delay(), cso // 8) * 2, cso * 3 // 4
     assert np.all(np.abs(y[0][lo:hi] - 0.5) < 0.02)
     b.close()
+
+
+def test_device_memspace_async_equals_host_memspace_and_reset_clears_the_overlap():
+    """The batched entry on device-resident buffers (RSB_FLAG_ASYNC + sync, what bench.py times) gives
+    the host-memspace result bit for bit; reset() clears the carried overlap (a second pass from a
+    reset handle reproduces the first)."""
+    from resampler_b200.fir import FLAG_ASYNC, MEM_DEVICE, DeviceBuffer
+    n, ch, i, o, chunks = 8, 2, 48000, 44100, 5
+    b = FftBatch(n, ch, i, o)
+    csi, cso = b.chunk_size_input(), b.chunk_size_output()
+    rng = np.random.default_rng(8)
+    ins = [rng.uniform(-1, 1, csi * chunks).astype(np.float32) for _ in range(n)]
+    host = b.process(ins)
+    b.reset(-1)
+    d_in, d_out = DeviceBuffer(0, n * csi * chunks), DeviceBuffer(0, n * cso * chunks)
+    for s in range(n):
+        d_in.upload(ins[s], s * csi * chunks)
+    for _ in range(2):                                  # second round after reset(): same result
+        done = b.process_ptrs([d_in.ptr + 4 * s * csi * chunks for s in range(n)], [csi * chunks] * n,
+                              [d_out.ptr + 4 * s * cso * chunks for s in range(n)], [cso * chunks] * n,
+                              memspace=MEM_DEVICE, flags=FLAG_ASYNC)
+        b.sync()
+        assert list(done[:]) == [chunks] * n
+        for s in range(n):
+            got = d_out.download(cso * chunks, s * cso * chunks)
+            assert np.array_equal(got.view(np.uint32), host[s].view(np.uint32)), s
+        b.reset(-1)
+    b.close()
+    d_in.free()
+    d_out.free()

@@ -777,3 +777,42 @@ def test_pcie_probe_reports_plausible_rates():
         assert lib.rsb_pcie_probe(0, 64 << 20, 2, mode, out) == 0
         assert (1.0 < out[0] < 200.0) == up and (1.0 < out[1] < 200.0) == dn, (mode, out[0], out[1])
     assert lib.rsb_pcie_probe(0, 0, 2, 0, out) != 0 and lib.rsb_pcie_probe(0, 1 << 20, 2, 7, out) != 0
+
+
+def test_host_pipeline_async_chained_calls_equal_synchronous_ones():
+    """RSB_FLAG_ASYNC on pipelined host-memspace calls (what bench.py's e2e leg does): two chained
+    calls followed by sync() give the counts and samples of two synchronous calls, bit for bit
+    (exact kernel), from pinned buffers."""
+    import ctypes as C
+    from resampler_b200 import _lib
+    from resampler_b200.fir import FLAG_ASYNC, MEM_HOST
+    lib = _lib.load()
+    n, ch, frames = 40, 2, 220_000          # 70 MB of input: above the pipeline threshold
+    bso_total = int(frames * 48000 / 44100) + 4400
+    in_vals, out_vals = frames * ch, bso_total * ch
+    h_in = lib.rsb_alloc_pinned(n * in_vals * 4)
+    h_out = [lib.rsb_alloc_pinned(n * out_vals * 4) for _ in range(2)]
+    src = np.ctypeslib.as_array(C.cast(h_in, C.POINTER(C.c_float)), shape=(n, in_vals))
+    src[:] = np.random.default_rng(12).uniform(-1, 1, (n, in_vals)).astype(np.float32)
+    results = {}
+    for mode, flags in (("async", FLAG_ASYNC), ("sync", 0)):
+        b = FirBatch(n, ch, 44100, 48000, Latency.Sample64, Attenuation.Db90, kernel=Kernel.EXACT)
+        outs, counts = [], []
+        for k in range(2):
+            cons, prod, calls = b.process_ptrs([h_in + 4 * s * in_vals for s in range(n)], [in_vals] * n, 512 * ch, 0,
+                                               [h_out[k] + 4 * s * out_vals for s in range(n)], [out_vals] * n,
+                                               memspace=MEM_HOST, flags=flags)
+            counts.append((list(cons[:]), list(prod[:]), list(calls[:])))
+        b.sync()
+        assert b.host_pipeline_stats()[0] == 2
+        for k in range(2):
+            a = np.ctypeslib.as_array(C.cast(h_out[k], C.POINTER(C.c_float)), shape=(n, out_vals))
+            outs.append(np.array([a[s, :counts[k][1][s]].copy() for s in range(n)]))
+        results[mode] = (counts, outs)
+        b.close()
+    assert results["async"][0] == results["sync"][0]
+    for k in range(2):
+        assert np.array_equal(results["async"][1][k].view(np.uint32), results["sync"][1][k].view(np.uint32))
+    lib.rsb_free_pinned(h_in)
+    for p in h_out:
+        lib.rsb_free_pinned(p)
