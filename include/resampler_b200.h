@@ -68,7 +68,12 @@ enum rsb_memspace { RSB_MEM_DEVICE = 0, /* pointers are device pointers on the h
  *          accumulation in tensor memory); samples within 1e-6 absolute of EXACT (measured
  *          <= 6e-7 on full-scale noise).  Serves batches whose streams share one plan and whose
  *          inputs and outputs lie at one constant stride (1, 2, 4 or 8 channels); other batches
- *          fall back to FAST / EXACT.
+ *          fall back to FAST / EXACT.  LAYOUT ADVICE: give every stream's input and output buffer
+ *          a 16-byte aligned start and lay them out at one stride that is a multiple of 16 bytes
+ *          (e.g. round buffer_size_output() up to a multiple of 4 values): the current kernel
+ *          moves rows with TMA; output rows that are not 16-byte aligned are served by its
+ *          predecessor (plain stores, ~0.7x the throughput), device input pointers that are not
+ *          by FAST / EXACT.
  *
  * Non-finite and out-of-range samples.  EXACT follows IEEE arithmetic sample by sample like the
  * reference: the same outputs become Inf / NaN, all others are bit-identical.  TENSOR and FAST
