@@ -517,10 +517,10 @@ int rsb_fft_process_batch(rsb_fft *h, uint32_t n, const uint32_t *streams, const
         }
     }
     FFT_CUDA(reserve(h->d_jobs, h->cap_jobs, sizeof(FftJob) * n));
-    // the job table is read by the kernel after this call may have returned (RSB_FLAG_ASYNC): stage it
-    // through a stream-ordered copy of a host vector that lives until the copy has been issued
+    // the job table is read by the kernel after this call may have returned (RSB_FLAG_ASYNC).  `jobs` is
+    // pageable memory: cudaMemcpyAsync returns once such a source has been staged for the DMA, so
+    // the vector may die with this call; the copy itself is ordered on the stream before the kernel
     FFT_CUDA(cudaMemcpyAsync(h->d_jobs, jobs.data(), sizeof(FftJob) * n, cudaMemcpyHostToDevice, h->stream));
-    FFT_CUDA(cudaStreamSynchronize(h->stream));          // pageable source: the copy must be complete before `jobs` dies
     if (max_chunks) {
         // the chunks' contributions are accumulated into the output: it starts from zero
         for (uint32_t i = 0; i < n; ++i)
