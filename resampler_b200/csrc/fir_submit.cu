@@ -170,10 +170,12 @@ __global__ void __launch_bounds__(256) submit_fused_kernel(const SubmitJob *jobs
 //     independently on blocks of 32 outputs (no CTA-wide barrier per block).
 //   * The two coefficient rows of an output differ from thread to thread (every output has its own
 //     phase), so a warp first copies the rows of its block's frames into shared memory with
-//     16-byte asynchronous copies (row stride TB + 4 floats: the later per-thread 16-byte reads are
-//     bank-conflict free), TB = 32 taps at a time.
+//     16-byte asynchronous copies (row stride TB + 4 floats, the phase-2 rows in a region of their
+//     own: the later per-thread 16-byte reads of eight consecutive slots touch eight different bank
+//     groups), TB = 16 taps at a time.
 constexpr uint32_t kTpThreads = 128;
 constexpr uint32_t kSuper = 512;           // frames expanded per pass
+constexpr uint32_t kTpRowsMax = 33;        // staged phases per warp at most (32 mono outputs + 1): offset of the phase-2 rows
 constexpr int kTpTapBlock = 16;            // taps staged per round (16: half the staging memory of 32, more CTAs per SM)
 
 __device__ __forceinline__ float2 fmul2(const float2 a, const float2 b) {
@@ -215,7 +217,8 @@ __device__ __forceinline__ void tp_block(uint32_t idx0, uint32_t n_vals, uint32_
     constexpr uint32_t CPR = TB / 4, kStageRows = 32u / (2u * CPR);
     // staging role of this lane: 16-byte piece st_q of phase st_ph, frames st_r, st_r + kStageRows, ...
     const uint32_t st_q = lane % CPR, st_ph = (lane / CPR) & 1u, st_r = lane / (2u * CPR);
-    const uint32_t st_dst = (uint32_t)__cvta_generic_to_shared(cw) + (st_ph * CS + st_q * 4u) * 4u;
+    // phase-1 rows from cw, phase-2 rows kTpRowsMax rows behind them: consecutive slots are CS floats apart
+    const uint32_t st_dst = (uint32_t)__cvta_generic_to_shared(cw) + (st_ph * kTpRowsMax * CS + st_q * 4u) * 4u;
     const uint32_t idx = idx0 + lane;
     const bool valid = idx < n_vals;
     const uint32_t idc = valid ? idx : n_vals - 1;
@@ -254,7 +257,7 @@ __device__ __forceinline__ void tp_block(uint32_t idx0, uint32_t n_vals, uint32_
                 for (uint32_t u = 0; u < 4; ++u) {
                     const uint32_t j = j0 + u * kStageRows + st_r;
                     if (j < n_lead)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(st_dst + j * (2u * CS * 4u)),
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(st_dst + j * (CS * 4u)),
                                      "l"(src_l + (size_t)p[u] * TAPS)
                                      : "memory");
                 }
@@ -262,8 +265,8 @@ __device__ __forceinline__ void tp_block(uint32_t idx0, uint32_t n_vals, uint32_
             asm volatile("cp.async.wait_all;" ::: "memory");
         }
         __syncwarp();
-        const float4 *r1 = reinterpret_cast<const float4 *>(cw + (size_t)fr_slot * 2u * CS);
-        const float4 *r2 = reinterpret_cast<const float4 *>(cw + (size_t)fr_slot * 2u * CS + CS);
+        const float4 *r1 = reinterpret_cast<const float4 *>(cw + (size_t)fr_slot * CS);
+        const float4 *r2 = reinterpret_cast<const float4 *>(cw + (size_t)fr_slot * CS + kTpRowsMax * CS);
         const uint32_t xq = xb + (uint32_t)tb * TB * ch;
 #pragma unroll
         for (int q = 0; q < TB / 4; ++q) {
@@ -335,15 +338,15 @@ __global__ void __launch_bounds__(256) submit_plan_kernel(const SubmitJob *jobs,
 }
 
 template <int TAPS>
-__global__ void __launch_bounds__(kTpThreads) submit_fused_tp_kernel(const SubmitJob *jobs, const SubmitResult *results,
+__global__ void __launch_bounds__(kTpThreads, 5) submit_fused_tp_kernel(const SubmitJob *jobs, const SubmitResult *results,
                                                                      const float *coeffs,
                                                                      const PlanSeg *seg_store, uint32_t ch,
                                                                      uint32_t rows_per_warp, uint32_t xw_vals) {
     constexpr int TB = TAPS < kTpTapBlock ? TAPS : kTpTapBlock;
     constexpr int CS = TB + 4;
     extern __shared__ __align__(16) float sm_tp[];
-    float *s_c = sm_tp;                                            // [4 warps][rows_per_warp][2][CS]
-    float *s_x = sm_tp + 4u * rows_per_warp * 2u * CS;             // [xw_vals]
+    float *s_c = sm_tp;                                            // [4 warps][kTpRowsMax + rows_per_warp][CS]
+    float *s_x = sm_tp + 4u * (kTpRowsMax + rows_per_warp) * CS;   // [xw_vals]
     __shared__ PlanSeg s_segs[kSubmitSegs];
     __shared__ int32_t s_v[kSuper];
     __shared__ float s_frac[kSuper];
@@ -377,7 +380,7 @@ __global__ void __launch_bounds__(kTpThreads) submit_fused_tp_kernel(const Submi
         }
     }
     __syncthreads();
-    float *cw = s_c + (size_t)warp * rows_per_warp * 2u * CS;
+    float *cw = s_c + (size_t)warp * (kTpRowsMax + rows_per_warp) * CS;
 
     for (uint32_t k0 = 0; k0 < produced; k0 += kSuper) {
         const uint32_t nf = min(kSuper, produced - k0);
@@ -425,7 +428,7 @@ static size_t tp_smem_bytes(uint32_t taps, uint32_t ch, uint32_t max_in_frames, 
     if (ch == 0 || ch > 32) return 0;
     const uint32_t tb = taps < (uint32_t)kTpTapBlock ? taps : (uint32_t)kTpTapBlock, cs = tb + 4;
     *rows_per_warp = 31u / ch + 2u;
-    const size_t c_bytes = (size_t)4 * *rows_per_warp * 2 * cs * sizeof(float);
+    const size_t c_bytes = (size_t)4 * (kTpRowsMax + *rows_per_warp) * cs * sizeof(float);
     // window: the call's new input plus the history a stream carries in steady state (taps + a few
     // frames of look-ahead); a stream holding more than that reads its window from global memory
     size_t want = ((size_t)max_in_frames + taps + 96u) * ch;
