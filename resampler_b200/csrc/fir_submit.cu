@@ -210,8 +210,8 @@ __device__ __forceinline__ float win_at(const float *s_x, const float *hist, con
 template <int TAPS, bool XS>
 __device__ __forceinline__ void tp_block(uint32_t idx0, uint32_t n_vals, uint32_t k0, uint32_t ch, const int32_t *s_v,
                                          const uint16_t *s_p1, const float *s_frac, const float *s_x, const float *hist,
-                                         const float *in, int64_t HC, const float *coeffs, float *cw, float *out,
-                                         uint32_t lane) {
+                                         const float *in, int64_t HC, const float *coeffs, float *cw, uint16_t *slot_p1,
+                                         float *out, uint32_t lane) {
     constexpr int TB = TAPS < kTpTapBlock ? TAPS : kTpTapBlock;
     constexpr int CS = TB + 4;
     constexpr uint32_t CPR = TB / 4, kStageRows = 32u / (2u * CPR);
@@ -238,8 +238,8 @@ __device__ __forceinline__ void tp_block(uint32_t idx0, uint32_t n_vals, uint32_
     const uint32_t n_lead = (uint32_t)__popc(lead_mask);
     const uint32_t my_slot = (uint32_t)__popc(lead_mask & ((1u << leader) - 1u));   // staged slot of frame `lane`
     const uint32_t fr_slot = __shfl_sync(0xffffffffu, my_slot, fr);                  // ... of this thread's frame
-    const uint32_t slot_lane = __fns(lead_mask, 0, (int)lane + 1) & 31u;             // frame that leads slot `lane`
-    const uint32_t slot_p1 = __shfl_sync(0xffffffffu, my_p1, slot_lane);             // valid for lane < n_lead
+    if (lane < nr && leader == lane) slot_p1[my_slot] = (uint16_t)my_p1;             // phase of staged slot j, j < n_lead
+    __syncwarp();
     float2 acc1[8], acc2[8];
 #pragma unroll
     for (int l = 0; l < 8; ++l) acc1[l] = acc2[l] = make_float2(0.0f, 0.0f);
@@ -247,12 +247,12 @@ __device__ __forceinline__ void tp_block(uint32_t idx0, uint32_t n_vals, uint32_
     for (int tb = 0; tb < TAPS / TB; ++tb) {
         {
             const float *src_l = coeffs + tb * TB + st_q * 4u;
-            for (uint32_t j0 = 0; j0 < n_lead; j0 += 4u * kStageRows) {   // warp-uniform trip count (shuffles inside)
+            for (uint32_t j0 = 0; j0 < n_lead; j0 += 4u * kStageRows) {
                 // four row pairs per trip: the phase look-ups first, then the copies
                 uint32_t p[4];
 #pragma unroll
                 for (uint32_t u = 0; u < 4; ++u)
-                    p[u] = min(__shfl_sync(0xffffffffu, slot_p1, min(j0 + u * kStageRows + st_r, 31u)) + st_ph, kPhases - 1);
+                    p[u] = min((uint32_t)slot_p1[min(j0 + u * kStageRows + st_r, 31u)] + st_ph, kPhases - 1);
 #pragma unroll
                 for (uint32_t u = 0; u < 4; ++u) {
                     const uint32_t j = j0 + u * kStageRows + st_r;
@@ -351,6 +351,7 @@ __global__ void __launch_bounds__(kTpThreads, 5) submit_fused_tp_kernel(const Su
     __shared__ int32_t s_v[kSuper];
     __shared__ float s_frac[kSuper];
     __shared__ uint16_t s_p1[kSuper];
+    __shared__ uint16_t s_slot[kTpThreads / 32u][32];      // per warp: phase of each staged row pair
 
     const SubmitJob job = jobs[blockIdx.x];
     const SubmitResult res = results[blockIdx.x];        // written by submit_plan_kernel
@@ -403,8 +404,8 @@ __global__ void __launch_bounds__(kTpThreads, 5) submit_fused_tp_kernel(const Su
         // ---- blocks of 32 output values, warps independent ----
         const uint32_t v0 = k0 * ch, n_vals = (k0 + nf) * ch;
         for (uint32_t idx0 = v0 + warp * 32u; idx0 < n_vals; idx0 += kTpThreads) {
-            if (xs) tp_block<TAPS, true>(idx0, n_vals, k0, ch, s_v, s_p1, s_frac, s_x, hist, in, HC, coeffs, cw, job.out, lane);
-            else tp_block<TAPS, false>(idx0, n_vals, k0, ch, s_v, s_p1, s_frac, s_x, hist, in, HC, coeffs, cw, job.out, lane);
+            if (xs) tp_block<TAPS, true>(idx0, n_vals, k0, ch, s_v, s_p1, s_frac, s_x, hist, in, HC, coeffs, cw, s_slot[warp], job.out, lane);
+            else tp_block<TAPS, false>(idx0, n_vals, k0, ch, s_v, s_p1, s_frac, s_x, hist, in, HC, coeffs, cw, s_slot[warp], job.out, lane);
         }
         __syncthreads();
     }
