@@ -93,8 +93,8 @@ enum rsb_flags {
     RSB_FLAG_NONE = 0,
     RSB_FLAG_ASYNC = 1,        /* device memspace: return after enqueueing (without it a call
                                   returns when its outputs are complete).  The count
-                                  arrays are written by rsb_fir_sync() or by the second
-                                  submit after this one (two submits may be in flight), so
+                                  arrays are written by rsb_fir_sync() or by the fourth
+                                  submit after this one (four submits may be in flight), so
                                   they must stay valid until then.  Host memspace: honoured by
                                   rsb_fir_process_batch calls that run as a pipeline of time
                                   slices (pinned buffers; counts are written at once, the output

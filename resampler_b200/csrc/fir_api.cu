@@ -166,8 +166,12 @@ struct rsb_fir {
     } tc2_key;
     DevBuf d_tct2, d_gmat2;          // 64-output tile records, fp16 G store (+ MMA lists) of tc2_key
     uint64_t tc2_cache_hits = 0;
-    // fused single-launch submits (fir_submit.cu): two slots so that one can be filled while the
-    // previous submit still runs; results are delivered when a slot is reused or at sync
+    // fused submits (fir_submit.cu): kFusedSlots of them in flight, so that the host runs ahead of the
+    // GPU and the next submits' job tables and planner kernels are queued underneath the running
+    // convolution (with two slots the host could only start on submit i once i - 2 had finished, and
+    // its enqueue + the plan stage then sat on the critical path: 69 us per 4096-call submit against
+    // a 45 us convolution); results are delivered when a slot is reused or at sync
+    static constexpr uint32_t kFusedSlots = 4;
     struct FusedSlot {
         PinBuf h_jobs, h_res;
         DevBuf d_jobs, d_res, d_segs;
@@ -177,7 +181,7 @@ struct rsb_fir {
         uint64_t seq = 0;
         std::vector<uint32_t> streams;
         size_t *consumed = nullptr, *produced = nullptr;
-    } fused[2];
+    } fused[kFusedSlots];
     uint64_t fused_count = 0;
     std::vector<uint32_t> seen_epoch;   // duplicate-stream check without clearing an array per submit
     uint32_t epoch = 0;
@@ -1023,9 +1027,12 @@ int finalize_fused(rsb_fir *h, rsb_fir::FusedSlot &F) {
 }
 
 int finalize_fused_all(rsb_fir *h) {
-    int rc = finalize_fused(h, h->fused[h->fused_count & 1]);      // older first
-    int rc2 = finalize_fused(h, h->fused[(h->fused_count + 1) & 1]);
-    return rc != RSB_OK ? rc : rc2;
+    int rc = RSB_OK;
+    for (uint32_t k = 0; k < rsb_fir::kFusedSlots; ++k) {           // oldest first
+        const int r = finalize_fused(h, h->fused[(h->fused_count + k) % rsb_fir::kFusedSlots]);
+        if (rc == RSB_OK) rc = r;
+    }
+    return rc;
 }
 
 // One launch for the whole submit (device memspace): see fir_submit.cu.
@@ -1036,7 +1043,7 @@ int run_submit_fused(rsb_fir *h, uint32_t n, const uint32_t *streams, const floa
                      const size_t *in_lens, float *const *out, const size_t *out_lens, size_t *consumed,
                      size_t *produced, uint32_t flags) {
     RSB_CUDA(cudaSetDevice(h->device));
-    rsb_fir::FusedSlot &F = h->fused[h->fused_count & 1];
+    rsb_fir::FusedSlot &F = h->fused[h->fused_count % rsb_fir::kFusedSlots];
     int rc = finalize_fused(h, F);
     if (rc != RSB_OK) return rc;
     // GPU-planned batches of the general path may still owe these streams a mirror refresh; their
@@ -1079,8 +1086,10 @@ int run_submit_fused(rsb_fir *h, uint32_t n, const uint32_t *streams, const floa
             return fail(RSB_ERR_INVALID_OUTPUT_BUFFER_SIZE, "output length of job " + std::to_string(i) +
                                                                 " is not a multiple of channels");
         if (s >= n_streams) return fail(RSB_ERR_INVALID_ARGUMENT, "bad stream index");
-        if (seen[s] == epoch) return fail(RSB_ERR_INVALID_ARGUMENT, "stream listed twice in one batch");
-        seen[s] = epoch;
+        if (streams) {      // the identity mapping cannot list a stream twice
+            if (seen[s] == epoch) return fail(RSB_ERR_INVALID_ARGUMENT, "stream listed twice in one batch");
+            seen[s] = epoch;
+        }
         if (il && !in[i]) return fail(RSB_ERR_INVALID_ARGUMENT, "null input pointer");
         if (ol && !out[i]) return fail(RSB_ERR_INVALID_ARGUMENT, "null output pointer");
         const uint64_t fin = pow2 ? il >> sh : il / ch, fout = pow2 ? ol >> sh : ol / ch;
@@ -1138,7 +1147,7 @@ int run_submit_fused(rsb_fir *h, uint32_t n, const uint32_t *streams, const floa
         RSB_CUDA(cudaEventRecord(F.ev_plan, sp));
         RSB_CUDA(cudaStreamWaitEvent(s, F.ev_plan, 0));
         rsb::launch_submit_conv(F.d_jobs.as<rsb::SubmitJob>(), F.d_res.as<rsb::SubmitResult>(), n, h->d_coeffs, h->taps,
-                                ch, max_in, F.d_segs.as<rsb::PlanSeg>(), s);
+                                ch, max_in, F.d_segs.as<rsb::PlanSeg>(), h->in_hz, h->out_hz, s);
         RSB_CUDA(cudaGetLastError());
         RSB_CUDA(cudaEventRecord(F.ev_done, s));
     } else {

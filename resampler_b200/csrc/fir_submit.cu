@@ -304,6 +304,110 @@ __device__ __forceinline__ void tp_block(uint32_t idx0, uint32_t n_vals, uint32_
     if (valid) out[idx] = y;
 }
 
+// Integer-ratio runs.  When out_hz / gcd = P is small the phases cycle with period P: output frames
+// k, k + P, k + 2 P, ... share their two coefficient rows and their windows slide by D = in_hz / gcd
+// input frames.  A lane = (group, residue r of the cycle, channel) then computes M such outputs with
+// ONE pair of 16-byte coefficient loads per tap quad (straight from the table: the P row pairs in use
+// stay in L1) and, for D == 1, a sliding window of M + 3 input values -- a third of the
+// L1 / shared-memory traffic of tp_block(), which is that kernel's limiter.  The arithmetic is the
+// same per-lane FMA chains, unfused blend and halving tree, evaluated lane group by lane group
+// (zmm lanes 0-3 and 8-11, then 4-7 and 12-15) so that only 8 accumulators per output are live:
+// bit-identical.  The block covers (32 / (P ch)) P M consecutive frames starting at fb; the plan is
+// CHECKED (same phase, offsets D apart) and the block handed to tp_block() when it does not hold.
+constexpr int kRunM = 3;
+template <int TAPS, int M, bool SLIDE>
+__device__ __forceinline__ bool tp_run_block(uint32_t fb, uint32_t k0, uint32_t ch, uint32_t P, uint32_t D, const int32_t *s_v,
+                                             const uint16_t *s_p1, const float *s_frac, const float *s_x,
+                                             const float *coeffs, float *out, uint32_t lane) {
+    const uint32_t L = P * ch, G = 32u / L;
+    const uint32_t g_raw = lane / L, w = lane - g_raw * L;
+    const bool on = g_raw < G;
+    const uint32_t g = on ? g_raw : 0u;              // spare lanes shadow group 0 (no store)
+    const uint32_t r = w / ch, c = w - r * ch;
+    const uint32_t f_first = fb + g * (P * M) + r;   // this lane's first frame of the call
+    const uint32_t f0 = f_first - k0;                // ... in the pass tables
+    const int32_t v0 = s_v[f0];
+    const uint32_t p1 = s_p1[f0];
+    bool ok = true;
+    float omf[M], fr[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const uint32_t f = f0 + (uint32_t)m * P;
+        ok = ok && s_v[f] == v0 + (int32_t)((uint32_t)m * D) && s_p1[f] == p1;
+        fr[m] = s_frac[f];
+        omf[m] = __fsub_rn(1.0f, fr[m]);
+    }
+    if (!__all_sync(0xffffffffu, ok)) return false;
+    const float4 *c1 = reinterpret_cast<const float4 *>(coeffs + (size_t)p1 * TAPS);
+    const float4 *c2 = reinterpret_cast<const float4 *>(coeffs + (size_t)min(p1 + 1u, kPhases - 1) * TAPS);
+    const float *xp = s_x + (size_t)v0 * ch + c;     // tap t of output m: xp[(t + m D) ch]
+    float s8a[M][4], y[M];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        float s8[M][4];
+#pragma unroll
+        for (int hi = 0; hi < 2; ++hi) {
+            const int q = half + 2 * hi;             // zmm lanes 4 q .. 4 q + 3
+            float a1[M][4], a2[M][4];
+#pragma unroll
+            for (int m = 0; m < M; ++m)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) a1[m][e] = a2[m][e] = 0.0f;
+#pragma unroll(TAPS / 16 > 2 ? 2 : TAPS / 16)
+            for (int j = 0; j < TAPS / 16; ++j) {
+                const float4 k1 = __ldg(c1 + 4 * j + q), k2 = __ldg(c2 + 4 * j + q);
+                const float k1v[4] = {k1.x, k1.y, k1.z, k1.w}, k2v[4] = {k2.x, k2.y, k2.z, k2.w};
+                const float *xq = xp + (size_t)(16 * j + 4 * q) * ch;
+                if (SLIDE) {
+                    float xv[M + 3];
+#pragma unroll
+                    for (int i = 0; i < M + 3; ++i) xv[i] = xq[(uint32_t)i * ch];
+#pragma unroll
+                    for (int m = 0; m < M; ++m)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            a1[m][e] = __fmaf_rn(k1v[e], xv[m + e], a1[m][e]);
+                            a2[m][e] = __fmaf_rn(k2v[e], xv[m + e], a2[m][e]);
+                        }
+                } else {
+#pragma unroll
+                    for (int m = 0; m < M; ++m)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float x = xq[((uint32_t)m * D + (uint32_t)e) * ch];
+                            a1[m][e] = __fmaf_rn(k1v[e], x, a1[m][e]);
+                            a2[m][e] = __fmaf_rn(k2v[e], x, a2[m][e]);
+                        }
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < M; ++m)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float t = __fadd_rn(__fmul_rn(a1[m][e], omf[m]), __fmul_rn(a2[m][e], fr[m]));   // blend, unfused
+                    s8[m][e] = hi == 0 ? t : __fadd_rn(s8[m][e], t);                                     // lanes l += l + 8
+                }
+        }
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            if (half == 0) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) s8a[m][e] = s8[m][e];
+            } else {
+                float s4[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) s4[e] = __fadd_rn(s8a[m][e], s8[m][e]);                      // l += l + 4
+                y[m] = __fadd_rn(__fadd_rn(s4[0], s4[2]), __fadd_rn(s4[1], s4[3]));                     // l += l + 2, l += l + 1
+            }
+        }
+    }
+    if (on) {
+#pragma unroll
+        for (int m = 0; m < M; ++m) out[(size_t)(f_first + (uint32_t)m * P) * ch + c] = y[m];
+    }
+    return true;
+}
+
 // The serial part, one call per WARP (lane 0 works: calls of different sizes take different paths
 // through the planner, 32 of them in one warp would run one after the other): exact phase plan of
 // the call (planner.h) from the stream's state -> result record, plan segments, new scalar state.
@@ -341,7 +445,8 @@ template <int TAPS>
 __global__ void __launch_bounds__(kTpThreads, 5) submit_fused_tp_kernel(const SubmitJob *jobs, const SubmitResult *results,
                                                                      const float *coeffs,
                                                                      const PlanSeg *seg_store, uint32_t ch,
-                                                                     uint32_t rows_per_warp, uint32_t xw_vals) {
+                                                                     uint32_t rows_per_warp, uint32_t xw_vals,
+                                                                     uint32_t run_p, uint32_t run_d) {
     constexpr int TB = TAPS < kTpTapBlock ? TAPS : kTpTapBlock;
     constexpr int CS = TB + 4;
     extern __shared__ __align__(16) float sm_tp[];
@@ -403,9 +508,25 @@ __global__ void __launch_bounds__(kTpThreads, 5) submit_fused_tp_kernel(const Su
         __syncthreads();
         // ---- blocks of 32 output values, warps independent ----
         const uint32_t v0 = k0 * ch, n_vals = (k0 + nf) * ch;
-        for (uint32_t idx0 = v0 + warp * 32u; idx0 < n_vals; idx0 += kTpThreads) {
-            if (xs) tp_block<TAPS, true>(idx0, n_vals, k0, ch, s_v, s_p1, s_frac, s_x, hist, in, HC, coeffs, cw, s_slot[warp], job.out, lane);
-            else tp_block<TAPS, false>(idx0, n_vals, k0, ch, s_v, s_p1, s_frac, s_x, hist, in, HC, coeffs, cw, s_slot[warp], job.out, lane);
+        if (run_p != 0 && xs) {
+            // integer-ratio runs, whole blocks only; ragged ends and blocks whose plan is not periodic
+            // take the general routine
+            const uint32_t bf = (32u / (run_p * ch)) * run_p * (uint32_t)kRunM;
+            for (uint32_t fb = k0 + warp * bf; fb < k0 + nf; fb += (kTpThreads / 32u) * bf) {
+                const uint32_t fe = min(fb + bf, k0 + nf);
+                bool done = false;
+                if (fe - fb == bf)
+                    done = run_d == 1u ? tp_run_block<TAPS, kRunM, true>(fb, k0, ch, run_p, run_d, s_v, s_p1, s_frac, s_x, coeffs, job.out, lane)
+                                       : tp_run_block<TAPS, kRunM, false>(fb, k0, ch, run_p, run_d, s_v, s_p1, s_frac, s_x, coeffs, job.out, lane);
+                if (!done)
+                    for (uint32_t idx0 = fb * ch; idx0 < fe * ch; idx0 += 32u)
+                        tp_block<TAPS, true>(idx0, fe * ch, k0, ch, s_v, s_p1, s_frac, s_x, hist, in, HC, coeffs, cw, s_slot[warp], job.out, lane);
+            }
+        } else {
+            for (uint32_t idx0 = v0 + warp * 32u; idx0 < n_vals; idx0 += kTpThreads) {
+                if (xs) tp_block<TAPS, true>(idx0, n_vals, k0, ch, s_v, s_p1, s_frac, s_x, hist, in, HC, coeffs, cw, s_slot[warp], job.out, lane);
+                else tp_block<TAPS, false>(idx0, n_vals, k0, ch, s_v, s_p1, s_frac, s_x, hist, in, HC, coeffs, cw, s_slot[warp], job.out, lane);
+            }
         }
         __syncthreads();
     }
@@ -462,19 +583,34 @@ void launch_submit_plan(const SubmitJob *jobs, SubmitResult *results, uint32_t n
 // Stage 2: samples and the new history
 void launch_submit_conv(const SubmitJob *jobs, const SubmitResult *results, uint32_t n_jobs, const float *coeffs,
                         uint32_t taps, uint32_t channels, uint32_t max_in_frames, const PlanSeg *seg_store,
-                        cudaStream_t stream) {
+                        uint32_t in_hz, uint32_t out_hz, cudaStream_t stream) {
     if (n_jobs == 0) return;
     uint32_t rpw = 0, xw = 0;
     const size_t smem = tp_smem_bytes(taps, channels, max_in_frames, &rpw, &xw);
-    auto go = [&](auto kern) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<n_jobs, kTpThreads, smem, stream>>>(jobs, results, coeffs, seg_store, channels, rpw, xw);
+    // integer-ratio runs (tp_run_block): phase cycle P = out_hz / gcd short enough for two or more
+    // (cycle x channels) groups per warp
+    uint32_t a = in_hz, g = out_hz;
+    while (a) { const uint32_t t = g % a; g = a; a = t; }
+    uint32_t run_p = g ? out_hz / g : 0, run_d = g ? in_hz / g : 0;
+    if (run_p == 0 || run_p * channels > 16u || run_d > 64u || getenv("RSB_SUBMIT_NO_RUNS")) run_p = 0;
+    auto go = [&](auto kern, int which) {
+        // the opt-in is per kernel and device: repeated only when a submit needs more than any before
+        // it on this device (a few microseconds of host time per call otherwise)
+        static size_t granted[4][64];
+        int dev = 0;
+        cudaGetDevice(&dev);
+        size_t &have = granted[which][dev & 63];
+        if (smem > have) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            have = smem;
+        }
+        kern<<<n_jobs, kTpThreads, smem, stream>>>(jobs, results, coeffs, seg_store, channels, rpw, xw, run_p, run_d);
     };
     switch (taps) {
-        case 16: go(submit_fused_tp_kernel<16>); break;
-        case 32: go(submit_fused_tp_kernel<32>); break;
-        case 64: go(submit_fused_tp_kernel<64>); break;
-        default: go(submit_fused_tp_kernel<128>); break;
+        case 16: go(submit_fused_tp_kernel<16>, 0); break;
+        case 32: go(submit_fused_tp_kernel<32>, 1); break;
+        case 64: go(submit_fused_tp_kernel<64>, 2); break;
+        default: go(submit_fused_tp_kernel<128>, 3); break;
     }
 }
 

@@ -9,6 +9,6 @@ void launch_submit_plan(const SubmitJob *jobs, SubmitResult *results, uint32_t n
                         uint32_t taps, PlanSeg *seg_store, cudaStream_t stream);
 void launch_submit_conv(const SubmitJob *jobs, const SubmitResult *results, uint32_t n_jobs, const float *coeffs,
                         uint32_t taps, uint32_t channels, uint32_t max_in_frames, const PlanSeg *seg_store,
-                        cudaStream_t stream);
+                        uint32_t in_hz, uint32_t out_hz, cudaStream_t stream);
 
 }  // namespace rsb

@@ -388,12 +388,12 @@ class FirBatch:
 
     def _hold(self, arrays) -> None:
         """Count arrays of an async call are written when a later call (or sync) completes it:
-        keep the most recent ones alive (two submits can be in flight)."""
+        keep the most recent ones alive (four submits can be in flight)."""
         keep = getattr(self, "_keep", None)
         if keep is None:
             keep = self._keep = []
         keep.append(arrays)
-        del keep[:-4]
+        del keep[:-8]
 
     def sync(self) -> None:
         _check(self._lib.rsb_fir_sync(self._h))

@@ -676,6 +676,12 @@ def test_config5_share_time_sliced_with_state_carry_matches_oracle():
     (1, 48000, 8000, 1, 2, [160, 480, 960]),                  # ratio 6
     (1, 8000, 48000, 3, 1, [1, 80, 160]),                     # ratio 1/6, 128 taps
     (2, 1000003, 999983, 2, 1, [512, 4096, 5000]),            # near-unity arbitrary rates, > capacity offers
+    # integer-ratio runs (tp_run_block): phase cycle 3 / 2 / 1, sliding (D = 1) and strided windows
+    (2, 16000, 48000, 1, 1, [45, 160, 333, 480]),             # cycle 3, stereo, 32 taps
+    (1, 32000, 48000, 2, 1, [100, 320, 479]),                 # cycle 3, windows 2 frames apart, 64 taps
+    (2, 44100, 88200, 3, 2, [256, 441]),                      # cycle 2, 128 taps
+    (4, 48000, 32000, 0, 0, [96, 480]),                       # cycle 2, windows 3 apart, 4 channels, 16 taps
+    (1, 48000, 48000, 1, 0, [100, 480]),                      # ratio 1: one phase
 ])
 def test_fused_submit_configurations_bit_exact(ch, in_hz, out_hz, lat, att, sizes):
     """The single-launch submit kernels (thread-per-output variant, fir_submit.cu) over channel

@@ -1,4 +1,4 @@
-# A/B of the submit kernels: build/ab/libold.so against the in-tree library (exact kernel forced so that
+# A/B of the submit path: build/ab/libold.so against the in-tree library (exact kernel forced so that
 # AUTO's tile-path crossover does not hide the thread-per-output kernel)
 L=resampler_b200/lib/libresampler_b200.so
 cp $L build/ab/libnew.so
@@ -11,4 +11,4 @@ for v in old new old new; do
   python tools/stream_calls.py 512 8 96000 48000 2 512 exact 2>&1 | tail -1
 done
 cp build/ab/libnew.so $L
-python -m pytest tests/test_gpu_parity.py -q -x -k "submit or fused or divergent" 2>&1 | tail -2
+python -m pytest tests/test_gpu_parity.py -q -x -k "submit or fused or divergent or async or handoff" 2>&1 | tail -2
