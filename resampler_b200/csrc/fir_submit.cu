@@ -314,7 +314,7 @@ __device__ __forceinline__ void tp_block(uint32_t idx0, uint32_t n_vals, uint32_
 // (zmm lanes 0-3 and 8-11, then 4-7 and 12-15) so that only 8 accumulators per output are live:
 // bit-identical.  The block covers (32 / (P ch)) P M consecutive frames starting at fb; the plan is
 // CHECKED (same phase, offsets D apart) and the block handed to tp_block() when it does not hold.
-constexpr int kRunM = 3;
+constexpr int kRunM = 3;      // outputs per lane (4 for 16 / 32 taps with sliding windows, see the kernel)
 template <int TAPS, int M, bool SLIDE>
 __device__ __forceinline__ bool tp_run_block(uint32_t fb, uint32_t k0, uint32_t ch, uint32_t P, uint32_t D, const int32_t *s_v,
                                              const uint16_t *s_p1, const float *s_frac, const float *s_x,
@@ -511,13 +511,21 @@ __global__ void __launch_bounds__(kTpThreads, 5) submit_fused_tp_kernel(const Su
         if (run_p != 0 && xs) {
             // integer-ratio runs, whole blocks only; ragged ends and blocks whose plan is not periodic
             // take the general routine
-            const uint32_t bf = (32u / (run_p * ch)) * run_p * (uint32_t)kRunM;
+            // outputs per lane: 4 with sliding windows at 16 / 32 taps, else 3 (registers; with strided
+            // windows 4 also puts the groups of an 8-channel batch on the same banks: 35 -> 50 us)
+            const bool wide = TAPS <= 32 && run_d == 1u;
+            const uint32_t bf = (32u / (run_p * ch)) * run_p * (wide ? 4u : (uint32_t)kRunM);
             for (uint32_t fb = k0 + warp * bf; fb < k0 + nf; fb += (kTpThreads / 32u) * bf) {
                 const uint32_t fe = min(fb + bf, k0 + nf);
                 bool done = false;
-                if (fe - fb == bf)
-                    done = run_d == 1u ? tp_run_block<TAPS, kRunM, true>(fb, k0, ch, run_p, run_d, s_v, s_p1, s_frac, s_x, coeffs, job.out, lane)
-                                       : tp_run_block<TAPS, kRunM, false>(fb, k0, ch, run_p, run_d, s_v, s_p1, s_frac, s_x, coeffs, job.out, lane);
+                if (fe - fb == bf) {
+                    if constexpr (TAPS <= 32) {
+                        if (wide) done = tp_run_block<TAPS, 4, true>(fb, k0, ch, run_p, run_d, s_v, s_p1, s_frac, s_x, coeffs, job.out, lane);
+                    }
+                    if (!wide)
+                        done = run_d == 1u ? tp_run_block<TAPS, kRunM, true>(fb, k0, ch, run_p, run_d, s_v, s_p1, s_frac, s_x, coeffs, job.out, lane)
+                                           : tp_run_block<TAPS, kRunM, false>(fb, k0, ch, run_p, run_d, s_v, s_p1, s_frac, s_x, coeffs, job.out, lane);
+                }
                 if (!done)
                     for (uint32_t idx0 = fb * ch; idx0 < fe * ch; idx0 += 32u)
                         tp_block<TAPS, true>(idx0, fe * ch, k0, ch, s_v, s_p1, s_frac, s_x, hist, in, HC, coeffs, cw, s_slot[warp], job.out, lane);
