@@ -408,6 +408,26 @@ __device__ __forceinline__ bool tp_run_block(uint32_t fb, uint32_t k0, uint32_t 
     return true;
 }
 
+// m outputs per lane (a whole block: 3 or 4; the ragged end of a pass: whatever whole units remain)
+template <int TAPS>
+__device__ __forceinline__ bool tp_run_dispatch(uint32_t m, bool slide, uint32_t fb, uint32_t k0, uint32_t ch, uint32_t P,
+                                                uint32_t D, const int32_t *s_v, const uint16_t *s_p1, const float *s_frac,
+                                                const float *s_x, const float *coeffs, float *out, uint32_t lane) {
+#define RSB_RUN(M_) \
+    (slide ? tp_run_block<TAPS, M_, true>(fb, k0, ch, P, D, s_v, s_p1, s_frac, s_x, coeffs, out, lane) \
+           : tp_run_block<TAPS, M_, false>(fb, k0, ch, P, D, s_v, s_p1, s_frac, s_x, coeffs, out, lane))
+    switch (m) {
+        case 4:
+            if constexpr (TAPS <= 32) return tp_run_block<TAPS, 4, true>(fb, k0, ch, P, D, s_v, s_p1, s_frac, s_x, coeffs, out, lane);
+            else return false;
+        case 3: return RSB_RUN(3);
+        case 2: return RSB_RUN(2);
+        case 1: return RSB_RUN(1);
+        default: return false;
+    }
+#undef RSB_RUN
+}
+
 // The serial part, one call per WARP (lane 0 works: calls of different sizes take different paths
 // through the planner, 32 of them in one warp would run one after the other): exact phase plan of
 // the call (planner.h) from the stream's state -> result record, plan segments, new scalar state.
@@ -488,8 +508,16 @@ __global__ void __launch_bounds__(kTpThreads, 5) submit_fused_tp_kernel(const Su
     __syncthreads();
     float *cw = s_c + (size_t)warp * (kTpRowsMax + rows_per_warp) * CS;
 
-    for (uint32_t k0 = 0; k0 < produced; k0 += kSuper) {
-        const uint32_t nf = min(kSuper, produced - k0);
+    // integer-ratio runs (tp_run_block): outputs per lane 4 with sliding windows at 16 / 32 taps, else 3
+    // (registers; with strided windows 4 also puts the groups of an 8-channel batch on the same banks:
+    // 35 -> 50 us); a pass is a whole number of blocks
+    const bool runs = run_p != 0 && xs;
+    const bool wide = TAPS <= 32 && run_d == 1u;
+    const uint32_t unit = runs ? (32u / (run_p * ch)) * run_p : 1u;         // frames per output-per-lane
+    const uint32_t bf = unit * (wide ? 4u : (uint32_t)kRunM);
+    const uint32_t pass = runs ? (kSuper / bf) * bf : kSuper;
+    for (uint32_t k0 = 0; k0 < produced; k0 += pass) {
+        const uint32_t nf = min(pass, produced - k0);
         // ---- per-frame plan of this pass ----
         for (uint32_t i = tid; i < nf; i += kTpThreads) {
             const uint32_t o = k0 + i;
@@ -508,27 +536,18 @@ __global__ void __launch_bounds__(kTpThreads, 5) submit_fused_tp_kernel(const Su
         __syncthreads();
         // ---- blocks of 32 output values, warps independent ----
         const uint32_t v0 = k0 * ch, n_vals = (k0 + nf) * ch;
-        if (run_p != 0 && xs) {
-            // integer-ratio runs, whole blocks only; ragged ends and blocks whose plan is not periodic
-            // take the general routine
-            // outputs per lane: 4 with sliding windows at 16 / 32 taps, else 3 (registers; with strided
-            // windows 4 also puts the groups of an 8-channel batch on the same banks: 35 -> 50 us)
-            const bool wide = TAPS <= 32 && run_d == 1u;
-            const uint32_t bf = (32u / (run_p * ch)) * run_p * (wide ? 4u : (uint32_t)kRunM);
+        if (runs) {
+            // integer-ratio runs: whole blocks of m_full outputs per lane, the ragged end of the pass with
+            // as many whole units as remain; what is left (less than one unit, or a block whose plan is not
+            // periodic) takes the general routine
             for (uint32_t fb = k0 + warp * bf; fb < k0 + nf; fb += (kTpThreads / 32u) * bf) {
                 const uint32_t fe = min(fb + bf, k0 + nf);
-                bool done = false;
-                if (fe - fb == bf) {
-                    if constexpr (TAPS <= 32) {
-                        if (wide) done = tp_run_block<TAPS, 4, true>(fb, k0, ch, run_p, run_d, s_v, s_p1, s_frac, s_x, coeffs, job.out, lane);
-                    }
-                    if (!wide)
-                        done = run_d == 1u ? tp_run_block<TAPS, kRunM, true>(fb, k0, ch, run_p, run_d, s_v, s_p1, s_frac, s_x, coeffs, job.out, lane)
-                                           : tp_run_block<TAPS, kRunM, false>(fb, k0, ch, run_p, run_d, s_v, s_p1, s_frac, s_x, coeffs, job.out, lane);
-                }
-                if (!done)
-                    for (uint32_t idx0 = fb * ch; idx0 < fe * ch; idx0 += 32u)
-                        tp_block<TAPS, true>(idx0, fe * ch, k0, ch, s_v, s_p1, s_frac, s_x, hist, in, HC, coeffs, cw, s_slot[warp], job.out, lane);
+                const uint32_t m = (fe - fb) / unit;
+                uint32_t f_gen = fb;
+                if (m != 0 && tp_run_dispatch<TAPS>(m, run_d == 1u, fb, k0, ch, run_p, run_d, s_v, s_p1, s_frac, s_x, coeffs, job.out, lane))
+                    f_gen = fb + m * unit;
+                for (uint32_t idx0 = f_gen * ch; idx0 < fe * ch; idx0 += 32u)
+                    tp_block<TAPS, true>(idx0, fe * ch, k0, ch, s_v, s_p1, s_frac, s_x, hist, in, HC, coeffs, cw, s_slot[warp], job.out, lane);
             }
         } else {
             for (uint32_t idx0 = v0 + warp * 32u; idx0 < n_vals; idx0 += kTpThreads) {
