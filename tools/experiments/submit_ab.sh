@@ -1,7 +1,7 @@
 # A/B of the submit path: build/ab/libold.so against the in-tree library (exact kernel forced so that
 # AUTO's tile-path crossover does not hide the thread-per-output kernel)
 L=resampler_b200/lib/libresampler_b200.so
-cp $L build/ab/libnew.so
+mkdir -p build/ab; cp $L build/ab/libnew.so
 for v in old new old new; do
   cp build/ab/lib$v.so $L
   echo "== $v"
