@@ -682,6 +682,9 @@ def test_config5_share_time_sliced_with_state_carry_matches_oracle():
     (2, 44100, 88200, 3, 2, [256, 441]),                      # cycle 2, 128 taps
     (4, 48000, 32000, 0, 0, [96, 480]),                       # cycle 2, windows 3 apart, 4 channels, 16 taps
     (1, 48000, 48000, 1, 0, [100, 480]),                      # ratio 1: one phase
+    (3, 16000, 48000, 0, 0, [50, 200]),                       # cycle 3 x 3 channels: 9 lanes per group, 5 spare lanes
+    (5, 96000, 48000, 1, 1, [64, 300]),                       # 5 channels: 6 groups, 2 spare lanes
+    (16, 48000, 24000, 0, 0, [128, 250]),                     # 16 channels: two groups per warp
 ])
 def test_fused_submit_configurations_bit_exact(ch, in_hz, out_hz, lat, att, sizes):
     """The single-launch submit kernels (thread-per-output variant, fir_submit.cu) over channel
