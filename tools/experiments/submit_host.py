@@ -18,8 +18,3 @@ for reps in (50, 500, 500):
         b.submit_ptrs(ins, il, outs, ol, memspace=MEM_DEVICE, flags=FLAG_ASYNC)
     t1 = time.perf_counter(); b.sync(); t2 = time.perf_counter()
     print(f"reps {reps}: host enqueue per submit {(t1 - t0) / reps * 1e6:.1f} us, total per submit {(t2 - t0) / reps * 1e6:.1f} us")
-# raw C call without the Python wrapper's per-call work
-cons = (C.c_size_t * n)(); prod = (C.c_size_t * n)()
-fn = lib.rsb_fir_submit_batch
-import inspect
-print(inspect.getsource(FirBatch.submit_ptrs)[:1500])
