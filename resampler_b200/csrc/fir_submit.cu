@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(256) submit_fused_kernel(const SubmitJob *jobs
 //     own: the later per-thread 16-byte reads of eight consecutive slots touch eight different bank
 //     groups), TB = 16 taps at a time.
 constexpr uint32_t kTpThreads = 128;
-constexpr uint32_t kSuper = 512;           // frames expanded per pass
+constexpr uint32_t kSuper = 1024;          // frames expanded per pass
 constexpr uint32_t kTpRowsMax = 33;        // staged phases per warp at most (32 mono outputs + 1): offset of the phase-2 rows
 constexpr int kTpTapBlock = 16;            // taps staged per round (16: half the staging memory of 32, more CTAs per SM)
 
